@@ -1,0 +1,584 @@
+// C ABI of libframefusion_b200.so — see include/framefusion_b200.h for the contract of every entry point.
+// Host side only: argument checks, workspace carving, kernel launches on the caller's stream.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "ff_common.cuh"
+#include "ff_fused.cuh"
+#include "ff_importance.cuh"
+#include "ff_links.cuh"
+#include "ff_merge.cuh"
+#include "ff_select.cuh"
+#include "ff_similarity.cuh"
+
+using namespace ff;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define FF_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(FF_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_));    \
+    } while (0)
+
+#define FF_LAUNCH_CHECK(name)                                                                      \
+    do {                                                                                           \
+        cudaError_t e_ = cudaGetLastError();                                                       \
+        if (e_ != cudaSuccess) return fail(FF_E_CUDA, "launch %s: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct ff_ctx {
+    int device;
+    int64_t* h_status;
+    int64_t* d_status;
+    int parity;          // which links / counter bank describes the current sequence
+    int last_parity;     // bank the last merge call read (ff_debug_read)
+    int64_t links_S;     // sequence length the links describe (-1: none, -2: S_keep of the last merge call)
+    int64_t cap;         // capacity the workspace is carved for (set by ff_build_links)
+    int64_t n_ids;
+    int have_order;      // by-patch order / rank arrays valid for `parity`
+    int have_link;       // successor links valid for `parity`
+    int sm_count;
+};
+
+// ------------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Ws {
+    int64_t* counters[2];
+    int* order[2];
+    int* chain[2];
+    int* rank[2];
+    int* link[2];
+    float* sim;
+    uint8_t* flag;
+    uint8_t* state;
+    int* dst;
+    int* srcidx;
+    int* term;
+    int* hist;
+    int* total;
+    int* base;
+    unsigned long long* tiles;
+    size_t bytes;
+};
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+Ws carve(void* base_ptr, int64_t cap, int64_t n_ids) {
+    Ws w;
+    char* p = (char*)base_ptr;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += align_up(bytes); return r; };
+    const int64_t n_chunks = (cap + LINK_CHUNK - 1) / LINK_CHUNK;
+    w.counters[0] = (int64_t*)take(C_SLOTS * 8);
+    w.counters[1] = (int64_t*)take(C_SLOTS * 8);
+    for (int b = 0; b < 2; ++b) {
+        w.order[b] = (int*)take(cap * 4);
+        w.chain[b] = (int*)take(cap * 4);
+        w.rank[b] = (int*)take(cap * 4);
+        w.link[b] = (int*)take(cap * 4);
+    }
+    w.sim = (float*)take(cap * 4);
+    w.flag = (uint8_t*)take(cap);
+    w.state = (uint8_t*)take(cap);
+    w.dst = (int*)take(cap * 4);
+    w.srcidx = (int*)take(cap * 4);
+    w.term = (int*)take(cap * 4);
+    w.hist = (int*)take((size_t)n_chunks * (size_t)(n_ids > 0 ? n_ids : 1) * 4);
+    w.total = (int*)take((size_t)(n_ids > 0 ? n_ids : 1) * 4);
+    w.base = (int*)take((size_t)(n_ids > 0 ? n_ids : 1) * 4);
+    w.tiles = (unsigned long long*)take((size_t)(cap / FUSED_MIN_ROWS + 2) * 8);
+    w.bytes = off;
+    return w;
+}
+
+int check_ws(const ff_ctx* ctx, const void* ws, int64_t ws_bytes, int64_t S, Ws* out) {
+    if (!ctx || !ws) return fail(FF_E_BADARG, "null ctx / workspace");
+    if (((uintptr_t)ws & 255) != 0) return fail(FF_E_BADARG, "workspace must be 256-byte aligned");
+    if (S > ctx->cap) return fail(FF_E_WORKSPACE, "sequence length %lld exceeds the capacity %lld the workspace was laid out for", (long long)S, (long long)ctx->cap);
+    *out = carve((void*)ws, ctx->cap, ctx->n_ids);
+    if ((int64_t)out->bytes > ws_bytes)
+        return fail(FF_E_WORKSPACE, "workspace too small: need %zu bytes, have %lld", out->bytes, (long long)ws_bytes);
+    return FF_OK;
+}
+
+inline bool vec_ok(const void* a, const void* b, int64_t H, int dtype) {
+    const int64_t eb = dtype == FF_F32 ? 4 : 2;
+    return ((H * eb) % 16 == 0) && (((uintptr_t)a | (uintptr_t)b) & 15) == 0;
+}
+
+__global__ void k_store_sim(const float* __restrict__ sim, const int64_t* __restrict__ counters, int dtype, void* out,
+                            const int* __restrict__ order, int64_t* order_out) {
+    const int N = (int)counters[C_N];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+        if (out) {
+            if (dtype == FF_BF16) Num<FF_BF16>::store(out, j, sim[j]);
+            else if (dtype == FF_F16) Num<FF_F16>::store(out, j, sim[j]);
+            else ((float*)out)[j] = sim[j];
+        }
+        if (order_out) order_out[j] = order[j];
+    }
+}
+
+__global__ void k_store_vals(const float* __restrict__ v, int n, int dtype, void* out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    if (dtype == FF_BF16) Num<FF_BF16>::store(out, j, v[j]);
+    else if (dtype == FF_F16) Num<FF_F16>::store(out, j, v[j]);
+    else ((float*)out)[j] = v[j];
+}
+
+__global__ void k_store_order(const int* __restrict__ order, int n, int64_t* out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out[j] = order[j];
+}
+
+__global__ void k_keep_from_dst(const int* __restrict__ dst, int n, uint8_t* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = dst[i] >= 0;
+}
+
+__global__ void k_copy_u8(const uint8_t* __restrict__ src, int n, uint8_t* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[i];
+}
+
+__global__ void k_links_status(const int64_t* counters, int64_t* status) {
+    status[FF_ST_NCHAIN] = counters[C_N];
+    status[FF_ST_NVIS] = counters[C_NVIS];
+    status[FF_ST_ERROR] = 0;
+}
+
+__global__ void k_count_status(const int64_t* counters, int64_t* status) {
+    status[FF_ST_NCHAIN] = counters[C_N];
+    status[FF_ST_NVIS] = counters[C_NVIS];
+    status[FF_ST_COUNT] = counters[C_COUNT];
+    status[FF_ST_ERROR] = 0;
+}
+
+template <typename F>
+int dispatch_dtype(int dtype, F&& f) {
+    switch (dtype) {
+        case FF_BF16: return f(std::integral_constant<int, FF_BF16>());
+        case FF_F16: return f(std::integral_constant<int, FF_F16>());
+        case FF_F32: return f(std::integral_constant<int, FF_F32>());
+    }
+    return fail(FF_E_BADARG, "unsupported dtype %d", dtype);
+}
+
+int pack_aux(const ff_aux* aux, int n_aux, AuxPack* p) {
+    if (n_aux < 0 || n_aux > FF_MAX_AUX) return fail(FF_E_BADARG, "n_aux %d outside [0, %d]", n_aux, FF_MAX_AUX);
+    if (n_aux && !aux) return fail(FF_E_BADARG, "aux is null");
+    p->n = n_aux;
+    for (int i = 0; i < n_aux; ++i) {
+        if (!aux[i].src || !aux[i].dst || aux[i].planes < 1 || aux[i].row_bytes < 1)
+            return fail(FF_E_BADARG, "aux[%d] malformed", i);
+        p->a[i] = aux[i];
+    }
+    return FF_OK;
+}
+
+int launch_similarity(const Ws& w, int bank, const void* hidden, int dtype, int64_t S, int64_t H, double thr,
+                      cudaStream_t st) {
+    const bool vec = vec_ok(hidden, hidden, H, dtype);
+    const int grid = (int)((S + 7) / 8);
+    if (grid == 0) return FF_OK;
+    return dispatch_dtype(dtype, [&](auto dt) {
+        constexpr int DT = decltype(dt)::value;
+        if (vec)
+            k_similarity<DT, true><<<grid, 256, 0, st>>>(hidden, (int)H, w.order[bank], w.chain[bank], w.counters[bank],
+                                                         (float)thr, w.sim, w.flag, w.counters[bank]);
+        else
+            k_similarity<DT, false><<<grid, 256, 0, st>>>(hidden, (int)H, w.order[bank], w.chain[bank], w.counters[bank],
+                                                          (float)thr, w.sim, w.flag, w.counters[bank]);
+        FF_LAUNCH_CHECK("k_similarity");
+        return (int)FF_OK;
+    });
+}
+
+int launch_merge_compact(const Ws& w, int bank, const void* hidden, void* out, int dtype, int64_t S, int64_t H,
+                         int use_flags, cudaStream_t st) {
+    const bool vec = vec_ok(hidden, out, H, dtype);
+    const int grid = (int)((S + 7) / 8);
+    if (grid == 0) return FF_OK;
+    return dispatch_dtype(dtype, [&](auto dt) {
+        constexpr int DT = decltype(dt)::value;
+        if (vec)
+            k_merge_compact<DT, true><<<grid, 256, 0, st>>>(hidden, out, (int)S, (int)H, w.rank[bank], w.order[bank], w.flag,
+                                                            w.dst, w.counters[bank], use_flags);
+        else
+            k_merge_compact<DT, false><<<grid, 256, 0, st>>>(hidden, out, (int)S, (int)H, w.rank[bank], w.order[bank], w.flag,
+                                                             w.dst, w.counters[bank], use_flags);
+        FF_LAUNCH_CHECK("k_merge_compact");
+        return (int)FF_OK;
+    });
+}
+
+// the sequence length the links describe becomes known to the host only after it has synchronised and read
+// S_keep from the status block; by then h_status holds it.
+int links_ready(ff_ctx* ctx, int64_t S, bool need_order) {
+    if (ctx->links_S == -2) ctx->links_S = ctx->h_status[FF_ST_SEQ_KEEP];
+    if (ctx->links_S != S)
+        return fail(FF_E_BADARG, "chain links in the workspace describe S=%lld, not %lld: call ff_build_links", (long long)ctx->links_S, (long long)S);
+    if (need_order && !ctx->have_order)
+        return fail(FF_E_BADARG, "by-patch order not in the workspace (the fused path does not keep it): call ff_build_links");
+    return FF_OK;
+}
+
+int check_shape(int64_t S, int64_t H, int dtype) {
+    if (dtype < 0 || dtype > 2) return fail(FF_E_BADARG, "unsupported dtype %d", dtype);
+    if (S < 0 || H < 1) return fail(FF_E_BADARG, "bad shape S=%lld H=%lld", (long long)S, (long long)H);
+    if (S > (1ll << 30) || H > (1ll << 24)) return fail(FF_E_UNSUPPORTED, "S=%lld H=%lld too large", (long long)S, (long long)H);
+    return FF_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int ff_abi_version(void) { return FF_ABI_VERSION; }
+
+const char* ff_last_error(void) { return g_err; }
+
+int ff_ctx_create(int device, ff_ctx** out) {
+    if (!out) return fail(FF_E_BADARG, "out is null");
+    *out = nullptr;
+    FF_CUDA(cudaSetDevice(device));
+    ff_ctx* c = new (std::nothrow) ff_ctx();
+    if (!c) return fail(FF_E_BADARG, "out of host memory");
+    c->device = device;
+    c->parity = 0;
+    c->last_parity = 0;
+    c->links_S = -1;
+    c->cap = 0;
+    c->n_ids = 0;
+    c->have_order = c->have_link = 0;
+    cudaError_t e = cudaHostAlloc((void**)&c->h_status, FF_ST_SLOTS * 8, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e != cudaSuccess) { delete c; return fail(FF_E_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
+    memset(c->h_status, 0, FF_ST_SLOTS * 8);
+    e = cudaHostGetDevicePointer((void**)&c->d_status, c->h_status, 0);
+    if (e != cudaSuccess) { cudaFreeHost(c->h_status); delete c; return fail(FF_E_CUDA, "cudaHostGetDevicePointer: %s", cudaGetErrorString(e)); }
+    e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) c->sm_count = 148;
+    *out = c;
+    return FF_OK;
+}
+
+int ff_ctx_destroy(ff_ctx* ctx) {
+    if (!ctx) return FF_OK;
+    cudaFreeHost(ctx->h_status);
+    delete ctx;
+    return FF_OK;
+}
+
+const int64_t* ff_ctx_status(const ff_ctx* ctx) { return ctx ? ctx->h_status : nullptr; }
+
+int64_t ff_workspace_bytes(int64_t seq_capacity, int64_t n_ids) {
+    if (seq_capacity < 0 || n_ids < 0) return -1;
+    return (int64_t)carve(nullptr, seq_capacity, n_ids).bytes;
+}
+
+int ff_build_links(ff_ctx* ctx, void* ws, int64_t ws_bytes, const int64_t* patch_type, int64_t S, int64_t n_ids,
+                   void* stream) {
+    Ws w;
+    if (S < 0 || n_ids < 0 || S > (1ll << 30) || n_ids > (1ll << 24)) return fail(FF_E_BADARG, "bad S / n_ids");
+    if (!ctx) return fail(FF_E_BADARG, "null ctx");
+    ctx->cap = S;
+    ctx->n_ids = n_ids;
+    ctx->links_S = -1;
+    if (int rc = check_ws(ctx, ws, ws_bytes, S, &w)) return rc;
+    if (S > 0 && !patch_type) return fail(FF_E_BADARG, "patch_type is null");
+    cudaStream_t st = (cudaStream_t)stream;
+    FF_CUDA(cudaSetDevice(ctx->device));
+    const int n_chunks = (int)((S + LINK_CHUNK - 1) / LINK_CHUNK);
+    FF_CUDA(cudaMemsetAsync(w.counters[0], 0, 2 * align_up(C_SLOTS * 8), st));
+    if (S > 0 && n_ids > 0) {
+        FF_CUDA(cudaMemsetAsync(w.hist, 0, (size_t)n_chunks * n_ids * 4, st));
+        k_links_hist<<<n_chunks, LINK_CHUNK, 0, st>>>(patch_type, (int)S, (int)n_ids, w.hist, w.counters[0]);
+        FF_LAUNCH_CHECK("k_links_hist");
+        k_links_colscan<<<(int)((n_ids + 7) / 8), 256, 0, st>>>(w.hist, n_chunks, (int)n_ids, w.total, w.base, w.counters[0]);
+        FF_LAUNCH_CHECK("k_links_colscan");
+        k_links_scatter<<<n_chunks, LINK_CHUNK, 0, st>>>(patch_type, (int)S, (int)n_ids, w.hist, w.base, w.order[0],
+                                                        w.chain[0], w.rank[0]);
+        FF_LAUNCH_CHECK("k_links_scatter");
+        k_links_derive<<<(int)((S + 255) / 256), 256, 0, st>>>((int)S, nullptr, w.order[0], w.chain[0], w.rank[0], w.counters[0], w.link[0]);
+        FF_LAUNCH_CHECK("k_links_derive");
+    } else if (S > 0) {
+        // no patch ids: count vision tokens only, every rank is -1
+        k_links_hist<<<n_chunks, LINK_CHUNK, 0, st>>>(patch_type, (int)S, 0, w.hist, w.counters[0]);
+        FF_LAUNCH_CHECK("k_links_hist");
+        FF_CUDA(cudaMemsetAsync(w.rank[0], 0xff, (size_t)S * 4, st));
+        FF_CUDA(cudaMemsetAsync(w.link[0], 0xff, (size_t)S * 4, st));
+    }
+    k_links_status<<<1, 1, 0, st>>>(w.counters[0], ctx->d_status);
+    FF_LAUNCH_CHECK("k_links_status");
+    ctx->parity = 0;
+    ctx->last_parity = 0;
+    ctx->links_S = S;
+    ctx->have_order = ctx->have_link = 1;
+    return FF_OK;
+}
+
+int ff_similarity(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, int dtype, int64_t S, int64_t H, double thr,
+                  void* sim_out, int64_t* order_out, void* stream) {
+    Ws w;
+    if (int rc = check_shape(S, H, dtype)) return rc;
+    if (!ctx) return fail(FF_E_BADARG, "null ctx");
+    if (int rc = links_ready(ctx, S, true)) return rc;
+    if (int rc = check_ws(ctx, ws, ws_bytes, S, &w)) return rc;
+    if (S > 0 && !hidden) return fail(FF_E_BADARG, "hidden is null");
+    cudaStream_t st = (cudaStream_t)stream;
+    FF_CUDA(cudaSetDevice(ctx->device));
+    const int bank = ctx->parity;
+    FF_CUDA(cudaMemsetAsync(&w.counters[bank][C_COUNT], 0, 8, st));
+    if (int rc = launch_similarity(w, bank, hidden, dtype, S, H, thr, st)) return rc;
+    if (S > 0 && (sim_out || order_out)) {
+        k_store_sim<<<(int)((S + 255) / 256), 256, 0, st>>>(w.sim, w.counters[bank], dtype, sim_out, w.order[bank], order_out);
+        FF_LAUNCH_CHECK("k_store_sim");
+    }
+    k_count_status<<<1, 1, 0, st>>>(w.counters[bank], ctx->d_status);
+    FF_LAUNCH_CHECK("k_count_status");
+    ctx->last_parity = bank;
+    return FF_OK;
+}
+
+int ff_merge_apply(ff_ctx* ctx, void* ws, int64_t ws_bytes, void* hidden, int dtype, int64_t S, int64_t H,
+                   const int64_t* order, int64_t N, const int64_t* merge_index, int64_t M, uint8_t* keep_mask_out,
+                   void* stream) {
+    Ws w;
+    if (int rc = check_shape(S, H, dtype)) return rc;
+    if (N < 0 || M < 0 || N > S) return fail(FF_E_BADARG, "bad N / M");
+    if (!ctx) return fail(FF_E_BADARG, "null ctx");
+    if (ctx->cap < S) { ctx->cap = S; ctx->n_ids = 0; }
+    ctx->links_S = -1;                                     // scratch use of the link arrays
+    ctx->have_order = ctx->have_link = 0;
+    if (int rc = check_ws(ctx, ws, ws_bytes, S, &w)) return rc;
+    if (!keep_mask_out && S > 0) return fail(FF_E_BADARG, "keep_mask_out is null");
+    cudaStream_t st = (cudaStream_t)stream;
+    FF_CUDA(cudaSetDevice(ctx->device));
+    if (S > 0) FF_CUDA(cudaMemsetAsync(keep_mask_out, 1, (size_t)S, st));
+    if (M == 0 || N == 0) return FF_OK;                    // main.py:264-266
+    if (!order || !merge_index || !hidden) return fail(FF_E_BADARG, "null order / merge_index / hidden");
+    FF_CUDA(cudaMemsetAsync(w.flag, 0, (size_t)N, st));
+    const int64_t n = N > M ? N : M;
+    k_flags_from_index<<<(int)((n + 255) / 256), 256, 0, st>>>(merge_index, (int)M, (int)N, order, w.order[0], w.flag, keep_mask_out);
+    FF_LAUNCH_CHECK("k_flags_from_index");
+    const bool vec = vec_ok(hidden, hidden, H, dtype);
+    const int grid = (int)((N + 7) / 8);
+    return dispatch_dtype(dtype, [&](auto dt) {
+        constexpr int DT = decltype(dt)::value;
+        if (vec) k_merge_inplace<DT, true><<<grid, 256, 0, st>>>(hidden, (int)H, (int)N, w.order[0], w.flag);
+        else k_merge_inplace<DT, false><<<grid, 256, 0, st>>>(hidden, (int)H, (int)N, w.order[0], w.flag);
+        FF_LAUNCH_CHECK("k_merge_inplace");
+        return (int)FF_OK;
+    });
+}
+
+int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, void* hidden_out, int dtype, int64_t S,
+                   int64_t H, double thr, double bound, const ff_aux* aux, int n_aux, int flags, void* stream) {
+    Ws w;
+    AuxPack ap;
+    if (int rc = check_shape(S, H, dtype)) return rc;
+    if (!ctx) return fail(FF_E_BADARG, "null ctx");
+    if (int rc = links_ready(ctx, S, false)) return rc;
+    if (int rc = check_ws(ctx, ws, ws_bytes, S, &w)) return rc;
+    if (int rc = pack_aux(aux, n_aux, &ap)) return rc;
+    if (S > 0 && (!hidden || !hidden_out)) return fail(FF_E_BADARG, "hidden / hidden_out is null");
+    if (hidden == hidden_out) return fail(FF_E_BADARG, "hidden_out must not alias hidden");
+    cudaStream_t st = (cudaStream_t)stream;
+    FF_CUDA(cudaSetDevice(ctx->device));
+    const int bank = ctx->parity, nb = bank ^ 1;
+
+    if ((flags & 1) && S > 0 && ctx->have_link) {
+        int rc = launch_fused(ctx->sm_count, w.counters[bank], w.counters[nb], ctx->d_status, w.link[bank], w.link[nb],
+                              w.state, w.sim, w.dst, w.term, w.tiles, w.rank[bank], hidden, hidden_out, dtype, S, H, thr,
+                              bound, ap, st);
+        if (rc == FF_OK) {
+            ctx->last_parity = bank;
+            ctx->parity = nb;
+            ctx->links_S = -2;
+            ctx->have_order = 0;
+            ctx->have_link = 1;
+            return FF_OK;
+        }
+        if (rc != FF_E_UNSUPPORTED) return fail(rc, "fused launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (!ctx->have_order) return fail(FF_E_BADARG, "by-patch order not in the workspace (the fused path does not keep it): call ff_build_links");
+
+    FF_CUDA(cudaMemsetAsync(&w.counters[bank][C_COUNT], 0, 8, st));
+    if (int rc = launch_similarity(w, bank, hidden, dtype, S, H, thr, st)) return rc;
+    DecideArgs a;
+    a.counters = w.counters[bank];
+    a.status = ctx->d_status;
+    a.bound = bound;
+    a.S = (int)S;
+    a.sim = w.sim;
+    a.flag = w.flag;
+    a.order = w.order[bank];
+    a.chain = w.chain[bank];
+    a.rank = w.rank[bank];
+    a.dst = w.dst;
+    a.srcidx = w.srcidx;
+    a.order_next = w.order[nb];
+    a.chain_next = w.chain[nb];
+    a.rank_next = w.rank[nb];
+    a.counters_next = w.counters[nb];
+    a.force_branch = -1;
+    k_decide_scan<<<1, SEL_THREADS, 0, st>>>(a);
+    FF_LAUNCH_CHECK("k_decide_scan");
+    if (int rc = launch_merge_compact(w, bank, hidden, hidden_out, dtype, S, H, 1, st)) return rc;
+    if (ap.n && S > 0) {
+        k_aux_compact<<<(int)((S + 7) / 8), 256, 0, st>>>(ap, (int)S, w.dst);
+        FF_LAUNCH_CHECK("k_aux_compact");
+    }
+    if (S > 0) {
+        k_links_derive<<<(int)((S + 255) / 256), 256, 0, st>>>((int)S, &w.counters[bank][C_SKEEP], w.order[nb], w.chain[nb], w.rank[nb], w.counters[nb], w.link[nb]);
+        FF_LAUNCH_CHECK("k_links_derive");
+    }
+    ctx->last_parity = bank;
+    ctx->parity = nb;
+    ctx->links_S = -2;                                     // = S_keep, known once the host has synchronised
+    ctx->have_order = ctx->have_link = 1;
+    return FF_OK;
+}
+
+int ff_importance(ff_ctx* ctx, const void* q, const void* k, int dtype, int64_t Hq, int64_t Hk, int64_t S, int64_t D,
+                  int64_t num, int64_t q_hs, int64_t q_ss, int64_t k_hs, int64_t k_ss, int is_causal, double scale,
+                  void* probs_out, void* scratch, int64_t scratch_bytes, void* stream) {
+    if (!ctx || !q || !k || !probs_out || !scratch) return fail(FF_E_BADARG, "null argument");
+    if (dtype < 0 || dtype > 2) return fail(FF_E_BADARG, "unsupported dtype %d", dtype);
+    if (Hq < 1 || Hk < 1 || Hq % Hk || S < 1 || D < 1 || num < 1 || num > S) return fail(FF_E_BADARG, "bad attention shape");
+    if (scratch_bytes < Hq * num * S * 4) return fail(FF_E_WORKSPACE, "scratch needs %lld bytes", (long long)(Hq * num * S * 4));
+    const int64_t group = Hq / Hk;
+    const size_t smem = (size_t)group * num * D * 4;
+    if (smem > 96 * 1024) return fail(FF_E_UNSUPPORTED, "group*num*head_dim = %lld floats do not fit shared memory", (long long)(group * num * D));
+    cudaStream_t st = (cudaStream_t)stream;
+    FF_CUDA(cudaSetDevice(ctx->device));
+    const int64_t eb = dtype == FF_F32 ? 4 : 2;
+    const bool vec = (D * eb) % 16 == 0 && ((uintptr_t)k & 15) == 0 && (k_hs * eb) % 16 == 0 && (k_ss * eb) % 16 == 0;
+    dim3 grid((unsigned)((S + IMP_THREADS - 1) / IMP_THREADS), (unsigned)Hk);
+    int rc = dispatch_dtype(dtype, [&](auto dt) {
+        constexpr int DT = decltype(dt)::value;
+        if (vec) {
+            if (smem > 48 * 1024) FF_CUDA(cudaFuncSetAttribute(k_importance_logits<DT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_importance_logits<DT, true><<<grid, IMP_THREADS, smem, st>>>(q, k, (int)Hq, (int)Hk, (int)S, (int)D, (int)num, q_hs, q_ss,
+                                                                           k_hs, k_ss, is_causal, (float)scale, (float*)scratch);
+        } else {
+            if (smem > 48 * 1024) FF_CUDA(cudaFuncSetAttribute(k_importance_logits<DT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_importance_logits<DT, false><<<grid, IMP_THREADS, smem, st>>>(q, k, (int)Hq, (int)Hk, (int)S, (int)D, (int)num, q_hs, q_ss,
+                                                                            k_hs, k_ss, is_causal, (float)scale, (float*)scratch);
+        }
+        FF_LAUNCH_CHECK("k_importance_logits");
+        k_softmax_rows<DT><<<(int)(Hq * num), 1024, 0, st>>>((const float*)scratch, (int)S, probs_out);
+        FF_LAUNCH_CHECK("k_softmax_rows");
+        return (int)FF_OK;
+    });
+    return rc;
+}
+
+int ff_prune_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* attn, int64_t n_rows, const void* hidden,
+                   void* hidden_out, int dtype, int64_t S, int64_t H, int64_t start, int64_t length, int64_t k,
+                   const ff_aux* aux, int n_aux, void* importance_out, void* stream) {
+    Ws w;
+    AuxPack ap;
+    if (int rc = check_shape(S, H, dtype)) return rc;
+    if (!ctx) return fail(FF_E_BADARG, "null ctx");
+    if (ctx->cap < S) { ctx->cap = S; ctx->n_ids = 0; ctx->links_S = -1; ctx->have_order = ctx->have_link = 0; }
+    if (int rc = check_ws(ctx, ws, ws_bytes, S, &w)) return rc;
+    if (int rc = pack_aux(aux, n_aux, &ap)) return rc;
+    if (!attn || !hidden || !hidden_out || n_rows < 1 || S < 1) return fail(FF_E_BADARG, "null / empty argument");
+    if (start < 0 || length < 0 || start + length > S) return fail(FF_E_BADARG, "vision span [%lld, %lld) outside the sequence", (long long)start, (long long)(start + length));
+    if (k < 0 || k > length) return fail(FF_E_BADARG, "k=%lld outside [0, %lld] (torch.topk would raise)", (long long)k, (long long)length);
+    cudaStream_t st = (cudaStream_t)stream;
+    FF_CUDA(cudaSetDevice(ctx->device));
+    const int bank = ctx->parity;
+    int rc = dispatch_dtype(dtype, [&](auto dt) {
+        constexpr int DT = decltype(dt)::value;
+        k_row_mean<DT><<<(int)((S + 255) / 256), 256, 0, st>>>(attn, (int)n_rows, (int)S, w.sim);
+        FF_LAUNCH_CHECK("k_row_mean");
+        return (int)FF_OK;
+    });
+    if (rc) return rc;
+    PruneArgs a;
+    a.counters = w.counters[bank];
+    a.status = ctx->d_status;
+    a.imp = w.sim;
+    a.sel = w.flag;
+    a.dst = w.dst;
+    a.srcidx = w.srcidx;
+    a.S = (int)S;
+    a.start = (int)start;
+    a.length = (int)length;
+    a.k = k;
+    k_prune_scan<<<1, SEL_THREADS, 0, st>>>(a);
+    FF_LAUNCH_CHECK("k_prune_scan");
+    if (int rc2 = launch_merge_compact(w, bank, hidden, hidden_out, dtype, S, H, 0, st)) return rc2;
+    if (ap.n) {
+        k_aux_compact<<<(int)((S + 7) / 8), 256, 0, st>>>(ap, (int)S, w.dst);
+        FF_LAUNCH_CHECK("k_aux_compact");
+    }
+    if (importance_out) {
+        // counters[C_N] is not S here: store with an explicit count
+        k_store_vals<<<(int)((S + 255) / 256), 256, 0, st>>>(w.sim, (int)S, dtype, importance_out);
+        FF_LAUNCH_CHECK("k_store_vals");
+    }
+    return FF_OK;
+}
+
+int ff_compact_mask(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* mask, void* mask_out, int64_t S, int64_t S_keep,
+                    int64_t elem_bytes, void* stream) {
+    Ws w;
+    if (!ctx) return fail(FF_E_BADARG, "null ctx");
+    if (int rc = check_ws(ctx, ws, ws_bytes, S, &w)) return rc;
+    if (S_keep < 0 || S_keep > S) return fail(FF_E_BADARG, "bad S_keep");
+    if (S_keep == 0) return FF_OK;
+    if (!mask || !mask_out) return fail(FF_E_BADARG, "null mask");
+    cudaStream_t st = (cudaStream_t)stream;
+    FF_CUDA(cudaSetDevice(ctx->device));
+    switch (elem_bytes) {
+        case 1: k_compact_mask<uint8_t><<<(int)S_keep, 256, 0, st>>>((const uint8_t*)mask, (uint8_t*)mask_out, (int)S, (int)S_keep, w.srcidx); break;
+        case 2: k_compact_mask<uint16_t><<<(int)S_keep, 256, 0, st>>>((const uint16_t*)mask, (uint16_t*)mask_out, (int)S, (int)S_keep, w.srcidx); break;
+        case 4: k_compact_mask<uint32_t><<<(int)S_keep, 256, 0, st>>>((const uint32_t*)mask, (uint32_t*)mask_out, (int)S, (int)S_keep, w.srcidx); break;
+        case 8: k_compact_mask<uint64_t><<<(int)S_keep, 256, 0, st>>>((const uint64_t*)mask, (uint64_t*)mask_out, (int)S, (int)S_keep, w.srcidx); break;
+        default: return fail(FF_E_BADARG, "elem_bytes %lld", (long long)elem_bytes);
+    }
+    FF_LAUNCH_CHECK("k_compact_mask");
+    return FF_OK;
+}
+
+int ff_debug_read(ff_ctx* ctx, void* ws, int64_t ws_bytes, int what, void* dst_device, int64_t n, int dtype, void* stream) {
+    Ws w;
+    if (!ctx || !dst_device) return fail(FF_E_BADARG, "null argument");
+    if (n < 0) return fail(FF_E_BADARG, "bad n");
+    if (int rc = check_ws(ctx, ws, ws_bytes, n, &w)) return rc;
+    if (n == 0) return FF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    FF_CUDA(cudaSetDevice(ctx->device));
+    const int bank = ctx->last_parity;
+    const int grid = (int)((n + 255) / 256);
+    switch (what) {
+        case 0: k_keep_from_dst<<<grid, 256, 0, st>>>(w.dst, (int)n, (uint8_t*)dst_device); break;
+        case 1: k_copy_u8<<<grid, 256, 0, st>>>(w.flag, (int)n, (uint8_t*)dst_device); break;
+        case 2: k_store_vals<<<grid, 256, 0, st>>>(w.sim, (int)n, dtype, dst_device); break;
+        case 3: k_store_order<<<grid, 256, 0, st>>>(w.order[bank], (int)n, (int64_t*)dst_device); break;
+        default: return fail(FF_E_BADARG, "what=%d", what);
+    }
+    FF_LAUNCH_CHECK("debug_read");
+    return FF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,223 @@
+// Shared device helpers for the FrameFusion token-reduction kernels (sm_100a).
+//
+// Numerics contract (SURVEY.md §8 a-N; every rounding below is one the reference performs because
+// it materialises a tensor in the hidden dtype T — /root/reference/framefusion/main.py:345-349, 304-317):
+//   prod_T(a,b)  = T(a*b)                    the elementwise product tensor of cosine_similarity
+//   sums are float32 (ATen accumulates bf16/f16 reductions in float32), then rounded to T once
+//   norm = T(sqrt(sum_f32 a*a)),  den = T(n1*n2),  sim = T(dot/den)
+//   merge: acc = T(acc + member) one member at a time in chain order, then T(acc / T(L+1))
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/framefusion_b200.h"
+
+namespace ff {
+
+constexpr int WARP = 32;
+constexpr unsigned FULL = 0xffffffffu;
+
+// device-side counters kept at the head of the workspace (int64 slots)
+enum Counter {
+    C_N = 0,        // by-patch chain tokens
+    C_NVIS = 1,     // patch_type != -1
+    C_COUNT = 2,    // sim >= thr
+    C_TICKET = 3,   // last-block-done ticket
+    C_SKEEP = 4,
+    C_BRANCH = 5,
+    C_K = 6,
+    C_ERR = 7,
+    C_NMERGED = 8,
+    C_NNEXT = 9,    // N of the links written for the next call
+    C_TICKET2 = 10,
+    C_SLOTS = 32
+};
+
+// ------------------------------------------------------------------------------------------------
+// dtype traits.  Values travel as float32 that are exactly representable in T.
+// ------------------------------------------------------------------------------------------------
+template <int DT> struct Num;
+
+template <> struct Num<FF_BF16> {
+    typedef uint16_t store_t;
+    static constexpr int EPV = 8;   // elements per 16-byte vector
+    static __device__ __forceinline__ float load(const void* p, int64_t i) {
+        return __uint_as_float(((uint32_t)((const uint16_t*)p)[i]) << 16);
+    }
+    static __device__ __forceinline__ float rnd(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+    static __device__ __forceinline__ void store(void* p, int64_t i, float x) {
+        ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(x);
+    }
+    static __device__ __forceinline__ void unpack(const uint4& v, float* f) {
+        f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+        f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+        f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+        f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+    }
+    static __device__ __forceinline__ uint32_t pack2(float a, float b) {   // rounds to T
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    static __device__ __forceinline__ uint4 pack(const float* f) {
+        return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+    }
+    // T(a*b) for two packed pairs, returned as two floats
+    static __device__ __forceinline__ void prod2(uint32_t a, uint32_t b, float& lo, float& hi) {
+        __nv_bfloat162 p = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+        uint32_t w = *reinterpret_cast<uint32_t*>(&p);
+        lo = __uint_as_float(w << 16); hi = __uint_as_float(w & 0xffff0000u);
+    }
+};
+
+template <> struct Num<FF_F16> {
+    typedef uint16_t store_t;
+    static constexpr int EPV = 8;
+    static __device__ __forceinline__ float load(const void* p, int64_t i) {
+        return __half2float(((const __half*)p)[i]);
+    }
+    static __device__ __forceinline__ float rnd(float x) { return __half2float(__float2half_rn(x)); }
+    static __device__ __forceinline__ void store(void* p, int64_t i, float x) { ((__half*)p)[i] = __float2half_rn(x); }
+    static __device__ __forceinline__ void unpack(const uint4& v, float* f) {
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    }
+    static __device__ __forceinline__ uint32_t pack2(float a, float b) {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    static __device__ __forceinline__ uint4 pack(const float* f) {
+        return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+    }
+    static __device__ __forceinline__ void prod2(uint32_t a, uint32_t b, float& lo, float& hi) {
+        float2 fa = __half22float2(*reinterpret_cast<__half2*>(&a));
+        float2 fb = __half22float2(*reinterpret_cast<__half2*>(&b));
+        lo = rnd(fa.x * fb.x); hi = rnd(fa.y * fb.y);      // float product of two f16 is exact; one rounding
+    }
+};
+
+template <> struct Num<FF_F32> {
+    typedef float store_t;
+    static constexpr int EPV = 4;
+    static __device__ __forceinline__ float load(const void* p, int64_t i) { return ((const float*)p)[i]; }
+    static __device__ __forceinline__ float rnd(float x) { return x; }
+    static __device__ __forceinline__ void store(void* p, int64_t i, float x) { ((float*)p)[i] = x; }
+    static __device__ __forceinline__ void unpack(const uint4& v, float* f) {
+        f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+    }
+    static __device__ __forceinline__ uint4 pack(const float* f) {
+        return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+    }
+};
+
+// Accumulates the three row sums of one 16-byte vector pair: dot += T(a*b), na += a*a, nb += b*b.
+template <int DT>
+__device__ __forceinline__ void acc_pair(const uint4& va, const uint4& vb, float& dot, float& na, float& nb) {
+    float a[Num<DT>::EPV], b[Num<DT>::EPV];
+    Num<DT>::unpack(va, a);
+    Num<DT>::unpack(vb, b);
+    if (DT == FF_F32) {
+#pragma unroll
+        for (int e = 0; e < Num<DT>::EPV; ++e) {
+            dot += __fmul_rn(a[e], b[e]);          // the product tensor is materialised before the sum
+            na = fmaf(a[e], a[e], na);
+            nb = fmaf(b[e], b[e], nb);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < Num<DT>::EPV; ++e) {
+            dot += Num<DT>::rnd(a[e] * b[e]);      // a*b is exact in float32 for 16-bit inputs: one rounding to T
+            na = fmaf(a[e], a[e], na);             // exact product, float32 accumulate
+            nb = fmaf(b[e], b[e], nb);
+        }
+    }
+}
+
+template <int DT>
+__device__ __forceinline__ void acc_pair_scalar(float a, float b, float& dot, float& na, float& nb) {
+    if (DT == FF_F32) dot += __fmul_rn(a, b); else dot += Num<DT>::rnd(a * b);
+    na = fmaf(a, a, na);
+    nb = fmaf(b, b, nb);
+}
+
+// sim = T( T(dot) / T( T(sqrt(na)) * T(sqrt(nb)) ) )
+template <int DT>
+__device__ __forceinline__ float finish_cosine(float dot, float na, float nb) {
+    float d = Num<DT>::rnd(dot);
+    float n1 = Num<DT>::rnd(sqrtf(na));
+    float n2 = Num<DT>::rnd(sqrtf(nb));
+    float den = Num<DT>::rnd(n1 * n2);
+    return Num<DT>::rnd(d / den);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// streaming 16-byte load / store (read once / written once: keep them out of L1)
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream16(void* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Block-wide exclusive scan of one int per thread (blockDim.x <= 1024, multiple of 32).
+// Returns the exclusive prefix; *total gets the block sum.  `smem` needs 33 ints.
+__device__ __forceinline__ int block_exclusive_scan(int v, int* smem, int* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();                       // protect smem reuse across calls
+    if (lane == 31) smem[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = lane < nw ? smem[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(FULL, wi, o);
+            if (lane >= o) wi += t;
+        }
+        smem[lane] = wi - w;               // exclusive warp offsets
+        if (lane == 31) smem[32] = wi;
+    }
+    __syncthreads();
+    int excl = smem[wid] + incl - v;
+    *total = smem[32];
+    return excl;
+}
+
+// order-preserving key of a float: larger float -> larger key; every NaN -> the largest key
+// (torch.topk ranks NaN above everything).
+__device__ __forceinline__ uint32_t float_key(float x) {
+    if (x != x) return 0xffffffffu;
+    uint32_t u = __float_as_uint(x);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+template <int DT>
+__device__ __forceinline__ float load_T(const void* p, int64_t i) { return Num<DT>::load(p, i); }
+
+}  // namespace ff

@@ -1,0 +1,94 @@
+// Importance signal: attention probabilities of the last `num` queries against all keys
+// (/root/reference/framefusion/utils.py:27-57).  The reference materialises repeat_kv(K) (7x the KV bytes)
+// and runs a [num x D] x [D x S] matmul per query head; here one thread owns one (kv head, key position),
+// reads that 256-byte K row once and serves every query head of the GQA group from shared memory.
+//   logits = T( T( T(q.k) * scale ) + bias ),  bias = -inf above the causal diagonal (triu(diagonal=S-L+1))
+//   probs  = T( exp(x - max) / sum exp(x - max) )   with float32 softmax internals
+#pragma once
+#include "ff_common.cuh"
+
+namespace ff {
+
+constexpr int IMP_THREADS = 128;
+
+template <int DT, bool VEC>
+__global__ void __launch_bounds__(IMP_THREADS)
+k_importance_logits(const void* __restrict__ q, const void* __restrict__ k, int n_q_heads, int n_kv_heads, int S, int D,
+                    int num, int64_t q_hs, int64_t q_ss, int64_t k_hs, int64_t k_ss, int is_causal, float scale,
+                    float* __restrict__ logits /* [Hq, num, S] float32 holding T values */) {
+    extern __shared__ float s_q[];                        // [group * num][D]
+    typedef typename Num<DT>::store_t st;
+    const int hk = blockIdx.y;
+    const int group = n_q_heads / n_kv_heads;
+    const int L = num;
+    for (int idx = threadIdx.x; idx < group * L * D; idx += blockDim.x) {
+        const int d = idx % D, r = (idx / D) % L, g = idx / (D * L);
+        const int h = hk * group + g;
+        s_q[idx] = Num<DT>::load(q, (int64_t)h * q_hs + (int64_t)(S - L + r) * q_ss + d);
+    }
+    __syncthreads();
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const st* krow = (const st*)k + (int64_t)hk * k_hs + (int64_t)s * k_ss;
+    for (int gr = 0; gr < group * L; ++gr) {
+        const float* qv = s_q + gr * D;
+        float acc = 0.f;
+        if (VEC) {
+            for (int v = 0; v < D / Num<DT>::EPV; ++v) {
+                float kf[Num<DT>::EPV];
+                Num<DT>::unpack(ldg16((const char*)krow + (int64_t)v * 16), kf);
+#pragma unroll
+                for (int e = 0; e < Num<DT>::EPV; ++e) acc = fmaf(kf[e], qv[v * Num<DT>::EPV + e], acc);
+            }
+        } else {
+            for (int d = 0; d < D; ++d) acc = fmaf(Num<DT>::load(krow, d), qv[d], acc);
+        }
+        const int r = gr % L, h = hk * group + gr / L;
+        float x = Num<DT>::rnd(acc);                       // matmul output in T
+        x = Num<DT>::rnd(x * scale);                       // * scale_factor
+        const float bias = (is_causal && s > S - L + r) ? -INFINITY : 0.f;
+        x = Num<DT>::rnd(x + bias);                        // += attn_bias
+        logits[((int64_t)h * L + r) * S + s] = x;
+    }
+}
+
+// one block per (head, query) row
+template <int DT>
+__global__ void __launch_bounds__(1024)
+k_softmax_rows(const float* __restrict__ logits, int S, void* __restrict__ probs) {
+    __shared__ float s_red[32];
+    __shared__ float s_val;
+    const float* x = logits + (int64_t)blockIdx.x * S;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float m = -INFINITY;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) m = fmaxf(m, x[s]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+    if (lane == 0) s_red[wid] = m;
+    __syncthreads();
+    if (wid == 0) {
+        float v = lane < nw ? s_red[lane] : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+        if (lane == 0) s_val = v;
+    }
+    __syncthreads();
+    m = s_val;
+    float sum = 0.f;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) sum += expf(x[s] - m);
+    sum = warp_sum(sum);
+    __syncthreads();
+    if (lane == 0) s_red[wid] = sum;
+    __syncthreads();
+    if (wid == 0) {
+        float v = lane < nw ? s_red[lane] : 0.f;
+        v = warp_sum(v);
+        if (lane == 0) s_val = v;
+    }
+    __syncthreads();
+    sum = s_val;
+    for (int s = threadIdx.x; s < S; s += blockDim.x)
+        Num<DT>::store(probs, (int64_t)blockIdx.x * S + s, expf(x[s] - m) / sum);
+}
+
+}  // namespace ff

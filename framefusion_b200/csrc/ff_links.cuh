@@ -1,0 +1,142 @@
+// Chain links: the by-patch order of the reference (main.py:208-214) as a stable counting sort.
+//
+// The reference builds a [patch_num, S] boolean matrix (patch_type == arange(P)[:, None]) and takes
+// nonzero() of it: 21 MB written and read back at 64x576 tokens plus a host sync.  Here the same
+// permutation comes from a three-kernel counting sort over 8 bytes per token:
+//   hist     per 512-token chunk, count tokens per patch id          (global atomics on a [C, n_ids] table)
+//   colscan  per patch id, exclusive scan of the chunk counts; the last block to finish scans the
+//            per-id totals into bucket bases
+//   scatter  by-patch position = base[id] + chunk offset + stable rank inside the chunk
+// Outputs (by-patch position j, sequence position i):
+//   order[j] = i,  chain[j] = patch id,  rank[i] = j or -1 (text / ids outside [0, n_ids))
+#pragma once
+#include "ff_common.cuh"
+
+namespace ff {
+
+constexpr int LINK_CHUNK = 512;
+
+__global__ void __launch_bounds__(LINK_CHUNK)
+k_links_hist(const int64_t* __restrict__ pt, int S, int n_ids, int* __restrict__ hist, int64_t* counters) {
+    __shared__ int s_nv[LINK_CHUNK / 32];
+    const int i = blockIdx.x * LINK_CHUNK + threadIdx.x;
+    int vis = 0;
+    if (i < S) {
+        const int64_t id = pt[i];
+        vis = (id != -1);
+        if (id >= 0 && id < n_ids) atomicAdd(&hist[(int64_t)blockIdx.x * n_ids + (int)id], 1);
+    }
+    vis = warp_sum_int(vis);
+    if ((threadIdx.x & 31) == 0) s_nv[threadIdx.x >> 5] = vis;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < LINK_CHUNK / 32; ++w) t += s_nv[w];
+        if (t) atomicAdd((unsigned long long*)&counters[C_NVIS], (unsigned long long)t);
+    }
+}
+
+// one warp per patch id: exclusive scan of hist[:, id] over chunks; totals -> total[id];
+// the last block scans total[] into base[] and writes N.
+__global__ void __launch_bounds__(256)
+k_links_colscan(int* __restrict__ hist, int n_chunks, int n_ids, int* __restrict__ total, int* __restrict__ base,
+                int64_t* counters) {
+    __shared__ int s_scan[33];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31;
+    const int id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (id < n_ids) {
+        int running = 0;
+        for (int c0 = 0; c0 < n_chunks; c0 += 32) {
+            const int c = c0 + lane;
+            const int v = c < n_chunks ? hist[(int64_t)c * n_ids + id] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (c < n_chunks) hist[(int64_t)c * n_ids + id] = running + incl - v;
+            running += __shfl_sync(FULL, incl, 31);
+        }
+        if (lane == 0) total[id] = running;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = atomicAdd((unsigned long long*)&counters[C_TICKET], 1ull);
+        s_last = (t == (unsigned long long)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    int carry = 0;
+    for (int b0 = 0; b0 < n_ids; b0 += blockDim.x) {
+        const int k = b0 + threadIdx.x;
+        const int v = k < n_ids ? __ldcg(&total[k]) : 0;
+        int tot;
+        const int ex = block_exclusive_scan(v, s_scan, &tot);
+        if (k < n_ids) base[k] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) {
+        counters[C_N] = carry;
+        counters[C_TICKET] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(LINK_CHUNK)
+k_links_scatter(const int64_t* __restrict__ pt, int S, int n_ids, const int* __restrict__ hist,
+                const int* __restrict__ base, int* __restrict__ order, int* __restrict__ chain,
+                int* __restrict__ rank) {
+    __shared__ __align__(16) int s_key[LINK_CHUNK];
+    const int t = threadIdx.x;
+    const int i = blockIdx.x * LINK_CHUNK + t;
+    int key = -1;
+    if (i < S) {
+        const int64_t id = pt[i];
+        if (id >= 0 && id < n_ids) key = (int)id;
+    }
+    s_key[t] = key;
+    __syncthreads();
+    if (i >= S) return;
+    if (key < 0) { rank[i] = -1; return; }
+    // stable rank inside the chunk: earlier tokens of the chunk with the same id (brute force, <= 511 compares)
+    int local = 0;
+    const int4* k4 = reinterpret_cast<const int4*>(s_key);
+    const int full = t >> 2;
+    for (int q = 0; q < full; ++q) {
+        const int4 v = k4[q];
+        local += (v.x == key) + (v.y == key) + (v.z == key) + (v.w == key);
+    }
+    for (int u = full * 4; u < t; ++u) local += (s_key[u] == key);
+    const int pos = base[key] + hist[(int64_t)blockIdx.x * n_ids + key] + local;
+    order[pos] = i;
+    chain[pos] = key;
+    rank[i] = pos;
+}
+
+// successor links for the single-pass kernel: link[i] = (has_pred << 31) | succ, succ = LINK_NONE when the
+// chain ends at i.  Text tokens: LINK_NONE, no predecessor.
+constexpr uint32_t LINK_NONE = 0x7fffffffu;
+constexpr uint32_t LINK_HASPRED = 0x80000000u;
+
+// `len_dev`, when not null, holds the sequence length on the device (S_keep of the call that made these links).
+__global__ void k_links_derive(int S, const int64_t* __restrict__ len_dev, const int* __restrict__ order,
+                               const int* __restrict__ chain, const int* __restrict__ rank,
+                               const int64_t* __restrict__ counters, int* __restrict__ link) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (len_dev) S = (int)*len_dev;
+    if (i >= S) return;
+    const int N = (int)counters[C_N];
+    const int j = rank[i];
+    uint32_t l = LINK_NONE;
+    if (j >= 0) {
+        const int c = chain[j];
+        if (j + 1 < N && chain[j + 1] == c) l = (uint32_t)order[j + 1];
+        if (j > 0 && chain[j - 1] == c) l |= LINK_HASPRED;
+    }
+    link[i] = (int)l;
+}
+
+}  // namespace ff

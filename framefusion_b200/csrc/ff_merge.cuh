@@ -1,0 +1,182 @@
+// Merge + compaction (main.py:285-317 and 132-138, 161-178), generic path: one warp per kept
+// sequence row.  A kept row whose by-patch successor positions are flagged is an anchor: it adds the run
+// members one at a time in chain order, every add rounded to T (the order torch-CPU index_add_ uses),
+// divides once by T(L+1), and writes the result straight to its compacted position — the reference's
+// separate index_add_ / div / boolean-mask passes (3 extra trips over the rows) collapse into one.
+#pragma once
+#include "ff_common.cuh"
+
+namespace ff {
+
+// run length starting after by-patch position j (flags are contiguous by-patch, chain boundaries are not
+// special: the reference's run detection works on the flat by-patch array, main.py:276)
+__device__ __forceinline__ int run_after(const uint8_t* __restrict__ flag, int j, int N) {
+    int m = j + 1;
+    while (m < N && flag[m]) ++m;
+    return m - j - 1;
+}
+
+template <int DT, bool VEC, bool INPLACE>
+__device__ __forceinline__ void merge_row(const void* hidden, void* out_row, const char* src_row, int H, int lane,
+                                          const int* __restrict__ order, int j, int L, int wrapL) {
+    typedef typename Num<DT>::store_t st;
+    const int64_t row_bytes = (int64_t)H * sizeof(st);
+    const float div = Num<DT>::rnd((float)(L + wrapL + 1));   // the divisor tensor is cast to T (main.py:317)
+    if (VEC) {
+        const int nvec = H / Num<DT>::EPV;
+        for (int v = lane; v < nvec; v += 32) {
+            float acc[Num<DT>::EPV], x[Num<DT>::EPV];
+            Num<DT>::unpack(ldg16(src_row + (int64_t)v * 16), acc);
+            for (int m = 1; m <= L; ++m) {
+                const char* mr = (const char*)hidden + (int64_t)order[j + m] * row_bytes;
+                Num<DT>::unpack(ldg16(mr + (int64_t)v * 16), x);
+#pragma unroll
+                for (int e = 0; e < Num<DT>::EPV; ++e) acc[e] = Num<DT>::rnd(acc[e] + x[e]);
+            }
+            for (int m = 0; m < wrapL; ++m) {
+                const char* mr = (const char*)hidden + (int64_t)order[m] * row_bytes;
+                Num<DT>::unpack(ldg16(mr + (int64_t)v * 16), x);
+#pragma unroll
+                for (int e = 0; e < Num<DT>::EPV; ++e) acc[e] = Num<DT>::rnd(acc[e] + x[e]);
+            }
+#pragma unroll
+            for (int e = 0; e < Num<DT>::EPV; ++e) acc[e] = Num<DT>::rnd(acc[e] / div);
+            *reinterpret_cast<uint4*>((char*)out_row + (int64_t)v * 16) = Num<DT>::pack(acc);
+        }
+    } else {
+        for (int e = lane; e < H; e += 32) {
+            float acc = Num<DT>::load(src_row, e);
+            for (int m = 1; m <= L; ++m)
+                acc = Num<DT>::rnd(acc + Num<DT>::load((const char*)hidden + (int64_t)order[j + m] * row_bytes, e));
+            for (int m = 0; m < wrapL; ++m)
+                acc = Num<DT>::rnd(acc + Num<DT>::load((const char*)hidden + (int64_t)order[m] * row_bytes, e));
+            acc = Num<DT>::rnd(acc / div);
+            Num<DT>::store(out_row, e, acc);
+        }
+    }
+}
+
+template <int DT, bool VEC>
+__global__ void __launch_bounds__(256)
+k_merge_compact(const void* __restrict__ hidden, void* __restrict__ out, int S, int H, const int* __restrict__ rank,
+                const int* __restrict__ order, const uint8_t* __restrict__ flag, const int* __restrict__ dst,
+                const int64_t* __restrict__ counters, int use_flags) {
+    typedef typename Num<DT>::store_t st;
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= S) return;
+    const int d = dst[i];
+    if (d < 0) return;
+    const int64_t row_bytes = (int64_t)H * sizeof(st);
+    const char* src = (const char*)hidden + (int64_t)i * row_bytes;
+    char* orow = (char*)out + (int64_t)d * row_bytes;
+    int L = 0, wrapL = 0, j = -1;
+    if (use_flags) {
+        j = rank[i];
+        if (j >= 0) {
+            const int N = (int)counters[C_N];
+            L = run_after(flag, j, N);
+            // a flagged run at by-patch position 0 has anchor index -1, which the reference's advanced
+            // indexing wraps to the last by-patch position (main.py:290, 306)
+            if (j == N - 1 && N > 1 && flag[0]) wrapL = run_after(flag, -1, N - 1);
+        }
+    }
+    if (L + wrapL == 0) {
+        if (VEC) {
+            const int nvec = H / Num<DT>::EPV;
+            int v = lane;
+            for (; v + 96 < nvec; v += 128) {
+                uint4 a0 = ld_stream16(src + (int64_t)v * 16), a1 = ld_stream16(src + (int64_t)(v + 32) * 16);
+                uint4 a2 = ld_stream16(src + (int64_t)(v + 64) * 16), a3 = ld_stream16(src + (int64_t)(v + 96) * 16);
+                st_stream16(orow + (int64_t)v * 16, a0);
+                st_stream16(orow + (int64_t)(v + 32) * 16, a1);
+                st_stream16(orow + (int64_t)(v + 64) * 16, a2);
+                st_stream16(orow + (int64_t)(v + 96) * 16, a3);
+            }
+            for (; v < nvec; v += 32) st_stream16(orow + (int64_t)v * 16, ld_stream16(src + (int64_t)v * 16));
+        } else {
+            const st* s = (const st*)src;
+            st* o = (st*)orow;
+            for (int e = lane; e < H; e += 32) o[e] = s[e];
+        }
+        return;
+    }
+    merge_row<DT, VEC, false>(hidden, orow, src, H, lane, order, j, L, wrapL);
+}
+
+// ---- in-place variant behind the reference's static merge_tokens_and_get_mask (main.py:243-319):
+// one warp per by-patch position; anchors are rewritten in place, nothing is compacted.
+template <int DT, bool VEC>
+__global__ void __launch_bounds__(256)
+k_merge_inplace(void* hidden, int H, int N, const int* __restrict__ order, const uint8_t* __restrict__ flag) {
+    typedef typename Num<DT>::store_t st;
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (j >= N || flag[j]) return;
+    const int L = run_after(flag, j, N);
+    int wrapL = 0;
+    if (j == N - 1 && N > 1 && flag[0]) wrapL = run_after(flag, -1, N - 1);
+    if (L + wrapL == 0) return;
+    char* row = (char*)hidden + (int64_t)order[j] * H * sizeof(st);
+    merge_row<DT, VEC, true>(hidden, row, row, H, lane, order, j, L, wrapL);
+}
+
+// flags from an explicit index list (static API): flag[merge_index[m]] = 1, keep[order[merge_index[m]]] = 0
+__global__ void k_flags_from_index(const int64_t* __restrict__ merge_index, int M, int N, const int64_t* __restrict__ order64,
+                                   int* __restrict__ order32, uint8_t* __restrict__ flag, uint8_t* __restrict__ keep) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < N) order32[t] = (int)order64[t];
+    if (t < M) {
+        int64_t j = merge_index[t];
+        if (j < 0) j += N;
+        if (j >= 0 && j < N) {
+            flag[j] = 1;
+            keep[order64[j]] = 0;
+        }
+    }
+}
+
+// ---- aux tensors (cos, sin, patch_type, position ids): row copy src[i] -> dst[dst_row[i]] ----------
+struct AuxPack {
+    ff_aux a[FF_MAX_AUX];
+    int n;
+};
+
+__global__ void __launch_bounds__(256)
+k_aux_compact(AuxPack p, int S, const int* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= S) return;
+    const int d = dst[i];
+    if (d < 0) return;
+    for (int q = 0; q < p.n; ++q) {
+        const ff_aux& a = p.a[q];
+        const int64_t rb = a.row_bytes;
+        for (int64_t pl = 0; pl < a.planes; ++pl) {
+            const char* s = (const char*)a.src + pl * a.src_plane_stride + (int64_t)i * rb;
+            char* o = (char*)a.dst + pl * a.dst_plane_stride + (int64_t)d * rb;
+            if (((rb | (int64_t)(uintptr_t)s | (int64_t)(uintptr_t)o) & 15) == 0) {
+                for (int64_t v = lane; v < rb / 16; v += 32)
+                    reinterpret_cast<uint4*>(o)[v] = __ldg(reinterpret_cast<const uint4*>(s) + v);
+            } else if (((rb | (int64_t)(uintptr_t)s | (int64_t)(uintptr_t)o) & 7) == 0) {
+                for (int64_t v = lane; v < rb / 8; v += 32)
+                    reinterpret_cast<uint2*>(o)[v] = __ldg(reinterpret_cast<const uint2*>(s) + v);
+            } else {
+                for (int64_t v = lane; v < rb; v += 32) o[v] = s[v];
+            }
+        }
+    }
+}
+
+// ---- mask[keep][:, keep]  (main.py:100, 138) ---------------------------------------------------------
+template <typename E>
+__global__ void k_compact_mask(const E* __restrict__ mask, E* __restrict__ out, int S, int S_keep,
+                               const int* __restrict__ srcidx) {
+    const int a = blockIdx.x;
+    if (a >= S_keep) return;
+    const E* row = mask + (int64_t)srcidx[a] * S;
+    E* orow = out + (int64_t)a * S_keep;
+    for (int b = threadIdx.x; b < S_keep; b += blockDim.x) orow[b] = row[srcidx[b]];
+}
+
+}  // namespace ff

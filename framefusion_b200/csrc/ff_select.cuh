@@ -1,0 +1,283 @@
+// Selection, run bookkeeping and compaction offsets — the integer part of a merge / prune call.
+// One 1024-thread block: these arrays are 1-8 bytes per token (tens of KB), the cost is latency, not
+// bytes, so a single block with 8 items per thread and no grid-wide synchronisation is the short path.
+//
+//   k_decide_scan   main.py:112-127 (branch), 269-301 (runs), 132 (keep mask) + links of the next call
+//   k_prune_scan    main.py:69-92
+#pragma once
+#include "ff_common.cuh"
+
+namespace ff {
+
+constexpr int SEL_THREADS = 1024;
+constexpr int SEL_ITEMS = 8;
+constexpr int SEL_TILE = SEL_THREADS * SEL_ITEMS;
+
+// ---- top-k flags over vals[0..n): selected = the k largest, NaN largest, ties at the k-th value go to
+// the lowest indices (the rule oracle/ff_oracle.py:topk_lowest_index states).  One block.  out[j] in {0,1}.
+// s_hist: 256 ints, s_scan: 33 ints, s_misc: 4 uint32.
+__device__ void block_topk_flags(const float* __restrict__ vals, int n, long long k, uint8_t* __restrict__ out,
+                                 int* s_hist, int* s_scan, uint32_t* s_misc) {
+    const int t = threadIdx.x;
+    if (k <= 0) {
+        for (int j = t; j < n; j += blockDim.x) out[j] = 0;
+        return;
+    }
+    if (k >= n) {
+        for (int j = t; j < n; j += blockDim.x) out[j] = 1;
+        return;
+    }
+    // radix select, 8 bits per pass from the top: find the key of the k-th largest element
+    uint32_t prefix = 0, mask = 0;
+    long long need = k;                                    // how many still to take among keys matching prefix
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int b = t; b < 256; b += blockDim.x) s_hist[b] = 0;
+        __syncthreads();
+        for (int j = t; j < n; j += blockDim.x) {
+            const uint32_t key = float_key(vals[j]);
+            if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255], 1);
+        }
+        __syncthreads();
+        if (t == 0) {
+            long long acc = 0;
+            int b = 255;
+            for (; b > 0; --b) {                           // walk from the largest digit down
+                if (acc + s_hist[b] >= need) break;
+                acc += s_hist[b];
+            }
+            s_misc[0] = (uint32_t)b;
+            s_misc[1] = (uint32_t)(need - acc);
+        }
+        __syncthreads();
+        prefix |= s_misc[0] << shift;
+        mask |= 255u << shift;
+        need = (long long)s_misc[1];
+        __syncthreads();
+    }
+    const uint32_t kth = prefix;                           // exact key of the k-th largest
+    // ordered pass: everything above kth, and the first `need` elements equal to kth
+    int carry = 0;
+    for (int base = 0; base < n; base += SEL_TILE) {
+        const int j0 = base + t * SEL_ITEMS;
+        uint32_t key[SEL_ITEMS];
+        int eq = 0;
+#pragma unroll
+        for (int e = 0; e < SEL_ITEMS; ++e) {
+            key[e] = (j0 + e < n) ? float_key(vals[j0 + e]) : 0u;
+            eq += (j0 + e < n) && (key[e] == kth);
+        }
+        int tot;
+        int ex = carry + block_exclusive_scan(eq, s_scan, &tot);
+#pragma unroll
+        for (int e = 0; e < SEL_ITEMS; ++e) {
+            if (j0 + e < n) {
+                uint8_t f = key[e] > kth;
+                if (key[e] == kth) { f = (ex < need); ++ex; }
+                out[j0 + e] = f;
+            }
+        }
+        carry += tot;
+    }
+    __syncthreads();
+}
+
+struct DecideArgs {
+    int64_t* counters;
+    int64_t* status;            // pinned, device-mapped
+    double bound;
+    int S;
+    const float* sim;
+    uint8_t* flag;              // by-patch merge flags (threshold flags on entry)
+    const int* order;
+    const int* chain;
+    const int* rank;
+    int* dst;                   // [S] destination row or -1
+    int* srcidx;                // [S_keep] source row of every destination row
+    int* order_next;
+    int* chain_next;
+    int* rank_next;
+    int64_t* counters_next;     // counter bank of the next call: N, n_vis carried over, count reset
+    int force_branch;           // -1 = decide from count (main.py:116); 0/1 = flags are given (static API)
+};
+
+__global__ void __launch_bounds__(SEL_THREADS)
+k_decide_scan(DecideArgs a) {
+    __shared__ int s_hist[256];
+    __shared__ int s_scan[33];
+    __shared__ uint32_t s_misc[4];
+    __shared__ long long s_k;
+    __shared__ int s_branch, s_err;
+    const int t = threadIdx.x;
+    const int N = (int)a.counters[C_N];
+    const int S = a.S;
+
+    if (t == 0) {
+        const long long count = a.counters[C_COUNT], n_vis = a.counters[C_NVIS];
+        int branch = 0, err = 0;
+        long long k = 0;
+        if (a.force_branch >= 0) {
+            branch = a.force_branch;
+        } else if (n_vis == 0) {
+            err = 1;                                       // the reference divides by zero here (main.py:114)
+        } else {
+            const double r = (double)count / (double)n_vis;            // above_k_ratio, Python float division
+            if (!(r < a.bound)) {
+                branch = 1;
+                k = (long long)(a.bound * (double)n_vis);  // int(sparsity_upper_bound * frame_token_num)
+                if (k > N) { err = 2; k = N; }             // torch.topk would raise
+                if (k < 0) k = 0;
+            }
+        }
+        s_branch = branch; s_k = k; s_err = err;
+    }
+    __syncthreads();
+    const int branch = s_branch;
+    if (branch == 1 && a.force_branch < 0)
+        block_topk_flags(a.sim, N, s_k, a.flag, s_hist, s_scan, s_misc);
+    __syncthreads();
+
+    // ---- sequence-order scan of the keep mask -> destination rows
+    int carry = 0;
+    for (int base = 0; base < S; base += SEL_TILE) {
+        const int i0 = base + t * SEL_ITEMS;
+        int r[SEL_ITEMS];
+        int keep[SEL_ITEMS];
+        int cnt = 0;
+#pragma unroll
+        for (int e = 0; e < SEL_ITEMS; ++e) r[e] = (i0 + e < S) ? a.rank[i0 + e] : -1;
+#pragma unroll
+        for (int e = 0; e < SEL_ITEMS; ++e) {
+            keep[e] = (i0 + e < S) && !(r[e] >= 0 && a.flag[r[e]]);
+            cnt += keep[e];
+        }
+        int tot;
+        int ex = carry + block_exclusive_scan(cnt, s_scan, &tot);
+#pragma unroll
+        for (int e = 0; e < SEL_ITEMS; ++e) {
+            if (i0 + e < S) {
+                if (keep[e]) {
+                    a.dst[i0 + e] = ex;
+                    a.srcidx[ex] = i0 + e;
+                    if (r[e] < 0) a.rank_next[ex] = -1;
+                    ++ex;
+                } else {
+                    a.dst[i0 + e] = -1;
+                }
+            }
+        }
+        carry += tot;
+    }
+    const int s_keep = carry;
+    __syncthreads();                                       // dst[] visible to the whole block below
+
+    // ---- by-patch-order compaction: the chain links the next call will use
+    carry = 0;
+    for (int base = 0; base < N; base += SEL_TILE) {
+        const int j0 = base + t * SEL_ITEMS;
+        int keep[SEL_ITEMS];
+        int cnt = 0;
+#pragma unroll
+        for (int e = 0; e < SEL_ITEMS; ++e) {
+            keep[e] = (j0 + e < N) && !a.flag[j0 + e];
+            cnt += keep[e];
+        }
+        int tot;
+        int ex = carry + block_exclusive_scan(cnt, s_scan, &tot);
+#pragma unroll
+        for (int e = 0; e < SEL_ITEMS; ++e) {
+            if (keep[e]) {
+                const int d = a.dst[a.order[j0 + e]];
+                a.order_next[ex] = d;
+                a.chain_next[ex] = a.chain[j0 + e];
+                a.rank_next[d] = ex;
+                ++ex;
+            }
+        }
+        carry += tot;
+    }
+    if (t == 0) {
+        const int n_next = carry;
+        a.counters[C_NNEXT] = n_next;
+        a.counters[C_SKEEP] = s_keep;
+        a.counters[C_BRANCH] = branch;
+        a.counters[C_K] = s_k;
+        a.counters[C_NMERGED] = N - n_next;
+        a.counters_next[C_N] = n_next;
+        a.counters_next[C_NVIS] = a.counters[C_NVIS] - (N - n_next);   // only chain tokens are ever merged away
+        a.counters_next[C_COUNT] = 0;
+        a.counters_next[C_TICKET] = 0;
+        a.counters_next[C_TICKET2] = 0;
+        a.status[FF_ST_SEQ_KEEP] = s_keep;
+        a.status[FF_ST_COUNT] = a.counters[C_COUNT];
+        a.status[FF_ST_NVIS] = a.counters[C_NVIS];
+        a.status[FF_ST_NCHAIN] = N;
+        a.status[FF_ST_BRANCH] = branch;
+        a.status[FF_ST_TOPK] = s_k;
+        a.status[FF_ST_ERROR] = s_err;
+        a.status[FF_ST_NMERGED] = N - n_next;
+    }
+}
+
+// ---- prune stage: importance = T(mean over rows) is computed by k_row_mean; this block selects and scans.
+struct PruneArgs {
+    int64_t* counters;
+    int64_t* status;
+    const float* imp;           // [S] float32 holding T values
+    uint8_t* sel;               // [length] scratch: 1 = kept by top-k
+    int* dst;
+    int* srcidx;
+    int S, start, length;
+    long long k;
+};
+
+__global__ void __launch_bounds__(SEL_THREADS)
+k_prune_scan(PruneArgs a) {
+    __shared__ int s_hist[256];
+    __shared__ int s_scan[33];
+    __shared__ uint32_t s_misc[4];
+    const int t = threadIdx.x;
+    block_topk_flags(a.imp + a.start, a.length, a.k, a.sel, s_hist, s_scan, s_misc);
+    __syncthreads();
+    int carry = 0;
+    for (int base = 0; base < a.S; base += SEL_TILE) {
+        const int i0 = base + t * SEL_ITEMS;
+        int keep[SEL_ITEMS];
+        int cnt = 0;
+#pragma unroll
+        for (int e = 0; e < SEL_ITEMS; ++e) {
+            const int i = i0 + e;
+            int kp = 0;
+            if (i < a.S) kp = (i < a.start || i >= a.start + a.length) ? 1 : a.sel[i - a.start];
+            keep[e] = kp;
+            cnt += kp;
+        }
+        int tot;
+        int ex = carry + block_exclusive_scan(cnt, s_scan, &tot);
+#pragma unroll
+        for (int e = 0; e < SEL_ITEMS; ++e) {
+            const int i = i0 + e;
+            if (i < a.S) {
+                if (keep[e]) { a.dst[i] = ex; a.srcidx[ex] = i; ++ex; } else a.dst[i] = -1;
+            }
+        }
+        carry += tot;
+    }
+    if (t == 0) {
+        a.counters[C_SKEEP] = carry;
+        a.status[FF_ST_SEQ_KEEP] = carry;
+        a.status[FF_ST_TOPK] = a.k;
+        a.status[FF_ST_ERROR] = 0;
+    }
+}
+
+// importance[s] = T( sum_rows attn[row][s] / n_rows )      (torch.mean(dim=(1,2)), main.py:70)
+template <int DT>
+__global__ void k_row_mean(const void* __restrict__ attn, int n_rows, int S, float* __restrict__ imp) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    float acc = 0.f;
+    for (int r = 0; r < n_rows; ++r) acc += Num<DT>::load(attn, (int64_t)r * S + s);
+    imp[s] = Num<DT>::rnd(acc / (float)n_rows);
+}
+
+}  // namespace ff

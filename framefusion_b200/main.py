@@ -1,0 +1,478 @@
+"""``FrameFusion`` — the token-reduction operator, host side.
+
+Mirror of ``/root/reference/framefusion/main.py`` (class ``FrameFusion``, lines 8-343): same constructor,
+``prepare`` / ``forward`` / static helpers, same attributes, same exceptions.  The state machine and the
+budget arithmetic stay in Python doubles exactly as the reference has them (main.py:109-127, 321-343); every
+tensor operation is one call into ``libframefusion_b200.so`` through the C ABI (``include/framefusion_b200.h``):
+
+* merge stage (main.py:104-138)  -> ``ff_build_links`` (first call of a prefill) + ``ff_merge_layer``
+* prune stage (main.py:61-101)   -> ``ff_prune_layer``
+* 4-D mask compaction            -> ``ff_compact_mask``
+
+A reducing call synchronises the stream exactly once (to learn ``S_keep``); the reference needs >= 10 syncs.
+There is no CPU / eager fallback: CPU tensors raise.
+
+Differences from the reference, all invisible to its callers (which rebind every returned value,
+models/qwen2/modeling_qwen2.py:46,67):
+* ``forward`` does not write merged anchors back into the *input* ``hidden_states`` (the reference mutates it
+  in place before compacting, main.py:304-317); the static ``merge_tokens_and_get_mask`` keeps the in-place
+  contract.
+* top-k ties are broken by the lowest by-patch index (``torch.topk`` leaves the choice unspecified).
+* the returned tensors are views of buffers sized for the incoming sequence (only ``S_keep`` rows are used).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+
+TEXT_TOKEN = -1
+IGNORE_TOKEN = -2
+
+_DT = {torch.bfloat16: _lib.FF_BF16, torch.float16: _lib.FF_F16, torch.float32: _lib.FF_F32}
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"framefusion_b200 supports bfloat16 / float16 / float32 hidden states, got {t.dtype}")
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _DeviceState:
+    """Context + workspace of one FrameFusion object on one device."""
+
+    def __init__(self, device: torch.device):
+        self.lib = _lib.load()
+        self.device = device
+        h = C.c_void_p()
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        _lib.check(self.lib.ff_ctx_create(idx, C.byref(h)))
+        self.ctx = h
+        self.status = np.ctypeslib.as_array(self.lib.ff_ctx_status(h), shape=(_lib.ST_SLOTS,))
+        self.ws = None
+        self.ws_cap = (-1, -1)
+
+    def workspace(self, seq_len: int, n_ids: int) -> torch.Tensor:
+        if self.ws is None or seq_len > self.ws_cap[0] or n_ids > self.ws_cap[1]:
+            cap = (max(seq_len, self.ws_cap[0]), max(n_ids, self.ws_cap[1]))
+            nbytes = self.lib.ff_workspace_bytes(cap[0], cap[1])
+            self.ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            self.ws_cap = cap
+        return self.ws
+
+    def ws_ptr(self):
+        p = self.ws.data_ptr()
+        a = (p + 255) // 256 * 256
+        return a, self.ws.numel() - (a - p)
+
+    def __del__(self):
+        try:
+            self.lib.ff_ctx_destroy(self.ctx)
+        except Exception:
+            pass
+
+
+def _aux_of(t: torch.Tensor, seq_dim: int):
+    """(src contiguous, dst buffer at full capacity, planes, plane stride bytes, row bytes) for a tensor that is
+    compacted along ``seq_dim``; everything before seq_dim is a 'plane', everything after it a 'row'."""
+    src = t.contiguous()
+    planes = 1
+    for d in src.shape[:seq_dim]:
+        planes *= d
+    row = src.element_size()
+    for d in src.shape[seq_dim + 1:]:
+        row *= d
+    dst = torch.empty_like(src)
+    stride = src.shape[seq_dim] * row
+    return src, dst, planes, stride, row
+
+
+class FrameFusion(nn.Module):
+    def __init__(self, cost=0.3, similarity_lower_bound=0.6, ratio_lower_bound=0.1):
+        super(FrameFusion, self).__init__()
+        self.cost = cost
+        self.similarity_lower_bound = similarity_lower_bound
+        self.ratio_lower_bound = ratio_lower_bound
+        self._dev = {}                  # torch.device -> _DeviceState
+        self._links_for = None          # (patch_type tensor, its _version, device) the workspace links describe
+        self.use_fused = True           # allow the single-pass kernel (threshold branch)
+        self.debug_trace = False        # tests: keep what flowed between the stages of the last call
+        self.last_trace = None
+
+    # ---------------------------------------------------------------------------------------------
+    def prepare(
+        self,
+        patch_type: torch.Tensor,
+        patch_num: int,
+        image_token_start_index: torch.Tensor,
+        image_token_end_index: torch.Tensor,
+        image_token_length: torch.Tensor,
+        original_length: int,
+        finish_merging: bool = False,
+        finish_pruning: bool = False,
+        sparsity_list: List[float] = None,
+    ):
+        """Per-prefill state reset (main.py:15-38)."""
+        self.patch_type = patch_type
+        self.patch_num = patch_num
+        self.image_token_start_index = image_token_start_index
+        self.image_token_end_index = image_token_end_index
+        self.image_token_length = image_token_length
+        self.original_length = original_length
+        self.finish_merging = finish_merging
+        self.finish_pruning = finish_pruning
+        if sparsity_list is None:
+            self.sparsity_list = []
+        else:
+            self.sparsity_list = sparsity_list
+        self._links_for = None
+
+    # ---------------------------------------------------------------------------------------------
+    def _state(self, device) -> _DeviceState:
+        st = self._dev.get(device)
+        if st is None:
+            st = self._dev[device] = _DeviceState(device)
+        return st
+
+    @staticmethod
+    def _n_ids(patch_num) -> int:
+        # torch.arange(patch_num) semantics: nvila passes a float, minicpmv a 0-d tensor
+        if isinstance(patch_num, torch.Tensor):
+            patch_num = patch_num.item()
+        return int(math.ceil(float(patch_num)))
+
+    def _ensure_links(self, st: _DeviceState, q_len: int):
+        pt = self.patch_type
+        key = self._links_for
+        if key is not None and key[0] is pt and key[1] == pt._version and key[2] == st.device:
+            return
+        if pt.numel() != q_len:
+            raise RuntimeError(f"patch_type has {pt.numel()} entries for a sequence of {q_len} tokens")
+        n_ids = self._n_ids(self.patch_num)
+        st.workspace(q_len, n_ids)
+        ptc = pt.reshape(-1).to(torch.int64).contiguous()
+        wp, wb = st.ws_ptr()
+        _lib.check(st.lib.ff_build_links(st.ctx, wp, wb, ptc.data_ptr(), q_len, n_ids, _stream(st.device)))
+        self._links_for = (pt, pt._version, st.device)
+
+    def _pos_aux(self, position_embeddings, auxes):
+        """Registers the position container's tensors for compaction; returns a closure that rebuilds it."""
+        if type(position_embeddings) == list:
+            assert len(position_embeddings) == 2
+            seq_dim = 2 if position_embeddings[0].ndim == 4 else 1
+            i0 = len(auxes)
+            auxes.append(_aux_of(position_embeddings[0], seq_dim) + (seq_dim,))
+            auxes.append(_aux_of(position_embeddings[1], seq_dim) + (seq_dim,))
+
+            def rebuild(outs):
+                position_embeddings[0] = outs[i0]
+                position_embeddings[1] = outs[i0 + 1]
+                return position_embeddings
+            return rebuild
+        elif type(position_embeddings) == torch.Tensor:
+            if position_embeddings.ndim == 2:
+                i0 = len(auxes)
+                auxes.append(_aux_of(position_embeddings, 1) + (1,))
+                return lambda outs: outs[i0]
+            else:
+                raise NotImplementedError("Only support 2D position embeddings")
+        else:
+            raise NotImplementedError("Only support list or tensor for position embeddings")
+
+    @staticmethod
+    def _pack_aux(auxes):
+        arr = (_lib.FFAux * max(len(auxes), 1))()
+        for i, (src, dst, planes, stride, row, _sd) in enumerate(auxes):
+            arr[i].src = src.data_ptr()
+            arr[i].dst = dst.data_ptr()
+            arr[i].planes = planes
+            arr[i].src_plane_stride = stride
+            arr[i].dst_plane_stride = stride
+            arr[i].row_bytes = row
+        return arr
+
+    @staticmethod
+    def _narrow(auxes, s_keep):
+        outs = []
+        for (_src, dst, planes, _stride, _row, seq_dim) in auxes:
+            v = dst.narrow(seq_dim, 0, s_keep)
+            outs.append(v if planes == 1 else v.contiguous())
+        return outs
+
+    def _compact_mask(self, st, attention_mask, q_len, s_keep):
+        if attention_mask.ndim != 4 or attention_mask.shape[-1] != q_len or attention_mask.shape[-2] != q_len \
+                or attention_mask.shape[0] != 1 or attention_mask.shape[1] != 1:
+            raise NotImplementedError("attention_mask must be [1, 1, S, S]")
+        m = attention_mask.contiguous()
+        out = torch.empty((1, 1, s_keep, s_keep), dtype=m.dtype, device=m.device)
+        wp, wb = st.ws_ptr()
+        _lib.check(st.lib.ff_compact_mask(st.ctx, wp, wb, m.data_ptr(), out.data_ptr(), q_len, s_keep,
+                                          m.element_size(), _stream(st.device)))
+        return out
+
+    # ---------------------------------------------------------------------------------------------
+    def forward(self, hidden_states, position_embeddings, attention_mask, self_attn_weights=None):
+        """Same contract as the reference forward (main.py:40-140): returns
+        ``(hidden_states, position_embeddings, attention_mask)`` after at most one prune and one merge stage."""
+        bsz, q_len, hidden_size = hidden_states.size()
+        device = hidden_states.device
+        self.last_trace = None
+
+        # pruning (main.py:61-101)
+        if q_len > 1 and self.finish_merging == True and self.finish_pruning == False:
+            hidden_states, position_embeddings, attention_mask = self._prune(
+                hidden_states, position_embeddings, attention_mask, self_attn_weights)
+            self.finish_pruning = True
+
+        # merging (main.py:104-138)
+        if q_len > 1 and (not self.finish_merging):
+            hidden_states, position_embeddings, attention_mask = self._merge(
+                hidden_states, position_embeddings, attention_mask)
+
+        return hidden_states, position_embeddings, attention_mask
+
+    # ---------------------------------------------------------------------------------------------
+    def _require_cuda(self, t):
+        if not t.is_cuda:
+            raise RuntimeError("framefusion_b200 runs on CUDA tensors only (there is no CPU fallback)")
+
+    def _prune(self, hidden_states, position_embeddings, attention_mask, self_attn_weights):
+        self._require_cuda(hidden_states)
+        bsz, q_len, hidden_size = hidden_states.size()
+        assert bsz == 1, "Only support batch size 1"
+        device = hidden_states.device
+        st = self._state(device)
+
+        def to_int(x):
+            return x.item() if isinstance(x, torch.Tensor) else int(x)
+        start = to_int(self.image_token_start_index)
+        length = to_int(self.image_token_length - (self.original_length - q_len))
+        if self_attn_weights is None:
+            raise TypeError("the prune stage needs self_attn_weights (last-query attention probabilities)")
+        attn = self_attn_weights[0]
+        if attn.shape[-1] != q_len:
+            raise RuntimeError(f"self_attn_weights covers {attn.shape[-1]} keys, hidden_states has {q_len} tokens")
+        attn = attn.reshape(-1, q_len).to(hidden_states.dtype).contiguous()
+        pruning_ratio = self._compute_pruning_ratio(self.sparsity_list, self.cost)
+        k = round(length * (1 - pruning_ratio))
+        if k < 0 or k > length or start < 0 or start + length > q_len:
+            raise RuntimeError(f"selected index k out of range (k={k}, vision span [{start}, {start + length}) of {q_len})")
+
+        auxes = []
+        rebuild = self._pos_aux(position_embeddings, auxes)
+        hidden = hidden_states.contiguous()
+        out = torch.empty_like(hidden)
+        imp = torch.empty(q_len, dtype=hidden.dtype, device=device) if self.debug_trace else None
+        if st.ws is None:
+            st.workspace(q_len, 0)
+        wp, wb = st.ws_ptr()
+        _lib.check(st.lib.ff_prune_layer(
+            st.ctx, wp, wb, attn.data_ptr(), attn.shape[0], hidden.data_ptr(), out.data_ptr(), _dtype_code(hidden),
+            q_len, hidden_size, start, length, k, self._pack_aux(auxes), len(auxes),
+            imp.data_ptr() if imp is not None else None, _stream(device)))
+        torch.cuda.current_stream(device).synchronize()
+        s_keep = int(st.status[_lib.ST_SEQ_KEEP])
+        outs = self._narrow(auxes, s_keep)
+        position_embeddings = rebuild(outs)
+        hidden_states = out.narrow(1, 0, s_keep)
+        if attention_mask != None:
+            attention_mask = self._compact_mask(st, attention_mask, q_len, s_keep)
+        if self.debug_trace:
+            keep = torch.empty(q_len, dtype=torch.uint8, device=device)
+            _lib.check(st.lib.ff_debug_read(st.ctx, wp, wb, 0, keep.data_ptr(), q_len, 0, _stream(device)))
+            self.last_trace = dict(stage="prune", keep=np.nonzero(keep.cpu().numpy())[0], importance=imp.float().cpu().numpy(),
+                                   start=start, length=length)
+        return hidden_states, position_embeddings, attention_mask
+
+    def _merge(self, hidden_states, position_embeddings, attention_mask):
+        self._require_cuda(hidden_states)
+        bsz, q_len, hidden_size = hidden_states.size()
+        assert bsz == 1, "Only support batch size 1"
+        device = hidden_states.device
+        st = self._state(device)
+
+        # align devices (main.py:106)
+        self.patch_type = self.patch_type.to(device)
+        sparsity_upper_bound = self._compute_pruning_ratio(self.sparsity_list, self.cost)
+        self._ensure_links(st, q_len)
+
+        dt = hidden_states.dtype
+        thr = torch.tensor(self.similarity_lower_bound, dtype=dt).item()     # the scalar is compared in T
+        hidden = hidden_states.contiguous()
+        out = torch.empty_like(hidden)
+        auxes = [_aux_of(self.patch_type.reshape(1, -1).to(torch.int64), 1) + (1,)]
+        rebuild = self._pos_aux(position_embeddings, auxes)
+        packed = self._pack_aux(auxes)
+        wp, wb = st.ws_ptr()
+        stream = _stream(device)
+        code = _dtype_code(hidden)
+
+        def launch(flags):
+            _lib.check(st.lib.ff_merge_layer(st.ctx, wp, wb, hidden.data_ptr(), out.data_ptr(), code, q_len, hidden_size,
+                                             thr, float(sparsity_upper_bound), packed, len(auxes), flags, stream))
+            torch.cuda.current_stream(device).synchronize()
+
+        fused = 1 if self.use_fused else 0
+        launch(fused)
+        status = st.status
+        if int(status[_lib.ST_ERROR]) == 3:
+            # the single-pass kernel speculates on the threshold branch; the count says top-k: redo generically
+            self._links_for = None
+            self._ensure_links(st, q_len)
+            launch(0)
+        err = int(status[_lib.ST_ERROR])
+        if err == 1:
+            raise ZeroDivisionError("division by zero")                      # frame_token_num == 0 (main.py:114)
+        if err == 2:
+            raise RuntimeError("selected index k out of range")              # torch.topk's complaint (main.py:122)
+        count, frame_token_num = int(status[_lib.ST_COUNT]), int(status[_lib.ST_NVIS])
+        s_keep, branch = int(status[_lib.ST_SEQ_KEEP]), int(status[_lib.ST_BRANCH])
+        above_k_ratio = count / frame_token_num
+        assert (above_k_ratio < sparsity_upper_bound) == (branch == 0), "device / host branch decision disagree"
+        if above_k_ratio < sparsity_upper_bound:
+            self.sparsity_list.append(above_k_ratio)
+            if above_k_ratio < self.ratio_lower_bound:
+                self.finish_merging = True
+        else:
+            self.finish_merging = True
+            self.finish_pruning = True
+
+        if self.debug_trace:
+            self._record_merge_trace(st, hidden, q_len, int(status[_lib.ST_NCHAIN]), branch)
+
+        outs = self._narrow(auxes, s_keep)
+        self.patch_type = outs[0].reshape(bsz, -1)
+        self._links_for = (self.patch_type, self.patch_type._version, device)
+        hidden_states = out.narrow(1, 0, s_keep)
+        position_embeddings = rebuild(outs)
+        if attention_mask is not None:
+            attention_mask = self._compact_mask(st, attention_mask, q_len, s_keep)
+        return hidden_states, position_embeddings, attention_mask
+
+    def _record_merge_trace(self, st, hidden, q_len, n_chain, branch):
+        device = hidden.device
+        wp, wb = st.ws_ptr()
+        stream = _stream(device)
+        keep = torch.empty(q_len, dtype=torch.uint8, device=device)
+        flags = torch.empty(max(n_chain, 1), dtype=torch.uint8, device=device)
+        sim = torch.empty(max(n_chain, 1), dtype=hidden.dtype, device=device)
+        order = torch.empty(max(n_chain, 1), dtype=torch.int64, device=device)
+        _lib.check(st.lib.ff_debug_read(st.ctx, wp, wb, 0, keep.data_ptr(), q_len, 0, stream))
+        _lib.check(st.lib.ff_debug_read(st.ctx, wp, wb, 1, flags.data_ptr(), n_chain, 0, stream))
+        _lib.check(st.lib.ff_debug_read(st.ctx, wp, wb, 2, sim.data_ptr(), n_chain, _dtype_code(hidden), stream))
+        _lib.check(st.lib.ff_debug_read(st.ctx, wp, wb, 3, order.data_ptr(), n_chain, 0, stream))
+        torch.cuda.current_stream(device).synchronize()
+        self.last_trace = dict(
+            stage="merge", branch="topk" if branch else "threshold",
+            keep_mask=keep[:q_len].cpu().numpy().astype(bool),
+            merge_index=np.nonzero(flags[:n_chain].cpu().numpy())[0],
+            sim_values=sim[:n_chain].float().cpu().numpy(),
+            order=order[:n_chain].cpu().numpy())
+
+    # ---------------------------------------------------------------------------------------------
+    # static helpers with the reference's signatures (main.py:180-343)
+    # ---------------------------------------------------------------------------------------------
+    _static_state = {}
+
+    @classmethod
+    def _static(cls, device) -> _DeviceState:
+        st = cls._static_state.get(device)
+        if st is None:
+            st = cls._static_state[device] = _DeviceState(device)
+        return st
+
+    @staticmethod
+    def compute_similarity_and_token_index_by_patch(hidden_states, token_patch_type, patch_num):
+        """(similarity_by_patch [1,N] in the hidden dtype, token_index_by_patch [1,N] int64) — main.py:180-241."""
+        bsz, q_len, hidden_size = hidden_states.size()
+        device = hidden_states.device
+        assert bsz == 1, "Only support batch size 1"
+        if not hidden_states.is_cuda:
+            raise RuntimeError("framefusion_b200 runs on CUDA tensors only (there is no CPU fallback)")
+        st = FrameFusion._static(device)
+        n_ids = FrameFusion._n_ids(patch_num)
+        st.workspace(q_len, n_ids)
+        wp, wb = st.ws_ptr()
+        stream = _stream(device)
+        pt = token_patch_type.to(device).reshape(-1).to(torch.int64).contiguous()
+        _lib.check(st.lib.ff_build_links(st.ctx, wp, wb, pt.data_ptr(), q_len, n_ids, stream))
+        torch.cuda.current_stream(device).synchronize()
+        n = int(st.status[_lib.ST_NCHAIN])
+        sim = torch.empty((bsz, n), dtype=hidden_states.dtype, device=device)
+        order = torch.empty((bsz, n), dtype=torch.int64, device=device)
+        hidden = hidden_states.contiguous()
+        _lib.check(st.lib.ff_similarity(st.ctx, wp, wb, hidden.data_ptr(), _dtype_code(hidden), q_len, hidden_size,
+                                        2.0, sim.data_ptr(), order.data_ptr(), stream))
+        return sim, order
+
+    @staticmethod
+    def merge_tokens_and_get_mask(hidden_states: torch.Tensor, similarity_by_patch, token_index_by_patch, merge_index_by_patch):
+        """In-place merge of ``hidden_states`` + keep mask ``[1,S]`` bool — main.py:243-319."""
+        device = hidden_states.device
+        if merge_index_by_patch.shape[0] == 0:
+            keep_mask = torch.ones(hidden_states.shape[:-1], dtype=torch.bool, device=device)
+            return hidden_states, keep_mask
+        if not hidden_states.is_cuda:
+            raise RuntimeError("framefusion_b200 runs on CUDA tensors only (there is no CPU fallback)")
+        bsz, q_len, hidden_size = hidden_states.size()
+        assert bsz == 1, "Only support batch size 1"
+        if not hidden_states.is_contiguous():
+            raise RuntimeError("merge_tokens_and_get_mask works in place and needs contiguous hidden_states")
+        st = FrameFusion._static(device)
+        st.workspace(q_len, 0)
+        wp, wb = st.ws_ptr()
+        order = token_index_by_patch.reshape(-1).to(device=device, dtype=torch.int64).contiguous()
+        idx = merge_index_by_patch.reshape(-1).to(device=device, dtype=torch.int64).contiguous()
+        keep = torch.empty(q_len, dtype=torch.uint8, device=device)
+        _lib.check(st.lib.ff_merge_apply(st.ctx, wp, wb, hidden_states.data_ptr(), _dtype_code(hidden_states), q_len,
+                                         hidden_size, order.data_ptr(), order.numel(), idx.data_ptr(), idx.numel(),
+                                         keep.data_ptr(), _stream(device)))
+        return hidden_states, keep.to(torch.bool).reshape(bsz, q_len)
+
+    @staticmethod
+    def _compute_pruning_ratio(sparsity_list, cost, num_layers=28):
+        """Budget formula, host doubles (main.py:321-343)."""
+        list_length = len(sparsity_list)
+        s = 1
+        total_calcution = 0
+        for i in range(list_length):
+            s *= (1 - sparsity_list[i])
+            total_calcution += s
+        remain_calcution = num_layers * cost - total_calcution
+        if remain_calcution < 0:
+            raise ValueError("The cost is too small")
+        if remain_calcution / ((num_layers - list_length) * s) > 1:
+            return 0
+        return 1 - (remain_calcution / ((num_layers - list_length) * s))
+
+
+def cosine_similarity(mat1, mat2):
+    """Exported helper of the reference (main.py:345-349); the operator itself uses the fused kernels."""
+    dot_product = torch.sum(mat1 * mat2, dim=-1)
+    norm_vec1 = torch.norm(mat1, dim=-1)
+    norm_vec2 = torch.norm(mat2, dim=-1)
+    return dot_product / (norm_vec1 * norm_vec2)
+
+
+def find_contigious_latter_index(index_tensor: torch.LongTensor) -> torch.Tensor:
+    """Run lengths at the last element of every run of ones, zeros elsewhere (main.py:351-380);
+    ``[0,1,1,1,0,0,1,1] -> [0,0,0,3,0,0,0,2]``.  Exported helper; the kernels carry runs implicitly."""
+    bsz, n = index_tensor.shape
+    ones = index_tensor == 1
+    idx = torch.arange(n, device=index_tensor.device).expand(bsz, n)
+    # position of the most recent non-one element, via a running maximum
+    last_zero = torch.where(ones, torch.full_like(idx, -1), idx).cummax(dim=1).values
+    run = (idx - last_zero).to(index_tensor.dtype)
+    nxt = torch.cat([ones[:, 1:], torch.zeros((bsz, 1), dtype=torch.bool, device=index_tensor.device)], dim=1)
+    return torch.where(ones & ~nxt, run, torch.zeros_like(run))

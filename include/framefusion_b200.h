@@ -1,0 +1,148 @@
+/*
+ * framefusion_b200 — C ABI of the B200-native FrameFusion token-reduction path.
+ *
+ * One shared library (libframefusion_b200.so, built from framefusion_b200/csrc/ for sm_100a).
+ * Plain pointers and sizes only: no torch / C++ types cross this boundary.  All device work is
+ * enqueued on the caller's stream (`stream` is a cudaStream_t passed as void*); nothing here
+ * synchronises the stream — the caller does that once, then reads the status block.
+ *
+ * The reference (thu-nics/FrameFusion) is pure Python/PyTorch and has no FFI; each entry point below
+ * replaces a span of ATen ops in /root/reference/framefusion/main.py (cited per function) and is what a
+ * reference-side binding (ctypes) calls instead of those ops.
+ *
+ * Conventions
+ *   - B = 1 (the reference asserts it, main.py:203).  hidden is row-major contiguous [S, H].
+ *   - dtype: FF_BF16 / FF_F16 / FF_F32 — the dtype of hidden_states ("T" below).
+ *   - every function returns 0 on success, a negative FF_E* code otherwise; ff_last_error() gives the
+ *     text for the calling thread.
+ *   - `ws` is a caller-allocated device workspace of at least ff_workspace_bytes(capacity, n_ids) bytes,
+ *     256-byte aligned.  It carries the chain links (by-patch order) from one call to the next, so one
+ *     workspace belongs to one FrameFusion object / one request at a time.
+ *   - ff_ctx owns a pinned, device-mapped status block; kernels write results there (sizes, counts, the
+ *     branch taken) so that a reducing call costs exactly one host<->device synchronisation.
+ */
+#ifndef FRAMEFUSION_B200_H
+#define FRAMEFUSION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FF_ABI_VERSION 1
+
+enum ff_dtype { FF_BF16 = 0, FF_F16 = 1, FF_F32 = 2 };
+
+enum ff_error {
+    FF_OK = 0,
+    FF_E_BADARG = -1,      /* null pointer, negative size, unsupported dtype, misaligned workspace */
+    FF_E_WORKSPACE = -2,   /* workspace too small for this call */
+    FF_E_CUDA = -3,        /* a CUDA runtime call or kernel launch failed */
+    FF_E_UNSUPPORTED = -4  /* shape outside what the kernels handle (see ff_last_error) */
+};
+
+/* status block layout (int64 slots, host-visible after the stream has been synchronised) */
+enum ff_status_slot {
+    FF_ST_SEQ_KEEP = 0,    /* S_keep: rows in the compacted outputs */
+    FF_ST_COUNT = 1,       /* #{j : sim[j] >= T(similarity_lower_bound)}            (main.py:113) */
+    FF_ST_NVIS = 2,        /* #{i : patch_type[i] != -1}                            (main.py:112) */
+    FF_ST_NCHAIN = 3,      /* N: tokens whose patch id is in [0, n_ids)             (main.py:208-214) */
+    FF_ST_BRANCH = 4,      /* 0 = threshold branch, 1 = top-k branch                (main.py:116-127) */
+    FF_ST_TOPK = 5,        /* k used by the branch that ran (merge top-k or prune top-k) */
+    FF_ST_ERROR = 6,       /* device-side error: 0 ok, 1 n_vis == 0, 2 k > N, 3 fused path declined */
+    FF_ST_NMERGED = 7,     /* tokens merged away by this call */
+    FF_ST_SLOTS = 16
+};
+
+typedef struct ff_ctx ff_ctx;
+
+/* aux tensor compacted along the sequence axis together with hidden (cos, sin, patch_type, position ids):
+ * `planes` slabs of [S, row_bytes] at src (slab stride src_plane_stride bytes) -> slabs of
+ * [S_keep, row_bytes] at dst (slab stride dst_plane_stride bytes).        (main.py:132, 142-178) */
+typedef struct ff_aux {
+    const void* src;
+    void* dst;
+    int64_t planes;
+    int64_t src_plane_stride;
+    int64_t dst_plane_stride;
+    int64_t row_bytes;
+} ff_aux;
+
+#define FF_MAX_AUX 6
+
+int ff_abi_version(void);
+const char* ff_last_error(void);
+
+/* ---- context -------------------------------------------------------------------------------- */
+int ff_ctx_create(int device, ff_ctx** out);
+int ff_ctx_destroy(ff_ctx* ctx);
+/* host pointer to FF_ST_SLOTS int64 values */
+const int64_t* ff_ctx_status(const ff_ctx* ctx);
+
+int64_t ff_workspace_bytes(int64_t seq_capacity, int64_t n_ids);
+
+/* ---- chain links: replaces the eq-broadcast + nonzero "sort by patch" of main.py:208-214 ------
+ * patch_type [S] int64 on the device; n_ids = ceil(patch_num).  Leaves in `ws` the by-patch order, the
+ * patch id of every by-patch position and the inverse map; status: NCHAIN, NVIS. */
+int ff_build_links(ff_ctx* ctx, void* ws, int64_t ws_bytes, const int64_t* patch_type, int64_t seq_len,
+                   int64_t n_ids, void* stream);
+
+/* ---- similarity: replaces main.py:216-238 + cosine_similarity (main.py:345-349) ----------------
+ * Needs links for this sequence in `ws`.  Writes sim_out [N] in T (-2 at chain heads) and, if not null,
+ * order_out [N] int64.  thr = the similarity lower bound already rounded to T (as a double); the count of
+ * sim >= thr goes to status COUNT and the flags stay in `ws`. */
+int ff_similarity(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, int dtype, int64_t seq_len,
+                  int64_t hidden_size, double thr, void* sim_out, int64_t* order_out, void* stream);
+
+/* ---- merge (in place) + keep mask: replaces merge_tokens_and_get_mask, main.py:243-319 ----------
+ * order [N] int64, merge_index [M] int64 ascending by-patch positions (both on the device).  hidden is
+ * modified in place at anchor rows exactly as the reference does; keep_mask_out [S] bytes (0/1). */
+int ff_merge_apply(ff_ctx* ctx, void* ws, int64_t ws_bytes, void* hidden, int dtype, int64_t seq_len,
+                   int64_t hidden_size, const int64_t* order, int64_t n_chain, const int64_t* merge_index,
+                   int64_t n_merge, uint8_t* keep_mask_out, void* stream);
+
+/* ---- one merge-stage call of FrameFusion.forward, fused: main.py:104-138 -----------------------
+ * similarity -> count -> branch (r = count / n_vis < bound ? threshold : top-k with k = int(bound*n_vis))
+ * -> runs -> merged rows -> compaction of hidden and of every aux tensor, and the links for the next call.
+ * hidden [S,H] is read only; hidden_out must hold S rows (only S_keep are written).  patch_type is aux[0]
+ * by convention of the host wrapper but the library does not care.  status: SEQ_KEEP, COUNT, NVIS, NCHAIN,
+ * BRANCH, TOPK, ERROR, NMERGED.  `flags`: bit 0 = allow the single-pass fused kernel. */
+int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, void* hidden_out, int dtype,
+                   int64_t seq_len, int64_t hidden_size, double thr, double bound, const ff_aux* aux,
+                   int n_aux, int flags, void* stream);
+
+/* ---- importance: replaces utils.scaled_dot_product_attention, utils.py:27-57 -------------------
+ * q [Hq, S, D] / k [Hk, S, D] with element strides (head, seq; last dim contiguous); only the last `num`
+ * queries are used.  probs_out [Hq, num, S] in T.  Hq % Hk == 0 (GQA aware: K is read once).
+ * scratch: device buffer of at least Hq*num*S*4 bytes (float32 logits). */
+int ff_importance(ff_ctx* ctx, const void* q, const void* k, int dtype, int64_t n_q_heads, int64_t n_kv_heads,
+                  int64_t seq_len, int64_t head_dim, int64_t num, int64_t q_head_stride, int64_t q_seq_stride,
+                  int64_t k_head_stride, int64_t k_seq_stride, int is_causal, double scale, void* probs_out,
+                  void* scratch, int64_t scratch_bytes, void* stream);
+
+/* ---- one prune-stage call: main.py:61-101 ------------------------------------------------------
+ * attn [n_rows, S] in T (n_rows = heads*num): importance = T(mean over rows); keeps [0,start), the top-k of
+ * [start, start+length) (ties: lowest index first) and [start+length, S); compacts hidden and aux.
+ * importance_out [S] in T may be null.  status: SEQ_KEEP, TOPK. */
+int ff_prune_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* attn, int64_t n_rows,
+                   const void* hidden, void* hidden_out, int dtype, int64_t seq_len, int64_t hidden_size,
+                   int64_t start, int64_t length, int64_t k, const ff_aux* aux, int n_aux,
+                   void* importance_out, void* stream);
+
+/* ---- 4-D mask compaction mask[keep][:, keep]: main.py:100, 138 ---------------------------------
+ * Uses the destination map the last merge/prune call left in `ws`.  mask [S, S] -> mask_out [S_keep, S_keep]. */
+int ff_compact_mask(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* mask, void* mask_out, int64_t seq_len,
+                    int64_t seq_keep, int64_t elem_bytes, void* stream);
+
+/* ---- introspection of the last merge call (tests, static API): copies device arrays out of `ws` ------
+ * what: 0 = keep mask by sequence position (uint8 [S]), 1 = merge flags by by-patch position (uint8 [N]),
+ *       2 = sim (T [N]), 3 = order (int64 [N]) */
+int ff_debug_read(ff_ctx* ctx, void* ws, int64_t ws_bytes, int what, void* dst_device, int64_t n, int dtype,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,180 @@
+"""GPU: the CUDA path (through the C ABI) against the golden fixtures of the unmodified reference and against
+the numpy oracle.  Bit-exact for indices, masks, patch types, position tensors and merged rows; similarities
+bit-exact except where the oracle proves a float32 summation order can move the value (then bracketed)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _harness import GOLDEN_DIR, DT, case_names, run_and_compare, t2f
+from oracle import ff_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+class CudaAdapter:
+    """``framefusion_b200.main.FrameFusion`` behind the interface the harness drives."""
+
+    def __init__(self, cost, slb, rlb, dtype, fused):
+        from framefusion_b200.main import FrameFusion
+        self.ff = FrameFusion(cost, slb, rlb)
+        self.ff.debug_trace = True
+        self.ff.use_fused = fused
+
+    def prepare(self, *args):
+        self.ff.prepare(*args)
+
+    def __call__(self, hidden, pos, mask, attn=None):
+        return self.ff(hidden, pos, mask, attn)
+
+    finish_merging = property(lambda s: s.ff.finish_merging)
+    finish_pruning = property(lambda s: s.ff.finish_pruning)
+    sparsity_list = property(lambda s: s.ff.sparsity_list)
+    patch_type = property(lambda s: s.ff.patch_type)
+
+    def last_trace(self):
+        return self.ff.last_trace
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["generic", "fused"])
+@pytest.mark.parametrize("name", case_names())
+def test_cuda_matches_reference_sequence(name, fused):
+    rep = run_and_compare(name, lambda c, s, r, dt: CudaAdapter(c, s, r, dt, fused), device="cuda")
+    assert rep["n_sim"] > 0
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16", "f32"])
+def test_static_similarity_and_merge_vs_oracle(dtype):
+    from framefusion_b200 import synth
+    from framefusion_b200.main import FrameFusion
+    wl = synth.make_workload(frames=9, patch_num=37, hidden=1024, dtype=DT[dtype], seed=21)
+    hidden = wl.hidden.cuda()
+    sim, order = FrameFusion.compute_similarity_and_token_index_by_patch(hidden, wl.patch_type.cuda(), wl.patch_num)
+    sr = orc.similarity_by_patch(t2f(wl.hidden[0]), wl.patch_type.numpy().reshape(-1), wl.patch_num, dtype)
+    assert sim.dtype == hidden.dtype and order.dtype == torch.int64 and sim.shape == order.shape == (1, sr.order.shape[0])
+    assert np.array_equal(order[0].cpu().numpy(), sr.order)
+    got = t2f(sim[0])
+    neq = got != sr.sim
+    assert not (neq & ~sr.fragile).any()
+    assert ((got >= sr.lo) & (got <= sr.hi))[neq].all()
+    # merge a hand-made index set (runs of length 1..4, never a chain head) in place
+    thr = orc.threshold_in_dtype(0.5, dtype)
+    idx = np.nonzero(got >= thr)[0]
+    want_h, want_keep = orc.merge_tokens_and_get_mask(t2f(wl.hidden[0]), sr.order, idx, dtype)
+    h2 = hidden.clone()
+    out, keep = FrameFusion.merge_tokens_and_get_mask(h2, sim, order, torch.from_numpy(idx).cuda())
+    assert out.data_ptr() == h2.data_ptr()                    # in place, like the reference
+    assert keep.dtype == torch.bool and np.array_equal(keep[0].cpu().numpy(), want_keep)
+    if dtype == "f32":
+        assert np.allclose(t2f(out[0]), want_h, rtol=1e-6, atol=1e-7)
+    else:
+        assert np.array_equal(t2f(out[0]), want_h)
+    # empty index: untouched, all-True mask (main.py:264-266)
+    out, keep = FrameFusion.merge_tokens_and_get_mask(h2, sim, order, torch.zeros(0, dtype=torch.int64).cuda())
+    assert bool(keep.all())
+
+
+def test_importance_vs_reference():
+    from framefusion_b200 import synth
+    from framefusion_b200.utils import scaled_dot_product_attention
+    z = np.load(os.path.join(GOLDEN_DIR, "importance.npz"))
+    for tag in "abcdef":
+        spec = json.loads(str(z[f"imp_{tag}_spec"]))
+        dt = spec["dtype"]
+        q, k = synth.make_attention_inputs(spec["s_len"], 28, 4, 128, DT[dt], seed=spec["s_len"])
+        # K is handed over before repeat_kv: the kernel is GQA aware
+        got = scaled_dot_product_attention(q.cuda(), k.cuda(), None, num=spec["num"], is_causal=spec["causal"], enable_gqa=True)
+        got = t2f(got[0])
+        want = orc.bits_to_f32(z[f"imp_{tag}_out"], dt).reshape(got.shape)
+        if dt == "f32":
+            assert np.allclose(got, want, rtol=3e-5, atol=1e-9)
+        else:
+            ulp = np.abs(want) * (2.0 ** -7 if dt == "bf16" else 2.0 ** -10) + 1e-30
+            assert (np.abs(got - want) <= ulp * 1.01).all()
+            assert (got != want).mean() < 0.02, (tag, (got != want).mean())
+
+
+def test_importance_strided_inputs():
+    """q / k as the attention hook has them: [1, S, heads, D] storage viewed as [1, heads, S, D]."""
+    from framefusion_b200 import synth
+    from framefusion_b200.utils import scaled_dot_product_attention
+    q, k = synth.make_attention_inputs(300, 28, 4, 128, torch.bfloat16, seed=5)
+    qs = q.transpose(1, 2).contiguous().transpose(1, 2).cuda()
+    ks = k.transpose(1, 2).contiguous().transpose(1, 2).cuda()
+    assert not qs.is_contiguous()
+    a = scaled_dot_product_attention(qs, ks, None, num=1, is_causal=True, enable_gqa=True)
+    b = scaled_dot_product_attention(q.cuda(), k.cuda(), None, num=1, is_causal=True, enable_gqa=True)
+    assert torch.equal(a, b)
+    kk = k.repeat_interleave(7, dim=1).cuda()
+    c = scaled_dot_product_attention(q.cuda(), kk, None, num=1, is_causal=True)
+    assert torch.equal(a, c)
+
+
+def test_errors_and_passthrough():
+    from framefusion_b200 import synth
+    from framefusion_b200.main import FrameFusion
+    wl = synth.make_workload(frames=4, patch_num=8, hidden=256, dtype=torch.bfloat16, seed=1)
+    ff = FrameFusion(0.01, 0.0, 0.1)
+    ff.prepare(*wl.prepare_args())
+    h = wl.hidden.cuda()
+    pos = [wl.cos.cuda(), wl.sin.cuda()]
+    # decode step: untouched (main.py:61,104 guards)
+    h1, p1, m1 = ff(h[:, :1], pos, None)
+    assert h1.shape[1] == 1 and p1 is pos and m1 is None
+    ff.sparsity_list = [0.0] * 10
+    with pytest.raises(ValueError, match="The cost is too small"):
+        ff(h, pos, None)
+    ff = FrameFusion()
+    ff.prepare(*wl.prepare_args())
+    with pytest.raises(NotImplementedError):
+        ff(h, (wl.cos.cuda(), wl.sin.cuda()), None)           # tuple, not list (main.py:176-177)
+    with pytest.raises(NotImplementedError):
+        ff(h, wl.cos.cuda(), None)                            # 3-D tensor (main.py:174-175)
+    with pytest.raises(AssertionError, match="Only support batch size 1"):
+        ff(torch.cat([h, h]), pos, None)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ff(wl.hidden, [wl.cos, wl.sin], None)
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["generic", "fused"])
+@pytest.mark.parametrize("cfg", ["C2", "C4"])
+def test_full_size_against_oracle(cfg, fused):
+    """BASELINE configs at full size: first merge call, CUDA vs the numpy oracle on identical bits."""
+    from framefusion_b200 import synth
+    from framefusion_b200.main import FrameFusion
+    c = synth.CONFIGS[cfg]
+    wl = synth.make_workload(c["frames"], c["patch_num"], c["hidden"], c["dtype"], seed=0)
+    ff = FrameFusion(c["cost"], c["slb"], c["rlb"])
+    ff.use_fused = fused
+    ff.debug_trace = True
+    ff.prepare(*wl.prepare_args())
+    pos = [wl.cos.cuda(), wl.sin.cuda()]
+    out, pos, _ = ff(wl.hidden.cuda(), pos, None)
+    tr = ff.last_trace
+    o = orc.OracleFrameFusion(c["cost"], c["slb"], c["rlb"], "bf16")
+    o.prepare(wl.patch_type.numpy(), wl.patch_num, *wl.prepare_args()[2:])
+    hid = t2f(wl.hidden[0])
+    want_h, want_pos, _ = o.forward(hid, [t2f(wl.cos[0]), t2f(wl.sin[0])], None)
+    sr = o.last["sim"]
+    got_sim = tr["sim_values"]
+    neq = got_sim != sr.sim
+    assert not (neq & ~sr.fragile).any()
+    assert ((got_sim >= sr.lo) & (got_sim <= sr.hi))[neq].all()
+    thr = orc.threshold_in_dtype(c["slb"], "bf16")
+    flips = int(((got_sim >= thr) != (sr.sim >= thr)).sum())
+    print(f"{cfg}: N={got_sim.shape[0]} sims differing from oracle (all inside the fragile bracket): {int(neq.sum())}, threshold flips: {flips}")
+    assert np.array_equal(tr["order"], sr.order)
+    if flips == 0:
+        assert np.array_equal(tr["keep_mask"], o.last["keep_mask"])
+        assert out.shape[1] == want_h.shape[0]
+        assert np.array_equal(t2f(out[0]), want_h)
+        assert np.array_equal(t2f(pos[0][0]), want_pos[0]) and np.array_equal(t2f(pos[1][0]), want_pos[1])
+        assert np.array_equal(ff.patch_type[0].cpu().numpy(), o.patch_type)
+        assert ff.sparsity_list == o.sparsity_list
+    else:
+        # a similarity sitting on a rounding boundary of T moved across the threshold: selection differs in
+        # exactly those positions
+        diff = np.nonzero(tr["keep_mask"] != o.last["keep_mask"])[0]
+        assert len(diff) == flips
