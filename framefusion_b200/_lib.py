@@ -17,7 +17,7 @@ FF_BF16, FF_F16, FF_F32 = 0, 1, 2
 FF_MAX_AUX = 6
 
 # status slots (enum ff_status_slot)
-ST_SEQ_KEEP, ST_COUNT, ST_NVIS, ST_NCHAIN, ST_BRANCH, ST_TOPK, ST_ERROR, ST_NMERGED = range(8)
+ST_SEQ_KEEP, ST_COUNT, ST_NVIS, ST_NCHAIN, ST_BRANCH, ST_TOPK, ST_ERROR, ST_NMERGED, ST_FUSED = range(9)
 ST_SLOTS = 16
 
 EXPORTS = [

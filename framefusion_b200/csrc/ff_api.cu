@@ -48,6 +48,8 @@ struct ff_ctx {
     int64_t n_ids;
     int have_order;      // by-patch order / rank arrays valid for `parity`
     int have_link;       // successor links valid for `parity`
+    int link_mapped;     // link[parity] holds indices of the previous call: translate through dst[parity ^ 1]
+    unsigned epoch;      // fused calls since ff_build_links (tags the flag bytes and look-back descriptors)
     int sm_count;
 };
 
@@ -65,13 +67,13 @@ struct Ws {
     float* sim;
     uint8_t* flag;
     uint8_t* state;
-    int* dst;
+    int* dst[2];
     int* srcidx;
-    int* term;
     int* hist;
     int* total;
     int* base;
     unsigned long long* tiles;
+    size_t n_tiles_cap;
     size_t bytes;
 };
 
@@ -94,13 +96,14 @@ Ws carve(void* base_ptr, int64_t cap, int64_t n_ids) {
     w.sim = (float*)take(cap * 4);
     w.flag = (uint8_t*)take(cap);
     w.state = (uint8_t*)take(cap);
-    w.dst = (int*)take(cap * 4);
+    w.dst[0] = (int*)take(cap * 4);
+    w.dst[1] = (int*)take(cap * 4);
     w.srcidx = (int*)take(cap * 4);
-    w.term = (int*)take(cap * 4);
     w.hist = (int*)take((size_t)n_chunks * (size_t)(n_ids > 0 ? n_ids : 1) * 4);
     w.total = (int*)take((size_t)(n_ids > 0 ? n_ids : 1) * 4);
     w.base = (int*)take((size_t)(n_ids > 0 ? n_ids : 1) * 4);
-    w.tiles = (unsigned long long*)take((size_t)(cap / FUSED_MIN_ROWS + 2) * 8);
+    w.n_tiles_cap = (size_t)(cap / FUSED_MIN_ROWS + 2);
+    w.tiles = (unsigned long long*)take(w.n_tiles_cap * 8);
     w.bytes = off;
     return w;
 }
@@ -149,6 +152,11 @@ __global__ void k_store_order(const int* __restrict__ order, int n, int64_t* out
 __global__ void k_keep_from_dst(const int* __restrict__ dst, int n, uint8_t* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = dst[i] >= 0;
+}
+
+__global__ void k_srcidx_from_dst(const int* __restrict__ dst, int n, int* __restrict__ srcidx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && dst[i] >= 0) srcidx[dst[i]] = i;
 }
 
 __global__ void k_copy_u8(const uint8_t* __restrict__ src, int n, uint8_t* out) {
@@ -218,10 +226,10 @@ int launch_merge_compact(const Ws& w, int bank, const void* hidden, void* out, i
         constexpr int DT = decltype(dt)::value;
         if (vec)
             k_merge_compact<DT, true><<<grid, 256, 0, st>>>(hidden, out, (int)S, (int)H, w.rank[bank], w.order[bank], w.flag,
-                                                            w.dst, w.counters[bank], use_flags);
+                                                            w.dst[bank], w.counters[bank], use_flags);
         else
             k_merge_compact<DT, false><<<grid, 256, 0, st>>>(hidden, out, (int)S, (int)H, w.rank[bank], w.order[bank], w.flag,
-                                                             w.dst, w.counters[bank], use_flags);
+                                                             w.dst[bank], w.counters[bank], use_flags);
         FF_LAUNCH_CHECK("k_merge_compact");
         return (int)FF_OK;
     });
@@ -267,6 +275,8 @@ int ff_ctx_create(int device, ff_ctx** out) {
     c->cap = 0;
     c->n_ids = 0;
     c->have_order = c->have_link = 0;
+    c->link_mapped = 0;
+    c->epoch = 0;
     cudaError_t e = cudaHostAlloc((void**)&c->h_status, FF_ST_SLOTS * 8, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e != cudaSuccess) { delete c; return fail(FF_E_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
     memset(c->h_status, 0, FF_ST_SLOTS * 8);
@@ -306,6 +316,12 @@ int ff_build_links(ff_ctx* ctx, void* ws, int64_t ws_bytes, const int64_t* patch
     FF_CUDA(cudaSetDevice(ctx->device));
     const int n_chunks = (int)((S + LINK_CHUNK - 1) / LINK_CHUNK);
     FF_CUDA(cudaMemsetAsync(w.counters[0], 0, 2 * align_up(C_SLOTS * 8), st));
+    if (S > 0) {
+        FF_CUDA(cudaMemsetAsync(w.state, 0, (size_t)S, st));
+        FF_CUDA(cudaMemsetAsync(w.tiles, 0, w.n_tiles_cap * 8, st));
+    }
+    ctx->epoch = 0;
+    ctx->link_mapped = 0;
     if (S > 0 && n_ids > 0) {
         FF_CUDA(cudaMemsetAsync(w.hist, 0, (size_t)n_chunks * n_ids * 4, st));
         k_links_hist<<<n_chunks, LINK_CHUNK, 0, st>>>(patch_type, (int)S, (int)n_ids, w.hist, w.counters[0]);
@@ -404,15 +420,33 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     const int bank = ctx->parity, nb = bank ^ 1;
 
     if ((flags & 1) && S > 0 && ctx->have_link) {
-        int rc = launch_fused(ctx->sm_count, w.counters[bank], w.counters[nb], ctx->d_status, w.link[bank], w.link[nb],
-                              w.state, w.sim, w.dst, w.term, w.tiles, w.rank[bank], hidden, hidden_out, dtype, S, H, thr,
-                              bound, ap, st);
+        FusedArgs fa;
+        fa.hidden = (const char*)hidden;
+        fa.out = (char*)hidden_out;
+        fa.link = w.link[bank];
+        fa.map = ctx->link_mapped ? w.dst[nb] : nullptr;
+        fa.link_next = w.link[nb];
+        fa.state = w.state;
+        fa.sim_seq = w.sim;
+        fa.dst = w.dst[bank];
+        fa.tiles = w.tiles;
+        fa.counters = w.counters[bank];
+        fa.counters_next = w.counters[nb];
+        fa.status = ctx->d_status;
+        fa.bound = bound;
+        const unsigned epoch = ctx->epoch + 1;
+        fa.tag = (epoch - 1) % 127 + 1;
+        fa.epoch = (unsigned long long)((epoch - 1) % 65535 + 1);
+        fa.aux = ap;
+        int rc = launch_fused(ctx->sm_count, dtype, S, H, thr, fa, st);
         if (rc == FF_OK) {
+            ctx->epoch = epoch;
             ctx->last_parity = bank;
             ctx->parity = nb;
             ctx->links_S = -2;
             ctx->have_order = 0;
             ctx->have_link = 1;
+            ctx->link_mapped = 1;
             return FF_OK;
         }
         if (rc != FF_E_UNSUPPORTED) return fail(rc, "fused launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -431,7 +465,7 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     a.order = w.order[bank];
     a.chain = w.chain[bank];
     a.rank = w.rank[bank];
-    a.dst = w.dst;
+    a.dst = w.dst[bank];
     a.srcidx = w.srcidx;
     a.order_next = w.order[nb];
     a.chain_next = w.chain[nb];
@@ -442,7 +476,7 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     FF_LAUNCH_CHECK("k_decide_scan");
     if (int rc = launch_merge_compact(w, bank, hidden, hidden_out, dtype, S, H, 1, st)) return rc;
     if (ap.n && S > 0) {
-        k_aux_compact<<<(int)((S + 7) / 8), 256, 0, st>>>(ap, (int)S, w.dst);
+        k_aux_compact<<<(int)((S + 7) / 8), 256, 0, st>>>(ap, (int)S, w.dst[bank]);
         FF_LAUNCH_CHECK("k_aux_compact");
     }
     if (S > 0) {
@@ -453,6 +487,7 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     ctx->parity = nb;
     ctx->links_S = -2;                                     // = S_keep, known once the host has synchronised
     ctx->have_order = ctx->have_link = 1;
+    ctx->link_mapped = 0;
     return FF_OK;
 }
 
@@ -518,7 +553,7 @@ int ff_prune_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* attn, in
     a.status = ctx->d_status;
     a.imp = w.sim;
     a.sel = w.flag;
-    a.dst = w.dst;
+    a.dst = w.dst[bank];
     a.srcidx = w.srcidx;
     a.S = (int)S;
     a.start = (int)start;
@@ -528,9 +563,10 @@ int ff_prune_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* attn, in
     FF_LAUNCH_CHECK("k_prune_scan");
     if (int rc2 = launch_merge_compact(w, bank, hidden, hidden_out, dtype, S, H, 0, st)) return rc2;
     if (ap.n) {
-        k_aux_compact<<<(int)((S + 7) / 8), 256, 0, st>>>(ap, (int)S, w.dst);
+        k_aux_compact<<<(int)((S + 7) / 8), 256, 0, st>>>(ap, (int)S, w.dst[bank]);
         FF_LAUNCH_CHECK("k_aux_compact");
     }
+    ctx->last_parity = bank;
     if (importance_out) {
         // counters[C_N] is not S here: store with an explicit count
         k_store_vals<<<(int)((S + 255) / 256), 256, 0, st>>>(w.sim, (int)S, dtype, importance_out);
@@ -549,6 +585,8 @@ int ff_compact_mask(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* mask, v
     if (!mask || !mask_out) return fail(FF_E_BADARG, "null mask");
     cudaStream_t st = (cudaStream_t)stream;
     FF_CUDA(cudaSetDevice(ctx->device));
+    k_srcidx_from_dst<<<(int)((S + 255) / 256), 256, 0, st>>>(w.dst[ctx->last_parity], (int)S, w.srcidx);
+    FF_LAUNCH_CHECK("k_srcidx_from_dst");
     switch (elem_bytes) {
         case 1: k_compact_mask<uint8_t><<<(int)S_keep, 256, 0, st>>>((const uint8_t*)mask, (uint8_t*)mask_out, (int)S, (int)S_keep, w.srcidx); break;
         case 2: k_compact_mask<uint16_t><<<(int)S_keep, 256, 0, st>>>((const uint16_t*)mask, (uint16_t*)mask_out, (int)S, (int)S_keep, w.srcidx); break;
@@ -571,7 +609,7 @@ int ff_debug_read(ff_ctx* ctx, void* ws, int64_t ws_bytes, int what, void* dst_d
     const int bank = ctx->last_parity;
     const int grid = (int)((n + 255) / 256);
     switch (what) {
-        case 0: k_keep_from_dst<<<grid, 256, 0, st>>>(w.dst, (int)n, (uint8_t*)dst_device); break;
+        case 0: k_keep_from_dst<<<grid, 256, 0, st>>>(w.dst[bank], (int)n, (uint8_t*)dst_device); break;
         case 1: k_copy_u8<<<grid, 256, 0, st>>>(w.flag, (int)n, (uint8_t*)dst_device); break;
         case 2: k_store_vals<<<grid, 256, 0, st>>>(w.sim, (int)n, dtype, dst_device); break;
         case 3: k_store_order<<<grid, 256, 0, st>>>(w.order[bank], (int)n, (int64_t*)dst_device); break;

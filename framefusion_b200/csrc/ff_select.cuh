@@ -215,6 +215,7 @@ k_decide_scan(DecideArgs a) {
         a.status[FF_ST_TOPK] = s_k;
         a.status[FF_ST_ERROR] = s_err;
         a.status[FF_ST_NMERGED] = N - n_next;
+        a.status[FF_ST_FUSED] = 0;
     }
 }
 

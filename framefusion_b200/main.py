@@ -106,6 +106,7 @@ class FrameFusion(nn.Module):
         self.ratio_lower_bound = ratio_lower_bound
         self._dev = {}                  # torch.device -> _DeviceState
         self._links_for = None          # (patch_type tensor, its _version, device) the workspace links describe
+        self._have_order = False        # the workspace also holds the by-patch order (the fused kernel drops it)
         self.use_fused = True           # allow the single-pass kernel (threshold branch)
         self.debug_trace = False        # tests: keep what flowed between the stages of the last call
         self.last_trace = None
@@ -152,10 +153,11 @@ class FrameFusion(nn.Module):
             patch_num = patch_num.item()
         return int(math.ceil(float(patch_num)))
 
-    def _ensure_links(self, st: _DeviceState, q_len: int):
+    def _ensure_links(self, st: _DeviceState, q_len: int, need_order: bool = False):
         pt = self.patch_type
         key = self._links_for
-        if key is not None and key[0] is pt and key[1] == pt._version and key[2] == st.device:
+        if key is not None and key[0] is pt and key[1] == pt._version and key[2] == st.device \
+                and (self._have_order or not need_order):
             return
         if pt.numel() != q_len:
             raise RuntimeError(f"patch_type has {pt.numel()} entries for a sequence of {q_len} tokens")
@@ -165,6 +167,7 @@ class FrameFusion(nn.Module):
         wp, wb = st.ws_ptr()
         _lib.check(st.lib.ff_build_links(st.ctx, wp, wb, ptc.data_ptr(), q_len, n_ids, _stream(st.device)))
         self._links_for = (pt, pt._version, st.device)
+        self._have_order = True
 
     def _pos_aux(self, position_embeddings, auxes):
         """Registers the position container's tensors for compaction; returns a closure that rebuilds it."""
@@ -305,7 +308,8 @@ class FrameFusion(nn.Module):
         # align devices (main.py:106)
         self.patch_type = self.patch_type.to(device)
         sparsity_upper_bound = self._compute_pruning_ratio(self.sparsity_list, self.cost)
-        self._ensure_links(st, q_len)
+        fused = 1 if self.use_fused else 0
+        self._ensure_links(st, q_len, need_order=not fused)
 
         dt = hidden_states.dtype
         thr = torch.tensor(self.similarity_lower_bound, dtype=dt).item()     # the scalar is compared in T
@@ -323,14 +327,15 @@ class FrameFusion(nn.Module):
                                              thr, float(sparsity_upper_bound), packed, len(auxes), flags, stream))
             torch.cuda.current_stream(device).synchronize()
 
-        fused = 1 if self.use_fused else 0
         launch(fused)
         status = st.status
-        if int(status[_lib.ST_ERROR]) == 3:
+        ran_fused = bool(fused) and int(status[_lib.ST_FUSED]) == 1
+        if fused and int(status[_lib.ST_ERROR]) == 3:
             # the single-pass kernel speculates on the threshold branch; the count says top-k: redo generically
             self._links_for = None
-            self._ensure_links(st, q_len)
+            self._ensure_links(st, q_len, need_order=True)
             launch(0)
+            ran_fused = False
         err = int(status[_lib.ST_ERROR])
         if err == 1:
             raise ZeroDivisionError("division by zero")                      # frame_token_num == 0 (main.py:114)
@@ -348,8 +353,12 @@ class FrameFusion(nn.Module):
             self.finish_merging = True
             self.finish_pruning = True
 
+        self._have_order = not ran_fused
         if self.debug_trace:
-            self._record_merge_trace(st, hidden, q_len, int(status[_lib.ST_NCHAIN]), branch)
+            if ran_fused:
+                self._record_fused_trace(st, hidden, q_len)
+            else:
+                self._record_merge_trace(st, hidden, q_len, int(status[_lib.ST_NCHAIN]), branch)
 
         outs = self._narrow(auxes, s_keep)
         self.patch_type = outs[0].reshape(bsz, -1)
@@ -379,6 +388,30 @@ class FrameFusion(nn.Module):
             merge_index=np.nonzero(flags[:n_chain].cpu().numpy())[0],
             sim_values=sim[:n_chain].float().cpu().numpy(),
             order=order[:n_chain].cpu().numpy())
+
+    def _record_fused_trace(self, st, hidden, q_len):
+        """The fused kernel keeps similarities by sequence position and no by-patch order: rebuild the by-patch
+        view the parity harness compares (order from the static API on a separate workspace)."""
+        device = hidden.device
+        wp, wb = st.ws_ptr()
+        stream = _stream(device)
+        keep = torch.empty(q_len, dtype=torch.uint8, device=device)
+        sim_seq = torch.empty(q_len, dtype=hidden.dtype, device=device)
+        _lib.check(st.lib.ff_debug_read(st.ctx, wp, wb, 0, keep.data_ptr(), q_len, 0, stream))
+        _lib.check(st.lib.ff_debug_read(st.ctx, wp, wb, 2, sim_seq.data_ptr(), q_len, _dtype_code(hidden), stream))
+        pt = self.patch_type.reshape(-1)
+        _sim, order = FrameFusion.compute_similarity_and_token_index_by_patch(hidden, pt, self.patch_num)
+        order = order[0]
+        ids = pt[order]
+        head = torch.ones_like(ids, dtype=torch.bool)
+        if ids.numel() > 1:
+            head[1:] = ids[1:] != ids[:-1]
+        sim = sim_seq[order].float()
+        sim[head] = IGNORE_TOKEN
+        keep_np = keep.cpu().numpy().astype(bool)
+        order_np = order.cpu().numpy()
+        self.last_trace = dict(stage="merge", branch="threshold", keep_mask=keep_np,
+                               merge_index=np.nonzero(~keep_np[order_np])[0], sim_values=sim.cpu().numpy(), order=order_np)
 
     # ---------------------------------------------------------------------------------------------
     # static helpers with the reference's signatures (main.py:180-343)

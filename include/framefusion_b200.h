@@ -53,6 +53,7 @@ enum ff_status_slot {
     FF_ST_TOPK = 5,        /* k used by the branch that ran (merge top-k or prune top-k) */
     FF_ST_ERROR = 6,       /* device-side error: 0 ok, 1 n_vis == 0, 2 k > N, 3 fused path declined */
     FF_ST_NMERGED = 7,     /* tokens merged away by this call */
+    FF_ST_FUSED = 8,       /* 1 if the single-pass fused kernel produced this result, 0 for the generic path */
     FF_ST_SLOTS = 16
 };
 
