@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — vision tokens/s through FrameFusion's merge+prune path, and achieved HBM GB/s vs the roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C2|C3|C4]
+
+One STEP = the FrameFusion calls of one prefill on one synthetic batch (BASELINE.json config 2 by default:
+64 frames x 576 tokens x 3584 bf16, cost 0.3, similarity_lower_bound 0.6, ratio_lower_bound 0.1):
+``prepare`` -> merge-stage calls until ``finish_merging`` (call #0 merges ~39 % of the vision tokens, call #1
+finds nothing above the bound and closes merging) -> last-query importance from q / K -> the prune call.
+The same schedule is what the torch-CPU port of the reference runs in the ``cpu_baseline`` / ``--impl reference``
+legs (DESIGN.md "Measurement").
+
+Printed line (rank 0): the contract of the task statement — ``value`` is device-resident throughput (CUDA events,
+max over ranks), ``e2e`` the same step driven from pinned HOST buffers with the copies inside the timed region,
+``roofline`` the dominant kernel (the fused merge kernel of call #0) timed live with CUDA events on its stream,
+``cpu_baseline`` the reference's algorithm on this box's host cores.
+
+N > 1: the operator does not shard (SURVEY.md §8e — one request, batch 1, global top-k/count): every rank runs
+an independent replica on its own GPU (``scaling: weak``), no data-path collective.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from framefusion_b200 import synth  # noqa: E402
+
+METRIC = "vision tokens/sec through merge+prune at 64f x 576tok x 3584 bf16"
+UNIT = "vision_tokens/s"
+FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+N_HEADS, N_KV_HEADS, HEAD_DIM = 28, 4, 128
+
+
+def workload_name(cfg):
+    c = synth.CONFIGS[cfg]
+    return (f"{cfg}: {c['frames']} frames x {c['patch_num']} tokens x {c['hidden']} "
+            f"{str(c['dtype']).replace('torch.', '')}, cost={c['cost']}, similarity_lower_bound={c['slb']}, "
+            f"ratio_lower_bound={c['rlb']}; 14 text + F*P vision + 20 text tokens, AR(1) frames with r~U(0,1), seed 0")
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        for key in ("hbm_gbs", "hbm_copy_gbs", "hbm_gb_s"):
+            if key in d:
+                return float(d[key]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(int(f[0]))
+                mx = max(mx, int(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# one step, any implementation with the FrameFusion call contract
+# --------------------------------------------------------------------------------------------------
+def run_step(ff, wl, hidden, cos, sin, q_last, keys, importance_fn):
+    ff.prepare(wl.patch_type, wl.patch_num, wl.n_pre, wl.n_pre + wl.n_vision - 1, wl.n_vision, wl.seq_len)
+    pos = [cos, sin]
+    h = hidden
+    guard = 0
+    while not ff.finish_merging and guard < 8:
+        h, pos, _ = ff(h, pos, None)
+        guard += 1
+    if not ff.finish_pruning:
+        s_now = h.shape[1]
+        attn = importance_fn(q_last, keys[:, :, :s_now])
+        h, pos, _ = ff(h, pos, None, attn)
+    return h, pos
+
+
+def reference_arm(args, cfg, rank, world):
+    """The reference's algorithm on the host cores (torch-CPU port, all threads) — rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import ff_torch_port as port
+    c = synth.CONFIGS[cfg]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    frames = c["frames"]
+    wl = synth.make_workload(frames, c["patch_num"], c["hidden"], c["dtype"], seed=0)
+    q, k = synth.make_attention_inputs(wl.seq_len, N_HEADS, N_KV_HEADS, HEAD_DIM, c["dtype"], seed=0)
+    q_last = q[:, :, -1:, :].contiguous()
+
+    def step():
+        ff = port.TorchPortFrameFusion(c["cost"], c["slb"], c["rlb"])
+        # the operator merges in place (main.py:304-317): every repetition gets a fresh copy, outside nothing
+        h = wl.hidden.clone()
+        return run_step(ff, wl, h, wl.cos, wl.sin, q_last, k,
+                        lambda qq, kk: port.last_query_attention(qq, kk, num=1, is_causal=True))
+
+    t0 = time.perf_counter()
+    step()
+    est = time.perf_counter() - t0
+    steps, warm = args.steps, args.warmup
+    budget = 150.0
+    if est * (steps + warm) > budget:          # keep the whole arm within a few minutes
+        steps = max(3, int(budget / est) - warm)
+    for _ in range(max(warm - 1, 0)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = wl.n_vision * steps / dt
+    sample = f"{steps} full steps of the {cfg} workload ({wl.n_vision} vision tokens each), torch {torch.__version__} CPU"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_name(cfg), "host_threads": cores},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(cfg, seconds=12.0):
+    from oracle import ff_torch_port as port
+    c = synth.CONFIGS[cfg]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wl = synth.make_workload(c["frames"], c["patch_num"], c["hidden"], c["dtype"], seed=0)
+    q, k = synth.make_attention_inputs(wl.seq_len, N_HEADS, N_KV_HEADS, HEAD_DIM, c["dtype"], seed=0)
+    q_last = q[:, :, -1:, :].contiguous()
+
+    def step():
+        ff = port.TorchPortFrameFusion(c["cost"], c["slb"], c["rlb"])
+        return run_step(ff, wl, wl.hidden.clone(), wl.cos, wl.sin, q_last, k,
+                        lambda qq, kk: port.last_query_attention(qq, kk, num=1, is_causal=True))
+
+    step()
+    n, t0 = 0, time.perf_counter()
+    while n < 3 or (time.perf_counter() - t0 < seconds and n < 50):
+        step()
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": wl.n_vision * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} full steps of the {cfg} workload on torch {torch.__version__} CPU, {dt:.1f} s"}
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(synth.CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = args.workload
+    if args.impl == "reference":
+        reference_arm(args, cfg, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    warm = max(args.warmup, 3)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from framefusion_b200 import _lib
+    from framefusion_b200.main import FrameFusion
+    from framefusion_b200.utils import scaled_dot_product_attention
+    lib = _lib.load()
+    c = synth.CONFIGS[cfg]
+    wl_host = synth.make_workload(c["frames"], c["patch_num"], c["hidden"], c["dtype"], seed=0)
+    q, k = synth.make_attention_inputs(wl_host.seq_len, N_HEADS, N_KV_HEADS, HEAD_DIM, c["dtype"], seed=0)
+    host = {"hidden": wl_host.hidden, "cos": wl_host.cos, "sin": wl_host.sin, "patch_type": wl_host.patch_type,
+            "q_last": q[:, :, -1:, :].contiguous(), "keys": k}
+    host = {n: t.pin_memory() for n, t in host.items()}
+    devt = {n: t.to(dev) for n, t in host.items()}
+    wl = synth.to_device(wl_host, dev)
+    wl.patch_type = devt["patch_type"]
+
+    ff = FrameFusion(c["cost"], c["slb"], c["rlb"])
+    imp = lambda qq, kk: scaled_dot_product_attention(qq, kk, None, num=1, is_causal=True, enable_gqa=True)
+
+    def step_resident():
+        return run_step(ff, wl, devt["hidden"], devt["cos"], devt["sin"], devt["q_last"], devt["keys"], imp)
+
+    out_host = {}
+
+    def step_e2e():
+        for n in host:
+            devt[n].copy_(host[n], non_blocking=True)
+        wl.patch_type = devt["patch_type"]
+        h, pos = step_resident()
+        pt = ff.patch_type
+        for n, t in (("hidden", h), ("patch_type", pt)):
+            buf = out_host.get(n)
+            if buf is None or buf.shape != t.shape:
+                buf = out_host[n] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            buf.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return h
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(warm):
+        step_resident()
+    ff.kernel_events = []
+    launches0 = lib.ff_launch_count()
+    with ClockSampler(local) as clk:
+        ms = timed(step_resident, args.steps)
+    launches = lib.ff_launch_count() - launches0
+    events, ff.kernel_events = ff.kernel_events, None
+    h_final, _ = step_resident()
+
+    # dominant kernel: the merge-stage launch of call #0 (the one that sees the full sequence)
+    full = [e0.elapsed_time(e1) for (_n, s, e0, e1) in events if s == wl.seq_len]
+    k_ms = sum(full) / max(len(full), 1)
+    s_keep0 = None
+    ff.prepare(*wl.prepare_args())
+    h1, _p, _m = ff(devt["hidden"], [devt["cos"], devt["sin"]], None)
+    s_keep0 = h1.shape[1]
+    fused = int(ff._state(dev).status[_lib.ST_FUSED])
+    alg = synth.algorithmic_bytes(wl.seq_len, s_keep0, c["hidden"], devt["hidden"].element_size())
+    peak, peak_src = hbm_peak()
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(cfg, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    achieved = alg / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, e2e_steps)
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
+    d2h = sum(t.numel() * t.element_size() for t in out_host.values())
+
+    n_tok = wl.n_vision
+    line = {
+        "metric": METRIC, "value": world * n_tok * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_name(cfg), "seq_len": wl.seq_len, "kept_after_merge": s_keep0,
+                   "kept_after_prune": int(h_final.shape[1]), "l2": "inputs (264 MB at C2) exceed the 126 MB L2; no explicit flush",
+                   "parallelism": "replicas" if world > 1 else "single-gpu",
+                   "calls_per_step": "merge, merge (closes merging), importance, prune"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "ff_merge_layer (k_fused_merge)" if fused else "ff_merge_layer (generic)",
+                     "kernel_us": k_ms * 1e3, "algorithmic_bytes": alg, "peak_source": peak_src,
+                     "frac_of_nominal_8TBs": achieved / 8000.0},
+        "e2e": {"value": world * n_tok * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(cfg)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -21,7 +21,7 @@ ST_SEQ_KEEP, ST_COUNT, ST_NVIS, ST_NCHAIN, ST_BRANCH, ST_TOPK, ST_ERROR, ST_NMER
 ST_SLOTS = 16
 
 EXPORTS = [
-    "ff_abi_version", "ff_last_error", "ff_ctx_create", "ff_ctx_destroy", "ff_ctx_status", "ff_workspace_bytes",
+    "ff_abi_version", "ff_last_error", "ff_launch_count", "ff_ctx_create", "ff_ctx_destroy", "ff_ctx_status", "ff_workspace_bytes",
     "ff_build_links", "ff_similarity", "ff_merge_apply", "ff_merge_layer", "ff_importance", "ff_prune_layer",
     "ff_compact_mask", "ff_debug_read",
 ]
@@ -54,6 +54,7 @@ def load():
     lib = C.CDLL(path)
     lib.ff_abi_version.restype = C.c_int
     lib.ff_last_error.restype = C.c_char_p
+    lib.ff_launch_count.restype = _i64
     lib.ff_ctx_create.argtypes = [C.c_int, C.POINTER(_vp)]
     lib.ff_ctx_destroy.argtypes = [_vp]
     lib.ff_ctx_status.argtypes = [_vp]
@@ -73,7 +74,7 @@ def load():
     lib.ff_debug_read.argtypes = [_vp, _vp, _i64, C.c_int, _vp, _i64, C.c_int, _vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("ff_last_error", "ff_ctx_status", "ff_workspace_bytes"):
+        if name not in ("ff_last_error", "ff_launch_count", "ff_ctx_status", "ff_workspace_bytes"):
             fn.restype = C.c_int
     if lib.ff_abi_version() != 1:
         raise FFError(f"ABI version {lib.ff_abi_version()} != 1")

@@ -1,5 +1,6 @@
 // C ABI of libframefusion_b200.so — see include/framefusion_b200.h for the contract of every entry point.
 // Host side only: argument checks, workspace carving, kernel launches on the caller's stream.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -16,6 +17,7 @@
 using namespace ff;
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};      // kernels this library has launched (ff_launch_count)
 
 static int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -33,6 +35,7 @@ static int fail(int code, const char* fmt, ...) {
 
 #define FF_LAUNCH_CHECK(name)                                                                      \
     do {                                                                                           \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                        \
         cudaError_t e_ = cudaGetLastError();                                                       \
         if (e_ != cudaSuccess) return fail(FF_E_CUDA, "launch %s: %s", name, cudaGetErrorString(e_)); \
     } while (0)
@@ -262,6 +265,8 @@ int ff_abi_version(void) { return FF_ABI_VERSION; }
 
 const char* ff_last_error(void) { return g_err; }
 
+int64_t ff_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+
 int ff_ctx_create(int device, ff_ctx** out) {
     if (!out) return fail(FF_E_BADARG, "out is null");
     *out = nullptr;
@@ -440,6 +445,7 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
         fa.aux = ap;
         int rc = launch_fused(ctx->sm_count, dtype, S, H, thr, fa, st);
         if (rc == FF_OK) {
+            g_launches.fetch_add(1, std::memory_order_relaxed);
             ctx->epoch = epoch;
             ctx->last_parity = bank;
             ctx->parity = nb;

@@ -110,6 +110,7 @@ class FrameFusion(nn.Module):
         self.use_fused = True           # allow the single-pass kernel (threshold branch)
         self.debug_trace = False        # tests: keep what flowed between the stages of the last call
         self.last_trace = None
+        self.kernel_events = None       # bench: a list collects (name, start, end) CUDA events around ff_* launches
 
     # ---------------------------------------------------------------------------------------------
     def prepare(
@@ -323,8 +324,15 @@ class FrameFusion(nn.Module):
         code = _dtype_code(hidden)
 
         def launch(flags):
+            ev = self.kernel_events
+            if ev is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             _lib.check(st.lib.ff_merge_layer(st.ctx, wp, wb, hidden.data_ptr(), out.data_ptr(), code, q_len, hidden_size,
                                              thr, float(sparsity_upper_bound), packed, len(auxes), flags, stream))
+            if ev is not None:
+                e1.record()
+                ev.append(("ff_merge_layer", q_len, e0, e1))
             torch.cuda.current_stream(device).synchronize()
 
         launch(fused)

@@ -75,6 +75,8 @@ typedef struct ff_aux {
 
 int ff_abi_version(void);
 const char* ff_last_error(void);
+/* number of kernels this library has launched since it was loaded (process-wide; bench.py's gpu_launches) */
+int64_t ff_launch_count(void);
 
 /* ---- context -------------------------------------------------------------------------------- */
 int ff_ctx_create(int device, ff_ctx** out);
