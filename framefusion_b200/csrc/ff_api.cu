@@ -7,12 +7,12 @@
 #include <new>
 
 #include "ff_common.cuh"
-#include "ff_fused.cuh"
 #include "ff_importance.cuh"
 #include "ff_links.cuh"
 #include "ff_merge.cuh"
 #include "ff_select.cuh"
 #include "ff_similarity.cuh"
+#include "ff_stream.cuh"
 
 using namespace ff;
 
@@ -49,11 +49,11 @@ struct ff_ctx {
     int64_t links_S;     // sequence length the links describe (-1: none, -2: S_keep of the last merge call)
     int64_t cap;         // capacity the workspace is carved for (set by ff_build_links)
     int64_t n_ids;
-    int have_order;      // by-patch order / rank arrays valid for `parity`
-    int have_link;       // successor links valid for `parity`
-    int link_mapped;     // link[parity] holds indices of the previous call: translate through dst[parity ^ 1]
-    unsigned epoch;      // fused calls since ff_build_links (tags the flag bytes and look-back descriptors)
+    int have_order;      // compact by-patch order / chain / rank arrays valid for `parity` (generic path)
+    int have_lists;      // per-chain lists (order at base[id], len[parity][id]) valid for `parity` (single-pass path)
+    unsigned epoch;      // single-pass calls since ff_build_links (tags the flag bytes)
     int sm_count;
+    int max_smem;        // opt-in dynamic shared memory per block
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -66,17 +66,14 @@ struct Ws {
     int* order[2];
     int* chain[2];
     int* rank[2];
-    int* link[2];
+    int* len[2];        // [n_ids + 1] rows per chain; bucket n_ids = rows outside the chains
     float* sim;
     uint8_t* flag;
     uint8_t* state;
     int* dst[2];
     int* srcidx;
     int* hist;
-    int* total;
-    int* base;
-    unsigned long long* tiles;
-    size_t n_tiles_cap;
+    int* base;          // [n_ids + 1] start of every chain list inside order[]
     size_t bytes;
 };
 
@@ -94,7 +91,7 @@ Ws carve(void* base_ptr, int64_t cap, int64_t n_ids) {
         w.order[b] = (int*)take(cap * 4);
         w.chain[b] = (int*)take(cap * 4);
         w.rank[b] = (int*)take(cap * 4);
-        w.link[b] = (int*)take(cap * 4);
+        w.len[b] = (int*)take((size_t)(n_ids + 1) * 4);
     }
     w.sim = (float*)take(cap * 4);
     w.flag = (uint8_t*)take(cap);
@@ -102,11 +99,8 @@ Ws carve(void* base_ptr, int64_t cap, int64_t n_ids) {
     w.dst[0] = (int*)take(cap * 4);
     w.dst[1] = (int*)take(cap * 4);
     w.srcidx = (int*)take(cap * 4);
-    w.hist = (int*)take((size_t)n_chunks * (size_t)(n_ids > 0 ? n_ids : 1) * 4);
-    w.total = (int*)take((size_t)(n_ids > 0 ? n_ids : 1) * 4);
-    w.base = (int*)take((size_t)(n_ids > 0 ? n_ids : 1) * 4);
-    w.n_tiles_cap = (size_t)(cap / FUSED_MIN_ROWS + 2);
-    w.tiles = (unsigned long long*)take(w.n_tiles_cap * 8);
+    w.hist = (int*)take((size_t)n_chunks * (size_t)(n_ids + 1) * 4);
+    w.base = (int*)take((size_t)(n_ids + 1) * 4);
     w.bytes = off;
     return w;
 }
@@ -256,6 +250,71 @@ int check_shape(int64_t S, int64_t H, int dtype) {
     return FF_OK;
 }
 
+// Fills the launch arguments of the single-pass kernel; false when the shape is outside what it handles.
+bool plan_stream_args(const ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* out, int dtype, int64_t S,
+                      int64_t H, double thr, double bound, const AuxPack& ap, StreamArgs* sa, StreamPlan* plan) {
+    const int64_t eb = dtype == FF_F32 ? 4 : 2;
+    const int64_t row_bytes = H * eb;
+    if (row_bytes % 16 != 0 || (((uintptr_t)hidden | (uintptr_t)out) & 15) != 0) return false;
+    const int64_t nvec = row_bytes / 16;
+    if (nvec > (int64_t)ST_NT * ST_MAX_VPT) return false;
+    if (!(thr > -2.0)) return false;                       // chain heads (sim = -2) must never be flagged
+    if (ctx->n_ids < 1) return false;
+    StreamArgs& a = *sa;
+    a.n_tma_aux = a.n_small_aux = 0;
+    int off = (int)row_bytes;
+    for (int q = 0; q < ap.n; ++q) {
+        const ff_aux& x = ap.a[q];
+        const uintptr_t al = (uintptr_t)x.src | (uintptr_t)x.dst | (uintptr_t)x.src_plane_stride | (uintptr_t)x.dst_plane_stride;
+        if (x.row_bytes % 16 == 0 && (al & 15) == 0 && x.row_bytes <= 4096) {
+            for (int64_t pl = 0; pl < x.planes; ++pl) {
+                if (a.n_tma_aux == ST_MAX_TMA_AUX) return false;
+                StreamAux& t = a.tma_aux[a.n_tma_aux++];
+                t.src = (const char*)x.src + pl * x.src_plane_stride;
+                t.dst = (char*)x.dst + pl * x.dst_plane_stride;
+                t.bytes = (int)x.row_bytes;
+                t.slot_off = off;
+                off += (int)x.row_bytes;
+            }
+        } else if (x.row_bytes == 8 && x.planes == 1 && (al & 7) == 0) {
+            if (a.n_small_aux == ST_MAX_SMALL_AUX) return false;
+            StreamAux& t = a.small_aux[a.n_small_aux++];
+            t.src = (const char*)x.src;
+            t.dst = (char*)x.dst;
+            t.bytes = 8;
+            t.slot_off = 0;
+        } else {
+            return false;
+        }
+    }
+    if (!plan_stream(ctx->sm_count, ctx->max_smem, row_bytes, (int)ctx->n_ids, off - (int)row_bytes, plan)) return false;
+    const int nb = bank ^ 1;
+    a.hidden = (const char*)hidden;
+    a.out = (char*)out;
+    a.S = (int)S;
+    a.nvec = (int)nvec;
+    a.row_bytes = (int)row_bytes;
+    a.slot_bytes = plan->slot_bytes;
+    a.n_slots = plan->n_slots;
+    a.n_ids = (int)ctx->n_ids;
+    a.cpc = plan->cpc;
+    a.order = w.order[bank];
+    a.base = w.base;
+    a.len = w.len[bank];
+    a.order_next = w.order[nb];
+    a.len_next = w.len[nb];
+    a.state = w.state;
+    a.sim_seq = w.sim;
+    a.dst = w.dst[bank];
+    a.counters = w.counters[bank];
+    a.counters_next = w.counters[nb];
+    a.status = ctx->d_status;
+    a.thr = (float)thr;
+    a.bound = bound;
+    a.tag = 1;
+    return true;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -279,8 +338,7 @@ int ff_ctx_create(int device, ff_ctx** out) {
     c->links_S = -1;
     c->cap = 0;
     c->n_ids = 0;
-    c->have_order = c->have_link = 0;
-    c->link_mapped = 0;
+    c->have_order = c->have_lists = 0;
     c->epoch = 0;
     cudaError_t e = cudaHostAlloc((void**)&c->h_status, FF_ST_SLOTS * 8, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e != cudaSuccess) { delete c; return fail(FF_E_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
@@ -289,6 +347,8 @@ int ff_ctx_create(int device, ff_ctx** out) {
     if (e != cudaSuccess) { cudaFreeHost(c->h_status); delete c; return fail(FF_E_CUDA, "cudaHostGetDevicePointer: %s", cudaGetErrorString(e)); }
     e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) c->sm_count = 148;
+    e = cudaDeviceGetAttribute(&c->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (e != cudaSuccess) c->max_smem = 48 * 1024;
     *out = c;
     return FF_OK;
 }
@@ -320,37 +380,27 @@ int ff_build_links(ff_ctx* ctx, void* ws, int64_t ws_bytes, const int64_t* patch
     cudaStream_t st = (cudaStream_t)stream;
     FF_CUDA(cudaSetDevice(ctx->device));
     const int n_chunks = (int)((S + LINK_CHUNK - 1) / LINK_CHUNK);
+    const int n_b = (int)n_ids + 1;                        // chain buckets + the bucket of rows outside the chains
     FF_CUDA(cudaMemsetAsync(w.counters[0], 0, 2 * align_up(C_SLOTS * 8), st));
+    FF_CUDA(cudaMemsetAsync(w.len[0], 0, (size_t)n_b * 4, st));
+    ctx->epoch = 0;
     if (S > 0) {
         FF_CUDA(cudaMemsetAsync(w.state, 0, (size_t)S, st));
-        FF_CUDA(cudaMemsetAsync(w.tiles, 0, w.n_tiles_cap * 8, st));
-    }
-    ctx->epoch = 0;
-    ctx->link_mapped = 0;
-    if (S > 0 && n_ids > 0) {
-        FF_CUDA(cudaMemsetAsync(w.hist, 0, (size_t)n_chunks * n_ids * 4, st));
+        FF_CUDA(cudaMemsetAsync(w.hist, 0, (size_t)n_chunks * n_b * 4, st));
         k_links_hist<<<n_chunks, LINK_CHUNK, 0, st>>>(patch_type, (int)S, (int)n_ids, w.hist, w.counters[0]);
         FF_LAUNCH_CHECK("k_links_hist");
-        k_links_colscan<<<(int)((n_ids + 7) / 8), 256, 0, st>>>(w.hist, n_chunks, (int)n_ids, w.total, w.base, w.counters[0]);
+        k_links_colscan<<<(n_b + 7) / 8, 256, 0, st>>>(w.hist, n_chunks, n_b, w.len[0], w.base, w.counters[0]);
         FF_LAUNCH_CHECK("k_links_colscan");
         k_links_scatter<<<n_chunks, LINK_CHUNK, 0, st>>>(patch_type, (int)S, (int)n_ids, w.hist, w.base, w.order[0],
                                                         w.chain[0], w.rank[0]);
         FF_LAUNCH_CHECK("k_links_scatter");
-        k_links_derive<<<(int)((S + 255) / 256), 256, 0, st>>>((int)S, nullptr, w.order[0], w.chain[0], w.rank[0], w.counters[0], w.link[0]);
-        FF_LAUNCH_CHECK("k_links_derive");
-    } else if (S > 0) {
-        // no patch ids: count vision tokens only, every rank is -1
-        k_links_hist<<<n_chunks, LINK_CHUNK, 0, st>>>(patch_type, (int)S, 0, w.hist, w.counters[0]);
-        FF_LAUNCH_CHECK("k_links_hist");
-        FF_CUDA(cudaMemsetAsync(w.rank[0], 0xff, (size_t)S * 4, st));
-        FF_CUDA(cudaMemsetAsync(w.link[0], 0xff, (size_t)S * 4, st));
     }
     k_links_status<<<1, 1, 0, st>>>(w.counters[0], ctx->d_status);
     FF_LAUNCH_CHECK("k_links_status");
     ctx->parity = 0;
     ctx->last_parity = 0;
     ctx->links_S = S;
-    ctx->have_order = ctx->have_link = 1;
+    ctx->have_order = ctx->have_lists = 1;
     return FF_OK;
 }
 
@@ -385,8 +435,8 @@ int ff_merge_apply(ff_ctx* ctx, void* ws, int64_t ws_bytes, void* hidden, int dt
     if (N < 0 || M < 0 || N > S) return fail(FF_E_BADARG, "bad N / M");
     if (!ctx) return fail(FF_E_BADARG, "null ctx");
     if (ctx->cap < S) { ctx->cap = S; ctx->n_ids = 0; }
-    ctx->links_S = -1;                                     // scratch use of the link arrays
-    ctx->have_order = ctx->have_link = 0;
+    ctx->links_S = -1;                                     // scratch use of the order arrays
+    ctx->have_order = ctx->have_lists = 0;
     if (int rc = check_ws(ctx, ws, ws_bytes, S, &w)) return rc;
     if (!keep_mask_out && S > 0) return fail(FF_E_BADARG, "keep_mask_out is null");
     cudaStream_t st = (cudaStream_t)stream;
@@ -424,38 +474,24 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     FF_CUDA(cudaSetDevice(ctx->device));
     const int bank = ctx->parity, nb = bank ^ 1;
 
-    if ((flags & 1) && S > 0 && ctx->have_link) {
-        FusedArgs fa;
-        fa.hidden = (const char*)hidden;
-        fa.out = (char*)hidden_out;
-        fa.link = w.link[bank];
-        fa.map = ctx->link_mapped ? w.dst[nb] : nullptr;
-        fa.link_next = w.link[nb];
-        fa.state = w.state;
-        fa.sim_seq = w.sim;
-        fa.dst = w.dst[bank];
-        fa.tiles = w.tiles;
-        fa.counters = w.counters[bank];
-        fa.counters_next = w.counters[nb];
-        fa.status = ctx->d_status;
-        fa.bound = bound;
-        const unsigned epoch = ctx->epoch + 1;
-        fa.tag = (epoch - 1) % 127 + 1;
-        fa.epoch = (unsigned long long)((epoch - 1) % 65535 + 1);
-        fa.aux = ap;
-        int rc = launch_fused(ctx->sm_count, dtype, S, H, thr, fa, st);
-        if (rc == FF_OK) {
+    if ((flags & 1) && S > 0 && ctx->have_lists) {
+        StreamArgs sa;
+        StreamPlan plan;
+        if (plan_stream_args(ctx, w, bank, hidden, hidden_out, dtype, S, H, thr, bound, ap, &sa, &plan)) {
+            const unsigned epoch = ctx->epoch + 1;
+            sa.tag = (epoch - 1) % 127 + 1;
+            if (epoch > 1 && sa.tag == 1) FF_CUDA(cudaMemsetAsync(w.state, 0, (size_t)ctx->cap, st));   // tags wrap
+            int rc = launch_stream(dtype, sa, plan, st);
+            if (rc != FF_OK) return fail(rc, "single-pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             g_launches.fetch_add(1, std::memory_order_relaxed);
             ctx->epoch = epoch;
             ctx->last_parity = bank;
             ctx->parity = nb;
             ctx->links_S = -2;
             ctx->have_order = 0;
-            ctx->have_link = 1;
-            ctx->link_mapped = 1;
+            ctx->have_lists = 1;
             return FF_OK;
         }
-        if (rc != FF_E_UNSUPPORTED) return fail(rc, "fused launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     if (!ctx->have_order) return fail(FF_E_BADARG, "by-patch order not in the workspace (the fused path does not keep it): call ff_build_links");
 
@@ -485,15 +521,11 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
         k_aux_compact<<<(int)((S + 7) / 8), 256, 0, st>>>(ap, (int)S, w.dst[bank]);
         FF_LAUNCH_CHECK("k_aux_compact");
     }
-    if (S > 0) {
-        k_links_derive<<<(int)((S + 255) / 256), 256, 0, st>>>((int)S, &w.counters[bank][C_SKEEP], w.order[nb], w.chain[nb], w.rank[nb], w.counters[nb], w.link[nb]);
-        FF_LAUNCH_CHECK("k_links_derive");
-    }
     ctx->last_parity = bank;
     ctx->parity = nb;
     ctx->links_S = -2;                                     // = S_keep, known once the host has synchronised
-    ctx->have_order = ctx->have_link = 1;
-    ctx->link_mapped = 0;
+    ctx->have_order = 1;
+    ctx->have_lists = 0;                                   // the generic path keeps the compact arrays only
     return FF_OK;
 }
 
@@ -538,7 +570,7 @@ int ff_prune_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* attn, in
     AuxPack ap;
     if (int rc = check_shape(S, H, dtype)) return rc;
     if (!ctx) return fail(FF_E_BADARG, "null ctx");
-    if (ctx->cap < S) { ctx->cap = S; ctx->n_ids = 0; ctx->links_S = -1; ctx->have_order = ctx->have_link = 0; }
+    if (ctx->cap < S) { ctx->cap = S; ctx->n_ids = 0; ctx->links_S = -1; ctx->have_order = ctx->have_lists = 0; }
     if (int rc = check_ws(ctx, ws, ws_bytes, S, &w)) return rc;
     if (int rc = pack_aux(aux, n_aux, &ap)) return rc;
     if (!attn || !hidden || !hidden_out || n_rows < 1 || S < 1) return fail(FF_E_BADARG, "null / empty argument");

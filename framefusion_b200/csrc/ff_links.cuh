@@ -24,7 +24,10 @@ k_links_hist(const int64_t* __restrict__ pt, int S, int n_ids, int* __restrict__
     if (i < S) {
         const int64_t id = pt[i];
         vis = (id != -1);
-        if (id >= 0 && id < n_ids) atomicAdd(&hist[(int64_t)blockIdx.x * n_ids + (int)id], 1);
+        // bucket n_ids collects every row outside the chains (text, ids >= n_ids): the single-pass kernel walks it
+        // like a chain that never merges
+        const int b = (id >= 0 && id < n_ids) ? (int)id : n_ids;
+        atomicAdd(&hist[(int64_t)blockIdx.x * (n_ids + 1) + b], 1);
     }
     vis = warp_sum_int(vis);
     if ((threadIdx.x & 31) == 0) s_nv[threadIdx.x >> 5] = vis;
@@ -36,11 +39,13 @@ k_links_hist(const int64_t* __restrict__ pt, int S, int n_ids, int* __restrict__
     }
 }
 
-// one warp per patch id: exclusive scan of hist[:, id] over chunks; totals -> total[id];
-// the last block scans total[] into base[] and writes N.
+// one warp per bucket (patch ids, then the non-chain bucket): exclusive scan of hist[:, id] over chunks;
+// totals -> total[id]; the last block scans total[] into base[] and writes N (chain tokens only).
+// n_b = n_ids + 1 buckets.
 __global__ void __launch_bounds__(256)
-k_links_colscan(int* __restrict__ hist, int n_chunks, int n_ids, int* __restrict__ total, int* __restrict__ base,
+k_links_colscan(int* __restrict__ hist, int n_chunks, int n_b, int* __restrict__ total, int* __restrict__ base,
                 int64_t* counters) {
+    const int n_ids = n_b;                                 // (name kept below: columns of hist)
     __shared__ int s_scan[33];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31;
@@ -80,7 +85,7 @@ k_links_colscan(int* __restrict__ hist, int n_chunks, int n_ids, int* __restrict
         carry += tot;
     }
     if (threadIdx.x == 0) {
-        counters[C_N] = carry;
+        counters[C_N] = carry - __ldcg(&total[n_b - 1]);   // the last bucket is not a chain
         counters[C_TICKET] = 0;
     }
 }
@@ -95,12 +100,11 @@ k_links_scatter(const int64_t* __restrict__ pt, int S, int n_ids, const int* __r
     int key = -1;
     if (i < S) {
         const int64_t id = pt[i];
-        if (id >= 0 && id < n_ids) key = (int)id;
+        key = (id >= 0 && id < n_ids) ? (int)id : n_ids;
     }
     s_key[t] = key;
     __syncthreads();
     if (i >= S) return;
-    if (key < 0) { rank[i] = -1; return; }
     // stable rank inside the chunk: earlier tokens of the chunk with the same id (brute force, <= 511 compares)
     int local = 0;
     const int4* k4 = reinterpret_cast<const int4*>(s_key);
@@ -110,33 +114,10 @@ k_links_scatter(const int64_t* __restrict__ pt, int S, int n_ids, const int* __r
         local += (v.x == key) + (v.y == key) + (v.z == key) + (v.w == key);
     }
     for (int u = full * 4; u < t; ++u) local += (s_key[u] == key);
-    const int pos = base[key] + hist[(int64_t)blockIdx.x * n_ids + key] + local;
+    const int pos = base[key] + hist[(int64_t)blockIdx.x * (n_ids + 1) + key] + local;
     order[pos] = i;
     chain[pos] = key;
-    rank[i] = pos;
-}
-
-// successor links for the single-pass kernel: link[i] = (has_pred << 31) | succ, succ = LINK_NONE when the
-// chain ends at i.  Text tokens: LINK_NONE, no predecessor.
-constexpr uint32_t LINK_NONE = 0x7fffffffu;
-constexpr uint32_t LINK_HASPRED = 0x80000000u;
-
-// `len_dev`, when not null, holds the sequence length on the device (S_keep of the call that made these links).
-__global__ void k_links_derive(int S, const int64_t* __restrict__ len_dev, const int* __restrict__ order,
-                               const int* __restrict__ chain, const int* __restrict__ rank,
-                               const int64_t* __restrict__ counters, int* __restrict__ link) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (len_dev) S = (int)*len_dev;
-    if (i >= S) return;
-    const int N = (int)counters[C_N];
-    const int j = rank[i];
-    uint32_t l = LINK_NONE;
-    if (j >= 0) {
-        const int c = chain[j];
-        if (j + 1 < N && chain[j + 1] == c) l = (uint32_t)order[j + 1];
-        if (j > 0 && chain[j - 1] == c) l |= LINK_HASPRED;
-    }
-    link[i] = (int)l;
+    rank[i] = key < n_ids ? pos : -1;                      // by-patch position, chain rows only
 }
 
 }  // namespace ff

@@ -106,7 +106,8 @@ class FrameFusion(nn.Module):
         self.ratio_lower_bound = ratio_lower_bound
         self._dev = {}                  # torch.device -> _DeviceState
         self._links_for = None          # (patch_type tensor, its _version, device) the workspace links describe
-        self._have_order = False        # the workspace also holds the by-patch order (the fused kernel drops it)
+        self._have_order = False        # the workspace holds the compact by-patch order (the generic kernels need it)
+        self._have_lists = False        # ... and the per-chain lists (the single-pass kernel needs them)
         self.use_fused = True           # allow the single-pass kernel (threshold branch)
         self.debug_trace = False        # tests: keep what flowed between the stages of the last call
         self.last_trace = None
@@ -154,11 +155,11 @@ class FrameFusion(nn.Module):
             patch_num = patch_num.item()
         return int(math.ceil(float(patch_num)))
 
-    def _ensure_links(self, st: _DeviceState, q_len: int, need_order: bool = False):
+    def _ensure_links(self, st: _DeviceState, q_len: int, need_order: bool = False, need_lists: bool = False):
         pt = self.patch_type
         key = self._links_for
         if key is not None and key[0] is pt and key[1] == pt._version and key[2] == st.device \
-                and (self._have_order or not need_order):
+                and (self._have_order or not need_order) and (self._have_lists or not need_lists):
             return
         if pt.numel() != q_len:
             raise RuntimeError(f"patch_type has {pt.numel()} entries for a sequence of {q_len} tokens")
@@ -169,6 +170,7 @@ class FrameFusion(nn.Module):
         _lib.check(st.lib.ff_build_links(st.ctx, wp, wb, ptc.data_ptr(), q_len, n_ids, _stream(st.device)))
         self._links_for = (pt, pt._version, st.device)
         self._have_order = True
+        self._have_lists = True
 
     def _pos_aux(self, position_embeddings, auxes):
         """Registers the position container's tensors for compaction; returns a closure that rebuilds it."""
@@ -310,7 +312,7 @@ class FrameFusion(nn.Module):
         self.patch_type = self.patch_type.to(device)
         sparsity_upper_bound = self._compute_pruning_ratio(self.sparsity_list, self.cost)
         fused = 1 if self.use_fused else 0
-        self._ensure_links(st, q_len, need_order=not fused)
+        self._ensure_links(st, q_len, need_order=not fused, need_lists=bool(fused))
 
         dt = hidden_states.dtype
         thr = torch.tensor(self.similarity_lower_bound, dtype=dt).item()     # the scalar is compared in T
@@ -362,6 +364,7 @@ class FrameFusion(nn.Module):
             self.finish_pruning = True
 
         self._have_order = not ran_fused
+        self._have_lists = ran_fused
         if self.debug_trace:
             if ran_fused:
                 self._record_fused_trace(st, hidden, q_len)
