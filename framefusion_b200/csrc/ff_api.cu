@@ -298,6 +298,7 @@ bool plan_stream_args(const ff_ctx* ctx, const Ws& w, int bank, const void* hidd
     a.n_slots = plan->n_slots;
     a.n_ids = (int)ctx->n_ids;
     a.cpc = plan->cpc;
+    a.lag = plan->lag;
     a.order = w.order[bank];
     a.base = w.base;
     a.len = w.len[bank];

@@ -65,6 +65,7 @@ struct StreamArgs {
     int n_slots;                                   // per team
     int n_ids;                                     // chain buckets; bucket n_ids = rows outside the chains
     int cpc;                                       // chains per CTA
+    int lag;                                       // iterations between a row's arrival and the scan that positions it
     const int* order;                              // chain lists: order[base[id] + t] = sequence index
     const int* base;
     const int* len;
@@ -94,34 +95,74 @@ __device__ __forceinline__ uint4 add_round(const uint4& a, const uint4& b) {    
     return Num<DT>::pack(x);
 }
 
+// T(x / div) elementwise, div = T(L + 1) (main.py:314-317: one true division, rounded to T).
+// bf16 fast path: a power-of-two divisor is an exact scaling; otherwise q0 = x * RN(1/div) is within 2 float32 ulp
+// of the correctly rounded quotient, so both round to the same bf16 unless q0 sits within a few ulp of a bf16
+// rounding boundary (low 16 bits ~ 0x8000) — those elements (about 1e-4 of them) take the IEEE division.
 template <int DT>
-__device__ __forceinline__ uint4 div_round(const uint4& a, float div) {           // T(a / div)
-    float x[Num<DT>::EPV];
-    Num<DT>::unpack(a, x);
+struct Divider {
+    float div, rcp;
+    bool pow2;
+    __device__ __forceinline__ explicit Divider(int n) {
+        div = Num<DT>::rnd((float)n);
+        rcp = 1.0f / div;
+        pow2 = (n & (n - 1)) == 0;
+    }
+    __device__ __forceinline__ float one(float x) const {
+        if (DT != FF_BF16) return x / div;
+        const float q0 = x * rcp;
+        if (pow2) return q0;
+        const uint32_t u = __float_as_uint(q0);
+        const bool risky = ((u & 0xffffu) - 0x7ff8u) <= 0x10u || ((u & 0x7f800000u) == 0u && (u << 1) != 0u);
+        return risky ? x / div : q0;
+    }
+    __device__ __forceinline__ uint4 vec(const uint4& a) const {
+        float x[Num<DT>::EPV];
+        Num<DT>::unpack(a, x);
 #pragma unroll
-    for (int e = 0; e < Num<DT>::EPV; ++e) x[e] = x[e] / div;
-    return Num<DT>::pack(x);
-}
+        for (int e = 0; e < Num<DT>::EPV; ++e) x[e] = one(x[e]);
+        return Num<DT>::pack(x);
+    }
+};
 
-// dot += T(a*b), nb += b*b for one 16-byte vector pair (the norm of `a` is carried over from the previous row)
+// Row sums for one 16-byte vector pair: dot += T(a*b), nb += b*b (the norm of `a` is carried over from the previous
+// row).  Two interleaved float32 accumulators per sum (even / odd elements), folded by the caller.
+// bf16: the product tensor element T(a*b) is one mul.rn.bf16x2 (exact product, one rounding — what the reference's
+// bf16 multiply does), sums run on the packed float32x2 pipe of sm_100.
 template <int DT>
-__device__ __forceinline__ void acc_dot_norm(const uint4& va, const uint4& vb, float& dot, float& nb) {
-    float a[Num<DT>::EPV], b[Num<DT>::EPV];
-    Num<DT>::unpack(va, a);
-    Num<DT>::unpack(vb, b);
+__device__ __forceinline__ void acc_dot_norm(const uint4& va, const uint4& vb, float2& dot, float2& nb) {
+    if (DT == FF_BF16) {
+        const uint32_t aw[4] = {va.x, va.y, va.z, va.w}, bw[4] = {vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
-    for (int e = 0; e < Num<DT>::EPV; ++e) {
-        if (DT == FF_F32) dot += __fmul_rn(a[e], b[e]); else dot += Num<DT>::rnd(a[e] * b[e]);
-        nb = fmaf(b[e], b[e], nb);
+        for (int q = 0; q < 4; ++q) {
+            __nv_bfloat162 pa = *reinterpret_cast<const __nv_bfloat162*>(&aw[q]);
+            __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&bw[q]);
+            __nv_bfloat162 pp = __hmul2(pa, pb);
+            const uint32_t pw = *reinterpret_cast<uint32_t*>(&pp);
+            dot = __fadd2_rn(dot, make_float2(__uint_as_float(pw << 16), __uint_as_float(pw & 0xffff0000u)));
+            const float2 bf = make_float2(__uint_as_float(bw[q] << 16), __uint_as_float(bw[q] & 0xffff0000u));
+            nb = __ffma2_rn(bf, bf, nb);
+        }
+    } else {
+        float a[Num<DT>::EPV], b[Num<DT>::EPV];
+        Num<DT>::unpack(va, a);
+        Num<DT>::unpack(vb, b);
+#pragma unroll
+        for (int e = 0; e < Num<DT>::EPV; e += 2) {
+            if (DT == FF_F32) { dot.x += __fmul_rn(a[e], b[e]); dot.y += __fmul_rn(a[e + 1], b[e + 1]); }
+            else { dot.x += Num<DT>::rnd(a[e] * b[e]); dot.y += Num<DT>::rnd(a[e + 1] * b[e + 1]); }
+            nb.x = fmaf(b[e], b[e], nb.x);
+            nb.y = fmaf(b[e + 1], b[e + 1], nb.y);
+        }
     }
 }
 
 template <int DT>
-__device__ __forceinline__ void acc_norm(const uint4& vb, float& nb) {
+__device__ __forceinline__ void acc_norm(const uint4& vb, float2& nb) {
     float b[Num<DT>::EPV];
     Num<DT>::unpack(vb, b);
 #pragma unroll
-    for (int e = 0; e < Num<DT>::EPV; ++e) nb = fmaf(b[e], b[e], nb);
+    for (int e = 0; e < Num<DT>::EPV; e += 2) { nb.x = fmaf(b[e], b[e], nb.x); nb.y = fmaf(b[e + 1], b[e + 1], nb.y); }
 }
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------
@@ -169,26 +210,34 @@ __device__ __forceinline__ void st_flag(uint8_t* p, unsigned v) {
     asm volatile("st.relaxed.gpu.global.u8 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
-// kept rows among the flag bytes [lo, hi) this thread is responsible for in one 16-byte vector at byte offset
-// `at` (16-aligned); *ok is cleared if a byte in range does not carry the call's tag yet.
-__device__ __forceinline__ int count_kept16(const uint8_t* state, int at, int lo, int hi, unsigned tag4, bool* ok) {
-    const uint4 v = ld_flags16(state + at);
+// kept rows among the flag bytes [lo, hi) that fall into the 16-byte vector `v` loaded from byte offset `at`
+// (16-aligned); *ok is cleared if a byte in range does not carry the call's tag yet.  tagm = tag4 << 1.
+__device__ __forceinline__ int count_kept_vec(const uint4& v, int at, int lo, int hi, unsigned tagm, bool* ok) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     int kept = 0;
+    if (at >= lo && at + 16 <= hi) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if ((w[q] & 0xfefefefeu) != tagm) *ok = false;
+            kept += __popc(~w[q] & 0x01010101u);
+        }
+        return kept;
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int b0 = at + 4 * q;
-        uint32_t m = 0xffffffffu;
-        if (b0 < lo || b0 + 4 > hi) {
-            m = 0;
+        uint32_t m = 0;
 #pragma unroll
-            for (int b = 0; b < 4; ++b)
-                if (b0 + b >= lo && b0 + b < hi) m |= 0xffu << (8 * b);
-        }
-        if ((((w[q] >> 1) & 0x7f7f7f7fu) ^ tag4) & m) *ok = false;
+        for (int b = 0; b < 4; ++b)
+            if (b0 + b >= lo && b0 + b < hi) m |= 0xffu << (8 * b);
+        if (((w[q] & 0xfefefefeu) ^ tagm) & m) *ok = false;
         kept += __popc(~w[q] & 0x01010101u & m);
     }
     return kept;
+}
+
+__device__ __forceinline__ int count_kept16(const uint8_t* state, int at, int lo, int hi, unsigned tagm, bool* ok) {
+    return count_kept_vec(ld_flags16(state + at), at, lo, hi, tagm, ok);
 }
 
 // ---- the kernel --------------------------------------------------------------------------------------------
@@ -212,12 +261,13 @@ k_stream_merge(const StreamArgs a) {
     const int n_teams = a.cpc;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int team = warp / ST_TEAM_WARPS;
-    const unsigned tag4 = a.tag * 0x01010101u;
+    const unsigned tag4 = (a.tag * 0x01010101u) << 1;       // the tag as it sits in every flag byte
 
     unsigned char* slots_base = smem;
     uint64_t* bars_base = reinterpret_cast<uint64_t*>(smem + (size_t)n_teams * a.n_slots * a.slot_bytes);
     TeamXchg* xchg_base = reinterpret_cast<TeamXchg*>(bars_base + n_teams * a.n_slots);
     int* idx_base = reinterpret_cast<int*>(xchg_base + n_teams);
+    uint64_t* small_base = reinterpret_cast<uint64_t*>(idx_base + n_teams * ST_IDX_WIN);
 
     if (threadIdx.x == 0) {
         for (int b = 0; b < n_teams * a.n_slots; ++b) mbar_init(smem_u32(bars_base + b), 1);
@@ -233,14 +283,16 @@ k_stream_merge(const StreamArgs a) {
         const int tw = tid >> 5;                             // warp inside the team
         const int id = blockIdx.x * a.cpc + team;
         const int bar_id = 1 + team;
+        const int K = a.lag;                                 // the position of row r is taken at iteration r + K
         unsigned char* slots = slots_base + (size_t)team * a.n_slots * a.slot_bytes;
         uint64_t* bars = bars_base + team * a.n_slots;
         TeamXchg* xc = xchg_base + team;
         int* s_idx = idx_base + team * ST_IDX_WIN;
+        uint64_t* q_small = small_base + team * 8 * ST_MAX_SMALL_AUX;   // thread 0 only: 8-byte aux values of recent anchors
         const int len = id < a.n_ids ? __ldg(a.len + id) : 0;
         const int cbase = id < a.n_ids ? __ldg(a.base + id) : 0;
 
-        // chain-list window: entries [0, 64) now, refilled half by half
+        // chain-list window: 64 consecutive entries of the chain, slid by 32 (see the refill below)
         if (tid < ST_IDX_WIN) s_idx[tid] = tid < len ? __ldg(a.order + cbase + tid) : 0;
         team_bar(bar_id);
 
@@ -286,51 +338,63 @@ k_stream_merge(const StreamArgs a) {
         // chain state (uniform across the team)
         int acc_slot = -1, last_slot = -1;                   // pending anchor / previous row of the chain
         int L = 0;                                           // members merged into the pending anchor
-        int anchor_i = -1;                                   // its sequence index
+        int anchor_t = -1, anchor_i = -1;                    // its chain position and sequence index
         int anchor_pos = -1;                                 // its compacted position (-1: not known yet)
-        int anchor_t = -1;                                   // its chain position
         float n_last = 0.f;                                  // |last|^2
-        int cnt = 0;                                         // kept rows in [0, i_{t-1}) once the scan of iteration t is done
-        int prev_i = -1, prev2_i = -1;                       // i_{t-1}, i_{t-2}
-        int prev_kept = 0, prev2_kept = 0;                   // whether those rows were kept
-        int kept_idx = 0;                                    // kept rows of this chain so far (next-call list position)
-        uint64_t small_cur[ST_MAX_SMALL_AUX] = {0, 0}, small_acc[ST_MAX_SMALL_AUX] = {0, 0};
+        int cnt = 0;                                         // kept rows in [0, i_r) after the scan step of row r
+        uint32_t kept_hist = 0;                              // bit (t & 31): row t of the chain was kept
+        uint32_t q_fin = 0, q_slot4 = 0;                     // closed anchors waiting for their position, by (t & 7)
+        int kept_idx = 0;                                    // kept rows of this chain written so far (next-call list position)
+        uint64_t small_acc[ST_MAX_SMALL_AUX] = {0, 0};       // thread 0: 8-byte aux values of the pending anchor
 
-        issue_loads(32);
+        issue_loads(20);
         int phase = 0;
 
-        // writes the pending anchor (finalised in its slot) to its compacted position; uniform call
-        auto flush_anchor = [&]() {
-            // average of the run (main.py:314-317); L == 0 rows go out untouched
-            unsigned char* arow = slots + (size_t)acc_slot * a.slot_bytes;
+        // one kept row, final in its slot, goes to its compacted position; uniform call
+        auto write_row = [&](int slot, int t_a, int i_a, int pos) {
+            if (pend1 >= 0) retire_oldest();                 // at most two stores in flight
+            if (tid == 0) {
+                const uint32_t src = smem_u32(slots + (size_t)slot * a.slot_bytes);
+                tma_store(a.out + (size_t)pos * a.row_bytes, src, (uint32_t)a.row_bytes);
+                for (int q = 0; q < a.n_tma_aux; ++q)
+                    tma_store(a.tma_aux[q].dst + (size_t)pos * a.tma_aux[q].bytes, src + a.tma_aux[q].slot_off,
+                              (uint32_t)a.tma_aux[q].bytes);
+                tma_commit();
+                for (int q = 0; q < a.n_small_aux; ++q)
+                    *reinterpret_cast<uint64_t*>(a.small_aux[q].dst + (size_t)pos * 8) = q_small[(t_a & 7) * ST_MAX_SMALL_AUX + q];
+                a.dst[i_a] = pos;
+                a.order_next[cbase + kept_idx] = pos;
+            }
+            if (pend0 < 0) pend0 = slot; else pend1 = slot;
+            ++kept_idx;
+        };
+
+        // the run of the pending anchor is over: average it (main.py:314-317) and write it, or park it until its
+        // position is known; uniform call
+        auto close_anchor = [&]() {
             if (L > 0) {
-                const float div = Num<DT>::rnd((float)(L + 1));
+                unsigned char* arow = slots + (size_t)acc_slot * a.slot_bytes;
+                const Divider<DT> dv(L + 1);
 #pragma unroll
                 for (int k = 0; k < VPT; ++k) {
                     const int v = tid + ST_NT * k;
                     if (v < a.nvec) {
                         uint4* p = reinterpret_cast<uint4*>(arow) + v;
-                        *p = div_round<DT>(*p, div);
+                        *p = dv.vec(*p);
                     }
                 }
                 fence_async_smem();
+                team_bar(bar_id);
             }
-            team_bar(bar_id);
-            if (pend1 >= 0) retire_oldest();                 // at most two stores in flight
-            if (tid == 0) {
-                const uint32_t src = smem_u32(arow);
-                tma_store(a.out + (size_t)anchor_pos * a.row_bytes, src, (uint32_t)a.row_bytes);
-                for (int q = 0; q < a.n_tma_aux; ++q)
-                    tma_store(a.tma_aux[q].dst + (size_t)anchor_pos * a.tma_aux[q].bytes, src + a.tma_aux[q].slot_off,
-                              (uint32_t)a.tma_aux[q].bytes);
-                tma_commit();
-                for (int q = 0; q < a.n_small_aux; ++q)
-                    *reinterpret_cast<uint64_t*>(a.small_aux[q].dst + (size_t)anchor_pos * 8) = small_acc[q];
-                a.dst[anchor_i] = anchor_pos;
-                a.order_next[cbase + kept_idx] = anchor_pos;
+            if (tid == 0)
+                for (int q = 0; q < a.n_small_aux; ++q) q_small[(anchor_t & 7) * ST_MAX_SMALL_AUX + q] = small_acc[q];
+            if (anchor_pos >= 0) {
+                write_row(acc_slot, anchor_t, anchor_i, anchor_pos);
+            } else {
+                const int sh = 4 * (anchor_t & 7);
+                q_fin |= 1u << (anchor_t & 7);
+                q_slot4 = (q_slot4 & ~(0xfu << sh)) | ((uint32_t)acc_slot << sh);
             }
-            if (pend0 < 0) pend0 = acc_slot; else pend1 = acc_slot;
-            ++kept_idx;
         };
 
         // counts the kept rows in (from, to) exclusive, waiting until every flag there is published
@@ -354,120 +418,154 @@ k_stream_merge(const StreamArgs a) {
                     for (int w = 0; w < ST_TEAM_WARPS; ++w) { k2 += xc->kept[phase][w]; o2 &= xc->ok[phase][w]; }
                     phase ^= 1;
                     if (o2) { total += k2; break; }
-                    __nanosleep(64);
+                    __nanosleep(100);
                 }
             }
             return total;
         };
 
-        for (int t = 0; t < len; ++t) {
-            // refill the other half of the chain-list window every 32 rows
-            if ((t & 31) == 0 && t + 32 < len) {
-                const int e = t + 32 + tid;
+        for (int t = 0; t < len + K; ++t) {
+            // slide the chain-list window: entries older than t - 8 make room for [t + 24, t + 56)
+            if ((t & 31) == 8 && t >= 40) {
+                const int e = t + 24 + tid;
                 if (tid < 32) s_idx[e & (ST_IDX_WIN - 1)] = e < len ? __ldg(a.order + cbase + e) : 0;
-                // visible to tid 0 after the next team barrier; issue_loads never runs more than 32 rows ahead
+                // visible to thread 0 after the next team barrier; loads are issued at most 20 rows ahead
             }
+            const bool have_row = t < len;
+            const int r = t - K;                             // the row whose position this iteration settles
             const int i = s_idx[t & (ST_IDX_WIN - 1)];
             const int s = (int)((ring >> (4 * (t & 15))) & 0xfull);
             unsigned char* crow = slots + (size_t)s * a.slot_bytes;
 
             // small aux rows of this token: issued now, consumed after the row arrived
             uint64_t small_new[ST_MAX_SMALL_AUX] = {0, 0};
-            if (tid == 0)
+            if (tid == 0 && have_row)
                 for (int q = 0; q < a.n_small_aux; ++q)
                     small_new[q] = __ldg(reinterpret_cast<const uint64_t*>(a.small_aux[q].src + (size_t)i * 8));
 
-            mbar_wait(smem_u32(bars + s), (parity >> s) & 1u);
-            parity ^= 1u << s;
+            // flags between rows r-1 and r of the chain: loaded now, looked at after the similarity, so that the L2
+            // round trip hides behind the arrival of the row and the arithmetic
+            const int i_r = r >= 0 ? s_idx[r & (ST_IDX_WIN - 1)] : 0;
+            const int i_r1 = r >= 1 ? s_idx[(r - 1) & (ST_IDX_WIN - 1)] : -1;
+            const int f_lo = i_r1 + 1, f_hi = i_r;
+            const int f_at = (f_lo & ~15) + tid * 16;
+            const bool f_mine = r >= 0 && f_at < f_hi;
+            const bool f_one_chunk = (f_hi - (f_lo & ~15)) <= ST_NT * 16;
+            uint4 fl = make_uint4(0, 0, 0, 0);
+            if (f_mine) fl = ld_flags16(a.state + f_at);
 
-            // ---- similarity with the previous row of the chain (main.py:345-349 rounding chain)
-            float dot = 0.f, nb = 0.f;
-            if (t > 0) {
-                const unsigned char* lrow = slots + (size_t)last_slot * a.slot_bytes;
+            float2 dot2 = make_float2(0.f, 0.f), nb2 = make_float2(0.f, 0.f);
+            if (have_row) {
+                mbar_wait(smem_u32(bars + s), (parity >> s) & 1u);
+                parity ^= 1u << s;
+                // ---- similarity with the previous row of the chain (main.py:345-349 rounding chain)
+                if (t > 0) {
+                    const unsigned char* lrow = slots + (size_t)last_slot * a.slot_bytes;
 #pragma unroll
-                for (int k = 0; k < VPT; ++k) {
-                    const int v = tid + ST_NT * k;
-                    if (v < a.nvec) {
-                        const uint4 x = reinterpret_cast<const uint4*>(lrow)[v];
-                        const uint4 y = reinterpret_cast<const uint4*>(crow)[v];
-                        acc_dot_norm<DT>(x, y, dot, nb);
+                    for (int k = 0; k < VPT; ++k) {
+                        const int v = tid + ST_NT * k;
+                        if (v < a.nvec) {
+                            const uint4 x = reinterpret_cast<const uint4*>(lrow)[v];
+                            const uint4 y = reinterpret_cast<const uint4*>(crow)[v];
+                            acc_dot_norm<DT>(x, y, dot2, nb2);
+                        }
                     }
-                }
-            } else {
+                } else {
 #pragma unroll
-                for (int k = 0; k < VPT; ++k) {
-                    const int v = tid + ST_NT * k;
-                    if (v < a.nvec) {
-                        acc_norm<DT>(reinterpret_cast<const uint4*>(crow)[v], nb);
+                    for (int k = 0; k < VPT; ++k) {
+                        const int v = tid + ST_NT * k;
+                        if (v < a.nvec) acc_norm<DT>(reinterpret_cast<const uint4*>(crow)[v], nb2);
                     }
                 }
             }
-            dot = warp_sum(dot);
-            nb = warp_sum(nb);
-            if (lane == 0) { xc->dot[phase][tw] = dot; xc->nrm[phase][tw] = nb; }
+            bool f_ok = true;
+            int f_kept = 0;
+            if (f_mine) f_kept = count_kept_vec(fl, f_at, f_lo, f_hi, tag4, &f_ok);
+            const float dot = warp_sum(dot2.x + dot2.y);
+            const float nb = warp_sum(nb2.x + nb2.y);
+            f_kept = warp_sum_int(f_kept);
+            const int f_wok = __all_sync(FULL, f_ok);
+            if (lane == 0) { xc->dot[phase][tw] = dot; xc->nrm[phase][tw] = nb; xc->kept[phase][tw] = f_kept; xc->ok[phase][tw] = f_wok; }
             team_bar(bar_id);
             float dsum = 0.f, nsum = 0.f;
+            int ksum = 0, oksum = 1;
 #pragma unroll
-            for (int w = 0; w < ST_TEAM_WARPS; ++w) { dsum += xc->dot[phase][w]; nsum += xc->nrm[phase][w]; }
+            for (int w = 0; w < ST_TEAM_WARPS; ++w) {
+                dsum += xc->dot[phase][w]; nsum += xc->nrm[phase][w]; ksum += xc->kept[phase][w]; oksum &= xc->ok[phase][w];
+            }
             phase ^= 1;
-            int hit = 0;
-            float sim = -2.0f;
-            if (t > 0) {
-                sim = finish_cosine<DT>(dsum, n_last, nsum);
-                hit = sim >= a.thr;
-            }
-            if (tid == 0) {
-                a.sim_seq[i] = sim;
-                st_flag(a.state + i, (a.tag << 1) | (unsigned)hit);
-                if (hit) a.dst[i] = -1;
-            }
-            my_hits += hit;
 
-            // ---- position of the previous row: kept rows in [0, i_{t-1})
-            if (t > 0) {
-                cnt += prev2_kept + scan_between(prev2_i, prev_i);
-                if (anchor_t == t - 1) anchor_pos = cnt;
-            }
+            if (have_row) {
+                int hit = 0;
+                float sim = -2.0f;
+                if (t > 0) {
+                    sim = finish_cosine<DT>(dsum, n_last, nsum);
+                    hit = sim >= a.thr;
+                }
+                if (tid == 0) {
+                    a.sim_seq[i] = sim;
+                    st_flag(a.state + i, (a.tag << 1) | (unsigned)hit);
+                    if (hit) a.dst[i] = -1;
+                }
+                my_hits += hit;
 
-            // ---- merge or close the run
-            if (hit) {
-                unsigned char* arow = slots + (size_t)acc_slot * a.slot_bytes;
+                // ---- merge into the pending anchor, or close its run and open a new one
+                if (hit) {
+                    unsigned char* arow = slots + (size_t)acc_slot * a.slot_bytes;
 #pragma unroll
-                for (int k = 0; k < VPT; ++k) {
-                    const int v = tid + ST_NT * k;
-                    if (v < a.nvec) {
-                        uint4* p = reinterpret_cast<uint4*>(arow) + v;
-                        *p = add_round<DT>(*p, reinterpret_cast<const uint4*>(crow)[v]);
+                    for (int k = 0; k < VPT; ++k) {
+                        const int v = tid + ST_NT * k;
+                        if (v < a.nvec) {
+                            uint4* p = reinterpret_cast<uint4*>(arow) + v;
+                            *p = add_round<DT>(*p, reinterpret_cast<const uint4*>(crow)[v]);
+                        }
+                    }
+                    fence_async_smem();                      // ordered before the bulk store by a later team barrier
+                    if (L > 0) free_mask |= 1u << last_slot; // nobody reads the old `last` any more
+                    ++L;
+                } else {
+                    if (t > 0) {
+                        close_anchor();
+                        if (L > 0) free_mask |= 1u << last_slot;
+                    }
+                    acc_slot = s;
+                    L = 0;
+                    anchor_t = t;
+                    anchor_i = i;
+                    anchor_pos = -1;
+#pragma unroll
+                    for (int q = 0; q < ST_MAX_SMALL_AUX; ++q) small_acc[q] = small_new[q];
+                    kept_hist |= 1u << (t & 31);
+                }
+                if (hit) kept_hist &= ~(1u << (t & 31));
+                last_slot = s;
+                n_last = nsum;
+            } else if (t == len && len > 0) {
+                close_anchor();                              // end of the chain: the last anchor
+                if (L > 0) free_mask |= 1u << last_slot;
+                anchor_t = -1;
+            }
+
+            // ---- position of row r: kept rows in [0, i_r).  The flags were usually all there; otherwise (or when
+            //      the gap spans more than one chunk) poll until they are.
+            if (r >= 0) {
+                if (!(oksum && f_one_chunk)) ksum = scan_between(i_r1, i_r);
+                const int prev_kept = r >= 1 ? (int)((kept_hist >> ((r - 1) & 31)) & 1u) : 0;
+                cnt += prev_kept + ksum;
+                if ((kept_hist >> (r & 31)) & 1u) {
+                    if (q_fin & (1u << (r & 7))) {
+                        q_fin &= ~(1u << (r & 7));
+                        write_row((int)((q_slot4 >> (4 * (r & 7))) & 0xfu), r, i_r, cnt);
+                    } else {
+                        anchor_pos = cnt;                    // row r is the pending anchor, still open
                     }
                 }
-                if (L > 0) free_mask |= 1u << last_slot;                 // nobody reads the old `last` any more
-                ++L;
-            } else {
-                if (t > 0) flush_anchor();
-                if (t > 0 && L > 0) free_mask |= 1u << last_slot;
-                acc_slot = s;
-                L = 0;
-                anchor_i = i;
-                anchor_t = t;
-                anchor_pos = -1;
-#pragma unroll
-                for (int q = 0; q < ST_MAX_SMALL_AUX; ++q) small_acc[q] = small_new[q];
             }
-            last_slot = s;
-            n_last = nsum;
-            prev2_i = prev_i; prev2_kept = prev_kept;
-            prev_i = i; prev_kept = !hit;
 
             if (!free_mask && issued < len) retire_oldest();
-            issue_loads(t + 1 + 32);
+            issue_loads(t + 1 + 20);
         }
 
-        if (len > 0) {
-            // the last row's position, then the pending anchor goes out
-            cnt += prev2_kept + scan_between(prev2_i, prev_i);
-            if (anchor_t == len - 1) anchor_pos = cnt;
-            flush_anchor();
-        }
         if (tid == 0) {
             tma_wait_all();
             if (id < a.n_ids) a.len_next[id] = kept_idx;
@@ -560,7 +658,7 @@ k_stream_merge(const StreamArgs a) {
 }
 
 struct StreamPlan {
-    int cpc, grid, n_slots, slot_bytes, threads;
+    int cpc, grid, n_slots, slot_bytes, threads, lag;
     size_t smem;
 };
 
@@ -570,7 +668,7 @@ inline bool plan_stream(int sm_count, int max_smem, int64_t row_bytes, int n_ids
     const int cpc = (n_ids + sm_count - 1) / sm_count;
     if (cpc > ST_MAX_TEAMS) return false;
     const int slot = (int)((row_bytes + aux_bytes + 127) / 128 * 128);
-    const size_t fixed = (size_t)cpc * (sizeof(TeamXchg) + ST_IDX_WIN * 4) + 256;
+    const size_t fixed = (size_t)cpc * (sizeof(TeamXchg) + ST_IDX_WIN * 4 + 8 * ST_MAX_SMALL_AUX * 8) + 256;
     const size_t static_smem = 64;
     if ((size_t)max_smem < fixed + static_smem) return false;
     size_t avail = (size_t)max_smem - fixed - static_smem;
@@ -580,6 +678,7 @@ inline bool plan_stream(int sm_count, int max_smem, int64_t row_bytes, int n_ids
     p->cpc = cpc;
     p->grid = (n_ids + cpc - 1) / cpc;
     p->n_slots = n_slots;
+    p->lag = n_slots >= 7 ? 3 : (n_slots == 6 ? 2 : 1);    // worst case held: anchor + last + (lag - 1) parked + 2 stores
     p->slot_bytes = slot;
     p->threads = cpc * ST_NT + 32;
     p->smem = (size_t)cpc * n_slots * (slot + 8) + fixed;
