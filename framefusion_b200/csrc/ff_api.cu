@@ -257,7 +257,8 @@ bool plan_stream_args(const ff_ctx* ctx, const Ws& w, int bank, const void* hidd
     const int64_t row_bytes = H * eb;
     if (row_bytes % 16 != 0 || (((uintptr_t)hidden | (uintptr_t)out) & 15) != 0) return false;
     const int64_t nvec = row_bytes / 16;
-    if (nvec > (int64_t)ST_NT * ST_MAX_VPT) return false;
+    if (nvec > (int64_t)32 * ST_MAX_VPL) return false;
+    if (S >= (1 << 20)) return false;                      // gap counts travel in 20 bits
     if (!(thr > -2.0)) return false;                       // chain heads (sim = -2) must never be flagged
     if (ctx->n_ids < 1) return false;
     StreamArgs& a = *sa;
@@ -266,7 +267,7 @@ bool plan_stream_args(const ff_ctx* ctx, const Ws& w, int bank, const void* hidd
     for (int q = 0; q < ap.n; ++q) {
         const ff_aux& x = ap.a[q];
         const uintptr_t al = (uintptr_t)x.src | (uintptr_t)x.dst | (uintptr_t)x.src_plane_stride | (uintptr_t)x.dst_plane_stride;
-        if (x.row_bytes % 16 == 0 && (al & 15) == 0 && x.row_bytes <= 4096) {
+        if (x.row_bytes % 16 == 0 && (al & 15) == 0 && x.row_bytes <= 512) {
             for (int64_t pl = 0; pl < x.planes; ++pl) {
                 if (a.n_tma_aux == ST_MAX_TMA_AUX) return false;
                 StreamAux& t = a.tma_aux[a.n_tma_aux++];
@@ -298,7 +299,7 @@ bool plan_stream_args(const ff_ctx* ctx, const Ws& w, int bank, const void* hidd
     a.n_slots = plan->n_slots;
     a.n_ids = (int)ctx->n_ids;
     a.cpc = plan->cpc;
-    a.lag = plan->lag;
+    a.n_sim = plan->n_sim;
     a.order = w.order[bank];
     a.base = w.base;
     a.len = w.len[bank];

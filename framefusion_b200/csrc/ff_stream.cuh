@@ -5,25 +5,29 @@
 // Shape of the problem.  Similarities couple a token only with the previous surviving token of the SAME patch id
 // (a "chain", main.py:216-238), while the output is compacted in SEQUENCE order (main.py:132-138).  So:
 //
-//   * chains are owned: a persistent grid of <= one CTA per SM, each CTA owns `cpc` consecutive patch ids, and
-//     inside the CTA a TEAM of two warps owns one chain for the whole kernel.  A team walks its chain front to
-//     back.  Rows arrive in shared memory by TMA (cp.async.bulk + mbarrier, a few rows ahead), the previous row
-//     of the chain is still there, so sim(prev, cur) costs no second read — not from HBM, not from L2.
-//   * the merge happens where the row already is: a kept row stays in its slot as the pending anchor; flagged
-//     successors are added into it one at a time with a rounding to T per add (the order torch-CPU index_add_
-//     uses, main.py:304-311), and when the run ends the sum is divided by T(L+1) (main.py:314-317) and the slot is
-//     written to its compacted position with a TMA bulk store.  The aux rows (cos, sin) ride in the same slot.
-//   * the compacted position of a kept row i is the number of kept rows before i.  Teams publish one flag byte
-//     per row (tagged with the call's epoch, so nothing is cleared between calls) and every team counts the
-//     flags between two consecutive rows of its own chain — a redundant, fully parallel scan: S bytes per team
-//     from L2 instead of a serial look-back chain.  The count for row t-1 is taken while row t is being processed,
-//     when those flags are one row-time old, so in steady state nobody waits; when CTAs drift apart the wait
-//     is bounded by the slots a team has for rows in flight.
+//   * chains are owned: a persistent grid of <= one CTA per SM, each CTA owns `cpc` consecutive patch ids for the
+//     whole kernel.  Rows of a chain arrive in shared memory by TMA (cp.async.bulk + mbarrier) into a small ring
+//     of slots, several rows ahead; the previous row of the chain is still there, so sim(prev, cur) costs no
+//     second read — not from HBM, not from L2.
+//   * inside a chain the work is a pipeline of warps.  SIM warps take the rows round-robin: wait for the row,
+//     compute sim(row t-1, row t) with the reference's rounding chain, publish the merge flag.  Nothing in that
+//     depends on the merge itself, so similarities run ahead.  One MERGE warp per chain follows in row order
+//     and holds the pending anchor in REGISTERS: a flagged row is added into it with one rounding to T per add
+//     (the order torch-CPU index_add_ uses, main.py:304-311); when the run ends the sum is divided by T(L+1)
+//     (main.py:314-317) and stored straight to its compacted position with 16-byte streaming stores, together
+//     with its cos / sin / patch_type entries.  A slot is recycled — and the next row of the chain requested — by
+//     whichever warp drops its last reference.
+//   * the compacted position of a kept row i is the number of kept rows before i.  Every row gets one flag byte
+//     in global memory (tagged with the call's epoch, so nothing is cleared between calls); the sim warp of row
+//     t counts the flags between rows t-2 and t-1 of its own chain (the loads are issued before it waits for
+//     the row, so the L2 round trip is hidden) and the merge warp adds these gap counts up.  Summed over the
+//     grid every team reads all S flag bytes: a redundant, fully parallel scan instead of a look-back chain.
 //
-// Progress: a team publishes the flag of row t BEFORE it waits for anything, and only ever waits for flags of
-// rows with a smaller sequence index than a row it has already published; the wait-for relation strictly
-// decreases in sequence index, all CTAs are co-resident (grid <= SM count, one CTA per SM), TMA always
-// completes: no deadlock.
+// Progress: a flag is published before its warp waits for anything else; a gap count only waits for flags of
+// rows with a smaller sequence index than a row whose flag that chain has already published, so the wait-for
+// relation strictly decreases in sequence index; all CTAs are co-resident (grid <= SM count, one CTA per SM);
+// a slot's references (row t as "current", as "previous" of row t+1, as merge input) only need rows t and t+1
+// resident, and rows are requested in order: no deadlock.
 //
 // The branch decision (main.py:114-116) needs the global count, known only at the end: the kernel speculates
 // on the threshold branch, the last CTA to finish checks count / n_vis < bound and otherwise reports
@@ -38,15 +42,15 @@
 
 namespace ff {
 
-constexpr int ST_TEAM_WARPS = 2;
-constexpr int ST_NT = ST_TEAM_WARPS * 32;          // threads per team
-constexpr int ST_MAX_VPT = 8;                      // 16-byte vectors per thread: rows up to 8 KB
-constexpr int ST_MAX_TEAMS = 7;                    // named barriers 1..7
-constexpr int ST_MAX_SLOTS = 12;
-constexpr int ST_MIN_SLOTS = 5;
-constexpr int ST_IDX_WIN = 64;                     // chain-list window kept in shared memory (two halves of 32)
-constexpr int ST_MAX_TMA_AUX = 6;                  // (aux, plane) pairs carried through the slot
-constexpr int ST_MAX_SMALL_AUX = 2;                // 8-byte aux rows (patch_type, position ids) carried in registers
+constexpr int ST_MAX_CHAINS = 8;                   // chains per CTA
+constexpr int ST_MAX_SLOTS = 12;                   // row slots per chain
+constexpr int ST_MIN_SLOTS = 3;
+constexpr int ST_RING = 16;                        // depth of the per-chain hand-over rings (> ST_MAX_SLOTS)
+constexpr int ST_MAX_LEN = 256;                    // rows per chain the index window holds
+constexpr int ST_MAX_VPL = 16;                     // 16-byte vectors per lane: rows up to 8 KB
+constexpr int ST_MAX_TMA_AUX = 6;                  // (aux, plane) pairs carried through the slot, <= 512 bytes each
+constexpr int ST_MAX_SMALL_AUX = 2;                // 8-byte aux rows (patch_type, position ids)
+constexpr int ST_MAX_WARPS = 16;                   // cpc * (n_sim + 1) + 1: 512 threads leave 128 registers each
 
 struct StreamAux {
     const char* src;
@@ -62,10 +66,10 @@ struct StreamArgs {
     int nvec;                                      // 16-byte vectors per row
     int row_bytes;
     int slot_bytes;                                // row + aux area, multiple of 128
-    int n_slots;                                   // per team
+    int n_slots;                                   // per chain
     int n_ids;                                     // chain buckets; bucket n_ids = rows outside the chains
     int cpc;                                       // chains per CTA
-    int lag;                                       // iterations between a row's arrival and the scan that positions it
+    int n_sim;                                     // sim warps per chain
     const int* order;                              // chain lists: order[base[id] + t] = sequence index
     const int* base;
     const int* len;
@@ -99,6 +103,8 @@ __device__ __forceinline__ uint4 add_round(const uint4& a, const uint4& b) {    
 // bf16 fast path: a power-of-two divisor is an exact scaling; otherwise q0 = x * RN(1/div) is within 2 float32 ulp
 // of the correctly rounded quotient, so both round to the same bf16 unless q0 sits within a few ulp of a bf16
 // rounding boundary (low 16 bits ~ 0x8000) — those elements (about 1e-4 of them) take the IEEE division.
+__device__ __noinline__ float ieee_div(float x, float d) { return x / d; }
+
 template <int DT>
 struct Divider {
     float div, rcp;
@@ -114,7 +120,7 @@ struct Divider {
         if (pow2) return q0;
         const uint32_t u = __float_as_uint(q0);
         const bool risky = ((u & 0xffffu) - 0x7ff8u) <= 0x10u || ((u & 0x7f800000u) == 0u && (u << 1) != 0u);
-        return risky ? x / div : q0;
+        return risky ? ieee_div(x, div) : q0;
     }
     __device__ __forceinline__ uint4 vec(const uint4& a) const {
         float x[Num<DT>::EPV];
@@ -151,6 +157,39 @@ __device__ __forceinline__ void acc_dot_norm(const uint4& va, const uint4& vb, f
         for (int e = 0; e < Num<DT>::EPV; e += 2) {
             if (DT == FF_F32) { dot.x += __fmul_rn(a[e], b[e]); dot.y += __fmul_rn(a[e + 1], b[e + 1]); }
             else { dot.x += Num<DT>::rnd(a[e] * b[e]); dot.y += Num<DT>::rnd(a[e + 1] * b[e + 1]); }
+            nb.x = fmaf(b[e], b[e], nb.x);
+            nb.y = fmaf(b[e + 1], b[e + 1], nb.y);
+        }
+    }
+}
+
+// the same with the norm of `a` as well (sim warps do not share norms: recomputing is cheaper than a hand-over)
+template <int DT>
+__device__ __forceinline__ void acc_pair2(const uint4& va, const uint4& vb, float2& dot, float2& na, float2& nb) {
+    if (DT == FF_BF16) {
+        const uint32_t aw[4] = {va.x, va.y, va.z, va.w}, bw[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            __nv_bfloat162 pa = *reinterpret_cast<const __nv_bfloat162*>(&aw[q]);
+            __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&bw[q]);
+            __nv_bfloat162 pp = __hmul2(pa, pb);
+            const uint32_t pw = *reinterpret_cast<uint32_t*>(&pp);
+            dot = __fadd2_rn(dot, make_float2(__uint_as_float(pw << 16), __uint_as_float(pw & 0xffff0000u)));
+            const float2 af = make_float2(__uint_as_float(aw[q] << 16), __uint_as_float(aw[q] & 0xffff0000u));
+            const float2 bf = make_float2(__uint_as_float(bw[q] << 16), __uint_as_float(bw[q] & 0xffff0000u));
+            na = __ffma2_rn(af, af, na);
+            nb = __ffma2_rn(bf, bf, nb);
+        }
+    } else {
+        float a[Num<DT>::EPV], b[Num<DT>::EPV];
+        Num<DT>::unpack(va, a);
+        Num<DT>::unpack(vb, b);
+#pragma unroll
+        for (int e = 0; e < Num<DT>::EPV; e += 2) {
+            if (DT == FF_F32) { dot.x += __fmul_rn(a[e], b[e]); dot.y += __fmul_rn(a[e + 1], b[e + 1]); }
+            else { dot.x += Num<DT>::rnd(a[e] * b[e]); dot.y += Num<DT>::rnd(a[e + 1] * b[e + 1]); }
+            na.x = fmaf(a[e], a[e], na.x);
+            na.y = fmaf(a[e + 1], a[e + 1], na.y);
             nb.x = fmaf(b[e], b[e], nb.x);
             nb.y = fmaf(b[e + 1], b[e + 1], nb.y);
         }
@@ -198,7 +237,6 @@ __device__ __forceinline__ void tma_wait_read_1() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void tma_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void team_bar(int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(ST_NT) : "memory"); }
 
 __device__ __forceinline__ uint4 ld_flags16(const uint8_t* p) {
     uint4 r;
@@ -226,10 +264,9 @@ __device__ __forceinline__ int count_kept_vec(const uint4& v, int at, int lo, in
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int b0 = at + 4 * q;
+        const int l = max(lo - b0, 0), h = min(hi - b0, 4);          // bytes [l, h) of this word are in range
         uint32_t m = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-            if (b0 + b >= lo && b0 + b < hi) m |= 0xffu << (8 * b);
+        if (h > l) m = (0xffffffffu >> (8 * (4 - h))) & (0xffffffffu << (8 * l));
         if (((w[q] & 0xfefefefeu) ^ tagm) & m) *ok = false;
         kept += __popc(~w[q] & 0x01010101u & m);
     }
@@ -241,337 +278,301 @@ __device__ __forceinline__ int count_kept16(const uint8_t* state, int at, int lo
 }
 
 // ---- the kernel --------------------------------------------------------------------------------------------
-// dynamic shared memory layout (per CTA):
-//   [teams][n_slots] slots of slot_bytes           (128-byte aligned)
-//   [teams][n_slots] mbarriers (8 bytes)
-//   [teams] exchange area: 2 phases x ST_TEAM_WARPS x 4 words
-//   [teams] chain-list window: ST_IDX_WIN ints
-struct TeamXchg {
-    float dot[2][ST_TEAM_WARPS];
-    float nrm[2][ST_TEAM_WARPS];
-    int kept[2][ST_TEAM_WARPS];
-    int ok[2][ST_TEAM_WARPS];
+// per-chain shared state (one per chain of the CTA, after the slots in dynamic shared memory)
+struct ChainShared {
+    uint64_t bars[ST_MAX_SLOTS];                    // one mbarrier per slot
+    unsigned long long small[ST_RING][ST_MAX_SMALL_AUX];   // 8-byte aux values of row t at [t % ST_RING]
+    int idx[ST_MAX_LEN];                            // sequence index of every row of the chain
+    int slot_of[ST_RING];                           // ((row + 1) << 8) | (parity << 4) | slot
+    int hit[ST_RING];                               // ((row + 1) << 8) | merge flag of the row
+    int gap[ST_RING];                               // (((row + 1) & 0x7ff) << 20) | kept rows between row - 1 and row (exclusive)
+    int refcnt[ST_MAX_SLOTS];
+    int uses[ST_MAX_SLOTS];
+    int issued;                                     // rows requested so far
+    int pad;
 };
 
-template <int DT, int VPT>
-__global__ void __launch_bounds__(ST_NT * ST_MAX_TEAMS + 32, 1)
+__device__ __forceinline__ int ring_wait(const int* slot, int want_tag, int tag_shift) {
+    int v;
+    while (((unsigned)(v = *(volatile const int*)slot) >> tag_shift) != (unsigned)want_tag) __nanosleep(20);
+    return v;
+}
+
+// sequence index of row t of a chain: from the shared-memory window, from the list in global memory beyond it
+__device__ __forceinline__ int row_index(const ChainShared* cs, const int* chain_order, int t) {
+    return t < ST_MAX_LEN ? cs->idx[t] : __ldg(chain_order + t);
+}
+
+// requests the next row of the chain into `slot` (called by one lane, only by whoever freed the slot)
+__device__ __forceinline__ void issue_row(const StreamArgs& a, ChainShared* cs, const int* chain_order, unsigned char* slots,
+                                          int slot, int len, uint32_t tx_bytes) {
+    const int row = atomicAdd(&cs->issued, 1);
+    if (row >= len) return;
+    const int parity = cs->uses[slot] & 1;
+    cs->uses[slot] += 1;
+    cs->refcnt[slot] = row + 1 < len ? 3 : 2;               // current of sim(row), previous of sim(row + 1), merge(row)
+    __threadfence_block();
+    *(volatile int*)&cs->slot_of[row & (ST_RING - 1)] = ((row + 1) << 8) | (parity << 4) | slot;
+    const int i = row_index(cs, chain_order, row);
+    const uint32_t bar = smem_u32(&cs->bars[slot]);
+    const uint32_t dst = smem_u32(slots + (size_t)slot * a.slot_bytes);
+    mbar_expect_tx(bar, tx_bytes);
+    tma_load(dst, a.hidden + (size_t)i * a.row_bytes, (uint32_t)a.row_bytes, bar);
+    for (int q = 0; q < a.n_tma_aux; ++q)
+        tma_load(dst + a.tma_aux[q].slot_off, a.tma_aux[q].src + (size_t)i * a.tma_aux[q].bytes,
+                 (uint32_t)a.tma_aux[q].bytes, bar);
+}
+
+__device__ __forceinline__ void release_slot(const StreamArgs& a, ChainShared* cs, const int* chain_order, unsigned char* slots,
+                                             int slot, int len, uint32_t tx_bytes) {
+    __threadfence_block();
+    if (atomicSub(&cs->refcnt[slot], 1) == 1) issue_row(a, cs, chain_order, slots, slot, len, tx_bytes);
+}
+
+template <int DT, int VPL>
+__global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1)
 k_stream_merge(const StreamArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int s_last_cta;
-    const int n_teams = a.cpc;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int team = warp / ST_TEAM_WARPS;
+    const int wpc = a.n_sim + 1;                             // warps per chain
+    const int chain = warp / wpc, role = warp - chain * wpc;
     const unsigned tag4 = (a.tag * 0x01010101u) << 1;       // the tag as it sits in every flag byte
 
-    unsigned char* slots_base = smem;
-    uint64_t* bars_base = reinterpret_cast<uint64_t*>(smem + (size_t)n_teams * a.n_slots * a.slot_bytes);
-    TeamXchg* xchg_base = reinterpret_cast<TeamXchg*>(bars_base + n_teams * a.n_slots);
-    int* idx_base = reinterpret_cast<int*>(xchg_base + n_teams);
-    uint64_t* small_base = reinterpret_cast<uint64_t*>(idx_base + n_teams * ST_IDX_WIN);
+    ChainShared* cs_base = reinterpret_cast<ChainShared*>(smem + (size_t)a.cpc * a.n_slots * a.slot_bytes);
+    uint32_t tx_bytes = (uint32_t)a.row_bytes;
+    for (int q = 0; q < a.n_tma_aux; ++q) tx_bytes += (uint32_t)a.tma_aux[q].bytes;
 
-    if (threadIdx.x == 0) {
-        for (int b = 0; b < n_teams * a.n_slots; ++b) mbar_init(smem_u32(bars_base + b), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // ---- set-up: the merge warp of every chain fills the chain's shared state
+    if (chain < a.cpc && role == a.n_sim) {
+        ChainShared* cs = cs_base + chain;
+        const int id = blockIdx.x * a.cpc + chain;
+        const int len = id < a.n_ids ? __ldg(a.len + id) : 0;
+        const int cbase = id < a.n_ids ? __ldg(a.base + id) : 0;
+        for (int e = lane; e < ST_MAX_LEN; e += 32) cs->idx[e] = e < len ? __ldg(a.order + cbase + e) : 0;
+        if (lane < ST_RING) { cs->slot_of[lane] = 0; cs->hit[lane] = 0; cs->gap[lane] = 0; }
+        if (lane < ST_MAX_SLOTS) { cs->refcnt[lane] = 0; cs->uses[lane] = 0; }
+        if (lane == 0) {
+            cs->issued = 0;
+            for (int b = 0; b < a.n_slots; ++b) mbar_init(smem_u32(&cs->bars[b]), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
     }
     __syncthreads();
 
-    int my_hits = 0;                                        // tokens merged away (counted by team thread 0)
-
-    if (team < n_teams) {
-        // =========================== chain team ===========================
-        const int tid = threadIdx.x - team * ST_NT;          // 0..63
-        const int tw = tid >> 5;                             // warp inside the team
-        const int id = blockIdx.x * a.cpc + team;
-        const int bar_id = 1 + team;
-        const int K = a.lag;                                 // the position of row r is taken at iteration r + K
-        unsigned char* slots = slots_base + (size_t)team * a.n_slots * a.slot_bytes;
-        uint64_t* bars = bars_base + team * a.n_slots;
-        TeamXchg* xc = xchg_base + team;
-        int* s_idx = idx_base + team * ST_IDX_WIN;
-        uint64_t* q_small = small_base + team * 8 * ST_MAX_SMALL_AUX;   // thread 0 only: 8-byte aux values of recent anchors
+    if (chain < a.cpc) {
+        ChainShared* cs = cs_base + chain;
+        unsigned char* slots = smem + (size_t)chain * a.n_slots * a.slot_bytes;
+        const int id = blockIdx.x * a.cpc + chain;
         const int len = id < a.n_ids ? __ldg(a.len + id) : 0;
         const int cbase = id < a.n_ids ? __ldg(a.base + id) : 0;
+        const int* chain_order = a.order + cbase;
 
-        // chain-list window: 64 consecutive entries of the chain, slid by 32 (see the refill below)
-        if (tid < ST_IDX_WIN) s_idx[tid] = tid < len ? __ldg(a.order + cbase + tid) : 0;
-        team_bar(bar_id);
+        if (role < a.n_sim) {
+            // =========================== sim warp ===========================
+            // rows t = role, role + n_sim, ...; t == len is the task that only counts the last gap
+            for (int t = role; t <= len && len > 0; t += a.n_sim) {
+                const bool have_row = t < len;
+                const int i = have_row ? row_index(cs, chain_order, t) : 0;
+                unsigned long long small_new[ST_MAX_SMALL_AUX] = {0, 0};
+                if (lane == 0 && have_row)
+                    for (int q = 0; q < a.n_small_aux; ++q)
+                        small_new[q] = __ldg(reinterpret_cast<const unsigned long long*>(a.small_aux[q].src + (size_t)i * 8));
 
-        // --- slot bookkeeping.  Every thread of the team tracks it identically (it only depends on uniform data);
-        //     thread 0 alone executes the TMA / bulk-group instructions.
-        uint32_t free_mask = (1u << a.n_slots) - 1u;
-        uint32_t parity = 0;                                 // per-slot mbarrier phase
-        int issued = 0;                                      // rows whose load was issued
-        int pend0 = -1, pend1 = -1;                          // slots with a bulk store in flight (oldest first)
-        unsigned long long ring = 0;                         // slot of row r at bits 4*(r & 15): <= 12 rows in flight
+                // flags between rows t-2 and t-1 of the chain (the gap that positions row t-1): requested now,
+                // looked at after the similarity
+                const int r = t - 1;
+                const int i_r = r >= 0 ? row_index(cs, chain_order, r) : 0;
+                const int i_r1 = r >= 1 ? row_index(cs, chain_order, r - 1) : -1;
+                const int f_lo = i_r1 + 1, f_hi = i_r;
+                const int f_al = f_lo & ~15;
+                const int f_at0 = f_al + lane * 16, f_at1 = f_at0 + 512;
+                const bool f_two = r >= 0 && (f_hi - f_al) <= 1024;          // the gap fits the two early loads
+                uint4 fl0 = make_uint4(0, 0, 0, 0), fl1 = fl0;
+                if (f_two && f_at0 < f_hi) fl0 = ld_flags16(a.state + f_at0);
+                if (f_two && f_at1 < f_hi) fl1 = ld_flags16(a.state + f_at1);
 
-        uint32_t tx_bytes = (uint32_t)a.row_bytes;
-        for (int q = 0; q < a.n_tma_aux; ++q) tx_bytes += (uint32_t)a.tma_aux[q].bytes;
-
-        auto issue_loads = [&](int upto) {                   // prefetch rows while slots are free
-            while (issued < len && issued < upto && free_mask) {
-                const int s = __ffs(free_mask) - 1;
-                free_mask &= ~(1u << s);
-                if (tid == 0) {
-                    const int i = s_idx[issued & (ST_IDX_WIN - 1)];
-                    const uint32_t bar = smem_u32(bars + s);
-                    const uint32_t dst = smem_u32(slots + (size_t)s * a.slot_bytes);
-                    mbar_expect_tx(bar, tx_bytes);
-                    tma_load(dst, a.hidden + (size_t)i * a.row_bytes, (uint32_t)a.row_bytes, bar);
-                    for (int q = 0; q < a.n_tma_aux; ++q)
-                        tma_load(dst + a.tma_aux[q].slot_off, a.tma_aux[q].src + (size_t)i * a.tma_aux[q].bytes,
-                                 (uint32_t)a.tma_aux[q].bytes, bar);
-                }
-                const int sh = 4 * (issued & 15);
-                ring = (ring & ~(0xfull << sh)) | ((unsigned long long)s << sh);
-                ++issued;
-            }
-        };
-        auto retire_oldest = [&]() {                         // frees the slot of the oldest bulk store once it was read
-            if (pend0 < 0) return;
-            if (pend1 < 0) { if (tid == 0) tma_wait_read_0(); }
-            else { if (tid == 0) tma_wait_read_1(); }
-            free_mask |= 1u << pend0;
-            pend0 = pend1;
-            pend1 = -1;
-        };
-
-        // chain state (uniform across the team)
-        int acc_slot = -1, last_slot = -1;                   // pending anchor / previous row of the chain
-        int L = 0;                                           // members merged into the pending anchor
-        int anchor_t = -1, anchor_i = -1;                    // its chain position and sequence index
-        int anchor_pos = -1;                                 // its compacted position (-1: not known yet)
-        float n_last = 0.f;                                  // |last|^2
-        int cnt = 0;                                         // kept rows in [0, i_r) after the scan step of row r
-        uint32_t kept_hist = 0;                              // bit (t & 31): row t of the chain was kept
-        uint32_t q_fin = 0, q_slot4 = 0;                     // closed anchors waiting for their position, by (t & 7)
-        int kept_idx = 0;                                    // kept rows of this chain written so far (next-call list position)
-        uint64_t small_acc[ST_MAX_SMALL_AUX] = {0, 0};       // thread 0: 8-byte aux values of the pending anchor
-
-        issue_loads(20);
-        int phase = 0;
-
-        // one kept row, final in its slot, goes to its compacted position; uniform call
-        auto write_row = [&](int slot, int t_a, int i_a, int pos) {
-            if (pend1 >= 0) retire_oldest();                 // at most two stores in flight
-            if (tid == 0) {
-                const uint32_t src = smem_u32(slots + (size_t)slot * a.slot_bytes);
-                tma_store(a.out + (size_t)pos * a.row_bytes, src, (uint32_t)a.row_bytes);
-                for (int q = 0; q < a.n_tma_aux; ++q)
-                    tma_store(a.tma_aux[q].dst + (size_t)pos * a.tma_aux[q].bytes, src + a.tma_aux[q].slot_off,
-                              (uint32_t)a.tma_aux[q].bytes);
-                tma_commit();
-                for (int q = 0; q < a.n_small_aux; ++q)
-                    *reinterpret_cast<uint64_t*>(a.small_aux[q].dst + (size_t)pos * 8) = q_small[(t_a & 7) * ST_MAX_SMALL_AUX + q];
-                a.dst[i_a] = pos;
-                a.order_next[cbase + kept_idx] = pos;
-            }
-            if (pend0 < 0) pend0 = slot; else pend1 = slot;
-            ++kept_idx;
-        };
-
-        // the run of the pending anchor is over: average it (main.py:314-317) and write it, or park it until its
-        // position is known; uniform call
-        auto close_anchor = [&]() {
-            if (L > 0) {
-                unsigned char* arow = slots + (size_t)acc_slot * a.slot_bytes;
-                const Divider<DT> dv(L + 1);
-#pragma unroll
-                for (int k = 0; k < VPT; ++k) {
-                    const int v = tid + ST_NT * k;
-                    if (v < a.nvec) {
-                        uint4* p = reinterpret_cast<uint4*>(arow) + v;
-                        *p = dv.vec(*p);
+                int s_cur = -1, s_last = -1;
+                if (have_row) {
+                    // ---- the row and its predecessor: slots and arrival
+                    int e_cur = 0, e_last = 0;
+                    if (lane == 0) {
+                        e_cur = ring_wait(&cs->slot_of[t & (ST_RING - 1)], t + 1, 8);
+                        if (t > 0) e_last = ring_wait(&cs->slot_of[(t - 1) & (ST_RING - 1)], t, 8);
                     }
-                }
-                fence_async_smem();
-                team_bar(bar_id);
-            }
-            if (tid == 0)
-                for (int q = 0; q < a.n_small_aux; ++q) q_small[(anchor_t & 7) * ST_MAX_SMALL_AUX + q] = small_acc[q];
-            if (anchor_pos >= 0) {
-                write_row(acc_slot, anchor_t, anchor_i, anchor_pos);
-            } else {
-                const int sh = 4 * (anchor_t & 7);
-                q_fin |= 1u << (anchor_t & 7);
-                q_slot4 = (q_slot4 & ~(0xfu << sh)) | ((uint32_t)acc_slot << sh);
-            }
-        };
-
-        // counts the kept rows in (from, to) exclusive, waiting until every flag there is published
-        auto scan_between = [&](int from, int to) -> int {
-            const int lo = from + 1, hi = to;
-            if (hi <= lo) return 0;
-            const int lo_al = lo & ~15;
-            int total = 0;
-            for (int chunk = lo_al; chunk < hi; chunk += ST_NT * 16) {
-                const int at = chunk + tid * 16;
-                for (;;) {
-                    bool ok = true;
-                    int kept = 0;
-                    if (at < hi) kept = count_kept16(a.state, at, lo, hi, tag4, &ok);
-                    kept = warp_sum_int(kept);
-                    const int wok = __all_sync(FULL, ok);
-                    if (lane == 0) { xc->kept[phase][tw] = kept; xc->ok[phase][tw] = wok; }
-                    team_bar(bar_id);
-                    int k2 = 0, o2 = 1;
-#pragma unroll
-                    for (int w = 0; w < ST_TEAM_WARPS; ++w) { k2 += xc->kept[phase][w]; o2 &= xc->ok[phase][w]; }
-                    phase ^= 1;
-                    if (o2) { total += k2; break; }
-                    __nanosleep(100);
-                }
-            }
-            return total;
-        };
-
-        for (int t = 0; t < len + K; ++t) {
-            // slide the chain-list window: entries older than t - 8 make room for [t + 24, t + 56)
-            if ((t & 31) == 8 && t >= 40) {
-                const int e = t + 24 + tid;
-                if (tid < 32) s_idx[e & (ST_IDX_WIN - 1)] = e < len ? __ldg(a.order + cbase + e) : 0;
-                // visible to thread 0 after the next team barrier; loads are issued at most 20 rows ahead
-            }
-            const bool have_row = t < len;
-            const int r = t - K;                             // the row whose position this iteration settles
-            const int i = s_idx[t & (ST_IDX_WIN - 1)];
-            const int s = (int)((ring >> (4 * (t & 15))) & 0xfull);
-            unsigned char* crow = slots + (size_t)s * a.slot_bytes;
-
-            // small aux rows of this token: issued now, consumed after the row arrived
-            uint64_t small_new[ST_MAX_SMALL_AUX] = {0, 0};
-            if (tid == 0 && have_row)
-                for (int q = 0; q < a.n_small_aux; ++q)
-                    small_new[q] = __ldg(reinterpret_cast<const uint64_t*>(a.small_aux[q].src + (size_t)i * 8));
-
-            // flags between rows r-1 and r of the chain: loaded now, looked at after the similarity, so that the L2
-            // round trip hides behind the arrival of the row and the arithmetic
-            const int i_r = r >= 0 ? s_idx[r & (ST_IDX_WIN - 1)] : 0;
-            const int i_r1 = r >= 1 ? s_idx[(r - 1) & (ST_IDX_WIN - 1)] : -1;
-            const int f_lo = i_r1 + 1, f_hi = i_r;
-            const int f_at = (f_lo & ~15) + tid * 16;
-            const bool f_mine = r >= 0 && f_at < f_hi;
-            const bool f_one_chunk = (f_hi - (f_lo & ~15)) <= ST_NT * 16;
-            uint4 fl = make_uint4(0, 0, 0, 0);
-            if (f_mine) fl = ld_flags16(a.state + f_at);
-
-            float2 dot2 = make_float2(0.f, 0.f), nb2 = make_float2(0.f, 0.f);
-            if (have_row) {
-                mbar_wait(smem_u32(bars + s), (parity >> s) & 1u);
-                parity ^= 1u << s;
-                // ---- similarity with the previous row of the chain (main.py:345-349 rounding chain)
-                if (t > 0) {
-                    const unsigned char* lrow = slots + (size_t)last_slot * a.slot_bytes;
-#pragma unroll
-                    for (int k = 0; k < VPT; ++k) {
-                        const int v = tid + ST_NT * k;
-                        if (v < a.nvec) {
-                            const uint4 x = reinterpret_cast<const uint4*>(lrow)[v];
-                            const uint4 y = reinterpret_cast<const uint4*>(crow)[v];
-                            acc_dot_norm<DT>(x, y, dot2, nb2);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < VPT; ++k) {
-                        const int v = tid + ST_NT * k;
-                        if (v < a.nvec) acc_norm<DT>(reinterpret_cast<const uint4*>(crow)[v], nb2);
-                    }
-                }
-            }
-            bool f_ok = true;
-            int f_kept = 0;
-            if (f_mine) f_kept = count_kept_vec(fl, f_at, f_lo, f_hi, tag4, &f_ok);
-            const float dot = warp_sum(dot2.x + dot2.y);
-            const float nb = warp_sum(nb2.x + nb2.y);
-            f_kept = warp_sum_int(f_kept);
-            const int f_wok = __all_sync(FULL, f_ok);
-            if (lane == 0) { xc->dot[phase][tw] = dot; xc->nrm[phase][tw] = nb; xc->kept[phase][tw] = f_kept; xc->ok[phase][tw] = f_wok; }
-            team_bar(bar_id);
-            float dsum = 0.f, nsum = 0.f;
-            int ksum = 0, oksum = 1;
-#pragma unroll
-            for (int w = 0; w < ST_TEAM_WARPS; ++w) {
-                dsum += xc->dot[phase][w]; nsum += xc->nrm[phase][w]; ksum += xc->kept[phase][w]; oksum &= xc->ok[phase][w];
-            }
-            phase ^= 1;
-
-            if (have_row) {
-                int hit = 0;
-                float sim = -2.0f;
-                if (t > 0) {
-                    sim = finish_cosine<DT>(dsum, n_last, nsum);
-                    hit = sim >= a.thr;
-                }
-                if (tid == 0) {
-                    a.sim_seq[i] = sim;
-                    st_flag(a.state + i, (a.tag << 1) | (unsigned)hit);
-                    if (hit) a.dst[i] = -1;
-                }
-                my_hits += hit;
-
-                // ---- merge into the pending anchor, or close its run and open a new one
-                if (hit) {
-                    unsigned char* arow = slots + (size_t)acc_slot * a.slot_bytes;
-#pragma unroll
-                    for (int k = 0; k < VPT; ++k) {
-                        const int v = tid + ST_NT * k;
-                        if (v < a.nvec) {
-                            uint4* p = reinterpret_cast<uint4*>(arow) + v;
-                            *p = add_round<DT>(*p, reinterpret_cast<const uint4*>(crow)[v]);
-                        }
-                    }
-                    fence_async_smem();                      // ordered before the bulk store by a later team barrier
-                    if (L > 0) free_mask |= 1u << last_slot; // nobody reads the old `last` any more
-                    ++L;
-                } else {
+                    e_cur = __shfl_sync(FULL, e_cur, 0);
+                    e_last = __shfl_sync(FULL, e_last, 0);
+                    s_cur = e_cur & 15;
+                    mbar_wait(smem_u32(&cs->bars[s_cur]), (e_cur >> 4) & 1);
+                    int hit = 0;
+                    float sim = -2.0f;
                     if (t > 0) {
-                        close_anchor();
-                        if (L > 0) free_mask |= 1u << last_slot;
+                        s_last = e_last & 15;
+                        mbar_wait(smem_u32(&cs->bars[s_last]), (e_last >> 4) & 1);
+                        // ---- similarity with the previous row of the chain (main.py:345-349 rounding chain)
+                        const uint4* lrow = reinterpret_cast<const uint4*>(slots + (size_t)s_last * a.slot_bytes);
+                        const uint4* crow = reinterpret_cast<const uint4*>(slots + (size_t)s_cur * a.slot_bytes);
+                        float2 dot2 = make_float2(0.f, 0.f), na2 = dot2, nb2 = dot2;
+#pragma unroll
+                        for (int k = 0; k < VPL; ++k) {
+                            const int v = lane + 32 * k;
+                            if (v < a.nvec) acc_pair2<DT>(lrow[v], crow[v], dot2, na2, nb2);
+                        }
+                        const float dot = warp_sum(dot2.x + dot2.y);
+                        const float na = warp_sum(na2.x + na2.y);
+                        const float nb = warp_sum(nb2.x + nb2.y);
+                        sim = finish_cosine<DT>(dot, na, nb);
+                        hit = sim >= a.thr;
                     }
-                    acc_slot = s;
+                    if (lane == 0) {
+                        st_flag(a.state + i, (a.tag << 1) | (unsigned)hit);
+                        a.sim_seq[i] = sim;
+                        if (hit) a.dst[i] = -1;
+                        for (int q = 0; q < a.n_small_aux; ++q) cs->small[t & (ST_RING - 1)][q] = small_new[q];
+                        __threadfence_block();
+                        *(volatile int*)&cs->hit[t & (ST_RING - 1)] = ((t + 1) << 8) | hit;
+                    }
+                }
+
+                // ---- gap count for row r = t - 1
+                if (r >= 0) {
+                    int kept = 0;
+                    bool ok = f_two;
+                    if (f_two) {
+                        if (f_at0 < f_hi) kept += count_kept_vec(fl0, f_at0, f_lo, f_hi, tag4, &ok);
+                        if (f_at1 < f_hi) kept += count_kept_vec(fl1, f_at1, f_lo, f_hi, tag4, &ok);
+                    }
+                    if (__all_sync(FULL, ok)) {
+                        kept = warp_sum_int(kept);
+                    } else {
+                        // some flag was not published yet, or the gap is long: walk it 512 bytes at a time
+                        kept = 0;
+                        for (int chunk = f_al; chunk < f_hi; chunk += 512) {
+                            const int at = chunk + lane * 16;
+                            for (;;) {
+                                bool ok2 = true;
+                                int k2 = 0;
+                                if (at < f_hi) k2 = count_kept16(a.state, at, f_lo, f_hi, tag4, &ok2);
+                                if (__all_sync(FULL, ok2)) { kept += warp_sum_int(k2); break; }
+                                __nanosleep(300);
+                            }
+                        }
+                    }
+                    if (lane == 0) *(volatile int*)&cs->gap[r & (ST_RING - 1)] = (((r + 1) & 0x7ff) << 20) | kept;
+                }
+
+                // ---- references: this row as "current", the previous one as "previous"
+                if (lane == 0) {
+                    if (have_row) release_slot(a, cs, chain_order, slots, s_cur, len, tx_bytes);
+                    if (have_row && t > 0) release_slot(a, cs, chain_order, slots, s_last, len, tx_bytes);
+                }
+            }
+        } else {
+            // =========================== merge warp ===========================
+            if (lane == 0)
+                for (int b = 0; b < a.n_slots && b < len; ++b) issue_row(a, cs, chain_order, slots, b, len, tx_bytes);
+
+            uint4 acc[VPL];                                  // the pending anchor
+            uint4 auxr[ST_MAX_TMA_AUX];                      // its cos / sin rows: vector `lane` of every entry
+            unsigned long long small_acc[ST_MAX_SMALL_AUX] = {0, 0};
+            int L = 0, anchor_t = -1, anchor_i = -1, anchor_pos = -1;
+            int cnt = 0;                                     // kept rows in [0, i_r) for the last r processed
+            int kept_prev = 0, kept_prev2 = 0;               // rows t-1, t-2 were kept
+            int kept_idx = 0, hits = 0;
+
+            auto flush = [&]() {                             // the pending anchor goes to its compacted position
+                if (L > 0) {
+                    const Divider<DT> dv(L + 1);
+#pragma unroll
+                    for (int k = 0; k < VPL; ++k) acc[k] = dv.vec(acc[k]);
+                }
+                char* orow = a.out + (size_t)anchor_pos * a.row_bytes;
+#pragma unroll
+                for (int k = 0; k < VPL; ++k) {
+                    const int v = lane + 32 * k;
+                    if (v < a.nvec) st_stream16(orow + (size_t)v * 16, acc[k]);
+                }
+#pragma unroll
+                for (int q = 0; q < ST_MAX_TMA_AUX; ++q)
+                    if (q < a.n_tma_aux && lane * 16 < a.tma_aux[q].bytes)
+                        st_stream16(a.tma_aux[q].dst + (size_t)anchor_pos * a.tma_aux[q].bytes + lane * 16, auxr[q]);
+                if (lane == 0) {
+                    for (int q = 0; q < a.n_small_aux; ++q)
+                        *reinterpret_cast<unsigned long long*>(a.small_aux[q].dst + (size_t)anchor_pos * 8) = small_acc[q];
+                    a.dst[anchor_i] = anchor_pos;
+                    a.order_next[cbase + kept_idx] = anchor_pos;
+                }
+                ++kept_idx;
+            };
+            auto take_gap = [&](int r) {                     // cnt becomes the number of kept rows in [0, i_r)
+                int g = 0;
+                if (lane == 0) g = ring_wait(&cs->gap[r & (ST_RING - 1)], (r + 1) & 0x7ff, 20) & 0xfffff;
+                g = __shfl_sync(FULL, g, 0);
+                cnt += kept_prev2 + g;
+            };
+
+            for (int t = 0; t < len; ++t) {
+                int e_hit = 0, e_slot = 0;
+                if (lane == 0) {
+                    e_hit = ring_wait(&cs->hit[t & (ST_RING - 1)], t + 1, 8);
+                    e_slot = *(volatile int*)&cs->slot_of[t & (ST_RING - 1)];
+                }
+                e_hit = __shfl_sync(FULL, e_hit, 0);
+                e_slot = __shfl_sync(FULL, e_slot, 0);
+                const int hit = e_hit & 1, s = e_slot & 15;
+                mbar_wait(smem_u32(&cs->bars[s]), (e_slot >> 4) & 1);      // complete long ago: orders our reads after the TMA writes
+                __threadfence_block();
+                const unsigned char* crow = slots + (size_t)s * a.slot_bytes;
+
+                if (t > 0) {
+                    // position of row t-1 (its gap was counted by the sim warp of row t, whose flag we just saw...
+                    // not necessarily its gap: wait for it)
+                    kept_prev2 = t >= 2 ? kept_prev2 : 0;
+                    take_gap(t - 1);
+                    if (anchor_t == t - 1) anchor_pos = cnt;
+                }
+
+                if (hit) {
+#pragma unroll
+                    for (int k = 0; k < VPL; ++k) {
+                        const int v = lane + 32 * k;
+                        if (v < a.nvec) acc[k] = add_round<DT>(acc[k], reinterpret_cast<const uint4*>(crow)[v]);
+                    }
+                    ++L;
+                    ++hits;
+                } else {
+                    if (t > 0) flush();
+#pragma unroll
+                    for (int k = 0; k < VPL; ++k) {
+                        const int v = lane + 32 * k;
+                        acc[k] = v < a.nvec ? reinterpret_cast<const uint4*>(crow)[v] : make_uint4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int q = 0; q < ST_MAX_TMA_AUX; ++q)
+                        if (q < a.n_tma_aux && lane * 16 < a.tma_aux[q].bytes)
+                            auxr[q] = *reinterpret_cast<const uint4*>(crow + a.tma_aux[q].slot_off + lane * 16);
+                    if (lane == 0)
+                        for (int q = 0; q < a.n_small_aux; ++q) small_acc[q] = cs->small[t & (ST_RING - 1)][q];
                     L = 0;
                     anchor_t = t;
-                    anchor_i = i;
+                    anchor_i = row_index(cs, chain_order, t);
                     anchor_pos = -1;
-#pragma unroll
-                    for (int q = 0; q < ST_MAX_SMALL_AUX; ++q) small_acc[q] = small_new[q];
-                    kept_hist |= 1u << (t & 31);
                 }
-                if (hit) kept_hist &= ~(1u << (t & 31));
-                last_slot = s;
-                n_last = nsum;
-            } else if (t == len && len > 0) {
-                close_anchor();                              // end of the chain: the last anchor
-                if (L > 0) free_mask |= 1u << last_slot;
-                anchor_t = -1;
+                kept_prev2 = kept_prev;
+                kept_prev = !hit;
+                if (lane == 0) release_slot(a, cs, chain_order, slots, s, len, tx_bytes);
             }
-
-            // ---- position of row r: kept rows in [0, i_r).  The flags were usually all there; otherwise (or when
-            //      the gap spans more than one chunk) poll until they are.
-            if (r >= 0) {
-                if (!(oksum && f_one_chunk)) ksum = scan_between(i_r1, i_r);
-                const int prev_kept = r >= 1 ? (int)((kept_hist >> ((r - 1) & 31)) & 1u) : 0;
-                cnt += prev_kept + ksum;
-                if ((kept_hist >> (r & 31)) & 1u) {
-                    if (q_fin & (1u << (r & 7))) {
-                        q_fin &= ~(1u << (r & 7));
-                        write_row((int)((q_slot4 >> (4 * (r & 7))) & 0xfu), r, i_r, cnt);
-                    } else {
-                        anchor_pos = cnt;                    // row r is the pending anchor, still open
-                    }
-                }
+            if (len > 0) {
+                take_gap(len - 1);
+                if (anchor_t == len - 1) anchor_pos = cnt;
+                flush();
             }
-
-            if (!free_mask && issued < len) retire_oldest();
-            issue_loads(t + 1 + 20);
+            if (lane == 0) {
+                if (id < a.n_ids) a.len_next[id] = kept_idx;
+                if (hits) atomicAdd((unsigned long long*)&a.counters[C_COUNT], (unsigned long long)hits);
+            }
         }
-
-        if (tid == 0) {
-            tma_wait_all();
-            if (id < a.n_ids) a.len_next[id] = kept_idx;
-            if (my_hits) atomicAdd((unsigned long long*)&a.counters[C_COUNT], (unsigned long long)my_hits);
-        }
-    } else if (warp == n_teams * ST_TEAM_WARPS) {
+    } else if (warp == a.cpc * wpc) {
         // =========================== rows outside the chains ===========================
         const int n_text = __ldg(a.len + a.n_ids);
         const int tbase = __ldg(a.base + a.n_ids);
@@ -592,7 +593,7 @@ k_stream_merge(const StreamArgs a) {
                 bool ok = true;
                 int kept = 0;
                 if (at < i) kept = count_kept16(a.state, at, cursor, i, tag4, &ok);
-                if (!__all_sync(FULL, ok)) { __nanosleep(200); continue; }
+                if (!__all_sync(FULL, ok)) { __nanosleep(500); continue; }
                 cnt += warp_sum_int(kept);
                 at0 += 32 * 16;
                 cursor = at0 < i ? at0 : i;
@@ -658,7 +659,7 @@ k_stream_merge(const StreamArgs a) {
 }
 
 struct StreamPlan {
-    int cpc, grid, n_slots, slot_bytes, threads, lag;
+    int cpc, grid, n_slots, slot_bytes, threads, n_sim;
     size_t smem;
 };
 
@@ -666,44 +667,46 @@ struct StreamPlan {
 inline bool plan_stream(int sm_count, int max_smem, int64_t row_bytes, int n_ids, int aux_bytes, StreamPlan* p) {
     if (n_ids < 1) return false;
     const int cpc = (n_ids + sm_count - 1) / sm_count;
-    if (cpc > ST_MAX_TEAMS) return false;
+    if (cpc > ST_MAX_CHAINS) return false;
+    int n_sim = (ST_MAX_WARPS - 1) / cpc - 1;
+    if (n_sim > 3) n_sim = 3;
+    if (n_sim < 1) return false;
     const int slot = (int)((row_bytes + aux_bytes + 127) / 128 * 128);
-    const size_t fixed = (size_t)cpc * (sizeof(TeamXchg) + ST_IDX_WIN * 4 + 8 * ST_MAX_SMALL_AUX * 8) + 256;
-    const size_t static_smem = 64;
-    if ((size_t)max_smem < fixed + static_smem) return false;
-    size_t avail = (size_t)max_smem - fixed - static_smem;
-    int n_slots = (int)(avail / ((size_t)cpc * (slot + 8)));
+    const size_t fixed = (size_t)cpc * sizeof(ChainShared) + 256;
+    if ((size_t)max_smem < fixed + 64) return false;
+    const size_t avail = (size_t)max_smem - fixed - 64;
+    int n_slots = (int)(avail / ((size_t)cpc * slot));
     if (n_slots > ST_MAX_SLOTS) n_slots = ST_MAX_SLOTS;
     if (n_slots < ST_MIN_SLOTS) return false;
     p->cpc = cpc;
     p->grid = (n_ids + cpc - 1) / cpc;
     p->n_slots = n_slots;
-    p->lag = n_slots >= 7 ? 3 : (n_slots == 6 ? 2 : 1);    // worst case held: anchor + last + (lag - 1) parked + 2 stores
+    p->n_sim = n_sim;
     p->slot_bytes = slot;
-    p->threads = cpc * ST_NT + 32;
-    p->smem = (size_t)cpc * n_slots * (slot + 8) + fixed;
+    p->threads = (cpc * (n_sim + 1) + 1) * 32;
+    p->smem = (size_t)cpc * n_slots * slot + fixed;
     return true;
 }
 
-template <int DT, int VPT>
+template <int DT, int VPL>
 inline int launch_stream_t(const StreamArgs& a, const StreamPlan& p, cudaStream_t st) {
     static size_t attr_set = 0;
     if (p.smem > attr_set) {
-        if (cudaFuncSetAttribute(k_stream_merge<DT, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_stream_merge<DT, VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess)
             return FF_E_CUDA;
         attr_set = p.smem;
     }
-    k_stream_merge<DT, VPT><<<p.grid, p.threads, p.smem, st>>>(a);
+    k_stream_merge<DT, VPL><<<p.grid, p.threads, p.smem, st>>>(a);
     return cudaGetLastError() == cudaSuccess ? FF_OK : FF_E_CUDA;
 }
 
 template <int DT>
 inline int launch_stream_dt(const StreamArgs& a, const StreamPlan& p, cudaStream_t st) {
-    const int vpt = (a.nvec + ST_NT - 1) / ST_NT;
-    if (vpt <= 2) return launch_stream_t<DT, 2>(a, p, st);
-    if (vpt <= 4) return launch_stream_t<DT, 4>(a, p, st);
-    if (vpt <= 7) return launch_stream_t<DT, 7>(a, p, st);
-    return launch_stream_t<DT, 8>(a, p, st);
+    const int vpl = (a.nvec + 31) / 32;
+    if (vpl <= 4) return launch_stream_t<DT, 4>(a, p, st);
+    if (vpl <= 8) return launch_stream_t<DT, 8>(a, p, st);
+    if (vpl <= 14) return launch_stream_t<DT, 14>(a, p, st);
+    return launch_stream_t<DT, 16>(a, p, st);
 }
 
 inline int launch_stream(int dtype, const StreamArgs& a, const StreamPlan& p, cudaStream_t st) {
