@@ -325,8 +325,12 @@ __device__ __forceinline__ void issue_row(const StreamArgs& a, ChainShared* cs, 
 
 __device__ __forceinline__ void release_slot(const StreamArgs& a, ChainShared* cs, const int* chain_order, unsigned char* slots,
                                              int slot, int len, uint32_t tx_bytes) {
-    __threadfence_block();
-    if (atomicSub(&cs->refcnt[slot], 1) == 1) issue_row(a, cs, chain_order, slots, slot, len, tx_bytes);
+    __threadfence_block();                                  // our reads of the slot are done before the count drops
+    if (atomicSub(&cs->refcnt[slot], 1) == 1) {
+        __threadfence_block();                              // ... and everybody else's before the TMA engine overwrites it
+        fence_async_smem();
+        issue_row(a, cs, chain_order, slots, slot, len, tx_bytes);
+    }
 }
 
 template <int DT, int VPL>
@@ -462,6 +466,7 @@ k_stream_merge(const StreamArgs a) {
                 }
 
                 // ---- references: this row as "current", the previous one as "previous"
+                __syncwarp();
                 if (lane == 0) {
                     if (have_row) release_slot(a, cs, chain_order, slots, s_cur, len, tx_bytes);
                     if (have_row && t > 0) release_slot(a, cs, chain_order, slots, s_last, len, tx_bytes);
@@ -560,6 +565,7 @@ k_stream_merge(const StreamArgs a) {
                 }
                 kept_prev2 = kept_prev;
                 kept_prev = !hit;
+                __syncwarp();
                 if (lane == 0) release_slot(a, cs, chain_order, slots, s, len, tx_bytes);
             }
             if (len > 0) {
