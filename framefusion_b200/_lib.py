@@ -23,7 +23,7 @@ ST_SLOTS = 16
 EXPORTS = [
     "ff_abi_version", "ff_last_error", "ff_launch_count", "ff_ctx_create", "ff_ctx_destroy", "ff_ctx_status", "ff_workspace_bytes",
     "ff_build_links", "ff_similarity", "ff_merge_apply", "ff_merge_layer", "ff_importance", "ff_prune_layer",
-    "ff_compact_mask", "ff_debug_read",
+    "ff_compact_mask", "ff_debug_read", "ff_debug_trace",
 ]
 
 
@@ -71,6 +71,7 @@ def load():
     lib.ff_prune_layer.argtypes = [_vp, _vp, _i64, _vp, _i64, _vp, _vp, C.c_int, _i64, _i64, _i64, _i64, _i64,
                                    C.POINTER(FFAux), C.c_int, _vp, _vp]
     lib.ff_compact_mask.argtypes = [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp]
+    lib.ff_debug_trace.argtypes = [_vp, _vp, _i64, _i64]
     lib.ff_debug_read.argtypes = [_vp, _vp, _i64, C.c_int, _vp, _i64, C.c_int, _vp]
     for name in EXPORTS:
         fn = getattr(lib, name)

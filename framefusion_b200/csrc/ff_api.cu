@@ -54,6 +54,7 @@ struct ff_ctx {
     unsigned epoch;      // single-pass calls since ff_build_links (tags the flag bytes)
     int sm_count;
     int max_smem;        // opt-in dynamic shared memory per block
+    long long* trace;    // development aid: device buffer for the single-pass kernel's time stamps (ff_debug_trace)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -300,6 +301,7 @@ bool plan_stream_args(const ff_ctx* ctx, const Ws& w, int bank, const void* hidd
     a.n_ids = (int)ctx->n_ids;
     a.cpc = plan->cpc;
     a.n_sim = plan->n_sim;
+    a.lag = plan->lag;
     a.order = w.order[bank];
     a.base = w.base;
     a.len = w.len[bank];
@@ -314,6 +316,7 @@ bool plan_stream_args(const ff_ctx* ctx, const Ws& w, int bank, const void* hidd
     a.thr = (float)thr;
     a.bound = bound;
     a.tag = 1;
+    a.trace = ctx->trace;
     return true;
 }
 
@@ -342,6 +345,7 @@ int ff_ctx_create(int device, ff_ctx** out) {
     c->n_ids = 0;
     c->have_order = c->have_lists = 0;
     c->epoch = 0;
+    c->trace = nullptr;
     cudaError_t e = cudaHostAlloc((void**)&c->h_status, FF_ST_SLOTS * 8, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e != cudaSuccess) { delete c; return fail(FF_E_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
     memset(c->h_status, 0, FF_ST_SLOTS * 8);
@@ -635,6 +639,14 @@ int ff_compact_mask(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* mask, v
         default: return fail(FF_E_BADARG, "elem_bytes %lld", (long long)elem_bytes);
     }
     FF_LAUNCH_CHECK("k_compact_mask");
+    return FF_OK;
+}
+
+int ff_debug_trace(ff_ctx* ctx, void* buffer_device, int64_t bytes, int64_t n_ids) {
+    if (!ctx) return fail(FF_E_BADARG, "null ctx");
+    if (buffer_device && bytes < n_ids * ST_TRACE_T * ST_TRACE_K * 8)
+        return fail(FF_E_WORKSPACE, "trace buffer needs %lld bytes", (long long)(n_ids * ST_TRACE_T * ST_TRACE_K * 8));
+    ctx->trace = (long long*)buffer_device;
     return FF_OK;
 }
 

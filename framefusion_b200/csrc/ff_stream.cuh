@@ -50,6 +50,7 @@ constexpr int ST_MAX_LEN = 256;                    // rows per chain the index w
 constexpr int ST_MAX_VPL = 16;                     // 16-byte vectors per lane: rows up to 8 KB
 constexpr int ST_MAX_TMA_AUX = 6;                  // (aux, plane) pairs carried through the slot, <= 512 bytes each
 constexpr int ST_MAX_SMALL_AUX = 2;                // 8-byte aux rows (patch_type, position ids)
+constexpr int ST_TRACE_T = 96, ST_TRACE_K = 8;    // development aid: rows x stamps per chain
 constexpr int ST_MAX_WARPS = 16;                   // cpc * (n_sim + 1) + 1: 512 threads leave 128 registers each
 
 struct StreamAux {
@@ -70,6 +71,7 @@ struct StreamArgs {
     int n_ids;                                     // chain buckets; bucket n_ids = rows outside the chains
     int cpc;                                       // chains per CTA
     int n_sim;                                     // sim warps per chain
+    int lag;                                       // the sim warp of row t counts the gap that positions row t - lag
     const int* order;                              // chain lists: order[base[id] + t] = sequence index
     const int* base;
     const int* len;
@@ -84,6 +86,7 @@ struct StreamArgs {
     float thr;
     double bound;
     unsigned tag;                                  // 1..127
+    long long* trace;                              // development aid: [chain][ST_TRACE_T][ST_TRACE_K] globaltimer stamps, or null
     int n_tma_aux, n_small_aux;
     StreamAux tma_aux[ST_MAX_TMA_AUX];
     StreamAux small_aux[ST_MAX_SMALL_AUX];
@@ -122,7 +125,7 @@ struct Divider {
         const bool risky = ((u & 0xffffu) - 0x7ff8u) <= 0x10u || ((u & 0x7f800000u) == 0u && (u << 1) != 0u);
         return risky ? ieee_div(x, div) : q0;
     }
-    __device__ __forceinline__ uint4 vec(const uint4& a) const {
+    __device__ __noinline__ uint4 vec(const uint4 a) const {      // out of line: called once per vector, rarely hot
         float x[Num<DT>::EPV];
         Num<DT>::unpack(a, x);
 #pragma unroll
@@ -238,6 +241,14 @@ __device__ __forceinline__ void tma_wait_read_0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// stamp k of row t of chain `id` (one lane)
+#define ST_STAMP(t, k) do { if (a.trace && (t) < ST_TRACE_T) a.trace[((size_t)id * ST_TRACE_T + (t)) * ST_TRACE_K + (k)] = gtime(); } while (0)
+
 __device__ __forceinline__ uint4 ld_flags16(const uint8_t* p) {
     uint4 r;
     asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -289,7 +300,7 @@ struct ChainShared {
     int refcnt[ST_MAX_SLOTS];
     int uses[ST_MAX_SLOTS];
     int issued;                                     // rows requested so far
-    int pad;
+    int chain_id;
 };
 
 __device__ __forceinline__ int ring_wait(const int* slot, int want_tag, int tag_shift) {
@@ -304,10 +315,11 @@ __device__ __forceinline__ int row_index(const ChainShared* cs, const int* chain
 }
 
 // requests the next row of the chain into `slot` (called by one lane, only by whoever freed the slot)
-__device__ __forceinline__ void issue_row(const StreamArgs& a, ChainShared* cs, const int* chain_order, unsigned char* slots,
+__device__ __noinline__ void issue_row(const StreamArgs& a, ChainShared* cs, const int* chain_order, unsigned char* slots,
                                           int slot, int len, uint32_t tx_bytes) {
     const int row = atomicAdd(&cs->issued, 1);
     if (row >= len) return;
+    if (a.trace) { const int id = cs->chain_id; ST_STAMP(row, 0); }
     const int parity = cs->uses[slot] & 1;
     cs->uses[slot] += 1;
     cs->refcnt[slot] = row + 1 < len ? 3 : 2;               // current of sim(row), previous of sim(row + 1), merge(row)
@@ -318,6 +330,7 @@ __device__ __forceinline__ void issue_row(const StreamArgs& a, ChainShared* cs, 
     const uint32_t dst = smem_u32(slots + (size_t)slot * a.slot_bytes);
     mbar_expect_tx(bar, tx_bytes);
     tma_load(dst, a.hidden + (size_t)i * a.row_bytes, (uint32_t)a.row_bytes, bar);
+#pragma unroll 1
     for (int q = 0; q < a.n_tma_aux; ++q)
         tma_load(dst + a.tma_aux[q].slot_off, a.tma_aux[q].src + (size_t)i * a.tma_aux[q].bytes,
                  (uint32_t)a.tma_aux[q].bytes, bar);
@@ -333,9 +346,9 @@ __device__ __forceinline__ void release_slot(const StreamArgs& a, ChainShared* c
     }
 }
 
-template <int DT, int VPL>
+template <int DT>
 __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1)
-k_stream_merge(const StreamArgs a) {
+k_stream_merge(const __grid_constant__ StreamArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int s_last_cta;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -345,6 +358,7 @@ k_stream_merge(const StreamArgs a) {
 
     ChainShared* cs_base = reinterpret_cast<ChainShared*>(smem + (size_t)a.cpc * a.n_slots * a.slot_bytes);
     uint32_t tx_bytes = (uint32_t)a.row_bytes;
+#pragma unroll 1
     for (int q = 0; q < a.n_tma_aux; ++q) tx_bytes += (uint32_t)a.tma_aux[q].bytes;
 
     // ---- set-up: the merge warp of every chain fills the chain's shared state
@@ -358,6 +372,7 @@ k_stream_merge(const StreamArgs a) {
         if (lane < ST_MAX_SLOTS) { cs->refcnt[lane] = 0; cs->uses[lane] = 0; }
         if (lane == 0) {
             cs->issued = 0;
+            cs->chain_id = id;
             for (int b = 0; b < a.n_slots; ++b) mbar_init(smem_u32(&cs->bars[b]), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -374,18 +389,20 @@ k_stream_merge(const StreamArgs a) {
 
         if (role < a.n_sim) {
             // =========================== sim warp ===========================
-            // rows t = role, role + n_sim, ...; t == len is the task that only counts the last gap
-            for (int t = role; t <= len && len > 0; t += a.n_sim) {
+            // rows t = role, role + n_sim, ...; tasks t >= len only count the last gaps
+            const int K = a.lag;
+            for (int t = role; t < len + K && len > 0; t += a.n_sim) {
                 const bool have_row = t < len;
                 const int i = have_row ? row_index(cs, chain_order, t) : 0;
                 unsigned long long small_new[ST_MAX_SMALL_AUX] = {0, 0};
                 if (lane == 0 && have_row)
+#pragma unroll 1
                     for (int q = 0; q < a.n_small_aux; ++q)
                         small_new[q] = __ldg(reinterpret_cast<const unsigned long long*>(a.small_aux[q].src + (size_t)i * 8));
 
-                // flags between rows t-2 and t-1 of the chain (the gap that positions row t-1): requested now,
-                // looked at after the similarity
-                const int r = t - 1;
+                // flags between rows r-1 and r of the chain, r = t - lag (the gap that positions row r; by now every
+                // chain is past it): requested now, looked at after the similarity
+                const int r = t - K;
                 const int i_r = r >= 0 ? row_index(cs, chain_order, r) : 0;
                 const int i_r1 = r >= 1 ? row_index(cs, chain_order, r - 1) : -1;
                 const int f_lo = i_r1 + 1, f_hi = i_r;
@@ -397,6 +414,7 @@ k_stream_merge(const StreamArgs a) {
                 if (f_two && f_at1 < f_hi) fl1 = ld_flags16(a.state + f_at1);
 
                 int s_cur = -1, s_last = -1;
+                if (lane == 0 && have_row) ST_STAMP(t, 1);                       // sim task starts
                 if (have_row) {
                     // ---- the row and its predecessor: slots and arrival
                     int e_cur = 0, e_last = 0;
@@ -410,6 +428,7 @@ k_stream_merge(const StreamArgs a) {
                     mbar_wait(smem_u32(&cs->bars[s_cur]), (e_cur >> 4) & 1);
                     int hit = 0;
                     float sim = -2.0f;
+                    if (lane == 0) ST_STAMP(t, 2);                                   // row arrived
                     if (t > 0) {
                         s_last = e_last & 15;
                         mbar_wait(smem_u32(&cs->bars[s_last]), (e_last >> 4) & 1);
@@ -417,11 +436,8 @@ k_stream_merge(const StreamArgs a) {
                         const uint4* lrow = reinterpret_cast<const uint4*>(slots + (size_t)s_last * a.slot_bytes);
                         const uint4* crow = reinterpret_cast<const uint4*>(slots + (size_t)s_cur * a.slot_bytes);
                         float2 dot2 = make_float2(0.f, 0.f), na2 = dot2, nb2 = dot2;
-#pragma unroll
-                        for (int k = 0; k < VPL; ++k) {
-                            const int v = lane + 32 * k;
-                            if (v < a.nvec) acc_pair2<DT>(lrow[v], crow[v], dot2, na2, nb2);
-                        }
+#pragma unroll 2                                                 // rolled: the I-cache is 32 KB, every role must stay small
+                        for (int v = lane; v < a.nvec; v += 32) acc_pair2<DT>(lrow[v], crow[v], dot2, na2, nb2);
                         const float dot = warp_sum(dot2.x + dot2.y);
                         const float na = warp_sum(na2.x + na2.y);
                         const float nb = warp_sum(nb2.x + nb2.y);
@@ -432,13 +448,15 @@ k_stream_merge(const StreamArgs a) {
                         st_flag(a.state + i, (a.tag << 1) | (unsigned)hit);
                         a.sim_seq[i] = sim;
                         if (hit) a.dst[i] = -1;
+#pragma unroll 1
                         for (int q = 0; q < a.n_small_aux; ++q) cs->small[t & (ST_RING - 1)][q] = small_new[q];
                         __threadfence_block();
                         *(volatile int*)&cs->hit[t & (ST_RING - 1)] = ((t + 1) << 8) | hit;
+                        ST_STAMP(t, 3);                                              // flag published
                     }
                 }
 
-                // ---- gap count for row r = t - 1
+                // ---- gap count for row r = t - lag
                 if (r >= 0) {
                     int kept = 0;
                     bool ok = f_two;
@@ -458,11 +476,12 @@ k_stream_merge(const StreamArgs a) {
                                 int k2 = 0;
                                 if (at < f_hi) k2 = count_kept16(a.state, at, f_lo, f_hi, tag4, &ok2);
                                 if (__all_sync(FULL, ok2)) { kept += warp_sum_int(k2); break; }
-                                __nanosleep(300);
+                                __nanosleep(200);
                             }
                         }
                     }
                     if (lane == 0) *(volatile int*)&cs->gap[r & (ST_RING - 1)] = (((r + 1) & 0x7ff) << 20) | kept;
+                    if (lane == 0 && have_row) ST_STAMP(t, 4);                       // gap of row t - lag counted
                 }
 
                 // ---- references: this row as "current", the previous one as "previous"
@@ -477,43 +496,57 @@ k_stream_merge(const StreamArgs a) {
             if (lane == 0)
                 for (int b = 0; b < a.n_slots && b < len; ++b) issue_row(a, cs, chain_order, slots, b, len, tx_bytes);
 
-            uint4 acc[VPL];                                  // the pending anchor
-            uint4 auxr[ST_MAX_TMA_AUX];                      // its cos / sin rows: vector `lane` of every entry
+            // The pending anchor lives in ITS OWN slot: flagged successors are added into it in place.  Nobody else
+            // reads that slot any more — its readers were sim(anchor) and sim(anchor + 1), and merge(anchor + 1) only
+            // starts after sim(anchor + 1) has published its flag.  The merge warp keeps its reference until the flush.
             unsigned long long small_acc[ST_MAX_SMALL_AUX] = {0, 0};
-            int L = 0, anchor_t = -1, anchor_i = -1, anchor_pos = -1;
-            int cnt = 0;                                     // kept rows in [0, i_r) for the last r processed
-            int kept_prev = 0, kept_prev2 = 0;               // rows t-1, t-2 were kept
+            int L = 0, anchor_t = -1, anchor_i = -1, anchor_pos = -1, anchor_slot = -1;
+            int cnt = 0;                                     // kept rows in [0, i_r), r = gaps_taken - 1
+            int gaps_taken = 0;                              // gap counts consumed so far (rows 0 .. gaps_taken - 1 are positioned)
+            uint32_t kept_hist = 0;                          // bit (t & 31): row t of the chain was kept
             int kept_idx = 0, hits = 0;
 
             auto flush = [&]() {                             // the pending anchor goes to its compacted position
-                if (L > 0) {
-                    const Divider<DT> dv(L + 1);
-#pragma unroll
-                    for (int k = 0; k < VPL; ++k) acc[k] = dv.vec(acc[k]);
-                }
+                const unsigned char* arow = slots + (size_t)anchor_slot * a.slot_bytes;
                 char* orow = a.out + (size_t)anchor_pos * a.row_bytes;
-#pragma unroll
-                for (int k = 0; k < VPL; ++k) {
-                    const int v = lane + 32 * k;
-                    if (v < a.nvec) st_stream16(orow + (size_t)v * 16, acc[k]);
+                if (L > 0) {                                 // average of the run (main.py:314-317)
+                    const Divider<DT> dv(L + 1);
+#pragma unroll 1
+                    for (int v = lane; v < a.nvec; v += 32)
+                        st_stream16(orow + (size_t)v * 16, dv.vec(reinterpret_cast<const uint4*>(arow)[v]));
+                } else {
+#pragma unroll 2
+                    for (int v = lane; v < a.nvec; v += 32)
+                        st_stream16(orow + (size_t)v * 16, reinterpret_cast<const uint4*>(arow)[v]);
                 }
-#pragma unroll
-                for (int q = 0; q < ST_MAX_TMA_AUX; ++q)
-                    if (q < a.n_tma_aux && lane * 16 < a.tma_aux[q].bytes)
-                        st_stream16(a.tma_aux[q].dst + (size_t)anchor_pos * a.tma_aux[q].bytes + lane * 16, auxr[q]);
+#pragma unroll 1
+                for (int q = 0; q < a.n_tma_aux; ++q)
+                    if (lane * 16 < a.tma_aux[q].bytes)
+                        st_stream16(a.tma_aux[q].dst + (size_t)anchor_pos * a.tma_aux[q].bytes + lane * 16,
+                                    *reinterpret_cast<const uint4*>(arow + a.tma_aux[q].slot_off + lane * 16));
                 if (lane == 0) {
+#pragma unroll 1
                     for (int q = 0; q < a.n_small_aux; ++q)
                         *reinterpret_cast<unsigned long long*>(a.small_aux[q].dst + (size_t)anchor_pos * 8) = small_acc[q];
                     a.dst[anchor_i] = anchor_pos;
                     a.order_next[cbase + kept_idx] = anchor_pos;
                 }
                 ++kept_idx;
+                __syncwarp();
+                if (lane == 0) release_slot(a, cs, chain_order, slots, anchor_slot, len, tx_bytes);
             };
-            auto take_gap = [&](int r) {                     // cnt becomes the number of kept rows in [0, i_r)
-                int g = 0;
-                if (lane == 0) g = ring_wait(&cs->gap[r & (ST_RING - 1)], (r + 1) & 0x7ff, 20) & 0xfffff;
-                g = __shfl_sync(FULL, g, 0);
-                cnt += kept_prev2 + g;
+            // consumes gap counts up to row r: cnt becomes the number of kept rows in [0, i_r); waits for the sim warps
+            // that count them (row r's gap is counted by the task of row r + lag)
+            auto position_upto = [&](int r) {
+                while (gaps_taken <= r) {
+                    const int q = gaps_taken;
+                    int g = 0;
+                    if (lane == 0) g = ring_wait(&cs->gap[q & (ST_RING - 1)], (q + 1) & 0x7ff, 20) & 0xfffff;
+                    g = __shfl_sync(FULL, g, 0);
+                    cnt += (q >= 1 ? (int)((kept_hist >> ((q - 1) & 31)) & 1u) : 0) + g;
+                    if (q == anchor_t) anchor_pos = cnt;
+                    ++gaps_taken;
+                }
             };
 
             for (int t = 0; t < len; ++t) {
@@ -525,52 +558,41 @@ k_stream_merge(const StreamArgs a) {
                 e_hit = __shfl_sync(FULL, e_hit, 0);
                 e_slot = __shfl_sync(FULL, e_slot, 0);
                 const int hit = e_hit & 1, s = e_slot & 15;
+                if (lane == 0) ST_STAMP(t, 5);                                       // merge step starts
                 mbar_wait(smem_u32(&cs->bars[s]), (e_slot >> 4) & 1);      // complete long ago: orders our reads after the TMA writes
                 __threadfence_block();
                 const unsigned char* crow = slots + (size_t)s * a.slot_bytes;
 
-                if (t > 0) {
-                    // position of row t-1 (its gap was counted by the sim warp of row t, whose flag we just saw...
-                    // not necessarily its gap: wait for it)
-                    kept_prev2 = t >= 2 ? kept_prev2 : 0;
-                    take_gap(t - 1);
-                    if (anchor_t == t - 1) anchor_pos = cnt;
-                }
-
                 if (hit) {
-#pragma unroll
-                    for (int k = 0; k < VPL; ++k) {
-                        const int v = lane + 32 * k;
-                        if (v < a.nvec) acc[k] = add_round<DT>(acc[k], reinterpret_cast<const uint4*>(crow)[v]);
-                    }
+                    uint4* arow = reinterpret_cast<uint4*>(slots + (size_t)anchor_slot * a.slot_bytes);
+#pragma unroll 2
+                    for (int v = lane; v < a.nvec; v += 32) arow[v] = add_round<DT>(arow[v], reinterpret_cast<const uint4*>(crow)[v]);
                     ++L;
                     ++hits;
+                    kept_hist &= ~(1u << (t & 31));
+                    __syncwarp();
+                    if (lane == 0) release_slot(a, cs, chain_order, slots, s, len, tx_bytes);
                 } else {
-                    if (t > 0) flush();
-#pragma unroll
-                    for (int k = 0; k < VPL; ++k) {
-                        const int v = lane + 32 * k;
-                        acc[k] = v < a.nvec ? reinterpret_cast<const uint4*>(crow)[v] : make_uint4(0, 0, 0, 0);
+                    if (t > 0) {
+                        position_upto(anchor_t);             // may wait for the sims of the next lag - 1 rows
+                        flush();
                     }
-#pragma unroll
-                    for (int q = 0; q < ST_MAX_TMA_AUX; ++q)
-                        if (q < a.n_tma_aux && lane * 16 < a.tma_aux[q].bytes)
-                            auxr[q] = *reinterpret_cast<const uint4*>(crow + a.tma_aux[q].slot_off + lane * 16);
+                    kept_hist |= 1u << (t & 31);
+                    anchor_slot = s;                         // our reference on this slot is kept until the flush
                     if (lane == 0)
+#pragma unroll 1
                         for (int q = 0; q < a.n_small_aux; ++q) small_acc[q] = cs->small[t & (ST_RING - 1)][q];
                     L = 0;
                     anchor_t = t;
                     anchor_i = row_index(cs, chain_order, t);
                     anchor_pos = -1;
                 }
-                kept_prev2 = kept_prev;
-                kept_prev = !hit;
-                __syncwarp();
-                if (lane == 0) release_slot(a, cs, chain_order, slots, s, len, tx_bytes);
+                if (lane == 0) ST_STAMP(t, 6);                                       // merge step done
+                // keep the gap ring drained (it is ST_RING deep): rows this far behind were counted long ago
+                if (t - a.lag - 4 >= 0) position_upto(t - a.lag - 4);
             }
             if (len > 0) {
-                take_gap(len - 1);
-                if (anchor_t == len - 1) anchor_pos = cnt;
+                position_upto(len - 1);
                 flush();
             }
             if (lane == 0) {
@@ -610,6 +632,7 @@ k_stream_merge(const StreamArgs a) {
             const char* src = a.hidden + (size_t)i * a.row_bytes;
             char* o = a.out + (size_t)pos * a.row_bytes;
             for (int v = lane; v < a.nvec; v += 32) st_stream16(o + (size_t)v * 16, ld_stream16(src + (size_t)v * 16));
+#pragma unroll 1
             for (int q = 0; q < a.n_tma_aux; ++q) {
                 const StreamAux& x = a.tma_aux[q];
                 for (int v = lane; v < x.bytes / 16; v += 32)
@@ -617,6 +640,7 @@ k_stream_merge(const StreamArgs a) {
                         __ldg(reinterpret_cast<const uint4*>(x.src + (size_t)i * x.bytes) + v);
             }
             if (lane == 0) {
+#pragma unroll 1
                 for (int q = 0; q < a.n_small_aux; ++q)
                     *reinterpret_cast<uint64_t*>(a.small_aux[q].dst + (size_t)pos * 8) =
                         __ldg(reinterpret_cast<const uint64_t*>(a.small_aux[q].src + (size_t)i * 8));
@@ -665,7 +689,7 @@ k_stream_merge(const StreamArgs a) {
 }
 
 struct StreamPlan {
-    int cpc, grid, n_slots, slot_bytes, threads, n_sim;
+    int cpc, grid, n_slots, slot_bytes, threads, n_sim, lag;
     size_t smem;
 };
 
@@ -688,31 +712,23 @@ inline bool plan_stream(int sm_count, int max_smem, int64_t row_bytes, int n_ids
     p->grid = (n_ids + cpc - 1) / cpc;
     p->n_slots = n_slots;
     p->n_sim = n_sim;
+    p->lag = n_slots >= 7 ? 3 : (n_slots >= 5 ? 2 : 1);    // rows t .. t + lag - 1 stay resident while merge(t) waits
     p->slot_bytes = slot;
     p->threads = (cpc * (n_sim + 1) + 1) * 32;
     p->smem = (size_t)cpc * n_slots * slot + fixed;
     return true;
 }
 
-template <int DT, int VPL>
-inline int launch_stream_t(const StreamArgs& a, const StreamPlan& p, cudaStream_t st) {
+template <int DT>
+inline int launch_stream_dt(const StreamArgs& a, const StreamPlan& p, cudaStream_t st) {
     static size_t attr_set = 0;
     if (p.smem > attr_set) {
-        if (cudaFuncSetAttribute(k_stream_merge<DT, VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_stream_merge<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess)
             return FF_E_CUDA;
         attr_set = p.smem;
     }
-    k_stream_merge<DT, VPL><<<p.grid, p.threads, p.smem, st>>>(a);
+    k_stream_merge<DT><<<p.grid, p.threads, p.smem, st>>>(a);
     return cudaGetLastError() == cudaSuccess ? FF_OK : FF_E_CUDA;
-}
-
-template <int DT>
-inline int launch_stream_dt(const StreamArgs& a, const StreamPlan& p, cudaStream_t st) {
-    const int vpl = (a.nvec + 31) / 32;
-    if (vpl <= 4) return launch_stream_t<DT, 4>(a, p, st);
-    if (vpl <= 8) return launch_stream_t<DT, 8>(a, p, st);
-    if (vpl <= 14) return launch_stream_t<DT, 14>(a, p, st);
-    return launch_stream_t<DT, 16>(a, p, st);
 }
 
 inline int launch_stream(int dtype, const StreamArgs& a, const StreamPlan& p, cudaStream_t st) {

@@ -145,6 +145,11 @@ int ff_compact_mask(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* mask, v
 int ff_debug_read(ff_ctx* ctx, void* ws, int64_t ws_bytes, int what, void* dst_device, int64_t n, int dtype,
                   void* stream);
 
+/* ---- development aid: time stamps of the single-pass kernel -------------------------------------------
+ * buffer_device: n_ids * 96 * 8 int64 (globaltimer ns at eight points in the life of every chain row), or null
+ * to switch tracing off.  Not part of the reference-facing surface. */
+int ff_debug_trace(ff_ctx* ctx, void* buffer_device, int64_t bytes, int64_t n_ids);
+
 #ifdef __cplusplus
 }
 #endif
