@@ -51,7 +51,7 @@ constexpr int ST_MAX_VPL = 16;                     // 16-byte vectors per lane: 
 constexpr int ST_MAX_TMA_AUX = 6;                  // (aux, plane) pairs carried through the slot, <= 512 bytes each
 constexpr int ST_MAX_SMALL_AUX = 2;                // 8-byte aux rows (patch_type, position ids)
 constexpr int ST_TRACE_T = 96, ST_TRACE_K = 8;    // development aid: rows x stamps per chain
-constexpr int ST_MAX_WARPS = 16;                   // cpc * (n_sim + 1) + 1: 512 threads leave 128 registers each
+constexpr int ST_MAX_WARPS = 24;                   // cpc * n_sim + 1: 768 threads leave 80 registers each
 
 struct StreamAux {
     const char* src;
@@ -292,20 +292,29 @@ __device__ __forceinline__ int count_kept16(const uint8_t* state, int at, int lo
 // per-chain shared state (one per chain of the CTA, after the slots in dynamic shared memory)
 struct ChainShared {
     uint64_t bars[ST_MAX_SLOTS];                    // one mbarrier per slot
-    unsigned long long small[ST_RING][ST_MAX_SMALL_AUX];   // 8-byte aux values of row t at [t % ST_RING]
+    unsigned long long small[ST_RING][ST_MAX_SMALL_AUX];       // 8-byte aux values of row t at [t % ST_RING]
+    unsigned long long pend_small[ST_RING][ST_MAX_SMALL_AUX];  // ... of a closed anchor waiting for its position
+    unsigned long long anchor_small[ST_MAX_SMALL_AUX];         // ... of the open anchor
     int idx[ST_MAX_LEN];                            // sequence index of every row of the chain
     int slot_of[ST_RING];                           // ((row + 1) << 8) | (parity << 4) | slot
-    int hit[ST_RING];                               // ((row + 1) << 8) | merge flag of the row
-    int gap[ST_RING];                               // (((row + 1) & 0x7ff) << 20) | kept rows between row - 1 and row (exclusive)
+    int kc[ST_RING];                                // kept rows of this chain before row t (set in the ordered section of t)
+    int keptbit[ST_RING];                           // row t was kept
+    int pend[ST_RING];                              // closed anchor t waiting for its position: (1 << 31) | (L << 4) | slot
     int refcnt[ST_MAX_SLOTS];
     int uses[ST_MAX_SLOTS];
     int issued;                                     // rows requested so far
     int chain_id;
+    // ordered state: read and written only inside the ordered section (by whoever holds the token)
+    int token;                                      // row whose ordered section may run next
+    int anchor_t, anchor_slot, anchor_L, anchor_pos, anchor_k;   // the open anchor; anchor_k = its rank among the chain's kept rows
+    int cum;                                        // kept rows outside this chain before row r, r = the last row positioned
+    int n_kept;                                     // anchors opened so far
+    int hits;                                       // rows merged away so far
 };
 
 __device__ __forceinline__ int ring_wait(const int* slot, int want_tag, int tag_shift) {
     int v;
-    while (((unsigned)(v = *(volatile const int*)slot) >> tag_shift) != (unsigned)want_tag) __nanosleep(20);
+    while (((unsigned)(v = *(volatile const int*)slot) >> tag_shift) != (unsigned)want_tag) __nanosleep(40);
     return v;
 }
 
@@ -316,13 +325,13 @@ __device__ __forceinline__ int row_index(const ChainShared* cs, const int* chain
 
 // requests the next row of the chain into `slot` (called by one lane, only by whoever freed the slot)
 __device__ __noinline__ void issue_row(const StreamArgs& a, ChainShared* cs, const int* chain_order, unsigned char* slots,
-                                          int slot, int len, uint32_t tx_bytes) {
+                                       int slot, int len, uint32_t tx_bytes) {
     const int row = atomicAdd(&cs->issued, 1);
     if (row >= len) return;
     if (a.trace) { const int id = cs->chain_id; ST_STAMP(row, 0); }
     const int parity = cs->uses[slot] & 1;
     cs->uses[slot] += 1;
-    cs->refcnt[slot] = row + 1 < len ? 3 : 2;               // current of sim(row), previous of sim(row + 1), merge(row)
+    cs->refcnt[slot] = row + 1 < len ? 3 : 2;               // current of sim(row), previous of sim(row + 1), merge / flush
     __threadfence_block();
     *(volatile int*)&cs->slot_of[row & (ST_RING - 1)] = ((row + 1) << 8) | (parity << 4) | slot;
     const int i = row_index(cs, chain_order, row);
@@ -336,14 +345,52 @@ __device__ __noinline__ void issue_row(const StreamArgs& a, ChainShared* cs, con
                  (uint32_t)a.tma_aux[q].bytes, bar);
 }
 
+// drops `n` references of a slot; the last one out requests the next row of the chain into it (one lane)
 __device__ __forceinline__ void release_slot(const StreamArgs& a, ChainShared* cs, const int* chain_order, unsigned char* slots,
-                                             int slot, int len, uint32_t tx_bytes) {
+                                             int slot, int n, int len, uint32_t tx_bytes) {
     __threadfence_block();                                  // our reads of the slot are done before the count drops
-    if (atomicSub(&cs->refcnt[slot], 1) == 1) {
+    if (atomicSub(&cs->refcnt[slot], n) == n) {
         __threadfence_block();                              // ... and everybody else's before the TMA engine overwrites it
         fence_async_smem();
         issue_row(a, cs, chain_order, slots, slot, len, tx_bytes);
     }
+}
+
+__device__ __forceinline__ int* chain_order_next(const StreamArgs& a, const ChainShared* cs) {
+    return a.order_next + __ldg(a.base + cs->chain_id);
+}
+
+// a closed anchor, final in its slot, goes to its compacted position (whole warp); drops the anchor's reference
+template <int DT>
+__device__ __noinline__ void flush_anchor(const StreamArgs& a, ChainShared* cs, const int* chain_order, unsigned char* slots,
+                                          int slot, int L, int pos, int k, int t_a, unsigned long long sm0,
+                                          unsigned long long sm1, int len, uint32_t tx_bytes) {
+    const int lane = threadIdx.x & 31;
+    const unsigned char* arow = slots + (size_t)slot * a.slot_bytes;
+    char* orow = a.out + (size_t)pos * a.row_bytes;
+    if (L > 0) {                                            // average of the run (main.py:314-317)
+        const Divider<DT> dv(L + 1);
+#pragma unroll 1
+        for (int v = lane; v < a.nvec; v += 32)
+            st_stream16(orow + (size_t)v * 16, dv.vec(reinterpret_cast<const uint4*>(arow)[v]));
+    } else {
+#pragma unroll 2
+        for (int v = lane; v < a.nvec; v += 32)
+            st_stream16(orow + (size_t)v * 16, reinterpret_cast<const uint4*>(arow)[v]);
+    }
+#pragma unroll 1
+    for (int q = 0; q < a.n_tma_aux; ++q)
+        if (lane * 16 < a.tma_aux[q].bytes)
+            st_stream16(a.tma_aux[q].dst + (size_t)pos * a.tma_aux[q].bytes + lane * 16,
+                        *reinterpret_cast<const uint4*>(arow + a.tma_aux[q].slot_off + lane * 16));
+    if (lane == 0) {
+        if (a.n_small_aux > 0) *reinterpret_cast<unsigned long long*>(a.small_aux[0].dst + (size_t)pos * 8) = sm0;
+        if (a.n_small_aux > 1) *reinterpret_cast<unsigned long long*>(a.small_aux[1].dst + (size_t)pos * 8) = sm1;
+        a.dst[row_index(cs, chain_order, t_a)] = pos;
+        chain_order_next(a, cs)[k] = pos;
+    }
+    __syncwarp();
+    if (lane == 0) release_slot(a, cs, chain_order, slots, slot, 1, len, tx_bytes);
 }
 
 template <int DT>
@@ -352,7 +399,7 @@ k_stream_merge(const __grid_constant__ StreamArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int s_last_cta;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wpc = a.n_sim + 1;                             // warps per chain
+    const int wpc = a.n_sim;                                 // warps per chain
     const int chain = warp / wpc, role = warp - chain * wpc;
     const unsigned tag4 = (a.tag * 0x01010101u) << 1;       // the tag as it sits in every flag byte
 
@@ -361,18 +408,21 @@ k_stream_merge(const __grid_constant__ StreamArgs a) {
 #pragma unroll 1
     for (int q = 0; q < a.n_tma_aux; ++q) tx_bytes += (uint32_t)a.tma_aux[q].bytes;
 
-    // ---- set-up: the merge warp of every chain fills the chain's shared state
-    if (chain < a.cpc && role == a.n_sim) {
+    // ---- set-up: the first warp of every chain fills the chain's shared state
+    if (chain < a.cpc && role == 0) {
         ChainShared* cs = cs_base + chain;
         const int id = blockIdx.x * a.cpc + chain;
         const int len = id < a.n_ids ? __ldg(a.len + id) : 0;
         const int cbase = id < a.n_ids ? __ldg(a.base + id) : 0;
         for (int e = lane; e < ST_MAX_LEN; e += 32) cs->idx[e] = e < len ? __ldg(a.order + cbase + e) : 0;
-        if (lane < ST_RING) { cs->slot_of[lane] = 0; cs->hit[lane] = 0; cs->gap[lane] = 0; }
+        if (lane < ST_RING) { cs->slot_of[lane] = 0; cs->kc[lane] = 0; cs->keptbit[lane] = 0; cs->pend[lane] = 0; }
         if (lane < ST_MAX_SLOTS) { cs->refcnt[lane] = 0; cs->uses[lane] = 0; }
         if (lane == 0) {
             cs->issued = 0;
             cs->chain_id = id;
+            cs->token = 0;
+            cs->anchor_t = -1; cs->anchor_slot = -1; cs->anchor_L = 0; cs->anchor_pos = -1; cs->anchor_k = 0;
+            cs->cum = 0; cs->n_kept = 0; cs->hits = 0;
             for (int b = 0; b < a.n_slots; ++b) mbar_init(smem_u32(&cs->bars[b]), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -380,224 +430,197 @@ k_stream_merge(const __grid_constant__ StreamArgs a) {
     __syncthreads();
 
     if (chain < a.cpc) {
+        // =========================== chain warp ===========================
+        // Rows t = role, role + n_sim, ...; tasks t >= len only position the last rows.  A task is: similarity and
+        // merge flag of its row (free-running), the gap count that positions row t - lag (free-running), then the
+        // ORDERED section — entered in row order through the chain's token — which books the row into the open
+        // anchor or opens a new one, and finally the flushes it took on (free-running again).
         ChainShared* cs = cs_base + chain;
         unsigned char* slots = smem + (size_t)chain * a.n_slots * a.slot_bytes;
         const int id = blockIdx.x * a.cpc + chain;
         const int len = id < a.n_ids ? __ldg(a.len + id) : 0;
         const int cbase = id < a.n_ids ? __ldg(a.base + id) : 0;
         const int* chain_order = a.order + cbase;
+        const int K = a.lag;
 
-        if (role < a.n_sim) {
-            // =========================== sim warp ===========================
-            // rows t = role, role + n_sim, ...; tasks t >= len only count the last gaps
-            const int K = a.lag;
-            for (int t = role; t < len + K && len > 0; t += a.n_sim) {
-                const bool have_row = t < len;
-                const int i = have_row ? row_index(cs, chain_order, t) : 0;
-                unsigned long long small_new[ST_MAX_SMALL_AUX] = {0, 0};
-                if (lane == 0 && have_row)
-#pragma unroll 1
-                    for (int q = 0; q < a.n_small_aux; ++q)
-                        small_new[q] = __ldg(reinterpret_cast<const unsigned long long*>(a.small_aux[q].src + (size_t)i * 8));
+        if (role == 0 && lane == 0)
+            for (int b = 0; b < a.n_slots && b < len; ++b) issue_row(a, cs, chain_order, slots, b, len, tx_bytes);
 
-                // flags between rows r-1 and r of the chain, r = t - lag (the gap that positions row r; by now every
-                // chain is past it): requested now, looked at after the similarity
-                const int r = t - K;
-                const int i_r = r >= 0 ? row_index(cs, chain_order, r) : 0;
-                const int i_r1 = r >= 1 ? row_index(cs, chain_order, r - 1) : -1;
-                const int f_lo = i_r1 + 1, f_hi = i_r;
-                const int f_al = f_lo & ~15;
-                const int f_at0 = f_al + lane * 16, f_at1 = f_at0 + 512;
-                const bool f_two = r >= 0 && (f_hi - f_al) <= 1024;          // the gap fits the two early loads
-                uint4 fl0 = make_uint4(0, 0, 0, 0), fl1 = fl0;
-                if (f_two && f_at0 < f_hi) fl0 = ld_flags16(a.state + f_at0);
-                if (f_two && f_at1 < f_hi) fl1 = ld_flags16(a.state + f_at1);
+        for (int t = role; t < len + K && len > 0; t += a.n_sim) {
+            const bool have_row = t < len;
+            const int i = have_row ? row_index(cs, chain_order, t) : 0;
+            unsigned long long small_new[ST_MAX_SMALL_AUX] = {0, 0};
+            if (lane == 0 && have_row) {
+                if (a.n_small_aux > 0) small_new[0] = __ldg(reinterpret_cast<const unsigned long long*>(a.small_aux[0].src + (size_t)i * 8));
+                if (a.n_small_aux > 1) small_new[1] = __ldg(reinterpret_cast<const unsigned long long*>(a.small_aux[1].src + (size_t)i * 8));
+            }
 
-                int s_cur = -1, s_last = -1;
-                if (lane == 0 && have_row) ST_STAMP(t, 1);                       // sim task starts
-                if (have_row) {
-                    // ---- the row and its predecessor: slots and arrival
-                    int e_cur = 0, e_last = 0;
-                    if (lane == 0) {
-                        e_cur = ring_wait(&cs->slot_of[t & (ST_RING - 1)], t + 1, 8);
-                        if (t > 0) e_last = ring_wait(&cs->slot_of[(t - 1) & (ST_RING - 1)], t, 8);
-                    }
-                    e_cur = __shfl_sync(FULL, e_cur, 0);
-                    e_last = __shfl_sync(FULL, e_last, 0);
-                    s_cur = e_cur & 15;
-                    mbar_wait(smem_u32(&cs->bars[s_cur]), (e_cur >> 4) & 1);
-                    int hit = 0;
-                    float sim = -2.0f;
-                    if (lane == 0) ST_STAMP(t, 2);                                   // row arrived
-                    if (t > 0) {
-                        s_last = e_last & 15;
-                        mbar_wait(smem_u32(&cs->bars[s_last]), (e_last >> 4) & 1);
-                        // ---- similarity with the previous row of the chain (main.py:345-349 rounding chain)
-                        const uint4* lrow = reinterpret_cast<const uint4*>(slots + (size_t)s_last * a.slot_bytes);
-                        const uint4* crow = reinterpret_cast<const uint4*>(slots + (size_t)s_cur * a.slot_bytes);
-                        float2 dot2 = make_float2(0.f, 0.f), na2 = dot2, nb2 = dot2;
-#pragma unroll 2                                                 // rolled: the I-cache is 32 KB, every role must stay small
-                        for (int v = lane; v < a.nvec; v += 32) acc_pair2<DT>(lrow[v], crow[v], dot2, na2, nb2);
-                        const float dot = warp_sum(dot2.x + dot2.y);
-                        const float na = warp_sum(na2.x + na2.y);
-                        const float nb = warp_sum(nb2.x + nb2.y);
-                        sim = finish_cosine<DT>(dot, na, nb);
-                        hit = sim >= a.thr;
-                    }
-                    if (lane == 0) {
-                        st_flag(a.state + i, (a.tag << 1) | (unsigned)hit);
-                        a.sim_seq[i] = sim;
-                        if (hit) a.dst[i] = -1;
-#pragma unroll 1
-                        for (int q = 0; q < a.n_small_aux; ++q) cs->small[t & (ST_RING - 1)][q] = small_new[q];
-                        __threadfence_block();
-                        *(volatile int*)&cs->hit[t & (ST_RING - 1)] = ((t + 1) << 8) | hit;
-                        ST_STAMP(t, 3);                                              // flag published
-                    }
+            // flags between rows r-1 and r of the chain, r = t - lag (the gap that positions row r; by now every
+            // chain is past it): requested now, looked at after the similarity
+            const int r = t - K;
+            const int i_r = r >= 0 ? row_index(cs, chain_order, r) : 0;
+            const int i_r1 = r >= 1 ? row_index(cs, chain_order, r - 1) : -1;
+            const int f_lo = i_r1 + 1, f_hi = i_r;
+            const int f_al = f_lo & ~15;
+            const int f_at0 = f_al + lane * 16, f_at1 = f_at0 + 512;
+            const bool f_two = r >= 0 && (f_hi - f_al) <= 1024;              // the gap fits the two early loads
+            uint4 fl0 = make_uint4(0, 0, 0, 0), fl1 = fl0;
+            if (f_two && f_at0 < f_hi) fl0 = ld_flags16(a.state + f_at0);
+            if (f_two && f_at1 < f_hi) fl1 = ld_flags16(a.state + f_at1);
+
+            int s_cur = -1, s_last = -1, hit = 0;
+            if (lane == 0 && have_row) ST_STAMP(t, 1);                       // task starts
+            if (have_row) {
+                // ---- the row and its predecessor: slots and arrival
+                int e_cur = 0, e_last = 0;
+                if (lane == 0) {
+                    e_cur = ring_wait(&cs->slot_of[t & (ST_RING - 1)], t + 1, 8);
+                    if (t > 0) e_last = ring_wait(&cs->slot_of[(t - 1) & (ST_RING - 1)], t, 8);
                 }
+                e_cur = __shfl_sync(FULL, e_cur, 0);
+                e_last = __shfl_sync(FULL, e_last, 0);
+                s_cur = e_cur & 15;
+                mbar_wait(smem_u32(&cs->bars[s_cur]), (e_cur >> 4) & 1);
+                float sim = -2.0f;
+                if (lane == 0) ST_STAMP(t, 2);                               // row arrived
+                if (t > 0) {
+                    s_last = e_last & 15;
+                    mbar_wait(smem_u32(&cs->bars[s_last]), (e_last >> 4) & 1);
+                    // ---- similarity with the previous row of the chain (main.py:345-349 rounding chain)
+                    const uint4* lrow = reinterpret_cast<const uint4*>(slots + (size_t)s_last * a.slot_bytes);
+                    const uint4* crow = reinterpret_cast<const uint4*>(slots + (size_t)s_cur * a.slot_bytes);
+                    float2 dot2 = make_float2(0.f, 0.f), na2 = dot2, nb2 = dot2;
+#pragma unroll 2                                             // rolled: the I-cache is 32 KB, every role must stay small
+                    for (int v = lane; v < a.nvec; v += 32) acc_pair2<DT>(lrow[v], crow[v], dot2, na2, nb2);
+                    const float dot = warp_sum(dot2.x + dot2.y);
+                    const float na = warp_sum(na2.x + na2.y);
+                    const float nb = warp_sum(nb2.x + nb2.y);
+                    sim = finish_cosine<DT>(dot, na, nb);
+                    hit = sim >= a.thr;
+                }
+                if (lane == 0) {
+                    st_flag(a.state + i, (a.tag << 1) | (unsigned)hit);
+                    a.sim_seq[i] = sim;
+                    if (hit) a.dst[i] = -1;
+                    cs->small[t & (ST_RING - 1)][0] = small_new[0];
+                    cs->small[t & (ST_RING - 1)][1] = small_new[1];
+                    ST_STAMP(t, 3);                                          // flag published
+                }
+            }
 
-                // ---- gap count for row r = t - lag
-                if (r >= 0) {
-                    int kept = 0;
-                    bool ok = f_two;
-                    if (f_two) {
-                        if (f_at0 < f_hi) kept += count_kept_vec(fl0, f_at0, f_lo, f_hi, tag4, &ok);
-                        if (f_at1 < f_hi) kept += count_kept_vec(fl1, f_at1, f_lo, f_hi, tag4, &ok);
-                    }
-                    if (__all_sync(FULL, ok)) {
-                        kept = warp_sum_int(kept);
-                    } else {
-                        // some flag was not published yet, or the gap is long: walk it 512 bytes at a time
-                        kept = 0;
-                        for (int chunk = f_al; chunk < f_hi; chunk += 512) {
-                            const int at = chunk + lane * 16;
-                            for (;;) {
-                                bool ok2 = true;
-                                int k2 = 0;
-                                if (at < f_hi) k2 = count_kept16(a.state, at, f_lo, f_hi, tag4, &ok2);
-                                if (__all_sync(FULL, ok2)) { kept += warp_sum_int(k2); break; }
-                                __nanosleep(200);
-                            }
+            // ---- gap count for row r = t - lag
+            int gap = 0;
+            if (r >= 0) {
+                int kept = 0;
+                bool ok = f_two;
+                if (f_two) {
+                    if (f_at0 < f_hi) kept += count_kept_vec(fl0, f_at0, f_lo, f_hi, tag4, &ok);
+                    if (f_at1 < f_hi) kept += count_kept_vec(fl1, f_at1, f_lo, f_hi, tag4, &ok);
+                }
+                if (__all_sync(FULL, ok)) {
+                    kept = warp_sum_int(kept);
+                } else {
+                    // some flag was not published yet, or the gap is long: walk it 512 bytes at a time
+                    kept = 0;
+                    for (int chunk = f_al; chunk < f_hi; chunk += 512) {
+                        const int at = chunk + lane * 16;
+                        for (;;) {
+                            bool ok2 = true;
+                            int k2 = 0;
+                            if (at < f_hi) k2 = count_kept16(a.state, at, f_lo, f_hi, tag4, &ok2);
+                            if (__all_sync(FULL, ok2)) { kept += warp_sum_int(k2); break; }
+                            __nanosleep(200);
                         }
                     }
-                    if (lane == 0) *(volatile int*)&cs->gap[r & (ST_RING - 1)] = (((r + 1) & 0x7ff) << 20) | kept;
-                    if (lane == 0 && have_row) ST_STAMP(t, 4);                       // gap of row t - lag counted
                 }
-
-                // ---- references: this row as "current", the previous one as "previous"
-                __syncwarp();
-                if (lane == 0) {
-                    if (have_row) release_slot(a, cs, chain_order, slots, s_cur, len, tx_bytes);
-                    if (have_row && t > 0) release_slot(a, cs, chain_order, slots, s_last, len, tx_bytes);
-                }
+                gap = kept;
+                if (lane == 0 && have_row) ST_STAMP(t, 4);                   // gap of row t - lag counted
             }
-        } else {
-            // =========================== merge warp ===========================
-            if (lane == 0)
-                for (int b = 0; b < a.n_slots && b < len; ++b) issue_row(a, cs, chain_order, slots, b, len, tx_bytes);
 
-            // The pending anchor lives in ITS OWN slot: flagged successors are added into it in place.  Nobody else
-            // reads that slot any more — its readers were sim(anchor) and sim(anchor + 1), and merge(anchor + 1) only
-            // starts after sim(anchor + 1) has published its flag.  The merge warp keeps its reference until the flush.
-            unsigned long long small_acc[ST_MAX_SMALL_AUX] = {0, 0};
-            int L = 0, anchor_t = -1, anchor_i = -1, anchor_pos = -1, anchor_slot = -1;
-            int cnt = 0;                                     // kept rows in [0, i_r), r = gaps_taken - 1
-            int gaps_taken = 0;                              // gap counts consumed so far (rows 0 .. gaps_taken - 1 are positioned)
-            uint32_t kept_hist = 0;                          // bit (t & 31): row t of the chain was kept
-            int kept_idx = 0, hits = 0;
-
-            auto flush = [&]() {                             // the pending anchor goes to its compacted position
-                const unsigned char* arow = slots + (size_t)anchor_slot * a.slot_bytes;
-                char* orow = a.out + (size_t)anchor_pos * a.row_bytes;
-                if (L > 0) {                                 // average of the run (main.py:314-317)
-                    const Divider<DT> dv(L + 1);
-#pragma unroll 1
-                    for (int v = lane; v < a.nvec; v += 32)
-                        st_stream16(orow + (size_t)v * 16, dv.vec(reinterpret_cast<const uint4*>(arow)[v]));
-                } else {
-#pragma unroll 2
-                    for (int v = lane; v < a.nvec; v += 32)
-                        st_stream16(orow + (size_t)v * 16, reinterpret_cast<const uint4*>(arow)[v]);
-                }
-#pragma unroll 1
-                for (int q = 0; q < a.n_tma_aux; ++q)
-                    if (lane * 16 < a.tma_aux[q].bytes)
-                        st_stream16(a.tma_aux[q].dst + (size_t)anchor_pos * a.tma_aux[q].bytes + lane * 16,
-                                    *reinterpret_cast<const uint4*>(arow + a.tma_aux[q].slot_off + lane * 16));
-                if (lane == 0) {
-#pragma unroll 1
-                    for (int q = 0; q < a.n_small_aux; ++q)
-                        *reinterpret_cast<unsigned long long*>(a.small_aux[q].dst + (size_t)anchor_pos * 8) = small_acc[q];
-                    a.dst[anchor_i] = anchor_pos;
-                    a.order_next[cbase + kept_idx] = anchor_pos;
-                }
-                ++kept_idx;
-                __syncwarp();
-                if (lane == 0) release_slot(a, cs, chain_order, slots, anchor_slot, len, tx_bytes);
-            };
-            // consumes gap counts up to row r: cnt becomes the number of kept rows in [0, i_r); waits for the sim warps
-            // that count them (row r's gap is counted by the task of row r + lag)
-            auto position_upto = [&](int r) {
-                while (gaps_taken <= r) {
-                    const int q = gaps_taken;
-                    int g = 0;
-                    if (lane == 0) g = ring_wait(&cs->gap[q & (ST_RING - 1)], (q + 1) & 0x7ff, 20) & 0xfffff;
-                    g = __shfl_sync(FULL, g, 0);
-                    cnt += (q >= 1 ? (int)((kept_hist >> ((q - 1) & 31)) & 1u) : 0) + g;
-                    if (q == anchor_t) anchor_pos = cnt;
-                    ++gaps_taken;
-                }
-            };
-
-            for (int t = 0; t < len; ++t) {
-                int e_hit = 0, e_slot = 0;
-                if (lane == 0) {
-                    e_hit = ring_wait(&cs->hit[t & (ST_RING - 1)], t + 1, 8);
-                    e_slot = *(volatile int*)&cs->slot_of[t & (ST_RING - 1)];
-                }
-                e_hit = __shfl_sync(FULL, e_hit, 0);
-                e_slot = __shfl_sync(FULL, e_slot, 0);
-                const int hit = e_hit & 1, s = e_slot & 15;
-                if (lane == 0) ST_STAMP(t, 5);                                       // merge step starts
-                mbar_wait(smem_u32(&cs->bars[s]), (e_slot >> 4) & 1);      // complete long ago: orders our reads after the TMA writes
-                __threadfence_block();
-                const unsigned char* crow = slots + (size_t)s * a.slot_bytes;
-
-                if (hit) {
-                    uint4* arow = reinterpret_cast<uint4*>(slots + (size_t)anchor_slot * a.slot_bytes);
-#pragma unroll 2
-                    for (int v = lane; v < a.nvec; v += 32) arow[v] = add_round<DT>(arow[v], reinterpret_cast<const uint4*>(crow)[v]);
-                    ++L;
-                    ++hits;
-                    kept_hist &= ~(1u << (t & 31));
-                    __syncwarp();
-                    if (lane == 0) release_slot(a, cs, chain_order, slots, s, len, tx_bytes);
-                } else {
-                    if (t > 0) {
-                        position_upto(anchor_t);             // may wait for the sims of the next lag - 1 rows
-                        flush();
+            // ---- ordered section: rows of a chain pass through here one at a time, in row order
+            if (lane == 0) while (*(volatile int*)&cs->token != t) __nanosleep(40);
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0 && have_row) ST_STAMP(t, 5);
+            int f1_slot = -1, f1_L = 0, f1_pos = 0, f1_k = 0, f1_t = 0;      // flush jobs taken on in this section
+            int f2_slot = -1, f2_L = 0, f2_pos = 0, f2_k = 0, f2_t = 0;
+            unsigned long long f1_s0 = 0, f1_s1 = 0, f2_s0 = 0, f2_s1 = 0;
+            {
+                int an_t = cs->anchor_t, an_slot = cs->anchor_slot, an_L = cs->anchor_L, an_pos = cs->anchor_pos, an_k = cs->anchor_k;
+                int n_kept = cs->n_kept;
+                // (A) row r gets its position: kept rows outside the chain before it + kept rows of the chain before it
+                int cum_new = 0;
+                if (r >= 0) {
+                    const int cum = cs->cum + gap;
+                    cum_new = cum;
+                    if (cs->keptbit[r & (ST_RING - 1)]) {
+                        const int pos_r = cum + cs->kc[r & (ST_RING - 1)];
+                        if (r == an_t) {
+                            an_pos = pos_r;                                  // still open: whoever closes it writes it
+                        } else {
+                            const int pe = cs->pend[r & (ST_RING - 1)];      // closed earlier, parked until now
+                            f1_slot = pe & 15; f1_L = (pe >> 4) & 0x7ffffff; f1_pos = pos_r; f1_k = cs->kc[r & (ST_RING - 1)]; f1_t = r;
+                            f1_s0 = cs->pend_small[r & (ST_RING - 1)][0]; f1_s1 = cs->pend_small[r & (ST_RING - 1)][1];
+                        }
                     }
-                    kept_hist |= 1u << (t & 31);
-                    anchor_slot = s;                         // our reference on this slot is kept until the flush
-                    if (lane == 0)
-#pragma unroll 1
-                        for (int q = 0; q < a.n_small_aux; ++q) small_acc[q] = cs->small[t & (ST_RING - 1)][q];
-                    L = 0;
-                    anchor_t = t;
-                    anchor_i = row_index(cs, chain_order, t);
-                    anchor_pos = -1;
                 }
-                if (lane == 0) ST_STAMP(t, 6);                                       // merge step done
-                // keep the gap ring drained (it is ST_RING deep): rows this far behind were counted long ago
-                if (t - a.lag - 4 >= 0) position_upto(t - a.lag - 4);
+                __syncwarp();                                                // every lane has read the state; lane 0 may write
+                if (lane == 0 && r >= 0) cs->cum = cum_new;
+                // (B) this row: into the open anchor, or close it and open a new one
+                if (have_row && hit) {
+                    uint4* arow = reinterpret_cast<uint4*>(slots + (size_t)an_slot * a.slot_bytes);
+                    const uint4* crow = reinterpret_cast<const uint4*>(slots + (size_t)s_cur * a.slot_bytes);
+#pragma unroll 2
+                    for (int v = lane; v < a.nvec; v += 32) arow[v] = add_round<DT>(arow[v], crow[v]);
+                    an_L += 1;
+                    if (lane == 0) { cs->keptbit[t & (ST_RING - 1)] = 0; cs->kc[t & (ST_RING - 1)] = n_kept; cs->hits += 1; }
+                } else if (t <= len) {
+                    if (an_t >= 0) {                                         // close the open anchor
+                        if (an_pos >= 0) {
+                            f2_slot = an_slot; f2_L = an_L; f2_pos = an_pos; f2_k = an_k; f2_t = an_t;
+                            f2_s0 = cs->anchor_small[0]; f2_s1 = cs->anchor_small[1];
+                        } else if (lane == 0) {
+                            cs->pend[an_t & (ST_RING - 1)] = (int)(0x80000000u | ((unsigned)an_L << 4) | (unsigned)an_slot);
+                            cs->pend_small[an_t & (ST_RING - 1)][0] = cs->anchor_small[0];
+                            cs->pend_small[an_t & (ST_RING - 1)][1] = cs->anchor_small[1];
+                        }
+                        an_t = -1;
+                    }
+                    __syncwarp();
+                    if (have_row) {                                          // this row is the new anchor
+                        an_t = t; an_slot = s_cur; an_L = 0; an_pos = -1; an_k = n_kept;
+                        if (lane == 0) {
+                            cs->anchor_small[0] = cs->small[t & (ST_RING - 1)][0];
+                            cs->anchor_small[1] = cs->small[t & (ST_RING - 1)][1];
+                            cs->keptbit[t & (ST_RING - 1)] = 1;
+                            cs->kc[t & (ST_RING - 1)] = n_kept;
+                        }
+                        n_kept += 1;
+                    }
+                }
+                if (lane == 0) {
+                    cs->anchor_t = an_t; cs->anchor_slot = an_slot; cs->anchor_L = an_L; cs->anchor_pos = an_pos; cs->anchor_k = an_k;
+                    cs->n_kept = n_kept;
+                    __threadfence_block();
+                    *(volatile int*)&cs->token = t + 1;
+                }
+                __syncwarp();
             }
-            if (len > 0) {
-                position_upto(len - 1);
-                flush();
+            if (lane == 0 && have_row) ST_STAMP(t, 6);                       // ordered section left
+
+            // ---- free-running again: the flushes taken on, then the references of this task
+            if (f1_slot >= 0) flush_anchor<DT>(a, cs, chain_order, slots, f1_slot, f1_L, f1_pos, f1_k, f1_t, f1_s0, f1_s1, len, tx_bytes);
+            if (f2_slot >= 0) flush_anchor<DT>(a, cs, chain_order, slots, f2_slot, f2_L, f2_pos, f2_k, f2_t, f2_s0, f2_s1, len, tx_bytes);
+            __syncwarp();
+            if (lane == 0 && have_row) {
+                // this row as "current" (and as merge input when it was merged away), the previous one as "previous"
+                release_slot(a, cs, chain_order, slots, s_cur, hit ? 2 : 1, len, tx_bytes);
+                if (t > 0) release_slot(a, cs, chain_order, slots, s_last, 1, len, tx_bytes);
             }
-            if (lane == 0) {
-                if (id < a.n_ids) a.len_next[id] = kept_idx;
-                if (hits) atomicAdd((unsigned long long*)&a.counters[C_COUNT], (unsigned long long)hits);
+            if (t == len + K - 1 && lane == 0) {
+                // the last task of the chain: every row is booked
+                if (id < a.n_ids) a.len_next[id] = cs->n_kept;
+                if (cs->hits) atomicAdd((unsigned long long*)&a.counters[C_COUNT], (unsigned long long)cs->hits);
             }
         }
     } else if (warp == a.cpc * wpc) {
@@ -698,9 +721,9 @@ inline bool plan_stream(int sm_count, int max_smem, int64_t row_bytes, int n_ids
     if (n_ids < 1) return false;
     const int cpc = (n_ids + sm_count - 1) / sm_count;
     if (cpc > ST_MAX_CHAINS) return false;
-    int n_sim = (ST_MAX_WARPS - 1) / cpc - 1;
-    if (n_sim > 3) n_sim = 3;
-    if (n_sim < 1) return false;
+    int n_sim = (ST_MAX_WARPS - 1) / cpc;                  // warps per chain
+    if (n_sim > 5) n_sim = 5;
+    if (n_sim < 2) return false;
     const int slot = (int)((row_bytes + aux_bytes + 127) / 128 * 128);
     const size_t fixed = (size_t)cpc * sizeof(ChainShared) + 256;
     if ((size_t)max_smem < fixed + 64) return false;
@@ -714,7 +737,7 @@ inline bool plan_stream(int sm_count, int max_smem, int64_t row_bytes, int n_ids
     p->n_sim = n_sim;
     p->lag = n_slots >= 7 ? 3 : (n_slots >= 5 ? 2 : 1);    // rows t .. t + lag - 1 stay resident while merge(t) waits
     p->slot_bytes = slot;
-    p->threads = (cpc * (n_sim + 1) + 1) * 32;
+    p->threads = (cpc * n_sim + 1) * 32;
     p->smem = (size_t)cpc * n_slots * slot + fixed;
     return true;
 }
