@@ -304,8 +304,9 @@ struct ChainShared {
     int uses[ST_MAX_SLOTS];
     int issued;                                     // rows requested so far
     int chain_id;
-    // ordered state: read and written only inside the ordered section (by whoever holds the token)
-    int token;                                      // row whose ordered section may run next
+    // ordered state: section A owns the anchor, section B owns cum; anchor_t / anchor_pos / pend are shared under `lock`
+    int token_a, token_b;                           // task whose section A / section B may run next
+    int lock;                                       // guards anchor_t / anchor_pos / pend between the two sections
     int anchor_t, anchor_slot, anchor_L, anchor_pos, anchor_k;   // the open anchor; anchor_k = its rank among the chain's kept rows
     int cum;                                        // kept rows outside this chain before row r, r = the last row positioned
     int n_kept;                                     // anchors opened so far
@@ -316,6 +317,15 @@ __device__ __forceinline__ int ring_wait(const int* slot, int want_tag, int tag_
     int v;
     while (((unsigned)(v = *(volatile const int*)slot) >> tag_shift) != (unsigned)want_tag) __nanosleep(40);
     return v;
+}
+
+__device__ __forceinline__ void chain_lock(ChainShared* cs) {
+    while (atomicCAS(&cs->lock, 0, 1) != 0) __nanosleep(20);
+    __threadfence_block();
+}
+__device__ __forceinline__ void chain_unlock(ChainShared* cs) {
+    __threadfence_block();
+    atomicExch(&cs->lock, 0);
 }
 
 // sequence index of row t of a chain: from the shared-memory window, from the list in global memory beyond it
@@ -420,7 +430,7 @@ k_stream_merge(const __grid_constant__ StreamArgs a) {
         if (lane == 0) {
             cs->issued = 0;
             cs->chain_id = id;
-            cs->token = 0;
+            cs->token_a = 0; cs->token_b = 0; cs->lock = 0;
             cs->anchor_t = -1; cs->anchor_slot = -1; cs->anchor_L = 0; cs->anchor_pos = -1; cs->anchor_k = 0;
             cs->cum = 0; cs->n_kept = 0; cs->hits = 0;
             for (int b = 0; b < a.n_slots; ++b) mbar_init(smem_u32(&cs->bars[b]), 1);
@@ -505,10 +515,88 @@ k_stream_merge(const __grid_constant__ StreamArgs a) {
                     cs->small[t & (ST_RING - 1)][0] = small_new[0];
                     cs->small[t & (ST_RING - 1)][1] = small_new[1];
                     ST_STAMP(t, 3);                                          // flag published
+                    // the previous row is not read again by this task
+                    if (t > 0) release_slot(a, cs, chain_order, slots, s_last, 1, len, tx_bytes);
                 }
             }
 
-            // ---- gap count for row r = t - lag
+            // ---- section A (row order, token A): book the row into the open anchor, or close it and open a new one.
+            //      Needs no position, so it never waits for other chains.
+            if (lane == 0) {
+                while (*(volatile int*)&cs->token_a != t) __nanosleep(40);
+                // the rings below are ST_RING deep: stay within reach of the slower section B
+                while (*(volatile int*)&cs->token_b < t - (ST_RING - 4)) __nanosleep(100);
+            }
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0 && have_row) ST_STAMP(t, 5);
+            int f2_slot = -1, f2_L = 0, f2_pos = 0, f2_k = 0, f2_t = 0;       // the anchor this section closes, if its position is known
+            unsigned long long f2_s0 = 0, f2_s1 = 0;
+            if (have_row && hit) {
+                const int an_slot = cs->anchor_slot;
+                uint4* arow = reinterpret_cast<uint4*>(slots + (size_t)an_slot * a.slot_bytes);
+                const uint4* crow = reinterpret_cast<const uint4*>(slots + (size_t)s_cur * a.slot_bytes);
+#pragma unroll 2
+                for (int v = lane; v < a.nvec; v += 32) arow[v] = add_round<DT>(arow[v], crow[v]);
+                if (lane == 0) {
+                    cs->anchor_L += 1;
+                    cs->hits += 1;
+                    cs->keptbit[t & (ST_RING - 1)] = 0;
+                    cs->kc[t & (ST_RING - 1)] = cs->n_kept;
+                }
+            } else if (t <= len) {
+                int take = 0;
+                if (lane == 0) {
+                    const int an_t = cs->anchor_t;                            // only section A changes it
+                    chain_lock(cs);
+                    if (an_t >= 0) {
+                        const int an_pos = cs->anchor_pos;
+                        if (an_pos >= 0) {
+                            take = 1;
+                            f2_slot = cs->anchor_slot; f2_L = cs->anchor_L; f2_pos = an_pos; f2_k = cs->anchor_k; f2_t = an_t;
+                            f2_s0 = cs->anchor_small[0]; f2_s1 = cs->anchor_small[1];
+                        } else {                                              // park it: section B flushes it when it positions it
+                            cs->pend[an_t & (ST_RING - 1)] = (int)(0x80000000u | ((unsigned)cs->anchor_L << 4) | (unsigned)cs->anchor_slot);
+                            cs->pend_small[an_t & (ST_RING - 1)][0] = cs->anchor_small[0];
+                            cs->pend_small[an_t & (ST_RING - 1)][1] = cs->anchor_small[1];
+                        }
+                    }
+                    if (have_row) {                                           // this row is the new anchor
+                        const int n_kept = cs->n_kept;
+                        cs->anchor_t = t; cs->anchor_slot = s_cur; cs->anchor_L = 0; cs->anchor_pos = -1; cs->anchor_k = n_kept;
+                        cs->anchor_small[0] = cs->small[t & (ST_RING - 1)][0];
+                        cs->anchor_small[1] = cs->small[t & (ST_RING - 1)][1];
+                        cs->keptbit[t & (ST_RING - 1)] = 1;
+                        cs->kc[t & (ST_RING - 1)] = n_kept;
+                        cs->n_kept = n_kept + 1;
+                    } else {
+                        cs->anchor_t = -1;
+                    }
+                    chain_unlock(cs);
+                }
+                take = __shfl_sync(FULL, take, 0);
+                if (take) {
+                    f2_slot = __shfl_sync(FULL, f2_slot, 0); f2_L = __shfl_sync(FULL, f2_L, 0); f2_pos = __shfl_sync(FULL, f2_pos, 0);
+                    f2_k = __shfl_sync(FULL, f2_k, 0); f2_t = __shfl_sync(FULL, f2_t, 0);
+                } else {
+                    f2_slot = -1;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                *(volatile int*)&cs->token_a = t + 1;
+            }
+            if (lane == 0 && have_row) ST_STAMP(t, 6);                       // section A left
+
+            // ---- free-running: references of this task, the flush taken on in section A
+            if (lane == 0 && have_row) {
+                // this row as "current" (and as merge input when it was merged away), the previous one as "previous"
+                release_slot(a, cs, chain_order, slots, s_cur, hit ? 2 : 1, len, tx_bytes);
+            }
+            if (f2_slot >= 0) flush_anchor<DT>(a, cs, chain_order, slots, f2_slot, f2_L, f2_pos, f2_k, f2_t, f2_s0, f2_s1, len, tx_bytes);
+
+            // ---- gap count for row r = t - lag (waits for the flags of every chain up to there)
             int gap = 0;
             if (r >= 0) {
                 int kept = 0;
@@ -537,86 +625,45 @@ k_stream_merge(const __grid_constant__ StreamArgs a) {
                 if (lane == 0 && have_row) ST_STAMP(t, 4);                   // gap of row t - lag counted
             }
 
-            // ---- ordered section: rows of a chain pass through here one at a time, in row order
-            if (lane == 0) while (*(volatile int*)&cs->token != t) __nanosleep(40);
-            __syncwarp();
-            __threadfence_block();
-            if (lane == 0 && have_row) ST_STAMP(t, 5);
-            int f1_slot = -1, f1_L = 0, f1_pos = 0, f1_k = 0, f1_t = 0;      // flush jobs taken on in this section
-            int f2_slot = -1, f2_L = 0, f2_pos = 0, f2_k = 0, f2_t = 0;
-            unsigned long long f1_s0 = 0, f1_s1 = 0, f2_s0 = 0, f2_s1 = 0;
+            // ---- section B (row order, token B): row r gets its position — kept rows outside the chain before it
+            //      (the gaps, summed) + kept rows of the chain before it — and, if it is a closed anchor, is flushed
+            int f1_slot = -1, f1_L = 0, f1_pos = 0, f1_k = 0, f1_t = 0;
+            unsigned long long f1_s0 = 0, f1_s1 = 0;
             {
-                int an_t = cs->anchor_t, an_slot = cs->anchor_slot, an_L = cs->anchor_L, an_pos = cs->anchor_pos, an_k = cs->anchor_k;
-                int n_kept = cs->n_kept;
-                // (A) row r gets its position: kept rows outside the chain before it + kept rows of the chain before it
-                int cum_new = 0;
-                if (r >= 0) {
-                    const int cum = cs->cum + gap;
-                    cum_new = cum;
-                    if (cs->keptbit[r & (ST_RING - 1)]) {
-                        const int pos_r = cum + cs->kc[r & (ST_RING - 1)];
-                        if (r == an_t) {
-                            an_pos = pos_r;                                  // still open: whoever closes it writes it
-                        } else {
-                            const int pe = cs->pend[r & (ST_RING - 1)];      // closed earlier, parked until now
-                            f1_slot = pe & 15; f1_L = (pe >> 4) & 0x7ffffff; f1_pos = pos_r; f1_k = cs->kc[r & (ST_RING - 1)]; f1_t = r;
-                            f1_s0 = cs->pend_small[r & (ST_RING - 1)][0]; f1_s1 = cs->pend_small[r & (ST_RING - 1)][1];
-                        }
-                    }
-                }
-                __syncwarp();                                                // every lane has read the state; lane 0 may write
-                if (lane == 0 && r >= 0) cs->cum = cum_new;
-                // (B) this row: into the open anchor, or close it and open a new one
-                if (have_row && hit) {
-                    uint4* arow = reinterpret_cast<uint4*>(slots + (size_t)an_slot * a.slot_bytes);
-                    const uint4* crow = reinterpret_cast<const uint4*>(slots + (size_t)s_cur * a.slot_bytes);
-#pragma unroll 2
-                    for (int v = lane; v < a.nvec; v += 32) arow[v] = add_round<DT>(arow[v], crow[v]);
-                    an_L += 1;
-                    if (lane == 0) { cs->keptbit[t & (ST_RING - 1)] = 0; cs->kc[t & (ST_RING - 1)] = n_kept; cs->hits += 1; }
-                } else if (t <= len) {
-                    if (an_t >= 0) {                                         // close the open anchor
-                        if (an_pos >= 0) {
-                            f2_slot = an_slot; f2_L = an_L; f2_pos = an_pos; f2_k = an_k; f2_t = an_t;
-                            f2_s0 = cs->anchor_small[0]; f2_s1 = cs->anchor_small[1];
-                        } else if (lane == 0) {
-                            cs->pend[an_t & (ST_RING - 1)] = (int)(0x80000000u | ((unsigned)an_L << 4) | (unsigned)an_slot);
-                            cs->pend_small[an_t & (ST_RING - 1)][0] = cs->anchor_small[0];
-                            cs->pend_small[an_t & (ST_RING - 1)][1] = cs->anchor_small[1];
-                        }
-                        an_t = -1;
-                    }
-                    __syncwarp();
-                    if (have_row) {                                          // this row is the new anchor
-                        an_t = t; an_slot = s_cur; an_L = 0; an_pos = -1; an_k = n_kept;
-                        if (lane == 0) {
-                            cs->anchor_small[0] = cs->small[t & (ST_RING - 1)][0];
-                            cs->anchor_small[1] = cs->small[t & (ST_RING - 1)][1];
-                            cs->keptbit[t & (ST_RING - 1)] = 1;
-                            cs->kc[t & (ST_RING - 1)] = n_kept;
-                        }
-                        n_kept += 1;
-                    }
-                }
+                int take = 0;
                 if (lane == 0) {
-                    cs->anchor_t = an_t; cs->anchor_slot = an_slot; cs->anchor_L = an_L; cs->anchor_pos = an_pos; cs->anchor_k = an_k;
-                    cs->n_kept = n_kept;
+                    while (*(volatile int*)&cs->token_b != t) __nanosleep(40);
                     __threadfence_block();
-                    *(volatile int*)&cs->token = t + 1;
+                    if (r >= 0) {
+                        const int cum = cs->cum + gap;
+                        cs->cum = cum;
+                        if (cs->keptbit[r & (ST_RING - 1)]) {
+                            const int pos_r = cum + cs->kc[r & (ST_RING - 1)];
+                            chain_lock(cs);
+                            if (cs->anchor_t == r) {
+                                cs->anchor_pos = pos_r;                      // still open: whoever closes it flushes it
+                            } else {
+                                const int pe = cs->pend[r & (ST_RING - 1)];  // closed earlier and parked
+                                take = 1;
+                                f1_slot = pe & 15; f1_L = (pe >> 4) & 0x7ffffff; f1_pos = pos_r; f1_k = cs->kc[r & (ST_RING - 1)]; f1_t = r;
+                                f1_s0 = cs->pend_small[r & (ST_RING - 1)][0]; f1_s1 = cs->pend_small[r & (ST_RING - 1)][1];
+                            }
+                            chain_unlock(cs);
+                        }
+                    }
+                    __threadfence_block();
+                    *(volatile int*)&cs->token_b = t + 1;
                 }
-                __syncwarp();
+                take = __shfl_sync(FULL, take, 0);
+                if (take) {
+                    f1_slot = __shfl_sync(FULL, f1_slot, 0); f1_L = __shfl_sync(FULL, f1_L, 0); f1_pos = __shfl_sync(FULL, f1_pos, 0);
+                    f1_k = __shfl_sync(FULL, f1_k, 0); f1_t = __shfl_sync(FULL, f1_t, 0);
+                } else {
+                    f1_slot = -1;
+                }
             }
-            if (lane == 0 && have_row) ST_STAMP(t, 6);                       // ordered section left
-
-            // ---- free-running again: the flushes taken on, then the references of this task
             if (f1_slot >= 0) flush_anchor<DT>(a, cs, chain_order, slots, f1_slot, f1_L, f1_pos, f1_k, f1_t, f1_s0, f1_s1, len, tx_bytes);
-            if (f2_slot >= 0) flush_anchor<DT>(a, cs, chain_order, slots, f2_slot, f2_L, f2_pos, f2_k, f2_t, f2_s0, f2_s1, len, tx_bytes);
             __syncwarp();
-            if (lane == 0 && have_row) {
-                // this row as "current" (and as merge input when it was merged away), the previous one as "previous"
-                release_slot(a, cs, chain_order, slots, s_cur, hit ? 2 : 1, len, tx_bytes);
-                if (t > 0) release_slot(a, cs, chain_order, slots, s_last, 1, len, tx_bytes);
-            }
             if (t == len + K - 1 && lane == 0) {
                 // the last task of the chain: every row is booked
                 if (id < a.n_ids) a.len_next[id] = cs->n_kept;
