@@ -51,7 +51,8 @@ constexpr int ST_MAX_VPL = 16;                     // 16-byte vectors per lane: 
 constexpr int ST_MAX_TMA_AUX = 6;                  // (aux, plane) pairs carried through the slot, <= 512 bytes each
 constexpr int ST_MAX_SMALL_AUX = 2;                // 8-byte aux rows (patch_type, position ids)
 constexpr int ST_TRACE_T = 96, ST_TRACE_K = 8;    // development aid: rows x stamps per chain
-constexpr int ST_MAX_WARPS = 24;                   // cpc * n_sim + 1: 768 threads leave 80 registers each
+constexpr int ST_POLL_NS = 250;                    // back-off of the shared-memory polls: spinning warps steal issue slots
+constexpr int ST_MAX_WARPS = 24;                   // cpc * (n_sim + 2) + 1: 768 threads leave 80 registers each
 
 struct StreamAux {
     const char* src;
@@ -289,33 +290,48 @@ __device__ __forceinline__ int count_kept16(const uint8_t* state, int at, int lo
 }
 
 // ---- the kernel --------------------------------------------------------------------------------------------
+// A kept row ("anchor") between its opening and its flush.  Shared by three parties under ChainShared::lock:
+// the sim warps close it (L is final), the positioner gives it its compacted position, whoever completes the
+// pair hands it to the flusher.
+struct AnchorRec {
+    int slot, L, pos, k;                            // k = rank among the kept rows of the chain
+    int closed, positioned;
+    unsigned long long small[ST_MAX_SMALL_AUX];     // its 8-byte aux values (patch_type, position id)
+};
+
+struct FlushJob {
+    int slot, L, pos, k, t_a, pad;
+    unsigned long long small[ST_MAX_SMALL_AUX];
+};
+
 // per-chain shared state (one per chain of the CTA, after the slots in dynamic shared memory)
 struct ChainShared {
     uint64_t bars[ST_MAX_SLOTS];                    // one mbarrier per slot
     unsigned long long small[ST_RING][ST_MAX_SMALL_AUX];       // 8-byte aux values of row t at [t % ST_RING]
-    unsigned long long pend_small[ST_RING][ST_MAX_SMALL_AUX];  // ... of a closed anchor waiting for its position
-    unsigned long long anchor_small[ST_MAX_SMALL_AUX];         // ... of the open anchor
+    AnchorRec arec[ST_RING];                        // anchor t at [t % ST_RING]
+    FlushJob fq[ST_RING];                           // flusher queue
     int idx[ST_MAX_LEN];                            // sequence index of every row of the chain
     int slot_of[ST_RING];                           // ((row + 1) << 8) | (parity << 4) | slot
-    int kc[ST_RING];                                // kept rows of this chain before row t (set in the ordered section of t)
+    int kc[ST_RING];                                // kept rows of this chain before row t (set in section A of t)
     int keptbit[ST_RING];                           // row t was kept
-    int pend[ST_RING];                              // closed anchor t waiting for its position: (1 << 31) | (L << 4) | slot
     int refcnt[ST_MAX_SLOTS];
     int uses[ST_MAX_SLOTS];
     int issued;                                     // rows requested so far
     int chain_id;
-    // ordered state: section A owns the anchor, section B owns cum; anchor_t / anchor_pos / pend are shared under `lock`
-    int token_a, token_b;                           // task whose section A / section B may run next
-    int lock;                                       // guards anchor_t / anchor_pos / pend between the two sections
-    int anchor_t, anchor_slot, anchor_L, anchor_pos, anchor_k;   // the open anchor; anchor_k = its rank among the chain's kept rows
-    int cum;                                        // kept rows outside this chain before row r, r = the last row positioned
+    int token_a;                                    // row whose section A may run next (sim warps, row order)
+    int token_b;                                    // rows the positioner is done with
+    int lock;                                       // guards arec[] and the flusher queue head
+    int fq_head, fq_tail;                           // jobs pushed / popped
+    int a_done;                                     // section A of the last row has run: n_kept is final
+    // owned by section A
+    int anchor_t, anchor_slot, anchor_L;            // the open anchor
     int n_kept;                                     // anchors opened so far
     int hits;                                       // rows merged away so far
 };
 
 __device__ __forceinline__ int ring_wait(const int* slot, int want_tag, int tag_shift) {
     int v;
-    while (((unsigned)(v = *(volatile const int*)slot) >> tag_shift) != (unsigned)want_tag) __nanosleep(40);
+    while (((unsigned)(v = *(volatile const int*)slot) >> tag_shift) != (unsigned)want_tag) __nanosleep(ST_POLL_NS);
     return v;
 }
 
@@ -366,41 +382,13 @@ __device__ __forceinline__ void release_slot(const StreamArgs& a, ChainShared* c
     }
 }
 
-__device__ __forceinline__ int* chain_order_next(const StreamArgs& a, const ChainShared* cs) {
-    return a.order_next + __ldg(a.base + cs->chain_id);
-}
-
-// a closed anchor, final in its slot, goes to its compacted position (whole warp); drops the anchor's reference
-template <int DT>
-__device__ __noinline__ void flush_anchor(const StreamArgs& a, ChainShared* cs, const int* chain_order, unsigned char* slots,
-                                          int slot, int L, int pos, int k, int t_a, unsigned long long sm0,
-                                          unsigned long long sm1, int len, uint32_t tx_bytes) {
-    const int lane = threadIdx.x & 31;
-    const unsigned char* arow = slots + (size_t)slot * a.slot_bytes;
-    char* orow = a.out + (size_t)pos * a.row_bytes;
-    if (L > 0) {                                            // average of the run (main.py:314-317)
-        const Divider<DT> dv(L + 1);
-#pragma unroll 1
-        for (int v = lane; v < a.nvec; v += 32)
-            st_stream16(orow + (size_t)v * 16, dv.vec(reinterpret_cast<const uint4*>(arow)[v]));
-    } else {
-#pragma unroll 2
-        for (int v = lane; v < a.nvec; v += 32)
-            st_stream16(orow + (size_t)v * 16, reinterpret_cast<const uint4*>(arow)[v]);
-    }
-#pragma unroll 1
-    for (int q = 0; q < a.n_tma_aux; ++q)
-        if (lane * 16 < a.tma_aux[q].bytes)
-            st_stream16(a.tma_aux[q].dst + (size_t)pos * a.tma_aux[q].bytes + lane * 16,
-                        *reinterpret_cast<const uint4*>(arow + a.tma_aux[q].slot_off + lane * 16));
-    if (lane == 0) {
-        if (a.n_small_aux > 0) *reinterpret_cast<unsigned long long*>(a.small_aux[0].dst + (size_t)pos * 8) = sm0;
-        if (a.n_small_aux > 1) *reinterpret_cast<unsigned long long*>(a.small_aux[1].dst + (size_t)pos * 8) = sm1;
-        a.dst[row_index(cs, chain_order, t_a)] = pos;
-        chain_order_next(a, cs)[k] = pos;
-    }
-    __syncwarp();
-    if (lane == 0) release_slot(a, cs, chain_order, slots, slot, 1, len, tx_bytes);
+// hands a closed and positioned anchor to the flusher (one lane, chain lock held)
+__device__ __forceinline__ void push_flush(ChainShared* cs, const AnchorRec& r, int t_a) {
+    FlushJob& j = cs->fq[cs->fq_head & (ST_RING - 1)];
+    j.slot = r.slot; j.L = r.L; j.pos = r.pos; j.k = r.k; j.t_a = t_a;
+    j.small[0] = r.small[0]; j.small[1] = r.small[1];
+    __threadfence_block();
+    *(volatile int*)&cs->fq_head = cs->fq_head + 1;
 }
 
 template <int DT>
@@ -409,7 +397,7 @@ k_stream_merge(const __grid_constant__ StreamArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int s_last_cta;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wpc = a.n_sim;                                 // warps per chain
+    const int wpc = a.n_sim + 2;                             // warps per chain: sims, positioner, flusher
     const int chain = warp / wpc, role = warp - chain * wpc;
     const unsigned tag4 = (a.tag * 0x01010101u) << 1;       // the tag as it sits in every flag byte
 
@@ -425,14 +413,14 @@ k_stream_merge(const __grid_constant__ StreamArgs a) {
         const int len = id < a.n_ids ? __ldg(a.len + id) : 0;
         const int cbase = id < a.n_ids ? __ldg(a.base + id) : 0;
         for (int e = lane; e < ST_MAX_LEN; e += 32) cs->idx[e] = e < len ? __ldg(a.order + cbase + e) : 0;
-        if (lane < ST_RING) { cs->slot_of[lane] = 0; cs->kc[lane] = 0; cs->keptbit[lane] = 0; cs->pend[lane] = 0; }
+        if (lane < ST_RING) { cs->slot_of[lane] = 0; cs->kc[lane] = 0; cs->keptbit[lane] = 0; }
         if (lane < ST_MAX_SLOTS) { cs->refcnt[lane] = 0; cs->uses[lane] = 0; }
         if (lane == 0) {
             cs->issued = 0;
             cs->chain_id = id;
-            cs->token_a = 0; cs->token_b = 0; cs->lock = 0;
-            cs->anchor_t = -1; cs->anchor_slot = -1; cs->anchor_L = 0; cs->anchor_pos = -1; cs->anchor_k = 0;
-            cs->cum = 0; cs->n_kept = 0; cs->hits = 0;
+            cs->token_a = 0; cs->token_b = 0; cs->lock = 0; cs->fq_head = 0; cs->fq_tail = 0; cs->a_done = 0;
+            cs->anchor_t = -1; cs->anchor_slot = -1; cs->anchor_L = 0;
+            cs->n_kept = 0; cs->hits = 0;
             for (int b = 0; b < a.n_slots; ++b) mbar_init(smem_u32(&cs->bars[b]), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -440,132 +428,109 @@ k_stream_merge(const __grid_constant__ StreamArgs a) {
     __syncthreads();
 
     if (chain < a.cpc) {
-        // =========================== chain warp ===========================
-        // Rows t = role, role + n_sim, ...; tasks t >= len only position the last rows.  A task is: similarity and
-        // merge flag of its row (free-running), the gap count that positions row t - lag (free-running), then the
-        // ORDERED section — entered in row order through the chain's token — which books the row into the open
-        // anchor or opens a new one, and finally the flushes it took on (free-running again).
         ChainShared* cs = cs_base + chain;
         unsigned char* slots = smem + (size_t)chain * a.n_slots * a.slot_bytes;
         const int id = blockIdx.x * a.cpc + chain;
         const int len = id < a.n_ids ? __ldg(a.len + id) : 0;
         const int cbase = id < a.n_ids ? __ldg(a.base + id) : 0;
         const int* chain_order = a.order + cbase;
-        const int K = a.lag;
 
-        if (role == 0 && lane == 0)
-            for (int b = 0; b < a.n_slots && b < len; ++b) issue_row(a, cs, chain_order, slots, b, len, tx_bytes);
+        if (role < a.n_sim) {
+            // =========================== sim warp ===========================
+            // Rows t = role, role + n_sim, ...; task t == len only closes the last anchor.  A task: similarity and merge
+            // flag of its row (free-running), then section A — entered in row order through the chain's token —
+            // which adds the row into the open anchor or closes that one and opens a new one.  Never waits for
+            // another chain.
+            if (role == 0 && lane == 0)
+                for (int b = 0; b < a.n_slots && b < len; ++b) issue_row(a, cs, chain_order, slots, b, len, tx_bytes);
 
-        for (int t = role; t < len + K && len > 0; t += a.n_sim) {
-            const bool have_row = t < len;
-            const int i = have_row ? row_index(cs, chain_order, t) : 0;
-            unsigned long long small_new[ST_MAX_SMALL_AUX] = {0, 0};
-            if (lane == 0 && have_row) {
-                if (a.n_small_aux > 0) small_new[0] = __ldg(reinterpret_cast<const unsigned long long*>(a.small_aux[0].src + (size_t)i * 8));
-                if (a.n_small_aux > 1) small_new[1] = __ldg(reinterpret_cast<const unsigned long long*>(a.small_aux[1].src + (size_t)i * 8));
-            }
-
-            // flags between rows r-1 and r of the chain, r = t - lag (the gap that positions row r; by now every
-            // chain is past it): requested now, looked at after the similarity
-            const int r = t - K;
-            const int i_r = r >= 0 ? row_index(cs, chain_order, r) : 0;
-            const int i_r1 = r >= 1 ? row_index(cs, chain_order, r - 1) : -1;
-            const int f_lo = i_r1 + 1, f_hi = i_r;
-            const int f_al = f_lo & ~15;
-            const int f_at0 = f_al + lane * 16, f_at1 = f_at0 + 512;
-            const bool f_two = r >= 0 && (f_hi - f_al) <= 1024;              // the gap fits the two early loads
-            uint4 fl0 = make_uint4(0, 0, 0, 0), fl1 = fl0;
-            if (f_two && f_at0 < f_hi) fl0 = ld_flags16(a.state + f_at0);
-            if (f_two && f_at1 < f_hi) fl1 = ld_flags16(a.state + f_at1);
-
-            int s_cur = -1, s_last = -1, hit = 0;
-            if (lane == 0 && have_row) ST_STAMP(t, 1);                       // task starts
-            if (have_row) {
-                // ---- the row and its predecessor: slots and arrival
-                int e_cur = 0, e_last = 0;
-                if (lane == 0) {
-                    e_cur = ring_wait(&cs->slot_of[t & (ST_RING - 1)], t + 1, 8);
-                    if (t > 0) e_last = ring_wait(&cs->slot_of[(t - 1) & (ST_RING - 1)], t, 8);
-                }
-                e_cur = __shfl_sync(FULL, e_cur, 0);
-                e_last = __shfl_sync(FULL, e_last, 0);
-                s_cur = e_cur & 15;
-                mbar_wait(smem_u32(&cs->bars[s_cur]), (e_cur >> 4) & 1);
-                float sim = -2.0f;
-                if (lane == 0) ST_STAMP(t, 2);                               // row arrived
-                if (t > 0) {
-                    s_last = e_last & 15;
-                    mbar_wait(smem_u32(&cs->bars[s_last]), (e_last >> 4) & 1);
-                    // ---- similarity with the previous row of the chain (main.py:345-349 rounding chain)
-                    const uint4* lrow = reinterpret_cast<const uint4*>(slots + (size_t)s_last * a.slot_bytes);
-                    const uint4* crow = reinterpret_cast<const uint4*>(slots + (size_t)s_cur * a.slot_bytes);
-                    float2 dot2 = make_float2(0.f, 0.f), na2 = dot2, nb2 = dot2;
+            for (int t = role; t <= len && len > 0; t += a.n_sim) {
+                const bool have_row = t < len;
+                int s_cur = -1, hit = 0;
+                if (have_row) {
+                    const int i = row_index(cs, chain_order, t);
+                    unsigned long long small_new[ST_MAX_SMALL_AUX] = {0, 0};
+                    if (lane == 0) {
+                        if (a.n_small_aux > 0) small_new[0] = __ldg(reinterpret_cast<const unsigned long long*>(a.small_aux[0].src + (size_t)i * 8));
+                        if (a.n_small_aux > 1) small_new[1] = __ldg(reinterpret_cast<const unsigned long long*>(a.small_aux[1].src + (size_t)i * 8));
+                        ST_STAMP(t, 1);                                       // task starts
+                    }
+                    // ---- the row and its predecessor: slots and arrival
+                    int e_cur = 0, e_last = 0;
+                    if (lane == 0) {
+                        e_cur = ring_wait(&cs->slot_of[t & (ST_RING - 1)], t + 1, 8);
+                        if (t > 0) e_last = ring_wait(&cs->slot_of[(t - 1) & (ST_RING - 1)], t, 8);
+                    }
+                    e_cur = __shfl_sync(FULL, e_cur, 0);
+                    e_last = __shfl_sync(FULL, e_last, 0);
+                    s_cur = e_cur & 15;
+                    const int s_last = e_last & 15;
+                    mbar_wait(smem_u32(&cs->bars[s_cur]), (e_cur >> 4) & 1);
+                    float sim = -2.0f;
+                    if (lane == 0) ST_STAMP(t, 2);                            // row arrived
+                    if (t > 0) {
+                        mbar_wait(smem_u32(&cs->bars[s_last]), (e_last >> 4) & 1);
+                        // ---- similarity with the previous row of the chain (main.py:345-349 rounding chain)
+                        const uint4* lrow = reinterpret_cast<const uint4*>(slots + (size_t)s_last * a.slot_bytes);
+                        const uint4* crow = reinterpret_cast<const uint4*>(slots + (size_t)s_cur * a.slot_bytes);
+                        float2 dot2 = make_float2(0.f, 0.f), na2 = dot2, nb2 = dot2;
 #pragma unroll 2                                             // rolled: the I-cache is 32 KB, every role must stay small
-                    for (int v = lane; v < a.nvec; v += 32) acc_pair2<DT>(lrow[v], crow[v], dot2, na2, nb2);
-                    const float dot = warp_sum(dot2.x + dot2.y);
-                    const float na = warp_sum(na2.x + na2.y);
-                    const float nb = warp_sum(nb2.x + nb2.y);
-                    sim = finish_cosine<DT>(dot, na, nb);
-                    hit = sim >= a.thr;
+                        for (int v = lane; v < a.nvec; v += 32) acc_pair2<DT>(lrow[v], crow[v], dot2, na2, nb2);
+                        const float dot = warp_sum(dot2.x + dot2.y);
+                        const float na = warp_sum(na2.x + na2.y);
+                        const float nb = warp_sum(nb2.x + nb2.y);
+                        sim = finish_cosine<DT>(dot, na, nb);
+                        hit = sim >= a.thr;
+                    }
+                    if (lane == 0) {
+                        st_flag(a.state + i, (a.tag << 1) | (unsigned)hit);
+                        a.sim_seq[i] = sim;
+                        if (hit) a.dst[i] = -1;
+                        cs->small[t & (ST_RING - 1)][0] = small_new[0];
+                        cs->small[t & (ST_RING - 1)][1] = small_new[1];
+                        ST_STAMP(t, 3);                                       // flag published
+                        // the previous row is not read again by this task
+                        if (t > 0) release_slot(a, cs, chain_order, slots, s_last, 1, len, tx_bytes);
+                    }
                 }
-                if (lane == 0) {
-                    st_flag(a.state + i, (a.tag << 1) | (unsigned)hit);
-                    a.sim_seq[i] = sim;
-                    if (hit) a.dst[i] = -1;
-                    cs->small[t & (ST_RING - 1)][0] = small_new[0];
-                    cs->small[t & (ST_RING - 1)][1] = small_new[1];
-                    ST_STAMP(t, 3);                                          // flag published
-                    // the previous row is not read again by this task
-                    if (t > 0) release_slot(a, cs, chain_order, slots, s_last, 1, len, tx_bytes);
-                }
-            }
 
-            // ---- section A (row order, token A): book the row into the open anchor, or close it and open a new one.
-            //      Needs no position, so it never waits for other chains.
-            if (lane == 0) {
-                while (*(volatile int*)&cs->token_a != t) __nanosleep(40);
-                // the rings below are ST_RING deep: stay within reach of the slower section B
-                while (*(volatile int*)&cs->token_b < t - (ST_RING - 4)) __nanosleep(100);
-            }
-            __syncwarp();
-            __threadfence_block();
-            if (lane == 0 && have_row) ST_STAMP(t, 5);
-            int f2_slot = -1, f2_L = 0, f2_pos = 0, f2_k = 0, f2_t = 0;       // the anchor this section closes, if its position is known
-            unsigned long long f2_s0 = 0, f2_s1 = 0;
-            if (have_row && hit) {
-                const int an_slot = cs->anchor_slot;
-                uint4* arow = reinterpret_cast<uint4*>(slots + (size_t)an_slot * a.slot_bytes);
-                const uint4* crow = reinterpret_cast<const uint4*>(slots + (size_t)s_cur * a.slot_bytes);
-#pragma unroll 2
-                for (int v = lane; v < a.nvec; v += 32) arow[v] = add_round<DT>(arow[v], crow[v]);
+                // ---- section A (row order)
                 if (lane == 0) {
-                    cs->anchor_L += 1;
-                    cs->hits += 1;
-                    cs->keptbit[t & (ST_RING - 1)] = 0;
-                    cs->kc[t & (ST_RING - 1)] = cs->n_kept;
+                    while (*(volatile int*)&cs->token_a != t) __nanosleep(ST_POLL_NS);
+                    // the rings are ST_RING deep: stay within reach of the positioner
+                    while (*(volatile int*)&cs->token_b < t - (ST_RING - 4)) __nanosleep(2 * ST_POLL_NS);
+                    if (have_row) ST_STAMP(t, 5);
                 }
-            } else if (t <= len) {
-                int take = 0;
-                if (lane == 0) {
-                    const int an_t = cs->anchor_t;                            // only section A changes it
+                __syncwarp();
+                __threadfence_block();
+                if (have_row && hit) {
+                    const int an_slot = cs->anchor_slot;
+                    uint4* arow = reinterpret_cast<uint4*>(slots + (size_t)an_slot * a.slot_bytes);
+                    const uint4* crow = reinterpret_cast<const uint4*>(slots + (size_t)s_cur * a.slot_bytes);
+#pragma unroll 2
+                    for (int v = lane; v < a.nvec; v += 32) arow[v] = add_round<DT>(arow[v], crow[v]);
+                    if (lane == 0) {
+                        cs->anchor_L += 1;
+                        cs->hits += 1;
+                        cs->keptbit[t & (ST_RING - 1)] = 0;
+                        cs->kc[t & (ST_RING - 1)] = cs->n_kept;
+                    }
+                } else if (lane == 0) {
+                    const int an_t = cs->anchor_t;
                     chain_lock(cs);
-                    if (an_t >= 0) {
-                        const int an_pos = cs->anchor_pos;
-                        if (an_pos >= 0) {
-                            take = 1;
-                            f2_slot = cs->anchor_slot; f2_L = cs->anchor_L; f2_pos = an_pos; f2_k = cs->anchor_k; f2_t = an_t;
-                            f2_s0 = cs->anchor_small[0]; f2_s1 = cs->anchor_small[1];
-                        } else {                                              // park it: section B flushes it when it positions it
-                            cs->pend[an_t & (ST_RING - 1)] = (int)(0x80000000u | ((unsigned)cs->anchor_L << 4) | (unsigned)cs->anchor_slot);
-                            cs->pend_small[an_t & (ST_RING - 1)][0] = cs->anchor_small[0];
-                            cs->pend_small[an_t & (ST_RING - 1)][1] = cs->anchor_small[1];
-                        }
+                    if (an_t >= 0) {                                          // close the open anchor
+                        AnchorRec& r = cs->arec[an_t & (ST_RING - 1)];
+                        r.L = cs->anchor_L;
+                        r.closed = 1;
+                        if (r.positioned) push_flush(cs, r, an_t);
                     }
                     if (have_row) {                                           // this row is the new anchor
                         const int n_kept = cs->n_kept;
-                        cs->anchor_t = t; cs->anchor_slot = s_cur; cs->anchor_L = 0; cs->anchor_pos = -1; cs->anchor_k = n_kept;
-                        cs->anchor_small[0] = cs->small[t & (ST_RING - 1)][0];
-                        cs->anchor_small[1] = cs->small[t & (ST_RING - 1)][1];
+                        AnchorRec& r = cs->arec[t & (ST_RING - 1)];
+                        r.slot = s_cur; r.L = 0; r.pos = -1; r.k = n_kept; r.closed = 0; r.positioned = 0;
+                        r.small[0] = cs->small[t & (ST_RING - 1)][0];
+                        r.small[1] = cs->small[t & (ST_RING - 1)][1];
+                        cs->anchor_t = t; cs->anchor_slot = s_cur; cs->anchor_L = 0;
                         cs->keptbit[t & (ST_RING - 1)] = 1;
                         cs->kc[t & (ST_RING - 1)] = n_kept;
                         cs->n_kept = n_kept + 1;
@@ -574,98 +539,144 @@ k_stream_merge(const __grid_constant__ StreamArgs a) {
                     }
                     chain_unlock(cs);
                 }
-                take = __shfl_sync(FULL, take, 0);
-                if (take) {
-                    f2_slot = __shfl_sync(FULL, f2_slot, 0); f2_L = __shfl_sync(FULL, f2_L, 0); f2_pos = __shfl_sync(FULL, f2_pos, 0);
-                    f2_k = __shfl_sync(FULL, f2_k, 0); f2_t = __shfl_sync(FULL, f2_t, 0);
-                } else {
-                    f2_slot = -1;
-                }
-            }
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                *(volatile int*)&cs->token_a = t + 1;
-            }
-            if (lane == 0 && have_row) ST_STAMP(t, 6);                       // section A left
-
-            // ---- free-running: references of this task, the flush taken on in section A
-            if (lane == 0 && have_row) {
-                // this row as "current" (and as merge input when it was merged away), the previous one as "previous"
-                release_slot(a, cs, chain_order, slots, s_cur, hit ? 2 : 1, len, tx_bytes);
-            }
-            if (f2_slot >= 0) flush_anchor<DT>(a, cs, chain_order, slots, f2_slot, f2_L, f2_pos, f2_k, f2_t, f2_s0, f2_s1, len, tx_bytes);
-
-            // ---- gap count for row r = t - lag (waits for the flags of every chain up to there)
-            int gap = 0;
-            if (r >= 0) {
-                int kept = 0;
-                bool ok = f_two;
-                if (f_two) {
-                    if (f_at0 < f_hi) kept += count_kept_vec(fl0, f_at0, f_lo, f_hi, tag4, &ok);
-                    if (f_at1 < f_hi) kept += count_kept_vec(fl1, f_at1, f_lo, f_hi, tag4, &ok);
-                }
-                if (__all_sync(FULL, ok)) {
-                    kept = warp_sum_int(kept);
-                } else {
-                    // some flag was not published yet, or the gap is long: walk it 512 bytes at a time
-                    kept = 0;
-                    for (int chunk = f_al; chunk < f_hi; chunk += 512) {
-                        const int at = chunk + lane * 16;
-                        for (;;) {
-                            bool ok2 = true;
-                            int k2 = 0;
-                            if (at < f_hi) k2 = count_kept16(a.state, at, f_lo, f_hi, tag4, &ok2);
-                            if (__all_sync(FULL, ok2)) { kept += warp_sum_int(k2); break; }
-                            __nanosleep(200);
-                        }
-                    }
-                }
-                gap = kept;
-                if (lane == 0 && have_row) ST_STAMP(t, 4);                   // gap of row t - lag counted
-            }
-
-            // ---- section B (row order, token B): row r gets its position — kept rows outside the chain before it
-            //      (the gaps, summed) + kept rows of the chain before it — and, if it is a closed anchor, is flushed
-            int f1_slot = -1, f1_L = 0, f1_pos = 0, f1_k = 0, f1_t = 0;
-            unsigned long long f1_s0 = 0, f1_s1 = 0;
-            {
-                int take = 0;
+                __syncwarp();
                 if (lane == 0) {
-                    while (*(volatile int*)&cs->token_b != t) __nanosleep(40);
+                    if (!have_row) cs->a_done = 1;
                     __threadfence_block();
-                    if (r >= 0) {
-                        const int cum = cs->cum + gap;
-                        cs->cum = cum;
-                        if (cs->keptbit[r & (ST_RING - 1)]) {
-                            const int pos_r = cum + cs->kc[r & (ST_RING - 1)];
-                            chain_lock(cs);
-                            if (cs->anchor_t == r) {
-                                cs->anchor_pos = pos_r;                      // still open: whoever closes it flushes it
-                            } else {
-                                const int pe = cs->pend[r & (ST_RING - 1)];  // closed earlier and parked
-                                take = 1;
-                                f1_slot = pe & 15; f1_L = (pe >> 4) & 0x7ffffff; f1_pos = pos_r; f1_k = cs->kc[r & (ST_RING - 1)]; f1_t = r;
-                                f1_s0 = cs->pend_small[r & (ST_RING - 1)][0]; f1_s1 = cs->pend_small[r & (ST_RING - 1)][1];
-                            }
-                            chain_unlock(cs);
+                    *(volatile int*)&cs->token_a = t + 1;
+                    if (have_row) {
+                        ST_STAMP(t, 6);                                       // section A left
+                        // this row as "current", and as merge input when it was merged away (an anchor keeps that
+                        // reference until the flusher has written it)
+                        release_slot(a, cs, chain_order, slots, s_cur, hit ? 2 : 1, len, tx_bytes);
+                    }
+                }
+                __syncwarp();
+            }
+        } else if (role == a.n_sim) {
+            // =========================== positioner ===========================
+            // Walks the chain's rows in order and gives every kept one its compacted position: the kept rows outside
+            // the chain before it (the flag bytes between consecutive rows of the chain, counted gap by gap) + the
+            // kept rows of the chain before it.  The only warp of the chain that waits for other chains.
+            int cum = 0;
+            // the flag bytes of the next gap are requested one row ahead (when the gap fits two 16-byte loads per lane),
+            // so that the L2 round trip overlaps the bookkeeping of the current row
+            auto gap_bounds = [&](int r, int& lo, int& hi) {
+                hi = row_index(cs, chain_order, r);
+                lo = (r >= 1 ? row_index(cs, chain_order, r - 1) : -1) + 1;
+            };
+            uint4 pf0 = make_uint4(0, 0, 0, 0), pf1 = pf0;
+            bool pf_valid = false;
+            if (len > 0) {
+                int lo, hi;
+                gap_bounds(0, lo, hi);
+                const int al = lo & ~15;
+                pf_valid = (hi - al) <= 1024;
+                if (pf_valid && al + lane * 16 < hi) pf0 = ld_flags16(a.state + al + lane * 16);
+                if (pf_valid && al + 512 + lane * 16 < hi) pf1 = ld_flags16(a.state + al + 512 + lane * 16);
+            }
+            for (int r = 0; r < len; ++r) {
+                int f_lo, f_hi;
+                gap_bounds(r, f_lo, f_hi);
+                const int f_al = f_lo & ~15;
+                uint4 fl0 = pf0, fl1 = pf1;
+                bool first = pf_valid;                      // the prefetched vectors cover the whole gap
+                if (r + 1 < len) {                          // request the next gap now
+                    int lo, hi;
+                    gap_bounds(r + 1, lo, hi);
+                    const int al = lo & ~15;
+                    pf_valid = (hi - al) <= 1024;
+                    if (pf_valid && al + lane * 16 < hi) pf0 = ld_flags16(a.state + al + lane * 16);
+                    if (pf_valid && al + 512 + lane * 16 < hi) pf1 = ld_flags16(a.state + al + 512 + lane * 16);
+                }
+                int kept = 0;
+                for (int chunk = f_al; chunk < f_hi; chunk += 1024) {
+                    const int at0 = chunk + lane * 16, at1 = at0 + 512;
+                    for (;;) {
+                        bool ok = true;
+                        int k2 = 0;
+                        if (!first) {
+                            if (at0 < f_hi) fl0 = ld_flags16(a.state + at0);
+                            if (at1 < f_hi) fl1 = ld_flags16(a.state + at1);
                         }
+                        if (at0 < f_hi) k2 += count_kept_vec(fl0, at0, f_lo, f_hi, tag4, &ok);
+                        if (at1 < f_hi) k2 += count_kept_vec(fl1, at1, f_lo, f_hi, tag4, &ok);
+                        if (__all_sync(FULL, ok)) { kept += warp_sum_int(k2); first = false; break; }
+                        if (!first) __nanosleep(3 * ST_POLL_NS);
+                        first = false;
+                    }
+                }
+                cum += kept;
+                if (lane == 0) {
+                    while (*(volatile int*)&cs->token_a <= r) __nanosleep(ST_POLL_NS);           // section A of row r has run
+                    __threadfence_block();
+                    if (cs->keptbit[r & (ST_RING - 1)]) {
+                        chain_lock(cs);
+                        AnchorRec& rec = cs->arec[r & (ST_RING - 1)];
+                        rec.pos = cum + cs->kc[r & (ST_RING - 1)];
+                        rec.positioned = 1;
+                        if (rec.closed) push_flush(cs, rec, r);
+                        chain_unlock(cs);
                     }
                     __threadfence_block();
-                    *(volatile int*)&cs->token_b = t + 1;
+                    *(volatile int*)&cs->token_b = r + 1;
+                    if (r < ST_TRACE_T) ST_STAMP(r, 4);                        // row r positioned
                 }
-                take = __shfl_sync(FULL, take, 0);
-                if (take) {
-                    f1_slot = __shfl_sync(FULL, f1_slot, 0); f1_L = __shfl_sync(FULL, f1_L, 0); f1_pos = __shfl_sync(FULL, f1_pos, 0);
-                    f1_k = __shfl_sync(FULL, f1_k, 0); f1_t = __shfl_sync(FULL, f1_t, 0);
-                } else {
-                    f1_slot = -1;
-                }
+                __syncwarp();
             }
-            if (f1_slot >= 0) flush_anchor<DT>(a, cs, chain_order, slots, f1_slot, f1_L, f1_pos, f1_k, f1_t, f1_s0, f1_s1, len, tx_bytes);
-            __syncwarp();
-            if (t == len + K - 1 && lane == 0) {
-                // the last task of the chain: every row is booked
+        } else {
+            // =========================== flusher ===========================
+            // Writes closed and positioned anchors to their compacted positions and recycles their slots.
+            int done = 0;
+            for (;;) {
+                int have = 0, fin = 0;
+                if (lane == 0) {
+                    for (;;) {
+                        if (*(volatile int*)&cs->fq_head > done) { have = 1; break; }
+                        if (*(volatile int*)&cs->a_done && done == *(volatile int*)&cs->n_kept) { fin = 1; break; }
+                        if (len == 0) { fin = 1; break; }
+                        __nanosleep(2 * ST_POLL_NS);
+                    }
+                }
+                have = __shfl_sync(FULL, have, 0);
+                fin = __shfl_sync(FULL, fin, 0);
+                if (fin && !have) break;
+                __threadfence_block();
+                const FlushJob& j = cs->fq[done & (ST_RING - 1)];
+                const int slot = j.slot, L = j.L, pos = j.pos, k = j.k, t_a = j.t_a;
+                const unsigned long long sm0 = j.small[0], sm1 = j.small[1];
+                __syncwarp();
+                ++done;
+                if (lane == 0) *(volatile int*)&cs->fq_tail = done;
+
+                const unsigned char* arow = slots + (size_t)slot * a.slot_bytes;
+                char* orow = a.out + (size_t)pos * a.row_bytes;
+                if (L > 0) {                                                  // average of the run (main.py:314-317)
+                    const Divider<DT> dv(L + 1);
+#pragma unroll 1
+                    for (int v = lane; v < a.nvec; v += 32)
+                        st_stream16(orow + (size_t)v * 16, dv.vec(reinterpret_cast<const uint4*>(arow)[v]));
+                } else {
+#pragma unroll 2
+                    for (int v = lane; v < a.nvec; v += 32)
+                        st_stream16(orow + (size_t)v * 16, reinterpret_cast<const uint4*>(arow)[v]);
+                }
+#pragma unroll 1
+                for (int q = 0; q < a.n_tma_aux; ++q)
+                    if (lane * 16 < a.tma_aux[q].bytes)
+                        st_stream16(a.tma_aux[q].dst + (size_t)pos * a.tma_aux[q].bytes + lane * 16,
+                                    *reinterpret_cast<const uint4*>(arow + a.tma_aux[q].slot_off + lane * 16));
+                if (lane == 0) {
+                    if (a.n_small_aux > 0) *reinterpret_cast<unsigned long long*>(a.small_aux[0].dst + (size_t)pos * 8) = sm0;
+                    if (a.n_small_aux > 1) *reinterpret_cast<unsigned long long*>(a.small_aux[1].dst + (size_t)pos * 8) = sm1;
+                    a.dst[row_index(cs, chain_order, t_a)] = pos;
+                    a.order_next[cbase + k] = pos;
+                }
+                __syncwarp();
+                if (lane == 0) release_slot(a, cs, chain_order, slots, slot, 1, len, tx_bytes);
+            }
+            if (lane == 0) {
+                // the chain is finished: every kept row is written
                 if (id < a.n_ids) a.len_next[id] = cs->n_kept;
                 if (cs->hits) atomicAdd((unsigned long long*)&a.counters[C_COUNT], (unsigned long long)cs->hits);
             }
@@ -768,9 +779,9 @@ inline bool plan_stream(int sm_count, int max_smem, int64_t row_bytes, int n_ids
     if (n_ids < 1) return false;
     const int cpc = (n_ids + sm_count - 1) / sm_count;
     if (cpc > ST_MAX_CHAINS) return false;
-    int n_sim = (ST_MAX_WARPS - 1) / cpc;                  // warps per chain
-    if (n_sim > 5) n_sim = 5;
-    if (n_sim < 2) return false;
+    int n_sim = (ST_MAX_WARPS - 1) / cpc - 2;              // warps per chain: sims + positioner + flusher
+    if (n_sim > 4) n_sim = 4;
+    if (n_sim < 1) return false;
     const int slot = (int)((row_bytes + aux_bytes + 127) / 128 * 128);
     const size_t fixed = (size_t)cpc * sizeof(ChainShared) + 256;
     if ((size_t)max_smem < fixed + 64) return false;
@@ -784,7 +795,7 @@ inline bool plan_stream(int sm_count, int max_smem, int64_t row_bytes, int n_ids
     p->n_sim = n_sim;
     p->lag = n_slots >= 7 ? 3 : (n_slots >= 5 ? 2 : 1);    // rows t .. t + lag - 1 stay resident while merge(t) waits
     p->slot_bytes = slot;
-    p->threads = (cpc * n_sim + 1) * 32;
+    p->threads = (cpc * (n_sim + 2) + 1) * 32;
     p->smem = (size_t)cpc * n_slots * slot + fixed;
     return true;
 }
