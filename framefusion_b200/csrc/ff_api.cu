@@ -54,6 +54,8 @@ struct ff_ctx {
     unsigned epoch;      // single-pass calls since ff_build_links (tags the flag bytes)
     int sm_count;
     int max_smem;        // opt-in dynamic shared memory per block
+    char* scratch;       // device buffer of the single-pass kernel (averaged anchors in flight), owned by the context
+    size_t scratch_bytes;
     long long* trace;    // development aid: device buffer for the single-pass kernel's time stamps (ff_debug_trace)
 };
 
@@ -252,7 +254,7 @@ int check_shape(int64_t S, int64_t H, int dtype) {
 }
 
 // Fills the launch arguments of the single-pass kernel; false when the shape is outside what it handles.
-bool plan_stream_args(const ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* out, int dtype, int64_t S,
+bool plan_stream_args(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* out, int dtype, int64_t S,
                       int64_t H, double thr, double bound, const AuxPack& ap, StreamArgs* sa, StreamPlan* plan) {
     const int64_t eb = dtype == FF_F32 ? 4 : 2;
     const int64_t row_bytes = H * eb;
@@ -289,7 +291,16 @@ bool plan_stream_args(const ff_ctx* ctx, const Ws& w, int bank, const void* hidd
             return false;
         }
     }
-    if (!plan_stream(ctx->sm_count, ctx->max_smem, row_bytes, (int)ctx->n_ids, off - (int)row_bytes, plan)) return false;
+    if (!plan_stream(ctx->sm_count, ctx->max_smem, row_bytes, (int)ctx->n_ids, plan)) return false;
+    const size_t need = (size_t)ctx->n_ids * ST_SCRATCH * (size_t)row_bytes;
+    if (need > ctx->scratch_bytes) {                       // grows rarely: once per model shape
+        if (ctx->scratch) cudaFree(ctx->scratch);
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+        if (cudaMalloc((void**)&ctx->scratch, need) != cudaSuccess) { cudaGetLastError(); return false; }
+        ctx->scratch_bytes = need;
+    }
+    a.scratch = ctx->scratch;
     const int nb = bank ^ 1;
     a.hidden = (const char*)hidden;
     a.out = (char*)out;
@@ -301,7 +312,6 @@ bool plan_stream_args(const ff_ctx* ctx, const Ws& w, int bank, const void* hidd
     a.n_ids = (int)ctx->n_ids;
     a.cpc = plan->cpc;
     a.n_sim = plan->n_sim;
-    a.lag = plan->lag;
     a.order = w.order[bank];
     a.base = w.base;
     a.len = w.len[bank];
@@ -346,6 +356,8 @@ int ff_ctx_create(int device, ff_ctx** out) {
     c->have_order = c->have_lists = 0;
     c->epoch = 0;
     c->trace = nullptr;
+    c->scratch = nullptr;
+    c->scratch_bytes = 0;
     cudaError_t e = cudaHostAlloc((void**)&c->h_status, FF_ST_SLOTS * 8, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e != cudaSuccess) { delete c; return fail(FF_E_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
     memset(c->h_status, 0, FF_ST_SLOTS * 8);
@@ -361,6 +373,7 @@ int ff_ctx_create(int device, ff_ctx** out) {
 
 int ff_ctx_destroy(ff_ctx* ctx) {
     if (!ctx) return FF_OK;
+    if (ctx->scratch) cudaFree(ctx->scratch);
     cudaFreeHost(ctx->h_status);
     delete ctx;
     return FF_OK;

@@ -45,14 +45,15 @@ namespace ff {
 constexpr int ST_MAX_CHAINS = 8;                   // chains per CTA
 constexpr int ST_MAX_SLOTS = 12;                   // row slots per chain
 constexpr int ST_MIN_SLOTS = 3;
-constexpr int ST_RING = 16;                        // depth of the per-chain hand-over rings (> ST_MAX_SLOTS)
+constexpr int ST_RING = 32;                        // depth of the per-chain hand-over rings: how far the positioner may trail
+constexpr int ST_SCRATCH = 8;                      // averaged anchors per chain waiting in global memory for their position
 constexpr int ST_MAX_LEN = 256;                    // rows per chain the index window holds
 constexpr int ST_MAX_VPL = 16;                     // 16-byte vectors per lane: rows up to 8 KB
 constexpr int ST_MAX_TMA_AUX = 6;                  // (aux, plane) pairs carried through the slot, <= 512 bytes each
 constexpr int ST_MAX_SMALL_AUX = 2;                // 8-byte aux rows (patch_type, position ids)
 constexpr int ST_TRACE_T = 96, ST_TRACE_K = 8;    // development aid: rows x stamps per chain
 constexpr int ST_POLL_NS = 250;                    // back-off of the shared-memory polls: spinning warps steal issue slots
-constexpr int ST_MAX_WARPS = 24;                   // cpc * (n_sim + 2) + 1: 768 threads leave 80 registers each
+constexpr int ST_MAX_WARPS = 20;                   // cpc * (n_sim + 2): 640 threads leave 96 registers each
 
 struct StreamAux {
     const char* src;
@@ -78,6 +79,7 @@ struct StreamArgs {
     const int* len;
     int* order_next;                               // same layout, indices of the compacted sequence
     int* len_next;
+    char* scratch;                                 // [n_ids][ST_SCRATCH][row_bytes] averaged anchors on their way out
     uint8_t* state;                                // per sequence row: (tag << 1) | merged
     float* sim_seq;                                // per sequence row: similarity with the chain predecessor (introspection)
     int* dst;                                      // per sequence row: compacted position or -1
@@ -291,29 +293,27 @@ __device__ __forceinline__ int count_kept16(const uint8_t* state, int at, int lo
 
 // ---- the kernel --------------------------------------------------------------------------------------------
 // A kept row ("anchor") between its opening and its flush.  Shared by three parties under ChainShared::lock:
-// the sim warps close it (L is final), the positioner gives it its compacted position, whoever completes the
-// pair hands it to the flusher.
+// the sim warps close it (L is final, its average is in the scratch ring), the positioner gives it its compacted
+// position, whoever completes the pair hands it to the flusher.
 struct AnchorRec {
-    int slot, L, pos, k;                            // k = rank among the kept rows of the chain
-    int closed, positioned;
-    unsigned long long small[ST_MAX_SMALL_AUX];     // its 8-byte aux values (patch_type, position id)
+    int L, pos, t;                                  // t = chain position of the anchor
+    short closed, positioned;
+    int live;                                       // from the opening until it is handed to the flusher
 };
 
 struct FlushJob {
-    int slot, L, pos, k, t_a, pad;
-    unsigned long long small[ST_MAX_SMALL_AUX];
+    int L, pos, k, t_a;
 };
 
 // per-chain shared state (one per chain of the CTA, after the slots in dynamic shared memory)
 struct ChainShared {
     uint64_t bars[ST_MAX_SLOTS];                    // one mbarrier per slot
-    unsigned long long small[ST_RING][ST_MAX_SMALL_AUX];       // 8-byte aux values of row t at [t % ST_RING]
-    AnchorRec arec[ST_RING];                        // anchor t at [t % ST_RING]
+    AnchorRec arec[ST_RING];                        // the k-th kept row of the chain at [k % ST_RING]
+    int scr_busy[ST_SCRATCH];                       // scratch entry holds an average the flusher has not copied yet
     FlushJob fq[ST_RING];                           // flusher queue
     int idx[ST_MAX_LEN];                            // sequence index of every row of the chain
     int slot_of[ST_RING];                           // ((row + 1) << 8) | (parity << 4) | slot
-    int kc[ST_RING];                                // kept rows of this chain before row t (set in section A of t)
-    int keptbit[ST_RING];                           // row t was kept
+    int kc[ST_RING];                                // (kept rows of this chain before row t) << 1 | row t was kept
     int refcnt[ST_MAX_SLOTS];
     int uses[ST_MAX_SLOTS];
     int issued;                                     // rows requested so far
@@ -321,7 +321,8 @@ struct ChainShared {
     int token_a;                                    // row whose section A may run next (sim warps, row order)
     int token_b;                                    // rows the positioner is done with
     int lock;                                       // guards arec[] and the flusher queue head
-    int fq_head, fq_tail;                           // jobs pushed / popped
+    int fq_head;                                    // jobs pushed
+    int flushed;                                    // jobs the flusher has finished
     int a_done;                                     // section A of the last row has run: n_kept is final
     // owned by section A
     int anchor_t, anchor_slot, anchor_L;            // the open anchor
@@ -351,44 +352,106 @@ __device__ __forceinline__ int row_index(const ChainShared* cs, const int* chain
 
 // requests the next row of the chain into `slot` (called by one lane, only by whoever freed the slot)
 __device__ __noinline__ void issue_row(const StreamArgs& a, ChainShared* cs, const int* chain_order, unsigned char* slots,
-                                       int slot, int len, uint32_t tx_bytes) {
+                                       int slot, int len) {
     const int row = atomicAdd(&cs->issued, 1);
     if (row >= len) return;
     if (a.trace) { const int id = cs->chain_id; ST_STAMP(row, 0); }
     const int parity = cs->uses[slot] & 1;
     cs->uses[slot] += 1;
-    cs->refcnt[slot] = row + 1 < len ? 3 : 2;               // current of sim(row), previous of sim(row + 1), merge / flush
+    cs->refcnt[slot] = row + 1 < len ? 3 : 2;               // current of sim(row), previous of sim(row + 1), merge input / anchor
     __threadfence_block();
     *(volatile int*)&cs->slot_of[row & (ST_RING - 1)] = ((row + 1) << 8) | (parity << 4) | slot;
     const int i = row_index(cs, chain_order, row);
     const uint32_t bar = smem_u32(&cs->bars[slot]);
-    const uint32_t dst = smem_u32(slots + (size_t)slot * a.slot_bytes);
-    mbar_expect_tx(bar, tx_bytes);
-    tma_load(dst, a.hidden + (size_t)i * a.row_bytes, (uint32_t)a.row_bytes, bar);
-#pragma unroll 1
-    for (int q = 0; q < a.n_tma_aux; ++q)
-        tma_load(dst + a.tma_aux[q].slot_off, a.tma_aux[q].src + (size_t)i * a.tma_aux[q].bytes,
-                 (uint32_t)a.tma_aux[q].bytes, bar);
+    mbar_expect_tx(bar, (uint32_t)a.row_bytes);
+    tma_load(smem_u32(slots + (size_t)slot * a.slot_bytes), a.hidden + (size_t)i * a.row_bytes, (uint32_t)a.row_bytes, bar);
 }
 
 // drops `n` references of a slot; the last one out requests the next row of the chain into it (one lane)
 __device__ __forceinline__ void release_slot(const StreamArgs& a, ChainShared* cs, const int* chain_order, unsigned char* slots,
-                                             int slot, int n, int len, uint32_t tx_bytes) {
+                                             int slot, int n, int len) {
     __threadfence_block();                                  // our reads of the slot are done before the count drops
     if (atomicSub(&cs->refcnt[slot], n) == n) {
         __threadfence_block();                              // ... and everybody else's before the TMA engine overwrites it
         fence_async_smem();
-        issue_row(a, cs, chain_order, slots, slot, len, tx_bytes);
+        issue_row(a, cs, chain_order, slots, slot, len);
     }
 }
 
 // hands a closed and positioned anchor to the flusher (one lane, chain lock held)
-__device__ __forceinline__ void push_flush(ChainShared* cs, const AnchorRec& r, int t_a) {
+__device__ __forceinline__ void push_flush(ChainShared* cs, AnchorRec& r, int k) {
     FlushJob& j = cs->fq[cs->fq_head & (ST_RING - 1)];
-    j.slot = r.slot; j.L = r.L; j.pos = r.pos; j.k = r.k; j.t_a = t_a;
-    j.small[0] = r.small[0]; j.small[1] = r.small[1];
+    j.L = r.L; j.pos = r.pos; j.k = k; j.t_a = r.t;
+    r.live = 0;
     __threadfence_block();
     *(volatile int*)&cs->fq_head = cs->fq_head + 1;
+}
+
+__device__ __forceinline__ uint4 ld_cg16(const void* p) {                  // L2-coherent 16-byte load (scratch ring)
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+
+// ---- rows outside the chains (text, ids >= patch_num): bucket n_ids of the chain lists.  CTA b takes the rows
+// k = b, b + G, ...  Their flags are published before anything else (nothing depends on them being late), the rows
+// themselves are copied once the flags of everything before them are there.
+__device__ __noinline__ void text_publish(const StreamArgs& a) {
+    const int lane = threadIdx.x & 31;
+    const int n_text = __ldg(a.len + a.n_ids);
+    const int tbase = __ldg(a.base + a.n_ids);
+    const int G = gridDim.x;
+    for (int k = blockIdx.x + G * lane; k < n_text; k += G * 32) {
+        const int i = __ldg(a.order + tbase + k);
+        st_flag(a.state + i, a.tag << 1);
+    }
+    __syncwarp();
+}
+
+__device__ __noinline__ void text_copy(const StreamArgs& a, unsigned tag4) {
+    const int lane = threadIdx.x & 31;
+    const int n_text = __ldg(a.len + a.n_ids);
+    const int tbase = __ldg(a.base + a.n_ids);
+    const int G = gridDim.x;
+    int cursor = 0, cnt = 0;                                // kept rows in [0, cursor)
+    for (int k = blockIdx.x; k < n_text; k += G) {
+        const int i = __ldg(a.order + tbase + k);
+        // advance the scan to i, 512 bytes per step, waiting for unpublished flags
+        int at0 = cursor & ~15;
+        while (at0 < i) {
+            const int at = at0 + lane * 16;
+            bool ok = true;
+            int kept = 0;
+            if (at < i) kept = count_kept16(a.state, at, cursor, i, tag4, &ok);
+            if (!__all_sync(FULL, ok)) { __nanosleep(500); continue; }
+            cnt += warp_sum_int(kept);
+            at0 += 32 * 16;
+            cursor = at0 < i ? at0 : i;
+        }
+        cursor = i;
+        const int pos = cnt;
+        // copy the row and its aux rows through registers
+        const char* src = a.hidden + (size_t)i * a.row_bytes;
+        char* o = a.out + (size_t)pos * a.row_bytes;
+#pragma unroll 4
+        for (int v = lane; v < a.nvec; v += 32) st_stream16(o + (size_t)v * 16, ld_stream16(src + (size_t)v * 16));
+#pragma unroll 1
+        for (int q = 0; q < a.n_tma_aux; ++q) {
+            const StreamAux& x = a.tma_aux[q];
+            if (lane * 16 < x.bytes)
+                st_stream16(x.dst + (size_t)pos * x.bytes + lane * 16, ld_stream16(x.src + (size_t)i * x.bytes + lane * 16));
+        }
+        if (lane == 0) {
+            if (a.n_small_aux > 0) *reinterpret_cast<unsigned long long*>(a.small_aux[0].dst + (size_t)pos * 8) =
+                __ldg(reinterpret_cast<const unsigned long long*>(a.small_aux[0].src + (size_t)i * 8));
+            if (a.n_small_aux > 1) *reinterpret_cast<unsigned long long*>(a.small_aux[1].dst + (size_t)pos * 8) =
+                __ldg(reinterpret_cast<const unsigned long long*>(a.small_aux[1].src + (size_t)i * 8));
+            a.dst[i] = pos;
+            a.sim_seq[i] = -2.0f;
+            a.order_next[tbase + k] = pos;
+        }
+    }
+    if (blockIdx.x == 0 && lane == 0) a.len_next[a.n_ids] = n_text;
 }
 
 template <int DT>
@@ -402,9 +465,6 @@ k_stream_merge(const __grid_constant__ StreamArgs a) {
     const unsigned tag4 = (a.tag * 0x01010101u) << 1;       // the tag as it sits in every flag byte
 
     ChainShared* cs_base = reinterpret_cast<ChainShared*>(smem + (size_t)a.cpc * a.n_slots * a.slot_bytes);
-    uint32_t tx_bytes = (uint32_t)a.row_bytes;
-#pragma unroll 1
-    for (int q = 0; q < a.n_tma_aux; ++q) tx_bytes += (uint32_t)a.tma_aux[q].bytes;
 
     // ---- set-up: the first warp of every chain fills the chain's shared state
     if (chain < a.cpc && role == 0) {
@@ -413,12 +473,13 @@ k_stream_merge(const __grid_constant__ StreamArgs a) {
         const int len = id < a.n_ids ? __ldg(a.len + id) : 0;
         const int cbase = id < a.n_ids ? __ldg(a.base + id) : 0;
         for (int e = lane; e < ST_MAX_LEN; e += 32) cs->idx[e] = e < len ? __ldg(a.order + cbase + e) : 0;
-        if (lane < ST_RING) { cs->slot_of[lane] = 0; cs->kc[lane] = 0; cs->keptbit[lane] = 0; }
+        for (int e = lane; e < ST_RING; e += 32) { cs->slot_of[e] = 0; cs->kc[e] = 0; cs->arec[e].live = 0; }
+        if (lane < ST_SCRATCH) cs->scr_busy[lane] = 0;
         if (lane < ST_MAX_SLOTS) { cs->refcnt[lane] = 0; cs->uses[lane] = 0; }
         if (lane == 0) {
             cs->issued = 0;
             cs->chain_id = id;
-            cs->token_a = 0; cs->token_b = 0; cs->lock = 0; cs->fq_head = 0; cs->fq_tail = 0; cs->a_done = 0;
+            cs->token_a = 0; cs->token_b = 0; cs->lock = 0; cs->fq_head = 0; cs->flushed = 0; cs->a_done = 0;
             cs->anchor_t = -1; cs->anchor_slot = -1; cs->anchor_L = 0;
             cs->n_kept = 0; cs->hits = 0;
             for (int b = 0; b < a.n_slots; ++b) mbar_init(smem_u32(&cs->bars[b]), 1);
@@ -434,27 +495,24 @@ k_stream_merge(const __grid_constant__ StreamArgs a) {
         const int len = id < a.n_ids ? __ldg(a.len + id) : 0;
         const int cbase = id < a.n_ids ? __ldg(a.base + id) : 0;
         const int* chain_order = a.order + cbase;
+        char* scratch = a.scratch + (size_t)id * ST_SCRATCH * a.row_bytes;       // averaged anchors waiting for their position
 
         if (role < a.n_sim) {
             // =========================== sim warp ===========================
             // Rows t = role, role + n_sim, ...; task t == len only closes the last anchor.  A task: similarity and merge
             // flag of its row (free-running), then section A — entered in row order through the chain's token —
-            // which adds the row into the open anchor or closes that one and opens a new one.  Never waits for
-            // another chain.
+            // which adds the row into the open anchor or closes that one and opens a new one.  A closed anchor that
+            // absorbed rows is averaged into the chain's scratch ring (global memory, L2 resident); its slot is free
+            // again at once.  Sim warps never wait for another chain.
             if (role == 0 && lane == 0)
-                for (int b = 0; b < a.n_slots && b < len; ++b) issue_row(a, cs, chain_order, slots, b, len, tx_bytes);
+                for (int b = 0; b < a.n_slots && b < len; ++b) issue_row(a, cs, chain_order, slots, b, len);
 
             for (int t = role; t <= len && len > 0; t += a.n_sim) {
                 const bool have_row = t < len;
                 int s_cur = -1, hit = 0;
                 if (have_row) {
                     const int i = row_index(cs, chain_order, t);
-                    unsigned long long small_new[ST_MAX_SMALL_AUX] = {0, 0};
-                    if (lane == 0) {
-                        if (a.n_small_aux > 0) small_new[0] = __ldg(reinterpret_cast<const unsigned long long*>(a.small_aux[0].src + (size_t)i * 8));
-                        if (a.n_small_aux > 1) small_new[1] = __ldg(reinterpret_cast<const unsigned long long*>(a.small_aux[1].src + (size_t)i * 8));
-                        ST_STAMP(t, 1);                                       // task starts
-                    }
+                    if (lane == 0) ST_STAMP(t, 1);                            // task starts
                     // ---- the row and its predecessor: slots and arrival
                     int e_cur = 0, e_last = 0;
                     if (lane == 0) {
@@ -486,11 +544,9 @@ k_stream_merge(const __grid_constant__ StreamArgs a) {
                         st_flag(a.state + i, (a.tag << 1) | (unsigned)hit);
                         a.sim_seq[i] = sim;
                         if (hit) a.dst[i] = -1;
-                        cs->small[t & (ST_RING - 1)][0] = small_new[0];
-                        cs->small[t & (ST_RING - 1)][1] = small_new[1];
                         ST_STAMP(t, 3);                                       // flag published
                         // the previous row is not read again by this task
-                        if (t > 0) release_slot(a, cs, chain_order, slots, s_last, 1, len, tx_bytes);
+                        if (t > 0) release_slot(a, cs, chain_order, slots, s_last, 1, len);
                     }
                 }
 
@@ -503,6 +559,7 @@ k_stream_merge(const __grid_constant__ StreamArgs a) {
                 }
                 __syncwarp();
                 __threadfence_block();
+                int c_t = -1, c_slot = -1, c_L = 0, c_k = 0;                  // the anchor this section closes
                 if (have_row && hit) {
                     const int an_slot = cs->anchor_slot;
                     uint4* arow = reinterpret_cast<uint4*>(slots + (size_t)an_slot * a.slot_bytes);
@@ -512,43 +569,71 @@ k_stream_merge(const __grid_constant__ StreamArgs a) {
                     if (lane == 0) {
                         cs->anchor_L += 1;
                         cs->hits += 1;
-                        cs->keptbit[t & (ST_RING - 1)] = 0;
-                        cs->kc[t & (ST_RING - 1)] = cs->n_kept;
+                        cs->kc[t & (ST_RING - 1)] = cs->n_kept << 1;
                     }
-                } else if (lane == 0) {
-                    const int an_t = cs->anchor_t;
-                    chain_lock(cs);
-                    if (an_t >= 0) {                                          // close the open anchor
-                        AnchorRec& r = cs->arec[an_t & (ST_RING - 1)];
-                        r.L = cs->anchor_L;
-                        r.closed = 1;
-                        if (r.positioned) push_flush(cs, r, an_t);
+                } else {
+                    c_t = cs->anchor_t; c_slot = cs->anchor_slot; c_L = cs->anchor_L;
+                    c_k = cs->n_kept - 1;                                     // the open anchor is the latest kept row
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (have_row) {                                       // this row is the new anchor
+                            const int n_kept = cs->n_kept;
+                            AnchorRec& r = cs->arec[n_kept & (ST_RING - 1)];
+                            // the record and the flusher queue are rings: wait for their previous occupants
+                            while (*(volatile int*)&r.live || *(volatile int*)&cs->flushed < n_kept - (ST_RING - 8)) __nanosleep(2 * ST_POLL_NS);
+                            chain_lock(cs);
+                            r.L = 0; r.pos = -1; r.t = t; r.closed = 0; r.positioned = 0; r.live = 1;
+                            chain_unlock(cs);
+                            cs->anchor_t = t; cs->anchor_slot = s_cur; cs->anchor_L = 0;
+                            cs->kc[t & (ST_RING - 1)] = (n_kept << 1) | 1;
+                            cs->n_kept = n_kept + 1;
+                        } else {
+                            cs->anchor_t = -1;
+                        }
                     }
-                    if (have_row) {                                           // this row is the new anchor
-                        const int n_kept = cs->n_kept;
-                        AnchorRec& r = cs->arec[t & (ST_RING - 1)];
-                        r.slot = s_cur; r.L = 0; r.pos = -1; r.k = n_kept; r.closed = 0; r.positioned = 0;
-                        r.small[0] = cs->small[t & (ST_RING - 1)][0];
-                        r.small[1] = cs->small[t & (ST_RING - 1)][1];
-                        cs->anchor_t = t; cs->anchor_slot = s_cur; cs->anchor_L = 0;
-                        cs->keptbit[t & (ST_RING - 1)] = 1;
-                        cs->kc[t & (ST_RING - 1)] = n_kept;
-                        cs->n_kept = n_kept + 1;
-                    } else {
-                        cs->anchor_t = -1;
-                    }
-                    chain_unlock(cs);
                 }
                 __syncwarp();
                 if (lane == 0) {
-                    if (!have_row) cs->a_done = 1;
                     __threadfence_block();
                     *(volatile int*)&cs->token_a = t + 1;
+                    if (have_row) ST_STAMP(t, 6);                             // section A left
+                }
+
+                // ---- free-running again: finish the anchor that was closed, then the references of this task
+                if (c_t >= 0) {
+                    if (c_L > 0) {
+                        // average of the run (main.py:314-317) -> scratch ring, where the flusher picks it up
+                        if (lane == 0) {
+                            while (*(volatile int*)&cs->scr_busy[c_k % ST_SCRATCH]) __nanosleep(2 * ST_POLL_NS);
+                            cs->scr_busy[c_k % ST_SCRATCH] = 1;
+                        }
+                        __syncwarp();
+                        const uint4* arow = reinterpret_cast<const uint4*>(slots + (size_t)c_slot * a.slot_bytes);
+                        char* srow = scratch + (size_t)(c_k % ST_SCRATCH) * a.row_bytes;
+                        const Divider<DT> dv(c_L + 1);
+#pragma unroll 1
+                        for (int v = lane; v < a.nvec; v += 32) *reinterpret_cast<uint4*>(srow + (size_t)v * 16) = dv.vec(arow[v]);
+                        __threadfence();                                      // visible device-wide before it is announced
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        chain_lock(cs);
+                        AnchorRec& r = cs->arec[c_k & (ST_RING - 1)];
+                        r.L = c_L;
+                        r.closed = 1;
+                        if (r.positioned) push_flush(cs, r, c_k);
+                        chain_unlock(cs);
+                        release_slot(a, cs, chain_order, slots, c_slot, 1, len);     // the anchor's own reference
+                    }
+                }
+                if (lane == 0) {
                     if (have_row) {
-                        ST_STAMP(t, 6);                                       // section A left
                         // this row as "current", and as merge input when it was merged away (an anchor keeps that
-                        // reference until the flusher has written it)
-                        release_slot(a, cs, chain_order, slots, s_cur, hit ? 2 : 1, len, tx_bytes);
+                        // reference until it is closed)
+                        release_slot(a, cs, chain_order, slots, s_cur, hit ? 2 : 1, len);
+                    } else {
+                        __threadfence_block();
+                        *(volatile int*)&cs->a_done = 1;
                     }
                 }
                 __syncwarp();
@@ -608,33 +693,36 @@ k_stream_merge(const __grid_constant__ StreamArgs a) {
                 }
                 cum += kept;
                 if (lane == 0) {
-                    while (*(volatile int*)&cs->token_a <= r) __nanosleep(ST_POLL_NS);           // section A of row r has run
+                    while (*(volatile int*)&cs->token_a <= r) __nanosleep(ST_POLL_NS);   // section A of row r has run
                     __threadfence_block();
-                    if (cs->keptbit[r & (ST_RING - 1)]) {
+                    const int kc = cs->kc[r & (ST_RING - 1)];
+                    if (kc & 1) {
                         chain_lock(cs);
-                        AnchorRec& rec = cs->arec[r & (ST_RING - 1)];
-                        rec.pos = cum + cs->kc[r & (ST_RING - 1)];
+                        AnchorRec& rec = cs->arec[(kc >> 1) & (ST_RING - 1)];
+                        rec.pos = cum + (kc >> 1);
                         rec.positioned = 1;
-                        if (rec.closed) push_flush(cs, rec, r);
+                        if (rec.closed) push_flush(cs, rec, kc >> 1);
                         chain_unlock(cs);
                     }
                     __threadfence_block();
                     *(volatile int*)&cs->token_b = r + 1;
-                    if (r < ST_TRACE_T) ST_STAMP(r, 4);                        // row r positioned
+                    ST_STAMP(r, 4);                                            // row r positioned
                 }
                 __syncwarp();
             }
         } else {
             // =========================== flusher ===========================
-            // Writes closed and positioned anchors to their compacted positions and recycles their slots.
+            // Copies closed and positioned anchors to their compacted positions: the row from hidden_states (still in
+            // L2 — it went through the TMA a moment ago) or, when it absorbed other rows, from the scratch ring; the
+            // cos / sin / patch_type entries straight from their source tensors.
+            if (chain == 0) text_publish(a);                  // the CTA's share of the rows outside the chains
             int done = 0;
             for (;;) {
                 int have = 0, fin = 0;
                 if (lane == 0) {
                     for (;;) {
                         if (*(volatile int*)&cs->fq_head > done) { have = 1; break; }
-                        if (*(volatile int*)&cs->a_done && done == *(volatile int*)&cs->n_kept) { fin = 1; break; }
-                        if (len == 0) { fin = 1; break; }
+                        if (len == 0 || (*(volatile int*)&cs->a_done && done == *(volatile int*)&cs->n_kept)) { fin = 1; break; }
                         __nanosleep(2 * ST_POLL_NS);
                     }
                 }
@@ -643,94 +731,56 @@ k_stream_merge(const __grid_constant__ StreamArgs a) {
                 if (fin && !have) break;
                 __threadfence_block();
                 const FlushJob& j = cs->fq[done & (ST_RING - 1)];
-                const int slot = j.slot, L = j.L, pos = j.pos, k = j.k, t_a = j.t_a;
-                const unsigned long long sm0 = j.small[0], sm1 = j.small[1];
+                const int L = j.L, pos = j.pos, k = j.k, t_a = j.t_a;
+                const int i_a = row_index(cs, chain_order, t_a);
+                __syncwarp();
+
+                // the whole row is requested at once (up to 16 x 512 bytes in flight per warp): one L2 round trip per row
+                char* orow = a.out + (size_t)pos * a.row_bytes;
+                uint4 buf[ST_MAX_VPL];
+                if (L > 0) {
+                    const char* srow = scratch + (size_t)(k % ST_SCRATCH) * a.row_bytes;
+#pragma unroll
+                    for (int q = 0; q < ST_MAX_VPL; ++q)
+                        if (lane + 32 * q < a.nvec) buf[q] = ld_cg16(srow + (size_t)(lane + 32 * q) * 16);
+                } else {
+                    const char* srow = a.hidden + (size_t)i_a * a.row_bytes;
+#pragma unroll
+                    for (int q = 0; q < ST_MAX_VPL; ++q)
+                        if (lane + 32 * q < a.nvec) buf[q] = ld_stream16(srow + (size_t)(lane + 32 * q) * 16);
+                }
+#pragma unroll
+                for (int q = 0; q < ST_MAX_VPL; ++q)
+                    if (lane + 32 * q < a.nvec) st_stream16(orow + (size_t)(lane + 32 * q) * 16, buf[q]);
+#pragma unroll 1
+                for (int q = 0; q < a.n_tma_aux; ++q) {
+                    const StreamAux& x = a.tma_aux[q];
+                    if (lane * 16 < x.bytes)
+                        st_stream16(x.dst + (size_t)pos * x.bytes + lane * 16, ld_stream16(x.src + (size_t)i_a * x.bytes + lane * 16));
+                }
+                if (lane == 0) {
+                    if (a.n_small_aux > 0) *reinterpret_cast<unsigned long long*>(a.small_aux[0].dst + (size_t)pos * 8) =
+                        __ldg(reinterpret_cast<const unsigned long long*>(a.small_aux[0].src + (size_t)i_a * 8));
+                    if (a.n_small_aux > 1) *reinterpret_cast<unsigned long long*>(a.small_aux[1].dst + (size_t)pos * 8) =
+                        __ldg(reinterpret_cast<const unsigned long long*>(a.small_aux[1].src + (size_t)i_a * 8));
+                    a.dst[i_a] = pos;
+                    a.order_next[cbase + k] = pos;
+                    ST_STAMP(t_a, 7);                                          // anchor written
+                }
                 __syncwarp();
                 ++done;
-                if (lane == 0) *(volatile int*)&cs->fq_tail = done;
-
-                const unsigned char* arow = slots + (size_t)slot * a.slot_bytes;
-                char* orow = a.out + (size_t)pos * a.row_bytes;
-                if (L > 0) {                                                  // average of the run (main.py:314-317)
-                    const Divider<DT> dv(L + 1);
-#pragma unroll 1
-                    for (int v = lane; v < a.nvec; v += 32)
-                        st_stream16(orow + (size_t)v * 16, dv.vec(reinterpret_cast<const uint4*>(arow)[v]));
-                } else {
-#pragma unroll 2
-                    for (int v = lane; v < a.nvec; v += 32)
-                        st_stream16(orow + (size_t)v * 16, reinterpret_cast<const uint4*>(arow)[v]);
-                }
-#pragma unroll 1
-                for (int q = 0; q < a.n_tma_aux; ++q)
-                    if (lane * 16 < a.tma_aux[q].bytes)
-                        st_stream16(a.tma_aux[q].dst + (size_t)pos * a.tma_aux[q].bytes + lane * 16,
-                                    *reinterpret_cast<const uint4*>(arow + a.tma_aux[q].slot_off + lane * 16));
                 if (lane == 0) {
-                    if (a.n_small_aux > 0) *reinterpret_cast<unsigned long long*>(a.small_aux[0].dst + (size_t)pos * 8) = sm0;
-                    if (a.n_small_aux > 1) *reinterpret_cast<unsigned long long*>(a.small_aux[1].dst + (size_t)pos * 8) = sm1;
-                    a.dst[row_index(cs, chain_order, t_a)] = pos;
-                    a.order_next[cbase + k] = pos;
+                    if (L > 0) *(volatile int*)&cs->scr_busy[k % ST_SCRATCH] = 0;   // the scratch entry of this job is free again
+                    *(volatile int*)&cs->flushed = done;
                 }
-                __syncwarp();
-                if (lane == 0) release_slot(a, cs, chain_order, slots, slot, 1, len, tx_bytes);
             }
             if (lane == 0) {
                 // the chain is finished: every kept row is written
                 if (id < a.n_ids) a.len_next[id] = cs->n_kept;
                 if (cs->hits) atomicAdd((unsigned long long*)&a.counters[C_COUNT], (unsigned long long)cs->hits);
             }
+            if (chain == 0) text_copy(a, tag4);
         }
-    } else if (warp == a.cpc * wpc) {
-        // =========================== rows outside the chains ===========================
-        const int n_text = __ldg(a.len + a.n_ids);
-        const int tbase = __ldg(a.base + a.n_ids);
-        const int G = gridDim.x;
-        // publish the flags first: nobody depends on anything here
-        for (int k = blockIdx.x + G * lane; k < n_text; k += G * 32) {
-            const int i = __ldg(a.order + tbase + k);
-            st_flag(a.state + i, a.tag << 1);
-        }
-        __syncwarp();
-        int cursor = 0, cnt = 0;                            // kept rows in [0, cursor)
-        for (int k = blockIdx.x; k < n_text; k += G) {
-            const int i = __ldg(a.order + tbase + k);
-            // advance the scan to i, 512 bytes per step, waiting for unpublished flags
-            int at0 = cursor & ~15;
-            while (at0 < i) {
-                const int at = at0 + lane * 16;
-                bool ok = true;
-                int kept = 0;
-                if (at < i) kept = count_kept16(a.state, at, cursor, i, tag4, &ok);
-                if (!__all_sync(FULL, ok)) { __nanosleep(500); continue; }
-                cnt += warp_sum_int(kept);
-                at0 += 32 * 16;
-                cursor = at0 < i ? at0 : i;
-            }
-            cursor = i;
-            const int pos = cnt;
-            // copy the row and its aux rows through registers
-            const char* src = a.hidden + (size_t)i * a.row_bytes;
-            char* o = a.out + (size_t)pos * a.row_bytes;
-            for (int v = lane; v < a.nvec; v += 32) st_stream16(o + (size_t)v * 16, ld_stream16(src + (size_t)v * 16));
-#pragma unroll 1
-            for (int q = 0; q < a.n_tma_aux; ++q) {
-                const StreamAux& x = a.tma_aux[q];
-                for (int v = lane; v < x.bytes / 16; v += 32)
-                    reinterpret_cast<uint4*>(x.dst + (size_t)pos * x.bytes)[v] =
-                        __ldg(reinterpret_cast<const uint4*>(x.src + (size_t)i * x.bytes) + v);
-            }
-            if (lane == 0) {
-#pragma unroll 1
-                for (int q = 0; q < a.n_small_aux; ++q)
-                    *reinterpret_cast<uint64_t*>(a.small_aux[q].dst + (size_t)pos * 8) =
-                        __ldg(reinterpret_cast<const uint64_t*>(a.small_aux[q].src + (size_t)i * 8));
-                a.dst[i] = pos;
-                a.sim_seq[i] = -2.0f;
-                a.order_next[tbase + k] = pos;
-            }
-        }
-        if (blockIdx.x == 0 && lane == 0) a.len_next[a.n_ids] = n_text;
     }
 
     // ---- last CTA out: the branch decision and the status block (main.py:112-127)
@@ -775,14 +825,14 @@ struct StreamPlan {
 };
 
 // Returns false when the shape is outside the single-pass kernel (caller falls back to the generic path).
-inline bool plan_stream(int sm_count, int max_smem, int64_t row_bytes, int n_ids, int aux_bytes, StreamPlan* p) {
+inline bool plan_stream(int sm_count, int max_smem, int64_t row_bytes, int n_ids, StreamPlan* p) {
     if (n_ids < 1) return false;
     const int cpc = (n_ids + sm_count - 1) / sm_count;
     if (cpc > ST_MAX_CHAINS) return false;
-    int n_sim = (ST_MAX_WARPS - 1) / cpc - 2;              // warps per chain: sims + positioner + flusher
+    int n_sim = ST_MAX_WARPS / cpc - 2;                    // warps per chain: sims + positioner + flusher
     if (n_sim > 4) n_sim = 4;
     if (n_sim < 1) return false;
-    const int slot = (int)((row_bytes + aux_bytes + 127) / 128 * 128);
+    const int slot = (int)((row_bytes + 127) / 128 * 128);
     const size_t fixed = (size_t)cpc * sizeof(ChainShared) + 256;
     if ((size_t)max_smem < fixed + 64) return false;
     const size_t avail = (size_t)max_smem - fixed - 64;
@@ -795,7 +845,7 @@ inline bool plan_stream(int sm_count, int max_smem, int64_t row_bytes, int n_ids
     p->n_sim = n_sim;
     p->lag = n_slots >= 7 ? 3 : (n_slots >= 5 ? 2 : 1);    // rows t .. t + lag - 1 stay resident while merge(t) waits
     p->slot_bytes = slot;
-    p->threads = (cpc * (n_sim + 2) + 1) * 32;
+    p->threads = cpc * (n_sim + 2) * 32;
     p->smem = (size_t)cpc * n_slots * slot + fixed;
     return true;
 }
