@@ -75,7 +75,10 @@ struct Ws {
     uint8_t* state;
     int* dst[2];
     int* srcidx;
+    int2* desc;         // [cap] (by-patch position, run length) per destination row
     int* hist;
+    int* part;          // [2 * 160] per-block counts of the multi-block scan
+    unsigned* barrier;  // its grid barrier
     int* base;          // [n_ids + 1] start of every chain list inside order[]
     size_t bytes;
 };
@@ -102,8 +105,11 @@ Ws carve(void* base_ptr, int64_t cap, int64_t n_ids) {
     w.dst[0] = (int*)take(cap * 4);
     w.dst[1] = (int*)take(cap * 4);
     w.srcidx = (int*)take(cap * 4);
+    w.desc = (int2*)take(cap * 8);
     w.hist = (int*)take((size_t)n_chunks * (size_t)(n_ids + 1) * 4);
     w.base = (int*)take((size_t)(n_ids + 1) * 4);
+    w.part = (int*)take(2 * 160 * 4);
+    w.barrier = (unsigned*)take(256);
     w.bytes = off;
     return w;
 }
@@ -233,6 +239,30 @@ int launch_merge_compact(const Ws& w, int bank, const void* hidden, void* out, i
         FF_LAUNCH_CHECK("k_merge_compact");
         return (int)FF_OK;
     });
+}
+
+
+// merged rows + compaction of hidden and aux, two-pass path: the gather kernel when rows are 16-byte multiples,
+// the generic kernels otherwise
+int launch_merge_gather(const ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* out, int dtype, int64_t S,
+                        int64_t H, const AuxPack& ap, cudaStream_t st) {
+    if (S == 0) return FF_OK;
+    const int64_t nvec = H * (dtype == FF_F32 ? 4 : 2) / 16;
+    if (vec_ok(hidden, out, H, dtype)) {
+        return dispatch_dtype(dtype, [&](auto dt) {
+            constexpr int DT = decltype(dt)::value;
+            k_merge_gather<DT><<<(int)((S + 7) / 8), 256, 0, st>>>(hidden, out, (int)nvec, w.srcidx, w.desc, w.order[bank], w.flag,
+                                                               w.counters[bank], ap);
+            FF_LAUNCH_CHECK("k_merge_gather");
+            return (int)FF_OK;
+        });
+    }
+    if (int rc = launch_merge_compact(w, bank, hidden, out, dtype, S, H, 1, st)) return rc;
+    if (ap.n) {
+        k_aux_compact<<<(int)((S + 7) / 8), 256, 0, st>>>(ap, (int)S, w.dst[bank]);
+        FF_LAUNCH_CHECK("k_aux_compact");
+    }
+    return FF_OK;
 }
 
 // the sequence length the links describe becomes known to the host only after it has synchronised and read
@@ -528,18 +558,30 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     a.rank = w.rank[bank];
     a.dst = w.dst[bank];
     a.srcidx = w.srcidx;
+    a.desc = w.desc;
     a.order_next = w.order[nb];
     a.chain_next = w.chain[nb];
     a.rank_next = w.rank[nb];
     a.counters_next = w.counters[nb];
     a.force_branch = -1;
+    a.topk_only = 0;
+    if (S >= 4 * SEL_TILE) {
+        // threshold branch on a grid of co-resident blocks; k_decide_scan then only runs for the top-k branch
+        ScanArgs sa;
+        sa.d = a;
+        sa.part = w.part;
+        sa.barrier = w.barrier;
+        int G = ctx->sm_count / 2;
+        if (G > 160) G = 160;
+        if (G < 1) G = 1;
+        FF_CUDA(cudaMemsetAsync(w.barrier, 0, 4, st));
+        k_keep_scan<<<G, SEL_THREADS, 0, st>>>(sa);
+        FF_LAUNCH_CHECK("k_keep_scan");
+        a.topk_only = 1;
+    }
     k_decide_scan<<<1, SEL_THREADS, 0, st>>>(a);
     FF_LAUNCH_CHECK("k_decide_scan");
-    if (int rc = launch_merge_compact(w, bank, hidden, hidden_out, dtype, S, H, 1, st)) return rc;
-    if (ap.n && S > 0) {
-        k_aux_compact<<<(int)((S + 7) / 8), 256, 0, st>>>(ap, (int)S, w.dst[bank]);
-        FF_LAUNCH_CHECK("k_aux_compact");
-    }
+    if (int rc = launch_merge_gather(ctx, w, bank, hidden, hidden_out, dtype, S, H, ap, st)) return rc;
     ctx->last_parity = bank;
     ctx->parity = nb;
     ctx->links_S = -2;                                     // = S_keep, known once the host has synchronised

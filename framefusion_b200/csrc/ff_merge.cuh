@@ -104,6 +104,98 @@ k_merge_compact(const void* __restrict__ hidden, void* __restrict__ out, int S, 
     merge_row<DT, VEC, false>(hidden, orow, src, H, lane, order, j, L, wrapL);
 }
 
+// ---- aux tensors (cos, sin, patch_type, position ids): row copy src[i] -> dst[dst_row[i]] ----------
+struct AuxPack {
+    ff_aux a[FF_MAX_AUX];
+    int n;
+};
+
+// ---- the same, tuned for the two-pass path at full size.  One warp per DESTINATION row, last rows first: the
+// similarity pass has just streamed the sequence front to back, so its tail is what the L2 still holds.
+// srcidx[d] and desc[d] = (by-patch position, run length) come from the scan kernel, so a row needs one dependent
+// load before its data is requested and no warp is launched for a row that was merged away.  Thin warps, full
+// occupancy: four 16-byte vectors per lane in flight per step; an anchor requests the same four vectors of every
+// run member together (main.py:304-311 order of the adds), i.e. one memory round trip per step instead of one per
+// vector and member.  The aux rows (cos, sin, patch_type, position ids) ride along.
+template <int DT>
+__global__ void __launch_bounds__(256, 4)
+k_merge_gather(const void* __restrict__ hidden, void* __restrict__ out, int nvec, const int* __restrict__ srcidx,
+               const int2* __restrict__ desc, const int* __restrict__ order, const uint8_t* __restrict__ flag,
+               const int64_t* __restrict__ counters, const __grid_constant__ AuxPack aux) {
+    const int lane = threadIdx.x & 31;
+    const int d = (int)counters[C_SKEEP] - 1 - (blockIdx.x * 8 + (threadIdx.x >> 5));
+    if (d < 0) return;
+    const int i = srcidx[d];
+    const int2 ds = desc ? desc[d] : make_int2(-1, 0);
+    const int64_t row_bytes = (int64_t)nvec * 16;
+    const char* src = (const char*)hidden + (int64_t)i * row_bytes;
+    char* orow = (char*)out + (int64_t)d * row_bytes;
+    const int j = ds.x;
+    int L = ds.y, wrapL = 0;
+    if (j >= 0) {
+        const int N = (int)counters[C_N];
+        if (j == N - 1 && N > 1 && flag[0]) wrapL = run_after(flag, -1, N - 1);       // main.py:290 wrap-around
+    }
+    if (L + wrapL == 0) {
+        int v = lane;
+        for (; v + 96 < nvec; v += 128) {
+            const uint4 a0 = ld_stream16(src + (int64_t)v * 16), a1 = ld_stream16(src + (int64_t)(v + 32) * 16);
+            const uint4 a2 = ld_stream16(src + (int64_t)(v + 64) * 16), a3 = ld_stream16(src + (int64_t)(v + 96) * 16);
+            st_stream16(orow + (int64_t)v * 16, a0);
+            st_stream16(orow + (int64_t)(v + 32) * 16, a1);
+            st_stream16(orow + (int64_t)(v + 64) * 16, a2);
+            st_stream16(orow + (int64_t)(v + 96) * 16, a3);
+        }
+        for (; v < nvec; v += 32) st_stream16(orow + (int64_t)v * 16, ld_stream16(src + (int64_t)v * 16));
+    } else {
+        const Divider<DT> dv(L + wrapL + 1);
+        for (int v0 = lane; v0 < nvec; v0 += 128) {
+            uint4 acc[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (v0 + 32 * q < nvec) acc[q] = ld_stream16(src + (int64_t)(v0 + 32 * q) * 16);
+            for (int m = 0; m < L + wrapL; ++m) {
+                const int jm = m < L ? j + 1 + m : m - L;
+                const char* mr = (const char*)hidden + (int64_t)order[jm] * row_bytes;
+                uint4 x[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (v0 + 32 * q < nvec) x[q] = ldg16(mr + (int64_t)(v0 + 32 * q) * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (v0 + 32 * q < nvec) {
+                        float a[Num<DT>::EPV], b[Num<DT>::EPV];
+                        Num<DT>::unpack(acc[q], a);
+                        Num<DT>::unpack(x[q], b);
+#pragma unroll
+                        for (int e = 0; e < Num<DT>::EPV; ++e) a[e] = a[e] + b[e];
+                        acc[q] = Num<DT>::pack(a);
+                    }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (v0 + 32 * q < nvec) st_stream16(orow + (int64_t)(v0 + 32 * q) * 16, dv.vec(acc[q]));
+        }
+    }
+#pragma unroll 1
+    for (int q = 0; q < aux.n; ++q) {
+        const ff_aux& x = aux.a[q];
+        for (int64_t pl = 0; pl < x.planes; ++pl) {
+            const char* s = (const char*)x.src + pl * x.src_plane_stride + (int64_t)i * x.row_bytes;
+            char* o = (char*)x.dst + pl * x.dst_plane_stride + (int64_t)d * x.row_bytes;
+            if (((x.row_bytes | (int64_t)(uintptr_t)s | (int64_t)(uintptr_t)o) & 15) == 0) {
+                for (int64_t v = lane; v < x.row_bytes / 16; v += 32)
+                    reinterpret_cast<uint4*>(o)[v] = __ldg(reinterpret_cast<const uint4*>(s) + v);
+            } else if (((x.row_bytes | (int64_t)(uintptr_t)s | (int64_t)(uintptr_t)o) & 7) == 0) {
+                for (int64_t v = lane; v < x.row_bytes / 8; v += 32)
+                    reinterpret_cast<uint2*>(o)[v] = __ldg(reinterpret_cast<const uint2*>(s) + v);
+            } else {
+                for (int64_t v = lane; v < x.row_bytes; v += 32) o[v] = s[v];
+            }
+        }
+    }
+}
+
 // ---- in-place variant behind the reference's static merge_tokens_and_get_mask (main.py:243-319):
 // one warp per by-patch position; anchors are rewritten in place, nothing is compacted.
 template <int DT, bool VEC>
@@ -135,12 +227,6 @@ __global__ void k_flags_from_index(const int64_t* __restrict__ merge_index, int 
         }
     }
 }
-
-// ---- aux tensors (cos, sin, patch_type, position ids): row copy src[i] -> dst[dst_row[i]] ----------
-struct AuxPack {
-    ff_aux a[FF_MAX_AUX];
-    int n;
-};
 
 __global__ void __launch_bounds__(256)
 k_aux_compact(AuxPack p, int S, const int* __restrict__ dst) {

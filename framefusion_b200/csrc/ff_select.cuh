@@ -93,11 +93,13 @@ struct DecideArgs {
     const int* rank;
     int* dst;                   // [S] destination row or -1
     int* srcidx;                // [S_keep] source row of every destination row
+    int2* desc;                 // [S_keep] (by-patch position, run length) of every destination row; (-1, 0) outside the chains
     int* order_next;
     int* chain_next;
     int* rank_next;
     int64_t* counters_next;     // counter bank of the next call: N, n_vis carried over, count reset
     int force_branch;           // -1 = decide from count (main.py:116); 0/1 = flags are given (static API)
+    int topk_only;              // 1 = k_keep_scan handles the threshold branch: return at once unless the count says top-k
 };
 
 __global__ void __launch_bounds__(SEL_THREADS)
@@ -110,6 +112,7 @@ k_decide_scan(DecideArgs a) {
     const int t = threadIdx.x;
     const int N = (int)a.counters[C_N];
     const int S = a.S;
+    if (a.topk_only && a.counters[C_NVIS] != 0 && (double)a.counters[C_COUNT] / (double)a.counters[C_NVIS] < a.bound) return;
 
     if (t == 0) {
         const long long count = a.counters[C_COUNT], n_vis = a.counters[C_NVIS];
@@ -158,7 +161,7 @@ k_decide_scan(DecideArgs a) {
                 if (keep[e]) {
                     a.dst[i0 + e] = ex;
                     a.srcidx[ex] = i0 + e;
-                    if (r[e] < 0) a.rank_next[ex] = -1;
+                    if (r[e] < 0) { a.rank_next[ex] = -1; a.desc[ex] = make_int2(-1, 0); }
                     ++ex;
                 } else {
                     a.dst[i0 + e] = -1;
@@ -190,6 +193,9 @@ k_decide_scan(DecideArgs a) {
                 a.order_next[ex] = d;
                 a.chain_next[ex] = a.chain[j0 + e];
                 a.rank_next[d] = ex;
+                int L = 0;
+                while (j0 + e + 1 + L < N && a.flag[j0 + e + 1 + L]) ++L;
+                a.desc[d] = make_int2(j0 + e, L);
                 ++ex;
             }
         }
@@ -216,6 +222,136 @@ k_decide_scan(DecideArgs a) {
         a.status[FF_ST_ERROR] = s_err;
         a.status[FF_ST_NMERGED] = N - n_next;
         a.status[FF_ST_FUSED] = 0;
+    }
+}
+
+// ---- threshold branch, many blocks: the same outputs as k_decide_scan (destination rows in sequence order, the
+// by-patch arrays of the next call, counters, status) from a grid of G co-resident blocks (G <= SM count) in three
+// phases separated by grid barriers.  One 1024-thread block needs ~100 us for 37 k tokens (latency bound); spread
+// over 74 blocks it is a few microseconds.  If the count says top-k (main.py:121-127) every block returns at once
+// and k_decide_scan — launched right after — does the whole job; if it says threshold, k_decide_scan returns at once.
+struct ScanArgs {
+    DecideArgs d;
+    int* part;                   // [2 * gridDim.x] kept rows per block (sequence order, by-patch order)
+    unsigned* barrier;           // zeroed by the host before the launch
+};
+
+__device__ __forceinline__ bool threshold_branch(const int64_t* counters, double bound) {
+    const long long count = counters[C_COUNT], n_vis = counters[C_NVIS];
+    if (n_vis == 0) return false;                          // k_decide_scan reports the division by zero
+    return (double)count / (double)n_vis < bound;
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (*(volatile unsigned*)bar < target) __nanosleep(20);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+k_keep_scan(ScanArgs a) {
+    __shared__ int s_scan[33];
+    __shared__ int s_base;
+    const DecideArgs& d = a.d;
+    if (!threshold_branch(d.counters, d.bound)) return;
+    const int t = threadIdx.x, G = gridDim.x, b = blockIdx.x;
+    const int N = (int)d.counters[C_N], S = d.S;
+    // block b owns sequence rows [s0, s1) and by-patch positions [n0, n1), both multiples of the scan tile
+    const int per_s = ((S + G - 1) / G + SEL_THREADS - 1) / SEL_THREADS * SEL_THREADS;
+    const int per_n = ((N + G - 1) / G + SEL_THREADS - 1) / SEL_THREADS * SEL_THREADS;
+    const int s0 = min(b * per_s, S), s1 = min(s0 + per_s, S);
+    const int n0 = min(b * per_n, N), n1 = min(n0 + per_n, N);
+
+    // ---- phase 1: kept rows of the block, in both orders
+    int c_seq = 0, c_bp = 0;
+    for (int i = s0 + t; i < s1; i += SEL_THREADS) {
+        const int r = d.rank[i];
+        c_seq += !(r >= 0 && d.flag[r]);
+    }
+    for (int j = n0 + t; j < n1; j += SEL_THREADS) c_bp += !d.flag[j];
+    int tot;
+    block_exclusive_scan(c_seq, s_scan, &tot);
+    if (t == 0) a.part[b] = tot;
+    block_exclusive_scan(c_bp, s_scan, &tot);
+    if (t == 0) a.part[G + b] = tot;
+    grid_barrier(a.barrier, (unsigned)G);
+
+    // ---- phase 2: destination rows in sequence order
+    if (t == 0) {
+        int base = 0;
+        for (int q = 0; q < b; ++q) base += __ldcg(&a.part[q]);
+        s_base = base;
+    }
+    __syncthreads();
+    int carry = s_base;
+    for (int base = s0; base < s1; base += SEL_THREADS) {
+        const int i = base + t;
+        const int r = i < s1 ? d.rank[i] : -1;
+        const int keep = i < s1 && !(r >= 0 && d.flag[r]);
+        const int ex = carry + block_exclusive_scan(keep, s_scan, &tot);
+        if (i < s1) {
+            if (keep) {
+                d.dst[i] = ex;
+                d.srcidx[ex] = i;
+                if (r < 0) { d.rank_next[ex] = -1; d.desc[ex] = make_int2(-1, 0); }
+            } else {
+                d.dst[i] = -1;
+            }
+        }
+        carry += tot;
+    }
+    grid_barrier(a.barrier, (unsigned)(2 * G));
+
+    // ---- phase 3: the by-patch arrays of the next call
+    if (t == 0) {
+        int base = 0;
+        for (int q = 0; q < b; ++q) base += __ldcg(&a.part[G + q]);
+        s_base = base;
+    }
+    __syncthreads();
+    carry = s_base;
+    for (int base = n0; base < n1; base += SEL_THREADS) {
+        const int j = base + t;
+        const int keep = j < n1 && !d.flag[j];
+        const int ex = carry + block_exclusive_scan(keep, s_scan, &tot);
+        if (keep) {
+            const int dd = __ldcg(&d.dst[d.order[j]]);
+            d.order_next[ex] = dd;
+            d.chain_next[ex] = d.chain[j];
+            d.rank_next[dd] = ex;
+            int L = 0;
+            while (j + 1 + L < N && d.flag[j + 1 + L]) ++L;
+            d.desc[dd] = make_int2(j, L);
+        }
+        carry += tot;
+    }
+    if (b == G - 1 && t == 0) {
+        int s_keep = 0, n_next = 0;
+        for (int q = 0; q < G; ++q) { s_keep += __ldcg(&a.part[q]); n_next += __ldcg(&a.part[G + q]); }
+        d.counters[C_NNEXT] = n_next;
+        d.counters[C_SKEEP] = s_keep;
+        d.counters[C_BRANCH] = 0;
+        d.counters[C_K] = 0;
+        d.counters[C_NMERGED] = N - n_next;
+        d.counters_next[C_N] = n_next;
+        d.counters_next[C_NVIS] = d.counters[C_NVIS] - (N - n_next);
+        d.counters_next[C_COUNT] = 0;
+        d.counters_next[C_TICKET] = 0;
+        d.counters_next[C_TICKET2] = 0;
+        d.status[FF_ST_SEQ_KEEP] = s_keep;
+        d.status[FF_ST_COUNT] = d.counters[C_COUNT];
+        d.status[FF_ST_NVIS] = d.counters[C_NVIS];
+        d.status[FF_ST_NCHAIN] = N;
+        d.status[FF_ST_BRANCH] = 0;
+        d.status[FF_ST_TOPK] = 0;
+        d.status[FF_ST_ERROR] = 0;
+        d.status[FF_ST_NMERGED] = N - n_next;
+        d.status[FF_ST_FUSED] = 0;
     }
 }
 

@@ -105,38 +105,6 @@ __device__ __forceinline__ uint4 add_round(const uint4& a, const uint4& b) {    
     return Num<DT>::pack(x);
 }
 
-// T(x / div) elementwise, div = T(L + 1) (main.py:314-317: one true division, rounded to T).
-// bf16 fast path: a power-of-two divisor is an exact scaling; otherwise q0 = x * RN(1/div) is within 2 float32 ulp
-// of the correctly rounded quotient, so both round to the same bf16 unless q0 sits within a few ulp of a bf16
-// rounding boundary (low 16 bits ~ 0x8000) — those elements (about 1e-4 of them) take the IEEE division.
-__device__ __noinline__ float ieee_div(float x, float d) { return x / d; }
-
-template <int DT>
-struct Divider {
-    float div, rcp;
-    bool pow2;
-    __device__ __forceinline__ explicit Divider(int n) {
-        div = Num<DT>::rnd((float)n);
-        rcp = 1.0f / div;
-        pow2 = (n & (n - 1)) == 0;
-    }
-    __device__ __forceinline__ float one(float x) const {
-        if (DT != FF_BF16) return x / div;
-        const float q0 = x * rcp;
-        if (pow2) return q0;
-        const uint32_t u = __float_as_uint(q0);
-        const bool risky = ((u & 0xffffu) - 0x7ff8u) <= 0x10u || ((u & 0x7f800000u) == 0u && (u << 1) != 0u);
-        return risky ? ieee_div(x, div) : q0;
-    }
-    __device__ __noinline__ uint4 vec(const uint4 a) const {      // out of line: called once per vector, rarely hot
-        float x[Num<DT>::EPV];
-        Num<DT>::unpack(a, x);
-#pragma unroll
-        for (int e = 0; e < Num<DT>::EPV; ++e) x[e] = one(x[e]);
-        return Num<DT>::pack(x);
-    }
-};
-
 // Row sums for one 16-byte vector pair: dot += T(a*b), nb += b*b (the norm of `a` is carried over from the previous
 // row).  Two interleaved float32 accumulators per sum (even / odd elements), folded by the caller.
 // bf16: the product tensor element T(a*b) is one mul.rn.bf16x2 (exact product, one rounding — what the reference's

@@ -25,8 +25,10 @@ def main():
     times = []
     ff = FrameFusion(c["cost"], c["slb"], c["rlb"])
     ff.use_fused = bool(a.fused)
+    ker = []
     for it in range(a.iters + 3):
         ff.prepare(*wl.prepare_args())
+        ff.kernel_events = []
         pos = [wl.cos, wl.sin]
         h = wl.hidden
         flush.zero_()
@@ -43,11 +45,13 @@ def main():
         t1 = time.perf_counter()
         if it >= 3:
             times.append((e0.elapsed_time(e1), (t1 - t0) * 1e3))
+            ker.append(ff.kernel_events[0][2].elapsed_time(ff.kernel_events[0][3]))
     dev = sorted(t[0] for t in times)[len(times) // 2]
     wall = sorted(t[1] for t in times)[len(times) // 2]
     s_keep = h.shape[1]
     nbytes = synth.algorithmic_bytes(wl.seq_len, s_keep, c["hidden"], wl.hidden.element_size())
-    print(f"{a.cfg} fused={a.fused}: S={wl.seq_len} -> {s_keep}  sparsity={ff.sparsity_list}  device {dev*1e3:.1f} us  wall {wall*1e3:.1f} us  "
+    k_us = sorted(ker)[len(ker) // 2] * 1e3
+    print(f"{a.cfg} fused={a.fused}: S={wl.seq_len} -> {s_keep}  ff_merge_layer {k_us:.1f} us = {nbytes/k_us/1e3:.0f} GB/s | whole call: device {dev*1e3:.1f} us  wall {wall*1e3:.1f} us  "
           f"alg {nbytes/1e6:.1f} MB -> {nbytes/dev/1e6:.0f} GB/s  {wl.n_vision/dev*1e3:.3e} vision tok/s")
 
 
