@@ -307,6 +307,22 @@ def main():
         pass
     achieved = alg / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
 
+    # the single-pass streaming kernel on the same call, for the record (DESIGN.md compares the two designs)
+    single_ms = None
+    try:
+        ff1 = FrameFusion(c["cost"], c["slb"], c["rlb"])
+        ff1.use_fused = True
+        ts = []
+        for _ in range(5):
+            ff1.prepare(*wl.prepare_args())
+            ff1.kernel_events = []
+            ff1(devt["hidden"], [devt["cos"], devt["sin"]], None)
+            torch.cuda.synchronize()
+            ts.append(ff1.kernel_events[0][2].elapsed_time(ff1.kernel_events[0][3]))
+        single_ms = sorted(ts[2:])[len(ts[2:]) // 2]
+    except Exception as e:  # noqa: BLE001
+        single_ms = None
+
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
         step_e2e()
@@ -324,7 +340,8 @@ def main():
                    "parallelism": "replicas" if world > 1 else "single-gpu",
                    "calls_per_step": "merge, merge (closes merging), importance, prune"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "ff_merge_layer (k_fused_merge)" if fused else "ff_merge_layer (generic)",
+                     "traffic": traffic, "kernel": "ff_merge_layer call #0: " + ("k_stream_merge (single pass)" if fused else "two-pass path (k_similarity + k_keep_scan + k_merge_gather)"),
+                     "single_pass_kernel_us": None if single_ms is None else single_ms * 1e3,
                      "kernel_us": k_ms * 1e3, "algorithmic_bytes": alg, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "e2e": {"value": world * n_tok * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,

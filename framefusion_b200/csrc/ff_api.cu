@@ -80,6 +80,8 @@ struct Ws {
     int* part;          // [2 * 160] per-block counts of the multi-block scan
     unsigned* barrier;  // its grid barrier
     int* base;          // [n_ids + 1] start of every chain list inside order[]
+    char* zero_begin;   // region ff_build_links clears
+    size_t zero_bytes;
     size_t bytes;
 };
 
@@ -91,25 +93,30 @@ Ws carve(void* base_ptr, int64_t cap, int64_t n_ids) {
     size_t off = 0;
     auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += align_up(bytes); return r; };
     const int64_t n_chunks = (cap + LINK_CHUNK - 1) / LINK_CHUNK;
+    // one region zeroed by ff_build_links with a single memset: counters, chain lengths, histogram, flag bytes
+    char* zero_begin = p ? p + off : nullptr;
     w.counters[0] = (int64_t*)take(C_SLOTS * 8);
     w.counters[1] = (int64_t*)take(C_SLOTS * 8);
+    w.len[0] = (int*)take((size_t)(n_ids + 1) * 4);
+    w.hist = (int*)take((size_t)n_chunks * (size_t)(n_ids + 1) * 4);
+    w.barrier = (unsigned*)take(256);
+    w.state = (uint8_t*)take(cap);
+    w.zero_begin = zero_begin;
+    w.zero_bytes = (size_t)((p ? p + off : (char*)nullptr) - zero_begin);
+    w.len[1] = (int*)take((size_t)(n_ids + 1) * 4);
     for (int b = 0; b < 2; ++b) {
         w.order[b] = (int*)take(cap * 4);
         w.chain[b] = (int*)take(cap * 4);
         w.rank[b] = (int*)take(cap * 4);
-        w.len[b] = (int*)take((size_t)(n_ids + 1) * 4);
     }
     w.sim = (float*)take(cap * 4);
     w.flag = (uint8_t*)take(cap);
-    w.state = (uint8_t*)take(cap);
     w.dst[0] = (int*)take(cap * 4);
     w.dst[1] = (int*)take(cap * 4);
     w.srcidx = (int*)take(cap * 4);
     w.desc = (int2*)take(cap * 8);
-    w.hist = (int*)take((size_t)n_chunks * (size_t)(n_ids + 1) * 4);
     w.base = (int*)take((size_t)(n_ids + 1) * 4);
     w.part = (int*)take(2 * 160 * 4);
-    w.barrier = (unsigned*)take(256);
     w.bytes = off;
     return w;
 }
@@ -430,22 +437,20 @@ int ff_build_links(ff_ctx* ctx, void* ws, int64_t ws_bytes, const int64_t* patch
     FF_CUDA(cudaSetDevice(ctx->device));
     const int n_chunks = (int)((S + LINK_CHUNK - 1) / LINK_CHUNK);
     const int n_b = (int)n_ids + 1;                        // chain buckets + the bucket of rows outside the chains
-    FF_CUDA(cudaMemsetAsync(w.counters[0], 0, 2 * align_up(C_SLOTS * 8), st));
-    FF_CUDA(cudaMemsetAsync(w.len[0], 0, (size_t)n_b * 4, st));
+    FF_CUDA(cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st));
     ctx->epoch = 0;
     if (S > 0) {
-        FF_CUDA(cudaMemsetAsync(w.state, 0, (size_t)S, st));
-        FF_CUDA(cudaMemsetAsync(w.hist, 0, (size_t)n_chunks * n_b * 4, st));
         k_links_hist<<<n_chunks, LINK_CHUNK, 0, st>>>(patch_type, (int)S, (int)n_ids, w.hist, w.counters[0]);
         FF_LAUNCH_CHECK("k_links_hist");
-        k_links_colscan<<<(n_b + 7) / 8, 256, 0, st>>>(w.hist, n_chunks, n_b, w.len[0], w.base, w.counters[0]);
+        k_links_colscan<<<(n_b + 7) / 8, 256, 0, st>>>(w.hist, n_chunks, n_b, w.len[0], w.base, w.counters[0], ctx->d_status);
         FF_LAUNCH_CHECK("k_links_colscan");
         k_links_scatter<<<n_chunks, LINK_CHUNK, 0, st>>>(patch_type, (int)S, (int)n_ids, w.hist, w.base, w.order[0],
                                                         w.chain[0], w.rank[0]);
         FF_LAUNCH_CHECK("k_links_scatter");
+    } else {
+        k_links_status<<<1, 1, 0, st>>>(w.counters[0], ctx->d_status);
+        FF_LAUNCH_CHECK("k_links_status");
     }
-    k_links_status<<<1, 1, 0, st>>>(w.counters[0], ctx->d_status);
-    FF_LAUNCH_CHECK("k_links_status");
     ctx->parity = 0;
     ctx->last_parity = 0;
     ctx->links_S = S;

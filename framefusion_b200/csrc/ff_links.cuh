@@ -44,7 +44,7 @@ k_links_hist(const int64_t* __restrict__ pt, int S, int n_ids, int* __restrict__
 // n_b = n_ids + 1 buckets.
 __global__ void __launch_bounds__(256)
 k_links_colscan(int* __restrict__ hist, int n_chunks, int n_b, int* __restrict__ total, int* __restrict__ base,
-                int64_t* counters) {
+                int64_t* counters, int64_t* status) {
     const int n_ids = n_b;                                 // (name kept below: columns of hist)
     __shared__ int s_scan[33];
     __shared__ int s_last;
@@ -87,6 +87,9 @@ k_links_colscan(int* __restrict__ hist, int n_chunks, int n_b, int* __restrict__
     if (threadIdx.x == 0) {
         counters[C_N] = carry - __ldcg(&total[n_b - 1]);   // the last bucket is not a chain
         counters[C_TICKET] = 0;
+        status[FF_ST_NCHAIN] = counters[C_N];              // NVIS is complete: k_links_hist ran before this kernel
+        status[FF_ST_NVIS] = counters[C_NVIS];
+        status[FF_ST_ERROR] = 0;
     }
 }
 

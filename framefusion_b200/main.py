@@ -45,6 +45,18 @@ def _dtype_code(t: torch.Tensor) -> int:
         raise TypeError(f"framefusion_b200 supports bfloat16 / float16 / float32 hidden states, got {t.dtype}")
 
 
+_THR_CACHE = {}
+
+
+def _threshold_in(value, dtype) -> float:
+    """``sim >= python_scalar`` compares in the tensor dtype: the scalar rounded to T, as a Python float."""
+    key = (float(value), dtype)
+    v = _THR_CACHE.get(key)
+    if v is None:
+        v = _THR_CACHE[key] = torch.tensor(value, dtype=dtype).item()
+    return v
+
+
 def _stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
@@ -108,7 +120,9 @@ class FrameFusion(nn.Module):
         self._links_for = None          # (patch_type tensor, its _version, device) the workspace links describe
         self._have_order = False        # the workspace holds the compact by-patch order (the generic kernels need it)
         self._have_lists = False        # ... and the per-chain lists (the single-pass kernel needs them)
-        self.use_fused = True           # allow the single-pass kernel (threshold branch)
+        # merge-stage kernel choice: False = two-pass path (similarity -> scan -> gather/merge; the faster one at
+        # the time of writing), True = the single-pass streaming kernel (one HBM read of hidden_states)
+        self.use_fused = False
         self.debug_trace = False        # tests: keep what flowed between the stages of the last call
         self.last_trace = None
         self.kernel_events = None       # bench: a list collects (name, start, end) CUDA events around ff_* launches
@@ -315,7 +329,7 @@ class FrameFusion(nn.Module):
         self._ensure_links(st, q_len, need_order=not fused, need_lists=bool(fused))
 
         dt = hidden_states.dtype
-        thr = torch.tensor(self.similarity_lower_bound, dtype=dt).item()     # the scalar is compared in T
+        thr = _threshold_in(self.similarity_lower_bound, dt)                 # the scalar is compared in T
         hidden = hidden_states.contiguous()
         out = torch.empty_like(hidden)
         auxes = [_aux_of(self.patch_type.reshape(1, -1).to(torch.int64), 1) + (1,)]
