@@ -79,6 +79,7 @@ struct Ws {
     int* hist;
     int* part;          // [2 * 160] per-block counts of the multi-block scan
     unsigned* barrier;  // its grid barrier
+    int* sel_hist;      // [4][256] digit histograms of the multi-block radix select (right after `barrier`)
     int* base;          // [n_ids + 1] start of every chain list inside order[]
     char* zero_begin;   // region ff_build_links clears
     size_t zero_bytes;
@@ -100,6 +101,7 @@ Ws carve(void* base_ptr, int64_t cap, int64_t n_ids) {
     w.len[0] = (int*)take((size_t)(n_ids + 1) * 4);
     w.hist = (int*)take((size_t)n_chunks * (size_t)(n_ids + 1) * 4);
     w.barrier = (unsigned*)take(256);
+    w.sel_hist = (int*)take(4 * 256 * 4);
     w.state = (uint8_t*)take(cap);
     w.zero_begin = zero_begin;
     w.zero_bytes = (size_t)((p ? p + off : (char*)nullptr) - zero_begin);
@@ -418,6 +420,12 @@ int ff_ctx_destroy(ff_ctx* ctx) {
 
 const int64_t* ff_ctx_status(const ff_ctx* ctx) { return ctx ? ctx->h_status : nullptr; }
 
+int ff_stream_sync(ff_ctx* ctx, void* stream) {
+    if (!ctx) return fail(FF_E_BADARG, "null ctx");
+    FF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return FF_OK;
+}
+
 int64_t ff_workspace_bytes(int64_t seq_capacity, int64_t n_ids) {
     if (seq_capacity < 0 || n_ids < 0) return -1;
     return (int64_t)carve(nullptr, seq_capacity, n_ids).bytes;
@@ -570,7 +578,7 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     a.counters_next = w.counters[nb];
     a.force_branch = -1;
     a.topk_only = 0;
-    if (S >= 4 * SEL_TILE) {
+    if (S >= 2 * SEL_THREADS) {
         // threshold branch on a grid of co-resident blocks; k_decide_scan then only runs for the top-k branch
         ScanArgs sa;
         sa.d = a;
@@ -663,12 +671,38 @@ int ff_prune_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* attn, in
     a.start = (int)start;
     a.length = (int)length;
     a.k = k;
-    k_prune_scan<<<1, SEL_THREADS, 0, st>>>(a);
-    FF_LAUNCH_CHECK("k_prune_scan");
-    if (int rc2 = launch_merge_compact(w, bank, hidden, hidden_out, dtype, S, H, 0, st)) return rc2;
-    if (ap.n) {
-        k_aux_compact<<<(int)((S + 7) / 8), 256, 0, st>>>(ap, (int)S, w.dst[bank]);
-        FF_LAUNCH_CHECK("k_aux_compact");
+    if (S >= 2 * SEL_THREADS) {
+        PruneGridArgs ga;
+        ga.p = a;
+        ga.hist = w.sel_hist;
+        ga.part = w.part;
+        ga.barrier = w.barrier;
+        int G = ctx->sm_count / 2;
+        if (G > 160) G = 160;
+        if (G < 1) G = 1;
+        FF_CUDA(cudaMemsetAsync(w.barrier, 0, 256 + 4 * 256 * 4, st));     // barrier word + histograms (adjacent)
+        k_prune_select<<<G, SEL_THREADS, 0, st>>>(ga);
+        FF_LAUNCH_CHECK("k_prune_select");
+    } else {
+        k_prune_scan<<<1, SEL_THREADS, 0, st>>>(a);
+        FF_LAUNCH_CHECK("k_prune_scan");
+    }
+    if (vec_ok(hidden, hidden_out, H, dtype)) {
+        const int64_t nvec = H * (dtype == FF_F32 ? 4 : 2) / 16;
+        int rcg = dispatch_dtype(dtype, [&](auto dt) {
+            constexpr int DT = decltype(dt)::value;
+            k_merge_gather<DT><<<(int)((S + 7) / 8), 256, 0, st>>>(hidden, hidden_out, (int)nvec, w.srcidx, nullptr, w.order[bank],
+                                                                  w.flag, w.counters[bank], ap);
+            FF_LAUNCH_CHECK("k_merge_gather");
+            return (int)FF_OK;
+        });
+        if (rcg) return rcg;
+    } else {
+        if (int rc2 = launch_merge_compact(w, bank, hidden, hidden_out, dtype, S, H, 0, st)) return rc2;
+        if (ap.n) {
+            k_aux_compact<<<(int)((S + 7) / 8), 256, 0, st>>>(ap, (int)S, w.dst[bank]);
+            FF_LAUNCH_CHECK("k_aux_compact");
+        }
     }
     ctx->last_parity = bank;
     if (importance_out) {

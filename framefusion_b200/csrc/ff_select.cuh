@@ -407,6 +407,135 @@ k_prune_scan(PruneArgs a) {
     }
 }
 
+// ---- prune stage on a grid of co-resident blocks: radix select of the k-th largest importance (4 passes of 8 bits,
+// block histograms merged with global atomics, a grid barrier per pass), ties at the k-th value to the lowest
+// indices, then the sequence-order scan of the keep flags.  Same outputs as k_prune_scan, a few microseconds
+// instead of ~75 us for 22 k tokens in one block.
+struct PruneGridArgs {
+    PruneArgs p;
+    int* hist;                  // [4][256], zeroed by the host
+    int* part;                  // [2 * gridDim.x]
+    unsigned* barrier;          // zeroed by the host
+};
+
+__global__ void __launch_bounds__(SEL_THREADS)
+k_prune_select(PruneGridArgs a) {
+    __shared__ int s_hist[256];
+    __shared__ int s_scan[33];
+    __shared__ uint32_t s_digit, s_need;
+    __shared__ int s_base;
+    const PruneArgs& p = a.p;
+    const int t = threadIdx.x, G = gridDim.x, b = blockIdx.x;
+    const int n = p.length, S = p.S;
+    const float* vals = p.imp + p.start;
+    const int per_n = ((n + G - 1) / G + SEL_THREADS - 1) / SEL_THREADS * SEL_THREADS;
+    const int n0 = min(b * per_n, n), n1 = min(n0 + per_n, n);
+    const int per_s = ((S + G - 1) / G + SEL_THREADS - 1) / SEL_THREADS * SEL_THREADS;
+    const int s0 = min(b * per_s, S), s1 = min(s0 + per_s, S);
+    unsigned bar_target = 0;
+
+    uint32_t kth = 0, need_eq = 0;
+    bool all = p.k >= n, none = p.k <= 0;
+    if (!all && !none) {
+        uint32_t prefix = 0, mask = 0;
+        long long need = p.k;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            for (int q = t; q < 256; q += SEL_THREADS) s_hist[q] = 0;
+            __syncthreads();
+            for (int j = n0 + t; j < n1; j += SEL_THREADS) {
+                const uint32_t key = float_key(vals[j]);
+                if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255], 1);
+            }
+            __syncthreads();
+            for (int q = t; q < 256; q += SEL_THREADS)
+                if (s_hist[q]) atomicAdd(&a.hist[pass * 256 + q], s_hist[q]);
+            bar_target += G;
+            grid_barrier(a.barrier, bar_target);
+            if (t == 0) {
+                long long acc = 0;
+                int q = 255;
+                for (; q > 0; --q) {                       // walk from the largest digit down
+                    const int h = __ldcg(&a.hist[pass * 256 + q]);
+                    if (acc + h >= need) break;
+                    acc += h;
+                }
+                s_digit = (uint32_t)q;
+                s_need = (uint32_t)(need - acc);
+            }
+            __syncthreads();
+            prefix |= s_digit << shift;
+            mask |= 255u << shift;
+            need = (long long)s_need;
+            __syncthreads();
+        }
+        kth = prefix;
+        need_eq = (uint32_t)need;
+    }
+
+    // ---- ties: how many elements equal to the k-th value sit before this block
+    int c_eq = 0;
+    if (!all && !none)
+        for (int j = n0 + t; j < n1; j += SEL_THREADS) c_eq += float_key(vals[j]) == kth;
+    int tot;
+    block_exclusive_scan(c_eq, s_scan, &tot);
+    if (t == 0) a.part[b] = tot;
+    bar_target += G;
+    grid_barrier(a.barrier, bar_target);
+    if (t == 0) {
+        int base = 0;
+        for (int q = 0; q < b; ++q) base += __ldcg(&a.part[q]);
+        s_base = base;
+    }
+    __syncthreads();
+    int carry = s_base;
+    for (int base = n0; base < n1; base += SEL_THREADS) {
+        const int j = base + t;
+        uint32_t key = 0;
+        int eq = 0;
+        if (j < n1 && !all && !none) { key = float_key(vals[j]); eq = key == kth; }
+        const int ex = carry + block_exclusive_scan(eq, s_scan, &tot);
+        if (j < n1) p.sel[j] = all ? 1 : (none ? 0 : (uint8_t)(key > kth || (eq && (uint32_t)ex < need_eq)));
+        carry += tot;
+    }
+    bar_target += G;
+    grid_barrier(a.barrier, bar_target);                   // sel[] complete
+
+    // ---- sequence-order scan of the keep flags
+    int c_keep = 0;
+    for (int i = s0 + t; i < s1; i += SEL_THREADS)
+        c_keep += (i < p.start || i >= p.start + n) ? 1 : (int)__ldcg(&p.sel[i - p.start]);
+    block_exclusive_scan(c_keep, s_scan, &tot);
+    if (t == 0) a.part[G + b] = tot;
+    bar_target += G;
+    grid_barrier(a.barrier, bar_target);
+    if (t == 0) {
+        int base = 0;
+        for (int q = 0; q < b; ++q) base += __ldcg(&a.part[G + q]);
+        s_base = base;
+    }
+    __syncthreads();
+    carry = s_base;
+    for (int base = s0; base < s1; base += SEL_THREADS) {
+        const int i = base + t;
+        int keep = 0;
+        if (i < s1) keep = (i < p.start || i >= p.start + n) ? 1 : (int)__ldcg(&p.sel[i - p.start]);
+        const int ex = carry + block_exclusive_scan(keep, s_scan, &tot);
+        if (i < s1) {
+            if (keep) { p.dst[i] = ex; p.srcidx[ex] = i; } else p.dst[i] = -1;
+        }
+        carry += tot;
+    }
+    if (b == G - 1 && t == 0) {
+        int s_keep = 0;
+        for (int q = 0; q < G; ++q) s_keep += __ldcg(&a.part[G + q]);
+        p.counters[C_SKEEP] = s_keep;
+        p.status[FF_ST_SEQ_KEEP] = s_keep;
+        p.status[FF_ST_TOPK] = p.k;
+        p.status[FF_ST_ERROR] = 0;
+    }
+}
+
 // importance[s] = T( sum_rows attn[row][s] / n_rows )      (torch.mean(dim=(1,2)), main.py:70)
 template <int DT>
 __global__ void k_row_mean(const void* __restrict__ attn, int n_rows, int S, float* __restrict__ imp) {

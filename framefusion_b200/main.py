@@ -111,6 +111,14 @@ def _aux_of(t: torch.Tensor, seq_dim: int):
 
 
 class FrameFusion(nn.Module):
+    def __setattr__(self, name, value):
+        # the operator has no parameters, buffers or sub-modules: skip nn.Module's bookkeeping (it costs ~4 us per
+        # assignment and forward() assigns a dozen state attributes per call)
+        if isinstance(value, (nn.Module, nn.Parameter)):
+            super().__setattr__(name, value)
+        else:
+            object.__setattr__(self, name, value)
+
     def __init__(self, cost=0.3, similarity_lower_bound=0.6, ratio_lower_bound=0.1):
         super(FrameFusion, self).__init__()
         self.cost = cost
@@ -297,11 +305,12 @@ class FrameFusion(nn.Module):
         if st.ws is None:
             st.workspace(q_len, 0)
         wp, wb = st.ws_ptr()
+        stream = _stream(device)
         _lib.check(st.lib.ff_prune_layer(
             st.ctx, wp, wb, attn.data_ptr(), attn.shape[0], hidden.data_ptr(), out.data_ptr(), _dtype_code(hidden),
             q_len, hidden_size, start, length, k, self._pack_aux(auxes), len(auxes),
-            imp.data_ptr() if imp is not None else None, _stream(device)))
-        torch.cuda.current_stream(device).synchronize()
+            imp.data_ptr() if imp is not None else None, stream))
+        _lib.check(st.lib.ff_stream_sync(st.ctx, stream))
         s_keep = int(st.status[_lib.ST_SEQ_KEEP])
         outs = self._narrow(auxes, s_keep)
         position_embeddings = rebuild(outs)
@@ -349,7 +358,7 @@ class FrameFusion(nn.Module):
             if ev is not None:
                 e1.record()
                 ev.append(("ff_merge_layer", q_len, e0, e1))
-            torch.cuda.current_stream(device).synchronize()
+            _lib.check(st.lib.ff_stream_sync(st.ctx, stream))
 
         launch(fused)
         status = st.status

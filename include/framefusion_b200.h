@@ -83,6 +83,9 @@ int ff_ctx_create(int device, ff_ctx** out);
 int ff_ctx_destroy(ff_ctx* ctx);
 /* host pointer to FF_ST_SLOTS int64 values */
 const int64_t* ff_ctx_status(const ff_ctx* ctx);
+/* waits for the work enqueued on `stream`: the one synchronisation a reducing call needs before the status block
+ * (S_keep, the branch taken) can be read */
+int ff_stream_sync(ff_ctx* ctx, void* stream);
 
 int64_t ff_workspace_bytes(int64_t seq_capacity, int64_t n_ids);
 
