@@ -196,6 +196,19 @@ def cpu_baseline(cfg, seconds=12.0):
             "sample": f"{n} full steps of the {cfg} workload on torch {torch.__version__} CPU, {dt:.1f} s"}
 
 
+def max_over_ranks(ms, dist, device):
+    """The timed region of a multi-GPU run is as long as its slowest rank."""
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def whole_job_throughput(n_tokens, steps, ms, world):
+    """Replicas: every rank pushes n_tokens per step through its own GPU; the job's rate is the sum."""
+    return world * n_tokens * steps / (ms * 1e-3)
+
+
 # --------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -274,10 +287,7 @@ def main():
             fn()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if dist is not None:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return max_over_ranks(e0.elapsed_time(e1), dist, dev)
 
     for _ in range(warm):
         step_resident()
@@ -332,7 +342,7 @@ def main():
 
     n_tok = wl.n_vision
     line = {
-        "metric": METRIC, "value": world * n_tok * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "metric": METRIC, "value": whole_job_throughput(n_tok, args.steps, ms, world), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_name(cfg), "seq_len": wl.seq_len, "kept_after_merge": s_keep0,
@@ -344,7 +354,7 @@ def main():
                      "single_pass_kernel_us": None if single_ms is None else single_ms * 1e3,
                      "kernel_us": k_ms * 1e3, "algorithmic_bytes": alg, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
-        "e2e": {"value": world * n_tok * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+        "e2e": {"value": whole_job_throughput(n_tok, e2e_steps, ms_e2e, world), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),

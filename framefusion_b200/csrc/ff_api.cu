@@ -677,6 +677,7 @@ int ff_prune_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* attn, in
         ga.hist = w.sel_hist;
         ga.part = w.part;
         ga.barrier = w.barrier;
+        ga.n_passes = dtype == FF_BF16 ? 2 : (dtype == FF_F16 ? 3 : 4);
         int G = ctx->sm_count / 2;
         if (G > 160) G = 160;
         if (G < 1) G = 1;

@@ -253,6 +253,15 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
     __syncthreads();
 }
 
+
+// sum of part[0 .. n) by the whole block (n <= blockDim.x): one parallel load instead of n dependent ones
+__device__ __forceinline__ int block_sum_prefix(const int* part, int n, int* s_scan) {
+    const int v = (int)threadIdx.x < n ? __ldcg(&part[threadIdx.x]) : 0;
+    int tot;
+    block_exclusive_scan(v, s_scan, &tot);
+    return tot;
+}
+
 __global__ void __launch_bounds__(SEL_THREADS)
 k_keep_scan(ScanArgs a) {
     __shared__ int s_scan[33];
@@ -282,13 +291,7 @@ k_keep_scan(ScanArgs a) {
     grid_barrier(a.barrier, (unsigned)G);
 
     // ---- phase 2: destination rows in sequence order
-    if (t == 0) {
-        int base = 0;
-        for (int q = 0; q < b; ++q) base += __ldcg(&a.part[q]);
-        s_base = base;
-    }
-    __syncthreads();
-    int carry = s_base;
+    int carry = block_sum_prefix(a.part, b, s_scan);
     for (int base = s0; base < s1; base += SEL_THREADS) {
         const int i = base + t;
         const int r = i < s1 ? d.rank[i] : -1;
@@ -308,13 +311,7 @@ k_keep_scan(ScanArgs a) {
     grid_barrier(a.barrier, (unsigned)(2 * G));
 
     // ---- phase 3: the by-patch arrays of the next call
-    if (t == 0) {
-        int base = 0;
-        for (int q = 0; q < b; ++q) base += __ldcg(&a.part[G + q]);
-        s_base = base;
-    }
-    __syncthreads();
-    carry = s_base;
+    carry = block_sum_prefix(a.part + G, b, s_scan);
     for (int base = n0; base < n1; base += SEL_THREADS) {
         const int j = base + t;
         const int keep = j < n1 && !d.flag[j];
@@ -330,9 +327,9 @@ k_keep_scan(ScanArgs a) {
         }
         carry += tot;
     }
+    const int s_keep = b == G - 1 ? block_sum_prefix(a.part, G, s_scan) : 0;
+    const int n_next = b == G - 1 ? block_sum_prefix(a.part + G, G, s_scan) : 0;
     if (b == G - 1 && t == 0) {
-        int s_keep = 0, n_next = 0;
-        for (int q = 0; q < G; ++q) { s_keep += __ldcg(&a.part[q]); n_next += __ldcg(&a.part[G + q]); }
         d.counters[C_NNEXT] = n_next;
         d.counters[C_SKEEP] = s_keep;
         d.counters[C_BRANCH] = 0;
@@ -416,6 +413,7 @@ struct PruneGridArgs {
     int* hist;                  // [4][256], zeroed by the host
     int* part;                  // [2 * gridDim.x]
     unsigned* barrier;          // zeroed by the host
+    int n_passes;               // 8-bit radix passes that can differ: 2 for bf16 values, 3 for f16, 4 for f32
 };
 
 __global__ void __launch_bounds__(SEL_THREADS)
@@ -439,7 +437,7 @@ k_prune_select(PruneGridArgs a) {
     if (!all && !none) {
         uint32_t prefix = 0, mask = 0;
         long long need = p.k;
-        for (int pass = 0; pass < 4; ++pass) {
+        for (int pass = 0; pass < a.n_passes; ++pass) {        // the remaining low bits are zero in every key
             const int shift = 24 - 8 * pass;
             for (int q = t; q < 256; q += SEL_THREADS) s_hist[q] = 0;
             __syncthreads();
@@ -452,13 +450,14 @@ k_prune_select(PruneGridArgs a) {
                 if (s_hist[q]) atomicAdd(&a.hist[pass * 256 + q], s_hist[q]);
             bar_target += G;
             grid_barrier(a.barrier, bar_target);
+            for (int q = t; q < 256; q += SEL_THREADS) s_hist[q] = __ldcg(&a.hist[pass * 256 + q]);
+            __syncthreads();
             if (t == 0) {
                 long long acc = 0;
                 int q = 255;
                 for (; q > 0; --q) {                       // walk from the largest digit down
-                    const int h = __ldcg(&a.hist[pass * 256 + q]);
-                    if (acc + h >= need) break;
-                    acc += h;
+                    if (acc + s_hist[q] >= need) break;
+                    acc += s_hist[q];
                 }
                 s_digit = (uint32_t)q;
                 s_need = (uint32_t)(need - acc);
@@ -482,13 +481,7 @@ k_prune_select(PruneGridArgs a) {
     if (t == 0) a.part[b] = tot;
     bar_target += G;
     grid_barrier(a.barrier, bar_target);
-    if (t == 0) {
-        int base = 0;
-        for (int q = 0; q < b; ++q) base += __ldcg(&a.part[q]);
-        s_base = base;
-    }
-    __syncthreads();
-    int carry = s_base;
+    int carry = block_sum_prefix(a.part, b, s_scan);
     for (int base = n0; base < n1; base += SEL_THREADS) {
         const int j = base + t;
         uint32_t key = 0;
@@ -509,13 +502,7 @@ k_prune_select(PruneGridArgs a) {
     if (t == 0) a.part[G + b] = tot;
     bar_target += G;
     grid_barrier(a.barrier, bar_target);
-    if (t == 0) {
-        int base = 0;
-        for (int q = 0; q < b; ++q) base += __ldcg(&a.part[G + q]);
-        s_base = base;
-    }
-    __syncthreads();
-    carry = s_base;
+    carry = block_sum_prefix(a.part + G, b, s_scan);
     for (int base = s0; base < s1; base += SEL_THREADS) {
         const int i = base + t;
         int keep = 0;
@@ -526,9 +513,8 @@ k_prune_select(PruneGridArgs a) {
         }
         carry += tot;
     }
+    const int s_keep = b == G - 1 ? block_sum_prefix(a.part + G, G, s_scan) : 0;
     if (b == G - 1 && t == 0) {
-        int s_keep = 0;
-        for (int q = 0; q < G; ++q) s_keep += __ldcg(&a.part[G + q]);
         p.counters[C_SKEEP] = s_keep;
         p.status[FF_ST_SEQ_KEEP] = s_keep;
         p.status[FF_ST_TOPK] = p.k;

@@ -1,0 +1,166 @@
+"""CPU: the Qwen2 hook trio and ``apply_framefusion`` on a tiny random-init decoder.
+
+The operator itself is CUDA-only, so the patched model is driven here with the numpy oracle standing in for it
+(tests may use the oracle as a checker): what is verified is the PLUMBING the reference's hooks define
+(models/qwen2/modeling_qwen2.py:44-47, 66-68, 84-86, 166-178, 262-266, 303-306) — where the operator is called,
+that the compacted position embeddings / mask travel from layer to layer, that importance is produced only while
+pruning is armed, that the KV cache keeps per-layer ragged lengths and a decode step passes through."""
+import numpy as np
+import pytest
+import torch
+from transformers import Qwen2Config, Qwen2ForCausalLM
+
+from _harness import OracleAdapter
+from oracle import ff_torch_port as port
+from framefusion_b200 import synth
+
+
+def tiny_model(attn="sdpa"):
+    torch.manual_seed(0)
+    cfg = Qwen2Config(vocab_size=128, hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4,
+                      num_key_value_heads=2, max_position_embeddings=4096, rope_theta=1e6)
+    cfg._attn_implementation = attn
+    return Qwen2ForCausalLM(cfg).eval().float()
+
+
+class OracleOperator(torch.nn.Module):
+    """OracleAdapter with the attribute surface the hooks read."""
+
+    def __init__(self, cost, slb, rlb):
+        super().__init__()
+        object.__setattr__(self, "ad", OracleAdapter(cost, slb, rlb, "f32"))
+        self.calls = []
+
+    def prepare(self, *a):
+        self.ad.prepare(*a)
+
+    def forward(self, hidden, pos, mask, attn=None):
+        self.calls.append((hidden.shape[1], attn is not None))
+        return self.ad(hidden, pos, mask, attn)
+
+    finish_merging = property(lambda s: s.ad.finish_merging)
+    finish_pruning = property(lambda s: s.ad.finish_pruning)
+    sparsity_list = property(lambda s: s.ad.sparsity_list)
+
+
+def install(model, op):
+    """apply_framefusion, then swap the CUDA operator for the stand-in on every module that holds it."""
+    from framefusion_b200.interface import apply_framefusion
+    apply_framefusion(model, cost=0.3, similarity_lower_bound=0.6, ratio_lower_bound=0.1)
+    shared = model.framefusion
+    assert type(shared).__name__ == "FrameFusion"
+    for m in [model, model.model] + list(model.model.layers) + [l.self_attn for l in model.model.layers]:
+        assert m.framefusion is shared                     # ONE shared operator (interface.py:187-212)
+        m.framefusion = op
+
+
+@pytest.fixture()
+def patched_importance(monkeypatch):
+    import framefusion_b200.hooks.qwen2 as hk
+
+    def cpu_importance(q, k, v, num=1, attn_mask=None, dropout_p=0.0, is_causal=False, scale=None, enable_gqa=False):
+        return port.last_query_attention(q, k, num=num, is_causal=is_causal, scale=scale)
+    monkeypatch.setattr(hk, "scaled_dot_product_attention", cpu_importance)
+
+
+def workload(frames=6, patches=12, hidden=64, lo=0.0, hi=1.0, seed=4):
+    return synth.make_workload(frames, patches, hidden, torch.float32, seed=seed, r_lo=lo, r_hi=hi, n_pre=3, n_post=5,
+                               rot_dim=16)
+
+
+def manual_reference(model, wl, op):
+    """The schedule of the reference hooks, spelled out with stock modules (no patched forwards)."""
+    m = model.model
+    h = wl.hidden.clone()
+    S = h.shape[1]
+    pos_ids = torch.arange(S)[None]
+    pe = list(m.rotary_emb(h, pos_ids))
+    op.prepare(*wl.prepare_args())
+    from transformers.models.qwen2.modeling_qwen2 import apply_rotary_pos_emb
+    for li, layer in enumerate(m.layers):
+        if li == 0:
+            h, pe, _ = op(h, pe, None)
+        res = h
+        x = layer.input_layernorm(h)
+        att = layer.self_attn
+        shp = (*x.shape[:-1], -1, att.head_dim)
+        q = att.q_proj(x).view(shp).transpose(1, 2)
+        k = att.k_proj(x).view(shp).transpose(1, 2)
+        v = att.v_proj(x).view(shp).transpose(1, 2)
+        q, k = apply_rotary_pos_emb(q, k, pe[0], pe[1])
+        w = None
+        if op.finish_merging and not op.finish_pruning:
+            w = port.last_query_attention(q, k, num=1, is_causal=True, scale=att.scaling)
+        kk = k.repeat_interleave(att.num_key_value_groups, dim=1)
+        vv = v.repeat_interleave(att.num_key_value_groups, dim=1)
+        o = torch.nn.functional.scaled_dot_product_attention(q, kk, vv, is_causal=True, scale=att.scaling)
+        o = att.o_proj(o.transpose(1, 2).reshape(*x.shape[:-1], -1))
+        h = res + o
+        h, pe, _ = op(h, pe, None, w)
+        h = h + layer.mlp(layer.post_attention_layernorm(h))
+    return m.norm(h)
+
+
+@pytest.mark.parametrize("lo,hi", [(0.0, 1.0), (0.0, 0.5), (0.8, 1.0)], ids=["mixed", "lowsim_prune", "topk"])
+def test_hook_schedule_matches_manual_reference(patched_importance, lo, hi):
+    model = tiny_model()
+    wl = workload(lo=lo, hi=hi)
+    with torch.no_grad():
+        want = manual_reference(model, wl, OracleOperator(0.3, 0.6, 0.1))
+        op = OracleOperator(0.3, 0.6, 0.1)
+        install(model, op)
+        model.framefusion.prepare(*wl.prepare_args())
+        out = model.model(inputs_embeds=wl.hidden.clone(), use_cache=True)
+    got = out.last_hidden_state
+    assert got.shape == want.shape and got.shape[1] < wl.seq_len
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-5)
+    # call #0 before layer-0 attention without importance, then one call per layer (modeling_qwen2.py:44-47, 66-68)
+    assert len(op.calls) == 1 + len(model.model.layers)
+    assert op.calls[0] == (wl.seq_len, False)
+    # importance only while pruning is armed (modeling_qwen2.py:168)
+    armed = [w for (_s, w) in op.calls]
+    assert sum(armed) <= 1
+    # the KV cache keeps, per layer, the length that layer SAW (modeling_qwen2.py:143-145): non-increasing, ragged
+    lens = [out.past_key_values.get_seq_length(i) for i in range(len(model.model.layers))]
+    assert lens[0] < wl.seq_len and all(a >= b for a, b in zip(lens, lens[1:])) and lens[-1] >= got.shape[1]
+
+
+def test_decode_step_passes_through(patched_importance):
+    model = tiny_model()
+    wl = workload()
+    op = OracleOperator(0.3, 0.6, 0.1)
+    install(model, op)
+    with torch.no_grad():
+        model.framefusion.prepare(*wl.prepare_args())
+        out = model.model(inputs_embeds=wl.hidden.clone(), use_cache=True)
+        n_calls = len(op.calls)
+        lens = [out.past_key_values.get_seq_length(i) for i in range(4)]
+        step = model.model(inputs_embeds=torch.randn(1, 1, 64), past_key_values=out.past_key_values, use_cache=True,
+                           attention_mask=torch.ones(1, wl.seq_len + 1, dtype=torch.long))   # generate() style mask
+    assert step.last_hidden_state.shape == (1, 1, 64)
+    assert [c[0] for c in op.calls[n_calls:]] == [1] * 5                       # q_len == 1: the operator is a no-op
+    assert [step.past_key_values.get_seq_length(i) for i in range(4)] == [l + 1 for l in lens]
+
+
+def test_eager_attention_compacts_the_4d_mask(patched_importance):
+    model = tiny_model("eager")
+    wl = workload()
+    op = OracleOperator(0.3, 0.6, 0.1)
+    install(model, op)
+    with torch.no_grad():
+        model.framefusion.prepare(*wl.prepare_args())
+        out = model.model(inputs_embeds=wl.hidden.clone(), use_cache=False)
+    assert out.last_hidden_state.shape[1] < wl.seq_len
+
+
+def test_unsupported_model_raises_like_the_reference(capsys):
+    from framefusion_b200.interface import apply_framefusion
+    with pytest.raises(NotImplementedError):
+        apply_framefusion(torch.nn.Linear(2, 2), 0.3, 0.6, 0.1)
+    assert "Model not supported" in capsys.readouterr().out
+
+
+def test_get_attr_by_name():
+    from framefusion_b200.utils import get_attr_by_name
+    model = tiny_model()
+    assert get_attr_by_name(model, "model.layers.1.self_attn.q_proj") is model.model.layers[1].self_attn.q_proj
