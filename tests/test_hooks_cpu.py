@@ -164,3 +164,66 @@ def test_get_attr_by_name():
     from framefusion_b200.utils import get_attr_by_name
     model = tiny_model()
     assert get_attr_by_name(model, "model.layers.1.self_attn.q_proj") is model.model.layers[1].self_attn.q_proj
+
+
+# ---- Qwen2-VL: M-RoPE (4-D cos / sin), importance from the last four queries -------------------------------
+def tiny_qwen2vl():
+    from transformers import Qwen2VLConfig, Qwen2VLForConditionalGeneration
+    torch.manual_seed(0)
+    cfg = Qwen2VLConfig(
+        text_config=dict(vocab_size=128, hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4,
+                         num_key_value_heads=2, max_position_embeddings=4096,
+                         rope_parameters={"rope_type": "default", "mrope_section": [2, 3, 3], "rope_theta": 1e6}),
+        vision_config=dict(depth=1, embed_dim=32, hidden_size=64, num_heads=2, in_channels=3, patch_size=14,
+                           spatial_merge_size=2, temporal_patch_size=2))
+    return Qwen2VLForConditionalGeneration(cfg).eval().float()
+
+
+def test_qwen2vl_trio_runs_with_mrope_and_four_query_importance(monkeypatch):
+    import framefusion_b200.hooks.qwen2_vl as hk
+    seen = []
+
+    def cpu_importance(q, k, v, num=1, attn_mask=None, dropout_p=0.0, is_causal=False, scale=None, enable_gqa=False):
+        seen.append(num)
+        return port.last_query_attention(q, k, num=num, is_causal=is_causal, scale=scale)
+    monkeypatch.setattr(hk, "scaled_dot_product_attention", cpu_importance)
+    from framefusion_b200.interface import apply_framefusion
+    model = tiny_qwen2vl()
+    apply_framefusion(model, 0.3, 0.6, 0.1)
+    llm = model.model.language_model
+    shared = model.framefusion
+    op = OracleOperator(0.3, 0.6, 0.1)
+    for m in [model, llm] + list(llm.layers) + [l.self_attn for l in llm.layers]:
+        assert m.framefusion is shared
+        m.framefusion = op
+    wl = workload(lo=0.0, hi=0.5)                           # little to merge: pruning gets armed
+    pos_cache = {}
+    inner = op.forward
+
+    def spy(hidden, pos, mask, attn=None):
+        pos_cache["in"] = [p.shape for p in pos]
+        out = inner(hidden, pos, mask, attn)
+        pos_cache["out"] = [p.shape for p in out[1]]
+        return out
+    op.forward = spy
+    with torch.no_grad():
+        op.prepare(*wl.prepare_args())
+        out = llm(inputs_embeds=wl.hidden.clone(), use_cache=True)
+    assert out.last_hidden_state.shape[1] < wl.seq_len
+    assert len(pos_cache["in"][0]) == 4 and pos_cache["in"][0][0] == 3            # [3, B, S, D]
+    assert pos_cache["out"][0][2] == out.last_hidden_state.shape[1]               # compacted along dim 2
+    assert seen and all(n == 4 for n in seen)                                     # reference :292-300
+
+
+def test_layout_builders_match_the_reference_formulas():
+    from framefusion_b200.layout import qwen2vl_prepare_args, llava_video_prepare_args
+    # Qwen2-VL (models/qwenvl/modeling_qwen2_vl.py:118-127): 3 frames of a 4x6 grid merged 2x2 -> 6 tokens per frame
+    ids = torch.tensor([[11, 12] + [99] * 18 + [13, 14, 15]])
+    pt, patch_num, start, end, length, orig = qwen2vl_prepare_args(ids, 99, torch.tensor([[3, 4, 6]]), 2)
+    want = [-1] * 2 + list(range(6)) * 3 + [-1] * (23 - 19 - 1)
+    assert (patch_num, start, end, length, orig) == (6, 2, 19, 18, 23) and pt.tolist() == [want]
+    # LLaVA-Video (models/llava_video/modeling_llava_video.py:322-336): 27 patches per side, bilinear pool -> 14 * 15
+    ids = torch.tensor([[1, 2, 3, -200, 4, 5]])
+    pt, patch_num, start, end, length, orig = llava_video_prepare_args(ids, -200, 210 * 4, 27)
+    assert patch_num == 210 and (start, end, length, orig) == (3, 3 + 840 - 1, 840, 6 + 840 - 1)
+    assert pt.tolist() == [[-1] * 3 + list(range(210)) * 4 + [-1] * (orig - end - 1)]
