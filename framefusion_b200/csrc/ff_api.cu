@@ -75,7 +75,7 @@ struct Ws {
     uint8_t* state;
     int* dst[2];
     int* srcidx;
-    int2* desc;         // [cap] (by-patch position, run length) per destination row
+    int4* rec;          // [cap] per kept chain row in by-patch order: (source row, destination row, by-patch position, run length)
     int* hist;
     int* part;          // [2 * 160] per-block counts of the multi-block scan
     unsigned* barrier;  // its grid barrier
@@ -116,7 +116,7 @@ Ws carve(void* base_ptr, int64_t cap, int64_t n_ids) {
     w.dst[0] = (int*)take(cap * 4);
     w.dst[1] = (int*)take(cap * 4);
     w.srcidx = (int*)take(cap * 4);
-    w.desc = (int2*)take(cap * 8);
+    w.rec = (int4*)take(cap * 16);
     w.base = (int*)take((size_t)(n_ids + 1) * 4);
     w.part = (int*)take(2 * 160 * 4);
     w.bytes = off;
@@ -251,6 +251,7 @@ int launch_merge_compact(const Ws& w, int bank, const void* hidden, void* out, i
 }
 
 
+
 // merged rows + compaction of hidden and aux, two-pass path: the gather kernel when rows are 16-byte multiples,
 // the generic kernels otherwise
 int launch_merge_gather(const ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* out, int dtype, int64_t S,
@@ -260,8 +261,9 @@ int launch_merge_gather(const ff_ctx* ctx, const Ws& w, int bank, const void* hi
     if (vec_ok(hidden, out, H, dtype)) {
         return dispatch_dtype(dtype, [&](auto dt) {
             constexpr int DT = decltype(dt)::value;
-            k_merge_gather<DT><<<(int)((S + 7) / 8), 256, 0, st>>>(hidden, out, (int)nvec, w.srcidx, w.desc, w.order[bank], w.flag,
-                                                               w.counters[bank], ap);
+            k_merge_gather<DT><<<(int)((S + GATHER_WARPS - 1) / GATHER_WARPS) * 2 + 1, GATHER_WARPS * 32, 0, st>>>(hidden, out, (int)nvec, w.srcidx, w.rec, w.order[bank],
+                                                                        w.flag, w.counters[bank], w.rank[bank ^ 1],
+                                                                        w.counters[bank ^ 1], ap);
             FF_LAUNCH_CHECK("k_merge_gather");
             return (int)FF_OK;
         });
@@ -571,7 +573,7 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     a.rank = w.rank[bank];
     a.dst = w.dst[bank];
     a.srcidx = w.srcidx;
-    a.desc = w.desc;
+    a.rec = w.rec;
     a.order_next = w.order[nb];
     a.chain_next = w.chain[nb];
     a.rank_next = w.rank[nb];
@@ -692,8 +694,8 @@ int ff_prune_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* attn, in
         const int64_t nvec = H * (dtype == FF_F32 ? 4 : 2) / 16;
         int rcg = dispatch_dtype(dtype, [&](auto dt) {
             constexpr int DT = decltype(dt)::value;
-            k_merge_gather<DT><<<(int)((S + 7) / 8), 256, 0, st>>>(hidden, hidden_out, (int)nvec, w.srcidx, nullptr, w.order[bank],
-                                                                  w.flag, w.counters[bank], ap);
+            k_merge_gather<DT><<<(int)((S + GATHER_WARPS - 1) / GATHER_WARPS), GATHER_WARPS * 32, 0, st>>>(hidden, hidden_out, (int)nvec, w.srcidx, nullptr, w.order[bank],
+                                                                  w.flag, w.counters[bank], nullptr, nullptr, ap);
             FF_LAUNCH_CHECK("k_merge_gather");
             return (int)FF_OK;
         });

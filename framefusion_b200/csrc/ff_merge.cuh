@@ -117,16 +117,40 @@ struct AuxPack {
 // occupancy: four 16-byte vectors per lane in flight per step; an anchor requests the same four vectors of every
 // run member together (main.py:304-311 order of the adds), i.e. one memory round trip per step instead of one per
 // vector and member.  The aux rows (cos, sin, patch_type, position ids) ride along.
+constexpr int GATHER_WARPS = 4;                  // small blocks: a slow anchor warp holds up only three others
+
 template <int DT>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(GATHER_WARPS * 32, 32 / GATHER_WARPS)
 k_merge_gather(const void* __restrict__ hidden, void* __restrict__ out, int nvec, const int* __restrict__ srcidx,
-               const int2* __restrict__ desc, const int* __restrict__ order, const uint8_t* __restrict__ flag,
-               const int64_t* __restrict__ counters, const __grid_constant__ AuxPack aux) {
+               const int4* __restrict__ rec, const int* __restrict__ order, const uint8_t* __restrict__ flag,
+               const int64_t* __restrict__ counters, const int* __restrict__ rank_of_dst,
+               const int64_t* __restrict__ counters_next, const __grid_constant__ AuxPack aux) {
     const int lane = threadIdx.x & 31;
-    const int d = (int)counters[C_SKEEP] - 1 - (blockIdx.x * 8 + (threadIdx.x >> 5));
-    if (d < 0) return;
-    const int i = srcidx[d];
-    const int2 ds = desc ? desc[d] : make_int2(-1, 0);
+    const int w = blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
+    const int s_keep = (int)counters[C_SKEEP];
+    int d, i;
+    int2 ds = make_int2(-1, 0);
+    if (rec) {
+        // merge stage: chain rows in by-patch order, last patch ids first (the similarity pass has just walked the
+        // chains in that order), one 16-byte record per row from the scan kernel; the rows outside the chains
+        // (text) are picked up by the blocks behind those
+        const int n_chain = (int)counters_next[C_N];
+        const int n_blocks_chain = (n_chain + GATHER_WARPS - 1) / GATHER_WARPS;
+        if ((int)blockIdx.x < n_blocks_chain) {
+            const int ex = n_chain - 1 - w;
+            if (ex < 0) return;
+            const int4 r = __ldg(rec + ex);
+            i = r.x; d = r.y; ds = make_int2(r.z, r.w);
+        } else {
+            d = w - n_blocks_chain * GATHER_WARPS;
+            if (d >= s_keep || rank_of_dst[d] >= 0) return;
+            i = srcidx[d];
+        }
+    } else {
+        d = s_keep - 1 - w;                                 // prune stage: destination rows, last first
+        if (d < 0) return;
+        i = srcidx[d];
+    }
     const int64_t row_bytes = (int64_t)nvec * 16;
     const char* src = (const char*)hidden + (int64_t)i * row_bytes;
     char* orow = (char*)out + (int64_t)d * row_bytes;
@@ -137,30 +161,35 @@ k_merge_gather(const void* __restrict__ hidden, void* __restrict__ out, int nvec
         if (j == N - 1 && N > 1 && flag[0]) wrapL = run_after(flag, -1, N - 1);       // main.py:290 wrap-around
     }
     if (L + wrapL == 0) {
-        int v = lane;
-        for (; v + 96 < nvec; v += 128) {
-            const uint4 a0 = ld_stream16(src + (int64_t)v * 16), a1 = ld_stream16(src + (int64_t)(v + 32) * 16);
-            const uint4 a2 = ld_stream16(src + (int64_t)(v + 64) * 16), a3 = ld_stream16(src + (int64_t)(v + 96) * 16);
-            st_stream16(orow + (int64_t)v * 16, a0);
-            st_stream16(orow + (int64_t)(v + 32) * 16, a1);
-            st_stream16(orow + (int64_t)(v + 64) * 16, a2);
-            st_stream16(orow + (int64_t)(v + 96) * 16, a3);
+        for (int v0 = lane; v0 < nvec; v0 += 256) {         // eight 16-byte vectors per lane in flight
+            uint4 x[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (v0 + 32 * q < nvec) x[q] = ld_stream16(src + (int64_t)(v0 + 32 * q) * 16);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (v0 + 32 * q < nvec) st_stream16(orow + (int64_t)(v0 + 32 * q) * 16, x[q]);
         }
-        for (; v < nvec; v += 32) st_stream16(orow + (int64_t)v * 16, ld_stream16(src + (int64_t)v * 16));
     } else {
         const Divider<DT> dv(L + wrapL + 1);
+        // the first member's row is addressed once, outside the loop: runs of one merged token are the common case
+        const char* mr0 = (const char*)hidden + (int64_t)order[L > 0 ? j + 1 : 0] * row_bytes;
         for (int v0 = lane; v0 < nvec; v0 += 128) {
-            uint4 acc[4];
+            uint4 acc[4], x[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (v0 + 32 * q < nvec) acc[q] = ld_stream16(src + (int64_t)(v0 + 32 * q) * 16);
+                if (v0 + 32 * q < nvec) {
+                    acc[q] = ld_stream16(src + (int64_t)(v0 + 32 * q) * 16);
+                    x[q] = ldg16(mr0 + (int64_t)(v0 + 32 * q) * 16);
+                }
             for (int m = 0; m < L + wrapL; ++m) {
-                const int jm = m < L ? j + 1 + m : m - L;
-                const char* mr = (const char*)hidden + (int64_t)order[jm] * row_bytes;
-                uint4 x[4];
+                if (m > 0) {
+                    const int jm = m < L ? j + 1 + m : m - L;
+                    const char* mr = (const char*)hidden + (int64_t)order[jm] * row_bytes;
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (v0 + 32 * q < nvec) x[q] = ldg16(mr + (int64_t)(v0 + 32 * q) * 16);
+                    for (int q = 0; q < 4; ++q)
+                        if (v0 + 32 * q < nvec) x[q] = ldg16(mr + (int64_t)(v0 + 32 * q) * 16);
+                }
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     if (v0 + 32 * q < nvec) {

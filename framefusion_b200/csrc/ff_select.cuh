@@ -93,7 +93,7 @@ struct DecideArgs {
     const int* rank;
     int* dst;                   // [S] destination row or -1
     int* srcidx;                // [S_keep] source row of every destination row
-    int2* desc;                 // [S_keep] (by-patch position, run length) of every destination row; (-1, 0) outside the chains
+    int4* rec;                  // [N_next] per kept chain row, by-patch order: (source row, destination row, by-patch position, run length)
     int* order_next;
     int* chain_next;
     int* rank_next;
@@ -161,7 +161,7 @@ k_decide_scan(DecideArgs a) {
                 if (keep[e]) {
                     a.dst[i0 + e] = ex;
                     a.srcidx[ex] = i0 + e;
-                    if (r[e] < 0) { a.rank_next[ex] = -1; a.desc[ex] = make_int2(-1, 0); }
+                    if (r[e] < 0) a.rank_next[ex] = -1;
                     ++ex;
                 } else {
                     a.dst[i0 + e] = -1;
@@ -195,7 +195,7 @@ k_decide_scan(DecideArgs a) {
                 a.rank_next[d] = ex;
                 int L = 0;
                 while (j0 + e + 1 + L < N && a.flag[j0 + e + 1 + L]) ++L;
-                a.desc[d] = make_int2(j0 + e, L);
+                a.rec[ex] = make_int4(a.order[j0 + e], d, j0 + e, L);
                 ++ex;
             }
         }
@@ -301,7 +301,7 @@ k_keep_scan(ScanArgs a) {
             if (keep) {
                 d.dst[i] = ex;
                 d.srcidx[ex] = i;
-                if (r < 0) { d.rank_next[ex] = -1; d.desc[ex] = make_int2(-1, 0); }
+                if (r < 0) d.rank_next[ex] = -1;
             } else {
                 d.dst[i] = -1;
             }
@@ -323,7 +323,7 @@ k_keep_scan(ScanArgs a) {
             d.rank_next[dd] = ex;
             int L = 0;
             while (j + 1 + L < N && d.flag[j + 1 + L]) ++L;
-            d.desc[dd] = make_int2(j, L);
+            d.rec[ex] = make_int4(d.order[j], dd, j, L);
         }
         carry += tot;
     }
