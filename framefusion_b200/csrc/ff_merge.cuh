@@ -130,6 +130,7 @@ k_merge_gather(const void* __restrict__ hidden, void* __restrict__ out, int nvec
     const int s_keep = (int)counters[C_SKEEP];
     int d, i;
     int2 ds = make_int2(-1, 0);
+    if (rec && counters[C_NMERGED] == 0) return;            // nothing merged: the host hands the input tensors back
     if (rec) {
         // merge stage: chain rows in by-patch order, last patch ids first (the similarity pass has just walked the
         // chains in that order), one 16-byte record per row from the scan kernel; the rows outside the chains

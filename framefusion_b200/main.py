@@ -394,6 +394,12 @@ class FrameFusion(nn.Module):
             else:
                 self._record_merge_trace(st, hidden, q_len, int(status[_lib.ST_NCHAIN]), branch)
 
+        if not ran_fused and int(status[_lib.ST_NMERGED]) == 0:
+            # nothing was merged: the sequence is unchanged and the gather kernel did not run — hand the inputs back
+            # (the reference returns copies with the same values; its callers rebind them, modeling_qwen2.py:46,67)
+            self._links_for = (self.patch_type, self.patch_type._version, device)
+            return hidden_states, position_embeddings, attention_mask
+
         outs = self._narrow(auxes, s_keep)
         self.patch_type = outs[0].reshape(bsz, -1)
         self._links_for = (self.patch_type, self.patch_type._version, device)
