@@ -137,39 +137,6 @@ __device__ __forceinline__ void acc_dot_norm(const uint4& va, const uint4& vb, f
     }
 }
 
-// the same with the norm of `a` as well (sim warps do not share norms: recomputing is cheaper than a hand-over)
-template <int DT>
-__device__ __forceinline__ void acc_pair2(const uint4& va, const uint4& vb, float2& dot, float2& na, float2& nb) {
-    if (DT == FF_BF16) {
-        const uint32_t aw[4] = {va.x, va.y, va.z, va.w}, bw[4] = {vb.x, vb.y, vb.z, vb.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            __nv_bfloat162 pa = *reinterpret_cast<const __nv_bfloat162*>(&aw[q]);
-            __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&bw[q]);
-            __nv_bfloat162 pp = __hmul2(pa, pb);
-            const uint32_t pw = *reinterpret_cast<uint32_t*>(&pp);
-            dot = __fadd2_rn(dot, make_float2(__uint_as_float(pw << 16), __uint_as_float(pw & 0xffff0000u)));
-            const float2 af = make_float2(__uint_as_float(aw[q] << 16), __uint_as_float(aw[q] & 0xffff0000u));
-            const float2 bf = make_float2(__uint_as_float(bw[q] << 16), __uint_as_float(bw[q] & 0xffff0000u));
-            na = __ffma2_rn(af, af, na);
-            nb = __ffma2_rn(bf, bf, nb);
-        }
-    } else {
-        float a[Num<DT>::EPV], b[Num<DT>::EPV];
-        Num<DT>::unpack(va, a);
-        Num<DT>::unpack(vb, b);
-#pragma unroll
-        for (int e = 0; e < Num<DT>::EPV; e += 2) {
-            if (DT == FF_F32) { dot.x += __fmul_rn(a[e], b[e]); dot.y += __fmul_rn(a[e + 1], b[e + 1]); }
-            else { dot.x += Num<DT>::rnd(a[e] * b[e]); dot.y += Num<DT>::rnd(a[e + 1] * b[e + 1]); }
-            na.x = fmaf(a[e], a[e], na.x);
-            na.y = fmaf(a[e + 1], a[e + 1], na.y);
-            nb.x = fmaf(b[e], b[e], nb.x);
-            nb.y = fmaf(b[e + 1], b[e + 1], nb.y);
-        }
-    }
-}
-
 template <int DT>
 __device__ __forceinline__ void acc_norm(const uint4& vb, float2& nb) {
     float b[Num<DT>::EPV];
