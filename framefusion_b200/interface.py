@@ -49,34 +49,20 @@ def _family(model):
 
 
 def apply_framefusion(model, cost, similarity_lower_bound, ratio_lower_bound):
-    """
-    Apply FrameFusion to the model
+    """Patch ``model`` in place so that its prefill runs FrameFusion (reference interface.py:47-137).
 
-    Args:
-        model: the model to apply FrameFusion to
-        cost: the cost of the FrameFusion
-        similarity_lower_bound: the similarity lower bound of the FrameFusion
-        ratio_lower_bound: the ratio lower bound of the FrameFusion
-    """
-    fam = _family(model)
-    if fam is None:
+    ``cost`` is the compute budget relative to the dense model, ``similarity_lower_bound`` the cosine threshold
+    above which adjacent-frame tokens merge, ``ratio_lower_bound`` the merged fraction below which merging stops
+    and pruning takes over.  Unsupported model types print the model and raise ``NotImplementedError``."""
+    family = _family(model)
+    if family is None:
         print(f"Model not supported")
         print(f"Model type: {type(model)}")
         print(model)
         raise NotImplementedError
-    llm_key, (llm_forward, decoder_forward, attention_forward) = fam
-    replace_framefusion_forward(
-        model,
-        cost=cost,
-        similarity_lower_bound=similarity_lower_bound,
-        ratio_lower_bound=ratio_lower_bound,
-        llm_forward=llm_forward,
-        decoder_forward=decoder_forward,
-        attention_forward=attention_forward,
-        llm_key=llm_key,
-        decoder_key="layers",
-        attention_key="self_attn",
-    )
+    llm_key, trio = family
+    replace_framefusion_forward(model, cost, similarity_lower_bound, ratio_lower_bound, *trio,
+                                llm_key=llm_key, decoder_key="layers", attention_key="self_attn")
 
 
 def get_token_type(model):
@@ -85,6 +71,25 @@ def get_token_type(model):
     if _family(model) is None:
         raise NotImplementedError
     return None
+
+
+def _rebind(target: nn.Module, fn: Callable, operator: FrameFusion):
+    target.framefusion = operator
+    target.forward = MethodType(fn, target)
+
+
+def _keep_accelerate_hook(layer: nn.Module, fn: Callable):
+    """accelerate's device-alignment hook wraps ``forward``; after the rebinding it has to wrap the new one
+    (reference :204-207).  A no-op when the layer was not dispatched or accelerate is not installed."""
+    hook = getattr(layer, "_hf_hook", None)
+    if hook is None:
+        return
+    try:
+        from accelerate.hooks import add_hook_to_module
+    except ModuleNotFoundError:
+        return
+    layer._old_forward = MethodType(fn, layer)
+    add_hook_to_module(layer, hook)
 
 
 def replace_framefusion_forward(
@@ -99,38 +104,20 @@ def replace_framefusion_forward(
     decoder_key: str = "layers",
     attention_key: str = "self_attn",
 ):
-    """
-    Replace the forward method of the model with the framefusion forward method.
-    Make framefusion a property of the model.
-
-    The keys are accessed in an hierarchical manner: llm_key -> decoder_key -> attention_key. Each key can have
-    multiple hierarchies, e.g. "llm.model", which will be accessed by module.llm.model
-    """
-    framefusion = FrameFusion(cost, similarity_lower_bound, ratio_lower_bound)
-    module.framefusion = framefusion
+    """Creates ONE ``FrameFusion`` operator, hangs it on ``module``, on the language model found under ``llm_key``,
+    on every decoder layer under ``decoder_key`` and on every attention module under ``attention_key`` (dotted
+    paths, e.g. ``"llm.model"``), and rebinds their ``forward`` to the three callables (reference :169-214)."""
+    operator = FrameFusion(cost, similarity_lower_bound, ratio_lower_bound)
+    module.framefusion = operator
 
     llm = get_attr_by_name(module, llm_key)
     assert isinstance(llm, PreTrainedModel), f"{llm_key} is not a PreTrainedModel"
-    llm.framefusion = framefusion
-    llm.forward = MethodType(llm_forward, llm)
+    _rebind(llm, llm_forward, operator)
 
-    decoder_layers = get_attr_by_name(llm, decoder_key)
-    for i, decoder_layer in enumerate(decoder_layers):
-        assert isinstance(decoder_layer, nn.Module), f"{decoder_key}[{i}] is not a nn.Module"
-        decoder_layer.framefusion = framefusion
-        decoder_layer.forward = MethodType(decoder_forward, decoder_layer)
-
-        # keep accelerate's device-alignment hook alive across the rebinding (reference :204-207)
-        if hasattr(decoder_layer, "_hf_hook"):
-            try:
-                from accelerate.hooks import add_hook_to_module
-            except ModuleNotFoundError:
-                add_hook_to_module = None
-            if add_hook_to_module is not None:
-                decoder_layer._old_forward = MethodType(decoder_forward, decoder_layer)
-                add_hook_to_module(decoder_layer, decoder_layer._hf_hook)
-
-        attention = get_attr_by_name(decoder_layer, attention_key)
-        assert isinstance(attention, nn.Module), f"{decoder_key}[{i}].{attention_key} is not a nn.Module"
-        attention.framefusion = framefusion
-        attention.forward = MethodType(attention_forward, attention)
+    for index, layer in enumerate(get_attr_by_name(llm, decoder_key)):
+        assert isinstance(layer, nn.Module), f"{decoder_key}[{index}] is not a nn.Module"
+        _rebind(layer, decoder_forward, operator)
+        _keep_accelerate_hook(layer, decoder_forward)
+        attention = get_attr_by_name(layer, attention_key)
+        assert isinstance(attention, nn.Module), f"{decoder_key}[{index}].{attention_key} is not a nn.Module"
+        _rebind(attention, attention_forward, operator)

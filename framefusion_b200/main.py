@@ -515,27 +515,22 @@ class FrameFusion(nn.Module):
 
     @staticmethod
     def _compute_pruning_ratio(sparsity_list, cost, num_layers=28):
-        """Budget formula, host doubles (main.py:321-343)."""
-        list_length = len(sparsity_list)
-        s = 1
-        total_calcution = 0
-        for i in range(list_length):
-            s *= (1 - sparsity_list[i])
-            total_calcution += s
-        remain_calcution = num_layers * cost - total_calcution
-        if remain_calcution < 0:
+        """Budget formula in host doubles (main.py:321-343): what fraction of the tokens still has to go so that the
+        remaining layers fit into ``num_layers * cost`` token-layers, given the fractions merged so far."""
+        alive, spent = 1, 0
+        for merged in sparsity_list:
+            alive *= (1 - merged)
+            spent += alive
+        budget_left = num_layers * cost - spent
+        if budget_left < 0:
             raise ValueError("The cost is too small")
-        if remain_calcution / ((num_layers - list_length) * s) > 1:
-            return 0
-        return 1 - (remain_calcution / ((num_layers - list_length) * s))
+        share = budget_left / ((num_layers - len(sparsity_list)) * alive)
+        return 0 if share > 1 else 1 - share
 
 
 def cosine_similarity(mat1, mat2):
-    """Exported helper of the reference (main.py:345-349); the operator itself uses the fused kernels."""
-    dot_product = torch.sum(mat1 * mat2, dim=-1)
-    norm_vec1 = torch.norm(mat1, dim=-1)
-    norm_vec2 = torch.norm(mat2, dim=-1)
-    return dot_product / (norm_vec1 * norm_vec2)
+    """Exported helper of the reference (main.py:345-349), in torch ops; the operator itself uses the kernels."""
+    return (mat1 * mat2).sum(dim=-1) / (mat1.norm(dim=-1) * mat2.norm(dim=-1))
 
 
 def find_contigious_latter_index(index_tensor: torch.LongTensor) -> torch.Tensor:
