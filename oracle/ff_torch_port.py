@@ -55,7 +55,7 @@ def similarity_by_patch(hidden: torch.Tensor, patch_type: torch.Tensor, patch_nu
     h = hidden[0]
     order = by_patch_order(patch_type, patch_num)
     n = order.numel()
-    sim = torch.full((n,), IGNORE_TOKEN, dtype=h.dtype)
+    sim = torch.full((n,), IGNORE_TOKEN, dtype=h.dtype, device=h.device)
     if n < 2:
         return sim, order
     rows = h[order]                                        # by-patch rows, gathered once
@@ -73,14 +73,15 @@ def merge_runs_(hidden: torch.Tensor, order: torch.Tensor, merge_index: torch.Te
     unflagged position in front of it: members are added one at a time in ascending order in the hidden dtype
     (``index_add_`` on CPU is sequential), then the sum is divided by the member count + 1."""
     h = hidden[0]
-    keep = torch.ones(h.shape[0], dtype=torch.bool)
+    dev = h.device
+    keep = torch.ones(h.shape[0], dtype=torch.bool, device=dev)
     if merge_index.numel() == 0:
         return keep
     n = order.numel()
-    flagged = torch.zeros(n, dtype=torch.bool)
+    flagged = torch.zeros(n, dtype=torch.bool, device=dev)
     flagged[merge_index] = True
     keep[order[merge_index]] = False
-    pos = torch.arange(n)
+    pos = torch.arange(n, device=dev)
     anchor = torch.where(flagged, torch.full_like(pos, -1), pos).cummax(0).values    # last unflagged position <= j
     members = merge_index
     a_of_m = anchor[members]                               # -1 (run at position 0) wraps like python indexing
@@ -101,6 +102,7 @@ class TorchPortFrameFusion:
         self.cost = cost
         self.similarity_lower_bound = similarity_lower_bound
         self.ratio_lower_bound = ratio_lower_bound
+        self.trace = True                 # keep what flowed between the stages (the parity harness reads it)
 
     def prepare(self, patch_type, patch_num, image_token_start_index, image_token_end_index, image_token_length,
                 original_length, finish_merging=False, finish_pruning=False, sparsity_list: Optional[List[float]] = None):
@@ -145,16 +147,19 @@ class TorchPortFrameFusion:
             ratio = pruning_ratio(self.sparsity_list, self.cost)
             k = round(length * (1 - ratio))
             top = torch.topk(imp[start:start + length], k).indices + start
-            keep = torch.cat((torch.arange(start), top, torch.arange(start + length, q_len))).sort().values
+            dev = hidden_states.device
+            keep = torch.cat((torch.arange(start, device=dev), top, torch.arange(start + length, q_len, device=dev))).sort().values
             hidden_states = hidden_states[:, keep, :]
             position_embeddings = self._select_pos(position_embeddings, keep)
             if attention_mask is not None:
                 attention_mask = attention_mask[:, :, keep, :][:, :, :, keep]
             self.finish_pruning = True
-            self.last = dict(stage="prune", keep=keep.numpy(), importance=imp.float().numpy(), start=start, length=length)
+            if self.trace:
+                self.last = dict(stage="prune", keep=keep.cpu().numpy(), importance=imp.float().cpu().numpy(), start=start, length=length)
 
         if q_len > 1 and not self.finish_merging:                                    # merge stage (:104-138)
             assert bsz == 1, "Only support batch size 1"
+            self.patch_type = self.patch_type.to(hidden_states.device)
             bound = pruning_ratio(self.sparsity_list, self.cost)
             sim, order = similarity_by_patch(hidden_states, self.patch_type, self.patch_num)
             n_vis = int((self.patch_type != TEXT_TOKEN).sum())
@@ -176,8 +181,9 @@ class TorchPortFrameFusion:
             position_embeddings = self._select_pos(position_embeddings, keep)
             if attention_mask is not None:
                 attention_mask = attention_mask[:, :, keep, :][:, :, :, keep]
-            self.last = dict(stage="merge", branch=branch, keep_mask=keep.numpy(), merge_index=merge_index.numpy(),
-                             sim_values=sim.float().numpy(), order=order.numpy())
+            if self.trace:
+                self.last = dict(stage="merge", branch=branch, keep_mask=keep.cpu().numpy(), merge_index=merge_index.cpu().numpy(),
+                                 sim_values=sim.float().cpu().numpy(), order=order.cpu().numpy())
         return hidden_states, position_embeddings, attention_mask
 
 
@@ -190,9 +196,9 @@ def last_query_attention(query, key, num=1, is_causal=False, scale=None):
     q = query[:, :, -num:, :]
     length, s_len = q.shape[-2], key.shape[-2]
     scale = q.shape[-1] ** -0.5 if scale is None else scale
-    bias = torch.zeros(length, s_len, dtype=q.dtype)
+    bias = torch.zeros(length, s_len, dtype=q.dtype, device=q.device)
     if is_causal:
-        hide = torch.ones(length, s_len, dtype=torch.bool).triu(diagonal=s_len - length + 1)
+        hide = torch.ones(length, s_len, dtype=torch.bool, device=q.device).triu(diagonal=s_len - length + 1)
         bias.masked_fill_(hide, float("-inf"))
     w = q @ key.transpose(-2, -1) * scale
     w += bias

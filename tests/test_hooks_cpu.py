@@ -227,3 +227,21 @@ def test_layout_builders_match_the_reference_formulas():
     pt, patch_num, start, end, length, orig = llava_video_prepare_args(ids, -200, 210 * 4, 27)
     assert patch_num == 210 and (start, end, length, orig) == (3, 3 + 840 - 1, 840, 6 + 840 - 1)
     assert pt.tolist() == [[-1] * 3 + list(range(210)) * 4 + [-1] * (orig - end - 1)]
+
+
+def test_layer_split_moves_inputs_between_blocks(patched_importance):
+    """dispatch.split_layers: contiguous layer blocks and input-moving pre-hooks (what accelerate's device_map does
+    for the reference).  On a CPU-only machine both "devices" are the CPU: the hooks must be transparent."""
+    from framefusion_b200.dispatch import layer_devices, split_layers
+    assert [str(d) for d in layer_devices(7, ["cuda:0", "cuda:1", "cuda:2"])] == ["cuda:0"] * 3 + ["cuda:1"] * 2 + ["cuda:2"] * 2
+    model = tiny_model()
+    wl = workload()
+    with torch.no_grad():
+        want = manual_reference(model, wl, OracleOperator(0.3, 0.6, 0.1))
+        op = OracleOperator(0.3, 0.6, 0.1)
+        install(model, op)
+        placement = split_layers(model.model, ["cpu", "cpu"])
+        assert len(placement) == len(model.model.layers)
+        model.framefusion.prepare(*wl.prepare_args())
+        got = model.model(inputs_embeds=wl.hidden.clone(), use_cache=True).last_hidden_state
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-5)
