@@ -40,6 +40,31 @@ static int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(FF_E_CUDA, "launch %s: %s", name, cudaGetErrorString(e_)); \
     } while (0)
 
+// Launch with programmatic stream serialisation: the grid may become resident while the previous kernel of the
+// stream drains (it has to pass pdl_wait() before touching that kernel's results), which hides the launch latency
+// between the short dependent kernels of one call.  Every kernel launched through here starts with pdl_wait().
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+#define FF_LAUNCH(name, kernel, grid, block, smem, st, ...)                                        \
+    do {                                                                                           \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                        \
+        cudaError_t e_ = launch_pdl(kernel, dim3(grid), dim3(block), smem, st, __VA_ARGS__);       \
+        if (e_ != cudaSuccess) return fail(FF_E_CUDA, "launch %s: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
 struct ff_ctx {
     int device;
     int64_t* h_status;
@@ -56,6 +81,9 @@ struct ff_ctx {
     int max_smem;        // opt-in dynamic shared memory per block
     char* scratch;       // device buffer of the single-pass kernel (averaged anchors in flight), owned by the context
     size_t scratch_bytes;
+    int count_clean[2];  // counters[bank][C_COUNT] is known to be zero (set by the kernel that decided the previous call)
+    unsigned bar_base;   // value of the grid-barrier word before the next k_keep_scan (it is not reset between merge calls)
+    int bar_dirty;       // the prune stage left the barrier word at an unknown value
     long long* trace;    // development aid: device buffer for the single-pass kernel's time stamps (ff_debug_trace)
 };
 
@@ -222,12 +250,11 @@ int launch_similarity(const Ws& w, int bank, const void* hidden, int dtype, int6
     return dispatch_dtype(dtype, [&](auto dt) {
         constexpr int DT = decltype(dt)::value;
         if (vec)
-            k_similarity<DT, true><<<grid, 256, 0, st>>>(hidden, (int)H, w.order[bank], w.chain[bank], w.counters[bank],
-                                                         (float)thr, w.sim, w.flag, w.counters[bank]);
+            FF_LAUNCH("k_similarity", (k_similarity<DT, true>), grid, 256, 0, st, hidden, (int)H, w.order[bank], w.chain[bank],
+                      w.counters[bank], (float)thr, w.sim, w.flag, w.counters[bank]);
         else
-            k_similarity<DT, false><<<grid, 256, 0, st>>>(hidden, (int)H, w.order[bank], w.chain[bank], w.counters[bank],
-                                                          (float)thr, w.sim, w.flag, w.counters[bank]);
-        FF_LAUNCH_CHECK("k_similarity");
+            FF_LAUNCH("k_similarity", (k_similarity<DT, false>), grid, 256, 0, st, hidden, (int)H, w.order[bank], w.chain[bank],
+                      w.counters[bank], (float)thr, w.sim, w.flag, w.counters[bank]);
         return (int)FF_OK;
     });
 }
@@ -261,10 +288,9 @@ int launch_merge_gather(const ff_ctx* ctx, const Ws& w, int bank, const void* hi
     if (vec_ok(hidden, out, H, dtype)) {
         return dispatch_dtype(dtype, [&](auto dt) {
             constexpr int DT = decltype(dt)::value;
-            k_merge_gather<DT><<<(int)((S + GATHER_WARPS - 1) / GATHER_WARPS) * 2 + 1, GATHER_WARPS * 32, 0, st>>>(hidden, out, (int)nvec, w.srcidx, w.rec, w.order[bank],
-                                                                        w.flag, w.counters[bank], w.rank[bank ^ 1],
-                                                                        w.counters[bank ^ 1], ap);
-            FF_LAUNCH_CHECK("k_merge_gather");
+            FF_LAUNCH("k_merge_gather", k_merge_gather<DT>, (int)((S + GATHER_WARPS - 1) / GATHER_WARPS) * 2 + 1, GATHER_WARPS * 32, 0, st,
+                      hidden, out, (int)nvec, w.srcidx, w.rec, w.order[bank], w.flag, w.counters[bank], w.rank[bank ^ 1],
+                      w.counters[bank ^ 1], ap);
             return (int)FF_OK;
         });
     }
@@ -449,14 +475,16 @@ int ff_build_links(ff_ctx* ctx, void* ws, int64_t ws_bytes, const int64_t* patch
     const int n_b = (int)n_ids + 1;                        // chain buckets + the bucket of rows outside the chains
     FF_CUDA(cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st));
     ctx->epoch = 0;
+    ctx->bar_base = 0;
+    ctx->bar_dirty = 0;
+    ctx->count_clean[0] = ctx->count_clean[1] = 1;
     if (S > 0) {
         k_links_hist<<<n_chunks, LINK_CHUNK, 0, st>>>(patch_type, (int)S, (int)n_ids, w.hist, w.counters[0]);
         FF_LAUNCH_CHECK("k_links_hist");
-        k_links_colscan<<<(n_b + 7) / 8, 256, 0, st>>>(w.hist, n_chunks, n_b, w.len[0], w.base, w.counters[0], ctx->d_status);
-        FF_LAUNCH_CHECK("k_links_colscan");
-        k_links_scatter<<<n_chunks, LINK_CHUNK, 0, st>>>(patch_type, (int)S, (int)n_ids, w.hist, w.base, w.order[0],
-                                                        w.chain[0], w.rank[0]);
-        FF_LAUNCH_CHECK("k_links_scatter");
+        FF_LAUNCH("k_links_colscan", k_links_colscan, (n_b + 7) / 8, 256, 0, st, w.hist, n_chunks, n_b, w.len[0], w.base,
+                  w.counters[0], ctx->d_status);
+        FF_LAUNCH("k_links_scatter", k_links_scatter, n_chunks, LINK_CHUNK, 0, st, patch_type, (int)S, (int)n_ids, w.hist,
+                  w.base, w.order[0], w.chain[0], w.rank[0]);
     } else {
         k_links_status<<<1, 1, 0, st>>>(w.counters[0], ctx->d_status);
         FF_LAUNCH_CHECK("k_links_status");
@@ -479,7 +507,8 @@ int ff_similarity(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, i
     cudaStream_t st = (cudaStream_t)stream;
     FF_CUDA(cudaSetDevice(ctx->device));
     const int bank = ctx->parity;
-    FF_CUDA(cudaMemsetAsync(&w.counters[bank][C_COUNT], 0, 8, st));
+    if (!ctx->count_clean[bank]) FF_CUDA(cudaMemsetAsync(&w.counters[bank][C_COUNT], 0, 8, st));
+    ctx->count_clean[bank] = 0;
     if (int rc = launch_similarity(w, bank, hidden, dtype, S, H, thr, st)) return rc;
     if (S > 0 && (sim_out || order_out)) {
         k_store_sim<<<(int)((S + 255) / 256), 256, 0, st>>>(w.sim, w.counters[bank], dtype, sim_out, w.order[bank], order_out);
@@ -544,11 +573,14 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
         if (plan_stream_args(ctx, w, bank, hidden, hidden_out, dtype, S, H, thr, bound, ap, &sa, &plan)) {
             const unsigned epoch = ctx->epoch + 1;
             sa.tag = (epoch - 1) % 127 + 1;
+            if (!ctx->count_clean[bank]) FF_CUDA(cudaMemsetAsync(&w.counters[bank][C_COUNT], 0, 8, st));
             if (epoch > 1 && sa.tag == 1) FF_CUDA(cudaMemsetAsync(w.state, 0, (size_t)ctx->cap, st));   // tags wrap
             int rc = launch_stream(dtype, sa, plan, st);
             if (rc != FF_OK) return fail(rc, "single-pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             g_launches.fetch_add(1, std::memory_order_relaxed);
             ctx->epoch = epoch;
+            ctx->count_clean[bank] = 0;
+            ctx->count_clean[nb] = 1;
             ctx->last_parity = bank;
             ctx->parity = nb;
             ctx->links_S = -2;
@@ -559,7 +591,9 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     }
     if (!ctx->have_order) return fail(FF_E_BADARG, "by-patch order not in the workspace (the fused path does not keep it): call ff_build_links");
 
-    FF_CUDA(cudaMemsetAsync(&w.counters[bank][C_COUNT], 0, 8, st));
+    if (!ctx->count_clean[bank]) FF_CUDA(cudaMemsetAsync(&w.counters[bank][C_COUNT], 0, 8, st));
+    ctx->count_clean[bank] = 0;
+    ctx->count_clean[nb] = 1;                              // the deciding kernel zeroes the next bank's count
     if (int rc = launch_similarity(w, bank, hidden, dtype, S, H, thr, st)) return rc;
     DecideArgs a;
     a.counters = w.counters[bank];
@@ -589,13 +623,17 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
         int G = ctx->sm_count / 2;
         if (G > 160) G = 160;
         if (G < 1) G = 1;
-        FF_CUDA(cudaMemsetAsync(w.barrier, 0, 4, st));
-        k_keep_scan<<<G, SEL_THREADS, 0, st>>>(sa);
-        FF_LAUNCH_CHECK("k_keep_scan");
+        if (ctx->bar_dirty) {
+            FF_CUDA(cudaMemsetAsync(w.barrier, 0, 4, st));
+            ctx->bar_base = 0;
+            ctx->bar_dirty = 0;
+        }
+        sa.bar_base = ctx->bar_base;
+        ctx->bar_base += 2u * (unsigned)G;                 // every block adds 2, on either branch
+        FF_LAUNCH("k_keep_scan", k_keep_scan, G, SEL_THREADS, 0, st, sa);
         a.topk_only = 1;
     }
-    k_decide_scan<<<1, SEL_THREADS, 0, st>>>(a);
-    FF_LAUNCH_CHECK("k_decide_scan");
+    FF_LAUNCH("k_decide_scan", k_decide_scan, 1, SEL_THREADS, 0, st, a);
     if (int rc = launch_merge_gather(ctx, w, bank, hidden, hidden_out, dtype, S, H, ap, st)) return rc;
     ctx->last_parity = bank;
     ctx->parity = nb;
@@ -624,16 +662,14 @@ int ff_importance(ff_ctx* ctx, const void* q, const void* k, int dtype, int64_t 
         constexpr int DT = decltype(dt)::value;
         if (vec) {
             if (smem > 48 * 1024) FF_CUDA(cudaFuncSetAttribute(k_importance_logits<DT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_importance_logits<DT, true><<<grid, IMP_THREADS, smem, st>>>(q, k, (int)Hq, (int)Hk, (int)S, (int)D, (int)num, q_hs, q_ss,
-                                                                           k_hs, k_ss, is_causal, (float)scale, (float*)scratch);
+            FF_LAUNCH("k_importance_logits", (k_importance_logits<DT, true>), grid, IMP_THREADS, smem, st, q, k, (int)Hq, (int)Hk,
+                      (int)S, (int)D, (int)num, q_hs, q_ss, k_hs, k_ss, is_causal, (float)scale, (float*)scratch);
         } else {
             if (smem > 48 * 1024) FF_CUDA(cudaFuncSetAttribute(k_importance_logits<DT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_importance_logits<DT, false><<<grid, IMP_THREADS, smem, st>>>(q, k, (int)Hq, (int)Hk, (int)S, (int)D, (int)num, q_hs, q_ss,
-                                                                            k_hs, k_ss, is_causal, (float)scale, (float*)scratch);
+            FF_LAUNCH("k_importance_logits", (k_importance_logits<DT, false>), grid, IMP_THREADS, smem, st, q, k, (int)Hq, (int)Hk,
+                      (int)S, (int)D, (int)num, q_hs, q_ss, k_hs, k_ss, is_causal, (float)scale, (float*)scratch);
         }
-        FF_LAUNCH_CHECK("k_importance_logits");
-        k_softmax_rows<DT><<<(int)(Hq * num), 1024, 0, st>>>((const float*)scratch, (int)S, probs_out);
-        FF_LAUNCH_CHECK("k_softmax_rows");
+        FF_LAUNCH("k_softmax_rows", k_softmax_rows<DT>, (int)(Hq * num), 1024, 0, st, (const float*)scratch, (int)S, probs_out);
         return (int)FF_OK;
     });
     return rc;
@@ -655,10 +691,13 @@ int ff_prune_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* attn, in
     cudaStream_t st = (cudaStream_t)stream;
     FF_CUDA(cudaSetDevice(ctx->device));
     const int bank = ctx->parity;
+    const bool grid_select = S >= 2 * SEL_THREADS;
+    if (grid_select) {
+        FF_CUDA(cudaMemsetAsync(w.barrier, 0, 256 + 4 * 256 * 4, st));     // barrier word + histograms (adjacent)
+    }
     int rc = dispatch_dtype(dtype, [&](auto dt) {
         constexpr int DT = decltype(dt)::value;
-        k_row_mean<DT><<<(int)((S + 255) / 256), 256, 0, st>>>(attn, (int)n_rows, (int)S, w.sim);
-        FF_LAUNCH_CHECK("k_row_mean");
+        FF_LAUNCH("k_row_mean", k_row_mean<DT>, (int)((S + 255) / 256), 256, 0, st, attn, (int)n_rows, (int)S, w.sim);
         return (int)FF_OK;
     });
     if (rc) return rc;
@@ -673,7 +712,7 @@ int ff_prune_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* attn, in
     a.start = (int)start;
     a.length = (int)length;
     a.k = k;
-    if (S >= 2 * SEL_THREADS) {
+    if (grid_select) {
         PruneGridArgs ga;
         ga.p = a;
         ga.hist = w.sel_hist;
@@ -683,20 +722,18 @@ int ff_prune_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* attn, in
         int G = ctx->sm_count / 2;
         if (G > 160) G = 160;
         if (G < 1) G = 1;
-        FF_CUDA(cudaMemsetAsync(w.barrier, 0, 256 + 4 * 256 * 4, st));     // barrier word + histograms (adjacent)
-        k_prune_select<<<G, SEL_THREADS, 0, st>>>(ga);
-        FF_LAUNCH_CHECK("k_prune_select");
+        FF_LAUNCH("k_prune_select", k_prune_select, G, SEL_THREADS, 0, st, ga);
+        ctx->bar_dirty = 1;
     } else {
-        k_prune_scan<<<1, SEL_THREADS, 0, st>>>(a);
-        FF_LAUNCH_CHECK("k_prune_scan");
+        FF_LAUNCH("k_prune_scan", k_prune_scan, 1, SEL_THREADS, 0, st, a);
     }
     if (vec_ok(hidden, hidden_out, H, dtype)) {
         const int64_t nvec = H * (dtype == FF_F32 ? 4 : 2) / 16;
         int rcg = dispatch_dtype(dtype, [&](auto dt) {
             constexpr int DT = decltype(dt)::value;
-            k_merge_gather<DT><<<(int)((S + GATHER_WARPS - 1) / GATHER_WARPS), GATHER_WARPS * 32, 0, st>>>(hidden, hidden_out, (int)nvec, w.srcidx, nullptr, w.order[bank],
-                                                                  w.flag, w.counters[bank], nullptr, nullptr, ap);
-            FF_LAUNCH_CHECK("k_merge_gather");
+            FF_LAUNCH("k_merge_gather", k_merge_gather<DT>, (int)((S + GATHER_WARPS - 1) / GATHER_WARPS), GATHER_WARPS * 32, 0, st,
+                      hidden, hidden_out, (int)nvec, w.srcidx, nullptr, w.order[bank], w.flag, w.counters[bank], nullptr,
+                      nullptr, ap);
             return (int)FF_OK;
         });
         if (rcg) return rcg;

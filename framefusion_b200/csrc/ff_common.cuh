@@ -220,6 +220,16 @@ struct Divider {
     }
 };
 
+// Programmatic dependent launch (ff_api.cu: launch_pdl).  pdl_wait() returns once the previous kernel of the stream
+// has completed and its writes are visible; pdl_trigger() lets the next kernel's blocks become resident early (they
+// stop at their own pdl_wait()).  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+    pdl_wait();
+    pdl_trigger();
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);

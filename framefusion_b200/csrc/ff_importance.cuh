@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(IMP_THREADS)
 k_importance_logits(const void* __restrict__ q, const void* __restrict__ k, int n_q_heads, int n_kv_heads, int S, int D,
                     int num, int64_t q_hs, int64_t q_ss, int64_t k_hs, int64_t k_ss, int is_causal, float scale,
                     float* __restrict__ logits /* [Hq, num, S] float32 holding T values */) {
+    pdl_enter();
     extern __shared__ float s_q[];                        // [group * num][D]
     typedef typename Num<DT>::store_t st;
     const int hk = blockIdx.y;
@@ -85,6 +86,7 @@ k_importance_logits(const void* __restrict__ q, const void* __restrict__ k, int 
 template <int DT>
 __global__ void __launch_bounds__(1024)
 k_softmax_rows(const float* __restrict__ logits, int S, void* __restrict__ probs) {
+    pdl_enter();
     __shared__ float s_red[32];
     __shared__ float s_val;
     const float* x = logits + (int64_t)blockIdx.x * S;

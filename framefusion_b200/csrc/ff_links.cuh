@@ -18,6 +18,7 @@ constexpr int LINK_CHUNK = 512;
 
 __global__ void __launch_bounds__(LINK_CHUNK)
 k_links_hist(const int64_t* __restrict__ pt, int S, int n_ids, int* __restrict__ hist, int64_t* counters) {
+    pdl_trigger();
     __shared__ int s_nv[LINK_CHUNK / 32];
     const int i = blockIdx.x * LINK_CHUNK + threadIdx.x;
     int vis = 0;
@@ -45,6 +46,7 @@ k_links_hist(const int64_t* __restrict__ pt, int S, int n_ids, int* __restrict__
 __global__ void __launch_bounds__(256)
 k_links_colscan(int* __restrict__ hist, int n_chunks, int n_b, int* __restrict__ total, int* __restrict__ base,
                 int64_t* counters, int64_t* status) {
+    pdl_enter();
     const int n_ids = n_b;                                 // (name kept below: columns of hist)
     __shared__ int s_scan[33];
     __shared__ int s_last;
@@ -97,6 +99,7 @@ __global__ void __launch_bounds__(LINK_CHUNK)
 k_links_scatter(const int64_t* __restrict__ pt, int S, int n_ids, const int* __restrict__ hist,
                 const int* __restrict__ base, int* __restrict__ order, int* __restrict__ chain,
                 int* __restrict__ rank) {
+    pdl_enter();
     __shared__ __align__(16) int s_key[LINK_CHUNK];
     const int t = threadIdx.x;
     const int i = blockIdx.x * LINK_CHUNK + t;

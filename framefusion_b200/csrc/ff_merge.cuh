@@ -125,6 +125,7 @@ k_merge_gather(const void* __restrict__ hidden, void* __restrict__ out, int nvec
                const int4* __restrict__ rec, const int* __restrict__ order, const uint8_t* __restrict__ flag,
                const int64_t* __restrict__ counters, const int* __restrict__ rank_of_dst,
                const int64_t* __restrict__ counters_next, const __grid_constant__ AuxPack aux) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
     const int s_keep = (int)counters[C_SKEEP];

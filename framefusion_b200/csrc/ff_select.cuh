@@ -104,6 +104,7 @@ struct DecideArgs {
 
 __global__ void __launch_bounds__(SEL_THREADS)
 k_decide_scan(DecideArgs a) {
+    pdl_enter();
     __shared__ int s_hist[256];
     __shared__ int s_scan[33];
     __shared__ uint32_t s_misc[4];
@@ -233,7 +234,8 @@ k_decide_scan(DecideArgs a) {
 struct ScanArgs {
     DecideArgs d;
     int* part;                   // [2 * gridDim.x] kept rows per block (sequence order, by-patch order)
-    unsigned* barrier;           // zeroed by the host before the launch
+    unsigned* barrier;           // counts up across the calls of one prefill: every block adds 2 per launch
+    unsigned bar_base;           // its value when this launch starts (host bookkeeping, ff_api.cu)
 };
 
 __device__ __forceinline__ bool threshold_branch(const int64_t* counters, double bound) {
@@ -247,7 +249,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(bar, 1u);
-        while (*(volatile unsigned*)bar < target) __nanosleep(20);
+        while ((int)(*(volatile unsigned*)bar - target) < 0) __nanosleep(20);
         __threadfence();
     }
     __syncthreads();
@@ -264,11 +266,15 @@ __device__ __forceinline__ int block_sum_prefix(const int* part, int n, int* s_s
 
 __global__ void __launch_bounds__(SEL_THREADS)
 k_keep_scan(ScanArgs a) {
+    pdl_enter();
     __shared__ int s_scan[33];
     __shared__ int s_base;
     const DecideArgs& d = a.d;
-    if (!threshold_branch(d.counters, d.bound)) return;
     const int t = threadIdx.x, G = gridDim.x, b = blockIdx.x;
+    if (!threshold_branch(d.counters, d.bound)) {
+        if (t == 0) atomicAdd(a.barrier, 2u);              // keep the barrier word in step with the host's count
+        return;
+    }
     const int N = (int)d.counters[C_N], S = d.S;
     // block b owns sequence rows [s0, s1) and by-patch positions [n0, n1), both multiples of the scan tile
     const int per_s = ((S + G - 1) / G + SEL_THREADS - 1) / SEL_THREADS * SEL_THREADS;
@@ -288,7 +294,7 @@ k_keep_scan(ScanArgs a) {
     if (t == 0) a.part[b] = tot;
     block_exclusive_scan(c_bp, s_scan, &tot);
     if (t == 0) a.part[G + b] = tot;
-    grid_barrier(a.barrier, (unsigned)G);
+    grid_barrier(a.barrier, a.bar_base + (unsigned)G);
 
     // ---- phase 2: destination rows in sequence order
     int carry = block_sum_prefix(a.part, b, s_scan);
@@ -308,7 +314,7 @@ k_keep_scan(ScanArgs a) {
         }
         carry += tot;
     }
-    grid_barrier(a.barrier, (unsigned)(2 * G));
+    grid_barrier(a.barrier, a.bar_base + (unsigned)(2 * G));
 
     // ---- phase 3: the by-patch arrays of the next call
     carry = block_sum_prefix(a.part + G, b, s_scan);
@@ -366,6 +372,7 @@ struct PruneArgs {
 
 __global__ void __launch_bounds__(SEL_THREADS)
 k_prune_scan(PruneArgs a) {
+    pdl_enter();
     __shared__ int s_hist[256];
     __shared__ int s_scan[33];
     __shared__ uint32_t s_misc[4];
@@ -418,6 +425,7 @@ struct PruneGridArgs {
 
 __global__ void __launch_bounds__(SEL_THREADS)
 k_prune_select(PruneGridArgs a) {
+    pdl_enter();
     __shared__ int s_hist[256];
     __shared__ int s_scan[33];
     __shared__ uint32_t s_digit, s_need;
@@ -525,6 +533,7 @@ k_prune_select(PruneGridArgs a) {
 // importance[s] = T( sum_rows attn[row][s] / n_rows )      (torch.mean(dim=(1,2)), main.py:70)
 template <int DT>
 __global__ void k_row_mean(const void* __restrict__ attn, int n_rows, int S, float* __restrict__ imp) {
+    pdl_enter();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     float acc = 0.f;

@@ -13,6 +13,7 @@ __global__ void __launch_bounds__(256)
 k_similarity(const void* __restrict__ hidden, int H, const int* __restrict__ order, const int* __restrict__ chain,
              const int64_t* __restrict__ counters_in, float thr, float* __restrict__ sim, uint8_t* __restrict__ flag,
              int64_t* counters) {
+    pdl_enter();
     __shared__ int s_cnt[8];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int N = (int)counters_in[C_N];
