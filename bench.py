@@ -188,12 +188,40 @@ def cpu_baseline(cfg, seconds=12.0):
 
     step()
     n, t0 = 0, time.perf_counter()
-    while n < 3 or (time.perf_counter() - t0 < seconds and n < 50):
+    while n < 3 or (time.perf_counter() - t0 < seconds and n < 200):
         step()
         n += 1
     dt = time.perf_counter() - t0
     return {"value": wl.n_vision * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n} full steps of the {cfg} workload on torch {torch.__version__} CPU, {dt:.1f} s"}
+
+
+def torch_gpu_port(cfg, device, steps=10):
+    """Informative second baseline: the reference's op sequence (torch port) run by torch-CUDA on the
+    same GPU — launch and synchronisation bound.  Only with --torch-gpu-port; never the product path."""
+    from oracle import ff_torch_port as port
+    c = synth.CONFIGS[cfg]
+    wl = synth.to_device(synth.make_workload(c["frames"], c["patch_num"], c["hidden"], c["dtype"], seed=0), device)
+    q, k = synth.make_attention_inputs(wl.seq_len, N_HEADS, N_KV_HEADS, HEAD_DIM, c["dtype"], seed=0)
+    q_last, k = q[:, :, -1:, :].contiguous().to(device), k.to(device)
+
+    def step():
+        ff = port.TorchPortFrameFusion(c["cost"], c["slb"], c["rlb"])
+        return run_step(ff, wl, wl.hidden.clone(), wl.cos, wl.sin, q_last, k,
+                        lambda qq, kk: port.last_query_attention(qq, kk, num=1, is_causal=True))
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": wl.n_vision / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "what": f"oracle/ff_torch_port.py on torch-CUDA {torch.__version__}, {steps} steps incl. one 264-MB clone per step"}
 
 
 def max_over_ranks(ms, dist, device):
@@ -218,6 +246,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(synth.CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-gpu-port", action="store_true", help="also time the torch port of the reference on this GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -362,6 +391,8 @@ def main():
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg)
+        if world == 1 and args.torch_gpu_port:
+            line["torch_gpu_port"] = torch_gpu_port(cfg, dev)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -44,8 +44,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if _build.needs_build():
+    path = os.environ.get("FF_LIB_PATH") or _build.LIB_PATH     # FF_LIB_PATH: a prebuilt library elsewhere (no rebuild)
+    if path == _build.LIB_PATH and _build.needs_build():
         try:
             _build.build()
         except Exception as e:  # no nvcc on a runtime box: use the shipped binary if there is one
