@@ -279,6 +279,12 @@ int launch_merge_compact(const Ws& w, int bank, const void* hidden, void* out, i
 
 
 
+// blocks of k_merge_gather: one warp per row, plus one block of aux rows behind every four of those
+static int gather_grid(int64_t S, int n_aux) {
+    const int64_t main_blocks = (S + GATHER_WARPS - 1) / GATHER_WARPS;
+    return (int)(n_aux ? 5 * ((main_blocks + 3) / 4) : main_blocks);
+}
+
 // merged rows + compaction of hidden and aux, two-pass path: the gather kernel when rows are 16-byte multiples,
 // the generic kernels otherwise
 int launch_merge_gather(const ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* out, int dtype, int64_t S,
@@ -288,9 +294,8 @@ int launch_merge_gather(const ff_ctx* ctx, const Ws& w, int bank, const void* hi
     if (vec_ok(hidden, out, H, dtype)) {
         return dispatch_dtype(dtype, [&](auto dt) {
             constexpr int DT = decltype(dt)::value;
-            FF_LAUNCH("k_merge_gather", k_merge_gather<DT>, (int)((S + GATHER_WARPS - 1) / GATHER_WARPS) * 2 + 1, GATHER_WARPS * 32, 0, st,
-                      hidden, out, (int)nvec, w.srcidx, w.rec, w.order[bank], w.flag, w.counters[bank], w.rank[bank ^ 1],
-                      w.counters[bank ^ 1], ap);
+            FF_LAUNCH("k_merge_gather", k_merge_gather<DT>, gather_grid(S, ap.n), GATHER_WARPS * 32, 0, st,
+                      hidden, out, (int)nvec, (int)S, w.srcidx, w.rec, w.order[bank], w.flag, w.counters[bank], w.counters[bank ^ 1], ap);
             return (int)FF_OK;
         });
     }
@@ -731,9 +736,8 @@ int ff_prune_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* attn, in
         const int64_t nvec = H * (dtype == FF_F32 ? 4 : 2) / 16;
         int rcg = dispatch_dtype(dtype, [&](auto dt) {
             constexpr int DT = decltype(dt)::value;
-            FF_LAUNCH("k_merge_gather", k_merge_gather<DT>, (int)((S + GATHER_WARPS - 1) / GATHER_WARPS), GATHER_WARPS * 32, 0, st,
-                      hidden, hidden_out, (int)nvec, w.srcidx, nullptr, w.order[bank], w.flag, w.counters[bank], nullptr,
-                      nullptr, ap);
+            FF_LAUNCH("k_merge_gather", k_merge_gather<DT>, gather_grid(S, ap.n), GATHER_WARPS * 32, 0, st,
+                      hidden, hidden_out, (int)nvec, (int)S, w.srcidx, nullptr, w.order[bank], w.flag, w.counters[bank], nullptr, ap);
             return (int)FF_OK;
         });
         if (rcg) return rcg;

@@ -32,7 +32,7 @@ enum Counter {
     C_ERR = 7,
     C_NMERGED = 8,
     C_NNEXT = 9,    // N of the links written for the next call
-    C_TICKET2 = 10,
+    C_TICKET2 = 10, // records handed out to the rows outside the chains (k_keep_scan / k_decide_scan)
     C_SLOTS = 32
 };
 
@@ -64,6 +64,25 @@ template <> struct Num<FF_BF16> {
     static __device__ __forceinline__ uint4 pack(const float* f) {
         return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
     }
+    // T(a + b) on a 16-byte vector: the packed add rounds the exact sum once, which equals the float32 add followed
+    // by the rounding to T (24 bits hold the sum of two 8-bit significands without a second rounding that matters)
+    static __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {
+        __nv_bfloat162 r = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+        return *reinterpret_cast<uint32_t*>(&r);
+    }
+    static __device__ __forceinline__ uint4 add_vec(const uint4& a, const uint4& b) {
+        return make_uint4(add2(a.x, b.x), add2(a.y, b.y), add2(a.z, b.z), add2(a.w, b.w));
+    }
+    // T(x * 2^-k): exact scaling (or one rounding into the subnormals), the same value x / 2^k rounds to
+    static __device__ __forceinline__ uint4 scale_vec(const uint4& a, float s) {
+        const __nv_bfloat162 m = __float2bfloat162_rn(s);
+        uint4 o;
+        const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+        __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) po[i] = __hmul2(pa[i], m);
+        return o;
+    }
     // T(a*b) for two packed pairs, returned as two floats
     static __device__ __forceinline__ void prod2(uint32_t a, uint32_t b, float& lo, float& hi) {
         __nv_bfloat162 p = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
@@ -92,6 +111,22 @@ template <> struct Num<FF_F16> {
     static __device__ __forceinline__ uint4 pack(const float* f) {
         return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
     }
+    static __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {       // see Num<FF_BF16>::add2 (11-bit significands)
+        __half2 r = __hadd2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+        return *reinterpret_cast<uint32_t*>(&r);
+    }
+    static __device__ __forceinline__ uint4 add_vec(const uint4& a, const uint4& b) {
+        return make_uint4(add2(a.x, b.x), add2(a.y, b.y), add2(a.z, b.z), add2(a.w, b.w));
+    }
+    static __device__ __forceinline__ uint4 scale_vec(const uint4& a, float s) {
+        const __half2 m = __float2half2_rn(s);
+        uint4 o;
+        const __half2* pa = reinterpret_cast<const __half2*>(&a);
+        __half2* po = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) po[i] = __hmul2(pa[i], m);
+        return o;
+    }
     static __device__ __forceinline__ void prod2(uint32_t a, uint32_t b, float& lo, float& hi) {
         float2 fa = __half22float2(*reinterpret_cast<__half2*>(&a));
         float2 fb = __half22float2(*reinterpret_cast<__half2*>(&b));
@@ -110,6 +145,14 @@ template <> struct Num<FF_F32> {
     }
     static __device__ __forceinline__ uint4 pack(const float* f) {
         return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+    }
+    static __device__ __forceinline__ uint32_t addf(uint32_t a, uint32_t b) { return __float_as_uint(__fadd_rn(__uint_as_float(a), __uint_as_float(b))); }
+    static __device__ __forceinline__ uint4 add_vec(const uint4& a, const uint4& b) {
+        return make_uint4(addf(a.x, b.x), addf(a.y, b.y), addf(a.z, b.z), addf(a.w, b.w));
+    }
+    static __device__ __forceinline__ uint4 scale_vec(const uint4& a, float s) {
+        return make_uint4(__float_as_uint(__uint_as_float(a.x) * s), __float_as_uint(__uint_as_float(a.y) * s),
+                          __float_as_uint(__uint_as_float(a.z) * s), __float_as_uint(__uint_as_float(a.w) * s));
     }
 };
 
@@ -189,29 +232,36 @@ __device__ __forceinline__ float finish_cosine(float dot, float na, float nb) {
 }
 
 // T(x / div) elementwise, div = T(L + 1) (main.py:314-317: one true division, rounded to T).
-// bf16 fast path: a power-of-two divisor is an exact scaling; otherwise q0 = x * RN(1/div) is within 2 float32 ulp
-// of the correctly rounded quotient, so both round to the same bf16 unless q0 sits within a few ulp of a bf16
-// rounding boundary (low 16 bits ~ 0x8000) — those elements (about 1e-4 of them) take the IEEE division.
+//  * a power-of-two run (2, 4, 8 ... rows: most runs) is an exact scaling, done on the packed vector;
+//  * bf16, any run up to 256 rows: T(x * RN(1/div)) equals T(x / div) for EVERY finite bf16 x (checked exhaustively,
+//    65 280 values x 256 divisors; a bf16 quotient by a small integer is never within float32 error of a rounding
+//    boundary of T), so the reciprocal multiply is exact and nothing needs the IEEE division;
+//  * everything else (f16 / f32 with other divisors — f16 does have exceptions in its subnormals —, longer runs) divides.
 __device__ __noinline__ float ieee_div(float x, float d) { return x / d; }
 
 template <int DT>
 struct Divider {
     float div, rcp;
-    bool pow2;
+    bool pow2, by_rcp;
     __device__ __forceinline__ explicit Divider(int n) {
         div = Num<DT>::rnd((float)n);
         rcp = 1.0f / div;
-        pow2 = (n & (n - 1)) == 0;
+        pow2 = (n & (n - 1)) == 0 && n <= 256;             // 2^-k is then a normal number in every T
+        by_rcp = pow2 || (DT == FF_BF16 && n <= 256);
     }
-    __device__ __forceinline__ float one(float x) const {
-        if (DT != FF_BF16) return x / div;
-        const float q0 = x * rcp;
-        if (pow2) return q0;
-        const uint32_t u = __float_as_uint(q0);
-        const bool risky = ((u & 0xffffu) - 0x7ff8u) <= 0x10u || ((u & 0x7f800000u) == 0u && (u << 1) != 0u);
-        return risky ? ieee_div(x, div) : q0;
+    __device__ __forceinline__ float one(float x) const { return by_rcp ? x * rcp : ieee_div(x, div); }
+    __device__ __forceinline__ uint4 vec_fast(const uint4& a) const {
+        if (pow2) return Num<DT>::scale_vec(a, rcp);
+        if (DT == FF_BF16 && by_rcp) {
+            float x[Num<DT>::EPV];
+            Num<DT>::unpack(a, x);
+#pragma unroll
+            for (int e = 0; e < Num<DT>::EPV; ++e) x[e] *= rcp;
+            return Num<DT>::pack(x);
+        }
+        return vec(a);
     }
-    __device__ __noinline__ uint4 vec(const uint4 a) const {      // out of line: called once per vector, rarely hot
+    __device__ __noinline__ uint4 vec(const uint4 a) const {      // out of line: rare
         float x[Num<DT>::EPV];
         Num<DT>::unpack(a, x);
 #pragma unroll

@@ -110,54 +110,131 @@ struct AuxPack {
     int n;
 };
 
-// ---- the same, tuned for the two-pass path at full size.  One warp per DESTINATION row, last rows first: the
-// similarity pass has just streamed the sequence front to back, so its tail is what the L2 still holds.
-// srcidx[d] and desc[d] = (by-patch position, run length) come from the scan kernel, so a row needs one dependent
-// load before its data is requested and no warp is launched for a row that was merged away.  Thin warps, full
-// occupancy: four 16-byte vectors per lane in flight per step; an anchor requests the same four vectors of every
-// run member together (main.py:304-311 order of the adds), i.e. one memory round trip per step instead of one per
-// vector and member.  The aux rows (cos, sin, patch_type, position ids) ride along.
+// ---- the same, tuned for the two-pass path at full size.  One warp per KEPT row, driven by the 16-byte records the
+// scan kernel leaves: (source row, destination row, by-patch position, run length) for the rows of the chains in
+// by-patch order from the front of rec[], for the rows outside the chains from its end (merge stage); srcidx[d] in the
+// prune stage.  A warp requests its record before anything else, so the row data is one dependent load away and no
+// warp is launched for a row that was merged away.  Thin warps: eight 16-byte vectors per lane in flight for a copied
+// row; an anchor requests the same four vectors of the anchor and of the next run member together (main.py:304-311
+// order of the adds).  The aux rows (cos, sin, patch_type, position ids) are copied by warps of their own (odd
+// blocks) with every load of a row in flight at once, so their latency never sits behind a hidden_states row.
 constexpr int GATHER_WARPS = 4;                  // small blocks: a slow anchor warp holds up only three others
+constexpr int AUX_SLOTS = 8;                     // (tensor, plane) pairs an aux warp keeps in flight
 
+__device__ __noinline__ void gather_aux_rows(const AuxPack& aux, int i, int d, int lane) {
+    // fast path: every (tensor, plane) row is at most 32 pieces of 16 or 8 bytes -> one piece per lane, all loads first
+    uint4 buf[AUX_SLOTS];
+    int k = 0;
+    bool fast = true;
+#pragma unroll 1
+    for (int q = 0; q < aux.n; ++q) {
+        const ff_aux& x = aux.a[q];
+        const int64_t al = x.row_bytes | (int64_t)(uintptr_t)x.src | (int64_t)(uintptr_t)x.dst | x.src_plane_stride | x.dst_plane_stride;
+        const int piece = (al & 15) == 0 ? 16 : ((al & 7) == 0 ? 8 : 0);
+        if (piece == 0 || x.row_bytes > 32 * piece) fast = false;
+        k += (int)x.planes;
+    }
+    if (fast && k <= AUX_SLOTS) {
+        k = 0;
+#pragma unroll 1
+        for (int q = 0; q < aux.n; ++q) {
+            const ff_aux& x = aux.a[q];
+            const bool wide = (x.row_bytes & 15) == 0;      // alignment of the bases was checked above
+            for (int64_t pl = 0; pl < x.planes; ++pl, ++k) {
+                const char* s = (const char*)x.src + pl * x.src_plane_stride + (int64_t)i * x.row_bytes;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (wide) {
+                    if (lane * 16 < x.row_bytes) v = __ldg(reinterpret_cast<const uint4*>(s) + lane);
+                } else if (lane * 8 < x.row_bytes) {
+                    const uint2 t = __ldg(reinterpret_cast<const uint2*>(s) + lane);
+                    v.x = t.x; v.y = t.y;
+                }
+#pragma unroll
+                for (int e = 0; e < AUX_SLOTS; ++e)
+                    if (e == k) buf[e] = v;                 // static register indexing
+            }
+        }
+        k = 0;
+#pragma unroll 1
+        for (int q = 0; q < aux.n; ++q) {
+            const ff_aux& x = aux.a[q];
+            const bool wide = (x.row_bytes & 15) == 0;
+            for (int64_t pl = 0; pl < x.planes; ++pl, ++k) {
+                char* o = (char*)x.dst + pl * x.dst_plane_stride + (int64_t)d * x.row_bytes;
+                uint4 v = buf[0];
+#pragma unroll
+                for (int e = 1; e < AUX_SLOTS; ++e)
+                    if (e == k) v = buf[e];
+                if (wide) {
+                    if (lane * 16 < x.row_bytes) reinterpret_cast<uint4*>(o)[lane] = v;
+                } else if (lane * 8 < x.row_bytes) {
+                    reinterpret_cast<uint2*>(o)[lane] = make_uint2(v.x, v.y);
+                }
+            }
+        }
+        return;
+    }
+#pragma unroll 1
+    for (int q = 0; q < aux.n; ++q) {                       // any shape
+        const ff_aux& x = aux.a[q];
+        for (int64_t pl = 0; pl < x.planes; ++pl) {
+            const char* s = (const char*)x.src + pl * x.src_plane_stride + (int64_t)i * x.row_bytes;
+            char* o = (char*)x.dst + pl * x.dst_plane_stride + (int64_t)d * x.row_bytes;
+            if (((x.row_bytes | (int64_t)(uintptr_t)s | (int64_t)(uintptr_t)o) & 15) == 0) {
+                for (int64_t v = lane; v < x.row_bytes / 16; v += 32)
+                    reinterpret_cast<uint4*>(o)[v] = __ldg(reinterpret_cast<const uint4*>(s) + v);
+            } else if (((x.row_bytes | (int64_t)(uintptr_t)s | (int64_t)(uintptr_t)o) & 7) == 0) {
+                for (int64_t v = lane; v < x.row_bytes / 8; v += 32)
+                    reinterpret_cast<uint2*>(o)[v] = __ldg(reinterpret_cast<const uint2*>(s) + v);
+            } else {
+                for (int64_t v = lane; v < x.row_bytes; v += 32) o[v] = s[v];
+            }
+        }
+    }
+}
+
+// One record -> (source row, destination row, by-patch position, run length); false when unit u is past the kept rows.
+// The record is requested before the counters it is checked against: one dependent load less before the row data.
+__device__ __forceinline__ bool gather_unit(int u, int S, const int* __restrict__ srcidx, const int4* __restrict__ rec,
+                                            const int64_t* __restrict__ counters, const int64_t* __restrict__ counters_next,
+                                            int4* out) {
+    if (u >= S) return false;
+    int4 r = rec ? __ldg(rec + u) : make_int4(__ldg(srcidx + u), u, -1, 0);
+    if (u >= (int)counters[C_SKEEP]) return false;
+    if (rec) {
+        const int n_chain = (int)counters_next[C_N];
+        if (u >= n_chain) r = __ldg(rec + (S - 1 - (u - n_chain)));
+    }
+    *out = r;
+    return true;
+}
+
+// grid: 5 * ceil(ceil(S / GATHER_WARPS) / 4) blocks when there are aux tensors — every fifth block copies the aux rows
+// of the sixteen units of its four neighbours, four rows per warp — else ceil(S / GATHER_WARPS)
 template <int DT>
 __global__ void __launch_bounds__(GATHER_WARPS * 32, 32 / GATHER_WARPS)
-k_merge_gather(const void* __restrict__ hidden, void* __restrict__ out, int nvec, const int* __restrict__ srcidx,
+k_merge_gather(const void* __restrict__ hidden, void* __restrict__ out, int nvec, int S, const int* __restrict__ srcidx,
                const int4* __restrict__ rec, const int* __restrict__ order, const uint8_t* __restrict__ flag,
-               const int64_t* __restrict__ counters, const int* __restrict__ rank_of_dst,
-               const int64_t* __restrict__ counters_next, const __grid_constant__ AuxPack aux) {
+               const int64_t* __restrict__ counters, const int64_t* __restrict__ counters_next,
+               const __grid_constant__ AuxPack aux) {
     pdl_enter();
-    const int lane = threadIdx.x & 31;
-    const int w = blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
-    const int s_keep = (int)counters[C_SKEEP];
-    int d, i;
-    int2 ds = make_int2(-1, 0);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (rec && counters[C_NMERGED] == 0) return;            // nothing merged: the host hands the input tensors back
-    if (rec) {
-        // merge stage: chain rows in by-patch order, last patch ids first (the similarity pass has just walked the
-        // chains in that order), one 16-byte record per row from the scan kernel; the rows outside the chains
-        // (text) are picked up by the blocks behind those
-        const int n_chain = (int)counters_next[C_N];
-        const int n_blocks_chain = (n_chain + GATHER_WARPS - 1) / GATHER_WARPS;
-        if ((int)blockIdx.x < n_blocks_chain) {
-            const int ex = n_chain - 1 - w;
-            if (ex < 0) return;
-            const int4 r = __ldg(rec + ex);
-            i = r.x; d = r.y; ds = make_int2(r.z, r.w);
-        } else {
-            d = w - n_blocks_chain * GATHER_WARPS;
-            if (d >= s_keep || rank_of_dst[d] >= 0) return;
-            i = srcidx[d];
-        }
-    } else {
-        d = s_keep - 1 - w;                                 // prune stage: destination rows, last first
-        if (d < 0) return;
-        i = srcidx[d];
+    int4 r;
+    if (aux.n > 0 && blockIdx.x % 5 == 4) {
+        const int u0 = ((int)blockIdx.x / 5) * (4 * GATHER_WARPS) + wid * 4;
+#pragma unroll 1
+        for (int e = 0; e < 4; ++e)
+            if (gather_unit(u0 + e, S, srcidx, rec, counters, counters_next, &r)) gather_aux_rows(aux, r.x, r.y, lane);
+        return;
     }
+    const int mb = aux.n > 0 ? (int)blockIdx.x - (int)blockIdx.x / 5 : (int)blockIdx.x;
+    if (!gather_unit(mb * GATHER_WARPS + wid, S, srcidx, rec, counters, counters_next, &r)) return;
+    const int i = r.x, d = r.y, j = r.z, L = r.w;
     const int64_t row_bytes = (int64_t)nvec * 16;
     const char* src = (const char*)hidden + (int64_t)i * row_bytes;
     char* orow = (char*)out + (int64_t)d * row_bytes;
-    const int j = ds.x;
-    int L = ds.y, wrapL = 0;
+    int wrapL = 0;
     if (j >= 0) {
         const int N = (int)counters[C_N];
         if (j == N - 1 && N > 1 && flag[0]) wrapL = run_after(flag, -1, N - 1);       // main.py:290 wrap-around
@@ -194,35 +271,11 @@ k_merge_gather(const void* __restrict__ hidden, void* __restrict__ out, int nvec
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                    if (v0 + 32 * q < nvec) {
-                        float a[Num<DT>::EPV], b[Num<DT>::EPV];
-                        Num<DT>::unpack(acc[q], a);
-                        Num<DT>::unpack(x[q], b);
-#pragma unroll
-                        for (int e = 0; e < Num<DT>::EPV; ++e) a[e] = a[e] + b[e];
-                        acc[q] = Num<DT>::pack(a);
-                    }
+                    if (v0 + 32 * q < nvec) acc[q] = Num<DT>::add_vec(acc[q], x[q]);      // T(acc + member), main.py:304
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (v0 + 32 * q < nvec) st_stream16(orow + (int64_t)(v0 + 32 * q) * 16, dv.vec(acc[q]));
-        }
-    }
-#pragma unroll 1
-    for (int q = 0; q < aux.n; ++q) {
-        const ff_aux& x = aux.a[q];
-        for (int64_t pl = 0; pl < x.planes; ++pl) {
-            const char* s = (const char*)x.src + pl * x.src_plane_stride + (int64_t)i * x.row_bytes;
-            char* o = (char*)x.dst + pl * x.dst_plane_stride + (int64_t)d * x.row_bytes;
-            if (((x.row_bytes | (int64_t)(uintptr_t)s | (int64_t)(uintptr_t)o) & 15) == 0) {
-                for (int64_t v = lane; v < x.row_bytes / 16; v += 32)
-                    reinterpret_cast<uint4*>(o)[v] = __ldg(reinterpret_cast<const uint4*>(s) + v);
-            } else if (((x.row_bytes | (int64_t)(uintptr_t)s | (int64_t)(uintptr_t)o) & 7) == 0) {
-                for (int64_t v = lane; v < x.row_bytes / 8; v += 32)
-                    reinterpret_cast<uint2*>(o)[v] = __ldg(reinterpret_cast<const uint2*>(s) + v);
-            } else {
-                for (int64_t v = lane; v < x.row_bytes; v += 32) o[v] = s[v];
-            }
+                if (v0 + 32 * q < nvec) st_stream16(orow + (int64_t)(v0 + 32 * q) * 16, dv.vec_fast(acc[q]));
         }
     }
 }

@@ -102,6 +102,13 @@ struct DecideArgs {
     int topk_only;              // 1 = k_keep_scan handles the threshold branch: return at once unless the count says top-k
 };
 
+// a kept row outside the chains (text): its record goes to the END of rec[], growing downwards, in no particular order
+// (the gather treats every record independently); the rows of the chains fill rec[] from the front in by-patch order
+__device__ __forceinline__ void text_record(const DecideArgs& a, int src_row, int dst_row) {
+    const int slot = (int)atomicAdd((unsigned long long*)&a.counters[C_TICKET2], 1ull);
+    a.rec[a.S - 1 - slot] = make_int4(src_row, dst_row, -1, 0);
+}
+
 __global__ void __launch_bounds__(SEL_THREADS)
 k_decide_scan(DecideArgs a) {
     pdl_enter();
@@ -162,7 +169,10 @@ k_decide_scan(DecideArgs a) {
                 if (keep[e]) {
                     a.dst[i0 + e] = ex;
                     a.srcidx[ex] = i0 + e;
-                    if (r[e] < 0) a.rank_next[ex] = -1;
+                    if (r[e] < 0) {
+                        a.rank_next[ex] = -1;
+                        text_record(a, i0 + e, ex);
+                    }
                     ++ex;
                 } else {
                     a.dst[i0 + e] = -1;
@@ -307,7 +317,10 @@ k_keep_scan(ScanArgs a) {
             if (keep) {
                 d.dst[i] = ex;
                 d.srcidx[ex] = i;
-                if (r < 0) d.rank_next[ex] = -1;
+                if (r < 0) {
+                    d.rank_next[ex] = -1;
+                    text_record(d, i, ex);
+                }
             } else {
                 d.dst[i] = -1;
             }

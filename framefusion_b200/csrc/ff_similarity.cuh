@@ -19,6 +19,7 @@ k_similarity(const void* __restrict__ hidden, int H, const int* __restrict__ ord
     const int N = (int)counters_in[C_N];
     const int j = blockIdx.x * 8 + wid;
     int hit = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[C_TICKET2] = 0;   // slot counter of the scan kernels' records
     if (j < N) {
         float s = -2.0f;                                   // IGNORE_TOKEN at chain heads (main.py:225-238)
         if (j > 0 && chain[j] == chain[j - 1]) {
