@@ -250,15 +250,17 @@ struct Divider {
         by_rcp = pow2 || (DT == FF_BF16 && n <= 256);
     }
     __device__ __forceinline__ float one(float x) const { return by_rcp ? x * rcp : ieee_div(x, div); }
+    // by_rcp only: x * rcp in float32, rounded to T
+    __device__ __forceinline__ uint4 vec_rcp(const uint4& a) const {
+        float x[Num<DT>::EPV];
+        Num<DT>::unpack(a, x);
+#pragma unroll
+        for (int e = 0; e < Num<DT>::EPV; ++e) x[e] *= rcp;
+        return Num<DT>::pack(x);
+    }
     __device__ __forceinline__ uint4 vec_fast(const uint4& a) const {
         if (pow2) return Num<DT>::scale_vec(a, rcp);
-        if (DT == FF_BF16 && by_rcp) {
-            float x[Num<DT>::EPV];
-            Num<DT>::unpack(a, x);
-#pragma unroll
-            for (int e = 0; e < Num<DT>::EPV; ++e) x[e] *= rcp;
-            return Num<DT>::pack(x);
-        }
+        if (by_rcp) return vec_rcp(a);
         return vec(a);
     }
     __device__ __noinline__ uint4 vec(const uint4 a) const {      // out of line: rare

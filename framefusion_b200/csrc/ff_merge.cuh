@@ -193,6 +193,12 @@ __device__ __noinline__ void gather_aux_rows(const AuxPack& aux, int i, int d, i
     }
 }
 
+template <int DT>
+__device__ __noinline__ void gather_anchor_ieee(const void* hidden, void* out_row, const char* src_row, int nvec, int lane,
+                                                const int* __restrict__ order, int j, int L, int wrapL) {
+    merge_row<DT, true, false>(hidden, out_row, src_row, nvec * Num<DT>::EPV, lane, order, j, L, wrapL);
+}
+
 // One record -> (source row, destination row, by-patch position, run length); false when unit u is past the kept rows.
 // The record is requested before the counters it is checked against: one dependent load less before the row data.
 __device__ __forceinline__ bool gather_unit(int u, int S, const int* __restrict__ srcidx, const int4* __restrict__ rec,
@@ -251,6 +257,10 @@ k_merge_gather(const void* __restrict__ hidden, void* __restrict__ out, int nvec
         }
     } else {
         const Divider<DT> dv(L + wrapL + 1);
+        if (!dv.by_rcp) {                                   // needs the IEEE division: the generic row routine, out of line
+            gather_anchor_ieee<DT>(hidden, orow, src, nvec, lane, order, j, L, wrapL);
+            return;
+        }
         // the first member's row is addressed once, outside the loop: runs of one merged token are the common case
         const char* mr0 = (const char*)hidden + (int64_t)order[L > 0 ? j + 1 : 0] * row_bytes;
         for (int v0 = lane; v0 < nvec; v0 += 128) {
@@ -273,9 +283,15 @@ k_merge_gather(const void* __restrict__ hidden, void* __restrict__ out, int nvec
                 for (int q = 0; q < 4; ++q)
                     if (v0 + 32 * q < nvec) acc[q] = Num<DT>::add_vec(acc[q], x[q]);      // T(acc + member), main.py:304
             }
+            if (dv.pow2) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (v0 + 32 * q < nvec) st_stream16(orow + (int64_t)(v0 + 32 * q) * 16, dv.vec_fast(acc[q]));
+                for (int q = 0; q < 4; ++q)
+                    if (v0 + 32 * q < nvec) st_stream16(orow + (int64_t)(v0 + 32 * q) * 16, Num<DT>::scale_vec(acc[q], dv.rcp));
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (v0 + 32 * q < nvec) st_stream16(orow + (int64_t)(v0 + 32 * q) * 16, dv.vec_rcp(acc[q]));
+            }
         }
     }
 }
