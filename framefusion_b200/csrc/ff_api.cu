@@ -618,9 +618,8 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     a.rank_next = w.rank[nb];
     a.counters_next = w.counters[nb];
     a.force_branch = -1;
-    a.topk_only = 0;
     if (S >= 2 * SEL_THREADS) {
-        // threshold branch on a grid of co-resident blocks; k_decide_scan then only runs for the top-k branch
+        // a grid of co-resident blocks for the threshold branch; its block 0 handles the top-k branch alone
         ScanArgs sa;
         sa.d = a;
         sa.part = w.part;
@@ -636,9 +635,9 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
         sa.bar_base = ctx->bar_base;
         ctx->bar_base += 2u * (unsigned)G;                 // every block adds 2, on either branch
         FF_LAUNCH("k_keep_scan", k_keep_scan, G, SEL_THREADS, 0, st, sa);
-        a.topk_only = 1;
+    } else {
+        FF_LAUNCH("k_decide_scan", k_decide_scan, 1, SEL_THREADS, 0, st, a);
     }
-    FF_LAUNCH("k_decide_scan", k_decide_scan, 1, SEL_THREADS, 0, st, a);
     if (int rc = launch_merge_gather(ctx, w, bank, hidden, hidden_out, dtype, S, H, ap, st)) return rc;
     ctx->last_parity = bank;
     ctx->parity = nb;

@@ -99,7 +99,6 @@ struct DecideArgs {
     int* rank_next;
     int64_t* counters_next;     // counter bank of the next call: N, n_vis carried over, count reset
     int force_branch;           // -1 = decide from count (main.py:116); 0/1 = flags are given (static API)
-    int topk_only;              // 1 = k_keep_scan handles the threshold branch: return at once unless the count says top-k
 };
 
 // a kept row outside the chains (text): its record goes to the END of rec[], growing downwards, in no particular order
@@ -109,9 +108,8 @@ __device__ __forceinline__ void text_record(const DecideArgs& a, int src_row, in
     a.rec[a.S - 1 - slot] = make_int4(src_row, dst_row, -1, 0);
 }
 
-__global__ void __launch_bounds__(SEL_THREADS)
-k_decide_scan(DecideArgs a) {
-    pdl_enter();
+// the whole selection + scan by ONE block of SEL_THREADS threads (short sequences, the top-k branch, the static API)
+__device__ __forceinline__ void decide_scan_block(const DecideArgs& a) {
     __shared__ int s_hist[256];
     __shared__ int s_scan[33];
     __shared__ uint32_t s_misc[4];
@@ -120,7 +118,6 @@ k_decide_scan(DecideArgs a) {
     const int t = threadIdx.x;
     const int N = (int)a.counters[C_N];
     const int S = a.S;
-    if (a.topk_only && a.counters[C_NVIS] != 0 && (double)a.counters[C_COUNT] / (double)a.counters[C_NVIS] < a.bound) return;
 
     if (t == 0) {
         const long long count = a.counters[C_COUNT], n_vis = a.counters[C_NVIS];
@@ -236,11 +233,17 @@ k_decide_scan(DecideArgs a) {
     }
 }
 
+__global__ void __launch_bounds__(SEL_THREADS)
+k_decide_scan(DecideArgs a) {
+    pdl_enter();
+    decide_scan_block(a);
+}
+
 // ---- threshold branch, many blocks: the same outputs as k_decide_scan (destination rows in sequence order, the
 // by-patch arrays of the next call, counters, status) from a grid of G co-resident blocks (G <= SM count) in three
 // phases separated by grid barriers.  One 1024-thread block needs ~100 us for 37 k tokens (latency bound); spread
-// over 74 blocks it is a few microseconds.  If the count says top-k (main.py:121-127) every block returns at once
-// and k_decide_scan — launched right after — does the whole job; if it says threshold, k_decide_scan returns at once.
+// over 74 blocks it is a few microseconds.  If the count says top-k (main.py:121-127) block 0 runs the single-block
+// routine and the others return at once.
 struct ScanArgs {
     DecideArgs d;
     int* part;                   // [2 * gridDim.x] kept rows per block (sequence order, by-patch order)
@@ -283,6 +286,7 @@ k_keep_scan(ScanArgs a) {
     const int t = threadIdx.x, G = gridDim.x, b = blockIdx.x;
     if (!threshold_branch(d.counters, d.bound)) {
         if (t == 0) atomicAdd(a.barrier, 2u);              // keep the barrier word in step with the host's count
+        if (b == 0) decide_scan_block(d);                  // top-k branch (rare: at most once per prefill): one block does it all
         return;
     }
     const int N = (int)d.counters[C_N], S = d.S;
