@@ -334,6 +334,8 @@ k_keep_scan(ScanArgs a) {
     grid_barrier(a.barrier, a.bar_base + (unsigned)(2 * G));
 
     // ---- phase 3: the by-patch arrays of the next call
+    // records go in last-to-first: the gather then starts with the rows the similarity pass read last (still in the L2)
+    const int n_all = block_sum_prefix(a.part + G, G, s_scan);
     carry = block_sum_prefix(a.part + G, b, s_scan);
     for (int base = n0; base < n1; base += SEL_THREADS) {
         const int j = base + t;
@@ -346,7 +348,7 @@ k_keep_scan(ScanArgs a) {
             d.rank_next[dd] = ex;
             int L = 0;
             while (j + 1 + L < N && d.flag[j + 1 + L]) ++L;
-            d.rec[ex] = make_int4(d.order[j], dd, j, L);
+            d.rec[n_all - 1 - ex] = make_int4(d.order[j], dd, j, L);
         }
         carry += tot;
     }
