@@ -82,7 +82,9 @@ k_importance_logits(const void* __restrict__ q, const void* __restrict__ k, int 
     }
 }
 
-// one block per (head, query) row
+// one block per (head, query) row; the row lives in registers between the three passes when it fits
+constexpr int SOFTMAX_CACHE = 40;                         // values per thread: rows up to 40 960 keys
+
 template <int DT>
 __global__ void __launch_bounds__(1024)
 k_softmax_rows(const float* __restrict__ logits, int S, void* __restrict__ probs) {
@@ -91,8 +93,20 @@ k_softmax_rows(const float* __restrict__ logits, int S, void* __restrict__ probs
     __shared__ float s_val;
     const float* x = logits + (int64_t)blockIdx.x * S;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const bool cached = S <= SOFTMAX_CACHE * (int)blockDim.x;
+    float c[SOFTMAX_CACHE];
     float m = -INFINITY;
-    for (int s = threadIdx.x; s < S; s += blockDim.x) m = fmaxf(m, x[s]);
+    if (cached) {
+#pragma unroll
+        for (int i = 0; i < SOFTMAX_CACHE; ++i) {
+            const int s = threadIdx.x + i * blockDim.x;
+            c[i] = s < S ? __ldg(x + s) : -INFINITY;
+        }
+#pragma unroll
+        for (int i = 0; i < SOFTMAX_CACHE; ++i) m = fmaxf(m, c[i]);
+    } else {
+        for (int s = threadIdx.x; s < S; s += blockDim.x) m = fmaxf(m, x[s]);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
     if (lane == 0) s_red[wid] = m;
@@ -106,7 +120,19 @@ k_softmax_rows(const float* __restrict__ logits, int S, void* __restrict__ probs
     __syncthreads();
     m = s_val;
     float sum = 0.f;
-    for (int s = threadIdx.x; s < S; s += blockDim.x) sum += expf(x[s] - m);
+    if (cached) {
+        // the same per-thread order of the additions as the loop below: s = tid, tid + blockDim, ...
+#pragma unroll
+        for (int i = 0; i < SOFTMAX_CACHE; ++i) {
+            const int s = threadIdx.x + i * blockDim.x;
+            if (s < S) {
+                c[i] = expf(c[i] - m);
+                sum += c[i];
+            }
+        }
+    } else {
+        for (int s = threadIdx.x; s < S; s += blockDim.x) sum += expf(x[s] - m);
+    }
     sum = warp_sum(sum);
     __syncthreads();
     if (lane == 0) s_red[wid] = sum;
@@ -118,8 +144,16 @@ k_softmax_rows(const float* __restrict__ logits, int S, void* __restrict__ probs
     }
     __syncthreads();
     sum = s_val;
-    for (int s = threadIdx.x; s < S; s += blockDim.x)
-        Num<DT>::store(probs, (int64_t)blockIdx.x * S + s, expf(x[s] - m) / sum);
+    if (cached) {
+#pragma unroll
+        for (int i = 0; i < SOFTMAX_CACHE; ++i) {
+            const int s = threadIdx.x + i * blockDim.x;
+            if (s < S) Num<DT>::store(probs, (int64_t)blockIdx.x * S + s, c[i] / sum);
+        }
+    } else {
+        for (int s = threadIdx.x; s < S; s += blockDim.x)
+            Num<DT>::store(probs, (int64_t)blockIdx.x * S + s, expf(x[s] - m) / sum);
+    }
 }
 
 }  // namespace ff
