@@ -281,7 +281,6 @@ __global__ void __launch_bounds__(SEL_THREADS)
 k_keep_scan(ScanArgs a) {
     pdl_enter();
     __shared__ int s_scan[33];
-    __shared__ int s_base;
     const DecideArgs& d = a.d;
     const int t = threadIdx.x, G = gridDim.x, b = blockIdx.x;
     if (!threshold_branch(d.counters, d.bound)) {
@@ -296,13 +295,25 @@ k_keep_scan(ScanArgs a) {
     const int s0 = min(b * per_s, S), s1 = min(s0 + per_s, S);
     const int n0 = min(b * per_n, N), n1 = min(n0 + per_n, N);
 
-    // ---- phase 1: kept rows of the block, in both orders
-    int c_seq = 0, c_bp = 0;
-    for (int i = s0 + t; i < s1; i += SEL_THREADS) {
+    // ---- phase 1: kept rows of the block, in both orders.  The first tile of each range (usually the only one) stays in
+    // registers for the later phases, and what phase 3 needs of it that no phase produces — source row, chain id, run
+    // length — is fetched here, ahead of both barriers.
+    const int i0 = s0 + t, j0 = n0 + t;
+    const int r0 = i0 < s1 ? d.rank[i0] : -1;
+    const int keep_s0 = i0 < s1 && !(r0 >= 0 && d.flag[r0]);
+    const int keep_n0 = j0 < n1 && !d.flag[j0];
+    int oj0 = 0, cj0 = 0, L0 = 0;
+    if (keep_n0) {
+        oj0 = d.order[j0];
+        cj0 = d.chain[j0];
+        while (j0 + 1 + L0 < N && d.flag[j0 + 1 + L0]) ++L0;
+    }
+    int c_seq = keep_s0, c_bp = keep_n0;
+    for (int i = i0 + SEL_THREADS; i < s1; i += SEL_THREADS) {
         const int r = d.rank[i];
         c_seq += !(r >= 0 && d.flag[r]);
     }
-    for (int j = n0 + t; j < n1; j += SEL_THREADS) c_bp += !d.flag[j];
+    for (int j = j0 + SEL_THREADS; j < n1; j += SEL_THREADS) c_bp += !d.flag[j];
     int tot;
     block_exclusive_scan(c_seq, s_scan, &tot);
     if (t == 0) a.part[b] = tot;
@@ -310,12 +321,18 @@ k_keep_scan(ScanArgs a) {
     if (t == 0) a.part[G + b] = tot;
     grid_barrier(a.barrier, a.bar_base + (unsigned)G);
 
-    // ---- phase 2: destination rows in sequence order
+    // every block count is known now: the three prefix sums of the block, and the totals
     int carry = block_sum_prefix(a.part, b, s_scan);
+    int carry_n = block_sum_prefix(a.part + G, b, s_scan);
+    const int n_next = block_sum_prefix(a.part + G, G, s_scan);
+    const int s_keep = b == G - 1 ? block_sum_prefix(a.part, G, s_scan) : 0;
+
+    // ---- phase 2: destination rows in sequence order
     for (int base = s0; base < s1; base += SEL_THREADS) {
         const int i = base + t;
-        const int r = i < s1 ? d.rank[i] : -1;
-        const int keep = i < s1 && !(r >= 0 && d.flag[r]);
+        const bool first = base == s0;
+        const int r = first ? r0 : (i < s1 ? d.rank[i] : -1);
+        const int keep = first ? keep_s0 : (i < s1 && !(r >= 0 && d.flag[r]));
         const int ex = carry + block_exclusive_scan(keep, s_scan, &tot);
         if (i < s1) {
             if (keep) {
@@ -333,27 +350,29 @@ k_keep_scan(ScanArgs a) {
     }
     grid_barrier(a.barrier, a.bar_base + (unsigned)(2 * G));
 
-    // ---- phase 3: the by-patch arrays of the next call
-    // records go in last-to-first: the gather then starts with the rows the similarity pass read last (still in the L2)
-    const int n_all = block_sum_prefix(a.part + G, G, s_scan);
-    carry = block_sum_prefix(a.part + G, b, s_scan);
+    // ---- phase 3: the by-patch arrays of the next call and the gather's records.  The records go in last-to-first: the
+    // gather then starts with the rows the similarity pass read last (still in the L2).
     for (int base = n0; base < n1; base += SEL_THREADS) {
         const int j = base + t;
-        const int keep = j < n1 && !d.flag[j];
-        const int ex = carry + block_exclusive_scan(keep, s_scan, &tot);
+        const bool first = base == n0;
+        const int keep = first ? keep_n0 : (j < n1 && !d.flag[j]);
+        const int ex = carry_n + block_exclusive_scan(keep, s_scan, &tot);
         if (keep) {
-            const int dd = __ldcg(&d.dst[d.order[j]]);
+            int oj = oj0, cj = cj0, L = L0;
+            if (!first) {
+                oj = d.order[j];
+                cj = d.chain[j];
+                L = 0;
+                while (j + 1 + L < N && d.flag[j + 1 + L]) ++L;
+            }
+            const int dd = __ldcg(&d.dst[oj]);
             d.order_next[ex] = dd;
-            d.chain_next[ex] = d.chain[j];
+            d.chain_next[ex] = cj;
             d.rank_next[dd] = ex;
-            int L = 0;
-            while (j + 1 + L < N && d.flag[j + 1 + L]) ++L;
-            d.rec[n_all - 1 - ex] = make_int4(d.order[j], dd, j, L);
+            d.rec[n_next - 1 - ex] = make_int4(oj, dd, j, L);
         }
-        carry += tot;
+        carry_n += tot;
     }
-    const int s_keep = b == G - 1 ? block_sum_prefix(a.part, G, s_scan) : 0;
-    const int n_next = b == G - 1 ? block_sum_prefix(a.part + G, G, s_scan) : 0;
     if (b == G - 1 && t == 0) {
         d.counters[C_NNEXT] = n_next;
         d.counters[C_SKEEP] = s_keep;
