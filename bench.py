@@ -287,19 +287,48 @@ def main():
         return run_step(ff, wl, devt["hidden"], devt["cos"], devt["sin"], devt["q_last"], devt["keys"], imp)
 
     out_host = {}
+    # End to end: every step copies ITS inputs from pinned host memory and ITS result back, inside the timed region.
+    # The device inputs are double buffered: the copy of step i+1's inputs is issued on a second stream before step i
+    # computes, so it overlaps step i's kernels and device->host read (PCIe is full duplex) — what a server feeding a
+    # stream of videos does.  The first step of a run has nothing to hide behind and pays its copy in full.
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [devt, {n: torch.empty_like(t) for n, t in devt.items()}]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    for e in consumed:
+        e.record()
+    e2e_state = {"i": 0, "remaining": 0, "prefetched": False}
+
+    def issue_h2d(slot):
+        copy_stream.wait_event(consumed[slot])              # the step that last read this buffer set is done with it
+        with torch.cuda.stream(copy_stream):
+            for n in host:
+                slots[slot][n].copy_(host[n], non_blocking=True)
+            ready[slot].record(copy_stream)
 
     def step_e2e():
-        for n in host:
-            devt[n].copy_(host[n], non_blocking=True)
-        wl.patch_type = devt["patch_type"]
-        h, pos = step_resident()
+        st = e2e_state
+        slot = st["i"] & 1
+        if not st["prefetched"]:
+            issue_h2d(slot)
+        st["prefetched"] = st["remaining"] > 1
+        if st["prefetched"]:
+            issue_h2d(slot ^ 1)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ready[slot])
+        d = slots[slot]
+        wl.patch_type = d["patch_type"]
+        h, pos = run_step(ff, wl, d["hidden"], d["cos"], d["sin"], d["q_last"], d["keys"], imp)
         pt = ff.patch_type
         for n, t in (("hidden", h), ("patch_type", pt)):
             buf = out_host.get(n)
             if buf is None or buf.shape != t.shape:
                 buf = out_host[n] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
             buf.copy_(t, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        consumed[slot].record(cur)
+        cur.synchronize()
+        st["i"] += 1
+        st["remaining"] -= 1
         return h
 
     def barrier():
@@ -363,9 +392,13 @@ def main():
         single_ms = None
 
     e2e_steps = max(3, min(args.steps, 10))
+    e2e_state["remaining"] = 2
     for _ in range(2):
         step_e2e()
+    wl.patch_type = devt["patch_type"]
+    e2e_state["remaining"] = e2e_steps
     ms_e2e = timed(step_e2e, e2e_steps)
+    wl.patch_type = devt["patch_type"]
     h2d = sum(t.numel() * t.element_size() for t in host.values())
     d2h = sum(t.numel() * t.element_size() for t in out_host.values())
 
@@ -384,7 +417,8 @@ def main():
                      "kernel_us": k_ms * 1e3, "algorithmic_bytes": alg, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "e2e": {"value": whole_job_throughput(n_tok, e2e_steps, ms_e2e, world), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps},
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps,
+                "pipelining": "double-buffered device inputs: the host->device copy of step i+1 overlaps the kernels and the device->host read of step i"},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
     }
