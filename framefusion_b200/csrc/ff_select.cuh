@@ -1,9 +1,11 @@
 // Selection, run bookkeeping and compaction offsets — the integer part of a merge / prune call.
-// One 1024-thread block: these arrays are 1-8 bytes per token (tens of KB), the cost is latency, not
-// bytes, so a single block with 8 items per thread and no grid-wide synchronisation is the short path.
+// These arrays are 1-8 bytes per token (tens of KB): the cost is latency, not bytes.  Short sequences (< 2 048 rows)
+// take ONE 1024-thread block with 8 items per thread and no grid-wide synchronisation; long ones a grid of co-resident
+// blocks with two (merge) or seven (prune) grid barriers.
 //
-//   k_decide_scan   main.py:112-127 (branch), 269-301 (runs), 132 (keep mask) + links of the next call
-//   k_prune_scan    main.py:69-92
+//   k_decide_scan / k_keep_scan    main.py:112-127 (branch), 269-301 (runs), 132 (keep mask) + links of the next call
+//                                  + the records k_merge_gather is driven by
+//   k_prune_scan / k_prune_select  main.py:69-92
 #pragma once
 #include "ff_common.cuh"
 
