@@ -12,9 +12,10 @@ from framefusion_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def drive(frames, patches, hidden, lo, hi, fused, drift=0.0, cost=0.3, max_calls=6, per_patch_r=False):
+def drive(frames, patches, hidden, lo, hi, fused, drift=0.0, cost=0.3, max_calls=6, per_patch_r=False, n_pre=14, n_post=20):
     from framefusion_b200.main import FrameFusion
-    wl = synth.make_workload(frames, patches, hidden, torch.bfloat16, seed=9, r_lo=lo, r_hi=hi, per_patch_r=per_patch_r)
+    wl = synth.make_workload(frames, patches, hidden, torch.bfloat16, seed=9, r_lo=lo, r_hi=hi, per_patch_r=per_patch_r,
+                             n_pre=n_pre, n_post=n_post)
     assert wl.seq_len >= 2048
     ff = FrameFusion(cost, 0.6, 0.1)
     ff.use_fused = fused
@@ -69,3 +70,9 @@ def test_low_similarity_goes_straight_to_prune():
 def test_long_runs_at_scale():
     stages = drive(40, 64, 512, 0.3, 1.0, False, per_patch_r=True)
     assert stages[0] in ("threshold", "topk")
+
+
+def test_long_text_spans_around_the_video():
+    """Hundreds of rows outside the chains on both sides (a long prompt): their records come from the end of rec[]."""
+    stages = drive(24, 100, 512, 0.0, 1.0, False, drift=0.3, n_pre=700, n_post=1100)
+    assert stages[0] == "threshold" and stages[-1] == "prune"
