@@ -76,3 +76,68 @@ def test_long_text_spans_around_the_video():
     """Hundreds of rows outside the chains on both sides (a long prompt): their records come from the end of rec[]."""
     stages = drive(24, 100, 512, 0.0, 1.0, False, drift=0.3, n_pre=700, n_post=1100)
     assert stages[0] == "threshold" and stages[-1] == "prune"
+
+
+def ragged_case(seed=3, frames=36, patches=120, hidden=512, n_pre=9, n_post=15):
+    """Chains of uneven length with text rows between the frames: every frame drops ~10 % of its patches and is
+    followed by 0-3 text rows — nothing about the layout is regular."""
+    g = torch.Generator().manual_seed(seed)
+    pt, rows = [-1] * n_pre, [torch.randn(n_pre, hidden, generator=g)]
+    prev = {}
+    for f in range(frames):
+        present = torch.nonzero(torch.rand(patches, generator=g) < 0.9).flatten().tolist()
+        for p in present:
+            eps = torch.randn(hidden, generator=g)
+            if p in prev:
+                r = float(torch.rand((), generator=g))
+                x = r * prev[p] + (1 - r * r) ** 0.5 * eps
+            else:
+                x = eps
+            prev[p] = x
+            rows.append(x[None])
+            pt.append(p)
+        n_text = int(torch.randint(0, 4, (), generator=g))
+        if n_text:
+            rows.append(torch.randn(n_text, hidden, generator=g))
+            pt += [-1] * n_text
+    rows.append(torch.randn(n_post, hidden, generator=g))
+    pt += [-1] * n_post
+    h = torch.cat(rows).to(torch.bfloat16)[None]
+    S = h.shape[1]
+    cos = torch.randn(1, S, 128, generator=g).to(torch.bfloat16)
+    sin = torch.randn(1, S, 128, generator=g).to(torch.bfloat16)
+    pt = torch.tensor(pt, dtype=torch.int64)[None]
+    first, last = n_pre, S - n_post - 1
+    return h, cos, sin, pt, patches, (first, last, last - first + 1, S)
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["two_pass", "single_pass"])
+def test_ragged_chains_with_text_between_frames(fused):
+    from framefusion_b200.main import FrameFusion
+    h, cos, sin, pt, P, span = ragged_case()
+    assert h.shape[1] >= 2048
+    ff = FrameFusion(0.3, 0.6, 0.1)
+    ff.use_fused = fused
+    ff.prepare(pt.cuda(), P, *span)
+    o = orc.OracleFrameFusion(0.3, 0.6, 0.1, "bf16")
+    o.prepare(pt.numpy(), P, *span)
+    hd, pos = h.cuda(), [cos.cuda(), sin.cuda()]
+    stages = []
+    for c in range(6):
+        if ff.finish_merging and ff.finish_pruning:
+            break
+        if c > 0:
+            hd = synth.apply_drift(hd, 0.3, 3, c)
+        attn = None
+        if ff.finish_merging:
+            attn = synth.make_attention_row(hd.shape[1], n_heads=28, num=1, dtype=torch.bfloat16, seed=c).cuda()
+        h_in, p_in = t2f(hd[0]), [t2f(pos[0][0]), t2f(pos[1][0])]
+        hd, pos, _ = ff(hd, pos, None, attn)
+        want_h, want_p, _ = o.forward(h_in, p_in, None, None if attn is None else t2f(attn[0]))
+        stages.append(o.last["stage"])
+        assert hd.shape[1] == want_h.shape[0], f"call {c}: kept {hd.shape[1]}, oracle {want_h.shape[0]}"
+        assert np.array_equal(t2f(hd[0]), want_h), f"call {c}: hidden_states differ"
+        assert np.array_equal(t2f(pos[0][0]), want_p[0]) and np.array_equal(t2f(pos[1][0]), want_p[1])
+        assert np.array_equal(ff.patch_type[0].cpu().numpy(), o.patch_type)
+        assert ff.sparsity_list == o.sparsity_list
+    assert stages.count("merge") >= 2 and stages[-1] == "prune"
