@@ -250,10 +250,10 @@ int launch_similarity(const Ws& w, int bank, const void* hidden, int dtype, int6
     return dispatch_dtype(dtype, [&](auto dt) {
         constexpr int DT = decltype(dt)::value;
         if (vec)
-            FF_LAUNCH("k_similarity", (k_similarity<DT, true>), grid, 256, 0, st, hidden, (int)H, w.order[bank], w.chain[bank],
+            FF_LAUNCH("k_similarity", (k_similarity<DT, true>), grid, 256, 0, st, hidden, (int)H, (int)S, w.order[bank], w.chain[bank],
                       w.counters[bank], (float)thr, w.sim, w.flag, w.counters[bank]);
         else
-            FF_LAUNCH("k_similarity", (k_similarity<DT, false>), grid, 256, 0, st, hidden, (int)H, w.order[bank], w.chain[bank],
+            FF_LAUNCH("k_similarity", (k_similarity<DT, false>), grid, 256, 0, st, hidden, (int)H, (int)S, w.order[bank], w.chain[bank],
                       w.counters[bank], (float)thr, w.sim, w.flag, w.counters[bank]);
         return (int)FF_OK;
     });

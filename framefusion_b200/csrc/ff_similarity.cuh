@@ -10,21 +10,25 @@ namespace ff {
 
 template <int DT, bool VEC>
 __global__ void __launch_bounds__(256)
-k_similarity(const void* __restrict__ hidden, int H, const int* __restrict__ order, const int* __restrict__ chain,
+k_similarity(const void* __restrict__ hidden, int H, int S, const int* __restrict__ order, const int* __restrict__ chain,
              const int64_t* __restrict__ counters_in, float thr, float* __restrict__ sim, uint8_t* __restrict__ flag,
              int64_t* counters) {
     pdl_enter();
     __shared__ int s_cnt[8];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int N = (int)counters_in[C_N];
     const int j = blockIdx.x * 8 + wid;
+    // the links of position j are requested before N (the count they are checked against) has arrived: the arrays
+    // hold S entries and the grid covers no more than S positions, so the reads are in bounds either way
+    const int jc = min(j, S - 1), jp = max(jc - 1, 0);
+    const int c_cur = chain[jc], c_prev = chain[jp], o_cur = order[jc], o_prev = order[jp];
+    const int N = (int)counters_in[C_N];
     int hit = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) counters[C_TICKET2] = 0;   // slot counter of the scan kernels' records
     if (j < N) {
         float s = -2.0f;                                   // IGNORE_TOKEN at chain heads (main.py:225-238)
-        if (j > 0 && chain[j] == chain[j - 1]) {
-            const char* ra = (const char*)hidden + (int64_t)order[j - 1] * H * sizeof(typename Num<DT>::store_t);
-            const char* rb = (const char*)hidden + (int64_t)order[j] * H * sizeof(typename Num<DT>::store_t);
+        if (j > 0 && c_cur == c_prev) {
+            const char* ra = (const char*)hidden + (int64_t)o_prev * H * sizeof(typename Num<DT>::store_t);
+            const char* rb = (const char*)hidden + (int64_t)o_cur * H * sizeof(typename Num<DT>::store_t);
             float dot = 0.f, na = 0.f, nb = 0.f;
             if (VEC) {
                 const int nvec = H / Num<DT>::EPV;
