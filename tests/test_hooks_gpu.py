@@ -78,3 +78,31 @@ def test_merge_call_is_repeatable_bit_for_bit(fused):
             ref = cur
         else:
             assert all(torch.equal(a, b) for a, b in zip(ref, cur)), f"repetition {rep} differs"
+
+
+def test_decode_after_reduced_prefill_on_the_gpu():
+    """Prefill through the CUDA operator, then decode: every layer's KV cache keeps the length that layer saw
+    (modeling_qwen2.py:143-145: ragged, non-increasing), decode steps pass through the operator untouched and grow
+    every layer by one; the result matches a dense decode of the same model only in shape, not in value."""
+    from framefusion_b200.interface import apply_framefusion
+    model = tiny_model()
+    apply_framefusion(model, cost=0.3, similarity_lower_bound=0.6, ratio_lower_bound=0.1)
+    ff = model.framefusion
+    wl = synth.make_workload(10, 24, 256, torch.bfloat16, seed=11, r_lo=0.0, r_hi=1.0, n_pre=5, n_post=7, rot_dim=64)
+    n_layers = len(model.model.layers)
+    with torch.no_grad():
+        ff.prepare(*synth.to_device(wl, "cuda").prepare_args())
+        out = model.model(inputs_embeds=wl.hidden.cuda(), use_cache=True)
+        lens = [out.past_key_values.get_seq_length(i) for i in range(n_layers)]
+        assert lens[0] < wl.seq_len and all(a >= b for a, b in zip(lens, lens[1:]))      # layer 0 already merges
+        assert out.last_hidden_state.shape[1] <= lens[-1]
+        cache = out.past_key_values
+        state = (ff.finish_merging, ff.finish_pruning, list(ff.sparsity_list))
+        for step in range(2):
+            tok = torch.randn(1, 1, 256, device="cuda", dtype=torch.bfloat16)
+            mask = torch.ones(1, wl.seq_len + 1 + step, dtype=torch.long, device="cuda")      # generate() style mask
+            res = model.model(inputs_embeds=tok, past_key_values=cache, use_cache=True, attention_mask=mask)
+            assert res.last_hidden_state.shape == (1, 1, 256) and torch.isfinite(res.last_hidden_state.float()).all()
+            cache = res.past_key_values
+            assert [cache.get_seq_length(i) for i in range(n_layers)] == [l + 1 + step for l in lens]
+        assert (ff.finish_merging, ff.finish_pruning, list(ff.sparsity_list)) == state      # q_len == 1: a no-op
