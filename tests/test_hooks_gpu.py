@@ -106,3 +106,52 @@ def test_decode_after_reduced_prefill_on_the_gpu():
             cache = res.past_key_values
             assert [cache.get_seq_length(i) for i in range(n_layers)] == [l + 1 + step for l in lens]
         assert (ff.finish_merging, ff.finish_pruning, list(ff.sparsity_list)) == state      # q_len == 1: a no-op
+
+
+def tiny_qwen2vl():
+    from transformers import Qwen2VLConfig, Qwen2VLForConditionalGeneration
+    torch.manual_seed(0)
+    cfg = Qwen2VLConfig(
+        text_config=dict(vocab_size=128, hidden_size=256, intermediate_size=512, num_hidden_layers=5, num_attention_heads=4,
+                         num_key_value_heads=2, max_position_embeddings=4096,
+                         rope_parameters={"rope_type": "default", "mrope_section": [8, 12, 12], "rope_theta": 1e6}),
+        vision_config=dict(depth=1, embed_dim=32, hidden_size=64, num_heads=2, in_channels=3, patch_size=14,
+                           spatial_merge_size=2, temporal_patch_size=2))
+    cfg.text_config._attn_implementation = "sdpa"
+    return Qwen2VLForConditionalGeneration(cfg).eval().to(torch.bfloat16).cuda()
+
+
+def test_qwen2vl_prefill_matches_oracle_call_by_call():
+    """The Qwen2-VL trio on the GPU: position embeddings are [3, 1, S, D] (M-RoPE, compacted along dim 2 as three
+    planes of one aux tensor) and the importance comes from the last FOUR queries (modeling_qwen2_vl.py:289-301)."""
+    from framefusion_b200.interface import apply_framefusion
+    model = tiny_qwen2vl()
+    apply_framefusion(model, cost=0.3, similarity_lower_bound=0.6, ratio_lower_bound=0.1)
+    ff, llm = model.framefusion, model.model.language_model
+    wl = synth.make_workload(10, 24, 256, torch.bfloat16, seed=13, r_lo=0.0, r_hi=0.5, n_pre=5, n_post=7, rot_dim=64)
+    o = orc.OracleFrameFusion(0.3, 0.6, 0.1, "bf16")
+    o.prepare(wl.patch_type.numpy(), wl.patch_num, *wl.prepare_args()[2:])
+    calls, inner = [], ff.forward
+
+    def checked(hidden, pos, mask, attn=None):
+        assert pos[0].dim() == 4 and pos[0].shape[0] == 3
+        h_in = t2f(hidden[0]); p_in = [t2f(pos[0][:, 0]), t2f(pos[1][:, 0])]
+        a_in = None if attn is None else t2f(attn[0])
+        if attn is not None:
+            assert attn.shape[2] == 4
+        out = inner(hidden, pos, mask, attn)
+        want_h, want_p, _ = o.forward(h_in, [p[:, None] for p in p_in], None, a_in)
+        assert np.array_equal(t2f(out[0][0]), want_h), f"call {len(calls)}: hidden_states differ from the oracle"
+        for k in range(2):
+            assert np.array_equal(t2f(out[1][k][:, 0]), np.asarray(want_p[k])[:, 0]), f"call {len(calls)}: position plane {k}"
+        assert (ff.finish_merging, ff.finish_pruning) == (o.finish_merging, o.finish_pruning)
+        calls.append((hidden.shape[1], out[0].shape[1], attn is not None))
+        return out
+
+    ff.forward = checked
+    with torch.no_grad():
+        ff.prepare(*synth.to_device(wl, "cuda").prepare_args())
+        res = llm(inputs_embeds=wl.hidden.cuda(), use_cache=True)
+    assert res.last_hidden_state.shape[1] == calls[-1][1] < wl.seq_len
+    assert ff.finish_pruning and any(c[2] for c in calls)
+    assert ff.sparsity_list == o.sparsity_list
