@@ -32,47 +32,41 @@ k_importance_logits(const void* __restrict__ q, const void* __restrict__ k, int 
     if (s >= S) return;
     const st* krow = (const st*)k + (int64_t)hk * k_hs + (int64_t)s * k_ss;
     const int GL = group * L;
-    if (VEC && GL <= 8) {
-        // the K row is read once (16-byte loads); up to eight (query head, query row) dot products advance together
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int v = 0; v < D / Num<DT>::EPV; ++v) {
-            float kf[Num<DT>::EPV];
-            Num<DT>::unpack(ldg16((const char*)krow + (int64_t)v * 16), kf);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                if (g < GL) {
-                    const float* qv = s_q + g * D + v * Num<DT>::EPV;
-#pragma unroll
-                    for (int e = 0; e < Num<DT>::EPV; ++e) acc[g] = fmaf(kf[e], qv[e], acc[g]);
-                }
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            if (g < GL) {
-                const int r = g % L, h = hk * group + g / L;
-                float x = Num<DT>::rnd(acc[g]);                // matmul output in T
-                x = Num<DT>::rnd(x * scale);                   // * scale_factor
-                const float bias = (is_causal && s > S - L + r) ? -INFINITY : 0.f;
-                x = Num<DT>::rnd(x + bias);                    // += attn_bias
-                logits[((int64_t)h * L + r) * S + s] = x;
-            }
-        }
-        return;
-    }
-    for (int gr = 0; gr < GL; ++gr) {
-        const float* qv = s_q + gr * D;
-        float acc = 0.f;
-        if (VEC) {
+    if (VEC) {
+        // eight (query head, query row) dot products advance together over one pass of the K row (16-byte loads); more
+        // pairs than eight (Qwen2-VL: 7 heads x 4 query rows per KV head) take further passes, which the L1 serves
+        for (int gb = 0; gb < GL; gb += 8) {
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             for (int v = 0; v < D / Num<DT>::EPV; ++v) {
                 float kf[Num<DT>::EPV];
                 Num<DT>::unpack(ldg16((const char*)krow + (int64_t)v * 16), kf);
 #pragma unroll
-                for (int e = 0; e < Num<DT>::EPV; ++e) acc = fmaf(kf[e], qv[v * Num<DT>::EPV + e], acc);
+                for (int g = 0; g < 8; ++g) {
+                    if (gb + g < GL) {
+                        const float* qv = s_q + (gb + g) * D + v * Num<DT>::EPV;
+#pragma unroll
+                        for (int e = 0; e < Num<DT>::EPV; ++e) acc[g] = fmaf(kf[e], qv[e], acc[g]);
+                    }
+                }
             }
-        } else {
-            for (int d = 0; d < D; ++d) acc = fmaf(Num<DT>::load(krow, d), qv[d], acc);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                if (gb + g < GL) {
+                    const int r = (gb + g) % L, h = hk * group + (gb + g) / L;
+                    float x = Num<DT>::rnd(acc[g]);            // matmul output in T
+                    x = Num<DT>::rnd(x * scale);               // * scale_factor
+                    const float bias = (is_causal && s > S - L + r) ? -INFINITY : 0.f;
+                    x = Num<DT>::rnd(x + bias);                // += attn_bias
+                    logits[((int64_t)h * L + r) * S + s] = x;
+                }
+            }
         }
+        return;
+    }
+    for (int gr = 0; gr < GL; ++gr) {                      // rows that are not 16-byte aligned: element by element
+        const float* qv = s_q + gr * D;
+        float acc = 0.f;
+        for (int d = 0; d < D; ++d) acc = fmaf(Num<DT>::load(krow, d), qv[d], acc);
         const int r = gr % L, h = hk * group + gr / L;
         float x = Num<DT>::rnd(acc);                       // matmul output in T
         x = Num<DT>::rnd(x * scale);                       // * scale_factor
