@@ -375,6 +375,25 @@ def main():
         pass
     achieved = alg / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
 
+    # The same launches once more, queued behind a spacer kernel that touches no memory: by the time the GPU reaches the
+    # first event the three kernels are already in the stream, so host submission latency (Python -> ctypes -> launch,
+    # which the figure above includes because the stream is idle when the call starts) is not counted.  Reported next
+    # to kernel_us, not instead of it.
+    queued_ms = None
+    try:
+        ffq = FrameFusion(c["cost"], c["slb"], c["rlb"])
+        ts = []
+        for _ in range(7):
+            ffq.prepare(*wl.prepare_args())
+            ffq.kernel_events = []
+            torch.cuda._sleep(600000)
+            ffq(devt["hidden"], [devt["cos"], devt["sin"]], None)
+            torch.cuda.synchronize()
+            ts.append(ffq.kernel_events[0][2].elapsed_time(ffq.kernel_events[0][3]))
+        queued_ms = sorted(ts[2:])[len(ts[2:]) // 2]
+    except Exception:  # noqa: BLE001
+        queued_ms = None
+
     # the single-pass streaming kernel on the same call, for the record (DESIGN.md compares the two designs)
     single_ms = None
     try:
@@ -414,7 +433,8 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "ff_merge_layer call #0: " + ("k_stream_merge (single pass)" if fused else "two-pass path (k_similarity + k_keep_scan + k_merge_gather)"),
                      "single_pass_kernel_us": None if single_ms is None else single_ms * 1e3,
-                     "kernel_us": k_ms * 1e3, "algorithmic_bytes": alg, "peak_source": peak_src,
+                     "kernel_us": k_ms * 1e3, "kernel_us_queued": None if queued_ms is None else queued_ms * 1e3,
+                     "algorithmic_bytes": alg, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "e2e": {"value": whole_job_throughput(n_tok, e2e_steps, ms_e2e, world), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps,
