@@ -21,7 +21,7 @@ ST_SEQ_KEEP, ST_COUNT, ST_NVIS, ST_NCHAIN, ST_BRANCH, ST_TOPK, ST_ERROR, ST_NMER
 ST_SLOTS = 16
 
 EXPORTS = [
-    "ff_abi_version", "ff_last_error", "ff_launch_count", "ff_ctx_create", "ff_ctx_destroy", "ff_ctx_status", "ff_stream_sync", "ff_workspace_bytes",
+    "ff_abi_version", "ff_last_error", "ff_launch_count", "ff_ctx_create", "ff_ctx_destroy", "ff_ctx_status", "ff_ctx_timing", "ff_stream_sync", "ff_workspace_bytes",
     "ff_build_links", "ff_similarity", "ff_merge_apply", "ff_merge_layer", "ff_importance", "ff_prune_layer",
     "ff_compact_mask", "ff_debug_read", "ff_debug_trace",
 ]
@@ -60,6 +60,7 @@ def load():
     lib.ff_ctx_status.argtypes = [_vp]
     lib.ff_ctx_status.restype = C.POINTER(_i64)
     lib.ff_stream_sync.argtypes = [_vp, _vp]
+    lib.ff_ctx_timing.argtypes = [_vp, _vp, _vp]
     lib.ff_workspace_bytes.argtypes = [_i64, _i64]
     lib.ff_workspace_bytes.restype = _i64
     lib.ff_build_links.argtypes = [_vp, _vp, _i64, _vp, _i64, _i64, _vp]

@@ -81,6 +81,7 @@ struct ff_ctx {
     int max_smem;        // opt-in dynamic shared memory per block
     char* scratch;       // device buffer of the single-pass kernel (averaged anchors in flight), owned by the context
     size_t scratch_bytes;
+    cudaEvent_t ev_start, ev_stop;   // ff_ctx_timing
     int count_clean[2];  // counters[bank][C_COUNT] is known to be zero (set by the kernel that decided the previous call)
     unsigned bar_base;   // value of the grid-barrier word before the next k_keep_scan (it is not reset between merge calls)
     int bar_dirty;       // the prune stage left the barrier word at an unknown value
@@ -453,6 +454,14 @@ int ff_ctx_destroy(ff_ctx* ctx) {
 
 const int64_t* ff_ctx_status(const ff_ctx* ctx) { return ctx ? ctx->h_status : nullptr; }
 
+int ff_ctx_timing(ff_ctx* ctx, void* ev_start, void* ev_stop) {
+    if (!ctx) return fail(FF_E_BADARG, "null ctx");
+    if ((ev_start == nullptr) != (ev_stop == nullptr)) return fail(FF_E_BADARG, "pass two events or two NULLs");
+    ctx->ev_start = (cudaEvent_t)ev_start;
+    ctx->ev_stop = (cudaEvent_t)ev_stop;
+    return FF_OK;
+}
+
 int ff_stream_sync(ff_ctx* ctx, void* stream) {
     if (!ctx) return fail(FF_E_BADARG, "null ctx");
     FF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
@@ -580,7 +589,9 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
             sa.tag = (epoch - 1) % 127 + 1;
             if (!ctx->count_clean[bank]) FF_CUDA(cudaMemsetAsync(&w.counters[bank][C_COUNT], 0, 8, st));
             if (epoch > 1 && sa.tag == 1) FF_CUDA(cudaMemsetAsync(w.state, 0, (size_t)ctx->cap, st));   // tags wrap
+            if (ctx->ev_start) FF_CUDA(cudaEventRecord(ctx->ev_start, st));
             int rc = launch_stream(dtype, sa, plan, st);
+            if (ctx->ev_stop) FF_CUDA(cudaEventRecord(ctx->ev_stop, st));
             if (rc != FF_OK) return fail(rc, "single-pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             g_launches.fetch_add(1, std::memory_order_relaxed);
             ctx->epoch = epoch;
@@ -599,6 +610,7 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     if (!ctx->count_clean[bank]) FF_CUDA(cudaMemsetAsync(&w.counters[bank][C_COUNT], 0, 8, st));
     ctx->count_clean[bank] = 0;
     ctx->count_clean[nb] = 1;                              // the deciding kernel zeroes the next bank's count
+    if (ctx->ev_start) FF_CUDA(cudaEventRecord(ctx->ev_start, st));
     if (int rc = launch_similarity(w, bank, hidden, dtype, S, H, thr, st)) return rc;
     DecideArgs a;
     a.counters = w.counters[bank];
@@ -639,6 +651,7 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
         FF_LAUNCH("k_decide_scan", k_decide_scan, 1, SEL_THREADS, 0, st, a);
     }
     if (int rc = launch_merge_gather(ctx, w, bank, hidden, hidden_out, dtype, S, H, ap, st)) return rc;
+    if (ctx->ev_stop) FF_CUDA(cudaEventRecord(ctx->ev_stop, st));
     ctx->last_parity = bank;
     ctx->parity = nb;
     ctx->links_S = -2;                                     // = S_keep, known once the host has synchronised
@@ -696,6 +709,7 @@ int ff_prune_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* attn, in
     FF_CUDA(cudaSetDevice(ctx->device));
     const int bank = ctx->parity;
     const bool grid_select = S >= 2 * SEL_THREADS;
+    if (ctx->ev_start) FF_CUDA(cudaEventRecord(ctx->ev_start, st));
     if (grid_select) {
         FF_CUDA(cudaMemsetAsync(w.barrier, 0, 256 + 4 * 256 * 4, st));     // barrier word + histograms (adjacent)
     }
@@ -747,6 +761,7 @@ int ff_prune_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* attn, in
             FF_LAUNCH_CHECK("k_aux_compact");
         }
     }
+    if (ctx->ev_stop) FF_CUDA(cudaEventRecord(ctx->ev_stop, st));
     ctx->last_parity = bank;
     if (importance_out) {
         // counters[C_N] is not S here: store with an explicit count

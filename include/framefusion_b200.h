@@ -86,6 +86,11 @@ const int64_t* ff_ctx_status(const ff_ctx* ctx);
 /* waits for the work enqueued on `stream`: the one synchronisation a reducing call needs before the status block
  * (S_keep, the branch taken) can be read */
 int ff_stream_sync(ff_ctx* ctx, void* stream);
+/* Profiling aid: two caller-owned cudaEvent_t (timing enabled), or NULLs to switch it off.  While set, ff_merge_layer and
+ * ff_prune_layer record `ev_start` on the stream right before their first kernel launch and `ev_stop` right after their
+ * last one, so the elapsed time between them is the GPU time of the call's launches and nothing of the host's path to
+ * the first launch (bench.py's roofline.kernel_us). */
+int ff_ctx_timing(ff_ctx* ctx, void* ev_start, void* ev_stop);
 
 int64_t ff_workspace_bytes(int64_t seq_capacity, int64_t n_ids);
 
