@@ -13,13 +13,13 @@ prof = os.path.join(ROOT, "profiles")
 
 
 def short(name):
-    return name.replace("void ", "").split("(")[0]
+    return name.replace("void ", "").replace("ff::", "").split("(")[0]
 
 
 rows = list(csv.reader(l for l in open(f"{out}/bench_launches_{tag}.csv") if l.startswith('"')))
 hdr = rows[0]
 ki, vi, gi, bi = (hdr.index(k) for k in ("Kernel Name", "Metric Value", "Grid Size", "Block Size"))
-data = [(r[ki], float(r[vi].replace(",", "")) / 1000, r[gi], r[bi]) for r in rows[1:]]
+data = [(r[ki].replace("void ", "").replace("ff::", ""), float(r[vi].replace(",", "")) / 1000, r[gi], r[bi]) for r in rows[1:]]
 start = max(i for i, d in enumerate(data) if d[0].startswith("k_links_hist"))
 step = data[start:]
 tot = sum(d[1] for d in step)
