@@ -12,15 +12,16 @@ from framefusion_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def drive(frames, patches, hidden, lo, hi, fused, drift=0.0, cost=0.3, max_calls=6, per_patch_r=False, n_pre=14, n_post=20):
+def drive(frames, patches, hidden, lo, hi, fused, drift=0.0, cost=0.3, max_calls=6, per_patch_r=False, n_pre=14, n_post=20,
+          dtype=torch.bfloat16):
     from framefusion_b200.main import FrameFusion
-    wl = synth.make_workload(frames, patches, hidden, torch.bfloat16, seed=9, r_lo=lo, r_hi=hi, per_patch_r=per_patch_r,
+    wl = synth.make_workload(frames, patches, hidden, dtype, seed=9, r_lo=lo, r_hi=hi, per_patch_r=per_patch_r,
                              n_pre=n_pre, n_post=n_post)
     assert wl.seq_len >= 2048
     ff = FrameFusion(cost, 0.6, 0.1)
     ff.use_fused = fused
     ff.prepare(*synth.to_device(wl, "cuda").prepare_args())
-    o = orc.OracleFrameFusion(cost, 0.6, 0.1, "bf16")
+    o = orc.OracleFrameFusion(cost, 0.6, 0.1, {torch.bfloat16: "bf16", torch.float16: "f16", torch.float32: "f32"}[dtype])
     o.prepare(wl.patch_type.numpy(), wl.patch_num, *wl.prepare_args()[2:])
     h, pos = wl.hidden.cuda(), [wl.cos.cuda(), wl.sin.cuda()]
     stages = []
@@ -31,7 +32,7 @@ def drive(frames, patches, hidden, lo, hi, fused, drift=0.0, cost=0.3, max_calls
             h = synth.apply_drift(h, drift, 9, c)
         attn = None
         if ff.finish_merging:
-            attn = synth.make_attention_row(h.shape[1], n_heads=28, num=1, dtype=torch.bfloat16, seed=c).cuda()
+            attn = synth.make_attention_row(h.shape[1], n_heads=28, num=1, dtype=dtype, seed=c).cuda()
         h_in, p_in = t2f(h[0]), [t2f(pos[0][0]), t2f(pos[1][0])]
         h, pos, _ = ff(h, pos, None, attn)
         want_h, want_p, _ = o.forward(h_in, p_in, None, None if attn is None else t2f(attn[0]))
@@ -141,3 +142,11 @@ def test_ragged_chains_with_text_between_frames(fused):
         assert np.array_equal(ff.patch_type[0].cpu().numpy(), o.patch_type)
         assert ff.sparsity_list == o.sparsity_list
     assert stages.count("merge") >= 2 and stages[-1] == "prune"
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32], ids=["f16", "f32"])
+def test_other_dtypes_at_scale(dtype):
+    """f16 (IEEE division for runs that are not a power of two, 16-byte vectors of 8) and f32 (vectors of 4) through the
+    multi-block kernels."""
+    stages = drive(24, 128, 384, 0.0, 1.0, False, drift=0.3, dtype=dtype)
+    assert stages[0] == "threshold" and stages[-1] == "prune"
