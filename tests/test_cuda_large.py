@@ -150,3 +150,9 @@ def test_other_dtypes_at_scale(dtype):
     multi-block kernels."""
     stages = drive(24, 128, 384, 0.0, 1.0, False, drift=0.3, dtype=dtype)
     assert stages[0] == "threshold" and stages[-1] == "prune"
+
+
+def test_hidden_size_without_16_byte_rows_at_scale():
+    """Rows of 500 bytes: the gather's vector path does not apply, the element-wise kernels take over after the grid scan."""
+    stages = drive(24, 128, 250, 0.0, 1.0, False, drift=0.3)
+    assert stages[0] == "threshold" and stages[-1] == "prune"
