@@ -58,7 +58,12 @@ def _threshold_in(value, dtype) -> float:
 
 
 def _stream(device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    """Handle of torch's current stream on ``device`` (the raw getter: ``torch.cuda.current_stream`` builds a Python
+    object per call, ~9 us, and a reducing call asks several times)."""
+    index = device.index
+    if index is None:
+        index = torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(index)
 
 
 class _DeviceState:
@@ -111,13 +116,21 @@ def _aux_of(t: torch.Tensor, seq_dim: int):
 
 
 class FrameFusion(nn.Module):
+    # per-prefill / per-call state: plain Python attributes
+    _PLAIN = frozenset((
+        "cost", "similarity_lower_bound", "ratio_lower_bound", "patch_type", "patch_num", "image_token_start_index",
+        "image_token_end_index", "image_token_length", "original_length", "finish_merging", "finish_pruning",
+        "sparsity_list", "use_fused", "debug_trace", "last_trace", "kernel_events", "_links_for", "_have_order",
+        "_have_lists", "_dev"))
+
     def __setattr__(self, name, value):
         # the operator has no parameters, buffers or sub-modules: skip nn.Module's bookkeeping (it costs ~4 us per
-        # assignment and forward() assigns a dozen state attributes per call)
-        if isinstance(value, (nn.Module, nn.Parameter)):
-            super().__setattr__(name, value)
-        else:
+        # assignment, the isinstance check against nn.Parameter alone ~1.5 us, and forward() assigns a dozen state
+        # attributes per call)
+        if name in FrameFusion._PLAIN or not isinstance(value, (nn.Module, nn.Parameter)):
             object.__setattr__(self, name, value)
+        else:
+            super().__setattr__(name, value)
 
     def __init__(self, cost=0.3, similarity_lower_bound=0.6, ratio_lower_bound=0.1):
         super(FrameFusion, self).__init__()
