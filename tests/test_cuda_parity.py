@@ -178,3 +178,25 @@ def test_full_size_against_oracle(cfg, fused):
         # exactly those positions
         diff = np.nonzero(tr["keep_mask"] != o.last["keep_mask"])[0]
         assert len(diff) == flips
+
+
+def test_kernel_events_hook_times_the_library_side_launches():
+    """``kernel_events`` hands two events to ff_ctx_timing: the library records them around its own launches."""
+    from framefusion_b200 import synth
+    from framefusion_b200.main import FrameFusion
+    wl = synth.to_device(synth.make_workload(24, 128, 512, torch.bfloat16, seed=2), "cuda")
+    ff = FrameFusion(0.3, 0.6, 0.1)
+    ff.reserve_kernel_events(2)
+    ff.prepare(*wl.prepare_args())
+    ff.kernel_events = []
+    h, _pos, _m = ff(wl.hidden, [wl.cos, wl.sin], None)
+    torch.cuda.synchronize()
+    assert len(ff.kernel_events) == 1
+    name, q_len, e0, e1 = ff.kernel_events[0]
+    assert name == "ff_merge_layer" and q_len == wl.seq_len
+    ms = e0.elapsed_time(e1)
+    assert 0.001 < ms < 50.0
+    ff.kernel_events = None
+    ff.prepare(*wl.prepare_args())
+    h2, _pos, _m = ff(wl.hidden, [wl.cos, wl.sin], None)               # the hook off again: same result, no events touched
+    assert torch.equal(h, h2)
