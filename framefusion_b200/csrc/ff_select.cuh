@@ -1,7 +1,7 @@
 // Selection, run bookkeeping and compaction offsets — the integer part of a merge / prune call.
 // These arrays are 1-8 bytes per token (tens of KB): the cost is latency, not bytes.  Short sequences (< 2 048 rows)
 // take ONE 1024-thread block with 8 items per thread and no grid-wide synchronisation; long ones a grid of co-resident
-// blocks with two (merge) or seven (prune) grid barriers.
+// blocks with two (merge) or three to five (prune) grid barriers.
 //
 //   k_decide_scan / k_keep_scan    main.py:112-127 (branch), 269-301 (runs), 132 (keep mask) + links of the next call
 //                                  + the records k_merge_gather is driven by
@@ -452,7 +452,7 @@ k_prune_scan(PruneArgs a) {
 }
 
 // ---- prune stage on a grid of co-resident blocks: radix select of the k-th largest importance (4 passes of 8 bits,
-// block histograms merged with global atomics, a grid barrier per pass), ties at the k-th value to the lowest
+// block histograms merged with global atomics, a grid barrier per pass, one more for the tie / greater prefixes), ties at the k-th value to the lowest
 // indices, then the sequence-order scan of the keep flags.  Same outputs as k_prune_scan, a few microseconds
 // instead of ~75 us for 22 k tokens in one block.
 struct PruneGridArgs {
@@ -469,15 +469,12 @@ k_prune_select(PruneGridArgs a) {
     __shared__ int s_hist[256];
     __shared__ int s_scan[33];
     __shared__ uint32_t s_digit, s_need;
-    __shared__ int s_base;
     const PruneArgs& p = a.p;
     const int t = threadIdx.x, G = gridDim.x, b = blockIdx.x;
     const int n = p.length, S = p.S;
     const float* vals = p.imp + p.start;
     const int per_n = ((n + G - 1) / G + SEL_THREADS - 1) / SEL_THREADS * SEL_THREADS;
     const int n0 = min(b * per_n, n), n1 = min(n0 + per_n, n);
-    const int per_s = ((S + G - 1) / G + SEL_THREADS - 1) / SEL_THREADS * SEL_THREADS;
-    const int s0 = min(b * per_s, S), s1 = min(s0 + per_s, S);
     unsigned bar_target = 0;
 
     uint32_t kth = 0, need_eq = 0;
@@ -520,48 +517,60 @@ k_prune_select(PruneGridArgs a) {
         need_eq = (uint32_t)need;
     }
 
-    // ---- ties: how many elements equal to the k-th value sit before this block
-    int c_eq = 0;
+    // ---- how many elements equal to / greater than the k-th value sit before this block.  With those two prefixes a
+    // row's destination follows directly: kept vision rows before it = (greater before) + min(equal before, need_eq)
+    // — ties go to the lowest indices — so neither the selection flags nor a second scan have to cross blocks.
+    int c_eq = 0, c_gt = 0;
     if (!all && !none)
-        for (int j = n0 + t; j < n1; j += SEL_THREADS) c_eq += float_key(vals[j]) == kth;
+        for (int j = n0 + t; j < n1; j += SEL_THREADS) {
+            const uint32_t key = float_key(vals[j]);
+            c_eq += key == kth;
+            c_gt += key > kth;
+        }
     int tot;
     block_exclusive_scan(c_eq, s_scan, &tot);
     if (t == 0) a.part[b] = tot;
-    bar_target += G;
-    grid_barrier(a.barrier, bar_target);
-    int carry = block_sum_prefix(a.part, b, s_scan);
-    for (int base = n0; base < n1; base += SEL_THREADS) {
-        const int j = base + t;
-        uint32_t key = 0;
-        int eq = 0;
-        if (j < n1 && !all && !none) { key = float_key(vals[j]); eq = key == kth; }
-        const int ex = carry + block_exclusive_scan(eq, s_scan, &tot);
-        if (j < n1) p.sel[j] = all ? 1 : (none ? 0 : (uint8_t)(key > kth || (eq && (uint32_t)ex < need_eq)));
-        carry += tot;
-    }
-    bar_target += G;
-    grid_barrier(a.barrier, bar_target);                   // sel[] complete
-
-    // ---- sequence-order scan of the keep flags
-    int c_keep = 0;
-    for (int i = s0 + t; i < s1; i += SEL_THREADS)
-        c_keep += (i < p.start || i >= p.start + n) ? 1 : (int)__ldcg(&p.sel[i - p.start]);
-    block_exclusive_scan(c_keep, s_scan, &tot);
+    block_exclusive_scan(c_gt, s_scan, &tot);
     if (t == 0) a.part[G + b] = tot;
     bar_target += G;
     grid_barrier(a.barrier, bar_target);
-    carry = block_sum_prefix(a.part + G, b, s_scan);
-    for (int base = s0; base < s1; base += SEL_THREADS) {
-        const int i = base + t;
-        int keep = 0;
-        if (i < s1) keep = (i < p.start || i >= p.start + n) ? 1 : (int)__ldcg(&p.sel[i - p.start]);
-        const int ex = carry + block_exclusive_scan(keep, s_scan, &tot);
-        if (i < s1) {
-            if (keep) { p.dst[i] = ex; p.srcidx[ex] = i; } else p.dst[i] = -1;
-        }
+    int carry = block_sum_prefix(a.part, b, s_scan);
+    int carry_gt = block_sum_prefix(a.part + G, b, s_scan);
+    const int k_sel = all ? n : (none ? 0 : (int)p.k);      // vision rows that stay
+    for (int base = n0; base < n1; base += SEL_THREADS) {
+        const int j = base + t;
+        uint32_t key = 0;
+        int eq = 0, gt = 0;
+        if (j < n1 && !all && !none) { key = float_key(vals[j]); eq = key == kth; gt = key > kth; }
+        const int ex_eq = carry + block_exclusive_scan(eq, s_scan, &tot);
         carry += tot;
+        const int ex_gt = carry_gt + block_exclusive_scan(gt, s_scan, &tot);
+        carry_gt += tot;
+        if (j < n1) {
+            const int keep = all ? 1 : (none ? 0 : (int)(gt || (eq && (uint32_t)ex_eq < need_eq)));
+            p.sel[j] = (uint8_t)keep;
+            const int i = p.start + j;
+            if (keep) {
+                const int d = p.start + (all ? j : ex_gt + (int)min((uint32_t)ex_eq, need_eq));
+                p.dst[i] = d;
+                p.srcidx[d] = i;
+            } else {
+                p.dst[i] = -1;
+            }
+        }
     }
-    const int s_keep = b == G - 1 ? block_sum_prefix(a.part + G, G, s_scan) : 0;
+    // the rows around the vision span always stay: before it in place, behind it shifted by the rows that went
+    for (int i = b * SEL_THREADS + t; i < S; i += G * SEL_THREADS) {
+        if (i < p.start) {
+            p.dst[i] = i;
+            p.srcidx[i] = i;
+        } else if (i >= p.start + n) {
+            const int d = i - (n - k_sel);
+            p.dst[i] = d;
+            p.srcidx[d] = i;
+        }
+    }
+    const int s_keep = S - (n - k_sel);
     if (b == G - 1 && t == 0) {
         p.counters[C_SKEEP] = s_keep;
         p.status[FF_ST_SEQ_KEEP] = s_keep;
