@@ -497,15 +497,32 @@ k_prune_select(PruneGridArgs a) {
             grid_barrier(a.barrier, bar_target);
             for (int q = t; q < 256; q += SEL_THREADS) s_hist[q] = __ldcg(&a.hist[pass * 256 + q]);
             __syncthreads();
-            if (t == 0) {
-                long long acc = 0;
-                int q = 255;
-                for (; q > 0; --q) {                       // walk from the largest digit down
-                    if (acc + s_hist[q] >= need) break;
-                    acc += s_hist[q];
+            if (t < 32) {
+                // the digit of the k-th value: walk from the largest digit down until `need` elements are covered.  One warp:
+                // lane l owns digits [8l, 8l + 8); a suffix sum over the lanes finds the lane the walk stops in.
+                int loc[8];
+                long long mine = 0;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { loc[e] = s_hist[8 * t + e]; mine += loc[e]; }
+                long long above = mine;                    // inclusive suffix sum: this lane's digits and all larger ones
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const long long v = __shfl_down_sync(FULL, above, o);
+                    if (t + o < 32) above += v;
                 }
-                s_digit = (uint32_t)q;
-                s_need = (uint32_t)(need - acc);
+                above -= mine;                             // elements in digits above this lane's range
+                if (t == 0) { s_digit = 0; s_need = (uint32_t)(need - above - (mine - loc[0])); }   // the walk never stops before digit 0
+                __syncwarp();
+                if (above < need && above + mine >= need && !(t == 0 && above + mine - loc[0] < need)) {
+                    long long acc = above;
+                    int e = 7;
+                    for (; e > 0; --e) {
+                        if (acc + loc[e] >= need) break;
+                        acc += loc[e];
+                    }
+                    s_digit = (uint32_t)(8 * t + e);
+                    s_need = (uint32_t)(need - acc);
+                }
             }
             __syncthreads();
             prefix |= s_digit << shift;
