@@ -156,3 +156,33 @@ def test_hidden_size_without_16_byte_rows_at_scale():
     """Rows of 500 bytes: the gather's vector path does not apply, the element-wise kernels take over after the grid scan."""
     stages = drive(24, 128, 250, 0.0, 1.0, False, drift=0.3)
     assert stages[0] == "threshold" and stages[-1] == "prune"
+
+
+@pytest.mark.parametrize("ratio,ties", [(0.0, False), (1.0, False), (0.55, True), (0.3, False)],
+                         ids=["keep_all", "keep_none", "heavy_ties", "plain"])
+def test_prune_stage_alone_at_scale(ratio, ties):
+    """The grid radix select: every vision row kept, none kept, thousands of equal importances (ties go to the lowest
+    index), and an ordinary case — straight into the prune stage with a pruning ratio of the test's choosing."""
+    from framefusion_b200.main import FrameFusion
+    frames, patches, hidden = 30, 128, 256
+    wl = synth.make_workload(frames, patches, hidden, torch.bfloat16, seed=4, n_pre=11, n_post=17)
+    S, start, length = wl.seq_len, 11, frames * patches
+    ff = FrameFusion(0.3, 0.6, 0.1)
+    ff.prepare(wl.patch_type.cuda(), patches, start, start + length - 1, length, S, finish_merging=True, sparsity_list=[])
+    ff._compute_pruning_ratio = lambda sparsity_list, cost, num_layers=28: ratio
+    g = torch.Generator().manual_seed(1)
+    attn = torch.rand(1, 28, 1, S, generator=g)
+    if ties:
+        attn = (attn * 6).floor() / 6 + 0.01                  # six distinct values per head, the same in every head
+        attn = attn[:, :1].expand(1, 28, 1, S).contiguous()
+    attn = (attn / attn.sum(-1, keepdim=True)).to(torch.bfloat16)
+    h, pos, _ = ff(wl.hidden.cuda(), [wl.cos.cuda(), wl.sin.cuda()], None, attn.cuda())
+    imp = orc.mean_heads(t2f(attn[0]), "bf16")
+    keep = orc.prune_keep_indices(imp, start, length, S, ratio)
+    if ties:
+        vals, counts = np.unique(imp[start:start + length], return_counts=True)
+        assert counts.max() > 300
+    assert h.shape[1] == len(keep)
+    assert np.array_equal(t2f(h[0]), t2f(wl.hidden[0])[keep])
+    assert np.array_equal(t2f(pos[0][0]), t2f(wl.cos[0])[keep]) and np.array_equal(t2f(pos[1][0]), t2f(wl.sin[0])[keep])
+    assert ff.finish_pruning
