@@ -17,7 +17,7 @@ k_importance_logits(const void* __restrict__ q, const void* __restrict__ k, int 
                     int num, int64_t q_hs, int64_t q_ss, int64_t k_hs, int64_t k_ss, int is_causal, float scale,
                     float* __restrict__ logits /* [Hq, num, S] float32 holding T values */) {
     pdl_enter();
-    extern __shared__ float s_q[];                        // [group * num][D]
+    extern __shared__ __align__(16) float s_q[];          // [group * num][D]
     typedef typename Num<DT>::store_t st;
     const int hk = blockIdx.y;
     const int group = n_q_heads / n_kv_heads;
@@ -43,9 +43,16 @@ k_importance_logits(const void* __restrict__ q, const void* __restrict__ k, int 
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
                     if (gb + g < GL) {
-                        const float* qv = s_q + (gb + g) * D + v * Num<DT>::EPV;
+                        // 16-byte shared-memory reads: D is a multiple of the vector length on this path
+                        const float4* qv = reinterpret_cast<const float4*>(s_q + (gb + g) * D + v * Num<DT>::EPV);
 #pragma unroll
-                        for (int e = 0; e < Num<DT>::EPV; ++e) acc[g] = fmaf(kf[e], qv[e], acc[g]);
+                        for (int f = 0; f < Num<DT>::EPV / 4; ++f) {
+                            const float4 qq = qv[f];
+                            acc[g] = fmaf(kf[4 * f + 0], qq.x, acc[g]);
+                            acc[g] = fmaf(kf[4 * f + 1], qq.y, acc[g]);
+                            acc[g] = fmaf(kf[4 * f + 2], qq.z, acc[g]);
+                            acc[g] = fmaf(kf[4 * f + 3], qq.w, acc[g]);
+                        }
                     }
                 }
             }
