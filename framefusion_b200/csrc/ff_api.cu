@@ -686,7 +686,7 @@ int ff_importance(ff_ctx* ctx, const void* q, const void* k, int dtype, int64_t 
             FF_LAUNCH("k_importance_logits", (k_importance_logits<DT, false>), grid, IMP_THREADS, smem, st, q, k, (int)Hq, (int)Hk,
                       (int)S, (int)D, (int)num, q_hs, q_ss, k_hs, k_ss, is_causal, (float)scale, (float*)scratch);
         }
-        FF_LAUNCH("k_softmax_rows", k_softmax_rows<DT>, (int)(Hq * num), 1024, 0, st, (const float*)scratch, (int)S, probs_out);
+        FF_LAUNCH("k_softmax_rows", k_softmax_rows<DT>, (int)(Hq * num) * SOFTMAX_CLUSTER, 1024, 0, st, (const float*)scratch, (int)S, probs_out);
         return (int)FF_OK;
     });
     return rc;

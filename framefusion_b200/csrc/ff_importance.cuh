@@ -5,6 +5,8 @@
 //   logits = T( T( T(q.k) * scale ) + bias ),  bias = -inf above the causal diagonal (triu(diagonal=S-L+1))
 //   probs  = T( exp(x - max) / sum exp(x - max) )   with float32 softmax internals
 #pragma once
+#include <cooperative_groups.h>
+
 #include "ff_common.cuh"
 
 namespace ff {
@@ -83,30 +85,40 @@ k_importance_logits(const void* __restrict__ q, const void* __restrict__ k, int 
     }
 }
 
-// one block per (head, query) row; the row lives in registers between the three passes when it fits
-constexpr int SOFTMAX_CACHE = 40;                         // values per thread: rows up to 40 960 keys
+// One thread-block CLUSTER of four CTAs per (head, query) row: each CTA owns a quarter of the row, keeps it in registers
+// between the passes when it fits, and the four partial maxima / sums meet through distributed shared memory (two
+// cluster barriers instead of a second kernel or 28 lonely blocks on 148 SMs).  The partial sums are added in rank order,
+// so the result does not depend on timing.
+constexpr int SOFTMAX_CLUSTER = 4;
+constexpr int SOFTMAX_CACHE = 10;                         // values per thread: rows up to 4 * 10 * 1024 = 40 960 keys
 
 template <int DT>
-__global__ void __launch_bounds__(1024)
+__global__ void __cluster_dims__(SOFTMAX_CLUSTER, 1, 1) __launch_bounds__(1024)
 k_softmax_rows(const float* __restrict__ logits, int S, void* __restrict__ probs) {
     pdl_enter();
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     __shared__ float s_red[32];
-    __shared__ float s_val;
-    const float* x = logits + (int64_t)blockIdx.x * S;
+    __shared__ float s_part[2];                            // this CTA's maximum and sum, read by the other three
+    const int rank = (int)cluster.block_rank();
+    const int row = blockIdx.x / SOFTMAX_CLUSTER;
+    const float* x = logits + (int64_t)row * S;
+    const int seg = (S + SOFTMAX_CLUSTER - 1) / SOFTMAX_CLUSTER;
+    const int lo = min(rank * seg, S), hi = min(lo + seg, S);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const bool cached = S <= SOFTMAX_CACHE * (int)blockDim.x;
+    const bool cached = seg <= SOFTMAX_CACHE * (int)blockDim.x;
     float c[SOFTMAX_CACHE];
     float m = -INFINITY;
     if (cached) {
 #pragma unroll
         for (int i = 0; i < SOFTMAX_CACHE; ++i) {
-            const int s = threadIdx.x + i * blockDim.x;
-            c[i] = s < S ? __ldg(x + s) : -INFINITY;
+            const int s = lo + threadIdx.x + i * blockDim.x;
+            c[i] = s < hi ? __ldg(x + s) : -INFINITY;
         }
 #pragma unroll
         for (int i = 0; i < SOFTMAX_CACHE; ++i) m = fmaxf(m, c[i]);
     } else {
-        for (int s = threadIdx.x; s < S; s += blockDim.x) m = fmaxf(m, x[s]);
+        for (int s = lo + threadIdx.x; s < hi; s += blockDim.x) m = fmaxf(m, x[s]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
@@ -116,44 +128,47 @@ k_softmax_rows(const float* __restrict__ logits, int S, void* __restrict__ probs
         float v = lane < nw ? s_red[lane] : -INFINITY;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
-        if (lane == 0) s_val = v;
+        if (lane == 0) s_part[0] = v;
     }
-    __syncthreads();
-    m = s_val;
+    cluster.sync();
+    m = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < SOFTMAX_CLUSTER; ++r) m = fmaxf(m, *cluster.map_shared_rank(&s_part[0], r));
     float sum = 0.f;
     if (cached) {
-        // the same per-thread order of the additions as the loop below: s = tid, tid + blockDim, ...
 #pragma unroll
         for (int i = 0; i < SOFTMAX_CACHE; ++i) {
-            const int s = threadIdx.x + i * blockDim.x;
-            if (s < S) {
+            const int s = lo + threadIdx.x + i * blockDim.x;
+            if (s < hi) {
                 c[i] = expf(c[i] - m);
                 sum += c[i];
             }
         }
     } else {
-        for (int s = threadIdx.x; s < S; s += blockDim.x) sum += expf(x[s] - m);
+        for (int s = lo + threadIdx.x; s < hi; s += blockDim.x) sum += expf(x[s] - m);
     }
     sum = warp_sum(sum);
-    __syncthreads();
     if (lane == 0) s_red[wid] = sum;
     __syncthreads();
     if (wid == 0) {
         float v = lane < nw ? s_red[lane] : 0.f;
         v = warp_sum(v);
-        if (lane == 0) s_val = v;
+        if (lane == 0) s_part[1] = v;
     }
-    __syncthreads();
-    sum = s_val;
+    cluster.sync();
+    sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < SOFTMAX_CLUSTER; ++r) sum += *cluster.map_shared_rank(&s_part[1], r);
+    cluster.sync();                                        // nobody leaves while its shared memory may still be read
     if (cached) {
 #pragma unroll
         for (int i = 0; i < SOFTMAX_CACHE; ++i) {
-            const int s = threadIdx.x + i * blockDim.x;
-            if (s < S) Num<DT>::store(probs, (int64_t)blockIdx.x * S + s, c[i] / sum);
+            const int s = lo + threadIdx.x + i * blockDim.x;
+            if (s < hi) Num<DT>::store(probs, (int64_t)row * S + s, c[i] / sum);
         }
     } else {
-        for (int s = threadIdx.x; s < S; s += blockDim.x)
-            Num<DT>::store(probs, (int64_t)blockIdx.x * S + s, expf(x[s] - m) / sum);
+        for (int s = lo + threadIdx.x; s < hi; s += blockDim.x)
+            Num<DT>::store(probs, (int64_t)row * S + s, expf(x[s] - m) / sum);
     }
 }
 
