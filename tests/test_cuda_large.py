@@ -186,3 +186,35 @@ def test_prune_stage_alone_at_scale(ratio, ties):
     assert np.array_equal(t2f(h[0]), t2f(wl.hidden[0])[keep])
     assert np.array_equal(t2f(pos[0][0]), t2f(wl.cos[0])[keep]) and np.array_equal(t2f(pos[1][0]), t2f(wl.sin[0])[keep])
     assert ff.finish_pruning
+
+
+def test_4d_mask_is_compacted_at_scale():
+    """An eager-attention style [1, 1, S, S] mask travels through merge calls and the prune call of a long sequence
+    (main.py:100, 138: mask[keep][:, keep]) — the destination maps come from the multi-block scan / select kernels."""
+    from framefusion_b200.main import FrameFusion
+    wl = synth.make_workload(18, 120, 256, torch.bfloat16, seed=21, r_lo=0.0, r_hi=1.0)
+    S = wl.seq_len
+    assert S >= 2048
+    g = torch.Generator().manual_seed(3)
+    mask = torch.randn(1, 1, S, S, generator=g).to(torch.bfloat16)
+    ff = FrameFusion(0.3, 0.6, 0.1)
+    ff.prepare(*synth.to_device(wl, "cuda").prepare_args())
+    o = orc.OracleFrameFusion(0.3, 0.6, 0.1, "bf16")
+    o.prepare(wl.patch_type.numpy(), wl.patch_num, *wl.prepare_args()[2:])
+    h, pos, m = wl.hidden.cuda(), [wl.cos.cuda(), wl.sin.cuda()], mask.cuda()
+    stages = []
+    for c in range(6):
+        if ff.finish_merging and ff.finish_pruning:
+            break
+        if c > 0:
+            h = synth.apply_drift(h, 0.3, 21, c)
+        attn = None
+        if ff.finish_merging:
+            attn = synth.make_attention_row(h.shape[1], n_heads=28, num=1, dtype=torch.bfloat16, seed=c).cuda()
+        h_in, p_in, m_in = t2f(h[0]), [t2f(pos[0][0]), t2f(pos[1][0])], t2f(m[0, 0])
+        h, pos, m = ff(h, pos, m, attn)
+        want_h, _want_p, want_m = o.forward(h_in, p_in, m_in, None if attn is None else t2f(attn[0]))
+        stages.append(o.last["stage"])
+        assert np.array_equal(t2f(h[0]), want_h), f"call {c}: hidden_states differ"
+        assert m.shape == (1, 1, want_m.shape[0], want_m.shape[1]) and np.array_equal(t2f(m[0, 0]), want_m), f"call {c}: mask differs"
+    assert "merge" in stages and stages[-1] == "prune"
