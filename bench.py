@@ -440,7 +440,7 @@ def main():
         "e2e": {"value": whole_job_throughput(n_tok, e2e_steps, ms_e2e, world), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps,
                 "pipelining": "double-buffered device inputs: the host->device copy of step i+1 overlaps the kernels and the device->host read of step i"},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches) * world,          # every replica launches the same kernels
         "clocks": clk.summary(),
     }
     if rank == 0:
