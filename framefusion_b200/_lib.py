@@ -17,13 +17,13 @@ FF_BF16, FF_F16, FF_F32 = 0, 1, 2
 FF_MAX_AUX = 6
 
 # status slots (enum ff_status_slot)
-ST_SEQ_KEEP, ST_COUNT, ST_NVIS, ST_NCHAIN, ST_BRANCH, ST_TOPK, ST_ERROR, ST_NMERGED, ST_FUSED = range(9)
+ST_SEQ_KEEP, ST_COUNT, ST_NVIS, ST_NCHAIN, ST_BRANCH, ST_TOPK, ST_ERROR, ST_NMERGED, ST_FUSED, ST_INTERNAL = range(10)
 ST_SLOTS = 16
 
 EXPORTS = [
     "ff_abi_version", "ff_last_error", "ff_launch_count", "ff_ctx_create", "ff_ctx_destroy", "ff_ctx_status", "ff_ctx_timing", "ff_stream_sync", "ff_workspace_bytes",
     "ff_build_links", "ff_similarity", "ff_merge_apply", "ff_merge_layer", "ff_importance", "ff_prune_layer",
-    "ff_compact_mask", "ff_debug_read", "ff_debug_trace",
+    "ff_compact_mask", "ff_debug_read",
 ]
 
 
@@ -73,14 +73,13 @@ def load():
     lib.ff_prune_layer.argtypes = [_vp, _vp, _i64, _vp, _i64, _vp, _vp, C.c_int, _i64, _i64, _i64, _i64, _i64,
                                    C.POINTER(FFAux), C.c_int, _vp, _vp]
     lib.ff_compact_mask.argtypes = [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp]
-    lib.ff_debug_trace.argtypes = [_vp, _vp, _i64, _i64]
     lib.ff_debug_read.argtypes = [_vp, _vp, _i64, C.c_int, _vp, _i64, C.c_int, _vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("ff_last_error", "ff_launch_count", "ff_ctx_status", "ff_workspace_bytes"):
             fn.restype = C.c_int
-    if lib.ff_abi_version() != 1:
-        raise FFError(f"ABI version {lib.ff_abi_version()} != 1")
+    if lib.ff_abi_version() != 2:
+        raise FFError(f"ABI version {lib.ff_abi_version()} != 2")
     _lib = lib
     return lib
 

@@ -7,12 +7,12 @@
 #include <new>
 
 #include "ff_common.cuh"
+#include "ff_fused.cuh"
 #include "ff_importance.cuh"
 #include "ff_links.cuh"
 #include "ff_merge.cuh"
 #include "ff_select.cuh"
 #include "ff_similarity.cuh"
-#include "ff_stream.cuh"
 
 using namespace ff;
 
@@ -74,19 +74,34 @@ struct ff_ctx {
     int64_t links_S;     // sequence length the links describe (-1: none, -2: S_keep of the last merge call)
     int64_t cap;         // capacity the workspace is carved for (set by ff_build_links)
     int64_t n_ids;
-    int have_order;      // compact by-patch order / chain / rank arrays valid for `parity` (generic path)
-    int have_lists;      // per-chain lists (order at base[id], len[parity][id]) valid for `parity` (single-pass path)
-    unsigned epoch;      // single-pass calls since ff_build_links (tags the flag bytes)
+    int have_order;      // compact by-patch order / chain / rank arrays valid for `parity` (multi-kernel path)
+    int have_seq;        // (pred, succ) of every sequence row valid for `parity` (read-once kernel)
+    int last_fused;      // the last merge call ran the read-once kernel: sim[] is indexed by sequence row
+    int fused_clean[2];  // state words / tile descriptors of the bank are known to be zero
+    int fused_attr[3];   // dynamic shared memory the kernel of each dtype was last opted in for
     int sm_count;
     int max_smem;        // opt-in dynamic shared memory per block
-    char* scratch;       // device buffer of the single-pass kernel (averaged anchors in flight), owned by the context
-    size_t scratch_bytes;
     cudaEvent_t ev_start, ev_stop;   // ff_ctx_timing
     int count_clean[2];  // counters[bank][C_COUNT] is known to be zero (set by the kernel that decided the previous call)
     unsigned bar_base;   // value of the grid-barrier word before the next k_keep_scan (it is not reset between merge calls)
     int bar_dirty;       // the prune stage left the barrier word at an unknown value
-    long long* trace;    // development aid: device buffer for the single-pass kernel's time stamps (ff_debug_trace)
 };
+
+// every entry point runs on the context's device and leaves the caller's current device as it found it (PyTorch
+// tracks the current device through the runtime: a layer-split model calls in from several devices)
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int device) : prev(-1), ok(true) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) ok = cudaSetDevice(device) == cudaSuccess;
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define FF_DEVICE(ctx)                                                                             \
+    DeviceGuard guard_((ctx)->device);                                                             \
+    if (!guard_.ok) return fail(FF_E_CUDA, "cudaSetDevice(%d) failed", (ctx)->device)
 
 // ------------------------------------------------------------------------------------------------
 // workspace
@@ -101,7 +116,9 @@ struct Ws {
     int* len[2];        // [n_ids + 1] rows per chain; bucket n_ids = rows outside the chains
     float* sim;
     uint8_t* flag;
-    uint8_t* state;
+    int2* link[2];      // [cap] (pred, succ) of every sequence row (read-once kernel)
+    unsigned long long* fstate[2];   // [cap] its state words
+    unsigned long long* desc[2];     // [1 + tiles] ticket + tile descriptors
     int* dst[2];
     int* srcidx;
     int4* rec;          // [cap] per kept chain row in by-patch order: (source row, destination row, by-patch position, run length)
@@ -131,7 +148,10 @@ Ws carve(void* base_ptr, int64_t cap, int64_t n_ids) {
     w.hist = (int*)take((size_t)n_chunks * (size_t)(n_ids + 1) * 4);
     w.barrier = (unsigned*)take(256);
     w.sel_hist = (int*)take(4 * 256 * 4);
-    w.state = (uint8_t*)take(cap);
+    for (int b = 0; b < 2; ++b) {
+        w.fstate[b] = (unsigned long long*)take((size_t)cap * 8);
+        w.desc[b] = (unsigned long long*)take(((size_t)(cap + 1) / 2 + 2) * 8);
+    }
     w.zero_begin = zero_begin;
     w.zero_bytes = (size_t)((p ? p + off : (char*)nullptr) - zero_begin);
     w.len[1] = (int*)take((size_t)(n_ids + 1) * 4);
@@ -142,6 +162,8 @@ Ws carve(void* base_ptr, int64_t cap, int64_t n_ids) {
     }
     w.sim = (float*)take(cap * 4);
     w.flag = (uint8_t*)take(cap);
+    w.link[0] = (int2*)take((size_t)cap * 8);
+    w.link[1] = (int2*)take((size_t)cap * 8);
     w.dst[0] = (int*)take(cap * 4);
     w.dst[1] = (int*)take(cap * 4);
     w.srcidx = (int*)take(cap * 4);
@@ -315,7 +337,7 @@ int links_ready(ff_ctx* ctx, int64_t S, bool need_order) {
     if (ctx->links_S != S)
         return fail(FF_E_BADARG, "chain links in the workspace describe S=%lld, not %lld: call ff_build_links", (long long)ctx->links_S, (long long)S);
     if (need_order && !ctx->have_order)
-        return fail(FF_E_BADARG, "by-patch order not in the workspace (the fused path does not keep it): call ff_build_links");
+        return fail(FF_E_BADARG, "by-patch order not in the workspace (the read-once kernel does not keep it): call ff_build_links");
     return FF_OK;
 }
 
@@ -326,71 +348,43 @@ int check_shape(int64_t S, int64_t H, int dtype) {
     return FF_OK;
 }
 
-// Fills the launch arguments of the single-pass kernel; false when the shape is outside what it handles.
-bool plan_stream_args(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* out, int dtype, int64_t S,
-                      int64_t H, double thr, double bound, const AuxPack& ap, StreamArgs* sa, StreamPlan* plan) {
-    const int64_t eb = dtype == FF_F32 ? 4 : 2;
-    const int64_t row_bytes = H * eb;
+// rows per tile (= warps per CTA) of the read-once kernel: two CTAs per SM, two slots per warp; 0 = rows too long
+int fused_tile_rows(const ff_ctx* ctx, int64_t row_bytes) {
+    const int64_t slot = (row_bytes + 127) / 128 * 128;
+    const int64_t per_cta = ctx->max_smem / 2 - 1024;      // a resident CTA also pays ~1 KB of system shared memory
+    int64_t w = (per_cta - 256) / (2 * slot);
+    if (w > FU_WARPS) w = FU_WARPS;
+    return w < 2 ? 0 : (int)w;
+}
+
+// rows the read-once kernel handles: 16-byte multiples, a threshold no chain head (sim = -2) can pass, shared memory
+// for at least two warps
+bool fused_shape_ok(const ff_ctx* ctx, const void* hidden, const void* out, int dtype, int64_t S, int64_t H, double thr) {
+    const int64_t row_bytes = H * (dtype == FF_F32 ? 4 : 2);
     if (row_bytes % 16 != 0 || (((uintptr_t)hidden | (uintptr_t)out) & 15) != 0) return false;
-    const int64_t nvec = row_bytes / 16;
-    if (nvec > (int64_t)32 * ST_MAX_VPL) return false;
-    if (S >= (1 << 20)) return false;                      // gap counts travel in 20 bits
-    if (!(thr > -2.0)) return false;                       // chain heads (sim = -2) must never be flagged
-    if (ctx->n_ids < 1) return false;
-    StreamArgs& a = *sa;
-    a.n_tma_aux = a.n_small_aux = 0;
-    int off = (int)row_bytes;
-    for (int q = 0; q < ap.n; ++q) {
-        const ff_aux& x = ap.a[q];
-        const uintptr_t al = (uintptr_t)x.src | (uintptr_t)x.dst | (uintptr_t)x.src_plane_stride | (uintptr_t)x.dst_plane_stride;
-        if (x.row_bytes % 16 == 0 && (al & 15) == 0 && x.row_bytes <= 512) {
-            for (int64_t pl = 0; pl < x.planes; ++pl) {
-                if (a.n_tma_aux == ST_MAX_TMA_AUX) return false;
-                StreamAux& t = a.tma_aux[a.n_tma_aux++];
-                t.src = (const char*)x.src + pl * x.src_plane_stride;
-                t.dst = (char*)x.dst + pl * x.dst_plane_stride;
-                t.bytes = (int)x.row_bytes;
-                t.slot_off = off;
-                off += (int)x.row_bytes;
-            }
-        } else if (x.row_bytes == 8 && x.planes == 1 && (al & 7) == 0) {
-            if (a.n_small_aux == ST_MAX_SMALL_AUX) return false;
-            StreamAux& t = a.small_aux[a.n_small_aux++];
-            t.src = (const char*)x.src;
-            t.dst = (char*)x.dst;
-            t.bytes = 8;
-            t.slot_off = 0;
-        } else {
-            return false;
-        }
-    }
-    if (!plan_stream(ctx->sm_count, ctx->max_smem, row_bytes, (int)ctx->n_ids, plan)) return false;
-    const size_t need = (size_t)ctx->n_ids * ST_SCRATCH * (size_t)row_bytes;
-    if (need > ctx->scratch_bytes) {                       // grows rarely: once per model shape
-        if (ctx->scratch) cudaFree(ctx->scratch);
-        ctx->scratch = nullptr;
-        ctx->scratch_bytes = 0;
-        if (cudaMalloc((void**)&ctx->scratch, need) != cudaSuccess) { cudaGetLastError(); return false; }
-        ctx->scratch_bytes = need;
-    }
-    a.scratch = ctx->scratch;
+    if (S >= (1ll << 30) - 2) return false;
+    if (!(thr > -2.0)) return false;
+    return fused_tile_rows(ctx, row_bytes) > 0;
+}
+
+int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* out, int dtype, int64_t S, int64_t H,
+                 double thr, double bound, const AuxPack& ap, cudaStream_t st) {
     const int nb = bank ^ 1;
+    FusedArgs a;
     a.hidden = (const char*)hidden;
     a.out = (char*)out;
     a.S = (int)S;
-    a.nvec = (int)nvec;
-    a.row_bytes = (int)row_bytes;
-    a.slot_bytes = plan->slot_bytes;
-    a.n_slots = plan->n_slots;
-    a.n_ids = (int)ctx->n_ids;
-    a.cpc = plan->cpc;
-    a.n_sim = plan->n_sim;
-    a.order = w.order[bank];
-    a.base = w.base;
-    a.len = w.len[bank];
-    a.order_next = w.order[nb];
-    a.len_next = w.len[nb];
-    a.state = w.state;
+    a.row_bytes = (int)(H * (dtype == FF_F32 ? 4 : 2));
+    a.nvec = a.row_bytes / 16;
+    a.slot_bytes = (a.row_bytes + 127) / 128 * 128;
+    a.tile_rows = fused_tile_rows(ctx, a.row_bytes);
+    a.ntiles = (int)((S + a.tile_rows - 1) / a.tile_rows);
+    a.link = w.link[bank];
+    a.link_next = w.link[nb];
+    a.fstate = w.fstate[bank];
+    a.desc = w.desc[bank];
+    a.fstate_clr = w.fstate[nb];
+    a.desc_clr = w.desc[nb];
     a.sim_seq = w.sim;
     a.dst = w.dst[bank];
     a.counters = w.counters[bank];
@@ -398,9 +392,28 @@ bool plan_stream_args(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, vo
     a.status = ctx->d_status;
     a.thr = (float)thr;
     a.bound = bound;
-    a.tag = 1;
-    a.trace = ctx->trace;
-    return true;
+    if (!ctx->fused_clean[bank]) {
+        FF_CUDA(cudaMemsetAsync(w.fstate[bank], 0, (size_t)S * 8, st));
+        FF_CUDA(cudaMemsetAsync(w.desc[bank], 0, ((size_t)a.ntiles + 1) * 8, st));
+    }
+    ctx->fused_clean[bank] = 0;
+    ctx->fused_clean[nb] = 1;                              // the kernel clears the other bank on its way out
+    ctx->h_status[FF_ST_INTERNAL] = 0;
+    const int smem = 2 * a.tile_rows * a.slot_bytes + 256;
+    return dispatch_dtype(dtype, [&](auto dt) {
+        constexpr int DT = decltype(dt)::value;
+        if (ctx->fused_attr[DT] < smem) {
+            FF_CUDA(cudaFuncSetAttribute(k_fused_merge<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            ctx->fused_attr[DT] = smem;
+        }
+        int per_sm = 0;
+        FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_merge<DT>, a.tile_rows * 32, smem));
+        if (per_sm < 1) return fail(FF_E_UNSUPPORTED, "the read-once kernel does not fit an SM (%d bytes of shared memory)", smem);
+        int grid = per_sm * ctx->sm_count;
+        if (grid > a.ntiles) grid = a.ntiles;
+        FF_LAUNCH("k_fused_merge", k_fused_merge<DT>, grid, a.tile_rows * 32, smem, st, a, ap);
+        return (int)FF_OK;
+    });
 }
 
 }  // namespace
@@ -417,7 +430,8 @@ int64_t ff_launch_count(void) { return (int64_t)g_launches.load(std::memory_orde
 int ff_ctx_create(int device, ff_ctx** out) {
     if (!out) return fail(FF_E_BADARG, "out is null");
     *out = nullptr;
-    FF_CUDA(cudaSetDevice(device));
+    DeviceGuard guard_(device);
+    if (!guard_.ok) return fail(FF_E_CUDA, "cudaSetDevice(%d) failed", device);
     ff_ctx* c = new (std::nothrow) ff_ctx();
     if (!c) return fail(FF_E_BADARG, "out of host memory");
     c->device = device;
@@ -426,11 +440,10 @@ int ff_ctx_create(int device, ff_ctx** out) {
     c->links_S = -1;
     c->cap = 0;
     c->n_ids = 0;
-    c->have_order = c->have_lists = 0;
-    c->epoch = 0;
-    c->trace = nullptr;
-    c->scratch = nullptr;
-    c->scratch_bytes = 0;
+    c->have_order = c->have_seq = 0;
+    c->last_fused = 0;
+    c->fused_clean[0] = c->fused_clean[1] = 0;
+    c->fused_attr[0] = c->fused_attr[1] = c->fused_attr[2] = 0;
     cudaError_t e = cudaHostAlloc((void**)&c->h_status, FF_ST_SLOTS * 8, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e != cudaSuccess) { delete c; return fail(FF_E_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
     memset(c->h_status, 0, FF_ST_SLOTS * 8);
@@ -446,7 +459,6 @@ int ff_ctx_create(int device, ff_ctx** out) {
 
 int ff_ctx_destroy(ff_ctx* ctx) {
     if (!ctx) return FF_OK;
-    if (ctx->scratch) cudaFree(ctx->scratch);
     cudaFreeHost(ctx->h_status);
     delete ctx;
     return FF_OK;
@@ -484,11 +496,11 @@ int ff_build_links(ff_ctx* ctx, void* ws, int64_t ws_bytes, const int64_t* patch
     if (int rc = check_ws(ctx, ws, ws_bytes, S, &w)) return rc;
     if (S > 0 && !patch_type) return fail(FF_E_BADARG, "patch_type is null");
     cudaStream_t st = (cudaStream_t)stream;
-    FF_CUDA(cudaSetDevice(ctx->device));
+    FF_DEVICE(ctx);
     const int n_chunks = (int)((S + LINK_CHUNK - 1) / LINK_CHUNK);
     const int n_b = (int)n_ids + 1;                        // chain buckets + the bucket of rows outside the chains
     FF_CUDA(cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st));
-    ctx->epoch = 0;
+    ctx->fused_clean[0] = ctx->fused_clean[1] = 1;         // inside the region cleared above
     ctx->bar_base = 0;
     ctx->bar_dirty = 0;
     ctx->count_clean[0] = ctx->count_clean[1] = 1;
@@ -499,6 +511,8 @@ int ff_build_links(ff_ctx* ctx, void* ws, int64_t ws_bytes, const int64_t* patch
                   w.counters[0], ctx->d_status);
         FF_LAUNCH("k_links_scatter", k_links_scatter, n_chunks, LINK_CHUNK, 0, st, patch_type, (int)S, (int)n_ids, w.hist,
                   w.base, w.order[0], w.chain[0], w.rank[0]);
+        FF_LAUNCH("k_links_seq", k_links_seq, (int)((S + 255) / 256), 256, 0, st, w.rank[0], w.order[0], w.chain[0], w.counters[0],
+                  (int)S, w.link[0]);
     } else {
         k_links_status<<<1, 1, 0, st>>>(w.counters[0], ctx->d_status);
         FF_LAUNCH_CHECK("k_links_status");
@@ -506,7 +520,8 @@ int ff_build_links(ff_ctx* ctx, void* ws, int64_t ws_bytes, const int64_t* patch
     ctx->parity = 0;
     ctx->last_parity = 0;
     ctx->links_S = S;
-    ctx->have_order = ctx->have_lists = 1;
+    ctx->have_order = ctx->have_seq = 1;
+    ctx->last_fused = 0;
     return FF_OK;
 }
 
@@ -519,7 +534,7 @@ int ff_similarity(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, i
     if (int rc = check_ws(ctx, ws, ws_bytes, S, &w)) return rc;
     if (S > 0 && !hidden) return fail(FF_E_BADARG, "hidden is null");
     cudaStream_t st = (cudaStream_t)stream;
-    FF_CUDA(cudaSetDevice(ctx->device));
+    FF_DEVICE(ctx);
     const int bank = ctx->parity;
     if (!ctx->count_clean[bank]) FF_CUDA(cudaMemsetAsync(&w.counters[bank][C_COUNT], 0, 8, st));
     ctx->count_clean[bank] = 0;
@@ -543,11 +558,12 @@ int ff_merge_apply(ff_ctx* ctx, void* ws, int64_t ws_bytes, void* hidden, int dt
     if (!ctx) return fail(FF_E_BADARG, "null ctx");
     if (ctx->cap < S) { ctx->cap = S; ctx->n_ids = 0; }
     ctx->links_S = -1;                                     // scratch use of the order arrays
-    ctx->have_order = ctx->have_lists = 0;
+    ctx->have_order = ctx->have_seq = 0;
+    ctx->last_fused = 0;
     if (int rc = check_ws(ctx, ws, ws_bytes, S, &w)) return rc;
     if (!keep_mask_out && S > 0) return fail(FF_E_BADARG, "keep_mask_out is null");
     cudaStream_t st = (cudaStream_t)stream;
-    FF_CUDA(cudaSetDevice(ctx->device));
+    FF_DEVICE(ctx);
     if (S > 0) FF_CUDA(cudaMemsetAsync(keep_mask_out, 1, (size_t)S, st));
     if (M == 0 || N == 0) return FF_OK;                    // main.py:264-266
     if (!order || !merge_index || !hidden) return fail(FF_E_BADARG, "null order / merge_index / hidden");
@@ -578,34 +594,27 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     if (S > 0 && (!hidden || !hidden_out)) return fail(FF_E_BADARG, "hidden / hidden_out is null");
     if (hidden == hidden_out) return fail(FF_E_BADARG, "hidden_out must not alias hidden");
     cudaStream_t st = (cudaStream_t)stream;
-    FF_CUDA(cudaSetDevice(ctx->device));
+    FF_DEVICE(ctx);
     const int bank = ctx->parity, nb = bank ^ 1;
 
-    if ((flags & 1) && S > 0 && ctx->have_lists) {
-        StreamArgs sa;
-        StreamPlan plan;
-        if (plan_stream_args(ctx, w, bank, hidden, hidden_out, dtype, S, H, thr, bound, ap, &sa, &plan)) {
-            const unsigned epoch = ctx->epoch + 1;
-            sa.tag = (epoch - 1) % 127 + 1;
-            if (!ctx->count_clean[bank]) FF_CUDA(cudaMemsetAsync(&w.counters[bank][C_COUNT], 0, 8, st));
-            if (epoch > 1 && sa.tag == 1) FF_CUDA(cudaMemsetAsync(w.state, 0, (size_t)ctx->cap, st));   // tags wrap
-            if (ctx->ev_start) FF_CUDA(cudaEventRecord(ctx->ev_start, st));
-            int rc = launch_stream(dtype, sa, plan, st);
-            if (ctx->ev_stop) FF_CUDA(cudaEventRecord(ctx->ev_stop, st));
-            if (rc != FF_OK) return fail(rc, "single-pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-            ctx->epoch = epoch;
-            ctx->count_clean[bank] = 0;
-            ctx->count_clean[nb] = 1;
-            ctx->last_parity = bank;
-            ctx->parity = nb;
-            ctx->links_S = -2;
-            ctx->have_order = 0;
-            ctx->have_lists = 1;
-            return FF_OK;
-        }
+    if ((flags & 1) && S > 0 && fused_shape_ok(ctx, hidden, hidden_out, dtype, S, H, thr) && (ctx->have_seq || ctx->have_order)) {
+        if (ctx->ev_start) FF_CUDA(cudaEventRecord(ctx->ev_start, st));
+        if (!ctx->have_seq)                                // the previous call took the multi-kernel path: links from its arrays
+            FF_LAUNCH("k_links_seq", k_links_seq, (int)((S + 255) / 256), 256, 0, st, w.rank[bank], w.order[bank], w.chain[bank],
+                      w.counters[bank], (int)S, w.link[bank]);
+        if (int rc = launch_fused(ctx, w, bank, hidden, hidden_out, dtype, S, H, thr, bound, ap, st)) return rc;
+        if (ctx->ev_stop) FF_CUDA(cudaEventRecord(ctx->ev_stop, st));
+        ctx->count_clean[bank] = 0;
+        ctx->count_clean[nb] = 1;
+        ctx->last_parity = bank;
+        ctx->parity = nb;
+        ctx->links_S = -2;
+        ctx->have_order = 0;
+        ctx->have_seq = 1;
+        ctx->last_fused = 1;
+        return FF_OK;
     }
-    if (!ctx->have_order) return fail(FF_E_BADARG, "by-patch order not in the workspace (the fused path does not keep it): call ff_build_links");
+    if (!ctx->have_order) return fail(FF_E_BADARG, "by-patch order not in the workspace (the read-once kernel does not keep it): call ff_build_links");
 
     if (!ctx->count_clean[bank]) FF_CUDA(cudaMemsetAsync(&w.counters[bank][C_COUNT], 0, 8, st));
     ctx->count_clean[bank] = 0;
@@ -656,7 +665,8 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     ctx->parity = nb;
     ctx->links_S = -2;                                     // = S_keep, known once the host has synchronised
     ctx->have_order = 1;
-    ctx->have_lists = 0;                                   // the generic path keeps the compact arrays only
+    ctx->have_seq = 0;                                     // the multi-kernel path keeps the compact arrays only
+    ctx->last_fused = 0;
     return FF_OK;
 }
 
@@ -671,7 +681,7 @@ int ff_importance(ff_ctx* ctx, const void* q, const void* k, int dtype, int64_t 
     const size_t smem = (size_t)group * num * D * 4;
     if (smem > 96 * 1024) return fail(FF_E_UNSUPPORTED, "group*num*head_dim = %lld floats do not fit shared memory", (long long)(group * num * D));
     cudaStream_t st = (cudaStream_t)stream;
-    FF_CUDA(cudaSetDevice(ctx->device));
+    FF_DEVICE(ctx);
     const int64_t eb = dtype == FF_F32 ? 4 : 2;
     const bool vec = (D * eb) % 16 == 0 && ((uintptr_t)k & 15) == 0 && (k_hs * eb) % 16 == 0 && (k_ss * eb) % 16 == 0;
     dim3 grid((unsigned)((S + IMP_THREADS - 1) / IMP_THREADS), (unsigned)Hk);
@@ -699,14 +709,14 @@ int ff_prune_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* attn, in
     AuxPack ap;
     if (int rc = check_shape(S, H, dtype)) return rc;
     if (!ctx) return fail(FF_E_BADARG, "null ctx");
-    if (ctx->cap < S) { ctx->cap = S; ctx->n_ids = 0; ctx->links_S = -1; ctx->have_order = ctx->have_lists = 0; }
+    if (ctx->cap < S) { ctx->cap = S; ctx->n_ids = 0; ctx->links_S = -1; ctx->have_order = ctx->have_seq = 0; }
     if (int rc = check_ws(ctx, ws, ws_bytes, S, &w)) return rc;
     if (int rc = pack_aux(aux, n_aux, &ap)) return rc;
     if (!attn || !hidden || !hidden_out || n_rows < 1 || S < 1) return fail(FF_E_BADARG, "null / empty argument");
     if (start < 0 || length < 0 || start + length > S) return fail(FF_E_BADARG, "vision span [%lld, %lld) outside the sequence", (long long)start, (long long)(start + length));
     if (k < 0 || k > length) return fail(FF_E_BADARG, "k=%lld outside [0, %lld] (torch.topk would raise)", (long long)k, (long long)length);
     cudaStream_t st = (cudaStream_t)stream;
-    FF_CUDA(cudaSetDevice(ctx->device));
+    FF_DEVICE(ctx);
     const int bank = ctx->parity;
     const bool grid_select = S >= 2 * SEL_THREADS;
     if (ctx->ev_start) FF_CUDA(cudaEventRecord(ctx->ev_start, st));
@@ -780,7 +790,7 @@ int ff_compact_mask(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* mask, v
     if (S_keep == 0) return FF_OK;
     if (!mask || !mask_out) return fail(FF_E_BADARG, "null mask");
     cudaStream_t st = (cudaStream_t)stream;
-    FF_CUDA(cudaSetDevice(ctx->device));
+    FF_DEVICE(ctx);
     k_srcidx_from_dst<<<(int)((S + 255) / 256), 256, 0, st>>>(w.dst[ctx->last_parity], (int)S, w.srcidx);
     FF_LAUNCH_CHECK("k_srcidx_from_dst");
     switch (elem_bytes) {
@@ -794,14 +804,6 @@ int ff_compact_mask(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* mask, v
     return FF_OK;
 }
 
-int ff_debug_trace(ff_ctx* ctx, void* buffer_device, int64_t bytes, int64_t n_ids) {
-    if (!ctx) return fail(FF_E_BADARG, "null ctx");
-    if (buffer_device && bytes < n_ids * ST_TRACE_T * ST_TRACE_K * 8)
-        return fail(FF_E_WORKSPACE, "trace buffer needs %lld bytes", (long long)(n_ids * ST_TRACE_T * ST_TRACE_K * 8));
-    ctx->trace = (long long*)buffer_device;
-    return FF_OK;
-}
-
 int ff_debug_read(ff_ctx* ctx, void* ws, int64_t ws_bytes, int what, void* dst_device, int64_t n, int dtype, void* stream) {
     Ws w;
     if (!ctx || !dst_device) return fail(FF_E_BADARG, "null argument");
@@ -809,7 +811,7 @@ int ff_debug_read(ff_ctx* ctx, void* ws, int64_t ws_bytes, int what, void* dst_d
     if (int rc = check_ws(ctx, ws, ws_bytes, n, &w)) return rc;
     if (n == 0) return FF_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    FF_CUDA(cudaSetDevice(ctx->device));
+    FF_DEVICE(ctx);
     const int bank = ctx->last_parity;
     const int grid = (int)((n + 255) / 256);
     switch (what) {

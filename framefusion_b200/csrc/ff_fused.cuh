@@ -1,0 +1,410 @@
+// Read-once merge kernel: similarity + threshold select + run merge + compaction of hidden_states and of the aux
+// tensors (cos / sin / patch_type / position ids) in ONE launch that fetches every row of hidden_states from HBM
+// exactly once (main.py:104-138, threshold branch — every merge call of a prefill but possibly the last).
+//
+// Shape of the problem.  A token is compared with the previous surviving token of the SAME patch id (its chain
+// predecessor, main.py:216-238) — 576 rows (4 MB) back on the first call of a uniform video — while the output is
+// compacted in SEQUENCE order (main.py:132-138), and a kept row can only be written once the flags of its chain
+// successors are known (they are averaged into it, main.py:285-317).  So:
+//
+//   * tiles of FU_WARPS consecutive rows are handed out in sequence order by a ticket; warp w of the CTA owns row
+//     tile * W + w.  Its own row (from HBM) and its chain predecessor (pred[r], an L2 hit: that row was some
+//     tile's "own" row a few microseconds ago) are staged by TMA (cp.async.bulk + mbarrier) into the warp's two
+//     shared-memory slots — no registers are tied up while the rows travel.  Three row sums out of shared memory, warp
+//     shuffles, the reference's rounding chain -> sim, flag.
+//   * compacted position = kept rows before it: tile aggregate + decoupled look-back over the tile descriptors
+//     (one warp per tile), then one 8-byte state word per row is published: (pred << 32) | code with
+//     code = 1 (merged away) or 2 + destination row.
+//   * the CLOSING row emits: a row that is NOT flagged ends the run of its predecessor.  In the common case the
+//     predecessor is a plain kept row: its state word gives the destination and the staged copy leaves shared memory
+//     with one TMA bulk store — no second read, no registers.  If the predecessor was merged away, the warp walks
+//     the state words back to the anchor, adds the run members in chain order with one rounding to T per add (the
+//     order torch-CPU index_add_ uses, main.py:304-311; the last member is the staged row), divides once by T(L+1)
+//     (main.py:314-317) and stores the result at the anchor's destination.  Chain tails close their own run.
+//     Every dependency points to a row with a SMALLER sequence index, tickets are taken in order by CTAs that are
+//     running, so the lowest unfinished tile never waits: no deadlock, whatever is resident.
+//   * the links of the next call (pred / succ of every kept row, by destination index) fall out of the same walk:
+//     the closer knows both ends.
+//
+// The branch decision (main.py:114-116) needs the global count, known only at the end: the kernel speculates on the
+// threshold branch, the CTA of the last tile checks count / n_vis < bound and otherwise reports FF_ST_ERROR = 3; the
+// host then redoes the call with the multi-kernel path (top-k branch, at most once per prefill).  The input is
+// never modified, so the redo sees the original rows.
+#pragma once
+#include "ff_common.cuh"
+#include "ff_merge.cuh"
+
+namespace ff {
+
+constexpr int FU_WARPS = 8;                        // most rows per tile = warps per CTA (fewer when the rows are long)
+constexpr int FU_SPIN_LIMIT = 1 << 18;             // polls (~64 ns apart) before a wait gives up and reports FF_ST_INTERNAL
+constexpr unsigned long long FU_AGG = 1ull << 32, FU_INCL = 2ull << 32;
+
+struct FusedArgs {
+    const char* hidden;
+    char* out;
+    int S, nvec, row_bytes, slot_bytes, ntiles, tile_rows;
+    const int2* link;                              // [S] (pred, succ): row index, -1 = chain head / tail, -2 = not a chain row
+    int2* link_next;                               // [S_keep] the same for the compacted sequence
+    unsigned long long* fstate;                    // [S] zero on entry
+    unsigned long long* desc;                      // [1 + ntiles] zero on entry: ticket, tile descriptors
+    unsigned long long* fstate_clr;                // other bank: cleared for the next call
+    unsigned long long* desc_clr;
+    float* sim_seq;                                // [S] similarity with the chain predecessor (introspection)
+    int* dst;                                      // [S] destination row or -1
+    int64_t* counters;
+    int64_t* counters_next;
+    int64_t* status;
+    float thr;
+    double bound;
+};
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store(void* dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned long long ld_relaxed64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+// state word of row x, once it has been published (code != 0).  Gives up after FU_SPIN_LIMIT polls: *err is set and the
+// caller skips what depended on it, so the kernel always terminates.
+__device__ __forceinline__ unsigned long long wait_state(const unsigned long long* fstate, int x, int* err) {
+    unsigned long long v = ld_relaxed64(fstate + x);
+    int spins = 0;
+    while ((uint32_t)v == 0u) {
+        if (++spins > FU_SPIN_LIMIT) { *err = 1; break; }
+        __nanosleep(64);
+        v = ld_relaxed64(fstate + x);
+    }
+    return v;
+}
+
+// the aux rows of sequence row r are wanted a few microseconds from now (first plane of each tensor, first 128 bytes
+// per lane q; rows are at most a few hundred bytes): pull them into the L2 behind the hidden_states row
+__device__ __forceinline__ void prefetch_aux(const AuxPack& aux, int r, int lane) {
+#pragma unroll
+    for (int q = 0; q < FF_MAX_AUX; ++q)
+        if (q < aux.n && (lane >> 2) == q) {
+            const int64_t off = (int64_t)(lane & 3) * 128;
+            if (off < aux.a[q].row_bytes) prefetch_l2((const char*)aux.a[q].src + (int64_t)r * aux.a[q].row_bytes + off);
+        }
+}
+
+__device__ __forceinline__ void copy_row(const char* src, char* dst, int nvec, int lane) {
+    for (int vb = 0; vb < nvec; vb += 256) {                // eight 16-byte vectors per lane in flight
+        const int v0 = vb + lane;
+        uint4 x[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (v0 + 32 * q < nvec) x[q] = ld_stream16(src + (int64_t)(v0 + 32 * q) * 16);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (v0 + 32 * q < nvec) st_stream16(dst + (int64_t)(v0 + 32 * q) * 16, x[q]);
+    }
+}
+
+// The run that ends at the merged-away row e (state word st_e, code 1): walks the state words back to the anchor, adds
+// the members in chain order — T(acc + member) per add, main.py:304-311 —, divides by T(L + 1) (main.py:314-317) and
+// writes the anchor's destination row.  slot_row: row e staged in shared memory, or null (then it is read like the
+// others).  Returns the anchor's destination row, -1 if a wait timed out.
+template <int DT>
+__device__ __noinline__ int emit_merged_run(const FusedArgs& a, int e, unsigned long long st_e, const uint4* slot_row,
+                                            int lane, int* err) {
+    int L = 0, x = e, mine = -1;
+    unsigned long long st = st_e;
+    while ((uint32_t)st == 1u) {
+        if (lane == (L & 31)) mine = x;                     // lane k keeps the k-th member from the end (runs up to 32)
+        ++L;
+        x = (int)(st >> 32);
+        st = wait_state(a.fstate, x, err);
+    }
+    if ((uint32_t)st < 2u) { *err = 1; return -1; }
+    const int anchor = x, da = (int)(uint32_t)st - 2;
+    const Divider<DT> dv(L + 1);
+    const int64_t row_bytes = a.row_bytes;
+    const char* arow = a.hidden + (int64_t)anchor * row_bytes;
+    char* orow = a.out + (int64_t)da * row_bytes;
+#pragma unroll 1
+    for (int vb = 0; vb < a.nvec; vb += 128) {              // warp-uniform trip count: the loop body shuffles
+        const int v0 = vb + lane;
+        uint4 acc[4], xv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (v0 + 32 * q < a.nvec) acc[q] = ldg16(arow + (int64_t)(v0 + 32 * q) * 16);
+        int walk = anchor;
+#pragma unroll 1
+        for (int m = L - 1; m >= 0; --m) {                  // m = L - 1: first member behind the anchor ... m = 0: row e
+            int idx;
+            if (L <= 32) idx = __shfl_sync(FULL, mine, m);
+            else { walk = __ldg(&a.link[walk].y); idx = walk; }      // longer runs: follow the successor links
+            if (m == 0 && slot_row) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (v0 + 32 * q < a.nvec) xv[q] = slot_row[v0 + 32 * q];
+            } else {
+                const char* mr = a.hidden + (int64_t)idx * row_bytes;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (v0 + 32 * q < a.nvec) xv[q] = ldg16(mr + (int64_t)(v0 + 32 * q) * 16);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (v0 + 32 * q < a.nvec) acc[q] = Num<DT>::add_vec(acc[q], xv[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (v0 + 32 * q < a.nvec) st_stream16(orow + (int64_t)(v0 + 32 * q) * 16, dv.vec_fast(acc[q]));
+    }
+    return da;
+}
+
+// exclusive prefix of the tile's kept-row count over all earlier tiles (decoupled look-back, one warp)
+__device__ __forceinline__ int tile_lookback(unsigned long long* D, int tile, int total, int lane, int* err) {
+    if (tile == 0) {
+        if (lane == 0) st_relaxed64(D, FU_INCL | (unsigned)total);
+        return 0;
+    }
+    if (lane == 0) st_relaxed64(D + tile, FU_AGG | (unsigned)total);
+    int excl = 0, base = tile - 1, spins = 0;
+    while (true) {
+        const int idx = base - lane;
+        unsigned long long d = idx >= 0 ? ld_relaxed64(D + idx) : FU_INCL;
+        if (__ballot_sync(FULL, (d >> 32) == 0ull)) {       // a predecessor has not posted yet
+            if (++spins > FU_SPIN_LIMIT) { *err = 1; break; }
+            __nanosleep(32);
+            continue;
+        }
+        const unsigned incl = __ballot_sync(FULL, (d >> 32) == 2ull);
+        int v = (int)(uint32_t)d;
+        if (incl) {
+            const int first = __ffs(incl) - 1;              // nearest predecessor that knows its inclusive prefix
+            if (lane > first) v = 0;
+            excl += warp_sum_int(v);
+            break;
+        }
+        excl += warp_sum_int(v);
+        base -= 32;
+    }
+    if (lane == 0) st_relaxed64(D + tile, FU_INCL | (unsigned)(excl + total));
+    return excl;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(FU_WARPS * 32, 2)
+k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPack aux) {
+    extern __shared__ __align__(128) unsigned char fu_smem[];
+    pdl_enter();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, W = blockDim.x >> 5;      // W rows per tile (a.tile_rows)
+    // per warp: slot P (chain predecessor) and slot C (own row), one mbarrier for both
+    unsigned char* slot_p = fu_smem + (size_t)(2 * wid) * a.slot_bytes;
+    unsigned char* slot_c = slot_p + a.slot_bytes;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(fu_smem + (size_t)(2 * W) * a.slot_bytes);
+    volatile int* s_int = reinterpret_cast<volatile int*>(bars + FU_WARPS);   // [0, W) flags, [8] prefix, [9] next tile
+    const uint32_t sp32 = smem_u32(slot_p), sc32 = smem_u32(slot_c), bar = smem_u32(bars + wid);
+    unsigned long long* D = a.desc + 1;
+    if (lane == 0) mbar_init(bar, 1);
+    if (threadIdx.x == 0) s_int[FU_WARPS + 1] = (int)atomicAdd(a.desc, 1ull);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    int tile = s_int[FU_WARPS + 1];
+    uint32_t phase = 0;
+    int err = 0;
+    bool store_pending = false;                             // lane 0: a bulk store may still be reading a slot
+    const int nvec = a.nvec;
+    const int64_t row_bytes = a.row_bytes;
+
+    while (tile < a.ntiles) {
+        const int r = tile * W + wid;
+        const bool valid = r < a.S;
+        int2 lk = make_int2(-2, -2);
+        if (valid) lk = __ldg(a.link + r);
+        const int p = lk.x, sc = lk.y;
+        const bool has_pred = valid && p >= 0;
+        const bool self_emit = valid && (p == -2 || sc < 0);   // not a chain row, or a chain tail: it writes its own run
+        const bool need_row = has_pred || self_emit;
+        __syncwarp();                                       // every lane is done with the slots before they are refilled
+        if (need_row && lane == 0) {
+            if (store_pending) { tma_wait_read_0(); store_pending = false; }
+            mbar_expect_tx(bar, (uint32_t)row_bytes * (has_pred ? 2u : 1u));
+            tma_load(sc32, a.hidden + (int64_t)r * row_bytes, (uint32_t)row_bytes, bar);
+            if (has_pred) tma_load(sp32, a.hidden + (int64_t)p * row_bytes, (uint32_t)row_bytes, bar);
+        }
+        if (valid) prefetch_aux(aux, r, lane);
+        float s = -2.0f;                                    // IGNORE_TOKEN at chain heads (main.py:225-238)
+        int flag = 0;
+        if (need_row) {
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        }
+        if (has_pred) {
+            const uint4* pr = reinterpret_cast<const uint4*>(slot_p);
+            const uint4* cr = reinterpret_cast<const uint4*>(slot_c);
+            float dot = 0.f, na = 0.f, nb = 0.f;
+#pragma unroll 4
+            for (int vb = 0; vb < nvec; vb += 32)           // lane l sums vectors l, l + 32, ... in this order (as k_similarity)
+                if (vb + lane < nvec) acc_pair<DT>(pr[vb + lane], cr[vb + lane], dot, na, nb);
+            dot = warp_sum(dot);
+            na = warp_sum(na);
+            nb = warp_sum(nb);
+            s = finish_cosine<DT>(dot, na, nb);
+            flag = (s >= a.thr);                            // NaN compares false
+        }
+        if (lane == 0) {
+            if (valid) a.sim_seq[r] = s;
+            s_int[wid] = valid ? flag : 2;
+        }
+        __syncthreads();                                    // (A) the tile's flags are in shared memory
+        int myrank = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < FU_WARPS; ++w) {
+            const int k = (w < W) && (s_int[w] == 0);
+            if (w < wid) myrank += k;
+            total += k;
+        }
+        unsigned long long st_p = 0;
+        const bool closer = has_pred && !flag;
+        if (wid == 0) {
+            int nt = 0;
+            if (lane == 0) nt = (int)atomicAdd(a.desc, 1ull);              // the next tile's ticket travels meanwhile
+            const int excl = tile_lookback(D, tile, total, lane, &err);
+            if (lane == 0) { s_int[FU_WARPS] = excl; s_int[FU_WARPS + 1] = nt; }
+        } else if (closer) {
+            st_p = ld_relaxed64(a.fstate + p);
+        }
+        __syncthreads();                                    // (B) prefix and next tile known to every warp
+        const int excl = s_int[FU_WARPS];
+        const int next_tile = s_int[FU_WARPS + 1];
+        const int d_r = (valid && !flag) ? excl + myrank : -1;
+        if (valid && lane == 0) {
+            st_relaxed64(a.fstate + r, ((unsigned long long)(uint32_t)p << 32) | (flag ? 1u : (uint32_t)(d_r + 2)));
+            a.dst[r] = d_r;
+        }
+        if (tile == a.ntiles - 1 && threadIdx.x == 0) {
+            // the sequence is done: sizes, the speculated branch, the counters of the next call (main.py:112-120)
+            const long long s_keep = excl + total, merged = a.S - s_keep;
+            const long long N = a.counters[C_N], n_vis = a.counters[C_NVIS];
+            int e = 0;
+            if (n_vis == 0) e = 1;                          // the reference divides by zero here (main.py:114)
+            else if (!((double)merged / (double)n_vis < a.bound)) e = 3;   // top-k branch: the host redoes the call
+            a.counters[C_COUNT] = merged;
+            a.counters[C_NNEXT] = N - merged;
+            a.counters[C_SKEEP] = s_keep;
+            a.counters[C_BRANCH] = 0;
+            a.counters[C_K] = 0;
+            a.counters[C_NMERGED] = merged;
+            a.counters_next[C_N] = N - merged;
+            a.counters_next[C_NVIS] = n_vis - merged;
+            a.counters_next[C_COUNT] = 0;
+            a.counters_next[C_TICKET] = 0;
+            a.counters_next[C_TICKET2] = 0;
+            a.status[FF_ST_SEQ_KEEP] = s_keep;
+            a.status[FF_ST_COUNT] = merged;
+            a.status[FF_ST_NVIS] = n_vis;
+            a.status[FF_ST_NCHAIN] = N;
+            a.status[FF_ST_BRANCH] = 0;
+            a.status[FF_ST_TOPK] = 0;
+            a.status[FF_ST_ERROR] = e;
+            a.status[FF_ST_NMERGED] = merged;
+            a.status[FF_ST_FUSED] = 1;
+        }
+        if (closer) {
+            // this row ends the run of its predecessor: emit it
+            if ((uint32_t)st_p == 0u) st_p = wait_state(a.fstate, p, &err);
+            int da = -1;
+            if ((uint32_t)st_p >= 2u) {
+                da = (int)(uint32_t)st_p - 2;               // a plain kept row: the staged copy goes out as it is
+                if (lane == 0) {
+                    tma_store(a.out + (int64_t)da * row_bytes, sp32, (uint32_t)row_bytes);
+                    tma_commit();
+                    store_pending = true;
+                }
+            } else if ((uint32_t)st_p == 1u) {
+                da = emit_merged_run<DT>(a, p, st_p, reinterpret_cast<const uint4*>(slot_p), lane, &err);
+            }
+            if (lane == 0 && da >= 0) {
+                a.link_next[d_r].x = da;
+                a.link_next[da].y = d_r;
+            }
+        }
+        if (d_r >= 0 && p < 0 && lane == 0) {               // chain head / not a chain row
+            a.link_next[d_r].x = p;
+            if (p == -2) a.link_next[d_r].y = -2;
+        }
+        if (self_emit) {                                    // nobody comes to close this row's run
+            int da = d_r;
+            if (!flag) {
+                if (lane == 0) {
+                    tma_store(a.out + (int64_t)d_r * row_bytes, sc32, (uint32_t)row_bytes);
+                    tma_commit();
+                    store_pending = true;
+                }
+            } else {
+                da = emit_merged_run<DT>(a, r, ((unsigned long long)(uint32_t)p << 32) | 1ull,
+                                         reinterpret_cast<const uint4*>(slot_c), lane, &err);
+            }
+            if (lane == 0 && da >= 0 && p != -2) a.link_next[da].y = -1;
+        }
+        if (d_r >= 0 && aux.n) gather_aux_rows(aux, r, d_r, lane);
+        tile = next_tile;
+    }
+
+    // leave the other bank's state words and descriptors zeroed for the next call of the prefill
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.S; i += (int64_t)gridDim.x * blockDim.x) a.fstate_clr[i] = 0ull;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= a.ntiles; i += (int64_t)gridDim.x * blockDim.x) a.desc_clr[i] = 0ull;
+    if (err && lane == 0) a.status[FF_ST_INTERNAL] = 1;
+    if (lane == 0) tma_wait_all();
+}
+
+// (pred, succ) of every sequence row from the compact by-patch arrays (ff_links.cuh / the scan kernels)
+__global__ void __launch_bounds__(256)
+k_links_seq(const int* __restrict__ rank, const int* __restrict__ order, const int* __restrict__ chain,
+            const int64_t* __restrict__ counters, int S, int2* __restrict__ link) {
+    pdl_enter();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const int N = (int)counters[C_N];
+    const int j = rank[i];
+    int2 l = make_int2(-2, -2);
+    if (j >= 0) {
+        const int c = chain[j];
+        l.x = (j > 0 && chain[j - 1] == c) ? order[j - 1] : -1;
+        l.y = (j + 1 < N && chain[j + 1] == c) ? order[j + 1] : -1;
+    }
+    link[i] = l;
+}
+
+}  // namespace ff

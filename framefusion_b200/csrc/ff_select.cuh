@@ -537,10 +537,13 @@ k_prune_select(PruneGridArgs a) {
     // ---- how many elements equal to / greater than the k-th value sit before this block.  With those two prefixes a
     // row's destination follows directly: kept vision rows before it = (greater before) + min(equal before, need_eq)
     // — ties go to the lowest indices — so neither the selection flags nor a second scan have to cross blocks.
+    // keys are compared under the mask of the digits the passes resolved: the low bits of a bf16 / f16 value are zero,
+    // but float_key() turns them into ones for negative values and NaN
+    const uint32_t kmask = a.n_passes >= 4 ? 0xffffffffu : ~(0xffffffffu >> (8 * a.n_passes));
     int c_eq = 0, c_gt = 0;
     if (!all && !none)
         for (int j = n0 + t; j < n1; j += SEL_THREADS) {
-            const uint32_t key = float_key(vals[j]);
+            const uint32_t key = float_key(vals[j]) & kmask;
             c_eq += key == kth;
             c_gt += key > kth;
         }
@@ -558,7 +561,7 @@ k_prune_select(PruneGridArgs a) {
         const int j = base + t;
         uint32_t key = 0;
         int eq = 0, gt = 0;
-        if (j < n1 && !all && !none) { key = float_key(vals[j]); eq = key == kth; gt = key > kth; }
+        if (j < n1 && !all && !none) { key = float_key(vals[j]) & kmask; eq = key == kth; gt = key > kth; }
         const int ex_eq = carry + block_exclusive_scan(eq, s_scan, &tot);
         carry += tot;
         const int ex_gt = carry_gt + block_exclusive_scan(gt, s_scan, &tot);

@@ -17,11 +17,16 @@ TEXT_TOKEN = -1
 
 
 def _layout(start: int, patch_num: int, image_token_length: int, original_length: int, device):
+    """``[-1]*start + range(patch_num)*n_frames + [-1]*(original_length - end - 1)``, built the way the reference builds it
+    (qwenvl/modeling_qwen2_vl.py:125-127).  If ``image_token_length % patch_num != 0`` that list is SHORTER than the
+    sequence (the tail shifts left) and the reference fails later at ``patch_type[keep_mask]`` (main.py:132); here
+    ``FrameFusion`` raises as soon as it sees the length mismatch, so the same construction is kept."""
     end = start + image_token_length - 1
     n_frames = image_token_length // patch_num
     body = torch.arange(patch_num, dtype=torch.int64).repeat(n_frames)
-    pt = torch.full((1, original_length), TEXT_TOKEN, dtype=torch.int64)
-    pt[0, start:start + body.numel()] = body            # a ragged remainder (length % patch_num) stays text, as in the reference
+    tail = original_length - end - 1
+    pt = torch.cat([torch.full((start,), TEXT_TOKEN, dtype=torch.int64), body,
+                    torch.full((max(tail, 0),), TEXT_TOKEN, dtype=torch.int64)])[None]
     return pt.to(device), patch_num, start, end, image_token_length, original_length
 
 

@@ -121,7 +121,7 @@ class FrameFusion(nn.Module):
         "cost", "similarity_lower_bound", "ratio_lower_bound", "patch_type", "patch_num", "image_token_start_index",
         "image_token_end_index", "image_token_length", "original_length", "finish_merging", "finish_pruning",
         "sparsity_list", "use_fused", "debug_trace", "last_trace", "kernel_events", "_links_for", "_have_order",
-        "_have_lists", "_dev"))
+        "_dev"))
 
     def __setattr__(self, name, value):
         # the operator has no parameters, buffers or sub-modules: skip nn.Module's bookkeeping (it costs ~4 us per
@@ -139,11 +139,11 @@ class FrameFusion(nn.Module):
         self.ratio_lower_bound = ratio_lower_bound
         self._dev = {}                  # torch.device -> _DeviceState
         self._links_for = None          # (patch_type tensor, its _version, device) the workspace links describe
-        self._have_order = False        # the workspace holds the compact by-patch order (the generic kernels need it)
-        self._have_lists = False        # ... and the per-chain lists (the single-pass kernel needs them)
-        # merge-stage kernel choice: False = two-pass path (similarity -> scan -> gather/merge; the faster one at
-        # the time of writing), True = the single-pass streaming kernel (one HBM read of hidden_states)
-        self.use_fused = False
+        self._have_order = False        # the workspace holds the compact by-patch order (the multi-kernel path needs it)
+        # merge-stage kernel choice: True = the read-once kernel (one launch, one HBM read of hidden_states; it falls
+        # back by itself for the top-k branch and for shapes it does not take), False = always the multi-kernel path
+        # (similarity -> scan -> gather/merge)
+        self.use_fused = True
         self.debug_trace = False        # tests: keep what flowed between the stages of the last call
         self.last_trace = None
         self.kernel_events = None       # bench: a list collects (name, start, end) CUDA events around ff_* launches
@@ -190,11 +190,11 @@ class FrameFusion(nn.Module):
             patch_num = patch_num.item()
         return int(math.ceil(float(patch_num)))
 
-    def _ensure_links(self, st: _DeviceState, q_len: int, need_order: bool = False, need_lists: bool = False):
+    def _ensure_links(self, st: _DeviceState, q_len: int, need_order: bool = False):
         pt = self.patch_type
         key = self._links_for
         if key is not None and key[0] is pt and key[1] == pt._version and key[2] == st.device \
-                and (self._have_order or not need_order) and (self._have_lists or not need_lists):
+                and (self._have_order or not need_order):
             return
         if pt.numel() != q_len:
             raise RuntimeError(f"patch_type has {pt.numel()} entries for a sequence of {q_len} tokens")
@@ -205,7 +205,6 @@ class FrameFusion(nn.Module):
         _lib.check(st.lib.ff_build_links(st.ctx, wp, wb, ptc.data_ptr(), q_len, n_ids, _stream(st.device)))
         self._links_for = (pt, pt._version, st.device)
         self._have_order = True
-        self._have_lists = True
 
     def _pos_aux(self, position_embeddings, auxes):
         """Registers the position container's tensors for compaction; returns a closure that rebuilds it."""
@@ -315,8 +314,7 @@ class FrameFusion(nn.Module):
         hidden = hidden_states.contiguous()
         out = torch.empty_like(hidden)
         imp = torch.empty(q_len, dtype=hidden.dtype, device=device) if self.debug_trace else None
-        if st.ws is None:
-            st.workspace(q_len, 0)
+        st.workspace(q_len, 0)                  # only ever grows (a layer-split model may prune on another device)
         wp, wb = st.ws_ptr()
         stream = _stream(device)
         _lib.check(st.lib.ff_prune_layer(
@@ -348,7 +346,7 @@ class FrameFusion(nn.Module):
         self.patch_type = self.patch_type.to(device)
         sparsity_upper_bound = self._compute_pruning_ratio(self.sparsity_list, self.cost)
         fused = 1 if self.use_fused else 0
-        self._ensure_links(st, q_len, need_order=not fused, need_lists=bool(fused))
+        self._ensure_links(st, q_len, need_order=not fused)
 
         dt = hidden_states.dtype
         thr = _threshold_in(self.similarity_lower_bound, dt)                 # the scalar is compared in T
@@ -379,11 +377,23 @@ class FrameFusion(nn.Module):
                 ev.append(("ff_merge_layer", q_len, e0, e1))
             _lib.check(st.lib.ff_stream_sync(st.ctx, stream))
 
-        launch(fused)
+        try:
+            launch(fused)
+        except ValueError:
+            if not fused or self._have_order:
+                raise
+            # the library declined the read-once kernel for this call (row size / alignment) and the previous call left
+            # no by-patch order: rebuild the links, multi-kernel path
+            self._links_for = None
+            self._ensure_links(st, q_len, need_order=True)
+            launch(0)
         status = st.status
         ran_fused = bool(fused) and int(status[_lib.ST_FUSED]) == 1
-        if fused and int(status[_lib.ST_ERROR]) == 3:
-            # the single-pass kernel speculates on the threshold branch; the count says top-k: redo generically
+        if ran_fused and int(status[_lib.ST_INTERNAL]) != 0:
+            raise _lib.FFError("framefusion_b200: a wait inside the read-once merge kernel timed out")
+        if ran_fused and int(status[_lib.ST_ERROR]) == 3:
+            # the read-once kernel speculates on the threshold branch; the count says top-k: redo with the multi-kernel
+            # path (the input is untouched)
             self._links_for = None
             self._ensure_links(st, q_len, need_order=True)
             launch(0)
@@ -406,7 +416,6 @@ class FrameFusion(nn.Module):
             self.finish_pruning = True
 
         self._have_order = not ran_fused
-        self._have_lists = ran_fused
         if self.debug_trace:
             if ran_fused:
                 self._record_fused_trace(st, hidden, q_len)

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FF_ABI_VERSION 1
+#define FF_ABI_VERSION 2
 
 enum ff_dtype { FF_BF16 = 0, FF_F16 = 1, FF_F32 = 2 };
 
@@ -51,9 +51,11 @@ enum ff_status_slot {
     FF_ST_NCHAIN = 3,      /* N: tokens whose patch id is in [0, n_ids)             (main.py:208-214) */
     FF_ST_BRANCH = 4,      /* 0 = threshold branch, 1 = top-k branch                (main.py:116-127) */
     FF_ST_TOPK = 5,        /* k used by the branch that ran (merge top-k or prune top-k) */
-    FF_ST_ERROR = 6,       /* device-side error: 0 ok, 1 n_vis == 0, 2 k > N, 3 fused path declined */
+    FF_ST_ERROR = 6,       /* device-side error: 0 ok, 1 n_vis == 0, 2 k > N, 3 the read-once kernel speculated on the
+                              threshold branch and the count says top-k: call again without flag bit 0 */
     FF_ST_NMERGED = 7,     /* tokens merged away by this call */
-    FF_ST_FUSED = 8,       /* 1 if the single-pass fused kernel produced this result, 0 for the generic path */
+    FF_ST_FUSED = 8,       /* 1 if the read-once kernel produced this result, 0 for the multi-kernel path */
+    FF_ST_INTERNAL = 9,    /* 1 if a wait inside the read-once kernel gave up (the results of the call are invalid) */
     FF_ST_SLOTS = 16
 };
 
@@ -119,7 +121,8 @@ int ff_merge_apply(ff_ctx* ctx, void* ws, int64_t ws_bytes, void* hidden, int dt
  * -> runs -> merged rows -> compaction of hidden and of every aux tensor, and the links for the next call.
  * hidden [S,H] is read only; hidden_out must hold S rows (only S_keep are written).  patch_type is aux[0]
  * by convention of the host wrapper but the library does not care.  status: SEQ_KEEP, COUNT, NVIS, NCHAIN,
- * BRANCH, TOPK, ERROR, NMERGED.  `flags`: bit 0 = allow the single-pass fused kernel. */
+ * BRANCH, TOPK, ERROR, NMERGED, FUSED, INTERNAL.  `flags`: bit 0 = allow the read-once kernel (one launch, one HBM
+ * read of hidden; it handles the threshold branch and reports ERROR = 3 otherwise, leaving hidden untouched). */
 int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, void* hidden_out, int dtype,
                    int64_t seq_len, int64_t hidden_size, double thr, double bound, const ff_aux* aux,
                    int n_aux, int flags, void* stream);
@@ -149,14 +152,10 @@ int ff_compact_mask(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* mask, v
 
 /* ---- introspection of the last merge call (tests, static API): copies device arrays out of `ws` ------
  * what: 0 = keep mask by sequence position (uint8 [S]), 1 = merge flags by by-patch position (uint8 [N]),
- *       2 = sim (T [N]), 3 = order (int64 [N]) */
+ *       2 = sim (T [N] by by-patch position; after a read-once call T [S] by sequence position), 3 = order (int64 [N]);
+ *       1 and 3 exist after a multi-kernel call only */
 int ff_debug_read(ff_ctx* ctx, void* ws, int64_t ws_bytes, int what, void* dst_device, int64_t n, int dtype,
                   void* stream);
-
-/* ---- development aid: time stamps of the single-pass kernel -------------------------------------------
- * buffer_device: n_ids * 96 * 8 int64 (globaltimer ns at eight points in the life of every chain row), or null
- * to switch tracing off.  Not part of the reference-facing surface. */
-int ff_debug_trace(ff_ctx* ctx, void* buffer_device, int64_t bytes, int64_t n_ids);
 
 #ifdef __cplusplus
 }
