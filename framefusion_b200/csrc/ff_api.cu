@@ -81,6 +81,7 @@ struct ff_ctx {
     int fused_attr[3];   // dynamic shared memory the kernel of each dtype was last opted in for
     int sm_count;
     int max_smem;        // opt-in dynamic shared memory per block
+    int smem_per_sm, smem_reserved;   // shared memory of an SM / what the system keeps per resident block
     cudaEvent_t ev_start, ev_stop;   // ff_ctx_timing
     int count_clean[2];  // counters[bank][C_COUNT] is known to be zero (set by the kernel that decided the previous call)
     unsigned bar_base;   // value of the grid-barrier word before the next k_keep_scan (it is not reset between merge calls)
@@ -348,11 +349,14 @@ int check_shape(int64_t S, int64_t H, int dtype) {
     return FF_OK;
 }
 
-// rows per tile (= warps per CTA) of the read-once kernel: two CTAs per SM, two slots per warp; 0 = rows too long
+// shared memory of one CTA of the read-once kernel besides the row slots: mbarriers, tile scratch, the worker queue
+constexpr int FU_SMEM_EXTRA = 8 * FU_WARPS + 64 + (int)sizeof(FusedQueue);
+
+// rows per tile (= tile warps per CTA) of the read-once kernel: two CTAs per SM, two slots per warp; 0 = rows too long
 int fused_tile_rows(const ff_ctx* ctx, int64_t row_bytes) {
     const int64_t slot = (row_bytes + 127) / 128 * 128;
-    const int64_t per_cta = ctx->max_smem / 2 - 1024;      // a resident CTA also pays ~1 KB of system shared memory
-    int64_t w = (per_cta - 256) / (2 * slot);
+    const int64_t per_cta = ctx->smem_per_sm / 2 - ctx->smem_reserved;
+    int64_t w = (per_cta - FU_SMEM_EXTRA) / (2 * slot);
     if (w > FU_WARPS) w = FU_WARPS;
     return w < 2 ? 0 : (int)w;
 }
@@ -362,7 +366,7 @@ int fused_tile_rows(const ff_ctx* ctx, int64_t row_bytes) {
 bool fused_shape_ok(const ff_ctx* ctx, const void* hidden, const void* out, int dtype, int64_t S, int64_t H, double thr) {
     const int64_t row_bytes = H * (dtype == FF_F32 ? 4 : 2);
     if (row_bytes % 16 != 0 || (((uintptr_t)hidden | (uintptr_t)out) & 15) != 0) return false;
-    if (S >= (1ll << 30) - 2) return false;
+    if (S >= (1ll << 24)) return false;                    // tile numbers travel in 24 bits of a queue item
     if (!(thr > -2.0)) return false;
     return fused_tile_rows(ctx, row_bytes) > 0;
 }
@@ -399,7 +403,8 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
     ctx->fused_clean[bank] = 0;
     ctx->fused_clean[nb] = 1;                              // the kernel clears the other bank on its way out
     ctx->h_status[FF_ST_INTERNAL] = 0;
-    const int smem = 2 * a.tile_rows * a.slot_bytes + 256;
+    const int smem = 2 * a.tile_rows * a.slot_bytes + FU_SMEM_EXTRA;
+    const int threads = (a.tile_rows + FU_WORKERS) * 32;
     return dispatch_dtype(dtype, [&](auto dt) {
         constexpr int DT = decltype(dt)::value;
         if (ctx->fused_attr[DT] < smem) {
@@ -407,11 +412,11 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
             ctx->fused_attr[DT] = smem;
         }
         int per_sm = 0;
-        FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_merge<DT>, a.tile_rows * 32, smem));
+        FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_merge<DT>, threads, smem));
         if (per_sm < 1) return fail(FF_E_UNSUPPORTED, "the read-once kernel does not fit an SM (%d bytes of shared memory)", smem);
         int grid = per_sm * ctx->sm_count;
         if (grid > a.ntiles) grid = a.ntiles;
-        FF_LAUNCH("k_fused_merge", k_fused_merge<DT>, grid, a.tile_rows * 32, smem, st, a, ap);
+        FF_LAUNCH("k_fused_merge", k_fused_merge<DT>, grid, threads, smem, st, a, ap);
         return (int)FF_OK;
     });
 }
@@ -453,6 +458,8 @@ int ff_ctx_create(int device, ff_ctx** out) {
     if (e != cudaSuccess) c->sm_count = 148;
     e = cudaDeviceGetAttribute(&c->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) c->max_smem = 48 * 1024;
+    if (cudaDeviceGetAttribute(&c->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device) != cudaSuccess) c->smem_per_sm = c->max_smem;
+    if (cudaDeviceGetAttribute(&c->smem_reserved, cudaDevAttrReservedSharedMemoryPerBlock, device) != cudaSuccess) c->smem_reserved = 1024;
     *out = c;
     return FF_OK;
 }

@@ -37,6 +37,8 @@
 namespace ff {
 
 constexpr int FU_WARPS = 8;                        // most rows per tile = warps per CTA (fewer when the rows are long)
+constexpr int FU_WORKERS = 4;                      // worker warps per CTA
+constexpr int FU_QSIZE = 64;                       // ring entries between the tile warps and the workers
 constexpr int FU_SPIN_LIMIT = 1 << 18;             // polls (~64 ns apart) before a wait gives up and reports FF_ST_INTERNAL
 constexpr unsigned long long FU_AGG = 1ull << 32, FU_INCL = 2ull << 32;
 
@@ -223,29 +225,101 @@ __device__ __forceinline__ int tile_lookback(unsigned long long* D, int tile, in
     return excl;
 }
 
+// ---- hand-over from the tile warps to the worker warps of the same CTA: a ring of 8-byte items in shared memory.
+// Items: a run that needs arithmetic (its last row e, the closing row's destination), or the aux rows of one tile.
+constexpr unsigned long long FU_ITEM_RUN = 1ull << 62, FU_ITEM_AUX = 2ull << 62, FU_ITEM_EXIT = 3ull << 62;
+
+struct FusedQueue {
+    unsigned long long item[FU_QSIZE];
+    unsigned seq[FU_QSIZE];                                 // item[i] of lap n is valid once seq[i] == n + 1
+    unsigned tail, head, freed, pad;
+};
+
+__device__ __forceinline__ void queue_push(FusedQueue* q, unsigned long long item, int* err) {     // one lane
+    const unsigned t = atomicAdd(&q->tail, 1u);
+    int spins = 0;
+    while ((int)(t - *(volatile unsigned*)&q->freed) >= FU_QSIZE) {                  // ring full: the workers are behind
+        if (++spins > FU_SPIN_LIMIT) { *err = 1; break; }
+        __nanosleep(100);
+    }
+    *(volatile unsigned long long*)&q->item[t % FU_QSIZE] = item;
+    __threadfence_block();
+    *(volatile unsigned*)&q->seq[t % FU_QSIZE] = t / FU_QSIZE + 1;
+}
+
+__device__ __forceinline__ unsigned long long queue_pop(FusedQueue* q, int lane) {             // whole warp
+    unsigned h = 0;
+    if (lane == 0) h = atomicAdd(&q->head, 1u);
+    h = __shfl_sync(FULL, h, 0);
+    const unsigned want = h / FU_QSIZE + 1;
+    while (*(volatile unsigned*)&q->seq[h % FU_QSIZE] != want) __nanosleep(200);    // the tile warps always end with EXIT items
+    __threadfence_block();
+    const unsigned long long item = *(volatile unsigned long long*)&q->item[h % FU_QSIZE];
+    __syncwarp();
+    if (lane == 0) atomicAdd(&q->freed, 1u);
+    return item;
+}
+
+__device__ __forceinline__ void tile_barrier(int n_threads) {                       // the tile warps only (named barrier 1)
+    asm volatile("bar.sync 1, %0;" :: "r"(n_threads) : "memory");
+}
+
+// CTA = W tile warps (W rows per tile, two shared-memory slots each) + FU_WORKERS worker warps.
 template <int DT>
-__global__ void __launch_bounds__(FU_WARPS * 32, 2)
+__global__ void __launch_bounds__((FU_WARPS + FU_WORKERS) * 32, 2)
 k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPack aux) {
     extern __shared__ __align__(128) unsigned char fu_smem[];
     pdl_enter();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, W = blockDim.x >> 5;      // W rows per tile (a.tile_rows)
-    // per warp: slot P (chain predecessor) and slot C (own row), one mbarrier for both
-    unsigned char* slot_p = fu_smem + (size_t)(2 * wid) * a.slot_bytes;
-    unsigned char* slot_c = slot_p + a.slot_bytes;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, W = a.tile_rows;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(fu_smem + (size_t)(2 * W) * a.slot_bytes);
     volatile int* s_int = reinterpret_cast<volatile int*>(bars + FU_WARPS);   // [0, W) flags, [8] prefix, [9] next tile
-    const uint32_t sp32 = smem_u32(slot_p), sc32 = smem_u32(slot_c), bar = smem_u32(bars + wid);
-    unsigned long long* D = a.desc + 1;
-    if (lane == 0) mbar_init(bar, 1);
-    if (threadIdx.x == 0) s_int[FU_WARPS + 1] = (int)atomicAdd(a.desc, 1ull);
+    FusedQueue* q = reinterpret_cast<FusedQueue*>(bars + FU_WARPS + 8);
+    if (wid < W && lane == 0) mbar_init(smem_u32(bars + wid), 1);
+    if (threadIdx.x == 0) {
+        s_int[FU_WARPS + 1] = (int)atomicAdd(a.desc, 1ull);
+        q->tail = q->head = q->freed = 0;
+    }
+    for (int i = threadIdx.x; i < FU_QSIZE; i += blockDim.x) q->seq[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    int tile = s_int[FU_WARPS + 1];
-    uint32_t phase = 0;
     int err = 0;
-    bool store_pending = false;                             // lane 0: a bulk store may still be reading a slot
     const int nvec = a.nvec;
     const int64_t row_bytes = a.row_bytes;
+
+    if (wid >= W) {
+        // ---- worker warps: runs that need arithmetic and the aux rows, off the tile warps' critical path
+        while (true) {
+            const unsigned long long item = queue_pop(q, lane);
+            const unsigned long long type = item & (3ull << 62);
+            if (type == FU_ITEM_EXIT) break;
+            if (type == FU_ITEM_RUN) {
+                const int e = (int)((item >> 31) & 0x7fffffffull), closer = (int)(item & 0x7fffffffull) - 1;
+                const unsigned long long st_e = wait_state(a.fstate, e, &err);
+                const int da = emit_merged_run<DT>(a, e, st_e, nullptr, lane, &err);
+                if (lane == 0 && da >= 0) {
+                    a.link_next[da].y = closer;             // -1: the run reached the end of its chain
+                    if (closer >= 0) a.link_next[closer].x = da;
+                }
+            } else {
+                const int tile = (int)((item >> 38) & 0xffffffull), excl = (int)((item >> 8) & 0x3fffffffull);
+                const unsigned mask = (unsigned)(item & 0xffull);
+#pragma unroll 1
+                for (int w = 0; w < W; ++w)
+                    if (mask >> w & 1u) gather_aux_rows(aux, tile * W + w, excl + __popc(mask & ((1u << w) - 1u)), lane);
+            }
+        }
+        if (err && lane == 0) a.status[FF_ST_INTERNAL] = 1;
+        return;
+    }
+
+    // ---- tile warps.  Per warp: slot P (chain predecessor) and slot C (own row), one mbarrier for both
+    unsigned char* slot_p = fu_smem + (size_t)(2 * wid) * a.slot_bytes;
+    unsigned char* slot_c = slot_p + a.slot_bytes;
+    const uint32_t sp32 = smem_u32(slot_p), sc32 = smem_u32(slot_c), bar = smem_u32(bars + wid);
+    unsigned long long* D = a.desc + 1;
+    int tile = s_int[FU_WARPS + 1];
+    uint32_t phase = 0;
+    bool store_pending = false;                             // lane 0: a bulk store may still be reading a slot
 
     while (tile < a.ntiles) {
         const int r = tile * W + wid;
@@ -287,104 +361,106 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             if (valid) a.sim_seq[r] = s;
             s_int[wid] = valid ? flag : 2;
         }
-        __syncthreads();                                    // (A) the tile's flags are in shared memory
+        tile_barrier(W * 32);                               // (A) the tile's flags are in shared memory
         int myrank = 0, total = 0;
+        unsigned keep_mask = 0;
 #pragma unroll
         for (int w = 0; w < FU_WARPS; ++w) {
             const int k = (w < W) && (s_int[w] == 0);
             if (w < wid) myrank += k;
             total += k;
+            keep_mask |= (unsigned)k << w;
         }
         unsigned long long st_p = 0;
         const bool closer = has_pred && !flag;
         if (wid == 0) {
-            int nt = 0;
-            if (lane == 0) nt = (int)atomicAdd(a.desc, 1ull);              // the next tile's ticket travels meanwhile
             const int excl = tile_lookback(D, tile, total, lane, &err);
-            if (lane == 0) { s_int[FU_WARPS] = excl; s_int[FU_WARPS + 1] = nt; }
+            if (lane == 0) s_int[FU_WARPS] = excl;
         } else if (closer) {
             st_p = ld_relaxed64(a.fstate + p);
         }
-        __syncthreads();                                    // (B) prefix and next tile known to every warp
+        tile_barrier(W * 32);                               // (B) the prefix is known to every warp
         const int excl = s_int[FU_WARPS];
-        const int next_tile = s_int[FU_WARPS + 1];
         const int d_r = (valid && !flag) ? excl + myrank : -1;
         if (valid && lane == 0) {
             st_relaxed64(a.fstate + r, ((unsigned long long)(uint32_t)p << 32) | (flag ? 1u : (uint32_t)(d_r + 2)));
             a.dst[r] = d_r;
         }
-        if (tile == a.ntiles - 1 && threadIdx.x == 0) {
-            // the sequence is done: sizes, the speculated branch, the counters of the next call (main.py:112-120)
-            const long long s_keep = excl + total, merged = a.S - s_keep;
-            const long long N = a.counters[C_N], n_vis = a.counters[C_NVIS];
-            int e = 0;
-            if (n_vis == 0) e = 1;                          // the reference divides by zero here (main.py:114)
-            else if (!((double)merged / (double)n_vis < a.bound)) e = 3;   // top-k branch: the host redoes the call
-            a.counters[C_COUNT] = merged;
-            a.counters[C_NNEXT] = N - merged;
-            a.counters[C_SKEEP] = s_keep;
-            a.counters[C_BRANCH] = 0;
-            a.counters[C_K] = 0;
-            a.counters[C_NMERGED] = merged;
-            a.counters_next[C_N] = N - merged;
-            a.counters_next[C_NVIS] = n_vis - merged;
-            a.counters_next[C_COUNT] = 0;
-            a.counters_next[C_TICKET] = 0;
-            a.counters_next[C_TICKET2] = 0;
-            a.status[FF_ST_SEQ_KEEP] = s_keep;
-            a.status[FF_ST_COUNT] = merged;
-            a.status[FF_ST_NVIS] = n_vis;
-            a.status[FF_ST_NCHAIN] = N;
-            a.status[FF_ST_BRANCH] = 0;
-            a.status[FF_ST_TOPK] = 0;
-            a.status[FF_ST_ERROR] = e;
-            a.status[FF_ST_NMERGED] = merged;
-            a.status[FF_ST_FUSED] = 1;
+        int nt = 0;
+        if (threadIdx.x == 0) {
+            nt = (int)atomicAdd(a.desc, 1ull);              // the next tile's ticket travels while this tile is emitted
+            if (aux.n && keep_mask)
+                queue_push(q, FU_ITEM_AUX | ((unsigned long long)tile << 38) | ((unsigned long long)excl << 8) | keep_mask, &err);
+            if (tile == a.ntiles - 1) {
+                // the sequence is done: sizes, the speculated branch, the counters of the next call (main.py:112-120)
+                const long long s_keep = excl + total, merged = a.S - s_keep;
+                const long long N = a.counters[C_N], n_vis = a.counters[C_NVIS];
+                int e = 0;
+                if (n_vis == 0) e = 1;                      // the reference divides by zero here (main.py:114)
+                else if (!((double)merged / (double)n_vis < a.bound)) e = 3;   // top-k branch: the host redoes the call
+                a.counters[C_COUNT] = merged;
+                a.counters[C_NNEXT] = N - merged;
+                a.counters[C_SKEEP] = s_keep;
+                a.counters[C_BRANCH] = 0;
+                a.counters[C_K] = 0;
+                a.counters[C_NMERGED] = merged;
+                a.counters_next[C_N] = N - merged;
+                a.counters_next[C_NVIS] = n_vis - merged;
+                a.counters_next[C_COUNT] = 0;
+                a.counters_next[C_TICKET] = 0;
+                a.counters_next[C_TICKET2] = 0;
+                a.status[FF_ST_SEQ_KEEP] = s_keep;
+                a.status[FF_ST_COUNT] = merged;
+                a.status[FF_ST_NVIS] = n_vis;
+                a.status[FF_ST_NCHAIN] = N;
+                a.status[FF_ST_BRANCH] = 0;
+                a.status[FF_ST_TOPK] = 0;
+                a.status[FF_ST_ERROR] = e;
+                a.status[FF_ST_NMERGED] = merged;
+                a.status[FF_ST_FUSED] = 1;
+            }
         }
         if (closer) {
-            // this row ends the run of its predecessor: emit it
+            // this row ends the run of its predecessor
             if ((uint32_t)st_p == 0u) st_p = wait_state(a.fstate, p, &err);
-            int da = -1;
-            if ((uint32_t)st_p >= 2u) {
-                da = (int)(uint32_t)st_p - 2;               // a plain kept row: the staged copy goes out as it is
-                if (lane == 0) {
+            if (lane == 0) {
+                if ((uint32_t)st_p >= 2u) {                 // a plain kept row: the staged copy goes out as it is
+                    const int da = (int)(uint32_t)st_p - 2;
                     tma_store(a.out + (int64_t)da * row_bytes, sp32, (uint32_t)row_bytes);
                     tma_commit();
                     store_pending = true;
+                    a.link_next[d_r].x = da;
+                    a.link_next[da].y = d_r;
+                } else if ((uint32_t)st_p == 1u) {          // a run with members: a worker warp adds it up
+                    queue_push(q, FU_ITEM_RUN | ((unsigned long long)p << 31) | (unsigned long long)(d_r + 1), &err);
                 }
-            } else if ((uint32_t)st_p == 1u) {
-                da = emit_merged_run<DT>(a, p, st_p, reinterpret_cast<const uint4*>(slot_p), lane, &err);
-            }
-            if (lane == 0 && da >= 0) {
-                a.link_next[d_r].x = da;
-                a.link_next[da].y = d_r;
             }
         }
         if (d_r >= 0 && p < 0 && lane == 0) {               // chain head / not a chain row
             a.link_next[d_r].x = p;
             if (p == -2) a.link_next[d_r].y = -2;
         }
-        if (self_emit) {                                    // nobody comes to close this row's run
-            int da = d_r;
+        if (self_emit && lane == 0) {                       // nobody comes to close this row's run
             if (!flag) {
-                if (lane == 0) {
-                    tma_store(a.out + (int64_t)d_r * row_bytes, sc32, (uint32_t)row_bytes);
-                    tma_commit();
-                    store_pending = true;
-                }
+                tma_store(a.out + (int64_t)d_r * row_bytes, sc32, (uint32_t)row_bytes);
+                tma_commit();
+                store_pending = true;
+                if (p != -2) a.link_next[d_r].y = -1;
             } else {
-                da = emit_merged_run<DT>(a, r, ((unsigned long long)(uint32_t)p << 32) | 1ull,
-                                         reinterpret_cast<const uint4*>(slot_c), lane, &err);
+                queue_push(q, FU_ITEM_RUN | ((unsigned long long)r << 31), &err);
             }
-            if (lane == 0 && da >= 0 && p != -2) a.link_next[da].y = -1;
         }
-        if (d_r >= 0 && aux.n) gather_aux_rows(aux, r, d_r, lane);
-        tile = next_tile;
+        if (threadIdx.x == 0) s_int[FU_WARPS + 1] = nt;
+        tile_barrier(W * 32);
+        tile = s_int[FU_WARPS + 1];
     }
 
+    if (threadIdx.x == 0)
+        for (int i = 0; i < (int)(blockDim.x >> 5) - W; ++i) queue_push(q, FU_ITEM_EXIT, &err);
     // leave the other bank's state words and descriptors zeroed for the next call of the prefill
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.S; i += (int64_t)gridDim.x * blockDim.x) a.fstate_clr[i] = 0ull;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= a.ntiles; i += (int64_t)gridDim.x * blockDim.x) a.desc_clr[i] = 0ull;
+    const int64_t n_thr = (int64_t)gridDim.x * W * 32, me = (int64_t)blockIdx.x * W * 32 + threadIdx.x;
+    for (int64_t i = me; i < a.S; i += n_thr) a.fstate_clr[i] = 0ull;
+    for (int64_t i = me; i <= a.ntiles; i += n_thr) a.desc_clr[i] = 0ull;
     if (err && lane == 0) a.status[FF_ST_INTERNAL] = 1;
     if (lane == 0) tma_wait_all();
 }

@@ -58,6 +58,11 @@ def Qwen2VLSdpaAttention_merge_then_fastv_cost_given_forward(
     if past_key_values is not None:
         key_states, value_states = past_key_values.update(key_states, value_states, self.layer_idx)
 
+    if attention_mask is not None and attention_mask.ndim == 4:
+        # a decode step after a reduced prefill: the 4-D mask was built for layer 0's cache, later layers hold fewer
+        # keys (reference models/qwen2/modeling_qwen2.py:150-152 slices the same way)
+        attention_mask = attention_mask[..., : key_states.shape[-2]]
+
     is_causal = attention_mask is None and q_len > 1
     attn_weights = None
     ff = self.framefusion

@@ -153,6 +153,28 @@ def test_eager_attention_compacts_the_4d_mask(patched_importance):
     assert out.last_hidden_state.shape[1] < wl.seq_len
 
 
+def test_eager_decode_after_a_reduced_prefill(patched_importance):
+    """Eager attention adds the 4-D mask without slicing it: after a reduced prefill the caches of later layers are shorter
+    than layer 0's, which the mask is built for — the attention hook slices it like modeling_qwen2.py:150-152.  The decode
+    step must also equal the sdpa path's (same weights, same caches)."""
+    outs = {}
+    for attn in ("eager", "sdpa"):
+        model = tiny_model(attn)
+        wl = workload()
+        op = OracleOperator(0.3, 0.6, 0.1)
+        install(model, op)
+        with torch.no_grad():
+            model.framefusion.prepare(*wl.prepare_args())
+            out = model.model(inputs_embeds=wl.hidden.clone(), use_cache=True)
+            lens = [out.past_key_values.get_seq_length(i) for i in range(4)]
+            assert lens[0] > lens[-1]                          # ragged: the case the slicing is for
+            torch.manual_seed(1)
+            step = model.model(inputs_embeds=torch.randn(1, 1, 64), past_key_values=out.past_key_values, use_cache=True)
+        outs[attn] = step.last_hidden_state
+        assert [step.past_key_values.get_seq_length(i) for i in range(4)] == [l + 1 for l in lens]
+    assert torch.allclose(outs["eager"], outs["sdpa"], rtol=1e-4, atol=1e-5)
+
+
 def test_unsupported_model_raises_like_the_reference(capsys):
     from framefusion_b200.interface import apply_framefusion
     with pytest.raises(NotImplementedError):

@@ -1,0 +1,9 @@
+#!/bin/bash
+# Short gpurun call while tuning the read-once kernel: its parity cases, timing, launch list, one full ncu capture.
+TAG=${1:-x}
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_cuda_parity.py tests/test_cuda_large.py -x -q -k "fused" 2>&1 | tail -4 | tee gpurun_out/pytest_fused_$TAG.txt
+for c in C2 C3 C4; do timeout 120 python tools/time_merge.py --cfg $c --fused 1 2>&1 | tail -1; done | tee gpurun_out/time_merge_$TAG.txt
+timeout 120 python tools/time_merge.py --cfg C2 --fused 1 --calls 4 2>&1 | tail -1 | tee -a gpurun_out/time_merge_$TAG.txt
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_fused_merge -s 3 -c 1 -o gpurun_out/prof_fused_$TAG python tools/time_merge.py --cfg C2 --fused 1 --iters 2 > gpurun_out/ncu_full.log 2>&1
+tail -1 gpurun_out/ncu_full.log
