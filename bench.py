@@ -125,75 +125,90 @@ def run_step(ff, wl, hidden, cos, sin, q_last, keys, importance_fn):
     return h, pos
 
 
-def reference_arm(args, cfg, rank, world):
-    """The reference's algorithm on the host cores (torch-CPU port, all threads) — rank 0 only."""
-    if rank != 0:
-        return
+def bench_config(cfg, seq_len):
+    """The ``config`` object of the JSON line — the same keys and values in both arms."""
+    return {"workload": workload_name(cfg), "seq_len": seq_len,
+            "calls_per_step": "merge, merge (closes merging), importance, prune",
+            "l2": "inputs (264 MB at C2) exceed the 126 MB L2; no explicit flush"}
+
+
+def cpu_operator(c):
+    """The reference's own CPU implementation of the path: the UNMODIFIED ``framefusion/main.py`` when a copy can be found
+    (``oracle/ref_locate.py``: $FF_REFERENCE_DIR -> /root/reference -> baseline/_ref), else the torch-CPU port of it.
+    Returns ``(make_operator, importance_fn, kind, what)``."""
+    from oracle import ref_locate
+    found = ref_locate.load_reference_operator()
+    if found is not None:
+        cls, sdpa, where = found
+        return (lambda: cls(c["cost"], c["slb"], c["rlb"]),
+                lambda qq, kk: sdpa(qq, kk, kk, num=1, is_causal=True, enable_gqa=True),   # value: the function repeats it, never reads it
+                "reference", f"unmodified framefusion/main.py + utils.scaled_dot_product_attention from {where}")
     from oracle import ff_torch_port as port
-    c = synth.CONFIGS[cfg]
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    frames = c["frames"]
-    wl = synth.make_workload(frames, c["patch_num"], c["hidden"], c["dtype"], seed=0)
-    q, k = synth.make_attention_inputs(wl.seq_len, N_HEADS, N_KV_HEADS, HEAD_DIM, c["dtype"], seed=0)
-    q_last = q[:, :, -1:, :].contiguous()
-
-    def step():
-        ff = port.TorchPortFrameFusion(c["cost"], c["slb"], c["rlb"])
-        # the operator merges in place (main.py:304-317): every repetition gets a fresh copy, outside nothing
-        h = wl.hidden.clone()
-        return run_step(ff, wl, h, wl.cos, wl.sin, q_last, k,
-                        lambda qq, kk: port.last_query_attention(qq, kk, num=1, is_causal=True))
-
-    t0 = time.perf_counter()
-    step()
-    est = time.perf_counter() - t0
-    steps, warm = args.steps, args.warmup
-    budget = 150.0
-    if est * (steps + warm) > budget:          # keep the whole arm within a few minutes
-        steps = max(3, int(budget / est) - warm)
-    for _ in range(max(warm - 1, 0)):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = time.perf_counter() - t0
-    val = wl.n_vision * steps / dt
-    sample = f"{steps} full steps of the {cfg} workload ({wl.n_vision} vision tokens each), torch {torch.__version__} CPU"
-    line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": workload_name(cfg), "host_threads": cores},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line), flush=True)
+    return (lambda: port.TorchPortFrameFusion(c["cost"], c["slb"], c["rlb"]),
+            lambda qq, kk: port.last_query_attention(qq, kk, num=1, is_causal=True),
+            "port", "oracle/ff_torch_port.py (no copy of the reference found)")
 
 
-def cpu_baseline(cfg, seconds=12.0):
-    from oracle import ff_torch_port as port
+def cpu_steps(cfg, n_steps=None, seconds=None, warm=1):
+    """Times full steps of the CPU operator on all host cores.  The operator merges in place (main.py:304-317), so every
+    step gets a fresh copy of the input — made OUTSIDE the timed span (it is not work the reference does per prefill)."""
     c = synth.CONFIGS[cfg]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     wl = synth.make_workload(c["frames"], c["patch_num"], c["hidden"], c["dtype"], seed=0)
     q, k = synth.make_attention_inputs(wl.seq_len, N_HEADS, N_KV_HEADS, HEAD_DIM, c["dtype"], seed=0)
     q_last = q[:, :, -1:, :].contiguous()
+    make, imp, kind, what = cpu_operator(c)
 
     def step():
-        ff = port.TorchPortFrameFusion(c["cost"], c["slb"], c["rlb"])
-        return run_step(ff, wl, wl.hidden.clone(), wl.cos, wl.sin, q_last, k,
-                        lambda qq, kk: port.last_query_attention(qq, kk, num=1, is_causal=True))
+        h = wl.hidden.clone()
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            run_step(make(), wl, h, wl.cos, wl.sin, q_last, k, imp)
+        return time.perf_counter() - t0
 
-    step()
-    n, t0 = 0, time.perf_counter()
-    while n < 3 or (time.perf_counter() - t0 < seconds and n < 200):
+    est = step()
+    for _ in range(max(warm - 1, 0)):
         step()
-        n += 1
-    dt = time.perf_counter() - t0
-    return {"value": wl.n_vision * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} full steps of the {cfg} workload on torch {torch.__version__} CPU, {dt:.1f} s"}
+    spent, n = 0.0, 0
+    if n_steps is not None:
+        budget = 150.0                                       # keep the whole arm within a few minutes
+        if est * n_steps > budget:
+            n_steps = max(3, int(budget / est))
+        while n < n_steps:
+            spent += step()
+            n += 1
+    else:
+        while n < 3 or (spent < seconds and n < 200):
+            spent += step()
+            n += 1
+    return {"value": wl.n_vision * n / spent, "steps": n, "seconds": spent, "cores": cores, "kind": kind, "what": what,
+            "seq_len": wl.seq_len, "n_vision": wl.n_vision}
+
+
+def reference_arm(args, cfg, rank, world):
+    """The reference's own path on the host cores, all threads — rank 0 only."""
+    if rank != 0:
+        return
+    r = cpu_steps(cfg, n_steps=args.steps, warm=max(args.warmup, 1))
+    sample = (f"{r['steps']} full steps of the {cfg} workload ({r['n_vision']} vision tokens each), {r['what']}, "
+              f"torch {torch.__version__} CPU, {r['cores']} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
+        "warmup": max(args.warmup, 1), "ms_per_step": r["seconds"] / r["steps"] * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": bench_config(cfg, r["seq_len"]),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(cfg, seconds=12.0):
+    r = cpu_steps(cfg, seconds=seconds)
+    return {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+            "sample": f"{r['steps']} full steps of the {cfg} workload, {r['what']}, torch {torch.__version__} CPU, {r['seconds']:.1f} s"}
 
 
 def torch_gpu_port(cfg, device, steps=10):

@@ -13,18 +13,24 @@
 //     shared-memory slots — no registers are tied up while the rows travel.  Three row sums out of shared memory, warp
 //     shuffles, the reference's rounding chain -> sim, flag.
 //   * compacted position = kept rows before it: tile aggregate + decoupled look-back over the tile descriptors
-//     (one warp per tile), then one 8-byte state word per row is published: (pred << 32) | code with
-//     code = 1 (merged away) or 2 + destination row.
-//   * the CLOSING row emits: a row that is NOT flagged ends the run of its predecessor.  In the common case the
-//     predecessor is a plain kept row: its state word gives the destination and the staged copy leaves shared memory
-//     with one TMA bulk store — no second read, no registers.  If the predecessor was merged away, the warp walks
-//     the state words back to the anchor, adds the run members in chain order with one rounding to T per add (the
-//     order torch-CPU index_add_ uses, main.py:304-311; the last member is the staged row), divides once by T(L+1)
-//     (main.py:314-317) and stores the result at the anchor's destination.  Chain tails close their own run.
-//     Every dependency points to a row with a SMALLER sequence index, tickets are taken in order by CTAs that are
-//     running, so the lowest unfinished tile never waits: no deadlock, whatever is resident.
-//   * the links of the next call (pred / succ of every kept row, by destination index) fall out of the same walk:
+//     (one warp per tile), then one 8-byte state word per row is published: kept + destination row, or merged away +
+//     (destination row of the run's anchor, members so far).
+//   * runs are accumulated IN the output: a merged-away row r adds itself to the running sum of its run, which lives
+//     in the anchor's destination row — T(acc + r) with one rounding to T per add, in chain order, exactly the
+//     sequence torch-CPU index_add_ performs (main.py:304-311); nothing is lost by parking the sum in a row of T
+//     because every partial sum is a value of T already.  Its state word carries (anchor destination, members so
+//     far), so the next row of the chain needs no walk.  The first member finds both operands in its two slots; a
+//     later one fetches the running sum (an L2 hit, by TMA, while the look-back runs).
+//   * the CLOSING row finishes: a row that is NOT flagged ends the run of its predecessor.  Predecessor a plain kept
+//     row (the common case): its staged copy leaves shared memory with one TMA bulk store — no second read, no
+//     registers.  Predecessor merged away: the running sum is divided once by T(L+1) (main.py:314-317) in place.
+//     Chain tails close their own run.  Every dependency points to a row with a SMALLER sequence index, tickets are
+//     taken in order by CTAs that are running, so the lowest unfinished tile never waits: no deadlock, whatever is
+//     resident.
+//   * the links of the next call (pred / succ of every kept row, by destination index) fall out of the same step:
 //     the closer knows both ends.
+//   * the aux rows (cos / sin / patch_type / position ids) of a tile are copied by worker warps of the same CTA, fed
+//     through a small ring in shared memory: their latency never sits on the tile warps' path.
 //
 // The branch decision (main.py:114-116) needs the global count, known only at the end: the kernel speculates on the
 // threshold branch, the CTA of the last tile checks count / n_vis < bound and otherwise reports FF_ST_ERROR = 3; the
@@ -107,7 +113,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 __device__ __forceinline__ unsigned long long wait_state(const unsigned long long* fstate, int x, int* err) {
     unsigned long long v = ld_relaxed64(fstate + x);
     int spins = 0;
-    while ((uint32_t)v == 0u) {
+    while ((v & 3ull) == 0ull) {
         if (++spins > FU_SPIN_LIMIT) { *err = 1; break; }
         __nanosleep(64);
         v = ld_relaxed64(fstate + x);
@@ -139,68 +145,23 @@ __device__ __forceinline__ void copy_row(const char* src, char* dst, int nvec, i
     }
 }
 
-// The run that ends at the merged-away row e (state word st_e, code 1): walks the state words back to the anchor, adds
-// the members in chain order — T(acc + member) per add, main.py:304-311 —, divides by T(L + 1) (main.py:314-317) and
-// writes the anchor's destination row.  slot_row: row e staged in shared memory, or null (then it is read like the
-// others).  Returns the anchor's destination row, -1 if a wait timed out.
-template <int DT>
-__device__ __noinline__ int emit_merged_run(const FusedArgs& a, int e, unsigned long long st_e, const uint4* slot_row,
-                                            int lane, int* err) {
-    int L = 0, x = e, mine = -1;
-    unsigned long long st = st_e;
-    while ((uint32_t)st == 1u) {
-        if (lane == (L & 31)) mine = x;                     // lane k keeps the k-th member from the end (runs up to 32)
-        ++L;
-        x = (int)(st >> 32);
-        st = wait_state(a.fstate, x, err);
-    }
-    if ((uint32_t)st < 2u) { *err = 1; return -1; }
-    const int anchor = x, da = (int)(uint32_t)st - 2;
-    const Divider<DT> dv(L + 1);
-    const int64_t row_bytes = a.row_bytes;
-    const char* arow = a.hidden + (int64_t)anchor * row_bytes;
-    char* orow = a.out + (int64_t)da * row_bytes;
-#pragma unroll 1
-    for (int vb = 0; vb < a.nvec; vb += 128) {              // warp-uniform trip count: the loop body shuffles
-        const int v0 = vb + lane;
-        uint4 acc[4], xv[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (v0 + 32 * q < a.nvec) acc[q] = ldg16(arow + (int64_t)(v0 + 32 * q) * 16);
-        int walk = anchor;
-#pragma unroll 1
-        for (int m = L - 1; m >= 0; --m) {                  // m = L - 1: first member behind the anchor ... m = 0: row e
-            int idx;
-            if (L <= 32) idx = __shfl_sync(FULL, mine, m);
-            else { walk = __ldg(&a.link[walk].y); idx = walk; }      // longer runs: follow the successor links
-            if (m == 0 && slot_row) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (v0 + 32 * q < a.nvec) xv[q] = slot_row[v0 + 32 * q];
-            } else {
-                const char* mr = a.hidden + (int64_t)idx * row_bytes;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (v0 + 32 * q < a.nvec) xv[q] = ldg16(mr + (int64_t)(v0 + 32 * q) * 16);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (v0 + 32 * q < a.nvec) acc[q] = Num<DT>::add_vec(acc[q], xv[q]);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (v0 + 32 * q < a.nvec) st_stream16(orow + (int64_t)(v0 + 32 * q) * 16, dv.vec_fast(acc[q]));
-    }
-    return da;
+// state word of a row: bits [1:0] 0 = not yet known, 1 = merged away, 2 = kept; bits [33:2] destination row (of the row
+// itself if kept, of its run's anchor if merged away); bits [63:34] members of the run so far (merged away only)
+__device__ __forceinline__ unsigned long long state_kept(int d) { return 2ull | ((unsigned long long)(uint32_t)d << 2); }
+__device__ __forceinline__ unsigned long long state_merged(int d_anchor, int L) {
+    return 1ull | ((unsigned long long)(uint32_t)d_anchor << 2) | ((unsigned long long)(uint32_t)L << 34);
 }
+__device__ __forceinline__ int state_type(unsigned long long st) { return (int)(st & 3ull); }
+__device__ __forceinline__ int state_dst(unsigned long long st) { return (int)(uint32_t)(st >> 2); }
+__device__ __forceinline__ int state_len(unsigned long long st) { return (int)(st >> 34); }
 
-// exclusive prefix of the tile's kept-row count over all earlier tiles (decoupled look-back, one warp)
+// Decoupled look-back over the tile descriptors (one warp per tile): the tile's kept-row count is posted first, before
+// the warp waits for anything, then the exclusive prefix over all earlier tiles is resolved.
+__device__ __forceinline__ void tile_post(unsigned long long* D, int tile, int total, int lane) {
+    if (lane == 0) st_relaxed64(D + tile, (tile == 0 ? FU_INCL : FU_AGG) | (unsigned)total);
+}
 __device__ __forceinline__ int tile_lookback(unsigned long long* D, int tile, int total, int lane, int* err) {
-    if (tile == 0) {
-        if (lane == 0) st_relaxed64(D, FU_INCL | (unsigned)total);
-        return 0;
-    }
-    if (lane == 0) st_relaxed64(D + tile, FU_AGG | (unsigned)total);
+    if (tile == 0) return 0;
     int excl = 0, base = tile - 1, spins = 0;
     while (true) {
         const int idx = base - lane;
@@ -226,8 +187,8 @@ __device__ __forceinline__ int tile_lookback(unsigned long long* D, int tile, in
 }
 
 // ---- hand-over from the tile warps to the worker warps of the same CTA: a ring of 8-byte items in shared memory.
-// Items: a run that needs arithmetic (its last row e, the closing row's destination), or the aux rows of one tile.
-constexpr unsigned long long FU_ITEM_RUN = 1ull << 62, FU_ITEM_AUX = 2ull << 62, FU_ITEM_EXIT = 3ull << 62;
+// Items: the aux rows of one tile (tile number, its exclusive prefix, the mask of its kept rows).
+constexpr unsigned long long FU_ITEM_AUX = 2ull << 62, FU_ITEM_EXIT = 3ull << 62;
 
 struct FusedQueue {
     unsigned long long item[FU_QSIZE];
@@ -287,28 +248,16 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
     const int64_t row_bytes = a.row_bytes;
 
     if (wid >= W) {
-        // ---- worker warps: runs that need arithmetic and the aux rows, off the tile warps' critical path
+        // ---- worker warps: the aux rows, off the tile warps' critical path
         while (true) {
             const unsigned long long item = queue_pop(q, lane);
-            const unsigned long long type = item & (3ull << 62);
-            if (type == FU_ITEM_EXIT) break;
-            if (type == FU_ITEM_RUN) {
-                const int e = (int)((item >> 31) & 0x7fffffffull), closer = (int)(item & 0x7fffffffull) - 1;
-                const unsigned long long st_e = wait_state(a.fstate, e, &err);
-                const int da = emit_merged_run<DT>(a, e, st_e, nullptr, lane, &err);
-                if (lane == 0 && da >= 0) {
-                    a.link_next[da].y = closer;             // -1: the run reached the end of its chain
-                    if (closer >= 0) a.link_next[closer].x = da;
-                }
-            } else {
-                const int tile = (int)((item >> 38) & 0xffffffull), excl = (int)((item >> 8) & 0x3fffffffull);
-                const unsigned mask = (unsigned)(item & 0xffull);
+            if ((item & (3ull << 62)) == FU_ITEM_EXIT) break;
+            const int tile = (int)((item >> 38) & 0xffffffull), excl = (int)((item >> 8) & 0x3fffffffull);
+            const unsigned mask = (unsigned)(item & 0xffull);
 #pragma unroll 1
-                for (int w = 0; w < W; ++w)
-                    if (mask >> w & 1u) gather_aux_rows(aux, tile * W + w, excl + __popc(mask & ((1u << w) - 1u)), lane);
-            }
+            for (int w = 0; w < W; ++w)
+                if (mask >> w & 1u) gather_aux_rows(aux, tile * W + w, excl + __popc(mask & ((1u << w) - 1u)), lane);
         }
-        if (err && lane == 0) a.status[FF_ST_INTERNAL] = 1;
         return;
     }
 
@@ -337,6 +286,9 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             tma_load(sc32, a.hidden + (int64_t)r * row_bytes, (uint32_t)row_bytes, bar);
             if (has_pred) tma_load(sp32, a.hidden + (int64_t)p * row_bytes, (uint32_t)row_bytes, bar);
         }
+        // the predecessor's state word was published a few microseconds ago (its tile is ~P / W tiles back): ask now
+        unsigned long long st_p = 0;
+        if (has_pred) st_p = ld_relaxed64(a.fstate + p);
         if (valid) prefetch_aux(aux, r, lane);
         float s = -2.0f;                                    // IGNORE_TOKEN at chain heads (main.py:225-238)
         int flag = 0;
@@ -344,9 +296,9 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             mbar_wait(bar, phase);
             phase ^= 1u;
         }
+        const uint4* pr = reinterpret_cast<const uint4*>(slot_p);
+        const uint4* cr = reinterpret_cast<const uint4*>(slot_c);
         if (has_pred) {
-            const uint4* pr = reinterpret_cast<const uint4*>(slot_p);
-            const uint4* cr = reinterpret_cast<const uint4*>(slot_c);
             float dot = 0.f, na = 0.f, nb = 0.f;
 #pragma unroll 4
             for (int vb = 0; vb < nvec; vb += 32)           // lane l sums vectors l, l + 32, ... in this order (as k_similarity)
@@ -371,24 +323,31 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             total += k;
             keep_mask |= (unsigned)k << w;
         }
-        unsigned long long st_p = 0;
-        const bool closer = has_pred && !flag;
+        if (wid == 0) tile_post(D, tile, total, lane);      // before this warp waits for anything
+        if (has_pred && state_type(st_p) == 0) st_p = wait_state(a.fstate, p, &err);
+        const bool p_merged = has_pred && state_type(st_p) == 1;
+        if (p_merged && lane == 0) {
+            // the predecessor is inside a run: its raw row has served (the similarity); fetch the running sum of the run
+            // — the anchor's destination row, written by the predecessor's warp before it published — into slot P
+            __threadfence();                                // acquire: the state word was read with a relaxed load
+            asm volatile("fence.proxy.async;" ::: "memory");   // ... and the row is fetched through the async proxy
+            mbar_expect_tx(bar, (uint32_t)row_bytes);
+            tma_load(sp32, a.out + (int64_t)state_dst(st_p) * row_bytes, (uint32_t)row_bytes, bar);
+        }
         if (wid == 0) {
-            const int excl = tile_lookback(D, tile, total, lane, &err);
-            if (lane == 0) s_int[FU_WARPS] = excl;
-        } else if (closer) {
-            st_p = ld_relaxed64(a.fstate + p);
+            const int ex = tile_lookback(D, tile, total, lane, &err);
+            if (lane == 0) s_int[FU_WARPS] = ex;
         }
         tile_barrier(W * 32);                               // (B) the prefix is known to every warp
         const int excl = s_int[FU_WARPS];
         const int d_r = (valid && !flag) ? excl + myrank : -1;
         if (valid && lane == 0) {
-            st_relaxed64(a.fstate + r, ((unsigned long long)(uint32_t)p << 32) | (flag ? 1u : (uint32_t)(d_r + 2)));
+            if (!flag) st_relaxed64(a.fstate + r, state_kept(d_r));
             a.dst[r] = d_r;
         }
         int nt = 0;
         if (threadIdx.x == 0) {
-            nt = (int)atomicAdd(a.desc, 1ull);              // the next tile's ticket travels while this tile is emitted
+            nt = (int)atomicAdd(a.desc, 1ull);              // the next tile's ticket travels while this tile is finished
             if (aux.n && keep_mask)
                 queue_push(q, FU_ITEM_AUX | ((unsigned long long)tile << 38) | ((unsigned long long)excl << 8) | keep_mask, &err);
             if (tile == a.ntiles - 1) {
@@ -420,34 +379,66 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
                 a.status[FF_ST_FUSED] = 1;
             }
         }
-        if (closer) {
-            // this row ends the run of its predecessor
-            if ((uint32_t)st_p == 0u) st_p = wait_state(a.fstate, p, &err);
-            if (lane == 0) {
-                if ((uint32_t)st_p >= 2u) {                 // a plain kept row: the staged copy goes out as it is
-                    const int da = (int)(uint32_t)st_p - 2;
-                    tma_store(a.out + (int64_t)da * row_bytes, sp32, (uint32_t)row_bytes);
-                    tma_commit();
-                    store_pending = true;
-                    a.link_next[d_r].x = da;
-                    a.link_next[da].y = d_r;
-                } else if ((uint32_t)st_p == 1u) {          // a run with members: a worker warp adds it up
-                    queue_push(q, FU_ITEM_RUN | ((unsigned long long)p << 31) | (unsigned long long)(d_r + 1), &err);
+        if (p_merged) {
+            mbar_wait(bar, phase);                          // the running sum is in slot P
+            phase ^= 1u;
+        }
+        if (has_pred && state_type(st_p) != 0) {
+            const int d_a = state_dst(st_p);                // destination row of the run's anchor (the predecessor itself if kept)
+            const int L_p = p_merged ? state_len(st_p) : 0;
+            char* orow = a.out + (int64_t)d_a * row_bytes;
+            if (!flag) {
+                // this row ends the run of its predecessor
+                if (!p_merged) {                            // a plain kept row: the staged copy goes out as it is
+                    if (lane == 0) {
+                        tma_store(orow, sp32, (uint32_t)row_bytes);
+                        tma_commit();
+                        store_pending = true;
+                    }
+                } else {                                    // T(sum / T(L + 1)), main.py:314-317
+                    const Divider<DT> dv(L_p + 1);
+#pragma unroll 2
+                    for (int vb = 0; vb < nvec; vb += 32)
+                        if (vb + lane < nvec) st_stream16(orow + (int64_t)(vb + lane) * 16, dv.vec_fast(pr[vb + lane]));
+                }
+                if (lane == 0) {
+                    a.link_next[d_r].x = d_a;
+                    a.link_next[d_a].y = d_r;
+                }
+            } else {
+                // this row is merged away: T(sum + row), main.py:304-311; slot P holds the sum so far (the anchor's raw row
+                // if this is the first member)
+                const int L = L_p + 1;
+                if (sc < 0) {                               // ... and the chain ends here: finish the run as well
+                    const Divider<DT> dv(L + 1);
+#pragma unroll 2
+                    for (int vb = 0; vb < nvec; vb += 32)
+                        if (vb + lane < nvec)
+                            st_stream16(orow + (int64_t)(vb + lane) * 16, dv.vec_fast(Num<DT>::add_vec(pr[vb + lane], cr[vb + lane])));
+                    if (lane == 0) a.link_next[d_a].y = -1;
+                } else {
+#pragma unroll 2
+                    for (int vb = 0; vb < nvec; vb += 32)
+                        if (vb + lane < nvec)
+                            st_stream16(orow + (int64_t)(vb + lane) * 16, Num<DT>::add_vec(pr[vb + lane], cr[vb + lane]));
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();                        // the sum is visible before the state word that announces it
+                    st_relaxed64(a.fstate + r, state_merged(d_a, L));
                 }
             }
         }
-        if (d_r >= 0 && p < 0 && lane == 0) {               // chain head / not a chain row
-            a.link_next[d_r].x = p;
-            if (p == -2) a.link_next[d_r].y = -2;
-        }
-        if (self_emit && lane == 0) {                       // nobody comes to close this row's run
-            if (!flag) {
+        if (d_r >= 0 && lane == 0) {
+            if (p < 0) {                                    // chain head / not a chain row
+                a.link_next[d_r].x = p;
+                if (p == -2) a.link_next[d_r].y = -2;
+            }
+            if (self_emit) {                                // an unmerged row nobody comes to close: it writes itself
                 tma_store(a.out + (int64_t)d_r * row_bytes, sc32, (uint32_t)row_bytes);
                 tma_commit();
                 store_pending = true;
                 if (p != -2) a.link_next[d_r].y = -1;
-            } else {
-                queue_push(q, FU_ITEM_RUN | ((unsigned long long)r << 31), &err);
             }
         }
         if (threadIdx.x == 0) s_int[FU_WARPS + 1] = nt;
