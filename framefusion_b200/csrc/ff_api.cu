@@ -350,7 +350,7 @@ int check_shape(int64_t S, int64_t H, int dtype) {
 }
 
 // shared memory of one CTA of the read-once kernel besides the row slots: mbarriers, tile scratch, the worker queue
-constexpr int FU_SMEM_EXTRA = 8 * FU_WARPS + 64 + (int)sizeof(FusedQueue);
+constexpr int FU_SMEM_EXTRA = (int)sizeof(FusedShared);
 
 // rows per tile (= tile warps per CTA) of the read-once kernel: two CTAs per SM, two slots per warp; 0 = rows too long
 int fused_tile_rows(const ff_ctx* ctx, int64_t row_bytes) {

@@ -43,8 +43,9 @@
 namespace ff {
 
 constexpr int FU_WARPS = 8;                        // most rows per tile = warps per CTA (fewer when the rows are long)
-constexpr int FU_WORKERS = 4;                      // worker warps per CTA
-constexpr int FU_QSIZE = 64;                       // ring entries between the tile warps and the workers
+constexpr int FU_WORKERS = 4;                      // warps per CTA besides the tile warps: one scan warp + aux workers
+constexpr int FU_QSIZE = 32;                       // ring entries between the scan warp and the aux workers
+constexpr int FU_SCANQ = 8;                        // ring entries between the tile warps and the scan warp
 constexpr int FU_SPIN_LIMIT = 1 << 18;             // polls (~64 ns apart) before a wait gives up and reports FF_ST_INTERNAL
 constexpr unsigned long long FU_AGG = 1ull << 32, FU_INCL = 2ull << 32;
 
@@ -186,14 +187,23 @@ __device__ __forceinline__ int tile_lookback(unsigned long long* D, int tile, in
     return excl;
 }
 
-// ---- hand-over from the tile warps to the worker warps of the same CTA: a ring of 8-byte items in shared memory.
-// Items: the aux rows of one tile (tile number, its exclusive prefix, the mask of its kept rows).
-constexpr unsigned long long FU_ITEM_AUX = 2ull << 62, FU_ITEM_EXIT = 3ull << 62;
+// ---- shared memory behind the row slots: the hand-over rings between the three kinds of warps of a CTA
+//   tile warps --(tile, kept / merged masks)--> scan warp --(tile, prefix, kept mask)--> aux workers
+constexpr unsigned long long FU_ITEM_TILE = 1ull << 62, FU_ITEM_AUX = 2ull << 62, FU_ITEM_EXIT = 3ull << 62;
 
-struct FusedQueue {
+struct FusedQueue {                                         // one producer lane, several consumer warps
     unsigned long long item[FU_QSIZE];
     unsigned seq[FU_QSIZE];                                 // item[i] of lap n is valid once seq[i] == n + 1
     unsigned tail, head, freed, pad;
+};
+
+struct FusedShared {
+    unsigned long long bars[FU_WARPS];                      // one mbarrier per tile warp
+    int flags[2][FU_WARPS];                                 // per iteration parity: 0 kept, 1 merged away, 2 no row
+    int next_tile[2], next_iter[2];                         // the ticket of the next tile, valid once next_iter == iteration + 1
+    unsigned long long scan_item[FU_SCANQ];                 // tile warps (thread 0) -> scan warp
+    unsigned scan_tail, scan_head;
+    FusedQueue auxq;                                        // scan warp -> aux workers
 };
 
 __device__ __forceinline__ void queue_push(FusedQueue* q, unsigned long long item, int* err) {     // one lane
@@ -213,7 +223,7 @@ __device__ __forceinline__ unsigned long long queue_pop(FusedQueue* q, int lane)
     if (lane == 0) h = atomicAdd(&q->head, 1u);
     h = __shfl_sync(FULL, h, 0);
     const unsigned want = h / FU_QSIZE + 1;
-    while (*(volatile unsigned*)&q->seq[h % FU_QSIZE] != want) __nanosleep(200);    // the tile warps always end with EXIT items
+    while (*(volatile unsigned*)&q->seq[h % FU_QSIZE] != want) __nanosleep(200);    // the producer always ends with EXIT items
     __threadfence_block();
     const unsigned long long item = *(volatile unsigned long long*)&q->item[h % FU_QSIZE];
     __syncwarp();
@@ -225,32 +235,33 @@ __device__ __forceinline__ void tile_barrier(int n_threads) {                   
     asm volatile("bar.sync 1, %0;" :: "r"(n_threads) : "memory");
 }
 
-// CTA = W tile warps (W rows per tile, two shared-memory slots each) + FU_WORKERS worker warps.
+// CTA = W tile warps (W rows per tile, two shared-memory slots each) + one scan warp + FU_WORKERS - 1 aux workers.
 template <int DT>
 __global__ void __launch_bounds__((FU_WARPS + FU_WORKERS) * 32, 2)
 k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPack aux) {
     extern __shared__ __align__(128) unsigned char fu_smem[];
     pdl_enter();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, W = a.tile_rows;
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(fu_smem + (size_t)(2 * W) * a.slot_bytes);
-    volatile int* s_int = reinterpret_cast<volatile int*>(bars + FU_WARPS);   // [0, W) flags, [8] prefix, [9] next tile
-    FusedQueue* q = reinterpret_cast<FusedQueue*>(bars + FU_WARPS + 8);
-    if (wid < W && lane == 0) mbar_init(smem_u32(bars + wid), 1);
+    FusedShared* sh = reinterpret_cast<FusedShared*>(fu_smem + (size_t)(2 * W) * a.slot_bytes);
+    unsigned long long* D = a.desc + 1;
+    if (wid < W && lane == 0) mbar_init(smem_u32(&sh->bars[wid]), 1);
     if (threadIdx.x == 0) {
-        s_int[FU_WARPS + 1] = (int)atomicAdd(a.desc, 1ull);
-        q->tail = q->head = q->freed = 0;
+        sh->next_tile[0] = (int)atomicAdd(a.desc, 1ull);
+        sh->next_iter[0] = sh->next_iter[1] = 0;
+        sh->scan_tail = sh->scan_head = 0;
+        sh->auxq.tail = sh->auxq.head = sh->auxq.freed = 0;
     }
-    for (int i = threadIdx.x; i < FU_QSIZE; i += blockDim.x) q->seq[i] = 0;
+    for (int i = threadIdx.x; i < FU_QSIZE; i += blockDim.x) sh->auxq.seq[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     int err = 0;
     const int nvec = a.nvec;
     const int64_t row_bytes = a.row_bytes;
 
-    if (wid >= W) {
-        // ---- worker warps: the aux rows, off the tile warps' critical path
+    if (wid > W) {
+        // ---- aux workers: the aux rows of a tile, off everybody's critical path
         while (true) {
-            const unsigned long long item = queue_pop(q, lane);
+            const unsigned long long item = queue_pop(&sh->auxq, lane);
             if ((item & (3ull << 62)) == FU_ITEM_EXIT) break;
             const int tile = (int)((item >> 38) & 0xffffffull), excl = (int)((item >> 8) & 0x3fffffffull);
             const unsigned mask = (unsigned)(item & 0xffull);
@@ -261,16 +272,104 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
         return;
     }
 
+    if (wid == W) {
+        // ---- scan warp: destination rows.  For every tile of this CTA, in order: resolve the exclusive prefix (the tile's
+        // count was posted by the tile warps), publish the state words of the kept rows, write the links of the next call.
+        const int n_aux_workers = (int)(blockDim.x >> 5) - W - 1;
+        unsigned head = 0;
+        while (true) {
+            int spins = 0;
+            while (*(volatile unsigned*)&sh->scan_tail == head) {
+                if (++spins > (FU_SPIN_LIMIT << 4)) { err = 1; break; }
+                __nanosleep(100);
+            }
+            __threadfence_block();
+            const unsigned long long item = *(volatile unsigned long long*)&sh->scan_item[head % FU_SCANQ];
+            __syncwarp();
+            ++head;
+            if (lane == 0) *(volatile unsigned*)&sh->scan_head = head;
+            if (err || (item & (3ull << 62)) == FU_ITEM_EXIT) break;
+            const int tile = (int)((item >> 16) & 0xffffffull);
+            const unsigned kept = (unsigned)(item >> 8) & 0xffu, merged = (unsigned)item & 0xffu;
+            const int total = __popc(kept);
+            const int excl = tile_lookback(D, tile, total, lane, &err);
+            const int r = tile * W + lane;
+            const bool mine = lane < W && (kept >> lane & 1u);
+            const int d = excl + __popc(kept & ((1u << lane) - 1u));
+            if (mine) {
+                st_relaxed64(a.fstate + r, state_kept(d));
+                a.dst[r] = d;
+            } else if (lane < W && (merged >> lane & 1u)) {
+                a.dst[r] = -1;
+            }
+            if (lane == 0) {
+                if (aux.n && kept)
+                    queue_push(&sh->auxq, FU_ITEM_AUX | ((unsigned long long)tile << 38) | ((unsigned long long)excl << 8) | kept, &err);
+                if (tile == a.ntiles - 1) {
+                    // the sequence is done: sizes, the speculated branch, the counters of the next call (main.py:112-120)
+                    const long long s_keep = excl + total, n_merged = a.S - s_keep;
+                    const long long N = a.counters[C_N], n_vis = a.counters[C_NVIS];
+                    int e = 0;
+                    if (n_vis == 0) e = 1;                  // the reference divides by zero here (main.py:114)
+                    else if (!((double)n_merged / (double)n_vis < a.bound)) e = 3;   // top-k branch: the host redoes the call
+                    a.counters[C_COUNT] = n_merged;
+                    a.counters[C_NNEXT] = N - n_merged;
+                    a.counters[C_SKEEP] = s_keep;
+                    a.counters[C_BRANCH] = 0;
+                    a.counters[C_K] = 0;
+                    a.counters[C_NMERGED] = n_merged;
+                    a.counters_next[C_N] = N - n_merged;
+                    a.counters_next[C_NVIS] = n_vis - n_merged;
+                    a.counters_next[C_COUNT] = 0;
+                    a.counters_next[C_TICKET] = 0;
+                    a.counters_next[C_TICKET2] = 0;
+                    a.status[FF_ST_SEQ_KEEP] = s_keep;
+                    a.status[FF_ST_COUNT] = n_merged;
+                    a.status[FF_ST_NVIS] = n_vis;
+                    a.status[FF_ST_NCHAIN] = N;
+                    a.status[FF_ST_BRANCH] = 0;
+                    a.status[FF_ST_TOPK] = 0;
+                    a.status[FF_ST_ERROR] = e;
+                    a.status[FF_ST_NMERGED] = n_merged;
+                    a.status[FF_ST_FUSED] = 1;
+                }
+            }
+            if (mine) {
+                // links of the next call: a kept row follows the anchor of its predecessor's run
+                const int2 lk = __ldg(a.link + r);
+                if (lk.x >= 0) {
+                    const unsigned long long st = wait_state(a.fstate, lk.x, &err);
+                    if (state_type(st) != 0) {
+                        a.link_next[d].x = state_dst(st);
+                        a.link_next[state_dst(st)].y = d;
+                    }
+                } else {
+                    a.link_next[d].x = lk.x;                // chain head / not a chain row
+                    if (lk.x == -2) a.link_next[d].y = -2;
+                }
+                if (lk.x != -2 && lk.y < 0) a.link_next[d].y = -1;          // chain tail
+            }
+            __syncwarp();
+        }
+        if (lane == 0)
+            for (int i = 0; i < n_aux_workers; ++i) queue_push(&sh->auxq, FU_ITEM_EXIT, &err);
+        if (err && lane == 0) a.status[FF_ST_INTERNAL] = 1;
+        return;
+    }
+
     // ---- tile warps.  Per warp: slot P (chain predecessor) and slot C (own row), one mbarrier for both
     unsigned char* slot_p = fu_smem + (size_t)(2 * wid) * a.slot_bytes;
     unsigned char* slot_c = slot_p + a.slot_bytes;
-    const uint32_t sp32 = smem_u32(slot_p), sc32 = smem_u32(slot_c), bar = smem_u32(bars + wid);
-    unsigned long long* D = a.desc + 1;
-    int tile = s_int[FU_WARPS + 1];
+    const uint32_t sp32 = smem_u32(slot_p), sc32 = smem_u32(slot_c), bar = smem_u32(&sh->bars[wid]);
+    const uint4* pr = reinterpret_cast<const uint4*>(slot_p);
+    const uint4* cr = reinterpret_cast<const uint4*>(slot_c);
+    int tile = sh->next_tile[0];
+    int iter = 0;
     uint32_t phase = 0;
     bool store_pending = false;                             // lane 0: a bulk store may still be reading a slot
 
     while (tile < a.ntiles) {
+        const int par = iter & 1;
         const int r = tile * W + wid;
         const bool valid = r < a.S;
         int2 lk = make_int2(-2, -2);
@@ -286,7 +385,7 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             tma_load(sc32, a.hidden + (int64_t)r * row_bytes, (uint32_t)row_bytes, bar);
             if (has_pred) tma_load(sp32, a.hidden + (int64_t)p * row_bytes, (uint32_t)row_bytes, bar);
         }
-        // the predecessor's state word was published a few microseconds ago (its tile is ~P / W tiles back): ask now
+        // the predecessor's state word: its tile is ~P / W tiles back; usually published by the time the rows are here
         unsigned long long st_p = 0;
         if (has_pred) st_p = ld_relaxed64(a.fstate + p);
         if (valid) prefetch_aux(aux, r, lane);
@@ -296,8 +395,6 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             mbar_wait(bar, phase);
             phase ^= 1u;
         }
-        const uint4* pr = reinterpret_cast<const uint4*>(slot_p);
-        const uint4* cr = reinterpret_cast<const uint4*>(slot_c);
         if (has_pred) {
             float dot = 0.f, na = 0.f, nb = 0.f;
 #pragma unroll 4
@@ -311,76 +408,48 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
         }
         if (lane == 0) {
             if (valid) a.sim_seq[r] = s;
-            s_int[wid] = valid ? flag : 2;
+            *(volatile int*)&sh->flags[par][wid] = valid ? flag : 2;
         }
         tile_barrier(W * 32);                               // (A) the tile's flags are in shared memory
-        int myrank = 0, total = 0;
-        unsigned keep_mask = 0;
+        if (threadIdx.x == 0) {
+            // the tile's count goes out at once (nobody's look-back waits for more than this tile's rows), the rest of the
+            // bookkeeping to the scan warp; the next tile's ticket travels while this tile is finished
+            unsigned kept = 0, merged = 0;
 #pragma unroll
-        for (int w = 0; w < FU_WARPS; ++w) {
-            const int k = (w < W) && (s_int[w] == 0);
-            if (w < wid) myrank += k;
-            total += k;
-            keep_mask |= (unsigned)k << w;
+            for (int w = 0; w < FU_WARPS; ++w)
+                if (w < W) {
+                    const int f = *(volatile int*)&sh->flags[par][w];
+                    kept |= (unsigned)(f == 0) << w;
+                    merged |= (unsigned)(f == 1) << w;
+                }
+            tile_post(D, tile, __popc(kept), 0);
+            const int nt = (int)atomicAdd(a.desc, 1ull);
+            const unsigned t = sh->scan_tail;
+            int spins = 0;
+            while ((int)(t - *(volatile unsigned*)&sh->scan_head) >= FU_SCANQ) {
+                if (++spins > FU_SPIN_LIMIT) { err = 1; break; }
+                __nanosleep(100);
+            }
+            *(volatile unsigned long long*)&sh->scan_item[t % FU_SCANQ] = FU_ITEM_TILE | ((unsigned long long)tile << 16) | (kept << 8) | merged;
+            __threadfence_block();
+            *(volatile unsigned*)&sh->scan_tail = t + 1;
+            *(volatile int*)&sh->next_tile[par] = nt;
+            __threadfence_block();
+            *(volatile int*)&sh->next_iter[par] = iter + 1;
         }
-        if (wid == 0) tile_post(D, tile, total, lane);      // before this warp waits for anything
+        // ---- finish the predecessor's run.  Needs the predecessor's state word, nothing of this tile's own prefix.
         if (has_pred && state_type(st_p) == 0) st_p = wait_state(a.fstate, p, &err);
         const bool p_merged = has_pred && state_type(st_p) == 1;
-        if (p_merged && lane == 0) {
+        if (p_merged) {
             // the predecessor is inside a run: its raw row has served (the similarity); fetch the running sum of the run
             // — the anchor's destination row, written by the predecessor's warp before it published — into slot P
-            __threadfence();                                // acquire: the state word was read with a relaxed load
-            asm volatile("fence.proxy.async;" ::: "memory");   // ... and the row is fetched through the async proxy
-            mbar_expect_tx(bar, (uint32_t)row_bytes);
-            tma_load(sp32, a.out + (int64_t)state_dst(st_p) * row_bytes, (uint32_t)row_bytes, bar);
-        }
-        if (wid == 0) {
-            const int ex = tile_lookback(D, tile, total, lane, &err);
-            if (lane == 0) s_int[FU_WARPS] = ex;
-        }
-        tile_barrier(W * 32);                               // (B) the prefix is known to every warp
-        const int excl = s_int[FU_WARPS];
-        const int d_r = (valid && !flag) ? excl + myrank : -1;
-        if (valid && lane == 0) {
-            if (!flag) st_relaxed64(a.fstate + r, state_kept(d_r));
-            a.dst[r] = d_r;
-        }
-        int nt = 0;
-        if (threadIdx.x == 0) {
-            nt = (int)atomicAdd(a.desc, 1ull);              // the next tile's ticket travels while this tile is finished
-            if (aux.n && keep_mask)
-                queue_push(q, FU_ITEM_AUX | ((unsigned long long)tile << 38) | ((unsigned long long)excl << 8) | keep_mask, &err);
-            if (tile == a.ntiles - 1) {
-                // the sequence is done: sizes, the speculated branch, the counters of the next call (main.py:112-120)
-                const long long s_keep = excl + total, merged = a.S - s_keep;
-                const long long N = a.counters[C_N], n_vis = a.counters[C_NVIS];
-                int e = 0;
-                if (n_vis == 0) e = 1;                      // the reference divides by zero here (main.py:114)
-                else if (!((double)merged / (double)n_vis < a.bound)) e = 3;   // top-k branch: the host redoes the call
-                a.counters[C_COUNT] = merged;
-                a.counters[C_NNEXT] = N - merged;
-                a.counters[C_SKEEP] = s_keep;
-                a.counters[C_BRANCH] = 0;
-                a.counters[C_K] = 0;
-                a.counters[C_NMERGED] = merged;
-                a.counters_next[C_N] = N - merged;
-                a.counters_next[C_NVIS] = n_vis - merged;
-                a.counters_next[C_COUNT] = 0;
-                a.counters_next[C_TICKET] = 0;
-                a.counters_next[C_TICKET2] = 0;
-                a.status[FF_ST_SEQ_KEEP] = s_keep;
-                a.status[FF_ST_COUNT] = merged;
-                a.status[FF_ST_NVIS] = n_vis;
-                a.status[FF_ST_NCHAIN] = N;
-                a.status[FF_ST_BRANCH] = 0;
-                a.status[FF_ST_TOPK] = 0;
-                a.status[FF_ST_ERROR] = e;
-                a.status[FF_ST_NMERGED] = merged;
-                a.status[FF_ST_FUSED] = 1;
+            if (lane == 0) {
+                __threadfence();                            // acquire: the state word was read with a relaxed load
+                asm volatile("fence.proxy.async;" ::: "memory");   // ... and the row is fetched through the async proxy
+                mbar_expect_tx(bar, (uint32_t)row_bytes);
+                tma_load(sp32, a.out + (int64_t)state_dst(st_p) * row_bytes, (uint32_t)row_bytes, bar);
             }
-        }
-        if (p_merged) {
-            mbar_wait(bar, phase);                          // the running sum is in slot P
+            mbar_wait(bar, phase);
             phase ^= 1u;
         }
         if (has_pred && state_type(st_p) != 0) {
@@ -400,10 +469,6 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
 #pragma unroll 2
                     for (int vb = 0; vb < nvec; vb += 32)
                         if (vb + lane < nvec) st_stream16(orow + (int64_t)(vb + lane) * 16, dv.vec_fast(pr[vb + lane]));
-                }
-                if (lane == 0) {
-                    a.link_next[d_r].x = d_a;
-                    a.link_next[d_a].y = d_r;
                 }
             } else {
                 // this row is merged away: T(sum + row), main.py:304-311; slot P holds the sum so far (the anchor's raw row
@@ -429,25 +494,32 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
                 }
             }
         }
-        if (d_r >= 0 && lane == 0) {
-            if (p < 0) {                                    // chain head / not a chain row
-                a.link_next[d_r].x = p;
-                if (p == -2) a.link_next[d_r].y = -2;
-            }
-            if (self_emit) {                                // an unmerged row nobody comes to close: it writes itself
-                tma_store(a.out + (int64_t)d_r * row_bytes, sc32, (uint32_t)row_bytes);
+        if (self_emit && !flag) {
+            // an unmerged row nobody comes to close (chain tail, row outside the chains): it writes itself, which takes its
+            // own destination — the one wait for this tile's own prefix, on the few rows of this kind
+            const unsigned long long st_r = wait_state(a.fstate, r, &err);
+            if (lane == 0 && state_type(st_r) == 2) {
+                tma_store(a.out + (int64_t)state_dst(st_r) * row_bytes, sc32, (uint32_t)row_bytes);
                 tma_commit();
                 store_pending = true;
-                if (p != -2) a.link_next[d_r].y = -1;
             }
         }
-        if (threadIdx.x == 0) s_int[FU_WARPS + 1] = nt;
-        tile_barrier(W * 32);
-        tile = s_int[FU_WARPS + 1];
+        // the next tile
+        // (thread 0 always gets there: its own waits are bounded.  All tile warps must see the same tile: no early exit.)
+        while (*(volatile int*)&sh->next_iter[par] != iter + 1) __nanosleep(20);
+        __threadfence_block();
+        tile = *(volatile int*)&sh->next_tile[par];
+        ++iter;
     }
 
-    if (threadIdx.x == 0)
-        for (int i = 0; i < (int)(blockDim.x >> 5) - W; ++i) queue_push(q, FU_ITEM_EXIT, &err);
+    tile_barrier(W * 32);
+    if (threadIdx.x == 0) {
+        const unsigned t = sh->scan_tail;
+        while ((int)(t - *(volatile unsigned*)&sh->scan_head) >= FU_SCANQ) __nanosleep(100);
+        *(volatile unsigned long long*)&sh->scan_item[t % FU_SCANQ] = FU_ITEM_EXIT;
+        __threadfence_block();
+        *(volatile unsigned*)&sh->scan_tail = t + 1;
+    }
     // leave the other bank's state words and descriptors zeroed for the next call of the prefill
     const int64_t n_thr = (int64_t)gridDim.x * W * 32, me = (int64_t)blockIdx.x * W * 32 + threadIdx.x;
     for (int64_t i = me; i < a.S; i += n_thr) a.fstate_clr[i] = 0ull;
