@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -375,6 +376,16 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
                  double thr, double bound, const AuxPack& ap, cudaStream_t st) {
     const int nb = bank ^ 1;
     FusedArgs a;
+    a.trace = nullptr;
+#ifdef FF_FUSED_TRACE
+    // development build: stamps of the last launch are left in a device buffer and dumped to $FF_FUSED_TRACE_FILE
+    static long long* g_trace = nullptr;
+    static size_t g_trace_n = 0;
+    const size_t need = ((size_t)(S + 1) / 2 + 2) * FU_TRACE_SLOTS;
+    if (need > g_trace_n) { if (g_trace) cudaFree(g_trace); cudaMalloc((void**)&g_trace, need * 8); g_trace_n = need; }
+    cudaMemsetAsync(g_trace, 0, need * 8, st);
+    a.trace = g_trace;
+#endif
     a.hidden = (const char*)hidden;
     a.out = (char*)out;
     a.S = (int)S;
@@ -417,6 +428,16 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
         int grid = per_sm * ctx->sm_count;
         if (grid > a.ntiles) grid = a.ntiles;
         FF_LAUNCH("k_fused_merge", k_fused_merge<DT>, grid, threads, smem, st, a, ap);
+#ifdef FF_FUSED_TRACE
+        if (const char* path = getenv("FF_FUSED_TRACE_FILE")) {
+            cudaStreamSynchronize(st);
+            const size_t n = (size_t)a.ntiles * FU_TRACE_SLOTS;
+            long long* h = (long long*)malloc(n * 8);
+            cudaMemcpy(h, a.trace, n * 8, cudaMemcpyDeviceToHost);
+            if (FILE* f = fopen(path, "wb")) { fwrite(h, 8, n, f); fclose(f); }
+            free(h);
+        }
+#endif
         return (int)FF_OK;
     });
 }

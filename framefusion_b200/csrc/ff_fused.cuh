@@ -49,7 +49,19 @@ constexpr int FU_SCANQ = 8;                        // ring entries between the t
 constexpr int FU_SPIN_LIMIT = 1 << 18;             // polls (~64 ns apart) before a wait gives up and reports FF_ST_INTERNAL
 constexpr unsigned long long FU_AGG = 1ull << 32, FU_INCL = 2ull << 32;
 
+// Development aid (tools/trace_fused.py builds a separate library with -DFF_FUSED_TRACE): globaltimer stamps per tile.
+#ifdef FF_FUSED_TRACE
+#define FU_TRACE_SLOTS 16
+#define FU_STAMP(tile, k) do { if (a.trace) a.trace[(size_t)(tile) * FU_TRACE_SLOTS + (k)] = fu_gtime(); } while (0)
+#define FU_STAMP_MAX(tile, k) do { if (a.trace) atomicMax((unsigned long long*)&a.trace[(size_t)(tile) * FU_TRACE_SLOTS + (k)], (unsigned long long)fu_gtime()); } while (0)
+__device__ __forceinline__ long long fu_gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#else
+#define FU_STAMP(tile, k) do { } while (0)
+#define FU_STAMP_MAX(tile, k) do { } while (0)
+#endif
+
 struct FusedArgs {
+    long long* trace;                              // FF_FUSED_TRACE builds only
     const char* hidden;
     char* out;
     int S, nvec, row_bytes, slot_bytes, ntiles, tile_rows;
@@ -133,6 +145,16 @@ __device__ __forceinline__ void prefetch_aux(const AuxPack& aux, int r, int lane
         }
 }
 
+// the same with a fixed number of polls: the caller has something else to do if the word is still missing
+__device__ __forceinline__ unsigned long long poll_state(const unsigned long long* fstate, int x, int polls) {
+    unsigned long long v = ld_relaxed64(fstate + x);
+    for (int i = 0; i < polls && (v & 3ull) == 0ull; ++i) {
+        __nanosleep(64);
+        v = ld_relaxed64(fstate + x);
+    }
+    return v;
+}
+
 __device__ __forceinline__ void copy_row(const char* src, char* dst, int nvec, int lane) {
     for (int vb = 0; vb < nvec; vb += 256) {                // eight 16-byte vectors per lane in flight
         const int v0 = vb + lane;
@@ -187,14 +209,86 @@ __device__ __forceinline__ int tile_lookback(unsigned long long* D, int tile, in
     return excl;
 }
 
+// coherent 16-byte load (rows of `out` are written and re-read inside the kernel: not the read-only path)
+__device__ __forceinline__ uint4 ld_cg16(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+
+// The emission step of row r out of global memory (the rows are L2 hits): what a tile warp does from its slots when the
+// predecessor's state word is already there, done later by a worker warp when it was not.
+//   r kept:    its predecessor's run ends -> the predecessor (a plain kept row) is copied to its destination, or the
+//              running sum of the run is divided by T(L + 1) in place (main.py:314-317)
+//   r merged:  T(sum + r) into the anchor's destination row (main.py:304-311), then r's state word (anchor, members)
+// Returns false if the predecessor's state word is still missing after a short wait (the caller puts the item back).
+template <int DT>
+__device__ __noinline__ bool emit_from_global(const FusedArgs& a, int r, int flag, int lane, int* err) {
+    const int2 lk = __ldg(a.link + r);
+    const int p = lk.x;
+    if (p < 0) return true;
+    const unsigned long long st_p = poll_state(a.fstate, p, 24);
+    if (state_type(st_p) == 0) return false;
+    const bool p_merged = state_type(st_p) == 1;
+    if (p_merged) __threadfence();                          // acquire: the running sum was written before the state word
+    const int d_a = state_dst(st_p), L_p = p_merged ? state_len(st_p) : 0, nvec = a.nvec;
+    const int64_t row_bytes = a.row_bytes;
+    char* orow = a.out + (int64_t)d_a * row_bytes;
+    const char* sum = p_merged ? orow : a.hidden + (int64_t)p * row_bytes;
+    const char* own = a.hidden + (int64_t)r * row_bytes;
+    const bool finish = !flag || lk.y < 0;                  // the run ends here (the closing row, or the end of the chain)
+    const Divider<DT> dv((flag ? L_p + 1 : L_p) + 1);
+    if (!flag && !p_merged) {
+        copy_row(sum, orow, nvec, lane);
+    } else {
+#pragma unroll 1
+        for (int vb = 0; vb < nvec; vb += 128) {
+            uint4 x[4], y[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int v = vb + 32 * q + lane;
+                if (v < nvec) {
+                    x[q] = ld_cg16(sum + (int64_t)v * 16);
+                    if (flag) y[q] = ldg16(own + (int64_t)v * 16);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int v = vb + 32 * q + lane;
+                if (v < nvec) {
+                    uint4 t = flag ? Num<DT>::add_vec(x[q], y[q]) : x[q];
+                    if (finish) t = dv.vec_fast(t);
+                    st_stream16(orow + (int64_t)v * 16, t);
+                }
+            }
+        }
+    }
+    if (flag) {
+        if (lk.y < 0 && lane == 0) a.link_next[d_a].y = -1;
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();                                // the sum is visible before the state word that announces it
+            st_relaxed64(a.fstate + r, state_merged(d_a, L_p + 1));
+        }
+    }
+    return true;
+}
+
 // ---- shared memory behind the row slots: the hand-over rings between the three kinds of warps of a CTA
 //   tile warps --(tile, kept / merged masks)--> scan warp --(tile, prefix, kept mask)--> aux workers
-constexpr unsigned long long FU_ITEM_TILE = 1ull << 62, FU_ITEM_AUX = 2ull << 62, FU_ITEM_EXIT = 3ull << 62;
+constexpr unsigned long long FU_ITEM_TILE = 1ull << 62, FU_ITEM_EXIT = 3ull << 62;
+// worker items: bits [63:62] kind
+//   POST  (tile << 38) | (exclusive prefix << 8) | kept mask: aux rows and next-call links of the tile's kept rows
+//   EMIT  (row << 1) | merged flag: the emission step of a row whose predecessor's state was not published in time
+//   COPY  (row << 31) | destination: a kept row that writes itself (chain tail, row outside the chains)
+//   LINK  (row << 31) | destination: the next-call link of one kept row whose predecessor's state was late
+constexpr unsigned long long FU_W_POST = 0ull << 62, FU_W_EMIT = 1ull << 62, FU_W_COPY = 2ull << 62, FU_W_LINK = 3ull << 62;
 
-struct FusedQueue {                                         // one producer lane, several consumer warps
+struct FusedQueue {                                         // several producer lanes, several consumer warps
     unsigned long long item[FU_QSIZE];
-    unsigned seq[FU_QSIZE];                                 // item[i] of lap n is valid once seq[i] == n + 1
-    unsigned tail, head, freed, pad;
+    unsigned seq[FU_QSIZE];                                 // slot i: 2n = free for lap n, 2n + 1 = holds the item of lap n
+    unsigned tail, head, done;
+    int pending;                                            // items pushed and not yet completed
 };
 
 struct FusedShared {
@@ -203,32 +297,106 @@ struct FusedShared {
     int next_tile[2], next_iter[2];                         // the ticket of the next tile, valid once next_iter == iteration + 1
     unsigned long long scan_item[FU_SCANQ];                 // tile warps (thread 0) -> scan warp
     unsigned scan_tail, scan_head;
-    FusedQueue auxq;                                        // scan warp -> aux workers
+    FusedQueue auxq;                                        // tile warps / scan warp -> workers
 };
 
-__device__ __forceinline__ void queue_push(FusedQueue* q, unsigned long long item, int* err) {     // one lane
-    const unsigned t = atomicAdd(&q->tail, 1u);
-    int spins = 0;
-    while ((int)(t - *(volatile unsigned*)&q->freed) >= FU_QSIZE) {                  // ring full: the workers are behind
-        if (++spins > FU_SPIN_LIMIT) { *err = 1; break; }
-        __nanosleep(100);
+// One lane.  Never waits for room: false if the ring is full, and the caller does the work itself — so nobody ever waits
+// for something only a later row's progress could provide.
+__device__ __forceinline__ bool queue_push(FusedQueue* q, unsigned long long item) {
+    unsigned t;
+    while (true) {
+        t = *(volatile unsigned*)&q->tail;
+        if ((int)(t - *(volatile unsigned*)&q->head) >= FU_QSIZE) return false;
+        if (atomicCAS(&q->tail, t, t + 1u) == t) break;
     }
+    atomicAdd(&q->pending, 1);
+    const unsigned want = 2u * (t / FU_QSIZE);
+    while (*(volatile unsigned*)&q->seq[t % FU_QSIZE] != want) __nanosleep(20);    // its last reader is just leaving
     *(volatile unsigned long long*)&q->item[t % FU_QSIZE] = item;
     __threadfence_block();
-    *(volatile unsigned*)&q->seq[t % FU_QSIZE] = t / FU_QSIZE + 1;
+    *(volatile unsigned*)&q->seq[t % FU_QSIZE] = want + 1u;
+    return true;
 }
 
-__device__ __forceinline__ unsigned long long queue_pop(FusedQueue* q, int lane) {             // whole warp
+// whole warp.  false: nothing left to do (the producers are done and every item has been completed)
+__device__ __forceinline__ bool queue_pop(FusedQueue* q, int lane, unsigned long long* out) {
     unsigned h = 0;
-    if (lane == 0) h = atomicAdd(&q->head, 1u);
+    int got = 0;
+    if (lane == 0) {
+        while (true) {
+            h = *(volatile unsigned*)&q->head;
+            if (h != *(volatile unsigned*)&q->tail) {
+                if (atomicCAS(&q->head, h, h + 1u) == h) { got = 1; break; }
+                continue;
+            }
+            if (*(volatile unsigned*)&q->done && *(volatile int*)&q->pending == 0) break;
+            __nanosleep(200);
+        }
+    }
+    got = __shfl_sync(FULL, got, 0);
+    if (!got) return false;
     h = __shfl_sync(FULL, h, 0);
-    const unsigned want = h / FU_QSIZE + 1;
-    while (*(volatile unsigned*)&q->seq[h % FU_QSIZE] != want) __nanosleep(200);    // the producer always ends with EXIT items
+    const unsigned want = 2u * (h / FU_QSIZE) + 1u;
+    while (*(volatile unsigned*)&q->seq[h % FU_QSIZE] != want) __nanosleep(50);     // claimed by its producer, being written
     __threadfence_block();
-    const unsigned long long item = *(volatile unsigned long long*)&q->item[h % FU_QSIZE];
+    *out = *(volatile unsigned long long*)&q->item[h % FU_QSIZE];
     __syncwarp();
-    if (lane == 0) atomicAdd(&q->freed, 1u);
-    return item;
+    if (lane == 0) *(volatile unsigned*)&q->seq[h % FU_QSIZE] = want + 1u;          // free for the next lap
+    return true;
+}
+
+__device__ __forceinline__ void queue_complete(FusedQueue* q, int lane) {
+    __syncwarp();
+    if (lane == 0) atomicSub(&q->pending, 1);
+}
+
+// A worker item of kind POST (aux rows + next-call links of a tile's kept rows; lane w: row w), LINK (the link of one
+// row, lane 0) or COPY (a kept row that writes itself).  requeue: a link whose predecessor state is missing goes back to
+// the ring if there is room (workers); otherwise the lane waits for it (an earlier row: it always comes).
+template <int DT>
+__device__ __noinline__ void run_post_item(const FusedArgs& a, const AuxPack& aux, FusedQueue* q, int W, unsigned long long item,
+                                           int lane, int* err, bool requeue) {
+    const unsigned long long kind = item & (3ull << 62);
+    if (kind == FU_W_COPY) {
+        const int r = (int)((item >> 31) & 0x3fffffffull), d = (int)(item & 0x7fffffffull);
+        copy_row(a.hidden + (int64_t)r * a.row_bytes, a.out + (int64_t)d * a.row_bytes, a.nvec, lane);
+        return;
+    }
+    int r = -1, d = -1;
+    if (kind == FU_W_POST) {
+        const int tile = (int)((item >> 38) & 0xffffffull), excl = (int)((item >> 8) & 0x3fffffffull);
+        const unsigned mask = (unsigned)(item & 0xffull);
+        if (aux.n) {
+#pragma unroll 1
+            for (int w = 0; w < W; ++w)
+                if (mask >> w & 1u) gather_aux_rows(aux, tile * W + w, excl + __popc(mask & ((1u << w) - 1u)), lane);
+        }
+        if (lane < W && (mask >> lane & 1u)) { r = tile * W + lane; d = excl + __popc(mask & ((1u << lane) - 1u)); }
+    } else if (lane == 0) {
+        r = (int)((item >> 31) & 0x3fffffffull);
+        d = (int)(item & 0x7fffffffull);
+    }
+    // links of the next call: a kept row follows the anchor of its predecessor's run
+    if (r >= 0) {
+        const int2 lk = __ldg(a.link + r);
+        if (kind == FU_W_POST) {
+            if (lk.x < 0) {
+                a.link_next[d].x = lk.x;                    // chain head / not a chain row
+                if (lk.x == -2) a.link_next[d].y = -2;
+            }
+            if (lk.x != -2 && lk.y < 0) a.link_next[d].y = -1;              // chain tail
+        }
+        if (lk.x >= 0) {
+            unsigned long long st = poll_state(a.fstate, lk.x, 24);
+            if (state_type(st) == 0 && !(requeue && queue_push(q, FU_W_LINK | ((unsigned long long)r << 31) | (unsigned long long)d)))
+                st = wait_state(a.fstate, lk.x, err);
+            if (state_type(st) != 0) {
+                a.link_next[d].x = state_dst(st);
+                a.link_next[state_dst(st)].y = d;
+            }
+        }
+    }
+    __syncwarp();
 }
 
 __device__ __forceinline__ void tile_barrier(int n_threads) {                       // the tile warps only (named barrier 1)
@@ -249,7 +417,8 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
         sh->next_tile[0] = (int)atomicAdd(a.desc, 1ull);
         sh->next_iter[0] = sh->next_iter[1] = 0;
         sh->scan_tail = sh->scan_head = 0;
-        sh->auxq.tail = sh->auxq.head = sh->auxq.freed = 0;
+        sh->auxq.tail = sh->auxq.head = sh->auxq.done = 0;
+        sh->auxq.pending = 0;
     }
     for (int i = threadIdx.x; i < FU_QSIZE; i += blockDim.x) sh->auxq.seq[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -259,23 +428,33 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
     const int64_t row_bytes = a.row_bytes;
 
     if (wid > W) {
-        // ---- aux workers: the aux rows of a tile, off everybody's critical path
-        while (true) {
-            const unsigned long long item = queue_pop(&sh->auxq, lane);
-            if ((item & (3ull << 62)) == FU_ITEM_EXIT) break;
-            const int tile = (int)((item >> 38) & 0xffffffull), excl = (int)((item >> 8) & 0x3fffffffull);
-            const unsigned mask = (unsigned)(item & 0xffull);
-#pragma unroll 1
-            for (int w = 0; w < W; ++w)
-                if (mask >> w & 1u) gather_aux_rows(aux, tile * W + w, excl + __popc(mask & ((1u << w) - 1u)), lane);
+        // ---- workers: everything that may have to wait or that nobody waits for — aux rows, next-call links, rows that write
+        // themselves, and the emission steps the tile warps could not do on the spot.  A worker does not sit on an item whose
+        // predecessor state is missing while the ring has room: the item goes back to the end of the ring.
+        FusedQueue* q = &sh->auxq;
+        unsigned long long item;
+        while (queue_pop(q, lane, &item)) {
+            if ((item & (3ull << 62)) == FU_W_EMIT) {
+                const int r = (int)((item >> 1) & 0x3fffffffull), flag = (int)(item & 1ull);
+                int tries = 0;
+                while (!emit_from_global<DT>(a, r, flag, lane, &err)) {
+                    int back = 0;
+                    if (lane == 0) back = queue_push(q, item) ? 1 : 0;
+                    if (__shfl_sync(FULL, back, 0)) break;
+                    if (++tries > (FU_SPIN_LIMIT >> 4)) { err = 1; break; }
+                }
+            } else {
+                run_post_item<DT>(a, aux, q, W, item, lane, &err, true);
+            }
+            queue_complete(q, lane);
         }
+        if (err && lane == 0) a.status[FF_ST_INTERNAL] = 1;
         return;
     }
 
     if (wid == W) {
         // ---- scan warp: destination rows.  For every tile of this CTA, in order: resolve the exclusive prefix (the tile's
         // count was posted by the tile warps), publish the state words of the kept rows, write the links of the next call.
-        const int n_aux_workers = (int)(blockDim.x >> 5) - W - 1;
         unsigned head = 0;
         while (true) {
             int spins = 0;
@@ -292,7 +471,9 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             const int tile = (int)((item >> 16) & 0xffffffull);
             const unsigned kept = (unsigned)(item >> 8) & 0xffu, merged = (unsigned)item & 0xffu;
             const int total = __popc(kept);
+            if (lane == 0) FU_STAMP(tile, 6);
             const int excl = tile_lookback(D, tile, total, lane, &err);
+            if (lane == 0) FU_STAMP(tile, 7);
             const int r = tile * W + lane;
             const bool mine = lane < W && (kept >> lane & 1u);
             const int d = excl + __popc(kept & ((1u << lane) - 1u));
@@ -302,9 +483,30 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             } else if (lane < W && (merged >> lane & 1u)) {
                 a.dst[r] = -1;
             }
+            // rows that write themselves (chain tails, rows outside the chains): their destination is known here
+            unsigned self = 0;
+            if (mine) {
+                const int2 lk = __ldg(a.link + r);
+                self = (lk.x == -2 || lk.y < 0) ? 1u : 0u;
+            }
+            unsigned self_mask = __ballot_sync(FULL, self != 0u);
+            // hand the rest of the tile's bookkeeping to the workers; with the ring full this warp does it itself
+            while (self_mask) {
+                const int w = __ffs(self_mask) - 1;
+                self_mask &= self_mask - 1;
+                const unsigned long long it = FU_W_COPY | ((unsigned long long)(tile * W + w) << 31) |
+                                              (unsigned long long)(excl + __popc(kept & ((1u << w) - 1u)));
+                int ok = 0;
+                if (lane == 0) ok = queue_push(&sh->auxq, it) ? 1 : 0;
+                if (!__shfl_sync(FULL, ok, 0)) run_post_item<DT>(a, aux, &sh->auxq, W, it, lane, &err, false);
+            }
+            if (kept) {
+                const unsigned long long it = FU_W_POST | ((unsigned long long)tile << 38) | ((unsigned long long)excl << 8) | kept;
+                int ok = 0;
+                if (lane == 0) ok = queue_push(&sh->auxq, it) ? 1 : 0;
+                if (!__shfl_sync(FULL, ok, 0)) run_post_item<DT>(a, aux, &sh->auxq, W, it, lane, &err, false);
+            }
             if (lane == 0) {
-                if (aux.n && kept)
-                    queue_push(&sh->auxq, FU_ITEM_AUX | ((unsigned long long)tile << 38) | ((unsigned long long)excl << 8) | kept, &err);
                 if (tile == a.ntiles - 1) {
                     // the sequence is done: sizes, the speculated branch, the counters of the next call (main.py:112-120)
                     const long long s_keep = excl + total, n_merged = a.S - s_keep;
@@ -334,25 +536,13 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
                     a.status[FF_ST_FUSED] = 1;
                 }
             }
-            if (mine) {
-                // links of the next call: a kept row follows the anchor of its predecessor's run
-                const int2 lk = __ldg(a.link + r);
-                if (lk.x >= 0) {
-                    const unsigned long long st = wait_state(a.fstate, lk.x, &err);
-                    if (state_type(st) != 0) {
-                        a.link_next[d].x = state_dst(st);
-                        a.link_next[state_dst(st)].y = d;
-                    }
-                } else {
-                    a.link_next[d].x = lk.x;                // chain head / not a chain row
-                    if (lk.x == -2) a.link_next[d].y = -2;
-                }
-                if (lk.x != -2 && lk.y < 0) a.link_next[d].y = -1;          // chain tail
-            }
             __syncwarp();
+            if (lane == 0) FU_STAMP(tile, 8);
         }
-        if (lane == 0)
-            for (int i = 0; i < n_aux_workers; ++i) queue_push(&sh->auxq, FU_ITEM_EXIT, &err);
+        if (lane == 0) {
+            __threadfence_block();
+            *(volatile unsigned*)&sh->auxq.done = 1u;       // every push of the tile warps came before their EXIT item
+        }
         if (err && lane == 0) a.status[FF_ST_INTERNAL] = 1;
         return;
     }
@@ -370,31 +560,33 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
 
     while (tile < a.ntiles) {
         const int par = iter & 1;
+        if (threadIdx.x == 0) FU_STAMP(tile, 0);
+        // the next tile's ticket travels during this iteration (nothing in an iteration waits for another tile any more, so
+        // a ticket is never held for long)
+        int nt = 0;
+        if (threadIdx.x == 0) nt = (int)atomicAdd(a.desc, 1ull);
         const int r = tile * W + wid;
         const bool valid = r < a.S;
         int2 lk = make_int2(-2, -2);
         if (valid) lk = __ldg(a.link + r);
         const int p = lk.x, sc = lk.y;
-        const bool has_pred = valid && p >= 0;
-        const bool self_emit = valid && (p == -2 || sc < 0);   // not a chain row, or a chain tail: it writes its own run
-        const bool need_row = has_pred || self_emit;
-        __syncwarp();                                       // every lane is done with the slots before they are refilled
-        if (need_row && lane == 0) {
+        const bool has_pred = valid && p >= 0;              // rows without a predecessor in their chain need no data here:
+        __syncwarp();                                       // a successor or a worker writes them
+        if (has_pred && lane == 0) {
             if (store_pending) { tma_wait_read_0(); store_pending = false; }
-            mbar_expect_tx(bar, (uint32_t)row_bytes * (has_pred ? 2u : 1u));
+            mbar_expect_tx(bar, (uint32_t)row_bytes * 2u);
             tma_load(sc32, a.hidden + (int64_t)r * row_bytes, (uint32_t)row_bytes, bar);
-            if (has_pred) tma_load(sp32, a.hidden + (int64_t)p * row_bytes, (uint32_t)row_bytes, bar);
+            tma_load(sp32, a.hidden + (int64_t)p * row_bytes, (uint32_t)row_bytes, bar);
         }
-        // the predecessor's state word: its tile is ~P / W tiles back; usually published by the time the rows are here
-        unsigned long long st_p = 0;
-        if (has_pred) st_p = ld_relaxed64(a.fstate + p);
         if (valid) prefetch_aux(aux, r, lane);
         float s = -2.0f;                                    // IGNORE_TOKEN at chain heads (main.py:225-238)
         int flag = 0;
-        if (need_row) {
+        if (has_pred) {
             mbar_wait(bar, phase);
             phase ^= 1u;
         }
+        if (threadIdx.x == 0) FU_STAMP(tile, 1);
+        if (lane == 0) FU_STAMP_MAX(tile, 10);
         if (has_pred) {
             float dot = 0.f, na = 0.f, nb = 0.f;
 #pragma unroll 4
@@ -410,10 +602,13 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             if (valid) a.sim_seq[r] = s;
             *(volatile int*)&sh->flags[par][wid] = valid ? flag : 2;
         }
+        // the predecessor's state word: its tile is ~P / W tiles back, usually published by now.  Asked once, never waited for.
+        unsigned long long st_p = 0;
+        if (has_pred) st_p = ld_relaxed64(a.fstate + p);
         tile_barrier(W * 32);                               // (A) the tile's flags are in shared memory
         if (threadIdx.x == 0) {
-            // the tile's count goes out at once (nobody's look-back waits for more than this tile's rows), the rest of the
-            // bookkeeping to the scan warp; the next tile's ticket travels while this tile is finished
+            FU_STAMP(tile, 2);
+            // the tile's count goes out at once: nobody's look-back ever waits for more than the rows of a tile to arrive
             unsigned kept = 0, merged = 0;
 #pragma unroll
             for (int w = 0; w < FU_WARPS; ++w)
@@ -423,7 +618,6 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
                     merged |= (unsigned)(f == 1) << w;
                 }
             tile_post(D, tile, __popc(kept), 0);
-            const int nt = (int)atomicAdd(a.desc, 1ull);
             const unsigned t = sh->scan_tail;
             int spins = 0;
             while ((int)(t - *(volatile unsigned*)&sh->scan_head) >= FU_SCANQ) {
@@ -436,76 +630,85 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             *(volatile int*)&sh->next_tile[par] = nt;
             __threadfence_block();
             *(volatile int*)&sh->next_iter[par] = iter + 1;
+            FU_STAMP(tile, 3);
         }
-        // ---- finish the predecessor's run.  Needs the predecessor's state word, nothing of this tile's own prefix.
-        if (has_pred && state_type(st_p) == 0) st_p = wait_state(a.fstate, p, &err);
-        const bool p_merged = has_pred && state_type(st_p) == 1;
-        if (p_merged) {
-            // the predecessor is inside a run: its raw row has served (the similarity); fetch the running sum of the run
-            // — the anchor's destination row, written by the predecessor's warp before it published — into slot P
-            if (lane == 0) {
-                __threadfence();                            // acquire: the state word was read with a relaxed load
-                asm volatile("fence.proxy.async;" ::: "memory");   // ... and the row is fetched through the async proxy
-                mbar_expect_tx(bar, (uint32_t)row_bytes);
-                tma_load(sp32, a.out + (int64_t)state_dst(st_p) * row_bytes, (uint32_t)row_bytes, bar);
+        // ---- the emission step of this row (its predecessor's run ends, or grows by this row)
+        if (has_pred) {
+            int tp = state_type(st_p);
+            if (lane == 0) FU_STAMP_MAX(tile, 9);
+            bool deferred = false;
+            if (tp == 0) {
+                // not published yet: a worker does the step later, out of the L2, and this warp moves on (ring full: wait here)
+                int ok = 0;
+                if (lane == 0) ok = queue_push(&sh->auxq, FU_W_EMIT | ((unsigned long long)r << 1) | (unsigned long long)flag) ? 1 : 0;
+                deferred = __shfl_sync(FULL, ok, 0) != 0;
+                if (!deferred) {
+                    st_p = wait_state(a.fstate, p, &err);
+                    tp = state_type(st_p);
+                }
+#ifdef FF_FUSED_TRACE
+                if (lane == 0 && a.trace) atomicAdd((unsigned long long*)&a.trace[(size_t)tile * FU_TRACE_SLOTS + 12], 1ull);
+#endif
             }
-            mbar_wait(bar, phase);
-            phase ^= 1u;
-        }
-        if (has_pred && state_type(st_p) != 0) {
-            const int d_a = state_dst(st_p);                // destination row of the run's anchor (the predecessor itself if kept)
-            const int L_p = p_merged ? state_len(st_p) : 0;
-            char* orow = a.out + (int64_t)d_a * row_bytes;
-            if (!flag) {
-                // this row ends the run of its predecessor
-                if (!p_merged) {                            // a plain kept row: the staged copy goes out as it is
+            if (!deferred && tp != 0) {
+                const bool p_merged = tp == 1;
+                if (p_merged) {
+                    // the predecessor is inside a run: its raw row has served (the similarity); fetch the running sum of the
+                    // run — the anchor's destination row, written before the state word was — into slot P
                     if (lane == 0) {
-                        tma_store(orow, sp32, (uint32_t)row_bytes);
-                        tma_commit();
-                        store_pending = true;
+                        __threadfence();                    // acquire: the state word was read with a relaxed load
+                        asm volatile("fence.proxy.async;" ::: "memory");   // ... and the row is fetched through the async proxy
+                        mbar_expect_tx(bar, (uint32_t)row_bytes);
+                        tma_load(sp32, a.out + (int64_t)state_dst(st_p) * row_bytes, (uint32_t)row_bytes, bar);
                     }
-                } else {                                    // T(sum / T(L + 1)), main.py:314-317
-                    const Divider<DT> dv(L_p + 1);
-#pragma unroll 2
-                    for (int vb = 0; vb < nvec; vb += 32)
-                        if (vb + lane < nvec) st_stream16(orow + (int64_t)(vb + lane) * 16, dv.vec_fast(pr[vb + lane]));
+                    mbar_wait(bar, phase);
+                    phase ^= 1u;
                 }
-            } else {
-                // this row is merged away: T(sum + row), main.py:304-311; slot P holds the sum so far (the anchor's raw row
-                // if this is the first member)
-                const int L = L_p + 1;
-                if (sc < 0) {                               // ... and the chain ends here: finish the run as well
-                    const Divider<DT> dv(L + 1);
+                const int d_a = state_dst(st_p);            // destination row of the run's anchor (the predecessor itself if kept)
+                const int L_p = p_merged ? state_len(st_p) : 0;
+                char* orow = a.out + (int64_t)d_a * row_bytes;
+                if (!flag) {
+                    // this row ends the run of its predecessor
+                    if (!p_merged) {                        // a plain kept row: the staged copy goes out as it is
+                        if (lane == 0) {
+                            tma_store(orow, sp32, (uint32_t)row_bytes);
+                            tma_commit();
+                            store_pending = true;
+                        }
+                    } else {                                // T(sum / T(L + 1)), main.py:314-317
+                        const Divider<DT> dv(L_p + 1);
 #pragma unroll 2
-                    for (int vb = 0; vb < nvec; vb += 32)
-                        if (vb + lane < nvec)
-                            st_stream16(orow + (int64_t)(vb + lane) * 16, dv.vec_fast(Num<DT>::add_vec(pr[vb + lane], cr[vb + lane])));
-                    if (lane == 0) a.link_next[d_a].y = -1;
+                        for (int vb = 0; vb < nvec; vb += 32)
+                            if (vb + lane < nvec) st_stream16(orow + (int64_t)(vb + lane) * 16, dv.vec_fast(pr[vb + lane]));
+                    }
                 } else {
+                    // this row is merged away: T(sum + row), main.py:304-311; slot P holds the sum so far (the anchor's raw
+                    // row if this is the first member)
+                    const int L = L_p + 1;
+                    if (sc < 0) {                           // ... and the chain ends here: finish the run as well
+                        const Divider<DT> dv(L + 1);
 #pragma unroll 2
-                    for (int vb = 0; vb < nvec; vb += 32)
-                        if (vb + lane < nvec)
-                            st_stream16(orow + (int64_t)(vb + lane) * 16, Num<DT>::add_vec(pr[vb + lane], cr[vb + lane]));
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    __threadfence();                        // the sum is visible before the state word that announces it
-                    st_relaxed64(a.fstate + r, state_merged(d_a, L));
+                        for (int vb = 0; vb < nvec; vb += 32)
+                            if (vb + lane < nvec)
+                                st_stream16(orow + (int64_t)(vb + lane) * 16, dv.vec_fast(Num<DT>::add_vec(pr[vb + lane], cr[vb + lane])));
+                        if (lane == 0) a.link_next[d_a].y = -1;
+                    } else {
+#pragma unroll 2
+                        for (int vb = 0; vb < nvec; vb += 32)
+                            if (vb + lane < nvec)
+                                st_stream16(orow + (int64_t)(vb + lane) * 16, Num<DT>::add_vec(pr[vb + lane], cr[vb + lane]));
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        __threadfence();                    // the sum is visible before the state word that announces it
+                        st_relaxed64(a.fstate + r, state_merged(d_a, L));
+                    }
                 }
             }
         }
-        if (self_emit && !flag) {
-            // an unmerged row nobody comes to close (chain tail, row outside the chains): it writes itself, which takes its
-            // own destination — the one wait for this tile's own prefix, on the few rows of this kind
-            const unsigned long long st_r = wait_state(a.fstate, r, &err);
-            if (lane == 0 && state_type(st_r) == 2) {
-                tma_store(a.out + (int64_t)state_dst(st_r) * row_bytes, sc32, (uint32_t)row_bytes);
-                tma_commit();
-                store_pending = true;
-            }
-        }
-        // the next tile
-        // (thread 0 always gets there: its own waits are bounded.  All tile warps must see the same tile: no early exit.)
+        if (threadIdx.x == 0) FU_STAMP(tile, 5);
+        if (lane == 0) FU_STAMP_MAX(tile, 11);
+        // the next tile (thread 0 always gets there: its own waits are bounded.  All tile warps must see the same tile.)
         while (*(volatile int*)&sh->next_iter[par] != iter + 1) __nanosleep(20);
         __threadfence_block();
         tile = *(volatile int*)&sh->next_tile[par];
