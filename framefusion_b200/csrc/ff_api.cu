@@ -353,13 +353,13 @@ int check_shape(int64_t S, int64_t H, int dtype) {
 // shared memory of one CTA of the read-once kernel besides the row slots: mbarriers, tile scratch, the worker queue
 constexpr int FU_SMEM_EXTRA = (int)sizeof(FusedShared);
 
-// rows per tile (= tile warps per CTA) of the read-once kernel: two CTAs per SM, two slots per warp; 0 = rows too long
+// rows per tile (= tile warps per CTA) of the read-once kernel: two CTAs per SM, four slots per warp; 0 = rows too long
 int fused_tile_rows(const ff_ctx* ctx, int64_t row_bytes) {
     const int64_t slot = (row_bytes + 127) / 128 * 128;
     const int64_t per_cta = ctx->smem_per_sm / 2 - ctx->smem_reserved;
-    int64_t w = (per_cta - FU_SMEM_EXTRA) / (2 * slot);
+    int64_t w = (per_cta - FU_SMEM_EXTRA) / (4 * slot);
     if (w > FU_WARPS) w = FU_WARPS;
-    return w < 2 ? 0 : (int)w;
+    return w < 1 ? 0 : (int)w;
 }
 
 // rows the read-once kernel handles: 16-byte multiples, a threshold no chain head (sim = -2) can pass, shared memory
@@ -414,7 +414,7 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
     ctx->fused_clean[bank] = 0;
     ctx->fused_clean[nb] = 1;                              // the kernel clears the other bank on its way out
     ctx->h_status[FF_ST_INTERNAL] = 0;
-    const int smem = 2 * a.tile_rows * a.slot_bytes + FU_SMEM_EXTRA;
+    const int smem = 4 * a.tile_rows * a.slot_bytes + FU_SMEM_EXTRA;
     const int threads = (a.tile_rows + FU_WORKERS) * 32;
     return dispatch_dtype(dtype, [&](auto dt) {
         constexpr int DT = decltype(dt)::value;

@@ -209,80 +209,14 @@ __device__ __forceinline__ int tile_lookback(unsigned long long* D, int tile, in
     return excl;
 }
 
-// coherent 16-byte load (rows of `out` are written and re-read inside the kernel: not the read-only path)
-__device__ __forceinline__ uint4 ld_cg16(const void* p) {
-    uint4 r;
-    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
-    return r;
-}
-
-// The emission step of row r out of global memory (the rows are L2 hits): what a tile warp does from its slots when the
-// predecessor's state word is already there, done later by a worker warp when it was not.
-//   r kept:    its predecessor's run ends -> the predecessor (a plain kept row) is copied to its destination, or the
-//              running sum of the run is divided by T(L + 1) in place (main.py:314-317)
-//   r merged:  T(sum + r) into the anchor's destination row (main.py:304-311), then r's state word (anchor, members)
-// Returns false if the predecessor's state word is still missing after a short wait (the caller puts the item back).
-template <int DT>
-__device__ __noinline__ bool emit_from_global(const FusedArgs& a, int r, int flag, int lane, int* err) {
-    const int2 lk = __ldg(a.link + r);
-    const int p = lk.x;
-    if (p < 0) return true;
-    const unsigned long long st_p = poll_state(a.fstate, p, 24);
-    if (state_type(st_p) == 0) return false;
-    const bool p_merged = state_type(st_p) == 1;
-    if (p_merged) __threadfence();                          // acquire: the running sum was written before the state word
-    const int d_a = state_dst(st_p), L_p = p_merged ? state_len(st_p) : 0, nvec = a.nvec;
-    const int64_t row_bytes = a.row_bytes;
-    char* orow = a.out + (int64_t)d_a * row_bytes;
-    const char* sum = p_merged ? orow : a.hidden + (int64_t)p * row_bytes;
-    const char* own = a.hidden + (int64_t)r * row_bytes;
-    const bool finish = !flag || lk.y < 0;                  // the run ends here (the closing row, or the end of the chain)
-    const Divider<DT> dv((flag ? L_p + 1 : L_p) + 1);
-    if (!flag && !p_merged) {
-        copy_row(sum, orow, nvec, lane);
-    } else {
-#pragma unroll 1
-        for (int vb = 0; vb < nvec; vb += 128) {
-            uint4 x[4], y[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int v = vb + 32 * q + lane;
-                if (v < nvec) {
-                    x[q] = ld_cg16(sum + (int64_t)v * 16);
-                    if (flag) y[q] = ldg16(own + (int64_t)v * 16);
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int v = vb + 32 * q + lane;
-                if (v < nvec) {
-                    uint4 t = flag ? Num<DT>::add_vec(x[q], y[q]) : x[q];
-                    if (finish) t = dv.vec_fast(t);
-                    st_stream16(orow + (int64_t)v * 16, t);
-                }
-            }
-        }
-    }
-    if (flag) {
-        if (lk.y < 0 && lane == 0) a.link_next[d_a].y = -1;
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence();                                // the sum is visible before the state word that announces it
-            st_relaxed64(a.fstate + r, state_merged(d_a, L_p + 1));
-        }
-    }
-    return true;
-}
-
 // ---- shared memory behind the row slots: the hand-over rings between the three kinds of warps of a CTA
 //   tile warps --(tile, kept / merged masks)--> scan warp --(tile, prefix, kept mask)--> aux workers
 constexpr unsigned long long FU_ITEM_TILE = 1ull << 62, FU_ITEM_EXIT = 3ull << 62;
 // worker items: bits [63:62] kind
 //   POST  (tile << 38) | (exclusive prefix << 8) | kept mask: aux rows and next-call links of the tile's kept rows
-//   EMIT  (row << 1) | merged flag: the emission step of a row whose predecessor's state was not published in time
 //   COPY  (row << 31) | destination: a kept row that writes itself (chain tail, row outside the chains)
 //   LINK  (row << 31) | destination: the next-call link of one kept row whose predecessor's state was late
-constexpr unsigned long long FU_W_POST = 0ull << 62, FU_W_EMIT = 1ull << 62, FU_W_COPY = 2ull << 62, FU_W_LINK = 3ull << 62;
+constexpr unsigned long long FU_W_POST = 0ull << 62, FU_W_COPY = 2ull << 62, FU_W_LINK = 3ull << 62;
 
 struct FusedQueue {                                         // several producer lanes, several consumer warps
     unsigned long long item[FU_QSIZE];
@@ -292,7 +226,7 @@ struct FusedQueue {                                         // several producer 
 };
 
 struct FusedShared {
-    unsigned long long bars[FU_WARPS];                      // one mbarrier per tile warp
+    unsigned long long bars[2 * FU_WARPS];                  // two mbarriers per tile warp: row loads, running-sum loads
     int flags[2][FU_WARPS];                                 // per iteration parity: 0 kept, 1 merged away, 2 no row
     int next_tile[2], next_iter[2];                         // the ticket of the next tile, valid once next_iter == iteration + 1
     unsigned long long scan_item[FU_SCANQ];                 // tile warps (thread 0) -> scan warp
@@ -403,16 +337,19 @@ __device__ __forceinline__ void tile_barrier(int n_threads) {                   
     asm volatile("bar.sync 1, %0;" :: "r"(n_threads) : "memory");
 }
 
-// CTA = W tile warps (W rows per tile, two shared-memory slots each) + one scan warp + FU_WORKERS - 1 aux workers.
+// CTA = W tile warps (W rows per tile, four shared-memory slots each) + one scan warp + FU_WORKERS - 1 workers.
 template <int DT>
 __global__ void __launch_bounds__((FU_WARPS + FU_WORKERS) * 32, 2)
 k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPack aux) {
     extern __shared__ __align__(128) unsigned char fu_smem[];
     pdl_enter();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, W = a.tile_rows;
-    FusedShared* sh = reinterpret_cast<FusedShared*>(fu_smem + (size_t)(2 * W) * a.slot_bytes);
+    FusedShared* sh = reinterpret_cast<FusedShared*>(fu_smem + (size_t)(4 * W) * a.slot_bytes);
     unsigned long long* D = a.desc + 1;
-    if (wid < W && lane == 0) mbar_init(smem_u32(&sh->bars[wid]), 1);
+    if (wid < W && lane == 0) {
+        mbar_init(smem_u32(&sh->bars[2 * wid]), 1);
+        mbar_init(smem_u32(&sh->bars[2 * wid + 1]), 1);
+    }
     if (threadIdx.x == 0) {
         sh->next_tile[0] = (int)atomicAdd(a.desc, 1ull);
         sh->next_iter[0] = sh->next_iter[1] = 0;
@@ -428,24 +365,12 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
     const int64_t row_bytes = a.row_bytes;
 
     if (wid > W) {
-        // ---- workers: everything that may have to wait or that nobody waits for — aux rows, next-call links, rows that write
-        // themselves, and the emission steps the tile warps could not do on the spot.  A worker does not sit on an item whose
-        // predecessor state is missing while the ring has room: the item goes back to the end of the ring.
+        // ---- workers: what nobody waits for — aux rows, next-call links, rows that write themselves.  A link whose
+        // predecessor state is missing goes back to the end of the ring while there is room.
         FusedQueue* q = &sh->auxq;
         unsigned long long item;
         while (queue_pop(q, lane, &item)) {
-            if ((item & (3ull << 62)) == FU_W_EMIT) {
-                const int r = (int)((item >> 1) & 0x3fffffffull), flag = (int)(item & 1ull);
-                int tries = 0;
-                while (!emit_from_global<DT>(a, r, flag, lane, &err)) {
-                    int back = 0;
-                    if (lane == 0) back = queue_push(q, item) ? 1 : 0;
-                    if (__shfl_sync(FULL, back, 0)) break;
-                    if (++tries > (FU_SPIN_LIMIT >> 4)) { err = 1; break; }
-                }
-            } else {
-                run_post_item<DT>(a, aux, q, W, item, lane, &err, true);
-            }
+            run_post_item<DT>(a, aux, q, W, item, lane, &err, true);
             queue_complete(q, lane);
         }
         if (err && lane == 0) a.status[FF_ST_INTERNAL] = 1;
@@ -458,16 +383,18 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
         unsigned head = 0;
         while (true) {
             int spins = 0;
+            bool dead = false;
             while (*(volatile unsigned*)&sh->scan_tail == head) {
-                if (++spins > (FU_SPIN_LIMIT << 4)) { err = 1; break; }
+                if (++spins > (FU_SPIN_LIMIT << 6)) { dead = true; break; }     // seconds without a tile: the tile warps are gone
                 __nanosleep(100);
             }
+            if (dead) { err = 1; break; }
             __threadfence_block();
             const unsigned long long item = *(volatile unsigned long long*)&sh->scan_item[head % FU_SCANQ];
             __syncwarp();
             ++head;
             if (lane == 0) *(volatile unsigned*)&sh->scan_head = head;
-            if (err || (item & (3ull << 62)) == FU_ITEM_EXIT) break;
+            if ((item & (3ull << 62)) == FU_ITEM_EXIT) break;
             const int tile = (int)((item >> 16) & 0xffffffull);
             const unsigned kept = (unsigned)(item >> 8) & 0xffu, merged = (unsigned)item & 0xffu;
             const int total = __popc(kept);
@@ -547,26 +474,92 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
         return;
     }
 
-    // ---- tile warps.  Per warp: slot P (chain predecessor) and slot C (own row), one mbarrier for both
-    unsigned char* slot_p = fu_smem + (size_t)(2 * wid) * a.slot_bytes;
-    unsigned char* slot_c = slot_p + a.slot_bytes;
-    const uint32_t sp32 = smem_u32(slot_p), sc32 = smem_u32(slot_c), bar = smem_u32(&sh->bars[wid]);
-    const uint4* pr = reinterpret_cast<const uint4*>(slot_p);
-    const uint4* cr = reinterpret_cast<const uint4*>(slot_c);
+    // ---- tile warps.  Per warp: two slot sets {P: chain predecessor, C: own row}, used alternately, so that the emission
+    // step of tile k - 1 runs while the rows of tile k travel — by then the predecessor's state word is an iteration old.
+    unsigned char* set0 = fu_smem + (size_t)(4 * wid) * a.slot_bytes;
+    const uint32_t barL = smem_u32(&sh->bars[2 * wid]), barS = smem_u32(&sh->bars[2 * wid + 1]);
     int tile = sh->next_tile[0];
     int iter = 0;
-    uint32_t phase = 0;
+    uint32_t phaseL = 0, phaseS = 0;
     bool store_pending = false;                             // lane 0: a bulk store may still be reading a slot
+    // the row of the previous tile whose emission step is still to do
+    bool prev_todo = false;
+    int prev_r = 0, prev_p = 0, prev_flag = 0, prev_sc = 0, prev_tile = 0;
+    unsigned long long prev_st = 0;
 
-    while (tile < a.ntiles) {
+    // The emission step of row prev_r out of slot set `ps`: its predecessor's run ends, or grows by this row.
+    auto emit_prev = [&](unsigned char* ps) {
+        const uint4* pr = reinterpret_cast<const uint4*>(ps);
+        const uint4* cr = reinterpret_cast<const uint4*>(ps + a.slot_bytes);
+        const uint32_t sp32 = smem_u32(ps);
+        const bool p_merged = state_type(prev_st) == 1;
+        if (p_merged) {
+            // the predecessor is inside a run: its raw row has served (the similarity); fetch the running sum of the run — the
+            // anchor's destination row, written before the state word was — into slot P
+            if (lane == 0) {
+                __threadfence();                            // acquire: the state word was read with a relaxed load
+                asm volatile("fence.proxy.async;" ::: "memory");   // ... and the row is fetched through the async proxy
+                mbar_expect_tx(barS, (uint32_t)row_bytes);
+                tma_load(sp32, a.out + (int64_t)state_dst(prev_st) * row_bytes, (uint32_t)row_bytes, barS);
+            }
+            mbar_wait(barS, phaseS);
+            phaseS ^= 1u;
+        }
+        const int d_a = state_dst(prev_st);                 // destination row of the run's anchor (the predecessor itself if kept)
+        const int L_p = p_merged ? state_len(prev_st) : 0;
+        char* orow = a.out + (int64_t)d_a * row_bytes;
+        if (!prev_flag) {
+            // this row ends the run of its predecessor
+            if (!p_merged) {                                // a plain kept row: the staged copy goes out as it is
+                if (lane == 0) {
+                    tma_store(orow, sp32, (uint32_t)row_bytes);
+                    tma_commit();
+                    store_pending = true;
+                }
+            } else {                                        // T(sum / T(L + 1)), main.py:314-317
+                const Divider<DT> dv(L_p + 1);
+#pragma unroll 2
+                for (int vb = 0; vb < nvec; vb += 32)
+                    if (vb + lane < nvec) st_stream16(orow + (int64_t)(vb + lane) * 16, dv.vec_fast(pr[vb + lane]));
+            }
+        } else {
+            // this row is merged away: T(sum + row), main.py:304-311; slot P holds the sum so far (the anchor's raw row if this
+            // is the first member)
+            const int L = L_p + 1;
+            if (prev_sc < 0) {                              // ... and the chain ends here: finish the run as well
+                const Divider<DT> dv(L + 1);
+#pragma unroll 2
+                for (int vb = 0; vb < nvec; vb += 32)
+                    if (vb + lane < nvec)
+                        st_stream16(orow + (int64_t)(vb + lane) * 16, dv.vec_fast(Num<DT>::add_vec(pr[vb + lane], cr[vb + lane])));
+                if (lane == 0) a.link_next[d_a].y = -1;
+            } else {
+#pragma unroll 2
+                for (int vb = 0; vb < nvec; vb += 32)
+                    if (vb + lane < nvec)
+                        st_stream16(orow + (int64_t)(vb + lane) * 16, Num<DT>::add_vec(pr[vb + lane], cr[vb + lane]));
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();                            // the sum is visible before the state word that announces it
+                st_relaxed64(a.fstate + prev_r, state_merged(d_a, L));
+            }
+        }
+        if (lane == 0) FU_STAMP_MAX(prev_tile, 11);
+        prev_todo = false;
+    };
+
+    while (tile < a.ntiles || prev_todo) {
         const int par = iter & 1;
-        if (threadIdx.x == 0) FU_STAMP(tile, 0);
-        // the next tile's ticket travels during this iteration (nothing in an iteration waits for another tile any more, so
-        // a ticket is never held for long)
+        const bool live = tile < a.ntiles;                  // false: only the last tile's emission step is left
+        unsigned char* cs = set0 + (size_t)(2 * par) * a.slot_bytes;         // slot set of this iteration
+        unsigned char* ps = set0 + (size_t)(2 * (par ^ 1)) * a.slot_bytes;   // ... of the previous one
+        if (live && threadIdx.x == 0) FU_STAMP(tile, 0);
+        // the next tile's ticket travels during this iteration
         int nt = 0;
-        if (threadIdx.x == 0) nt = (int)atomicAdd(a.desc, 1ull);
+        if (live && threadIdx.x == 0) nt = (int)atomicAdd(a.desc, 1ull);
         const int r = tile * W + wid;
-        const bool valid = r < a.S;
+        const bool valid = live && r < a.S;
         int2 lk = make_int2(-2, -2);
         if (valid) lk = __ldg(a.link + r);
         const int p = lk.x, sc = lk.y;
@@ -574,20 +567,29 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
         __syncwarp();                                       // a successor or a worker writes them
         if (has_pred && lane == 0) {
             if (store_pending) { tma_wait_read_0(); store_pending = false; }
-            mbar_expect_tx(bar, (uint32_t)row_bytes * 2u);
-            tma_load(sc32, a.hidden + (int64_t)r * row_bytes, (uint32_t)row_bytes, bar);
-            tma_load(sp32, a.hidden + (int64_t)p * row_bytes, (uint32_t)row_bytes, bar);
+            mbar_expect_tx(barL, (uint32_t)row_bytes * 2u);
+            tma_load(smem_u32(cs + a.slot_bytes), a.hidden + (int64_t)r * row_bytes, (uint32_t)row_bytes, barL);
+            tma_load(smem_u32(cs), a.hidden + (int64_t)p * row_bytes, (uint32_t)row_bytes, barL);
         }
         if (valid) prefetch_aux(aux, r, lane);
+        // while the rows travel: the previous tile's emission step, if its predecessor's state word is there (it nearly
+        // always is: that row's tile posted an iteration ago at the latest)
+        if (prev_todo) {
+            if (state_type(prev_st) == 0) prev_st = ld_relaxed64(a.fstate + prev_p);
+            if (lane == 0) FU_STAMP_MAX(prev_tile, 9);
+            if (state_type(prev_st) != 0) emit_prev(ps);
+        }
         float s = -2.0f;                                    // IGNORE_TOKEN at chain heads (main.py:225-238)
         int flag = 0;
         if (has_pred) {
-            mbar_wait(bar, phase);
-            phase ^= 1u;
+            mbar_wait(barL, phaseL);
+            phaseL ^= 1u;
         }
-        if (threadIdx.x == 0) FU_STAMP(tile, 1);
-        if (lane == 0) FU_STAMP_MAX(tile, 10);
+        if (live && threadIdx.x == 0) FU_STAMP(tile, 1);
+        if (live && lane == 0) FU_STAMP_MAX(tile, 10);
         if (has_pred) {
+            const uint4* pr = reinterpret_cast<const uint4*>(cs);
+            const uint4* cr = reinterpret_cast<const uint4*>(cs + a.slot_bytes);
             float dot = 0.f, na = 0.f, nb = 0.f;
 #pragma unroll 4
             for (int vb = 0; vb < nvec; vb += 32)           // lane l sums vectors l, l + 32, ... in this order (as k_similarity)
@@ -598,127 +600,72 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             s = finish_cosine<DT>(dot, na, nb);
             flag = (s >= a.thr);                            // NaN compares false
         }
-        if (lane == 0) {
-            if (valid) a.sim_seq[r] = s;
-            *(volatile int*)&sh->flags[par][wid] = valid ? flag : 2;
-        }
-        // the predecessor's state word: its tile is ~P / W tiles back, usually published by now.  Asked once, never waited for.
-        unsigned long long st_p = 0;
-        if (has_pred) st_p = ld_relaxed64(a.fstate + p);
-        tile_barrier(W * 32);                               // (A) the tile's flags are in shared memory
-        if (threadIdx.x == 0) {
-            FU_STAMP(tile, 2);
-            // the tile's count goes out at once: nobody's look-back ever waits for more than the rows of a tile to arrive
-            unsigned kept = 0, merged = 0;
+        if (live) {
+            if (lane == 0) {
+                if (valid) a.sim_seq[r] = s;
+                *(volatile int*)&sh->flags[par][wid] = valid ? flag : 2;
+            }
+            tile_barrier(W * 32);                           // (A) the tile's flags are in shared memory
+            if (threadIdx.x == 0) {
+                FU_STAMP(tile, 2);
+                // the tile's count goes out at once: nobody's look-back ever waits for more than the rows of a tile to arrive
+                unsigned kept = 0, merged = 0;
 #pragma unroll
-            for (int w = 0; w < FU_WARPS; ++w)
-                if (w < W) {
-                    const int f = *(volatile int*)&sh->flags[par][w];
-                    kept |= (unsigned)(f == 0) << w;
-                    merged |= (unsigned)(f == 1) << w;
+                for (int w = 0; w < FU_WARPS; ++w)
+                    if (w < W) {
+                        const int f = *(volatile int*)&sh->flags[par][w];
+                        kept |= (unsigned)(f == 0) << w;
+                        merged |= (unsigned)(f == 1) << w;
+                    }
+                tile_post(D, tile, __popc(kept), 0);
+                const unsigned t = sh->scan_tail;
+                int spins = 0;
+                while ((int)(t - *(volatile unsigned*)&sh->scan_head) >= FU_SCANQ) {
+                    if (++spins > FU_SPIN_LIMIT) { err = 1; break; }
+                    __nanosleep(100);
                 }
-            tile_post(D, tile, __popc(kept), 0);
-            const unsigned t = sh->scan_tail;
-            int spins = 0;
-            while ((int)(t - *(volatile unsigned*)&sh->scan_head) >= FU_SCANQ) {
-                if (++spins > FU_SPIN_LIMIT) { err = 1; break; }
-                __nanosleep(100);
+                *(volatile unsigned long long*)&sh->scan_item[t % FU_SCANQ] = FU_ITEM_TILE | ((unsigned long long)tile << 16) | (kept << 8) | merged;
+                __threadfence_block();
+                *(volatile unsigned*)&sh->scan_tail = t + 1;
+                *(volatile int*)&sh->next_tile[par] = nt;
+                __threadfence_block();
+                *(volatile int*)&sh->next_iter[par] = iter + 1;
+                FU_STAMP(tile, 3);
             }
-            *(volatile unsigned long long*)&sh->scan_item[t % FU_SCANQ] = FU_ITEM_TILE | ((unsigned long long)tile << 16) | (kept << 8) | merged;
-            __threadfence_block();
-            *(volatile unsigned*)&sh->scan_tail = t + 1;
-            *(volatile int*)&sh->next_tile[par] = nt;
-            __threadfence_block();
-            *(volatile int*)&sh->next_iter[par] = iter + 1;
-            FU_STAMP(tile, 3);
         }
-        // ---- the emission step of this row (its predecessor's run ends, or grows by this row)
-        if (has_pred) {
-            int tp = state_type(st_p);
-            if (lane == 0) FU_STAMP_MAX(tile, 9);
-            bool deferred = false;
-            if (tp == 0) {
-                // not published yet: a worker does the step later, out of the L2, and this warp moves on (ring full: wait here)
-                int ok = 0;
-                if (lane == 0) ok = queue_push(&sh->auxq, FU_W_EMIT | ((unsigned long long)r << 1) | (unsigned long long)flag) ? 1 : 0;
-                deferred = __shfl_sync(FULL, ok, 0) != 0;
-                if (!deferred) {
-                    st_p = wait_state(a.fstate, p, &err);
-                    tp = state_type(st_p);
-                }
+        // the previous tile's emission step if it could not be done above: now this warp waits (its count is out already)
+        if (prev_todo) {
+            prev_st = wait_state(a.fstate, prev_p, &err);
 #ifdef FF_FUSED_TRACE
-                if (lane == 0 && a.trace) atomicAdd((unsigned long long*)&a.trace[(size_t)tile * FU_TRACE_SLOTS + 12], 1ull);
+            if (lane == 0 && a.trace) atomicAdd((unsigned long long*)&a.trace[(size_t)prev_tile * FU_TRACE_SLOTS + 12], 1ull);
 #endif
-            }
-            if (!deferred && tp != 0) {
-                const bool p_merged = tp == 1;
-                if (p_merged) {
-                    // the predecessor is inside a run: its raw row has served (the similarity); fetch the running sum of the
-                    // run — the anchor's destination row, written before the state word was — into slot P
-                    if (lane == 0) {
-                        __threadfence();                    // acquire: the state word was read with a relaxed load
-                        asm volatile("fence.proxy.async;" ::: "memory");   // ... and the row is fetched through the async proxy
-                        mbar_expect_tx(bar, (uint32_t)row_bytes);
-                        tma_load(sp32, a.out + (int64_t)state_dst(st_p) * row_bytes, (uint32_t)row_bytes, bar);
-                    }
-                    mbar_wait(bar, phase);
-                    phase ^= 1u;
-                }
-                const int d_a = state_dst(st_p);            // destination row of the run's anchor (the predecessor itself if kept)
-                const int L_p = p_merged ? state_len(st_p) : 0;
-                char* orow = a.out + (int64_t)d_a * row_bytes;
-                if (!flag) {
-                    // this row ends the run of its predecessor
-                    if (!p_merged) {                        // a plain kept row: the staged copy goes out as it is
-                        if (lane == 0) {
-                            tma_store(orow, sp32, (uint32_t)row_bytes);
-                            tma_commit();
-                            store_pending = true;
-                        }
-                    } else {                                // T(sum / T(L + 1)), main.py:314-317
-                        const Divider<DT> dv(L_p + 1);
-#pragma unroll 2
-                        for (int vb = 0; vb < nvec; vb += 32)
-                            if (vb + lane < nvec) st_stream16(orow + (int64_t)(vb + lane) * 16, dv.vec_fast(pr[vb + lane]));
-                    }
-                } else {
-                    // this row is merged away: T(sum + row), main.py:304-311; slot P holds the sum so far (the anchor's raw
-                    // row if this is the first member)
-                    const int L = L_p + 1;
-                    if (sc < 0) {                           // ... and the chain ends here: finish the run as well
-                        const Divider<DT> dv(L + 1);
-#pragma unroll 2
-                        for (int vb = 0; vb < nvec; vb += 32)
-                            if (vb + lane < nvec)
-                                st_stream16(orow + (int64_t)(vb + lane) * 16, dv.vec_fast(Num<DT>::add_vec(pr[vb + lane], cr[vb + lane])));
-                        if (lane == 0) a.link_next[d_a].y = -1;
-                    } else {
-#pragma unroll 2
-                        for (int vb = 0; vb < nvec; vb += 32)
-                            if (vb + lane < nvec)
-                                st_stream16(orow + (int64_t)(vb + lane) * 16, Num<DT>::add_vec(pr[vb + lane], cr[vb + lane]));
-                    }
-                    __syncwarp();
-                    if (lane == 0) {
-                        __threadfence();                    // the sum is visible before the state word that announces it
-                        st_relaxed64(a.fstate + r, state_merged(d_a, L));
-                    }
-                }
-            }
+            if (state_type(prev_st) != 0) emit_prev(ps);
+            prev_todo = false;
         }
-        if (threadIdx.x == 0) FU_STAMP(tile, 5);
-        if (lane == 0) FU_STAMP_MAX(tile, 11);
-        // the next tile (thread 0 always gets there: its own waits are bounded.  All tile warps must see the same tile.)
-        while (*(volatile int*)&sh->next_iter[par] != iter + 1) __nanosleep(20);
-        __threadfence_block();
-        tile = *(volatile int*)&sh->next_tile[par];
+        // this tile's row becomes the pending one
+        if (has_pred) {
+            prev_todo = true;
+            prev_r = r; prev_p = p; prev_flag = flag; prev_sc = sc; prev_tile = tile;
+            prev_st = ld_relaxed64(a.fstate + p);
+        }
+        if (live) {
+            if (threadIdx.x == 0) FU_STAMP(tile, 5);
+            // the next tile (thread 0 always gets there: its own waits are bounded.  All tile warps must see the same tile.)
+            while (*(volatile int*)&sh->next_iter[par] != iter + 1) __nanosleep(20);
+            __threadfence_block();
+            tile = *(volatile int*)&sh->next_tile[par];
+        }
         ++iter;
     }
 
     tile_barrier(W * 32);
     if (threadIdx.x == 0) {
         const unsigned t = sh->scan_tail;
-        while ((int)(t - *(volatile unsigned*)&sh->scan_head) >= FU_SCANQ) __nanosleep(100);
+        int spins = 0;
+        while ((int)(t - *(volatile unsigned*)&sh->scan_head) >= FU_SCANQ) {
+            if (++spins > FU_SPIN_LIMIT) { err = 1; break; }
+            __nanosleep(100);
+        }
         *(volatile unsigned long long*)&sh->scan_item[t % FU_SCANQ] = FU_ITEM_EXIT;
         __threadfence_block();
         *(volatile unsigned*)&sh->scan_tail = t + 1;
