@@ -80,6 +80,8 @@ struct ff_ctx {
     int last_fused;      // the last merge call ran the read-once kernel: sim[] is indexed by sequence row
     int fused_clean[2];  // state words / tile descriptors of the bank are known to be zero
     int fused_attr[3];   // dynamic shared memory the kernel of each dtype was last opted in for
+    char* scratch;       // running sums of the read-once kernel: one row per sequence row (touched at run anchors only)
+    size_t scratch_bytes;
     int sm_count;
     int max_smem;        // opt-in dynamic shared memory per block
     int smem_per_sm, smem_reserved;   // shared memory of an SM / what the system keeps per resident block
@@ -119,7 +121,8 @@ struct Ws {
     float* sim;
     uint8_t* flag;
     int2* link[2];      // [cap] (pred, succ) of every sequence row (read-once kernel)
-    unsigned long long* fstate[2];   // [cap] its state words
+    unsigned long long* fflag[2];    // [cap] its front flags
+    unsigned* fdst[2];               // [cap] its destination words
     unsigned long long* desc[2];     // [1 + tiles] ticket + tile descriptors
     int* dst[2];
     int* srcidx;
@@ -151,7 +154,8 @@ Ws carve(void* base_ptr, int64_t cap, int64_t n_ids) {
     w.barrier = (unsigned*)take(256);
     w.sel_hist = (int*)take(4 * 256 * 4);
     for (int b = 0; b < 2; ++b) {
-        w.fstate[b] = (unsigned long long*)take((size_t)cap * 8);
+        w.fflag[b] = (unsigned long long*)take((size_t)cap * 8);
+        w.fdst[b] = (unsigned*)take((size_t)cap * 4);
         w.desc[b] = (unsigned long long*)take(((size_t)(cap + 1) / 2 + 2) * 8);
     }
     w.zero_begin = zero_begin;
@@ -353,11 +357,11 @@ int check_shape(int64_t S, int64_t H, int dtype) {
 // shared memory of one CTA of the read-once kernel besides the row slots: mbarriers, tile scratch, the worker queue
 constexpr int FU_SMEM_EXTRA = (int)sizeof(FusedShared);
 
-// rows per tile (= tile warps per CTA) of the read-once kernel: two CTAs per SM, four slots per warp; 0 = rows too long
+// rows per tile (= tile warps per CTA) of the read-once kernel: two CTAs per SM, two slots per warp; 0 = rows too long
 int fused_tile_rows(const ff_ctx* ctx, int64_t row_bytes) {
     const int64_t slot = (row_bytes + 127) / 128 * 128;
     const int64_t per_cta = ctx->smem_per_sm / 2 - ctx->smem_reserved;
-    int64_t w = (per_cta - FU_SMEM_EXTRA) / (4 * slot);
+    int64_t w = (per_cta - FU_SMEM_EXTRA) / (2 * slot);
     if (w > FU_WARPS) w = FU_WARPS;
     return w < 1 ? 0 : (int)w;
 }
@@ -393,12 +397,23 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
     a.nvec = a.row_bytes / 16;
     a.slot_bytes = (a.row_bytes + 127) / 128 * 128;
     a.tile_rows = fused_tile_rows(ctx, a.row_bytes);
+    const size_t need_scratch = (size_t)S * (size_t)a.row_bytes;
+    if (need_scratch > ctx->scratch_bytes) {               // grows rarely: once per model shape / longest sequence
+        if (ctx->scratch) cudaFree(ctx->scratch);
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+        FF_CUDA(cudaMalloc((void**)&ctx->scratch, need_scratch));
+        ctx->scratch_bytes = need_scratch;
+    }
+    a.scratch = ctx->scratch;
     a.ntiles = (int)((S + a.tile_rows - 1) / a.tile_rows);
     a.link = w.link[bank];
     a.link_next = w.link[nb];
-    a.fstate = w.fstate[bank];
+    a.fflag = w.fflag[bank];
+    a.fdst = w.fdst[bank];
     a.desc = w.desc[bank];
-    a.fstate_clr = w.fstate[nb];
+    a.fflag_clr = w.fflag[nb];
+    a.fdst_clr = w.fdst[nb];
     a.desc_clr = w.desc[nb];
     a.sim_seq = w.sim;
     a.dst = w.dst[bank];
@@ -408,13 +423,14 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
     a.thr = (float)thr;
     a.bound = bound;
     if (!ctx->fused_clean[bank]) {
-        FF_CUDA(cudaMemsetAsync(w.fstate[bank], 0, (size_t)S * 8, st));
+        FF_CUDA(cudaMemsetAsync(w.fflag[bank], 0, (size_t)S * 8, st));
+        FF_CUDA(cudaMemsetAsync(w.fdst[bank], 0, (size_t)S * 4, st));
         FF_CUDA(cudaMemsetAsync(w.desc[bank], 0, ((size_t)a.ntiles + 1) * 8, st));
     }
     ctx->fused_clean[bank] = 0;
     ctx->fused_clean[nb] = 1;                              // the kernel clears the other bank on its way out
     ctx->h_status[FF_ST_INTERNAL] = 0;
-    const int smem = 4 * a.tile_rows * a.slot_bytes + FU_SMEM_EXTRA;
+    const int smem = 2 * a.tile_rows * a.slot_bytes + FU_SMEM_EXTRA;
     const int threads = (a.tile_rows + FU_WORKERS) * 32;
     return dispatch_dtype(dtype, [&](auto dt) {
         constexpr int DT = decltype(dt)::value;
@@ -470,6 +486,8 @@ int ff_ctx_create(int device, ff_ctx** out) {
     c->last_fused = 0;
     c->fused_clean[0] = c->fused_clean[1] = 0;
     c->fused_attr[0] = c->fused_attr[1] = c->fused_attr[2] = 0;
+    c->scratch = nullptr;
+    c->scratch_bytes = 0;
     cudaError_t e = cudaHostAlloc((void**)&c->h_status, FF_ST_SLOTS * 8, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e != cudaSuccess) { delete c; return fail(FF_E_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
     memset(c->h_status, 0, FF_ST_SLOTS * 8);
@@ -487,6 +505,7 @@ int ff_ctx_create(int device, ff_ctx** out) {
 
 int ff_ctx_destroy(ff_ctx* ctx) {
     if (!ctx) return FF_OK;
+    if (ctx->scratch) cudaFree(ctx->scratch);
     cudaFreeHost(ctx->h_status);
     delete ctx;
     return FF_OK;

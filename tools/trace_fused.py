@@ -1,10 +1,8 @@
 """Development aid: per-tile time stamps of the read-once merge kernel (a separate library built with -DFF_FUSED_TRACE).
 
     python tools/trace_fused.py [--cfg C2]      -> gpurun_out/trace_fused_<cfg>.npy + a summary on stdout
-Stamps per tile (ns, globaltimer): 0 iteration start, 1 rows of warp 0 arrived, 2 barrier (A) passed, 3 count posted and
-scan item pushed, 4 predecessor state known (warp 0), 5 iteration end (warp 0), 6 scan warp dequeued the tile, 7 its
-look-back resolved (kept states published), 8 links written, 9 / 10 / 11 latest warp: predecessor state known / rows
-arrived / iteration end."""
+Stamps per tile (ns, globaltimer): 0 tile taken, 10 / 9 / 11 latest warp: rows arrived / predecessor flag known / front
+step done, 6 scan warp has the flags, 7 look-back resolved and destinations published, 8 tile handed to the workers."""
 import argparse, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -31,15 +29,21 @@ np.save(out[:-4] + ".npy", t)
 t0 = t[:, 0][t[:, 0] > 0].min()
 us = lambda x: (x - t0) / 1e3
 n = t.shape[0]
-print(f"{n} tiles; kernel span {us(t[:, [5, 8, 11]].max()):.1f} us")
-d = lambda i, j: np.median((t[:, i] - t[:, j])[(t[:, i] > 0) & (t[:, j] > 0)]) / 1e3
-p90 = lambda i, j: np.percentile((t[:, i] - t[:, j])[(t[:, i] > 0) & (t[:, j] > 0)], 90) / 1e3
-for name, i, j in [("rows arrive (warp 0)", 1, 0), ("rows arrive (last warp)", 10, 0), ("barrier A after last rows", 2, 10), ("post+push", 3, 2),
-                   ("pred state known, warp 0, after A", 4, 2), ("pred state known, last warp, after A", 9, 2), ("iteration (warp 0)", 5, 0),
-                   ("iteration (last warp)", 11, 0), ("scan dequeue after push", 6, 3), ("look-back", 7, 6), ("scan tail (pushes)", 8, 7),
-                   ("publish after iteration start", 7, 0)]:
-    print(f"  {name:40s} median {d(i, j):7.2f} us   p90 {p90(i, j):7.2f} us")
-print(f"  deferred emission steps: {int(t[:, 12].sum())} of {n * 8} rows")
+print(f"{n} tiles; kernel span {us(t[:, [8, 11]].max()):.1f} us")
+def dd(i, j):
+    m = (t[:, i] > 0) & (t[:, j] > 0)
+    if not m.any():
+        return "no samples"
+    x = (t[:, i] - t[:, j])[m] / 1e3
+    return f"median {np.median(x):7.2f} us   p90 {np.percentile(x, 90):7.2f} us   max {x.max():7.2f} us"
+# stamps: 0 tile taken (thread 0), 10 rows arrived (latest warp), 9 predecessor flag known (latest warp), 11 front step done
+# (latest warp), 6 scan warp has the tile's flags, 7 look-back resolved / destinations published, 8 tile handed to the workers
+for name, i, j in [("rows arrive (latest warp)", 10, 0), ("predecessor flag known (latest warp)", 9, 0), ("front step done (latest warp)", 11, 0),
+                   ("scan has the flags, after front done", 6, 11), ("look-back", 7, 6), ("hand-over to workers", 8, 7),
+                   ("destinations after tile taken", 7, 0)]:
+    print(f"  {name:40s} {dd(i, j)}")
+st = np.sort(t[:, 0][t[:, 0] > 0])
+print(f"  tiles taken per us (middle half): {(len(st) // 2) / ((st[3 * len(st) // 4] - st[len(st) // 4]) / 1e3):.1f}")
 for q in (0.1, 0.25, 0.5, 0.75, 1.0):
     k = min(int(q * n), n - 1)
-    print(f"  tile {k:5d}: start {us(t[k, 0]):7.1f}  published {us(t[k, 7]):7.1f}  end {us(t[k, 11]):7.1f}")
+    print(f"  tile {k:5d}: taken {us(t[k, 0]):7.1f}  front done {us(t[k, 11]):7.1f}  destinations {us(t[k, 7]):7.1f}  handed over {us(t[k, 8]):7.1f}")
