@@ -17,9 +17,10 @@
 //     order — the sequence torch-CPU index_add_ performs (main.py:304-311).  The sum lives in a scratch row named
 //     after the run's ANCHOR ROW (not its destination, which nobody knows yet); the first member finds both operands
 //     in its slots, a later one fetches the sum (an L2 hit, by TMA).  The row that ends a run divides it once by T(L+1)
-//     (main.py:314-317).  Each row then publishes its front flag: kept, or merged + (anchor row, members so far) —
-//     all the next row of the chain needs.  The only thing a front warp ever waits for is the front flag of its
-//     predecessor: another front step, ~P / W tiles back, never a look-back.
+//     (main.py:314-317).  Each row publishes its front flag in two steps: kept / merged right after the similarity
+//     (all the scan needs), then DONE with (anchor row, members so far) once its step is complete — what the next row
+//     of a run needs.  The only thing a front warp ever waits for is the front flag of its predecessor: another front
+//     step, ~P / W tiles back, never a look-back; and only inside runs does one step wait for another step's end.
 //   SCAN (one warp per CTA).  Collects the front flags of each of the CTA's tiles, posts the tile's kept-row count,
 //     resolves the exclusive prefix by decoupled look-back over the tile descriptors, publishes the destinations.
 //   WORKERS.  Per tile: every kept row whose run is complete (the row that ended it is in this tile) is copied — the
@@ -138,22 +139,26 @@ __device__ __forceinline__ void st_relaxed32(unsigned* p, unsigned v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
-// front flag of a row: bits [1:0] 0 = not yet known, 1 = merged away, 2 = kept; merged away: bits [31:2] the row of its
-// run's anchor, bits [63:32] members of the run so far
-__device__ __forceinline__ unsigned long long flag_kept() { return 2ull; }
-__device__ __forceinline__ unsigned long long flag_merged(int anchor, int L) {
-    return 1ull | ((unsigned long long)(uint32_t)anchor << 2) | ((unsigned long long)(uint32_t)L << 32);
+// front flag of a row, published in two steps.  Bits [1:0], right after the similarity: 0 = not yet known, 1 = merged away,
+// 2 = kept — all the scan warp needs, and all a successor needs of a kept row.  Bit 2 (DONE), when the row's front step is
+// complete: for a merged-away row bits [32:3] then hold the row of its run's anchor and bits [63:33] the members of the run
+// so far, and the running sum in the scratch row includes this row; for a kept row, the run it ended has been divided.
+constexpr unsigned long long FU_DONE = 4ull;
+__device__ __forceinline__ unsigned long long flag_kept_done() { return 2ull | FU_DONE; }
+__device__ __forceinline__ unsigned long long flag_merged_done(int anchor, int L) {
+    return 1ull | FU_DONE | ((unsigned long long)(uint32_t)anchor << 3) | ((unsigned long long)(uint32_t)L << 33);
 }
 __device__ __forceinline__ int flag_type(unsigned long long f) { return (int)(f & 3ull); }
-__device__ __forceinline__ int flag_anchor(unsigned long long f) { return (int)((uint32_t)f >> 2); }
-__device__ __forceinline__ int flag_len(unsigned long long f) { return (int)(f >> 32); }
+__device__ __forceinline__ bool flag_done(unsigned long long f) { return (f & FU_DONE) != 0ull; }
+__device__ __forceinline__ int flag_anchor(unsigned long long f) { return (int)((f >> 3) & 0x3fffffffull); }
+__device__ __forceinline__ int flag_len(unsigned long long f) { return (int)(f >> 33); }
 
 // Waits are for rows with a smaller sequence index, and give up after FU_SPIN_LIMIT polls: *err is set, the caller skips
 // what depended on the value, the kernel always terminates.
-__device__ __forceinline__ unsigned long long wait_flag(const unsigned long long* fflag, int x, int* err) {
-    unsigned long long v = ld_relaxed64(fflag + x);
+__device__ __forceinline__ unsigned long long wait_flag(const unsigned long long* fflag, int x, unsigned long long need, int* err) {
+    unsigned long long v = ld_relaxed64(fflag + x);         // need = 3: the type is there; need = FU_DONE: the step is complete
     int spins = 0;
-    while ((v & 3ull) == 0ull) {
+    while ((v & need) == 0ull) {
         if (++spins > FU_SPIN_LIMIT) { *err = 1; break; }
         __nanosleep(64);
         v = ld_relaxed64(fflag + x);
@@ -308,7 +313,8 @@ __device__ __noinline__ void run_tile_item(const FusedArgs& a, const AuxPack& au
         if (is_kept) {
             d_r = excl + __popc(kept & ((1u << lane) - 1u));
             if (lk.x >= 0) {
-                const unsigned long long fp = ld_relaxed64(a.fflag + lk.x);      // known: this row's front step read it
+                wait_flag(a.fflag, r, FU_DONE, err);        // this row's front step (it divides the run it ends) is complete
+                const unsigned long long fp = ld_relaxed64(a.fflag + lk.x);      // complete as well: this row's step read it
                 const bool run = flag_type(fp) == 1;
                 const int anchor = run ? flag_anchor(fp) : lk.x;
                 const int d_a = wait_dst(a.fdst, anchor, err);
@@ -328,8 +334,8 @@ __device__ __noinline__ void run_tile_item(const FusedArgs& a, const AuxPack& au
                 if (lk.x != -2) a.link_next[d_r].y = -1;
             }
         } else if (lk.x >= 0 && lk.y < 0) {
-            const unsigned long long fr = ld_relaxed64(a.fflag + r);
-            if (flag_type(fr) == 1) {
+            const unsigned long long fr = wait_flag(a.fflag, r, FU_DONE, err);
+            if (flag_type(fr) == 1 && flag_done(fr)) {
                 const int anchor = flag_anchor(fr);
                 const int d_a = wait_dst(a.fdst, anchor, err);
                 if (d_a >= 0) {
@@ -408,7 +414,7 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             const int tile = (int)item;
             const int r = tile * W + lane;
             unsigned long long f = 0;
-            if (lane < W && r < a.S) f = wait_flag(a.fflag, r, &err);
+            if (lane < W && r < a.S) f = wait_flag(a.fflag, r, 3ull, &err);
             const unsigned kept = __ballot_sync(FULL, flag_type(f) == 2), merged = __ballot_sync(FULL, flag_type(f) == 1);
             const int total = __popc(kept);
             if (lane == 0) FU_STAMP(tile, 6);
@@ -538,16 +544,23 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             nb = warp_sum(nb);
             const float s = finish_cosine<DT>(dot, na, nb);
             const int flag = (s >= a.thr);                  // NaN compares false
-            if (lane == 0) a.sim_seq[r] = s;
-            if (flag_type(fp) == 0) fp = wait_flag(a.fflag, p, &err);
+            if (lane == 0) {
+                a.sim_seq[r] = s;
+                st_relaxed64(a.fflag + r, flag ? 1ull : 2ull);      // the type goes out at once: the count of the tile needs no more
+            }
+            // the predecessor's step: its type is there as soon as its rows were (a tile P / W back); if it is inside a run,
+            // this row needs the run's anchor and its sum too, i.e. that step complete
+            if (flag_type(fp) == 0) fp = wait_flag(a.fflag, p, 3ull, &err);
+            if (flag_type(fp) == 1 && !flag_done(fp)) fp = wait_flag(a.fflag, p, FU_DONE, &err);
             if (lane == 0) FU_STAMP_MAX(tile, 9);
             const bool p_merged = flag_type(fp) == 1;
+            const bool ok = flag_type(fp) == 2 || (p_merged && flag_done(fp));
             const int anchor = p_merged ? flag_anchor(fp) : p;
             const int L_p = p_merged ? flag_len(fp) : 0;
             char* srow = a.scratch + (int64_t)anchor * row_bytes;
-            if (p_merged && flag_type(fp) != 0) {
+            if (ok && p_merged) {
                 // the predecessor is inside a run: its raw row has served (the similarity); fetch the running sum of the run —
-                // written before the predecessor's flag was — into slot P
+                // written before the predecessor's step was marked complete — into slot P
                 if (lane == 0) {
                     __threadfence();                        // acquire: the flag was read with a relaxed load
                     asm volatile("fence.proxy.async;" ::: "memory");   // ... and the row is fetched through the async proxy
@@ -557,7 +570,7 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
                 mbar_wait(bar, phase);
                 phase ^= 1u;
             }
-            if (flag_type(fp) != 0) {
+            if (ok) {
                 if (!flag) {
                     if (p_merged) {                         // this row ends the run: T(sum / T(L + 1)), main.py:314-317
                         const Divider<DT> dv(L_p + 1);
@@ -568,7 +581,7 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
                     __syncwarp();
                     if (lane == 0) {
                         if (p_merged) __threadfence();      // the finished sum is visible before the flag that lets it be copied
-                        st_relaxed64(a.fflag + r, flag_kept());
+                        st_relaxed64(a.fflag + r, flag_kept_done());
                     }
                 } else {
                     // this row is merged away: T(sum + row), main.py:304-311; slot P holds the sum so far (the anchor's raw row
@@ -585,13 +598,13 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
                     __syncwarp();
                     if (lane == 0) {
                         __threadfence();                    // the sum is visible before the flag that announces it
-                        st_relaxed64(a.fflag + r, flag_merged(anchor, L_p + 1));
+                        st_relaxed64(a.fflag + r, flag_merged_done(anchor, L_p + 1));
                     }
                 }
             }
         } else if (valid && lane == 0) {
             a.sim_seq[r] = -2.0f;                           // IGNORE_TOKEN at chain heads (main.py:225-238)
-            st_relaxed64(a.fflag + r, flag_kept());
+            st_relaxed64(a.fflag + r, flag_kept_done());
         }
         if (lane == 0) {
             FU_STAMP_MAX(tile, 11);
