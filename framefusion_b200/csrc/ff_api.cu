@@ -80,8 +80,6 @@ struct ff_ctx {
     int last_fused;      // the last merge call ran the read-once kernel: sim[] is indexed by sequence row
     int fused_clean[2];  // state words / tile descriptors of the bank are known to be zero
     int fused_attr[3];   // dynamic shared memory the kernel of each dtype was last opted in for
-    char* scratch;       // running sums of the read-once kernel: one row per sequence row (touched at run anchors only)
-    size_t scratch_bytes;
     int sm_count;
     int max_smem;        // opt-in dynamic shared memory per block
     int smem_per_sm, smem_reserved;   // shared memory of an SM / what the system keeps per resident block
@@ -121,7 +119,7 @@ struct Ws {
     float* sim;
     uint8_t* flag;
     int2* link[2];      // [cap] (pred, succ) of every sequence row (read-once kernel)
-    unsigned long long* fflag[2];    // [cap] its front flags
+    unsigned* fflag[2];              // [cap] its front flags
     unsigned* fdst[2];               // [cap] its destination words
     unsigned long long* desc[2];     // [1 + tiles] ticket + tile descriptors
     int* dst[2];
@@ -154,7 +152,7 @@ Ws carve(void* base_ptr, int64_t cap, int64_t n_ids) {
     w.barrier = (unsigned*)take(256);
     w.sel_hist = (int*)take(4 * 256 * 4);
     for (int b = 0; b < 2; ++b) {
-        w.fflag[b] = (unsigned long long*)take((size_t)cap * 8);
+        w.fflag[b] = (unsigned*)take((size_t)cap * 4);
         w.fdst[b] = (unsigned*)take((size_t)cap * 4);
         w.desc[b] = (unsigned long long*)take(((size_t)(cap + 1) / 2 + 2) * 8);
     }
@@ -397,15 +395,6 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
     a.nvec = a.row_bytes / 16;
     a.slot_bytes = (a.row_bytes + 127) / 128 * 128;
     a.tile_rows = fused_tile_rows(ctx, a.row_bytes);
-    const size_t need_scratch = (size_t)S * (size_t)a.row_bytes;
-    if (need_scratch > ctx->scratch_bytes) {               // grows rarely: once per model shape / longest sequence
-        if (ctx->scratch) cudaFree(ctx->scratch);
-        ctx->scratch = nullptr;
-        ctx->scratch_bytes = 0;
-        FF_CUDA(cudaMalloc((void**)&ctx->scratch, need_scratch));
-        ctx->scratch_bytes = need_scratch;
-    }
-    a.scratch = ctx->scratch;
     a.ntiles = (int)((S + a.tile_rows - 1) / a.tile_rows);
     a.link = w.link[bank];
     a.link_next = w.link[nb];
@@ -423,7 +412,7 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
     a.thr = (float)thr;
     a.bound = bound;
     if (!ctx->fused_clean[bank]) {
-        FF_CUDA(cudaMemsetAsync(w.fflag[bank], 0, (size_t)S * 8, st));
+        FF_CUDA(cudaMemsetAsync(w.fflag[bank], 0, (size_t)S * 4, st));
         FF_CUDA(cudaMemsetAsync(w.fdst[bank], 0, (size_t)S * 4, st));
         FF_CUDA(cudaMemsetAsync(w.desc[bank], 0, ((size_t)a.ntiles + 1) * 8, st));
     }
@@ -486,8 +475,6 @@ int ff_ctx_create(int device, ff_ctx** out) {
     c->last_fused = 0;
     c->fused_clean[0] = c->fused_clean[1] = 0;
     c->fused_attr[0] = c->fused_attr[1] = c->fused_attr[2] = 0;
-    c->scratch = nullptr;
-    c->scratch_bytes = 0;
     cudaError_t e = cudaHostAlloc((void**)&c->h_status, FF_ST_SLOTS * 8, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e != cudaSuccess) { delete c; return fail(FF_E_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
     memset(c->h_status, 0, FF_ST_SLOTS * 8);
@@ -505,7 +492,6 @@ int ff_ctx_create(int device, ff_ctx** out) {
 
 int ff_ctx_destroy(ff_ctx* ctx) {
     if (!ctx) return FF_OK;
-    if (ctx->scratch) cudaFree(ctx->scratch);
     cudaFreeHost(ctx->h_status);
     delete ctx;
     return FF_OK;

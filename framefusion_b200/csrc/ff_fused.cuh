@@ -12,21 +12,16 @@
 //   FRONT (tile warps).  Tiles of W consecutive rows are handed out in sequence order by a ticket; warp w of the CTA owns
 //     row tile * W + w.  Its own row (HBM) and its chain predecessor (pred[r]: an L2 hit, that row was some tile's own row
 //     a few microseconds ago) are staged by TMA (cp.async.bulk + mbarrier) into the warp's two shared-memory slots.
-//     Three row sums out of shared memory, warp shuffles, the reference's rounding chain -> sim, flag.  A merged-away
-//     row adds itself to the running sum of its run right here: T(sum + row), one rounding to T per add, in chain
-//     order — the sequence torch-CPU index_add_ performs (main.py:304-311).  The sum lives in a scratch row named
-//     after the run's ANCHOR ROW (not its destination, which nobody knows yet); the first member finds both operands
-//     in its slots, a later one fetches the sum (an L2 hit, by TMA).  The row that ends a run divides it once by T(L+1)
-//     (main.py:314-317).  Each row publishes its front flag in two steps: kept / merged right after the similarity
-//     (all the scan needs), then DONE with (anchor row, members so far) once its step is complete — what the next row
-//     of a run needs.  The only thing a front warp ever waits for is the front flag of its predecessor: another front
-//     step, ~P / W tiles back, never a look-back; and only inside runs does one step wait for another step's end.
-//   SCAN (one warp per CTA).  Collects the front flags of each of the CTA's tiles, posts the tile's kept-row count,
-//     resolves the exclusive prefix by decoupled look-back over the tile descriptors, publishes the destinations.
-//   WORKERS.  Per tile: every kept row whose run is complete (the row that ended it is in this tile) is copied — the
-//     raw row, or the finished sum out of the scratch row — to the anchor's destination, out of the L2; aux rows
-//     (cos / sin / patch_type / position ids) and the links of the next call (pred / succ by destination index) go
-//     with it.  Pure copies with no dependencies among themselves.
+//     Three row sums out of shared memory, warp shuffles, the reference's rounding chain -> sim, and the row's flag
+//     (kept / merged away) is published.  A front warp waits for its rows and for nothing else.
+//   SCAN (one warp per CTA).  Collects the flags of each of the CTA's tiles, posts the tile's kept-row count, resolves
+//     the exclusive prefix by decoupled look-back over the tile descriptors, publishes the destinations.
+//   WORKERS.  Per tile, out of the L2: a kept row ends the run of its predecessor — the worker walks the flags back to
+//     the run's anchor and writes the anchor's destination row: the raw row if the run has no members, else
+//     T(T(..T(anchor + m1) + ..) + mL) / T(L+1) with one rounding to T per add in chain order (the sequence torch-CPU
+//     index_add_ performs, main.py:304-311) and one division (main.py:314-317).  Chain tails end their own run.  The
+//     aux rows (cos / sin / patch_type / position ids) and the links of the next call (pred / succ by destination
+//     index) go with it.  Items are independent of each other.
 //
 // Every wait is for a row with a SMALLER sequence index, tickets are taken in order by CTAs that are running, and every
 // spin is bounded: no deadlock whatever is resident, and a kernel that always ends.
@@ -42,7 +37,7 @@
 namespace ff {
 
 constexpr int FU_WARPS = 8;                        // most rows per tile = tile warps per CTA (fewer when the rows are long)
-constexpr int FU_WORKERS = 5;                      // warps per CTA besides the tile warps: one scan warp + workers
+constexpr int FU_WORKERS = 7;                      // warps per CTA besides the tile warps: one scan warp + workers
 constexpr int FU_QSIZE = 32;                       // ring entries between the scan warp and the workers
 constexpr int FU_SCANQ = 8;                        // ring entries between the tile warps and the scan warp
 constexpr int FU_TICKETS = 4;                      // how many iterations the tile warps of a CTA may drift apart
@@ -64,14 +59,13 @@ struct FusedArgs {
     long long* trace;                              // FF_FUSED_TRACE builds only
     const char* hidden;
     char* out;
-    char* scratch;                                 // [S] rows: running sums, indexed by the anchor's row
     int S, nvec, row_bytes, slot_bytes, ntiles, tile_rows;
     const int2* link;                              // [S] (pred, succ): row index, -1 = chain head / tail, -2 = not a chain row
     int2* link_next;                               // [S_keep] the same for the compacted sequence
-    unsigned long long* fflag;                     // [S] front flags, zero on entry
+    unsigned* fflag;                               // [S] front flags, zero on entry
     unsigned* fdst;                                // [S] destination + 1, zero on entry
     unsigned long long* desc;                      // [1 + ntiles] zero on entry: ticket, tile descriptors
-    unsigned long long* fflag_clr;                 // other bank: cleared for the next call
+    unsigned* fflag_clr;                           // other bank: cleared for the next call
     unsigned* fdst_clr;
     unsigned long long* desc_clr;
     float* sim_seq;                                // [S] similarity with the chain predecessor (introspection)
@@ -124,7 +118,7 @@ __device__ __forceinline__ void st_relaxed64(unsigned long long* p, unsigned lon
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
-// coherent 16-byte load (scratch rows are written and re-read inside the kernel: not the read-only path)
+// 16-byte load that stays in the L2 (rows the front pulled in a few microseconds ago)
 __device__ __forceinline__ uint4 ld_cg16(const void* p) {
     uint4 r;
     asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
@@ -139,29 +133,16 @@ __device__ __forceinline__ void st_relaxed32(unsigned* p, unsigned v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
-// front flag of a row, published in two steps.  Bits [1:0], right after the similarity: 0 = not yet known, 1 = merged away,
-// 2 = kept — all the scan warp needs, and all a successor needs of a kept row.  Bit 2 (DONE), when the row's front step is
-// complete: for a merged-away row bits [32:3] then hold the row of its run's anchor and bits [63:33] the members of the run
-// so far, and the running sum in the scratch row includes this row; for a kept row, the run it ended has been divided.
-constexpr unsigned long long FU_DONE = 4ull;
-__device__ __forceinline__ unsigned long long flag_kept_done() { return 2ull | FU_DONE; }
-__device__ __forceinline__ unsigned long long flag_merged_done(int anchor, int L) {
-    return 1ull | FU_DONE | ((unsigned long long)(uint32_t)anchor << 3) | ((unsigned long long)(uint32_t)L << 33);
-}
-__device__ __forceinline__ int flag_type(unsigned long long f) { return (int)(f & 3ull); }
-__device__ __forceinline__ bool flag_done(unsigned long long f) { return (f & FU_DONE) != 0ull; }
-__device__ __forceinline__ int flag_anchor(unsigned long long f) { return (int)((f >> 3) & 0x3fffffffull); }
-__device__ __forceinline__ int flag_len(unsigned long long f) { return (int)(f >> 33); }
-
+// front flag of a row: 0 = not yet known, 1 = merged away, 2 = kept
 // Waits are for rows with a smaller sequence index, and give up after FU_SPIN_LIMIT polls: *err is set, the caller skips
 // what depended on the value, the kernel always terminates.
-__device__ __forceinline__ unsigned long long wait_flag(const unsigned long long* fflag, int x, unsigned long long need, int* err) {
-    unsigned long long v = ld_relaxed64(fflag + x);         // need = 3: the type is there; need = FU_DONE: the step is complete
+__device__ __forceinline__ unsigned wait_flag(const unsigned* fflag, int x, int* err) {
+    unsigned v = ld_relaxed32(fflag + x);
     int spins = 0;
-    while ((v & need) == 0ull) {
+    while (v == 0u) {
         if (++spins > FU_SPIN_LIMIT) { *err = 1; break; }
         __nanosleep(64);
-        v = ld_relaxed64(fflag + x);
+        v = ld_relaxed32(fflag + x);
     }
     return v;
 }
@@ -292,71 +273,110 @@ __device__ __forceinline__ bool queue_pop(FusedQueue* q, int lane, unsigned long
     return true;
 }
 
-// The rows of one tile whose final value exists now, L2 -> destination, with their aux rows and the links of the next call.
+// A run: anchor row a and its L members, written to destination row d_a as T(T(..T(a + m1) ..+ mL) / T(L + 1)); L = 0 is
+// a plain copy.  `last` = the last member (the walk back along the predecessor links starts there).
+template <int DT>
+__device__ __forceinline__ void emit_run(const FusedArgs& a, int anchor, int last, int L, int d_a, int lane) {
+    const int64_t row_bytes = a.row_bytes;
+    const char* arow = a.hidden + (int64_t)anchor * row_bytes;
+    char* orow = a.out + (int64_t)d_a * row_bytes;
+    if (L == 0) {
+        copy_row(arow, orow, a.nvec, lane);
+        return;
+    }
+    // members in chain order: lane k keeps the k-th member from the end (runs up to 32; longer ones follow the successor links)
+    int mine = -1;
+    {
+        int x = last;
+        for (int k = 0; k < L && k < 32; ++k) {
+            if (lane == k) mine = x;
+            x = __ldg(&a.link[x].x);
+        }
+    }
+    const Divider<DT> dv(L + 1);
+#pragma unroll 1
+    for (int vb = 0; vb < a.nvec; vb += 128) {              // warp-uniform trip count: the loop body shuffles
+        const int v0 = vb + lane;
+        uint4 acc[4], xv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (v0 + 32 * q < a.nvec) acc[q] = ld_cg16(arow + (int64_t)(v0 + 32 * q) * 16);
+        int walk = anchor;
+#pragma unroll 1
+        for (int m = L - 1; m >= 0; --m) {                  // m = L - 1: first member behind the anchor ... m = 0: the last
+            int idx;
+            if (L <= 32) idx = __shfl_sync(FULL, mine, m);
+            else { walk = __ldg(&a.link[walk].y); idx = walk; }
+            const char* mr = a.hidden + (int64_t)idx * row_bytes;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (v0 + 32 * q < a.nvec) xv[q] = ld_cg16(mr + (int64_t)(v0 + 32 * q) * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (v0 + 32 * q < a.nvec) acc[q] = Num<DT>::add_vec(acc[q], xv[q]);      // T(acc + member), main.py:304
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (v0 + 32 * q < a.nvec) st_stream16(orow + (int64_t)(v0 + 32 * q) * 16, dv.vec_fast(acc[q]));
+    }
+}
+
+// The runs that end in one tile, L2 -> destination, with the aux rows of its kept rows and the links of the next call.
 // item = (tile << 38) | (exclusive prefix << 8) | kept mask.  Lane w looks after row w of the tile:
-//   kept, with a predecessor: it ends the predecessor's run -> the run's anchor goes out (its raw row if the run has no
-//                            members, else the finished sum in the scratch row named after it)
+//   kept, with a predecessor: it ends the predecessor's run -> that run goes out
 //   kept, nobody behind it (chain tail, row outside the chains): it goes out itself
-//   merged away at the end of its chain: its run is finished too -> the anchor goes out
+//   merged away at the end of its chain: it ends its own run -> that run goes out
+// Every flag the walks read belongs to an earlier row than the tile's last: known since the tile's look-back resolved.
 template <int DT>
 __device__ __noinline__ void run_tile_item(const FusedArgs& a, const AuxPack& aux, int W, unsigned long long item, int lane, int* err) {
     const int tile = (int)((item >> 38) & 0xffffffull), excl = (int)((item >> 8) & 0x3fffffffull);
     const unsigned kept = (unsigned)(item & 0xffull);
-    const int64_t row_bytes = a.row_bytes;
     const int r = tile * W + lane;
-    const char *srcA = nullptr, *srcB = nullptr;            // up to two rows to copy per lane
-    char *dstA = nullptr, *dstB = nullptr;
-    int d_r = -1;
+    int run_last = -1, run_anchor = -1, run_L = 0, run_dst = -1;    // the run this lane's row ends
+    int self_dst = -1, d_r = -1;
     if (lane < W && r < a.S) {
         const int2 lk = __ldg(a.link + r);
         const bool is_kept = kept >> lane & 1u;
+        int start = -1;                                     // where the walk back starts
         if (is_kept) {
             d_r = excl + __popc(kept & ((1u << lane) - 1u));
-            if (lk.x >= 0) {
-                wait_flag(a.fflag, r, FU_DONE, err);        // this row's front step (it divides the run it ends) is complete
-                const unsigned long long fp = ld_relaxed64(a.fflag + lk.x);      // complete as well: this row's step read it
-                const bool run = flag_type(fp) == 1;
-                const int anchor = run ? flag_anchor(fp) : lk.x;
-                const int d_a = wait_dst(a.fdst, anchor, err);
-                if (d_a >= 0) {
-                    srcA = (run ? a.scratch : a.hidden) + (int64_t)anchor * row_bytes;
-                    dstA = a.out + (int64_t)d_a * row_bytes;
-                    a.link_next[d_r].x = d_a;
-                    a.link_next[d_a].y = d_r;
-                }
-            } else {
+            if (lk.x >= 0) start = lk.x;
+            else {
                 a.link_next[d_r].x = lk.x;                  // chain head / not a chain row
                 if (lk.x == -2) a.link_next[d_r].y = -2;
             }
             if (lk.x == -2 || lk.y < 0) {
-                srcB = a.hidden + (int64_t)r * row_bytes;
-                dstB = a.out + (int64_t)d_r * row_bytes;
+                self_dst = d_r;
                 if (lk.x != -2) a.link_next[d_r].y = -1;
             }
         } else if (lk.x >= 0 && lk.y < 0) {
-            const unsigned long long fr = wait_flag(a.fflag, r, FU_DONE, err);
-            if (flag_type(fr) == 1 && flag_done(fr)) {
-                const int anchor = flag_anchor(fr);
-                const int d_a = wait_dst(a.fdst, anchor, err);
+            start = r;                                      // merged away, and the chain ends here
+        }
+        if (start >= 0) {
+            int x = start, L = 0;
+            while (wait_flag(a.fflag, x, err) == 1u) {      // merged away: one more member, on to its predecessor
+                ++L;
+                x = __ldg(&a.link[x].x);
+                if (x < 0) break;                           // (cannot happen: a chain head is never merged away)
+            }
+            if (x >= 0) {
+                const int d_a = wait_dst(a.fdst, x, err);
                 if (d_a >= 0) {
-                    srcA = a.scratch + (int64_t)anchor * row_bytes;
-                    dstA = a.out + (int64_t)d_a * row_bytes;
-                    a.link_next[d_a].y = -1;
+                    run_last = start; run_anchor = x; run_L = L; run_dst = d_a;
+                    if (is_kept) { a.link_next[d_r].x = d_a; a.link_next[d_a].y = d_r; }
+                    else a.link_next[d_a].y = -1;
                 }
             }
         }
     }
-    __threadfence();                                        // acquire: the sums were written before the flags read above
     __syncwarp();
 #pragma unroll 1
     for (int w = 0; w < W; ++w) {
-        const char* sA = (const char*)__shfl_sync(FULL, (unsigned long long)srcA, w);
-        char* dA = (char*)__shfl_sync(FULL, (unsigned long long)dstA, w);
-        const char* sB = (const char*)__shfl_sync(FULL, (unsigned long long)srcB, w);
-        char* dB = (char*)__shfl_sync(FULL, (unsigned long long)dstB, w);
-        const int d_w = __shfl_sync(FULL, d_r, w);
-        if (sA) copy_row(sA, dA, a.nvec, lane);
-        if (sB) copy_row(sB, dB, a.nvec, lane);
+        const int anchor = __shfl_sync(FULL, run_anchor, w), last = __shfl_sync(FULL, run_last, w);
+        const int L = __shfl_sync(FULL, run_L, w), d_a = __shfl_sync(FULL, run_dst, w);
+        const int sd = __shfl_sync(FULL, self_dst, w), d_w = __shfl_sync(FULL, d_r, w);
+        if (anchor >= 0) emit_run<DT>(a, anchor, last, L, d_a, lane);
+        if (sd >= 0) copy_row(a.hidden + (int64_t)(tile * W + w) * a.row_bytes, a.out + (int64_t)sd * a.row_bytes, a.nvec, lane);
         if (d_w >= 0 && aux.n) gather_aux_rows(aux, tile * W + w, d_w, lane);
     }
 }
@@ -413,9 +433,9 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             if (item == FU_ITEM_EXIT) break;
             const int tile = (int)item;
             const int r = tile * W + lane;
-            unsigned long long f = 0;
-            if (lane < W && r < a.S) f = wait_flag(a.fflag, r, 3ull, &err);
-            const unsigned kept = __ballot_sync(FULL, flag_type(f) == 2), merged = __ballot_sync(FULL, flag_type(f) == 1);
+            unsigned f = 0;
+            if (lane < W && r < a.S) f = wait_flag(a.fflag, r, &err);
+            const unsigned kept = __ballot_sync(FULL, f == 2u), merged = __ballot_sync(FULL, f == 1u);
             const int total = __popc(kept);
             if (lane == 0) FU_STAMP(tile, 6);
             tile_post(D, tile, total, lane);
@@ -473,7 +493,7 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
         return;
     }
 
-    // ---- tile warps (the front).  Per warp: slot P (chain predecessor, later the running sum) and slot C (own row).
+    // ---- tile warps (the front).  Per warp: slot P (chain predecessor) and slot C (own row).
     unsigned char* slot_p = fu_smem + (size_t)(2 * wid) * a.slot_bytes;
     unsigned char* slot_c = slot_p + a.slot_bytes;
     const uint32_t sp32 = smem_u32(slot_p), sc32 = smem_u32(slot_c), bar = smem_u32(&sh->bars[wid]);
@@ -503,17 +523,13 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
         const bool valid = r < a.S;
         int2 lk = make_int2(-2, -2);
         if (valid) lk = __ldg(a.link + r);
-        const int p = lk.x, sc = lk.y;
+        const int p = lk.x;
         const bool has_pred = valid && p >= 0;
         __syncwarp();                                       // every lane is done with the slots before they are refilled
-        unsigned long long fp = 0;
-        if (has_pred) {
-            if (lane == 0) {
-                mbar_expect_tx(bar, (uint32_t)row_bytes * 2u);
-                tma_load(sc32, a.hidden + (int64_t)r * row_bytes, (uint32_t)row_bytes, bar);
-                tma_load(sp32, a.hidden + (int64_t)p * row_bytes, (uint32_t)row_bytes, bar);
-            }
-            fp = ld_relaxed64(a.fflag + p);                 // the predecessor's front flag: usually there already
+        if (has_pred && lane == 0) {
+            mbar_expect_tx(bar, (uint32_t)row_bytes * 2u);
+            tma_load(sc32, a.hidden + (int64_t)r * row_bytes, (uint32_t)row_bytes, bar);
+            tma_load(sp32, a.hidden + (int64_t)p * row_bytes, (uint32_t)row_bytes, bar);
         }
         if (valid) prefetch_aux(aux, r, lane);
         if (has_pred) {
@@ -543,68 +559,13 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             na = warp_sum(na);
             nb = warp_sum(nb);
             const float s = finish_cosine<DT>(dot, na, nb);
-            const int flag = (s >= a.thr);                  // NaN compares false
             if (lane == 0) {
                 a.sim_seq[r] = s;
-                st_relaxed64(a.fflag + r, flag ? 1ull : 2ull);      // the type goes out at once: the count of the tile needs no more
-            }
-            // the predecessor's step: its type is there as soon as its rows were (a tile P / W back); if it is inside a run,
-            // this row needs the run's anchor and its sum too, i.e. that step complete
-            if (flag_type(fp) == 0) fp = wait_flag(a.fflag, p, 3ull, &err);
-            if (flag_type(fp) == 1 && !flag_done(fp)) fp = wait_flag(a.fflag, p, FU_DONE, &err);
-            if (lane == 0) FU_STAMP_MAX(tile, 9);
-            const bool p_merged = flag_type(fp) == 1;
-            const bool ok = flag_type(fp) == 2 || (p_merged && flag_done(fp));
-            const int anchor = p_merged ? flag_anchor(fp) : p;
-            const int L_p = p_merged ? flag_len(fp) : 0;
-            char* srow = a.scratch + (int64_t)anchor * row_bytes;
-            if (ok && p_merged) {
-                // the predecessor is inside a run: its raw row has served (the similarity); fetch the running sum of the run —
-                // written before the predecessor's step was marked complete — into slot P
-                if (lane == 0) {
-                    __threadfence();                        // acquire: the flag was read with a relaxed load
-                    asm volatile("fence.proxy.async;" ::: "memory");   // ... and the row is fetched through the async proxy
-                    mbar_expect_tx(bar, (uint32_t)row_bytes);
-                    tma_load(sp32, srow, (uint32_t)row_bytes, bar);
-                }
-                mbar_wait(bar, phase);
-                phase ^= 1u;
-            }
-            if (ok) {
-                if (!flag) {
-                    if (p_merged) {                         // this row ends the run: T(sum / T(L + 1)), main.py:314-317
-                        const Divider<DT> dv(L_p + 1);
-#pragma unroll 2
-                        for (int vb = 0; vb < nvec; vb += 32)
-                            if (vb + lane < nvec) st_stream16(srow + (int64_t)(vb + lane) * 16, dv.vec_fast(pr[vb + lane]));
-                    }
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (p_merged) __threadfence();      // the finished sum is visible before the flag that lets it be copied
-                        st_relaxed64(a.fflag + r, flag_kept_done());
-                    }
-                } else {
-                    // this row is merged away: T(sum + row), main.py:304-311; slot P holds the sum so far (the anchor's raw row
-                    // if this is the first member); at the end of the chain the run is finished as well
-                    const Divider<DT> dv(L_p + 2);
-                    const bool finish = sc < 0;
-#pragma unroll 2
-                    for (int vb = 0; vb < nvec; vb += 32)
-                        if (vb + lane < nvec) {
-                            uint4 t = Num<DT>::add_vec(pr[vb + lane], cr[vb + lane]);
-                            if (finish) t = dv.vec_fast(t);
-                            st_stream16(srow + (int64_t)(vb + lane) * 16, t);
-                        }
-                    __syncwarp();
-                    if (lane == 0) {
-                        __threadfence();                    // the sum is visible before the flag that announces it
-                        st_relaxed64(a.fflag + r, flag_merged_done(anchor, L_p + 1));
-                    }
-                }
+                st_relaxed32(a.fflag + r, (s >= a.thr) ? 1u : 2u);          // NaN compares false: kept
             }
         } else if (valid && lane == 0) {
             a.sim_seq[r] = -2.0f;                           // IGNORE_TOKEN at chain heads (main.py:225-238)
-            st_relaxed64(a.fflag + r, flag_kept_done());
+            st_relaxed32(a.fflag + r, 2u);
         }
         if (lane == 0) {
             FU_STAMP_MAX(tile, 11);
