@@ -420,13 +420,17 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
     ctx->fused_clean[nb] = 1;                              // the kernel clears the other bank on its way out
     ctx->h_status[FF_ST_INTERNAL] = 0;
     const int smem = 2 * a.tile_rows * a.slot_bytes + FU_SMEM_EXTRA;
-    const int threads = (a.tile_rows + FU_WORKERS) * 32;
+    const int threads = (FU_WARPS + FU_WORKERS) * 32;
     return dispatch_dtype(dtype, [&](auto dt) {
         constexpr int DT = decltype(dt)::value;
         if (ctx->fused_attr[DT] < smem) {
             FF_CUDA(cudaFuncSetAttribute(k_fused_merge<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             ctx->fused_attr[DT] = smem;
         }
+        cudaFuncAttributes fa;
+        FF_CUDA(cudaFuncGetAttributes(&fa, k_fused_merge<DT>));
+        if (fa.numRegs != FU_REGS_LAUNCH)                  // the warpgroups' register trade is computed for this allocation
+            return fail(FF_E_UNSUPPORTED, "k_fused_merge was built with %d registers per thread, the register trade expects %d", fa.numRegs, FU_REGS_LAUNCH);
         int per_sm = 0;
         FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_merge<DT>, threads, smem));
         if (per_sm < 1) return fail(FF_E_UNSUPPORTED, "the read-once kernel does not fit an SM (%d bytes of shared memory)", smem);

@@ -37,7 +37,8 @@
 namespace ff {
 
 constexpr int FU_WARPS = 8;                        // most rows per tile = tile warps per CTA (fewer when the rows are long)
-constexpr int FU_WORKERS = 7;                      // warps per CTA besides the tile warps: one scan warp + workers
+constexpr int FU_WORKERS = 4;                      // warps per CTA besides the tile warps: one scan warp + workers (one warpgroup)
+constexpr int FU_REGS_LAUNCH = 80, FU_REGS_FRONT = 56, FU_REGS_BACK = 128;   // setmaxnreg: 12 * 32 * 80 = 8 * 32 * 56 + 4 * 32 * 128
 constexpr int FU_QSIZE = 32;                       // ring entries between the scan warp and the workers
 constexpr int FU_SCANQ = 8;                        // ring entries between the tile warps and the scan warp
 constexpr int FU_TICKETS = 4;                      // how many iterations the tile warps of a CTA may drift apart
@@ -168,17 +169,29 @@ __device__ __forceinline__ void prefetch_aux(const AuxPack& aux, int r, int lane
         }
 }
 
-// one row, L2 -> destination, eight 16-byte vectors per lane in flight
+// N 16-byte vectors per lane, src -> dst, all loads in flight before the first store.  No predicates: a register array that
+// is only conditionally written ends up in local memory.
+template <int N>
+__device__ __forceinline__ void copy_vecs(const char* src, char* dst, int lane) {
+    uint4 x[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) x[q] = ld_cg16(src + (int64_t)(lane + 32 * q) * 16);
+#pragma unroll
+    for (int q = 0; q < N; ++q) st_stream16(dst + (int64_t)(lane + 32 * q) * 16, x[q]);
+}
+
+// one row, L2 -> destination: the whole row in flight for the usual row sizes (14 or 16 vectors per lane: 7 / 8 KB)
 __device__ __forceinline__ void copy_row(const char* src, char* dst, int nvec, int lane) {
-    for (int vb = 0; vb < nvec; vb += 256) {
-        const int v0 = vb + lane;
-        uint4 x[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-            if (v0 + 32 * q < nvec) x[q] = ld_cg16(src + (int64_t)(v0 + 32 * q) * 16);
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-            if (v0 + 32 * q < nvec) st_stream16(dst + (int64_t)(v0 + 32 * q) * 16, x[q]);
+    const int nfull = nvec >> 5;                            // vectors every lane has
+    int v = 0;
+    if (nfull == 14) { copy_vecs<14>(src, dst, lane); v = 14; }
+    else if (nfull == 16) { copy_vecs<16>(src, dst, lane); v = 16; }
+    for (; v + 8 <= nfull; v += 8) copy_vecs<8>(src + (int64_t)v * 512, dst + (int64_t)v * 512, lane);
+    for (; v + 2 <= nfull; v += 2) copy_vecs<2>(src + (int64_t)v * 512, dst + (int64_t)v * 512, lane);
+    for (; v < nfull; ++v) copy_vecs<1>(src + (int64_t)v * 512, dst + (int64_t)v * 512, lane);
+    if (nfull * 32 + lane < nvec) {                         // ragged end
+        const int64_t o = (int64_t)(nfull * 32 + lane) * 16;
+        st_stream16(dst + o, ld_cg16(src + o));
     }
 }
 
@@ -273,18 +286,43 @@ __device__ __forceinline__ bool queue_pop(FusedQueue* q, int lane, unsigned long
     return true;
 }
 
-// A run: anchor row a and its L members, written to destination row d_a as T(T(..T(a + m1) ..+ mL) / T(L + 1)); L = 0 is
-// a plain copy.  `last` = the last member (the walk back along the predecessor links starts there).
+// N vectors per lane of one run: T(T(..T(anchor + m1) ..+ mL) / T(L + 1)), starting at vector `v` of the rows.  The members
+// come in chain order out of `mine` (lane k: the k-th member from the end; runs up to 32) or by following the successor links.
+template <int DT, int N>
+__device__ __forceinline__ void run_vecs(const FusedArgs& a, int anchor, int L, int mine, const Divider<DT>& dv, int64_t off,
+                                         char* orow, int lane, bool pred) {
+    const int64_t row_bytes = a.row_bytes;
+    const char* arow = a.hidden + (int64_t)anchor * row_bytes + off;
+    uint4 acc[N], xv[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) acc[q] = pred ? ld_cg16(arow + (int64_t)(lane + 32 * q) * 16) : make_uint4(0, 0, 0, 0);
+    int walk = anchor;
+#pragma unroll 1
+    for (int m = L - 1; m >= 0; --m) {                      // m = L - 1: first member behind the anchor ... m = 0: the last
+        int idx;
+        if (L <= 32) idx = __shfl_sync(FULL, mine, m);
+        else { walk = __ldg(&a.link[walk].y); idx = walk; }
+        const char* mr = a.hidden + (int64_t)idx * row_bytes + off;
+#pragma unroll
+        for (int q = 0; q < N; ++q) xv[q] = pred ? ld_cg16(mr + (int64_t)(lane + 32 * q) * 16) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int q = 0; q < N; ++q) acc[q] = Num<DT>::add_vec(acc[q], xv[q]);            // T(acc + member), main.py:304
+    }
+#pragma unroll
+    for (int q = 0; q < N; ++q)
+        if (pred) st_stream16(orow + off + (int64_t)(lane + 32 * q) * 16, dv.vec_fast(acc[q]));
+}
+
+// A run: anchor row a and its L members, written to destination row d_a; L = 0 is a plain copy.  `last` = the last member
+// (the walk back along the predecessor links starts there).
 template <int DT>
 __device__ __forceinline__ void emit_run(const FusedArgs& a, int anchor, int last, int L, int d_a, int lane) {
     const int64_t row_bytes = a.row_bytes;
-    const char* arow = a.hidden + (int64_t)anchor * row_bytes;
     char* orow = a.out + (int64_t)d_a * row_bytes;
     if (L == 0) {
-        copy_row(arow, orow, a.nvec, lane);
+        copy_row(a.hidden + (int64_t)anchor * row_bytes, orow, a.nvec, lane);
         return;
     }
-    // members in chain order: lane k keeps the k-th member from the end (runs up to 32; longer ones follow the successor links)
     int mine = -1;
     {
         int x = last;
@@ -294,31 +332,17 @@ __device__ __forceinline__ void emit_run(const FusedArgs& a, int anchor, int las
         }
     }
     const Divider<DT> dv(L + 1);
-#pragma unroll 1
-    for (int vb = 0; vb < a.nvec; vb += 128) {              // warp-uniform trip count: the loop body shuffles
-        const int v0 = vb + lane;
-        uint4 acc[4], xv[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (v0 + 32 * q < a.nvec) acc[q] = ld_cg16(arow + (int64_t)(v0 + 32 * q) * 16);
-        int walk = anchor;
-#pragma unroll 1
-        for (int m = L - 1; m >= 0; --m) {                  // m = L - 1: first member behind the anchor ... m = 0: the last
-            int idx;
-            if (L <= 32) idx = __shfl_sync(FULL, mine, m);
-            else { walk = __ldg(&a.link[walk].y); idx = walk; }
-            const char* mr = a.hidden + (int64_t)idx * row_bytes;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (v0 + 32 * q < a.nvec) xv[q] = ld_cg16(mr + (int64_t)(v0 + 32 * q) * 16);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (v0 + 32 * q < a.nvec) acc[q] = Num<DT>::add_vec(acc[q], xv[q]);      // T(acc + member), main.py:304
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (v0 + 32 * q < a.nvec) st_stream16(orow + (int64_t)(v0 + 32 * q) * 16, dv.vec_fast(acc[q]));
+    const int nfull = a.nvec >> 5;
+    int v = 0;
+    if (nfull == 14) {                                      // 7-KB rows: two halves, anchor + member = 14 loads per lane in flight
+        run_vecs<DT, 7>(a, anchor, L, mine, dv, 0, orow, lane, true);
+        run_vecs<DT, 7>(a, anchor, L, mine, dv, 7 * 512, orow, lane, true);
+        v = 14;
     }
+    for (; v + 8 <= nfull; v += 8) run_vecs<DT, 8>(a, anchor, L, mine, dv, (int64_t)v * 512, orow, lane, true);
+    for (; v + 2 <= nfull; v += 2) run_vecs<DT, 2>(a, anchor, L, mine, dv, (int64_t)v * 512, orow, lane, true);
+    for (; v < nfull; ++v) run_vecs<DT, 1>(a, anchor, L, mine, dv, (int64_t)v * 512, orow, lane, true);
+    if (a.nvec & 31) run_vecs<DT, 1>(a, anchor, L, mine, dv, (int64_t)nfull * 512, orow, lane, lane < (a.nvec & 31));
 }
 
 // The runs that end in one tile, L2 -> destination, with the aux rows of its kept rows and the links of the next call.
@@ -328,7 +352,7 @@ __device__ __forceinline__ void emit_run(const FusedArgs& a, int anchor, int las
 //   merged away at the end of its chain: it ends its own run -> that run goes out
 // Every flag the walks read belongs to an earlier row than the tile's last: known since the tile's look-back resolved.
 template <int DT>
-__device__ __noinline__ void run_tile_item(const FusedArgs& a, const AuxPack& aux, int W, unsigned long long item, int lane, int* err) {
+__device__ __forceinline__ void run_tile_item(const FusedArgs& a, const AuxPack& aux, int W, unsigned long long item, int lane, int* err) {
     const int tile = (int)((item >> 38) & 0xffffffull), excl = (int)((item >> 8) & 0x3fffffffull);
     const unsigned kept = (unsigned)(item & 0xffull);
     const int r = tile * W + lane;
@@ -381,7 +405,9 @@ __device__ __noinline__ void run_tile_item(const FusedArgs& a, const AuxPack& au
     }
 }
 
-// CTA = W tile warps (W rows per tile, two shared-memory slots each) + one scan warp + FU_WORKERS - 1 workers.
+// CTA = two front warpgroups (warps 0 .. 7: the W tile warps, W rows per tile, two shared-memory slots each) + one back
+// warpgroup (warp 8: scan, warps 9 .. 11: workers).  The warpgroups trade registers (setmaxnreg): the front needs few, the
+// back keeps whole rows in flight.
 template <int DT>
 __global__ void __launch_bounds__((FU_WARPS + FU_WORKERS) * 32, 2)
 k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPack aux) {
@@ -405,7 +431,9 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
     const int nvec = a.nvec;
     const int64_t row_bytes = a.row_bytes;
 
-    if (wid > W) {
+    // each role's code lives entirely inside its branch: the register budget set at its top holds to its end
+    if (wid > FU_WARPS) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(FU_REGS_BACK));
         // ---- workers: copies nobody waits for
         unsigned long long item;
         while (queue_pop(&sh->q, lane, &item)) run_tile_item<DT>(a, aux, W, item, lane, &err);
@@ -413,7 +441,8 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
         return;
     }
 
-    if (wid == W) {
+    if (wid == FU_WARPS) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(FU_REGS_BACK));
         // ---- scan warp: destinations.  For every tile of this CTA, in order: collect the front flags of its rows, post the
         // count, resolve the exclusive prefix, publish the destinations, hand the tile to the workers.
         unsigned head = 0;
@@ -494,6 +523,8 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
     }
 
     // ---- tile warps (the front).  Per warp: slot P (chain predecessor) and slot C (own row).
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(FU_REGS_FRONT));
+    if (wid >= W) return;                                   // rows too long for eight slot pairs: fewer tile warps
     unsigned char* slot_p = fu_smem + (size_t)(2 * wid) * a.slot_bytes;
     unsigned char* slot_c = slot_p + a.slot_bytes;
     const uint32_t sp32 = smem_u32(slot_p), sc32 = smem_u32(slot_c), bar = smem_u32(&sh->bars[wid]);
@@ -572,7 +603,7 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             *(volatile int*)&sh->progress[wid] = iter + 1;
         }
         // the next tile (thread 0 always gets there: its own waits are bounded.  All tile warps see the same sequence of tiles.)
-        while (*(volatile int*)&sh->next_iter[tk] != iter + 1) __nanosleep(20);
+        while (*(volatile int*)&sh->next_iter[tk] != iter + 1) __nanosleep(100);
         __threadfence_block();
         tile = *(volatile int*)&sh->next_tile[tk];
         ++iter;
