@@ -359,7 +359,7 @@ constexpr int FU_SMEM_EXTRA = (int)sizeof(FusedShared);
 int fused_tile_rows(const ff_ctx* ctx, int64_t row_bytes) {
     const int64_t slot = (row_bytes + 127) / 128 * 128;
     const int64_t per_cta = ctx->smem_per_sm / 2 - ctx->smem_reserved;
-    int64_t w = (per_cta - FU_SMEM_EXTRA) / (2 * slot);
+    int64_t w = ((per_cta - FU_SMEM_EXTRA) / slot - FU_WSLOTS) / 2;       // the workers' slots come first
     if (w > FU_WARPS) w = FU_WARPS;
     return w < 1 ? 0 : (int)w;
 }
@@ -411,6 +411,21 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
     a.status = ctx->d_status;
     a.thr = (float)thr;
     a.bound = bound;
+    // the aux tensors as (tensor, plane) entries of one piece per lane, when they have that form
+    a.auxf.n = 0;
+    for (int q = 0; q < ap.n && a.auxf.n >= 0; ++q) {
+        const ff_aux& x = ap.a[q];
+        const uintptr_t al = (uintptr_t)x.src | (uintptr_t)x.dst | (uintptr_t)x.src_plane_stride | (uintptr_t)x.dst_plane_stride | (uintptr_t)x.row_bytes;
+        const int piece = (al & 15) == 0 ? 16 : ((al & 7) == 0 ? 8 : 0);
+        if (piece == 0 || x.row_bytes > 32 * piece || a.auxf.n + x.planes > 8) { a.auxf.n = -1; break; }
+        for (int64_t pl = 0; pl < x.planes; ++pl) {
+            const int e = a.auxf.n++;
+            a.auxf.row_bytes[e] = (int)x.row_bytes;
+            a.auxf.piece[e] = piece;
+            a.auxf.src[e] = (const char*)x.src + pl * x.src_plane_stride;
+            a.auxf.dst[e] = (char*)x.dst + pl * x.dst_plane_stride;
+        }
+    }
     if (!ctx->fused_clean[bank]) {
         FF_CUDA(cudaMemsetAsync(w.fflag[bank], 0, (size_t)S * 4, st));
         FF_CUDA(cudaMemsetAsync(w.fdst[bank], 0, (size_t)S * 4, st));
@@ -419,7 +434,7 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
     ctx->fused_clean[bank] = 0;
     ctx->fused_clean[nb] = 1;                              // the kernel clears the other bank on its way out
     ctx->h_status[FF_ST_INTERNAL] = 0;
-    const int smem = 2 * a.tile_rows * a.slot_bytes + FU_SMEM_EXTRA;
+    const int smem = (2 * a.tile_rows + FU_WSLOTS) * a.slot_bytes + FU_SMEM_EXTRA;
     const int threads = (FU_WARPS + FU_WORKERS) * 32;
     return dispatch_dtype(dtype, [&](auto dt) {
         constexpr int DT = decltype(dt)::value;

@@ -38,6 +38,7 @@ namespace ff {
 
 constexpr int FU_WARPS = 8;                        // most rows per tile = tile warps per CTA (fewer when the rows are long)
 constexpr int FU_WORKERS = 4;                      // warps per CTA besides the tile warps: one scan warp + workers (one warpgroup)
+constexpr int FU_WSLOTS = 2 * (FU_WORKERS - 1);    // shared-memory row slots of the workers: two each
 constexpr int FU_REGS_LAUNCH = 80, FU_REGS_FRONT = 56, FU_REGS_BACK = 128;   // setmaxnreg: 12 * 32 * 80 = 8 * 32 * 56 + 4 * 32 * 128
 constexpr int FU_QSIZE = 32;                       // ring entries between the scan warp and the workers
 constexpr int FU_SCANQ = 8;                        // ring entries between the tile warps and the scan warp
@@ -56,8 +57,18 @@ __device__ __forceinline__ long long fu_gtime() { long long t; asm volatile("mov
 #define FU_STAMP_MAX(tile, k) do { } while (0)
 #endif
 
+// the aux tensors, one entry per (tensor, plane): rows of at most 512 bytes in 16- or 8-byte pieces, one piece per lane
+struct AuxFlat {
+    int n;                                         // entries; -1: the tensors do not fit this form (gather_aux_rows instead)
+    int row_bytes[8];
+    int piece[8];                                  // 16 or 8: bytes per lane
+    const char* src[8];
+    char* dst[8];
+};
+
 struct FusedArgs {
     long long* trace;                              // FF_FUSED_TRACE builds only
+    AuxFlat auxf;
     const char* hidden;
     char* out;
     int S, nvec, row_bytes, slot_bytes, ntiles, tile_rows;
@@ -169,32 +180,6 @@ __device__ __forceinline__ void prefetch_aux(const AuxPack& aux, int r, int lane
         }
 }
 
-// N 16-byte vectors per lane, src -> dst, all loads in flight before the first store.  No predicates: a register array that
-// is only conditionally written ends up in local memory.
-template <int N>
-__device__ __forceinline__ void copy_vecs(const char* src, char* dst, int lane) {
-    uint4 x[N];
-#pragma unroll
-    for (int q = 0; q < N; ++q) x[q] = ld_cg16(src + (int64_t)(lane + 32 * q) * 16);
-#pragma unroll
-    for (int q = 0; q < N; ++q) st_stream16(dst + (int64_t)(lane + 32 * q) * 16, x[q]);
-}
-
-// one row, L2 -> destination: the whole row in flight for the usual row sizes (14 or 16 vectors per lane: 7 / 8 KB)
-__device__ __forceinline__ void copy_row(const char* src, char* dst, int nvec, int lane) {
-    const int nfull = nvec >> 5;                            // vectors every lane has
-    int v = 0;
-    if (nfull == 14) { copy_vecs<14>(src, dst, lane); v = 14; }
-    else if (nfull == 16) { copy_vecs<16>(src, dst, lane); v = 16; }
-    for (; v + 8 <= nfull; v += 8) copy_vecs<8>(src + (int64_t)v * 512, dst + (int64_t)v * 512, lane);
-    for (; v + 2 <= nfull; v += 2) copy_vecs<2>(src + (int64_t)v * 512, dst + (int64_t)v * 512, lane);
-    for (; v < nfull; ++v) copy_vecs<1>(src + (int64_t)v * 512, dst + (int64_t)v * 512, lane);
-    if (nfull * 32 + lane < nvec) {                         // ragged end
-        const int64_t o = (int64_t)(nfull * 32 + lane) * 16;
-        st_stream16(dst + o, ld_cg16(src + o));
-    }
-}
-
 // Decoupled look-back over the tile descriptors (one warp per tile): the tile's kept-row count is posted first, then the
 // exclusive prefix over all earlier tiles is resolved.
 __device__ __forceinline__ void tile_post(unsigned long long* D, int tile, int total, int lane) {
@@ -238,6 +223,7 @@ struct FusedQueue {                                         // one producer (the
 
 struct FusedShared {
     unsigned long long bars[FU_WARPS];                      // one mbarrier per tile warp
+    unsigned long long wbars[FU_WSLOTS];                    // one per worker slot
     int next_tile[FU_TICKETS], next_iter[FU_TICKETS];       // the ticket of the next tile, valid once next_iter == iteration + 1
     int progress[FU_WARPS];                                 // iterations each tile warp has finished
     unsigned long long scan_item[FU_SCANQ];                 // tile warps (thread 0) -> scan warp: tile numbers
@@ -286,43 +272,61 @@ __device__ __forceinline__ bool queue_pop(FusedQueue* q, int lane, unsigned long
     return true;
 }
 
-// N vectors per lane of one run: T(T(..T(anchor + m1) ..+ mL) / T(L + 1)), starting at vector `v` of the rows.  The members
-// come in chain order out of `mine` (lane k: the k-th member from the end; runs up to 32) or by following the successor links.
-template <int DT, int N>
-__device__ __forceinline__ void run_vecs(const FusedArgs& a, int anchor, int L, int mine, const Divider<DT>& dv, int64_t off,
-                                         char* orow, int lane, bool pred) {
-    const int64_t row_bytes = a.row_bytes;
-    const char* arow = a.hidden + (int64_t)anchor * row_bytes + off;
-    uint4 acc[N], xv[N];
-#pragma unroll
-    for (int q = 0; q < N; ++q) acc[q] = pred ? ld_cg16(arow + (int64_t)(lane + 32 * q) * 16) : make_uint4(0, 0, 0, 0);
-    int walk = anchor;
-#pragma unroll 1
-    for (int m = L - 1; m >= 0; --m) {                      // m = L - 1: first member behind the anchor ... m = 0: the last
-        int idx;
-        if (L <= 32) idx = __shfl_sync(FULL, mine, m);
-        else { walk = __ldg(&a.link[walk].y); idx = walk; }
-        const char* mr = a.hidden + (int64_t)idx * row_bytes + off;
-#pragma unroll
-        for (int q = 0; q < N; ++q) xv[q] = pred ? ld_cg16(mr + (int64_t)(lane + 32 * q) * 16) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int q = 0; q < N; ++q) acc[q] = Num<DT>::add_vec(acc[q], xv[q]);            // T(acc + member), main.py:304
+// ---- the workers' side.  A worker owns two shared-memory row slots; rows travel L2 -> slot -> destination by TMA bulk
+// copies (no registers, two rows in flight per worker), runs are summed in the slots.
+struct WorkerSlots {
+    unsigned char* ptr[2];
+    uint32_t addr[2], bar[2], phase[2];
+    int state[2];                                           // 0 free, 1 a row is arriving (to be stored to dst), 2 a store is reading it
+    char* dst[2];
+    int next;
+};
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// the row that is arriving in slot s goes on to its destination
+__device__ __forceinline__ void slot_finish(WorkerSlots& ws, int s, int row_bytes, int lane) {
+    if (ws.state[s] != 1) return;
+    mbar_wait(ws.bar[s], ws.phase[s]);
+    ws.phase[s] ^= 1u;
+    if (lane == 0) {
+        tma_store(ws.dst[s], ws.addr[s], (uint32_t)row_bytes);
+        tma_commit();
     }
-#pragma unroll
-    for (int q = 0; q < N; ++q)
-        if (pred) st_stream16(orow + off + (int64_t)(lane + 32 * q) * 16, dv.vec_fast(acc[q]));
+    ws.state[s] = 2;
+}
+// slot s can be overwritten
+__device__ __forceinline__ void slot_free(WorkerSlots& ws, int s, int row_bytes, int lane) {
+    slot_finish(ws, s, row_bytes, lane);
+    if (ws.state[s] == 2) {
+        if (lane == 0) tma_wait_read_0();                   // (every store this lane has issued: the other slot's too)
+        __syncwarp();
+        ws.state[0] = ws.state[0] == 2 ? 0 : ws.state[0];
+        ws.state[1] = ws.state[1] == 2 ? 0 : ws.state[1];
+    }
+}
+// src row -> dst row through the next slot; returns with the row (and possibly the one before it) still travelling
+__device__ __forceinline__ void worker_copy(WorkerSlots& ws, const char* src, char* dst, int row_bytes, int lane) {
+    const int s = ws.next;
+    ws.next ^= 1;
+    slot_free(ws, s, row_bytes, lane);
+    if (lane == 0) {
+        mbar_expect_tx(ws.bar[s], (uint32_t)row_bytes);
+        tma_load(ws.addr[s], src, (uint32_t)row_bytes, ws.bar[s]);
+    }
+    ws.state[s] = 1;
+    ws.dst[s] = dst;
+    slot_finish(ws, s ^ 1, row_bytes, lane);                // meanwhile the previous row has arrived: send it on
 }
 
-// A run: anchor row a and its L members, written to destination row d_a; L = 0 is a plain copy.  `last` = the last member
-// (the walk back along the predecessor links starts there).
+// A run: anchor row and its L >= 1 members -> destination row d_a as T(T(..T(anchor + m1) ..+ mL) / T(L + 1)): one rounding to
+// T per add in chain order (main.py:304-311), one division (main.py:314-317).  `last` = the last member; the members are
+// visited front to back (lane k remembers the k-th from the end; runs longer than 32 follow the successor links).
 template <int DT>
-__device__ __forceinline__ void emit_run(const FusedArgs& a, int anchor, int last, int L, int d_a, int lane) {
-    const int64_t row_bytes = a.row_bytes;
-    char* orow = a.out + (int64_t)d_a * row_bytes;
-    if (L == 0) {
-        copy_row(a.hidden + (int64_t)anchor * row_bytes, orow, a.nvec, lane);
-        return;
-    }
+__device__ __forceinline__ void worker_run(const FusedArgs& a, WorkerSlots& ws, int anchor, int last, int L, int d_a, int lane) {
+    const int row_bytes = a.row_bytes, nvec = a.nvec;
+    slot_free(ws, 0, row_bytes, lane);
+    slot_free(ws, 1, row_bytes, lane);
     int mine = -1;
     {
         int x = last;
@@ -331,18 +335,68 @@ __device__ __forceinline__ void emit_run(const FusedArgs& a, int anchor, int las
             x = __ldg(&a.link[x].x);
         }
     }
-    const Divider<DT> dv(L + 1);
-    const int nfull = a.nvec >> 5;
-    int v = 0;
-    if (nfull == 14) {                                      // 7-KB rows: two halves, anchor + member = 14 loads per lane in flight
-        run_vecs<DT, 7>(a, anchor, L, mine, dv, 0, orow, lane, true);
-        run_vecs<DT, 7>(a, anchor, L, mine, dv, 7 * 512, orow, lane, true);
-        v = 14;
+    uint4* A = reinterpret_cast<uint4*>(ws.ptr[0]);
+    const uint4* B = reinterpret_cast<const uint4*>(ws.ptr[1]);
+    int walk = anchor;
+#pragma unroll 1
+    for (int m = L - 1; m >= 0; --m) {                      // m = L - 1: first member behind the anchor ... m = 0: the last
+        int idx;
+        if (L <= 32) idx = __shfl_sync(FULL, mine, m);
+        else { walk = __ldg(&a.link[walk].y); idx = walk; }
+        __syncwarp();                                       // every lane has read slot B
+        if (lane == 0) {
+            if (m == L - 1) {
+                mbar_expect_tx(ws.bar[0], (uint32_t)row_bytes);
+                tma_load(ws.addr[0], a.hidden + (int64_t)anchor * row_bytes, (uint32_t)row_bytes, ws.bar[0]);
+            }
+            mbar_expect_tx(ws.bar[1], (uint32_t)row_bytes);
+            tma_load(ws.addr[1], a.hidden + (int64_t)idx * row_bytes, (uint32_t)row_bytes, ws.bar[1]);
+        }
+        if (m == L - 1) { mbar_wait(ws.bar[0], ws.phase[0]); ws.phase[0] ^= 1u; }
+        mbar_wait(ws.bar[1], ws.phase[1]);
+        ws.phase[1] ^= 1u;
+        if (m > 0) {
+#pragma unroll 2
+            for (int v = lane; v < nvec; v += 32) A[v] = Num<DT>::add_vec(A[v], B[v]);       // T(acc + member)
+        } else {
+            const Divider<DT> dv(L + 1);
+#pragma unroll 2
+            for (int v = lane; v < nvec; v += 32) A[v] = dv.vec_fast(Num<DT>::add_vec(A[v], B[v]));
+        }
     }
-    for (; v + 8 <= nfull; v += 8) run_vecs<DT, 8>(a, anchor, L, mine, dv, (int64_t)v * 512, orow, lane, true);
-    for (; v + 2 <= nfull; v += 2) run_vecs<DT, 2>(a, anchor, L, mine, dv, (int64_t)v * 512, orow, lane, true);
-    for (; v < nfull; ++v) run_vecs<DT, 1>(a, anchor, L, mine, dv, (int64_t)v * 512, orow, lane, true);
-    if (a.nvec & 31) run_vecs<DT, 1>(a, anchor, L, mine, dv, (int64_t)nfull * 512, orow, lane, lane < (a.nvec & 31));
+    fence_async_smem();                                     // the sums were written through the generic proxy
+    __syncwarp();
+    if (lane == 0) {
+        tma_store(a.out + (int64_t)d_a * row_bytes, ws.addr[0], (uint32_t)row_bytes);
+        tma_commit();
+    }
+    ws.state[0] = 2;
+    ws.next = 1;
+}
+
+// the aux rows of sequence row r -> destination row d: one 16- or 8-byte piece per lane and entry, all loads first
+__device__ __forceinline__ void worker_aux(const FusedArgs& a, const AuxPack& aux, int r, int d, int lane) {
+    const AuxFlat& f = a.auxf;
+    if (f.n < 0) { gather_aux_rows(aux, r, d, lane); return; }
+    uint4 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        v[e] = make_uint4(0, 0, 0, 0);
+        if (e < f.n) {
+            const int rb = f.row_bytes[e];
+            const char* s = f.src[e] + (int64_t)r * rb;
+            if (f.piece[e] == 8) { if (lane * 8 < rb) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(s) + lane); v[e].x = t.x; v[e].y = t.y; } }
+            else if (lane * 16 < rb) v[e] = __ldg(reinterpret_cast<const uint4*>(s) + lane);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        if (e < f.n) {
+            const int rb = f.row_bytes[e];
+            char* o = f.dst[e] + (int64_t)d * rb;
+            if (f.piece[e] == 8) { if (lane * 8 < rb) reinterpret_cast<uint2*>(o)[lane] = make_uint2(v[e].x, v[e].y); }
+            else if (lane * 16 < rb) reinterpret_cast<uint4*>(o)[lane] = v[e];
+        }
 }
 
 // The runs that end in one tile, L2 -> destination, with the aux rows of its kept rows and the links of the next call.
@@ -352,7 +406,8 @@ __device__ __forceinline__ void emit_run(const FusedArgs& a, int anchor, int las
 //   merged away at the end of its chain: it ends its own run -> that run goes out
 // Every flag the walks read belongs to an earlier row than the tile's last: known since the tile's look-back resolved.
 template <int DT>
-__device__ __forceinline__ void run_tile_item(const FusedArgs& a, const AuxPack& aux, int W, unsigned long long item, int lane, int* err) {
+__device__ __forceinline__ void run_tile_item(const FusedArgs& a, const AuxPack& aux, WorkerSlots& ws, int W, unsigned long long item,
+                                              int lane, int* err) {
     const int tile = (int)((item >> 38) & 0xffffffull), excl = (int)((item >> 8) & 0x3fffffffull);
     const unsigned kept = (unsigned)(item & 0xffull);
     const int r = tile * W + lane;
@@ -394,14 +449,18 @@ __device__ __forceinline__ void run_tile_item(const FusedArgs& a, const AuxPack&
         }
     }
     __syncwarp();
+    const int row_bytes = a.row_bytes;
 #pragma unroll 1
     for (int w = 0; w < W; ++w) {
         const int anchor = __shfl_sync(FULL, run_anchor, w), last = __shfl_sync(FULL, run_last, w);
         const int L = __shfl_sync(FULL, run_L, w), d_a = __shfl_sync(FULL, run_dst, w);
         const int sd = __shfl_sync(FULL, self_dst, w), d_w = __shfl_sync(FULL, d_r, w);
-        if (anchor >= 0) emit_run<DT>(a, anchor, last, L, d_a, lane);
-        if (sd >= 0) copy_row(a.hidden + (int64_t)(tile * W + w) * a.row_bytes, a.out + (int64_t)sd * a.row_bytes, a.nvec, lane);
-        if (d_w >= 0 && aux.n) gather_aux_rows(aux, tile * W + w, d_w, lane);
+        if (anchor >= 0) {
+            if (L == 0) worker_copy(ws, a.hidden + (int64_t)anchor * row_bytes, a.out + (int64_t)d_a * row_bytes, row_bytes, lane);
+            else worker_run<DT>(a, ws, anchor, last, L, d_a, lane);
+        }
+        if (sd >= 0) worker_copy(ws, a.hidden + (int64_t)(tile * W + w) * row_bytes, a.out + (int64_t)sd * row_bytes, row_bytes, lane);
+        if (d_w >= 0 && aux.n) worker_aux(a, aux, tile * W + w, d_w, lane);
     }
 }
 
@@ -414,9 +473,11 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
     extern __shared__ __align__(128) unsigned char fu_smem[];
     pdl_enter();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, W = a.tile_rows;
-    FusedShared* sh = reinterpret_cast<FusedShared*>(fu_smem + (size_t)(2 * W) * a.slot_bytes);
+    unsigned char* wslots = fu_smem + (size_t)(2 * W) * a.slot_bytes;        // behind the front's slots: the workers'
+    FusedShared* sh = reinterpret_cast<FusedShared*>(wslots + (size_t)FU_WSLOTS * a.slot_bytes);
     unsigned long long* D = a.desc + 1;
     if (wid < W && lane == 0) mbar_init(smem_u32(&sh->bars[wid]), 1);
+    if (threadIdx.x < FU_WSLOTS) mbar_init(smem_u32(&sh->wbars[threadIdx.x]), 1);
     if (threadIdx.x == 0) {
         sh->next_tile[0] = (int)atomicAdd(a.desc, 1ull);
         for (int i = 0; i < FU_TICKETS; ++i) sh->next_iter[i] = 0;
@@ -435,8 +496,22 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
     if (wid > FU_WARPS) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(FU_REGS_BACK));
         // ---- workers: copies nobody waits for
+        WorkerSlots ws;
+        const int me = wid - FU_WARPS - 1;
+        for (int s = 0; s < 2; ++s) {
+            ws.ptr[s] = wslots + (size_t)(2 * me + s) * a.slot_bytes;
+            ws.addr[s] = smem_u32(ws.ptr[s]);
+            ws.bar[s] = smem_u32(&sh->wbars[2 * me + s]);
+            ws.phase[s] = 0;
+            ws.state[s] = 0;
+            ws.dst[s] = nullptr;
+        }
+        ws.next = 0;
         unsigned long long item;
-        while (queue_pop(&sh->q, lane, &item)) run_tile_item<DT>(a, aux, W, item, lane, &err);
+        while (queue_pop(&sh->q, lane, &item)) run_tile_item<DT>(a, aux, ws, W, item, lane, &err);
+        slot_free(ws, 0, a.row_bytes, lane);
+        slot_free(ws, 1, a.row_bytes, lane);
+        if (lane == 0) tma_wait_all();
         if (err && lane == 0) a.status[FF_ST_INTERNAL] = 1;
         return;
     }
@@ -479,9 +554,13 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             }
             if (kept | merged) {
                 const unsigned long long it = ((unsigned long long)tile << 38) | ((unsigned long long)excl << 8) | kept;
-                int ok = 0;
-                if (lane == 0) ok = queue_push(&sh->q, it) ? 1 : 0;
-                if (!__shfl_sync(FULL, ok, 0)) run_tile_item<DT>(a, aux, W, it, lane, &err);     // ring full: do it here
+                if (lane == 0) {                            // ring full: the workers are behind, and so is everything upstream
+                    int spins = 0;
+                    while (!queue_push(&sh->q, it)) {
+                        if (++spins > FU_SPIN_LIMIT) { err = 1; break; }
+                        __nanosleep(200);
+                    }
+                }
             }
             if (lane == 0 && tile == a.ntiles - 1) {
                 // the sequence is done: sizes, the speculated branch, the counters of the next call (main.py:112-120)
