@@ -661,13 +661,23 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             *(volatile int*)&sh->next_iter[tk] = iter + 1;
         }
         if (has_pred) {
-            float dot = 0.f, na = 0.f, nb = 0.f;
-#pragma unroll 4
-            for (int vb = 0; vb < nvec; vb += 32)           // lane l sums vectors l, l + 32, ... in this order (as k_similarity)
-                if (vb + lane < nvec) acc_pair<DT>(pr[vb + lane], cr[vb + lane], dot, na, nb);
-            dot = warp_sum(dot);
-            na = warp_sum(na);
-            nb = warp_sum(nb);
+            // three row sums in float32 (the reference's reductions accumulate in float32; their order is torch's own and
+            // unknown, which the oracle brackets).  One warp has the whole row to itself, so the sums are split over four
+            // independent chains per lane — packed pairs of even / odd elements, alternating vectors — or the dependent adds
+            // alone would take microseconds.
+            float2 d0 = make_float2(0.f, 0.f), d1 = d0, a0 = d0, a1 = d0, b0 = d0, b1 = d0;
+            const int nfull = nvec >> 5;
+            int v = 0;
+#pragma unroll 2
+            for (; v + 2 <= nfull; v += 2) {
+                acc_pair2<DT>(pr[v * 32 + lane], cr[v * 32 + lane], d0, a0, b0);
+                acc_pair2<DT>(pr[v * 32 + 32 + lane], cr[v * 32 + 32 + lane], d1, a1, b1);
+            }
+            if (v < nfull) acc_pair2<DT>(pr[v * 32 + lane], cr[v * 32 + lane], d0, a0, b0);
+            if (nfull * 32 + lane < nvec) acc_pair2<DT>(pr[nfull * 32 + lane], cr[nfull * 32 + lane], d1, a1, b1);
+            const float dot = warp_sum((d0.x + d0.y) + (d1.x + d1.y));
+            const float na = warp_sum((a0.x + a0.y) + (a1.x + a1.y));
+            const float nb = warp_sum((b0.x + b0.y) + (b1.x + b1.y));
             const float s = finish_cosine<DT>(dot, na, nb);
             if (lane == 0) {
                 a.sim_seq[r] = s;
