@@ -360,7 +360,7 @@ int fused_tile_rows(const ff_ctx* ctx, int64_t row_bytes) {
     const int64_t slot = (row_bytes + 127) / 128 * 128;
     const int64_t per_cta = ctx->smem_per_sm / 2 - ctx->smem_reserved;
     int64_t w = ((per_cta - FU_SMEM_EXTRA) / slot - FU_WSLOTS) / 2;       // the workers' slots come first
-    if (w > FU_WARPS) w = FU_WARPS;
+    if (w > FU_WARPS - 1) w = FU_WARPS - 1;             // one warp of the front warpgroups is the dispatcher
     return w < 1 ? 0 : (int)w;
 }
 

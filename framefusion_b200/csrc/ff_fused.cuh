@@ -9,8 +9,8 @@
 // behind the rows, and an SM cannot park rows that long (latency x bandwidth of the loads alone fills its shared
 // memory).  So the kernel is three feed-forward stages, and nothing upstream ever waits for anything downstream:
 //
-//   FRONT (tile warps).  Tiles of W consecutive rows are handed out in sequence order by a ticket; warp w of the CTA owns
-//     row tile * W + w.  Its own row (HBM) and its chain predecessor (pred[r]: an L2 hit, that row was some tile's own row
+//   FRONT (tile warps).  Tiles of W consecutive rows are handed out in sequence order by a ticket (a dispatcher warp per
+//     CTA takes them a few iterations ahead); warp w of the CTA owns row tile * W + w.  Its own row (HBM) and its chain predecessor (pred[r]: an L2 hit, that row was some tile's own row
 //     a few microseconds ago) are staged by TMA (cp.async.bulk + mbarrier) into the warp's two shared-memory slots.
 //     Three row sums out of shared memory, warp shuffles, the reference's rounding chain -> sim, and the row's flag
 //     (kept / merged away) is published.  A front warp waits for its rows and for nothing else.
@@ -36,7 +36,7 @@
 
 namespace ff {
 
-constexpr int FU_WARPS = 8;                        // most rows per tile = tile warps per CTA (fewer when the rows are long)
+constexpr int FU_WARPS = 8;                        // warps of the two front warpgroups: up to seven tile warps (rows per tile) and the dispatcher
 constexpr int FU_WORKERS = 4;                      // warps per CTA besides the tile warps: one scan warp + workers (one warpgroup)
 constexpr int FU_WSLOTS = 2 * (FU_WORKERS - 1);    // shared-memory row slots of the workers: two each
 constexpr int FU_REGS_LAUNCH = 80, FU_REGS_FRONT = 56, FU_REGS_BACK = 128;   // setmaxnreg: 12 * 32 * 80 = 8 * 32 * 56 + 4 * 32 * 128
@@ -479,7 +479,6 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
     if (wid < W && lane == 0) mbar_init(smem_u32(&sh->bars[wid]), 1);
     if (threadIdx.x < FU_WSLOTS) mbar_init(smem_u32(&sh->wbars[threadIdx.x]), 1);
     if (threadIdx.x == 0) {
-        sh->next_tile[0] = (int)atomicAdd(a.desc, 1ull);
         for (int i = 0; i < FU_TICKETS; ++i) sh->next_iter[i] = 0;
         for (int i = 0; i < FU_WARPS; ++i) sh->progress[i] = 0;
         sh->scan_tail = sh->scan_head = 0;
@@ -601,36 +600,69 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
         return;
     }
 
-    // ---- tile warps (the front).  Per warp: slot P (chain predecessor) and slot C (own row).
+    // ---- the front warpgroups: W tile warps and, in warp FU_WARPS - 1, the dispatcher
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(FU_REGS_FRONT));
-    if (wid >= W) return;                                   // rows too long for eight slot pairs: fewer tile warps
+    if (wid == FU_WARPS - 1) {
+        // ---- dispatcher: takes the tiles' tickets a few iterations ahead of the tile warps (an atomic on one hot word is a
+        // microsecond away), tells the scan warp about every tile, ends both streams.  Never more than FU_TICKETS - 1 iterations
+        // ahead of the slowest tile warp: a slot of the ticket ring is rewritten only when everybody has read it.
+        for (int k = 0;; ++k) {
+            int spins = 0;
+            for (int w = 0; w < W; ++w)
+                while (*(volatile int*)&sh->progress[w] < k - (FU_TICKETS - 1)) {
+                    if (++spins > (FU_SPIN_LIMIT << 4)) { err = 1; break; }
+                    __nanosleep(100);
+                }
+            int t = 0;
+            if (lane == 0) t = (int)atomicAdd(a.desc, 1ull);
+            t = __shfl_sync(FULL, t, 0);
+            if (lane == 0) {
+                const unsigned q = sh->scan_tail;           // the scan warp learns of the tile now: it waits for its flags
+                spins = 0;
+                while ((int)(q - *(volatile unsigned*)&sh->scan_head) >= FU_SCANQ) {
+                    if (++spins > (FU_SPIN_LIMIT << 4)) { err = 1; break; }
+                    __nanosleep(100);
+                }
+                *(volatile unsigned long long*)&sh->scan_item[q % FU_SCANQ] = t < a.ntiles ? (unsigned long long)t : FU_ITEM_EXIT;
+                __threadfence_block();
+                *(volatile unsigned*)&sh->scan_tail = q + 1;
+                if (t < a.ntiles) FU_STAMP(t, 0);
+                *(volatile int*)&sh->next_tile[k % FU_TICKETS] = t;
+                __threadfence_block();
+                *(volatile int*)&sh->next_iter[k % FU_TICKETS] = k + 1;
+            }
+            if (t >= a.ntiles) break;
+        }
+        if (err && lane == 0) a.status[FF_ST_INTERNAL] = 1;
+        return;
+    }
+    if (wid >= W) return;                                   // rows too long for seven slot pairs: fewer tile warps
+
+    // ---- tile warps (the front).  Per warp: slot P (chain predecessor) and slot C (own row).
     unsigned char* slot_p = fu_smem + (size_t)(2 * wid) * a.slot_bytes;
     unsigned char* slot_c = slot_p + a.slot_bytes;
     const uint32_t sp32 = smem_u32(slot_p), sc32 = smem_u32(slot_c), bar = smem_u32(&sh->bars[wid]);
     const uint4* pr = reinterpret_cast<const uint4*>(slot_p);
     const uint4* cr = reinterpret_cast<const uint4*>(slot_c);
-    int tile = sh->next_tile[0];
-    int iter = 0;
     uint32_t phase = 0;
 
-    while (tile < a.ntiles) {
+    for (int iter = 0;; ++iter) {
         const int tk = iter % FU_TICKETS;
-        int nt = 0;
-        if (threadIdx.x == 0) {
-            FU_STAMP(tile, 0);
-            nt = (int)atomicAdd(a.desc, 1ull);              // the next tile's ticket travels during this iteration
-            const unsigned t = sh->scan_tail;               // the scan warp learns of the tile now: it waits for the flags
+        {
             int spins = 0;
-            while ((int)(t - *(volatile unsigned*)&sh->scan_head) >= FU_SCANQ) {
-                if (++spins > FU_SPIN_LIMIT) { err = 1; break; }
-                __nanosleep(100);
+            while (*(volatile int*)&sh->next_iter[tk] != iter + 1) {          // (the dispatcher's own waits are bounded)
+                if (++spins > (FU_SPIN_LIMIT << 5)) { err = 1; break; }
+                __nanosleep(50);
             }
-            *(volatile unsigned long long*)&sh->scan_item[t % FU_SCANQ] = (unsigned long long)tile;
-            __threadfence_block();
-            *(volatile unsigned*)&sh->scan_tail = t + 1;
         }
+        __threadfence_block();
+        const int tile = err ? a.ntiles : *(volatile int*)&sh->next_tile[tk];
+        if (tile >= a.ntiles) break;
         const int r = tile * W + wid;
         const bool valid = r < a.S;
+#ifdef FF_FUSED_TRACE
+        if (wid == W - 1 && lane == 0 && a.trace) { FU_STAMP(tile, 2); a.trace[(size_t)tile * FU_TRACE_SLOTS + 13] = blockIdx.x + 1; }
+#endif
         int2 lk = make_int2(-2, -2);
         if (valid) lk = __ldg(a.link + r);
         const int p = lk.x;
@@ -641,25 +673,14 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             tma_load(sc32, a.hidden + (int64_t)r * row_bytes, (uint32_t)row_bytes, bar);
             tma_load(sp32, a.hidden + (int64_t)p * row_bytes, (uint32_t)row_bytes, bar);
         }
+        if (wid == W - 1 && lane == 0) FU_STAMP(tile, 4);
         if (valid) prefetch_aux(aux, r, lane);
         if (has_pred) {
             mbar_wait(bar, phase);
             phase ^= 1u;
         }
+        if (wid == W - 1 && lane == 0) FU_STAMP(tile, 5);
         if (lane == 0) FU_STAMP_MAX(tile, 10);
-        if (threadIdx.x == 0) {
-            // the ticket has long arrived: tell the other tile warps, but never run more than FU_TICKETS - 1 iterations ahead
-            // of the slowest of them (it would miss its ticket)
-            int spins = 0;
-            for (int w = 0; w < W; ++w)
-                while (*(volatile int*)&sh->progress[w] < iter - (FU_TICKETS - 2)) {
-                    if (++spins > FU_SPIN_LIMIT) { err = 1; break; }
-                    __nanosleep(50);
-                }
-            *(volatile int*)&sh->next_tile[tk] = nt;
-            __threadfence_block();
-            *(volatile int*)&sh->next_iter[tk] = iter + 1;
-        }
         if (has_pred) {
             // three row sums in float32 (the reference's reductions accumulate in float32; their order is torch's own and
             // unknown, which the oracle brackets).  One warp has the whole row to itself, so the sums are split over four
@@ -687,30 +708,13 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             a.sim_seq[r] = -2.0f;                           // IGNORE_TOKEN at chain heads (main.py:225-238)
             st_relaxed32(a.fflag + r, 2u);
         }
+        if (wid == W - 1 && lane == 0) FU_STAMP(tile, 14);
         if (lane == 0) {
             FU_STAMP_MAX(tile, 11);
             *(volatile int*)&sh->progress[wid] = iter + 1;
         }
-        // the next tile (thread 0 always gets there: its own waits are bounded.  All tile warps see the same sequence of tiles.)
-        while (*(volatile int*)&sh->next_iter[tk] != iter + 1) __nanosleep(100);
-        __threadfence_block();
-        tile = *(volatile int*)&sh->next_tile[tk];
-        ++iter;
     }
-
     if (lane == 0) *(volatile int*)&sh->progress[wid] = 0x7fffffff;
-    asm volatile("bar.sync 1, %0;" :: "r"(W * 32) : "memory");     // the tile warps only
-    if (threadIdx.x == 0) {
-        const unsigned t = sh->scan_tail;
-        int spins = 0;
-        while ((int)(t - *(volatile unsigned*)&sh->scan_head) >= FU_SCANQ) {
-            if (++spins > FU_SPIN_LIMIT) { err = 1; break; }
-            __nanosleep(100);
-        }
-        *(volatile unsigned long long*)&sh->scan_item[t % FU_SCANQ] = FU_ITEM_EXIT;
-        __threadfence_block();
-        *(volatile unsigned*)&sh->scan_tail = t + 1;
-    }
     // leave the other bank's flags, destinations and descriptors zeroed for the next call of the prefill
     const int64_t n_thr = (int64_t)gridDim.x * W * 32, me = (int64_t)blockIdx.x * W * 32 + threadIdx.x;
     for (int64_t i = me; i < a.S; i += n_thr) { a.fflag_clr[i] = 0ull; a.fdst_clr[i] = 0u; }

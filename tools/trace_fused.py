@@ -42,6 +42,19 @@ for name, i, j in [("rows arrive (latest warp)", 10, 0), ("predecessor flag know
                    ("scan has the flags, after front done", 6, 11), ("look-back", 7, 6), ("hand-over to workers", 8, 7),
                    ("destinations after tile taken", 7, 0)]:
     print(f"  {name:40s} {dd(i, j)}")
+print("  last tile warp, one iteration:")
+for name, i, j in [("tile known after its ticket was taken", 2, 0), ("link known, TMA issued", 4, 2), ("rows arrived", 5, 4), ("similarity done", 14, 5)]:
+    print(f"    {name:38s} {dd(i, j)}")
+# per CTA: iteration period, and the wait between one tile's end and the next tile's start (last tile warp)
+cta = t[:, 13].astype(int)
+per, gap = [], []
+for c in np.unique(cta[cta > 0])[:64]:
+    m = cta == c
+    o = np.argsort(t[m, 2])
+    per += list(np.diff(t[m, 2][o]) / 1e3)
+    gap += list((t[m, 2][o][1:] - t[m, 14][o][:-1]) / 1e3)
+print(f"    {'wait for the next tile':38s} median {np.median(gap):7.2f} us   p90 {np.percentile(gap, 90):7.2f} us")
+print(f"  iteration period of a CTA              median {np.median(per):7.2f} us   p90 {np.percentile(per, 90):7.2f} us")
 st = np.sort(t[:, 0][t[:, 0] > 0])
 print(f"  tiles taken per us (middle half): {(len(st) // 2) / ((st[3 * len(st) // 4] - st[len(st) // 4]) / 1e3):.1f}")
 for q in (0.1, 0.25, 0.5, 0.75, 1.0):
