@@ -187,25 +187,48 @@ __device__ __forceinline__ void tile_post(unsigned long long* D, int tile, int t
 }
 __device__ __forceinline__ int tile_lookback(unsigned long long* D, int tile, int total, int lane, int* err) {
     if (tile == 0) return 0;
+    // 128 descriptors per hop, four per lane (lane 0 holds the four nearest): with hundreds of tiles in flight whose
+    // prefixes resolve together, the walk back to the last inclusive prefix is long, and every hop is an L2 round trip
     int excl = 0, base = tile - 1, spins = 0;
     while (true) {
-        const int idx = base - lane;
-        unsigned long long d = idx >= 0 ? ld_relaxed64(D + idx) : FU_INCL;
-        if (__ballot_sync(FULL, (d >> 32) == 0ull)) {       // a predecessor has not posted yet
+        unsigned long long d[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int idx = base - (lane * 4 + j);
+            d[j] = idx >= 0 ? ld_relaxed64(D + idx) : FU_INCL;
+        }
+        const bool missing = (d[0] >> 32) == 0ull || (d[1] >> 32) == 0ull || (d[2] >> 32) == 0ull || (d[3] >> 32) == 0ull;
+        // a lane's sum stops at its first inclusive prefix
+        int v = 0;
+        bool incl = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (!incl) {
+                v += (int)(uint32_t)d[j];
+                incl = (d[j] >> 32) == 2ull;
+            }
+        const unsigned has_incl = __ballot_sync(FULL, incl);
+        // descriptors behind the nearest inclusive prefix do not matter: only what is nearer has to be posted
+        const int first = has_incl ? __ffs(has_incl) - 1 : 32;
+        bool need_missing = false;
+        if (lane < first) need_missing = missing;
+        else if (lane == first) {
+            bool seen = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!seen && (d[j] >> 32) == 0ull) need_missing = true;
+                if ((d[j] >> 32) == 2ull) seen = true;
+            }
+        }
+        if (__ballot_sync(FULL, need_missing)) {           // a predecessor that matters has not posted yet
             if (++spins > FU_SPIN_LIMIT) { *err = 1; break; }
             __nanosleep(32);
             continue;
         }
-        const unsigned incl = __ballot_sync(FULL, (d >> 32) == 2ull);
-        int v = (int)(uint32_t)d;
-        if (incl) {
-            const int first = __ffs(incl) - 1;              // nearest predecessor that knows its inclusive prefix
-            if (lane > first) v = 0;
-            excl += warp_sum_int(v);
-            break;
-        }
+        if (lane > first) v = 0;
         excl += warp_sum_int(v);
-        base -= 32;
+        if (has_incl) break;
+        base -= 128;
     }
     if (lane == 0) st_relaxed64(D + tile, FU_INCL | (unsigned)(excl + total));
     return excl;
