@@ -154,7 +154,7 @@ Ws carve(void* base_ptr, int64_t cap, int64_t n_ids) {
     for (int b = 0; b < 2; ++b) {
         w.fflag[b] = (unsigned*)take((size_t)cap * 4);
         w.fdst[b] = (unsigned*)take((size_t)cap * 4);
-        w.desc[b] = (unsigned long long*)take(((size_t)(cap + 1) / 2 + 2) * 8);
+        w.desc[b] = (unsigned long long*)take(((size_t)cap + 4) * 8);      // ticket + u32 prefix + status byte per tile, rounded up
     }
     w.zero_begin = zero_begin;
     w.zero_bytes = (size_t)((p ? p + off : (char*)nullptr) - zero_begin);
@@ -396,6 +396,8 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
     a.slot_bytes = (a.row_bytes + 127) / 128 * 128;
     a.tile_rows = fused_tile_rows(ctx, a.row_bytes);
     a.ntiles = (int)((S + a.tile_rows - 1) / a.tile_rows);
+    a.ntiles_pad = (a.ntiles + 15) / 16 * 16;
+    a.desc_words = 1 + (a.ntiles_pad * 5 + 7) / 8;
     a.link = w.link[bank];
     a.link_next = w.link[nb];
     a.fflag = w.fflag[bank];
@@ -429,7 +431,7 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
     if (!ctx->fused_clean[bank]) {
         FF_CUDA(cudaMemsetAsync(w.fflag[bank], 0, (size_t)S * 4, st));
         FF_CUDA(cudaMemsetAsync(w.fdst[bank], 0, (size_t)S * 4, st));
-        FF_CUDA(cudaMemsetAsync(w.desc[bank], 0, ((size_t)a.ntiles + 1) * 8, st));
+        FF_CUDA(cudaMemsetAsync(w.desc[bank], 0, (size_t)a.desc_words * 8, st));
     }
     ctx->fused_clean[bank] = 0;
     ctx->fused_clean[nb] = 1;                              // the kernel clears the other bank on its way out

@@ -44,7 +44,6 @@ constexpr int FU_QSIZE = 32;                       // ring entries between the s
 constexpr int FU_SCANQ = 8;                        // ring entries between the tile warps and the scan warp
 constexpr int FU_TICKETS = 4;                      // how many iterations the tile warps of a CTA may drift apart
 constexpr int FU_SPIN_LIMIT = 1 << 18;             // polls (~64 ns apart) before a wait gives up and reports FF_ST_INTERNAL
-constexpr unsigned long long FU_AGG = 1ull << 32, FU_INCL = 2ull << 32;
 
 // Development aid (tools/trace_fused.py builds a separate library with -DFF_FUSED_TRACE): globaltimer stamps per tile.
 #ifdef FF_FUSED_TRACE
@@ -76,7 +75,9 @@ struct FusedArgs {
     int2* link_next;                               // [S_keep] the same for the compacted sequence
     unsigned* fflag;                               // [S] front flags, zero on entry
     unsigned* fdst;                                // [S] destination + 1, zero on entry
-    unsigned long long* desc;                      // [1 + ntiles] zero on entry: ticket, tile descriptors
+    unsigned long long* desc;                      // zero on entry: the ticket (8 bytes), the tiles' inclusive prefixes (u32
+                                                   // [ntiles_pad]), the tiles' status bytes ([ntiles_pad]); desc_words u64 in all
+    int desc_words, ntiles_pad;
     unsigned* fflag_clr;                           // other bank: cleared for the next call
     unsigned* fdst_clr;
     unsigned long long* desc_clr;
@@ -180,57 +181,70 @@ __device__ __forceinline__ void prefetch_aux(const AuxPack& aux, int r, int lane
         }
 }
 
-// Decoupled look-back over the tile descriptors (one warp per tile): the tile's kept-row count is posted first, then the
-// exclusive prefix over all earlier tiles is resolved.
-__device__ __forceinline__ void tile_post(unsigned long long* D, int tile, int total, int lane) {
-    if (lane == 0) st_relaxed64(D + tile, (tile == 0 ? FU_INCL : FU_AGG) | (unsigned)total);
+// Decoupled look-back over the tiles (one warp per tile).  Hundreds of scan warps poll the same few hundred descriptors, and
+// an L2 slice serves the requests for one line one after the other: the cost of a poll is its sector count times the number
+// of pollers.  So a tile's descriptor is ONE status byte — 0 nothing, 0x40 | kept rows (the count is posted), 0x80 (its
+// inclusive prefix is in incl[tile]) — and a hop of 128 tiles is four sectors.
+__device__ __forceinline__ unsigned ld_relaxed8(const uint8_t* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
-__device__ __forceinline__ int tile_lookback(unsigned long long* D, int tile, int total, int lane, int* err) {
+__device__ __forceinline__ void st_relaxed8(uint8_t* p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u8 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tile_post(uint8_t* stat, unsigned* incl, int tile, int total, int lane) {
+    if (lane != 0) return;
+    if (tile == 0) {
+        st_relaxed32(incl, (unsigned)total);
+        __threadfence();
+        st_relaxed8(stat, 0x80u);
+    } else {
+        st_relaxed8(stat + tile, 0x40u | (unsigned)total);
+    }
+}
+__device__ __forceinline__ int tile_lookback(uint8_t* stat, unsigned* incl, int tile, int total, int lane, int* err) {
     if (tile == 0) return 0;
-    // 128 descriptors per hop, four per lane (lane 0 holds the four nearest): with hundreds of tiles in flight whose
-    // prefixes resolve together, the walk back to the last inclusive prefix is long, and every hop is an L2 round trip
     int excl = 0, base = tile - 1, spins = 0;
-    while (true) {
-        unsigned long long d[4];
+    bool done = false;
+    while (!done) {
+        // 128 tiles per hop: window j = tiles base - 32 j - lane, nearest window first; one 32-byte sector each
+        unsigned d[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int idx = base - (lane * 4 + j);
-            d[j] = idx >= 0 ? ld_relaxed64(D + idx) : FU_INCL;
+            const int idx = base - 32 * j - lane;
+            d[j] = idx >= 0 ? ld_relaxed8(stat + idx) : 0x80u;
         }
-        const bool missing = (d[0] >> 32) == 0ull || (d[1] >> 32) == 0ull || (d[2] >> 32) == 0ull || (d[3] >> 32) == 0ull;
-        // a lane's sum stops at its first inclusive prefix
-        int v = 0;
-        bool incl = false;
+        int add = 0;
+        bool retry = false;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (!incl) {
-                v += (int)(uint32_t)d[j];
-                incl = (d[j] >> 32) == 2ull;
-            }
-        const unsigned has_incl = __ballot_sync(FULL, incl);
-        // descriptors behind the nearest inclusive prefix do not matter: only what is nearer has to be posted
-        const int first = has_incl ? __ffs(has_incl) - 1 : 32;
-        bool need_missing = false;
-        if (lane < first) need_missing = missing;
-        else if (lane == first) {
-            bool seen = false;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (!seen && (d[j] >> 32) == 0ull) need_missing = true;
-                if ((d[j] >> 32) == 2ull) seen = true;
+        for (int j = 0; j < 4; ++j) {
+            if (done || retry) continue;
+            const unsigned missing = __ballot_sync(FULL, d[j] == 0u), has = __ballot_sync(FULL, (d[j] & 0x80u) != 0u);
+            const int first = has ? __ffs(has) - 1 : 32;    // nearest tile of the window that knows its inclusive prefix
+            const unsigned nearer = first >= 32 ? FULL : ((1u << first) - 1u);
+            if (missing & nearer) { retry = true; continue; }       // a predecessor that matters has not posted yet
+            add += warp_sum_int(lane < first ? (int)(d[j] & 0x3fu) : 0);
+            if (has) {
+                const int idx = base - 32 * j - first;
+                __threadfence();                            // acquire: the prefix was written before the status byte
+                if (idx >= 0) add += (int)ld_relaxed32(incl + idx);
+                done = true;
             }
         }
-        if (__ballot_sync(FULL, need_missing)) {           // a predecessor that matters has not posted yet
+        if (retry) {
             if (++spins > FU_SPIN_LIMIT) { *err = 1; break; }
-            __nanosleep(32);
+            __nanosleep(64);
             continue;
         }
-        if (lane > first) v = 0;
-        excl += warp_sum_int(v);
-        if (has_incl) break;
+        excl += add;
         base -= 128;
     }
-    if (lane == 0) st_relaxed64(D + tile, FU_INCL | (unsigned)(excl + total));
+    if (lane == 0) {
+        st_relaxed32(incl + tile, (unsigned)(excl + total));
+        __threadfence();
+        st_relaxed8(stat + tile, 0x80u);
+    }
     return excl;
 }
 
@@ -498,7 +512,8 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, W = a.tile_rows;
     unsigned char* wslots = fu_smem + (size_t)(2 * W) * a.slot_bytes;        // behind the front's slots: the workers'
     FusedShared* sh = reinterpret_cast<FusedShared*>(wslots + (size_t)FU_WSLOTS * a.slot_bytes);
-    unsigned long long* D = a.desc + 1;
+    unsigned* d_incl = reinterpret_cast<unsigned*>(a.desc + 1);
+    uint8_t* d_stat = reinterpret_cast<uint8_t*>(d_incl + a.ntiles_pad);
     if (wid < W && lane == 0) mbar_init(smem_u32(&sh->bars[wid]), 1);
     if (threadIdx.x < FU_WSLOTS) mbar_init(smem_u32(&sh->wbars[threadIdx.x]), 1);
     if (threadIdx.x == 0) {
@@ -564,8 +579,8 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
             const unsigned kept = __ballot_sync(FULL, f == 2u), merged = __ballot_sync(FULL, f == 1u);
             const int total = __popc(kept);
             if (lane == 0) FU_STAMP(tile, 6);
-            tile_post(D, tile, total, lane);
-            const int excl = tile_lookback(D, tile, total, lane, &err);
+            tile_post(d_stat, d_incl, tile, total, lane);
+            const int excl = tile_lookback(d_stat, d_incl, tile, total, lane, &err);
             if (lane == 0) FU_STAMP(tile, 7);
             if (kept >> lane & 1u) {
                 const int d = excl + __popc(kept & ((1u << lane) - 1u));
@@ -741,7 +756,7 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
     // leave the other bank's flags, destinations and descriptors zeroed for the next call of the prefill
     const int64_t n_thr = (int64_t)gridDim.x * W * 32, me = (int64_t)blockIdx.x * W * 32 + threadIdx.x;
     for (int64_t i = me; i < a.S; i += n_thr) { a.fflag_clr[i] = 0ull; a.fdst_clr[i] = 0u; }
-    for (int64_t i = me; i <= a.ntiles; i += n_thr) a.desc_clr[i] = 0ull;
+    for (int64_t i = me; i < a.desc_words; i += n_thr) a.desc_clr[i] = 0ull;
     if (err && lane == 0) a.status[FF_ST_INTERNAL] = 1;
 }
 
