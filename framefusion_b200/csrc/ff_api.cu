@@ -154,7 +154,7 @@ Ws carve(void* base_ptr, int64_t cap, int64_t n_ids) {
     for (int b = 0; b < 2; ++b) {
         w.fflag[b] = (unsigned*)take((size_t)cap * 4);
         w.fdst[b] = (unsigned*)take((size_t)cap * 4);
-        w.desc[b] = (unsigned long long*)take(((size_t)cap + 4) * 8);      // ticket + u32 prefix + status byte per tile, rounded up
+        w.desc[b] = (unsigned long long*)take(((size_t)cap + 2 * FU_ROUND + 16) * 8 + (size_t)cap / 16);   // ticket, per tile two u32, per round u32 + u64 (one row per tile at worst)
     }
     w.zero_begin = zero_begin;
     w.zero_bytes = (size_t)((p ? p + off : (char*)nullptr) - zero_begin);
@@ -396,8 +396,9 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
     a.slot_bytes = (a.row_bytes + 127) / 128 * 128;
     a.tile_rows = fused_tile_rows(ctx, a.row_bytes);
     a.ntiles = (int)((S + a.tile_rows - 1) / a.tile_rows);
-    a.ntiles_pad = (a.ntiles + 15) / 16 * 16;
-    a.desc_words = 1 + (a.ntiles_pad * 5 + 7) / 8;
+    a.nrounds = (a.ntiles + FU_ROUND - 1) / FU_ROUND;
+    a.ntiles_pad = a.nrounds * FU_ROUND;
+    a.desc_words = 1 + (a.nrounds + 1) + (2 * a.ntiles_pad + a.nrounds + 1) / 2;
     a.link = w.link[bank];
     a.link_next = w.link[nb];
     a.fflag = w.fflag[bank];

@@ -75,9 +75,9 @@ struct FusedArgs {
     int2* link_next;                               // [S_keep] the same for the compacted sequence
     unsigned* fflag;                               // [S] front flags, zero on entry
     unsigned* fdst;                                // [S] destination + 1, zero on entry
-    unsigned long long* desc;                      // zero on entry: the ticket (8 bytes), the tiles' inclusive prefixes (u32
-                                                   // [ntiles_pad]), the tiles' status bytes ([ntiles_pad]); desc_words u64 in all
-    int desc_words, ntiles_pad;
+    unsigned long long* desc;                      // zero on entry, desc_words u64 in all: the ticket, round_base [nrounds + 1],
+                                                   // then u32 slot [ntiles_pad], excl [ntiles_pad], round_cnt [nrounds]
+    int desc_words, ntiles_pad, nrounds;
     unsigned* fflag_clr;                           // other bank: cleared for the next call
     unsigned* fdst_clr;
     unsigned long long* desc_clr;
@@ -181,71 +181,55 @@ __device__ __forceinline__ void prefetch_aux(const AuxPack& aux, int r, int lane
         }
 }
 
-// Decoupled look-back over the tiles (one warp per tile).  Hundreds of scan warps poll the same few hundred descriptors, and
-// an L2 slice serves the requests for one line one after the other: the cost of a poll is its sector count times the number
-// of pollers.  So a tile's descriptor is ONE status byte — 0 nothing, 0x40 | kept rows (the count is posted), 0x80 (its
-// inclusive prefix is in incl[tile]) — and a hop of 128 tiles is four sectors.
-__device__ __forceinline__ unsigned ld_relaxed8(const uint8_t* p) {
-    unsigned v;
-    asm volatile("ld.relaxed.gpu.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed8(uint8_t* p, unsigned v) {
-    asm volatile("st.relaxed.gpu.global.u8 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void tile_post(uint8_t* stat, unsigned* incl, int tile, int total, int lane) {
-    if (lane != 0) return;
-    if (tile == 0) {
-        st_relaxed32(incl, (unsigned)total);
-        __threadfence();
-        st_relaxed8(stat, 0x80u);
-    } else {
-        st_relaxed8(stat + tile, 0x40u | (unsigned)total);
-    }
-}
-__device__ __forceinline__ int tile_lookback(uint8_t* stat, unsigned* incl, int tile, int total, int lane, int* err) {
-    if (tile == 0) return 0;
-    int excl = 0, base = tile - 1, spins = 0;
-    bool done = false;
-    while (!done) {
-        // 128 tiles per hop: window j = tiles base - 32 j - lane, nearest window first; one 32-byte sector each
-        unsigned d[4];
+// ---- the prefix over the tiles, without anybody polling shared descriptors (hundreds of tiles resolve together here: a
+// decoupled look-back has every one of them poll the same few cache lines, and the L2 serves a line one request at a
+// time).  Tiles are grouped in rounds of FU_ROUND by number.  A tile posts its kept mask into its own slot and bumps the
+// round's counter; whoever brings the counter to the round's size scans the round — one warp, eight slots per lane — takes
+// the round's base from the previous round's scanner through one word, and writes every tile's exclusive prefix into that
+// tile's own word.  A tile only ever polls its own word.
+constexpr int FU_ROUND = 256;
+
+struct ScanArrays {
+    unsigned* slot;              // [ntiles_pad] 0x100 | kept mask once posted
+    unsigned* excl;              // [ntiles_pad] exclusive prefix + 1
+    unsigned* round_cnt;         // [nrounds] tiles of the round that have posted
+    unsigned long long* round_base;   // [nrounds + 1] kept rows before the round + 1
+};
+
+__device__ __forceinline__ void round_scan(const ScanArrays& sa, int round, int ntiles, int lane, int* err) {
+    const int t0 = round * FU_ROUND + lane * 8;             // this lane's eight tiles (the arrays are padded to whole rounds)
+    __threadfence();                                        // acquire: every slot of the round was written before its bump
+    unsigned m[8];
+    int sum = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int idx = base - 32 * j - lane;
-            d[j] = idx >= 0 ? ld_relaxed8(stat + idx) : 0x80u;
-        }
-        int add = 0;
-        bool retry = false;
+    for (int j = 0; j < 8; ++j) {
+        m[j] = (t0 + j < ntiles) ? ld_relaxed32(sa.slot + t0 + j) : 0u;
+        sum += __popc(m[j] & 0xffu);
+    }
+    int incl = sum;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (done || retry) continue;
-            const unsigned missing = __ballot_sync(FULL, d[j] == 0u), has = __ballot_sync(FULL, (d[j] & 0x80u) != 0u);
-            const int first = has ? __ffs(has) - 1 : 32;    // nearest tile of the window that knows its inclusive prefix
-            const unsigned nearer = first >= 32 ? FULL : ((1u << first) - 1u);
-            if (missing & nearer) { retry = true; continue; }       // a predecessor that matters has not posted yet
-            add += warp_sum_int(lane < first ? (int)(d[j] & 0x3fu) : 0);
-            if (has) {
-                const int idx = base - 32 * j - first;
-                __threadfence();                            // acquire: the prefix was written before the status byte
-                if (idx >= 0) add += (int)ld_relaxed32(incl + idx);
-                done = true;
-            }
-        }
-        if (retry) {
-            if (++spins > FU_SPIN_LIMIT) { *err = 1; break; }
-            __nanosleep(64);
-            continue;
-        }
-        excl += add;
-        base -= 128;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
     }
-    if (lane == 0) {
-        st_relaxed32(incl + tile, (unsigned)(excl + total));
-        __threadfence();
-        st_relaxed8(stat + tile, 0x80u);
+    const int total = __shfl_sync(FULL, incl, 31);
+    unsigned long long base = 1ull;                         // round 0 starts at 0 (+ 1)
+    if (round > 0) {
+        int spins = 0;
+        base = ld_relaxed64(sa.round_base + round);
+        while (base == 0ull) {                              // the previous round's scanner is still at it
+            if (++spins > FU_SPIN_LIMIT) { *err = 1; base = 1ull; break; }
+            __nanosleep(100);
+            base = ld_relaxed64(sa.round_base + round);
+        }
     }
-    return excl;
+    if (lane == 0) st_relaxed64(sa.round_base + round + 1, base + (unsigned long long)total);
+    unsigned e = (unsigned)base + (unsigned)(incl - sum);   // exclusive prefix + 1 of this lane's first tile
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (t0 + j < ntiles) st_relaxed32(sa.excl + t0 + j, e);
+        e += __popc(m[j] & 0xffu);
+    }
 }
 
 // ---- shared memory behind the row slots: the hand-over rings between the three kinds of warps of a CTA
@@ -512,8 +496,11 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, W = a.tile_rows;
     unsigned char* wslots = fu_smem + (size_t)(2 * W) * a.slot_bytes;        // behind the front's slots: the workers'
     FusedShared* sh = reinterpret_cast<FusedShared*>(wslots + (size_t)FU_WSLOTS * a.slot_bytes);
-    unsigned* d_incl = reinterpret_cast<unsigned*>(a.desc + 1);
-    uint8_t* d_stat = reinterpret_cast<uint8_t*>(d_incl + a.ntiles_pad);
+    ScanArrays sa;
+    sa.round_base = a.desc + 1;
+    sa.slot = reinterpret_cast<unsigned*>(a.desc + 1 + a.nrounds + 1);
+    sa.excl = sa.slot + a.ntiles_pad;
+    sa.round_cnt = sa.excl + a.ntiles_pad;
     if (wid < W && lane == 0) mbar_init(smem_u32(&sh->bars[wid]), 1);
     if (threadIdx.x < FU_WSLOTS) mbar_init(smem_u32(&sh->wbars[threadIdx.x]), 1);
     if (threadIdx.x == 0) {
@@ -555,80 +542,123 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
 
     if (wid == FU_WARPS) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(FU_REGS_BACK));
-        // ---- scan warp: destinations.  For every tile of this CTA, in order: collect the front flags of its rows, post the
-        // count, resolve the exclusive prefix, publish the destinations, hand the tile to the workers.
+        // ---- scan warp: destinations.  Two steps per tile, pipelined: POST as soon as the front has flagged the tile's rows
+        // (mask into the tile's slot, bump the round, scan the round if this was its last tile), RESOLVE when the tile's
+        // exclusive prefix has been written (publish the destinations, hand the tile to the workers).  Posting never waits for
+        // resolving, so rounds fill at the front's pace.
+        constexpr int PEND = 8;
+        unsigned long long pend[PEND];                      // posted, not yet resolved: (tile << 16) | (merged << 8) | kept
+        int n_pend = 0, p_head = 0;
         unsigned head = 0;
+        long long cur = -1;                                 // tile being posted
+        bool exiting = false;
+        int idle = 0;
         while (true) {
-            int spins = 0;
-            bool dead = false;
-            while (*(volatile unsigned*)&sh->scan_tail == head) {
-                if (++spins > (FU_SPIN_LIMIT << 6)) { dead = true; break; }     // seconds without a tile: the tile warps are gone
-                __nanosleep(100);
+            bool progress = false;
+            if (cur < 0 && !exiting && n_pend < PEND && *(volatile unsigned*)&sh->scan_tail != head) {
+                __threadfence_block();
+                const unsigned long long item = *(volatile unsigned long long*)&sh->scan_item[head % FU_SCANQ];
+                __syncwarp();
+                ++head;
+                if (lane == 0) *(volatile unsigned*)&sh->scan_head = head;
+                if (item == FU_ITEM_EXIT) exiting = true;
+                else cur = (long long)item;
+                progress = true;
             }
-            if (dead) { err = 1; break; }
-            __threadfence_block();
-            const unsigned long long item = *(volatile unsigned long long*)&sh->scan_item[head % FU_SCANQ];
-            __syncwarp();
-            ++head;
-            if (lane == 0) *(volatile unsigned*)&sh->scan_head = head;
-            if (item == FU_ITEM_EXIT) break;
-            const int tile = (int)item;
-            const int r = tile * W + lane;
-            unsigned f = 0;
-            if (lane < W && r < a.S) f = wait_flag(a.fflag, r, &err);
-            const unsigned kept = __ballot_sync(FULL, f == 2u), merged = __ballot_sync(FULL, f == 1u);
-            const int total = __popc(kept);
-            if (lane == 0) FU_STAMP(tile, 6);
-            tile_post(d_stat, d_incl, tile, total, lane);
-            const int excl = tile_lookback(d_stat, d_incl, tile, total, lane, &err);
-            if (lane == 0) FU_STAMP(tile, 7);
-            if (kept >> lane & 1u) {
-                const int d = excl + __popc(kept & ((1u << lane) - 1u));
-                st_relaxed32(a.fdst + r, (unsigned)d + 1u);
-                a.dst[r] = d;
-            } else if (merged >> lane & 1u) {
-                a.dst[r] = -1;
+            // both polls travel together
+            unsigned f = 2u;
+            if (cur >= 0) {
+                const int r = (int)cur * W + lane;
+                if (lane < W && r < a.S) f = ld_relaxed32(a.fflag + r);
             }
-            if (kept | merged) {
-                const unsigned long long it = ((unsigned long long)tile << 38) | ((unsigned long long)excl << 8) | kept;
-                if (lane == 0) {                            // ring full: the workers are behind, and so is everything upstream
-                    int spins = 0;
-                    while (!queue_push(&sh->q, it)) {
-                        if (++spins > FU_SPIN_LIMIT) { err = 1; break; }
-                        __nanosleep(200);
+            unsigned e = 0;
+            const int ptile = n_pend ? (int)(pend[p_head] >> 16) : 0;
+            if (n_pend) e = ld_relaxed32(sa.excl + ptile);
+            if (cur >= 0 && !__ballot_sync(FULL, f == 0u)) {
+                // POST
+                const int tile = (int)cur, r = tile * W + lane;
+                const bool mine = lane < W && r < a.S;
+                const unsigned kept = __ballot_sync(FULL, mine && f == 2u), merged = __ballot_sync(FULL, mine && f == 1u);
+                if (lane == 0) FU_STAMP(tile, 6);
+                const int round = tile / FU_ROUND;
+                const int round_size = min(FU_ROUND, a.ntiles - round * FU_ROUND);
+                unsigned old = 0;
+                if (lane == 0) {
+                    st_relaxed32(sa.slot + tile, 0x100u | kept);
+                    __threadfence();                        // the slot is visible before the bump that may complete the round
+                    old = atomicAdd(sa.round_cnt + round, 1u);
+                }
+                old = __shfl_sync(FULL, old, 0);
+                if ((int)old == round_size - 1) round_scan(sa, round, a.ntiles, lane, &err);
+                pend[(p_head + n_pend) % PEND] = ((unsigned long long)tile << 16) | (merged << 8) | kept;
+                ++n_pend;
+                cur = -1;
+                progress = true;
+            }
+            if (n_pend && e != 0u) {
+                // RESOLVE
+                const unsigned long long pe = pend[p_head];
+                const int tile = ptile, excl = (int)e - 1, r = tile * W + lane;
+                const unsigned kept = (unsigned)pe & 0xffu, merged = (unsigned)(pe >> 8) & 0xffu;
+                const int total = __popc(kept);
+                if (lane == 0) FU_STAMP(tile, 7);
+                if (kept >> lane & 1u) {
+                    const int d = excl + __popc(kept & ((1u << lane) - 1u));
+                    st_relaxed32(a.fdst + r, (unsigned)d + 1u);
+                    a.dst[r] = d;
+                } else if (merged >> lane & 1u) {
+                    a.dst[r] = -1;
+                }
+                if (kept | merged) {
+                    const unsigned long long it = ((unsigned long long)tile << 38) | ((unsigned long long)excl << 8) | kept;
+                    if (lane == 0) {                        // ring full: the workers are behind, and so is everything upstream
+                        int spins = 0;
+                        while (!queue_push(&sh->q, it)) {
+                            if (++spins > FU_SPIN_LIMIT) { err = 1; break; }
+                            __nanosleep(200);
+                        }
                     }
                 }
+                if (lane == 0 && tile == a.ntiles - 1) {
+                    // the sequence is done: sizes, the speculated branch, the counters of the next call (main.py:112-120)
+                    const long long s_keep = excl + total, n_merged = a.S - s_keep;
+                    const long long N = a.counters[C_N], n_vis = a.counters[C_NVIS];
+                    int ec = 0;
+                    if (n_vis == 0) ec = 1;                 // the reference divides by zero here (main.py:114)
+                    else if (!((double)n_merged / (double)n_vis < a.bound)) ec = 3;   // top-k branch: the host redoes the call
+                    a.counters[C_COUNT] = n_merged;
+                    a.counters[C_NNEXT] = N - n_merged;
+                    a.counters[C_SKEEP] = s_keep;
+                    a.counters[C_BRANCH] = 0;
+                    a.counters[C_K] = 0;
+                    a.counters[C_NMERGED] = n_merged;
+                    a.counters_next[C_N] = N - n_merged;
+                    a.counters_next[C_NVIS] = n_vis - n_merged;
+                    a.counters_next[C_COUNT] = 0;
+                    a.counters_next[C_TICKET] = 0;
+                    a.counters_next[C_TICKET2] = 0;
+                    a.status[FF_ST_SEQ_KEEP] = s_keep;
+                    a.status[FF_ST_COUNT] = n_merged;
+                    a.status[FF_ST_NVIS] = n_vis;
+                    a.status[FF_ST_NCHAIN] = N;
+                    a.status[FF_ST_BRANCH] = 0;
+                    a.status[FF_ST_TOPK] = 0;
+                    a.status[FF_ST_ERROR] = ec;
+                    a.status[FF_ST_NMERGED] = n_merged;
+                    a.status[FF_ST_FUSED] = 1;
+                }
+                __syncwarp();
+                if (lane == 0) FU_STAMP(tile, 8);
+                p_head = (p_head + 1) % PEND;
+                --n_pend;
+                progress = true;
             }
-            if (lane == 0 && tile == a.ntiles - 1) {
-                // the sequence is done: sizes, the speculated branch, the counters of the next call (main.py:112-120)
-                const long long s_keep = excl + total, n_merged = a.S - s_keep;
-                const long long N = a.counters[C_N], n_vis = a.counters[C_NVIS];
-                int e = 0;
-                if (n_vis == 0) e = 1;                      // the reference divides by zero here (main.py:114)
-                else if (!((double)n_merged / (double)n_vis < a.bound)) e = 3;   // top-k branch: the host redoes the call
-                a.counters[C_COUNT] = n_merged;
-                a.counters[C_NNEXT] = N - n_merged;
-                a.counters[C_SKEEP] = s_keep;
-                a.counters[C_BRANCH] = 0;
-                a.counters[C_K] = 0;
-                a.counters[C_NMERGED] = n_merged;
-                a.counters_next[C_N] = N - n_merged;
-                a.counters_next[C_NVIS] = n_vis - n_merged;
-                a.counters_next[C_COUNT] = 0;
-                a.counters_next[C_TICKET] = 0;
-                a.counters_next[C_TICKET2] = 0;
-                a.status[FF_ST_SEQ_KEEP] = s_keep;
-                a.status[FF_ST_COUNT] = n_merged;
-                a.status[FF_ST_NVIS] = n_vis;
-                a.status[FF_ST_NCHAIN] = N;
-                a.status[FF_ST_BRANCH] = 0;
-                a.status[FF_ST_TOPK] = 0;
-                a.status[FF_ST_ERROR] = e;
-                a.status[FF_ST_NMERGED] = n_merged;
-                a.status[FF_ST_FUSED] = 1;
+            if (exiting && cur < 0 && n_pend == 0) break;
+            if (progress) idle = 0;
+            else {
+                if (++idle > (FU_SPIN_LIMIT << 4)) { err = 1; break; }      // seconds without progress: give up
+                __nanosleep(100);
             }
-            __syncwarp();
-            if (lane == 0) FU_STAMP(tile, 8);
         }
         if (lane == 0) {
             __threadfence_block();
