@@ -395,29 +395,53 @@ __device__ __forceinline__ void worker_run(const FusedArgs& a, WorkerSlots& ws, 
     ws.next = 1;
 }
 
-// the aux rows of sequence row r -> destination row d: one 16- or 8-byte piece per lane and entry, all loads first
-__device__ __forceinline__ void worker_aux(const FusedArgs& a, const AuxPack& aux, int r, int d, int lane) {
+// The aux rows of a tile's kept rows (row tile * W + w -> destination d_of[w], -1: none): one 16- or 8-byte piece per lane and
+// entry; the loads of up to FU_AUX_BATCH (row, entry) pairs are in flight before the first store.
+constexpr int FU_AUX_BATCH = 12;
+__device__ __forceinline__ void worker_aux_tile(const FusedArgs& a, const AuxPack& aux, int tile, int W, int d_mine, int lane) {
     const AuxFlat& f = a.auxf;
-    if (f.n < 0) { gather_aux_rows(aux, r, d, lane); return; }
-    uint4 v[8];
+    if (f.n < 0) {
+#pragma unroll 1
+        for (int w = 0; w < W; ++w) {
+            const int d = __shfl_sync(FULL, d_mine, w);
+            if (d >= 0) gather_aux_rows(aux, tile * W + w, d, lane);
+        }
+        return;
+    }
+    const int n_pairs = W * f.n;                            // pair k = (row k / n, entry k % n)
+#pragma unroll 1
+    for (int k0 = 0; k0 < n_pairs; k0 += FU_AUX_BATCH) {
+        uint4 v[FU_AUX_BATCH];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        v[e] = make_uint4(0, 0, 0, 0);
-        if (e < f.n) {
-            const int rb = f.row_bytes[e];
-            const char* s = f.src[e] + (int64_t)r * rb;
-            if (f.piece[e] == 8) { if (lane * 8 < rb) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(s) + lane); v[e].x = t.x; v[e].y = t.y; } }
-            else if (lane * 16 < rb) v[e] = __ldg(reinterpret_cast<const uint4*>(s) + lane);
+        for (int i = 0; i < FU_AUX_BATCH; ++i) {
+            v[i] = make_uint4(0, 0, 0, 0);
+            const int k = k0 + i;
+            if (k < n_pairs) {
+                const int w = k / f.n, e = k - w * f.n;
+                const int d = __shfl_sync(FULL, d_mine, w);
+                if (d >= 0) {
+                    const int rb = f.row_bytes[e];
+                    const char* src = f.src[e] + (int64_t)(tile * W + w) * rb;
+                    if (f.piece[e] == 8) { if (lane * 8 < rb) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(src) + lane); v[i].x = t.x; v[i].y = t.y; } }
+                    else if (lane * 16 < rb) v[i] = __ldg(reinterpret_cast<const uint4*>(src) + lane);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < FU_AUX_BATCH; ++i) {
+            const int k = k0 + i;
+            if (k < n_pairs) {
+                const int w = k / f.n, e = k - w * f.n;
+                const int d = __shfl_sync(FULL, d_mine, w);
+                if (d >= 0) {
+                    const int rb = f.row_bytes[e];
+                    char* o = f.dst[e] + (int64_t)d * rb;
+                    if (f.piece[e] == 8) { if (lane * 8 < rb) reinterpret_cast<uint2*>(o)[lane] = make_uint2(v[i].x, v[i].y); }
+                    else if (lane * 16 < rb) reinterpret_cast<uint4*>(o)[lane] = v[i];
+                }
+            }
         }
     }
-#pragma unroll
-    for (int e = 0; e < 8; ++e)
-        if (e < f.n) {
-            const int rb = f.row_bytes[e];
-            char* o = f.dst[e] + (int64_t)d * rb;
-            if (f.piece[e] == 8) { if (lane * 8 < rb) reinterpret_cast<uint2*>(o)[lane] = make_uint2(v[e].x, v[e].y); }
-            else if (lane * 16 < rb) reinterpret_cast<uint4*>(o)[lane] = v[e];
-        }
 }
 
 // The runs that end in one tile, L2 -> destination, with the aux rows of its kept rows and the links of the next call.
@@ -432,6 +456,7 @@ __device__ __forceinline__ void run_tile_item(const FusedArgs& a, const AuxPack&
     const int tile = (int)((item >> 38) & 0xffffffull), excl = (int)((item >> 8) & 0x3fffffffull);
     const unsigned kept = (unsigned)(item & 0xffull);
     const int r = tile * W + lane;
+    if (lane == 0) FU_STAMP(tile, 12);
     int run_last = -1, run_anchor = -1, run_L = 0, run_dst = -1;    // the run this lane's row ends
     int self_dst = -1, d_r = -1;
     if (lane < W && r < a.S) {
@@ -470,19 +495,24 @@ __device__ __forceinline__ void run_tile_item(const FusedArgs& a, const AuxPack&
         }
     }
     __syncwarp();
+    if (lane == 0) FU_STAMP(tile, 3);
     const int row_bytes = a.row_bytes;
+    // plain copies first (two in flight through the slots), then the runs (they need both slots), then the aux rows
+#pragma unroll 1
+    for (int w = 0; w < W; ++w) {
+        const int anchor = __shfl_sync(FULL, run_anchor, w), L = __shfl_sync(FULL, run_L, w), d_a = __shfl_sync(FULL, run_dst, w);
+        const int sd = __shfl_sync(FULL, self_dst, w);
+        if (anchor >= 0 && L == 0) worker_copy(ws, a.hidden + (int64_t)anchor * row_bytes, a.out + (int64_t)d_a * row_bytes, row_bytes, lane);
+        if (sd >= 0) worker_copy(ws, a.hidden + (int64_t)(tile * W + w) * row_bytes, a.out + (int64_t)sd * row_bytes, row_bytes, lane);
+    }
+    if (aux.n) worker_aux_tile(a, aux, tile, W, d_r, lane);
 #pragma unroll 1
     for (int w = 0; w < W; ++w) {
         const int anchor = __shfl_sync(FULL, run_anchor, w), last = __shfl_sync(FULL, run_last, w);
         const int L = __shfl_sync(FULL, run_L, w), d_a = __shfl_sync(FULL, run_dst, w);
-        const int sd = __shfl_sync(FULL, self_dst, w), d_w = __shfl_sync(FULL, d_r, w);
-        if (anchor >= 0) {
-            if (L == 0) worker_copy(ws, a.hidden + (int64_t)anchor * row_bytes, a.out + (int64_t)d_a * row_bytes, row_bytes, lane);
-            else worker_run<DT>(a, ws, anchor, last, L, d_a, lane);
-        }
-        if (sd >= 0) worker_copy(ws, a.hidden + (int64_t)(tile * W + w) * row_bytes, a.out + (int64_t)sd * row_bytes, row_bytes, lane);
-        if (d_w >= 0 && aux.n) worker_aux(a, aux, tile * W + w, d_w, lane);
+        if (anchor >= 0 && L > 0) worker_run<DT>(a, ws, anchor, last, L, d_a, lane);
     }
+    if (lane == 0) FU_STAMP(tile, 15);
 }
 
 // CTA = two front warpgroups (warps 0 .. 7: the W tile warps, W rows per tile, two shared-memory slots each) + one back
@@ -549,6 +579,7 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
         constexpr int PEND = 8;
         unsigned long long pend[PEND];                      // posted, not yet resolved: (tile << 16) | (merged << 8) | kept
         int n_pend = 0, p_head = 0;
+        bool head_published = false;
         unsigned head = 0;
         long long cur = -1;                                 // tile being posted
         bool exiting = false;
@@ -596,62 +627,65 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
                 progress = true;
             }
             if (n_pend && e != 0u) {
-                // RESOLVE
+                // RESOLVE: publish the destinations once; hand the tile to the workers when their ring has room (a full ring
+                // must not keep this warp from posting the tiles behind it)
                 const unsigned long long pe = pend[p_head];
                 const int tile = ptile, excl = (int)e - 1, r = tile * W + lane;
                 const unsigned kept = (unsigned)pe & 0xffu, merged = (unsigned)(pe >> 8) & 0xffu;
                 const int total = __popc(kept);
-                if (lane == 0) FU_STAMP(tile, 7);
-                if (kept >> lane & 1u) {
-                    const int d = excl + __popc(kept & ((1u << lane) - 1u));
-                    st_relaxed32(a.fdst + r, (unsigned)d + 1u);
-                    a.dst[r] = d;
-                } else if (merged >> lane & 1u) {
-                    a.dst[r] = -1;
+                if (!head_published) {
+                    if (lane == 0) FU_STAMP(tile, 7);
+                    if (kept >> lane & 1u) {
+                        const int d = excl + __popc(kept & ((1u << lane) - 1u));
+                        st_relaxed32(a.fdst + r, (unsigned)d + 1u);
+                        a.dst[r] = d;
+                    } else if (merged >> lane & 1u) {
+                        a.dst[r] = -1;
+                    }
+                    if (lane == 0 && tile == a.ntiles - 1) {
+                        // the sequence is done: sizes, the speculated branch, the counters of the next call (main.py:112-120)
+                        const long long s_keep = excl + total, n_merged = a.S - s_keep;
+                        const long long N = a.counters[C_N], n_vis = a.counters[C_NVIS];
+                        int ec = 0;
+                        if (n_vis == 0) ec = 1;             // the reference divides by zero here (main.py:114)
+                        else if (!((double)n_merged / (double)n_vis < a.bound)) ec = 3;   // top-k branch: the host redoes the call
+                        a.counters[C_COUNT] = n_merged;
+                        a.counters[C_NNEXT] = N - n_merged;
+                        a.counters[C_SKEEP] = s_keep;
+                        a.counters[C_BRANCH] = 0;
+                        a.counters[C_K] = 0;
+                        a.counters[C_NMERGED] = n_merged;
+                        a.counters_next[C_N] = N - n_merged;
+                        a.counters_next[C_NVIS] = n_vis - n_merged;
+                        a.counters_next[C_COUNT] = 0;
+                        a.counters_next[C_TICKET] = 0;
+                        a.counters_next[C_TICKET2] = 0;
+                        a.status[FF_ST_SEQ_KEEP] = s_keep;
+                        a.status[FF_ST_COUNT] = n_merged;
+                        a.status[FF_ST_NVIS] = n_vis;
+                        a.status[FF_ST_NCHAIN] = N;
+                        a.status[FF_ST_BRANCH] = 0;
+                        a.status[FF_ST_TOPK] = 0;
+                        a.status[FF_ST_ERROR] = ec;
+                        a.status[FF_ST_NMERGED] = n_merged;
+                        a.status[FF_ST_FUSED] = 1;
+                    }
+                    head_published = true;
+                    progress = true;
                 }
+                int ok = 1;
                 if (kept | merged) {
                     const unsigned long long it = ((unsigned long long)tile << 38) | ((unsigned long long)excl << 8) | kept;
-                    if (lane == 0) {                        // ring full: the workers are behind, and so is everything upstream
-                        int spins = 0;
-                        while (!queue_push(&sh->q, it)) {
-                            if (++spins > FU_SPIN_LIMIT) { err = 1; break; }
-                            __nanosleep(200);
-                        }
-                    }
+                    if (lane == 0) ok = queue_push(&sh->q, it) ? 1 : 0;
+                    ok = __shfl_sync(FULL, ok, 0);
                 }
-                if (lane == 0 && tile == a.ntiles - 1) {
-                    // the sequence is done: sizes, the speculated branch, the counters of the next call (main.py:112-120)
-                    const long long s_keep = excl + total, n_merged = a.S - s_keep;
-                    const long long N = a.counters[C_N], n_vis = a.counters[C_NVIS];
-                    int ec = 0;
-                    if (n_vis == 0) ec = 1;                 // the reference divides by zero here (main.py:114)
-                    else if (!((double)n_merged / (double)n_vis < a.bound)) ec = 3;   // top-k branch: the host redoes the call
-                    a.counters[C_COUNT] = n_merged;
-                    a.counters[C_NNEXT] = N - n_merged;
-                    a.counters[C_SKEEP] = s_keep;
-                    a.counters[C_BRANCH] = 0;
-                    a.counters[C_K] = 0;
-                    a.counters[C_NMERGED] = n_merged;
-                    a.counters_next[C_N] = N - n_merged;
-                    a.counters_next[C_NVIS] = n_vis - n_merged;
-                    a.counters_next[C_COUNT] = 0;
-                    a.counters_next[C_TICKET] = 0;
-                    a.counters_next[C_TICKET2] = 0;
-                    a.status[FF_ST_SEQ_KEEP] = s_keep;
-                    a.status[FF_ST_COUNT] = n_merged;
-                    a.status[FF_ST_NVIS] = n_vis;
-                    a.status[FF_ST_NCHAIN] = N;
-                    a.status[FF_ST_BRANCH] = 0;
-                    a.status[FF_ST_TOPK] = 0;
-                    a.status[FF_ST_ERROR] = ec;
-                    a.status[FF_ST_NMERGED] = n_merged;
-                    a.status[FF_ST_FUSED] = 1;
+                if (ok) {
+                    if (lane == 0) FU_STAMP(tile, 8);
+                    p_head = (p_head + 1) % PEND;
+                    --n_pend;
+                    head_published = false;
+                    progress = true;
                 }
-                __syncwarp();
-                if (lane == 0) FU_STAMP(tile, 8);
-                p_head = (p_head + 1) % PEND;
-                --n_pend;
-                progress = true;
             }
             if (exiting && cur < 0 && n_pend == 0) break;
             if (progress) idle = 0;

@@ -29,7 +29,7 @@ np.save(out[:-4] + ".npy", t)
 t0 = t[:, 0][t[:, 0] > 0].min()
 us = lambda x: (x - t0) / 1e3
 n = t.shape[0]
-print(f"{n} tiles; kernel span {us(t[:, [8, 11]].max()):.1f} us")
+print(f"{n} tiles; kernel span {us(t[:, [8, 11, 15]].max()):.1f} us")
 def dd(i, j):
     m = (t[:, i] > 0) & (t[:, j] > 0)
     if not m.any():
@@ -40,7 +40,8 @@ def dd(i, j):
 # (latest warp), 6 scan warp has the tile's flags, 7 look-back resolved / destinations published, 8 tile handed to the workers
 for name, i, j in [("rows arrive (latest warp)", 10, 0), ("predecessor flag known (latest warp)", 9, 0), ("front step done (latest warp)", 11, 0),
                    ("scan has the flags, after front done", 6, 11), ("look-back", 7, 6), ("hand-over to workers", 8, 7),
-                   ("destinations after tile taken", 7, 0)]:
+                   ("destinations after tile taken", 7, 0), ("worker takes the tile, after hand-over", 12, 8),
+                   ("worker: walks and destinations", 3, 12), ("worker: copies, aux rows, runs", 15, 3)]:
     print(f"  {name:40s} {dd(i, j)}")
 print("  last tile warp, one iteration:")
 for name, i, j in [("tile known after its ticket was taken", 2, 0), ("link known, TMA issued", 4, 2), ("rows arrived", 5, 4), ("similarity done", 14, 5)]:
