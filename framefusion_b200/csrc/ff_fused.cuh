@@ -37,9 +37,9 @@
 namespace ff {
 
 constexpr int FU_WARPS = 8;                        // warps of the two front warpgroups: up to seven tile warps (rows per tile) and the dispatcher
-constexpr int FU_WORKERS = 4;                      // warps per CTA besides the tile warps: one scan warp + workers (one warpgroup)
-constexpr int FU_WSLOTS = 2 * (FU_WORKERS - 1);    // shared-memory row slots of the workers: two each
-constexpr int FU_REGS_LAUNCH = 80, FU_REGS_FRONT = 56, FU_REGS_BACK = 128;   // setmaxnreg: 12 * 32 * 80 = 8 * 32 * 56 + 4 * 32 * 128
+constexpr int FU_WORKERS = 8;                      // warps of the two back warpgroups: the scan warp, six workers, one spare
+constexpr int FU_WSLOTS = 6;                       // shared-memory row slots of the workers: one each
+constexpr int FU_REGS_LAUNCH = 64, FU_REGS_FRONT = 40, FU_REGS_BACK = 88;    // setmaxnreg: 16 * 32 * 64 = 8 * 32 * 40 + 8 * 32 * 88
 constexpr int FU_QSIZE = 32;                       // ring entries between the scan warp and the workers
 constexpr int FU_SCANQ = 8;                        // ring entries between the tile warps and the scan warp
 constexpr int FU_TICKETS = 4;                      // how many iterations the tile warps of a CTA may drift apart
@@ -293,61 +293,46 @@ __device__ __forceinline__ bool queue_pop(FusedQueue* q, int lane, unsigned long
     return true;
 }
 
-// ---- the workers' side.  A worker owns two shared-memory row slots; rows travel L2 -> slot -> destination by TMA bulk
-// copies (no registers, two rows in flight per worker), runs are summed in the slots.
-struct WorkerSlots {
-    unsigned char* ptr[2];
-    uint32_t addr[2], bar[2], phase[2];
-    int state[2];                                           // 0 free, 1 a row is arriving (to be stored to dst), 2 a store is reading it
-    char* dst[2];
-    int next;
+// ---- the workers' side.  A worker owns one shared-memory row slot; plain rows travel L2 -> slot -> destination by TMA bulk
+// copies (no registers), a run keeps its sum in the slot while the members stream through registers.
+struct WorkerSlot {
+    unsigned char* ptr;
+    uint32_t addr, bar, phase;
+    bool storing;                                           // lane 0: a bulk store may still be reading the slot
 };
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// the row that is arriving in slot s goes on to its destination
-__device__ __forceinline__ void slot_finish(WorkerSlots& ws, int s, int row_bytes, int lane) {
-    if (ws.state[s] != 1) return;
-    mbar_wait(ws.bar[s], ws.phase[s]);
-    ws.phase[s] ^= 1u;
+__device__ __forceinline__ void slot_free(WorkerSlot& ws, int lane) {
+    if (lane == 0 && ws.storing) { tma_wait_read_0(); ws.storing = false; }
+    __syncwarp();
+}
+// src row -> dst row through the slot
+__device__ __forceinline__ void worker_copy(WorkerSlot& ws, const char* src, char* dst, int row_bytes, int lane) {
+    slot_free(ws, lane);
     if (lane == 0) {
-        tma_store(ws.dst[s], ws.addr[s], (uint32_t)row_bytes);
+        mbar_expect_tx(ws.bar, (uint32_t)row_bytes);
+        tma_load(ws.addr, src, (uint32_t)row_bytes, ws.bar);
+        mbar_wait(ws.bar, ws.phase);
+        tma_store(dst, ws.addr, (uint32_t)row_bytes);
         tma_commit();
+        ws.storing = true;
     }
-    ws.state[s] = 2;
-}
-// slot s can be overwritten
-__device__ __forceinline__ void slot_free(WorkerSlots& ws, int s, int row_bytes, int lane) {
-    slot_finish(ws, s, row_bytes, lane);
-    if (ws.state[s] == 2) {
-        if (lane == 0) tma_wait_read_0();                   // (every store this lane has issued: the other slot's too)
-        __syncwarp();
-        ws.state[0] = ws.state[0] == 2 ? 0 : ws.state[0];
-        ws.state[1] = ws.state[1] == 2 ? 0 : ws.state[1];
-    }
-}
-// src row -> dst row through the next slot; returns with the row (and possibly the one before it) still travelling
-__device__ __forceinline__ void worker_copy(WorkerSlots& ws, const char* src, char* dst, int row_bytes, int lane) {
-    const int s = ws.next;
-    ws.next ^= 1;
-    slot_free(ws, s, row_bytes, lane);
-    if (lane == 0) {
-        mbar_expect_tx(ws.bar[s], (uint32_t)row_bytes);
-        tma_load(ws.addr[s], src, (uint32_t)row_bytes, ws.bar[s]);
-    }
-    ws.state[s] = 1;
-    ws.dst[s] = dst;
-    slot_finish(ws, s ^ 1, row_bytes, lane);                // meanwhile the previous row has arrived: send it on
+    ws.phase ^= 1u;
 }
 
 // A run: anchor row and its L >= 1 members -> destination row d_a as T(T(..T(anchor + m1) ..+ mL) / T(L + 1)): one rounding to
 // T per add in chain order (main.py:304-311), one division (main.py:314-317).  `last` = the last member; the members are
-// visited front to back (lane k remembers the k-th from the end; runs longer than 32 follow the successor links).
+// visited front to back (lane k remembers the k-th from the end; runs longer than 32 follow the successor links).  The
+// anchor arrives in the slot by TMA while the first member's vectors are already on their way into registers.
 template <int DT>
-__device__ __forceinline__ void worker_run(const FusedArgs& a, WorkerSlots& ws, int anchor, int last, int L, int d_a, int lane) {
+__device__ __forceinline__ void worker_run(const FusedArgs& a, WorkerSlot& ws, int anchor, int last, int L, int d_a, int lane) {
     const int row_bytes = a.row_bytes, nvec = a.nvec;
-    slot_free(ws, 0, row_bytes, lane);
-    slot_free(ws, 1, row_bytes, lane);
+    slot_free(ws, lane);
+    if (lane == 0) {
+        mbar_expect_tx(ws.bar, (uint32_t)row_bytes);
+        tma_load(ws.addr, a.hidden + (int64_t)anchor * row_bytes, (uint32_t)row_bytes, ws.bar);
+    }
     int mine = -1;
     {
         int x = last;
@@ -356,48 +341,51 @@ __device__ __forceinline__ void worker_run(const FusedArgs& a, WorkerSlots& ws, 
             x = __ldg(&a.link[x].x);
         }
     }
-    uint4* A = reinterpret_cast<uint4*>(ws.ptr[0]);
-    const uint4* B = reinterpret_cast<const uint4*>(ws.ptr[1]);
+    uint4* A = reinterpret_cast<uint4*>(ws.ptr);
+    const Divider<DT> dv(L + 1);
+    const int nfull = nvec >> 5;
     int walk = anchor;
+    bool arrived = false;
 #pragma unroll 1
     for (int m = L - 1; m >= 0; --m) {                      // m = L - 1: first member behind the anchor ... m = 0: the last
         int idx;
         if (L <= 32) idx = __shfl_sync(FULL, mine, m);
         else { walk = __ldg(&a.link[walk].y); idx = walk; }
-        __syncwarp();                                       // every lane has read slot B
-        if (lane == 0) {
-            if (m == L - 1) {
-                mbar_expect_tx(ws.bar[0], (uint32_t)row_bytes);
-                tma_load(ws.addr[0], a.hidden + (int64_t)anchor * row_bytes, (uint32_t)row_bytes, ws.bar[0]);
+        const uint4* mr = reinterpret_cast<const uint4*>(a.hidden + (int64_t)idx * row_bytes);
+        const bool fin = m == 0;
+        int v = 0;
+#pragma unroll 1
+        for (; v + 7 <= nfull; v += 7) {                    // seven vectors per lane in flight (7-KB rows: two rounds)
+            uint4 x[7];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) x[q] = ld_cg16(mr + (v + q) * 32 + lane);
+            if (!arrived) { mbar_wait(ws.bar, ws.phase); ws.phase ^= 1u; arrived = true; }
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                uint4 t = Num<DT>::add_vec(A[(v + q) * 32 + lane], x[q]);        // T(acc + member)
+                if (fin) t = dv.vec_fast(t);
+                A[(v + q) * 32 + lane] = t;
             }
-            mbar_expect_tx(ws.bar[1], (uint32_t)row_bytes);
-            tma_load(ws.addr[1], a.hidden + (int64_t)idx * row_bytes, (uint32_t)row_bytes, ws.bar[1]);
         }
-        if (m == L - 1) { mbar_wait(ws.bar[0], ws.phase[0]); ws.phase[0] ^= 1u; }
-        mbar_wait(ws.bar[1], ws.phase[1]);
-        ws.phase[1] ^= 1u;
-        if (m > 0) {
-#pragma unroll 2
-            for (int v = lane; v < nvec; v += 32) A[v] = Num<DT>::add_vec(A[v], B[v]);       // T(acc + member)
-        } else {
-            const Divider<DT> dv(L + 1);
-#pragma unroll 2
-            for (int v = lane; v < nvec; v += 32) A[v] = dv.vec_fast(Num<DT>::add_vec(A[v], B[v]));
+        if (!arrived) { mbar_wait(ws.bar, ws.phase); ws.phase ^= 1u; arrived = true; }
+        for (int i = v * 32 + lane; i < nvec; i += 32) {    // what is left of the row
+            uint4 t = Num<DT>::add_vec(A[i], ld_cg16(mr + i));
+            if (fin) t = dv.vec_fast(t);
+            A[i] = t;
         }
     }
     fence_async_smem();                                     // the sums were written through the generic proxy
     __syncwarp();
     if (lane == 0) {
-        tma_store(a.out + (int64_t)d_a * row_bytes, ws.addr[0], (uint32_t)row_bytes);
+        tma_store(a.out + (int64_t)d_a * row_bytes, ws.addr, (uint32_t)row_bytes);
         tma_commit();
+        ws.storing = true;
     }
-    ws.state[0] = 2;
-    ws.next = 1;
 }
 
 // The aux rows of a tile's kept rows (row tile * W + w -> destination d_of[w], -1: none): one 16- or 8-byte piece per lane and
 // entry; the loads of up to FU_AUX_BATCH (row, entry) pairs are in flight before the first store.
-constexpr int FU_AUX_BATCH = 12;
+constexpr int FU_AUX_BATCH = 8;
 __device__ __forceinline__ void worker_aux_tile(const FusedArgs& a, const AuxPack& aux, int tile, int W, int d_mine, int lane) {
     const AuxFlat& f = a.auxf;
     if (f.n < 0) {
@@ -451,7 +439,7 @@ __device__ __forceinline__ void worker_aux_tile(const FusedArgs& a, const AuxPac
 //   merged away at the end of its chain: it ends its own run -> that run goes out
 // Every flag the walks read belongs to an earlier row than the tile's last: known since the tile's look-back resolved.
 template <int DT>
-__device__ __forceinline__ void run_tile_item(const FusedArgs& a, const AuxPack& aux, WorkerSlots& ws, int W, unsigned long long item,
+__device__ __forceinline__ void run_tile_item(const FusedArgs& a, const AuxPack& aux, WorkerSlot& ws, int W, unsigned long long item,
                                               int lane, int* err) {
     const int tile = (int)((item >> 38) & 0xffffffull), excl = (int)((item >> 8) & 0x3fffffffull);
     const unsigned kept = (unsigned)(item & 0xffull);
@@ -497,7 +485,7 @@ __device__ __forceinline__ void run_tile_item(const FusedArgs& a, const AuxPack&
     __syncwarp();
     if (lane == 0) FU_STAMP(tile, 3);
     const int row_bytes = a.row_bytes;
-    // plain copies first (two in flight through the slots), then the runs (they need both slots), then the aux rows
+    // the aux rows' loads first (they travel while the rows are copied), then the plain copies, then the runs
 #pragma unroll 1
     for (int w = 0; w < W; ++w) {
         const int anchor = __shfl_sync(FULL, run_anchor, w), L = __shfl_sync(FULL, run_L, w), d_a = __shfl_sync(FULL, run_dst, w);
@@ -515,9 +503,9 @@ __device__ __forceinline__ void run_tile_item(const FusedArgs& a, const AuxPack&
     if (lane == 0) FU_STAMP(tile, 15);
 }
 
-// CTA = two front warpgroups (warps 0 .. 7: the W tile warps, W rows per tile, two shared-memory slots each) + one back
-// warpgroup (warp 8: scan, warps 9 .. 11: workers).  The warpgroups trade registers (setmaxnreg): the front needs few, the
-// back keeps whole rows in flight.
+// CTA = two front warpgroups (warps 0 .. 7: the W tile warps — W rows per tile, two shared-memory slots each — and the
+// dispatcher) + two back warpgroups (warp 8: scan, warps 9 .. 14: workers, one slot each).  The warpgroups trade registers
+// (setmaxnreg): the front needs few.
 template <int DT>
 __global__ void __launch_bounds__((FU_WARPS + FU_WORKERS) * 32, 2)
 k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPack aux) {
@@ -550,21 +538,17 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
     if (wid > FU_WARPS) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(FU_REGS_BACK));
         // ---- workers: copies nobody waits for
-        WorkerSlots ws;
         const int me = wid - FU_WARPS - 1;
-        for (int s = 0; s < 2; ++s) {
-            ws.ptr[s] = wslots + (size_t)(2 * me + s) * a.slot_bytes;
-            ws.addr[s] = smem_u32(ws.ptr[s]);
-            ws.bar[s] = smem_u32(&sh->wbars[2 * me + s]);
-            ws.phase[s] = 0;
-            ws.state[s] = 0;
-            ws.dst[s] = nullptr;
-        }
-        ws.next = 0;
+        if (me >= FU_WSLOTS) return;                        // the spare warp of the back warpgroups
+        WorkerSlot ws;
+        ws.ptr = wslots + (size_t)me * a.slot_bytes;
+        ws.addr = smem_u32(ws.ptr);
+        ws.bar = smem_u32(&sh->wbars[me]);
+        ws.phase = 0;
+        ws.storing = false;
         unsigned long long item;
         while (queue_pop(&sh->q, lane, &item)) run_tile_item<DT>(a, aux, ws, W, item, lane, &err);
-        slot_free(ws, 0, a.row_bytes, lane);
-        slot_free(ws, 1, a.row_bytes, lane);
+        slot_free(ws, lane);
         if (lane == 0) tma_wait_all();
         if (err && lane == 0) a.status[FF_ST_INTERNAL] = 1;
         return;
