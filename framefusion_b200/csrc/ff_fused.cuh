@@ -37,9 +37,9 @@
 namespace ff {
 
 constexpr int FU_WARPS = 8;                        // warps of the two front warpgroups: up to seven tile warps (rows per tile) and the dispatcher
-constexpr int FU_WORKERS = 8;                      // warps of the two back warpgroups: the scan warp, six workers, one spare
-constexpr int FU_WSLOTS = 6;                       // shared-memory row slots of the workers: one each
-constexpr int FU_REGS_LAUNCH = 64, FU_REGS_FRONT = 40, FU_REGS_BACK = 88;    // setmaxnreg: 16 * 32 * 64 = 8 * 32 * 40 + 8 * 32 * 88
+constexpr int FU_WORKERS = 4;                      // warps per CTA besides the tile warps: one scan warp + workers (one warpgroup)
+constexpr int FU_WSLOTS = 2 * (FU_WORKERS - 1);    // shared-memory row slots of the workers: two each
+constexpr int FU_REGS_LAUNCH = 80, FU_REGS_FRONT = 56, FU_REGS_BACK = 128;   // setmaxnreg: 12 * 32 * 80 = 8 * 32 * 56 + 4 * 32 * 128
 constexpr int FU_QSIZE = 32;                       // ring entries between the scan warp and the workers
 constexpr int FU_SCANQ = 8;                        // ring entries between the tile warps and the scan warp
 constexpr int FU_TICKETS = 4;                      // how many iterations the tile warps of a CTA may drift apart
@@ -293,46 +293,61 @@ __device__ __forceinline__ bool queue_pop(FusedQueue* q, int lane, unsigned long
     return true;
 }
 
-// ---- the workers' side.  A worker owns one shared-memory row slot; plain rows travel L2 -> slot -> destination by TMA bulk
-// copies (no registers), a run keeps its sum in the slot while the members stream through registers.
-struct WorkerSlot {
-    unsigned char* ptr;
-    uint32_t addr, bar, phase;
-    bool storing;                                           // lane 0: a bulk store may still be reading the slot
+// ---- the workers' side.  A worker owns two shared-memory row slots; rows travel L2 -> slot -> destination by TMA bulk
+// copies (no registers, two rows in flight per worker), runs are summed in the slots.
+struct WorkerSlots {
+    unsigned char* ptr[2];
+    uint32_t addr[2], bar[2], phase[2];
+    int state[2];                                           // 0 free, 1 a row is arriving (to be stored to dst), 2 a store is reading it
+    char* dst[2];
+    int next;
 };
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void slot_free(WorkerSlot& ws, int lane) {
-    if (lane == 0 && ws.storing) { tma_wait_read_0(); ws.storing = false; }
-    __syncwarp();
-}
-// src row -> dst row through the slot
-__device__ __forceinline__ void worker_copy(WorkerSlot& ws, const char* src, char* dst, int row_bytes, int lane) {
-    slot_free(ws, lane);
+// the row that is arriving in slot s goes on to its destination
+__device__ __forceinline__ void slot_finish(WorkerSlots& ws, int s, int row_bytes, int lane) {
+    if (ws.state[s] != 1) return;
+    mbar_wait(ws.bar[s], ws.phase[s]);
+    ws.phase[s] ^= 1u;
     if (lane == 0) {
-        mbar_expect_tx(ws.bar, (uint32_t)row_bytes);
-        tma_load(ws.addr, src, (uint32_t)row_bytes, ws.bar);
-        mbar_wait(ws.bar, ws.phase);
-        tma_store(dst, ws.addr, (uint32_t)row_bytes);
+        tma_store(ws.dst[s], ws.addr[s], (uint32_t)row_bytes);
         tma_commit();
-        ws.storing = true;
     }
-    ws.phase ^= 1u;
+    ws.state[s] = 2;
+}
+// slot s can be overwritten
+__device__ __forceinline__ void slot_free(WorkerSlots& ws, int s, int row_bytes, int lane) {
+    slot_finish(ws, s, row_bytes, lane);
+    if (ws.state[s] == 2) {
+        if (lane == 0) tma_wait_read_0();                   // (every store this lane has issued: the other slot's too)
+        __syncwarp();
+        ws.state[0] = ws.state[0] == 2 ? 0 : ws.state[0];
+        ws.state[1] = ws.state[1] == 2 ? 0 : ws.state[1];
+    }
+}
+// src row -> dst row through the next slot; returns with the row (and possibly the one before it) still travelling
+__device__ __forceinline__ void worker_copy(WorkerSlots& ws, const char* src, char* dst, int row_bytes, int lane) {
+    const int s = ws.next;
+    ws.next ^= 1;
+    slot_free(ws, s, row_bytes, lane);
+    if (lane == 0) {
+        mbar_expect_tx(ws.bar[s], (uint32_t)row_bytes);
+        tma_load(ws.addr[s], src, (uint32_t)row_bytes, ws.bar[s]);
+    }
+    ws.state[s] = 1;
+    ws.dst[s] = dst;
+    slot_finish(ws, s ^ 1, row_bytes, lane);                // meanwhile the previous row has arrived: send it on
 }
 
 // A run: anchor row and its L >= 1 members -> destination row d_a as T(T(..T(anchor + m1) ..+ mL) / T(L + 1)): one rounding to
 // T per add in chain order (main.py:304-311), one division (main.py:314-317).  `last` = the last member; the members are
-// visited front to back (lane k remembers the k-th from the end; runs longer than 32 follow the successor links).  The
-// anchor arrives in the slot by TMA while the first member's vectors are already on their way into registers.
+// visited front to back (lane k remembers the k-th from the end; runs longer than 32 follow the successor links).
 template <int DT>
-__device__ __forceinline__ void worker_run(const FusedArgs& a, WorkerSlot& ws, int anchor, int last, int L, int d_a, int lane) {
+__device__ __forceinline__ void worker_run(const FusedArgs& a, WorkerSlots& ws, int anchor, int last, int L, int d_a, int lane) {
     const int row_bytes = a.row_bytes, nvec = a.nvec;
-    slot_free(ws, lane);
-    if (lane == 0) {
-        mbar_expect_tx(ws.bar, (uint32_t)row_bytes);
-        tma_load(ws.addr, a.hidden + (int64_t)anchor * row_bytes, (uint32_t)row_bytes, ws.bar);
-    }
+    slot_free(ws, 0, row_bytes, lane);
+    slot_free(ws, 1, row_bytes, lane);
     int mine = -1;
     {
         int x = last;
@@ -341,95 +356,68 @@ __device__ __forceinline__ void worker_run(const FusedArgs& a, WorkerSlot& ws, i
             x = __ldg(&a.link[x].x);
         }
     }
-    uint4* A = reinterpret_cast<uint4*>(ws.ptr);
-    const Divider<DT> dv(L + 1);
-    const int nfull = nvec >> 5;
+    uint4* A = reinterpret_cast<uint4*>(ws.ptr[0]);
+    const uint4* B = reinterpret_cast<const uint4*>(ws.ptr[1]);
     int walk = anchor;
-    bool arrived = false;
 #pragma unroll 1
     for (int m = L - 1; m >= 0; --m) {                      // m = L - 1: first member behind the anchor ... m = 0: the last
         int idx;
         if (L <= 32) idx = __shfl_sync(FULL, mine, m);
         else { walk = __ldg(&a.link[walk].y); idx = walk; }
-        const uint4* mr = reinterpret_cast<const uint4*>(a.hidden + (int64_t)idx * row_bytes);
-        const bool fin = m == 0;
-        int v = 0;
-#pragma unroll 1
-        for (; v + 7 <= nfull; v += 7) {                    // seven vectors per lane in flight (7-KB rows: two rounds)
-            uint4 x[7];
-#pragma unroll
-            for (int q = 0; q < 7; ++q) x[q] = ld_cg16(mr + (v + q) * 32 + lane);
-            if (!arrived) { mbar_wait(ws.bar, ws.phase); ws.phase ^= 1u; arrived = true; }
-#pragma unroll
-            for (int q = 0; q < 7; ++q) {
-                uint4 t = Num<DT>::add_vec(A[(v + q) * 32 + lane], x[q]);        // T(acc + member)
-                if (fin) t = dv.vec_fast(t);
-                A[(v + q) * 32 + lane] = t;
+        __syncwarp();                                       // every lane has read slot B
+        if (lane == 0) {
+            if (m == L - 1) {
+                mbar_expect_tx(ws.bar[0], (uint32_t)row_bytes);
+                tma_load(ws.addr[0], a.hidden + (int64_t)anchor * row_bytes, (uint32_t)row_bytes, ws.bar[0]);
             }
+            mbar_expect_tx(ws.bar[1], (uint32_t)row_bytes);
+            tma_load(ws.addr[1], a.hidden + (int64_t)idx * row_bytes, (uint32_t)row_bytes, ws.bar[1]);
         }
-        if (!arrived) { mbar_wait(ws.bar, ws.phase); ws.phase ^= 1u; arrived = true; }
-        for (int i = v * 32 + lane; i < nvec; i += 32) {    // what is left of the row
-            uint4 t = Num<DT>::add_vec(A[i], ld_cg16(mr + i));
-            if (fin) t = dv.vec_fast(t);
-            A[i] = t;
+        if (m == L - 1) { mbar_wait(ws.bar[0], ws.phase[0]); ws.phase[0] ^= 1u; }
+        mbar_wait(ws.bar[1], ws.phase[1]);
+        ws.phase[1] ^= 1u;
+        if (m > 0) {
+#pragma unroll 2
+            for (int v = lane; v < nvec; v += 32) A[v] = Num<DT>::add_vec(A[v], B[v]);       // T(acc + member)
+        } else {
+            const Divider<DT> dv(L + 1);
+#pragma unroll 2
+            for (int v = lane; v < nvec; v += 32) A[v] = dv.vec_fast(Num<DT>::add_vec(A[v], B[v]));
         }
     }
     fence_async_smem();                                     // the sums were written through the generic proxy
     __syncwarp();
     if (lane == 0) {
-        tma_store(a.out + (int64_t)d_a * row_bytes, ws.addr, (uint32_t)row_bytes);
+        tma_store(a.out + (int64_t)d_a * row_bytes, ws.addr[0], (uint32_t)row_bytes);
         tma_commit();
-        ws.storing = true;
     }
+    ws.state[0] = 2;
+    ws.next = 1;
 }
 
-// The aux rows of a tile's kept rows (row tile * W + w -> destination d_of[w], -1: none): one 16- or 8-byte piece per lane and
-// entry; the loads of up to FU_AUX_BATCH (row, entry) pairs are in flight before the first store.
-constexpr int FU_AUX_BATCH = 8;
-__device__ __forceinline__ void worker_aux_tile(const FusedArgs& a, const AuxPack& aux, int tile, int W, int d_mine, int lane) {
+// the aux rows of sequence row r -> destination row d: one 16- or 8-byte piece per lane and entry, all loads first
+__device__ __forceinline__ void worker_aux(const FusedArgs& a, const AuxPack& aux, int r, int d, int lane) {
     const AuxFlat& f = a.auxf;
-    if (f.n < 0) {
-#pragma unroll 1
-        for (int w = 0; w < W; ++w) {
-            const int d = __shfl_sync(FULL, d_mine, w);
-            if (d >= 0) gather_aux_rows(aux, tile * W + w, d, lane);
-        }
-        return;
-    }
-    const int n_pairs = W * f.n;                            // pair k = (row k / n, entry k % n)
-#pragma unroll 1
-    for (int k0 = 0; k0 < n_pairs; k0 += FU_AUX_BATCH) {
-        uint4 v[FU_AUX_BATCH];
+    if (f.n < 0) { gather_aux_rows(aux, r, d, lane); return; }
+    uint4 v[8];
 #pragma unroll
-        for (int i = 0; i < FU_AUX_BATCH; ++i) {
-            v[i] = make_uint4(0, 0, 0, 0);
-            const int k = k0 + i;
-            if (k < n_pairs) {
-                const int w = k / f.n, e = k - w * f.n;
-                const int d = __shfl_sync(FULL, d_mine, w);
-                if (d >= 0) {
-                    const int rb = f.row_bytes[e];
-                    const char* src = f.src[e] + (int64_t)(tile * W + w) * rb;
-                    if (f.piece[e] == 8) { if (lane * 8 < rb) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(src) + lane); v[i].x = t.x; v[i].y = t.y; } }
-                    else if (lane * 16 < rb) v[i] = __ldg(reinterpret_cast<const uint4*>(src) + lane);
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < FU_AUX_BATCH; ++i) {
-            const int k = k0 + i;
-            if (k < n_pairs) {
-                const int w = k / f.n, e = k - w * f.n;
-                const int d = __shfl_sync(FULL, d_mine, w);
-                if (d >= 0) {
-                    const int rb = f.row_bytes[e];
-                    char* o = f.dst[e] + (int64_t)d * rb;
-                    if (f.piece[e] == 8) { if (lane * 8 < rb) reinterpret_cast<uint2*>(o)[lane] = make_uint2(v[i].x, v[i].y); }
-                    else if (lane * 16 < rb) reinterpret_cast<uint4*>(o)[lane] = v[i];
-                }
-            }
+    for (int e = 0; e < 8; ++e) {
+        v[e] = make_uint4(0, 0, 0, 0);
+        if (e < f.n) {
+            const int rb = f.row_bytes[e];
+            const char* s = f.src[e] + (int64_t)r * rb;
+            if (f.piece[e] == 8) { if (lane * 8 < rb) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(s) + lane); v[e].x = t.x; v[e].y = t.y; } }
+            else if (lane * 16 < rb) v[e] = __ldg(reinterpret_cast<const uint4*>(s) + lane);
         }
     }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        if (e < f.n) {
+            const int rb = f.row_bytes[e];
+            char* o = f.dst[e] + (int64_t)d * rb;
+            if (f.piece[e] == 8) { if (lane * 8 < rb) reinterpret_cast<uint2*>(o)[lane] = make_uint2(v[e].x, v[e].y); }
+            else if (lane * 16 < rb) reinterpret_cast<uint4*>(o)[lane] = v[e];
+        }
 }
 
 // The runs that end in one tile, L2 -> destination, with the aux rows of its kept rows and the links of the next call.
@@ -439,12 +427,11 @@ __device__ __forceinline__ void worker_aux_tile(const FusedArgs& a, const AuxPac
 //   merged away at the end of its chain: it ends its own run -> that run goes out
 // Every flag the walks read belongs to an earlier row than the tile's last: known since the tile's look-back resolved.
 template <int DT>
-__device__ __forceinline__ void run_tile_item(const FusedArgs& a, const AuxPack& aux, WorkerSlot& ws, int W, unsigned long long item,
+__device__ __forceinline__ void run_tile_item(const FusedArgs& a, const AuxPack& aux, WorkerSlots& ws, int W, unsigned long long item,
                                               int lane, int* err) {
     const int tile = (int)((item >> 38) & 0xffffffull), excl = (int)((item >> 8) & 0x3fffffffull);
     const unsigned kept = (unsigned)(item & 0xffull);
     const int r = tile * W + lane;
-    if (lane == 0) FU_STAMP(tile, 12);
     int run_last = -1, run_anchor = -1, run_L = 0, run_dst = -1;    // the run this lane's row ends
     int self_dst = -1, d_r = -1;
     if (lane < W && r < a.S) {
@@ -483,29 +470,24 @@ __device__ __forceinline__ void run_tile_item(const FusedArgs& a, const AuxPack&
         }
     }
     __syncwarp();
-    if (lane == 0) FU_STAMP(tile, 3);
     const int row_bytes = a.row_bytes;
-    // the aux rows' loads first (they travel while the rows are copied), then the plain copies, then the runs
-#pragma unroll 1
-    for (int w = 0; w < W; ++w) {
-        const int anchor = __shfl_sync(FULL, run_anchor, w), L = __shfl_sync(FULL, run_L, w), d_a = __shfl_sync(FULL, run_dst, w);
-        const int sd = __shfl_sync(FULL, self_dst, w);
-        if (anchor >= 0 && L == 0) worker_copy(ws, a.hidden + (int64_t)anchor * row_bytes, a.out + (int64_t)d_a * row_bytes, row_bytes, lane);
-        if (sd >= 0) worker_copy(ws, a.hidden + (int64_t)(tile * W + w) * row_bytes, a.out + (int64_t)sd * row_bytes, row_bytes, lane);
-    }
-    if (aux.n) worker_aux_tile(a, aux, tile, W, d_r, lane);
 #pragma unroll 1
     for (int w = 0; w < W; ++w) {
         const int anchor = __shfl_sync(FULL, run_anchor, w), last = __shfl_sync(FULL, run_last, w);
         const int L = __shfl_sync(FULL, run_L, w), d_a = __shfl_sync(FULL, run_dst, w);
-        if (anchor >= 0 && L > 0) worker_run<DT>(a, ws, anchor, last, L, d_a, lane);
+        const int sd = __shfl_sync(FULL, self_dst, w), d_w = __shfl_sync(FULL, d_r, w);
+        if (anchor >= 0) {
+            if (L == 0) worker_copy(ws, a.hidden + (int64_t)anchor * row_bytes, a.out + (int64_t)d_a * row_bytes, row_bytes, lane);
+            else worker_run<DT>(a, ws, anchor, last, L, d_a, lane);
+        }
+        if (sd >= 0) worker_copy(ws, a.hidden + (int64_t)(tile * W + w) * row_bytes, a.out + (int64_t)sd * row_bytes, row_bytes, lane);
+        if (d_w >= 0 && aux.n) worker_aux(a, aux, tile * W + w, d_w, lane);
     }
-    if (lane == 0) FU_STAMP(tile, 15);
 }
 
-// CTA = two front warpgroups (warps 0 .. 7: the W tile warps — W rows per tile, two shared-memory slots each — and the
-// dispatcher) + two back warpgroups (warp 8: scan, warps 9 .. 14: workers, one slot each).  The warpgroups trade registers
-// (setmaxnreg): the front needs few.
+// CTA = two front warpgroups (warps 0 .. 7: the W tile warps, W rows per tile, two shared-memory slots each) + one back
+// warpgroup (warp 8: scan, warps 9 .. 11: workers).  The warpgroups trade registers (setmaxnreg): the front needs few, the
+// back keeps whole rows in flight.
 template <int DT>
 __global__ void __launch_bounds__((FU_WARPS + FU_WORKERS) * 32, 2)
 k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPack aux) {
@@ -538,17 +520,21 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
     if (wid > FU_WARPS) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(FU_REGS_BACK));
         // ---- workers: copies nobody waits for
+        WorkerSlots ws;
         const int me = wid - FU_WARPS - 1;
-        if (me >= FU_WSLOTS) return;                        // the spare warp of the back warpgroups
-        WorkerSlot ws;
-        ws.ptr = wslots + (size_t)me * a.slot_bytes;
-        ws.addr = smem_u32(ws.ptr);
-        ws.bar = smem_u32(&sh->wbars[me]);
-        ws.phase = 0;
-        ws.storing = false;
+        for (int s = 0; s < 2; ++s) {
+            ws.ptr[s] = wslots + (size_t)(2 * me + s) * a.slot_bytes;
+            ws.addr[s] = smem_u32(ws.ptr[s]);
+            ws.bar[s] = smem_u32(&sh->wbars[2 * me + s]);
+            ws.phase[s] = 0;
+            ws.state[s] = 0;
+            ws.dst[s] = nullptr;
+        }
+        ws.next = 0;
         unsigned long long item;
         while (queue_pop(&sh->q, lane, &item)) run_tile_item<DT>(a, aux, ws, W, item, lane, &err);
-        slot_free(ws, lane);
+        slot_free(ws, 0, a.row_bytes, lane);
+        slot_free(ws, 1, a.row_bytes, lane);
         if (lane == 0) tma_wait_all();
         if (err && lane == 0) a.status[FF_ST_INTERNAL] = 1;
         return;
@@ -563,7 +549,6 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
         constexpr int PEND = 8;
         unsigned long long pend[PEND];                      // posted, not yet resolved: (tile << 16) | (merged << 8) | kept
         int n_pend = 0, p_head = 0;
-        bool head_published = false;
         unsigned head = 0;
         long long cur = -1;                                 // tile being posted
         bool exiting = false;
@@ -611,65 +596,62 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
                 progress = true;
             }
             if (n_pend && e != 0u) {
-                // RESOLVE: publish the destinations once; hand the tile to the workers when their ring has room (a full ring
-                // must not keep this warp from posting the tiles behind it)
+                // RESOLVE
                 const unsigned long long pe = pend[p_head];
                 const int tile = ptile, excl = (int)e - 1, r = tile * W + lane;
                 const unsigned kept = (unsigned)pe & 0xffu, merged = (unsigned)(pe >> 8) & 0xffu;
                 const int total = __popc(kept);
-                if (!head_published) {
-                    if (lane == 0) FU_STAMP(tile, 7);
-                    if (kept >> lane & 1u) {
-                        const int d = excl + __popc(kept & ((1u << lane) - 1u));
-                        st_relaxed32(a.fdst + r, (unsigned)d + 1u);
-                        a.dst[r] = d;
-                    } else if (merged >> lane & 1u) {
-                        a.dst[r] = -1;
-                    }
-                    if (lane == 0 && tile == a.ntiles - 1) {
-                        // the sequence is done: sizes, the speculated branch, the counters of the next call (main.py:112-120)
-                        const long long s_keep = excl + total, n_merged = a.S - s_keep;
-                        const long long N = a.counters[C_N], n_vis = a.counters[C_NVIS];
-                        int ec = 0;
-                        if (n_vis == 0) ec = 1;             // the reference divides by zero here (main.py:114)
-                        else if (!((double)n_merged / (double)n_vis < a.bound)) ec = 3;   // top-k branch: the host redoes the call
-                        a.counters[C_COUNT] = n_merged;
-                        a.counters[C_NNEXT] = N - n_merged;
-                        a.counters[C_SKEEP] = s_keep;
-                        a.counters[C_BRANCH] = 0;
-                        a.counters[C_K] = 0;
-                        a.counters[C_NMERGED] = n_merged;
-                        a.counters_next[C_N] = N - n_merged;
-                        a.counters_next[C_NVIS] = n_vis - n_merged;
-                        a.counters_next[C_COUNT] = 0;
-                        a.counters_next[C_TICKET] = 0;
-                        a.counters_next[C_TICKET2] = 0;
-                        a.status[FF_ST_SEQ_KEEP] = s_keep;
-                        a.status[FF_ST_COUNT] = n_merged;
-                        a.status[FF_ST_NVIS] = n_vis;
-                        a.status[FF_ST_NCHAIN] = N;
-                        a.status[FF_ST_BRANCH] = 0;
-                        a.status[FF_ST_TOPK] = 0;
-                        a.status[FF_ST_ERROR] = ec;
-                        a.status[FF_ST_NMERGED] = n_merged;
-                        a.status[FF_ST_FUSED] = 1;
-                    }
-                    head_published = true;
-                    progress = true;
+                if (lane == 0) FU_STAMP(tile, 7);
+                if (kept >> lane & 1u) {
+                    const int d = excl + __popc(kept & ((1u << lane) - 1u));
+                    st_relaxed32(a.fdst + r, (unsigned)d + 1u);
+                    a.dst[r] = d;
+                } else if (merged >> lane & 1u) {
+                    a.dst[r] = -1;
                 }
-                int ok = 1;
                 if (kept | merged) {
                     const unsigned long long it = ((unsigned long long)tile << 38) | ((unsigned long long)excl << 8) | kept;
-                    if (lane == 0) ok = queue_push(&sh->q, it) ? 1 : 0;
-                    ok = __shfl_sync(FULL, ok, 0);
+                    if (lane == 0) {                        // ring full: the workers are behind, and so is everything upstream
+                        int spins = 0;
+                        while (!queue_push(&sh->q, it)) {
+                            if (++spins > FU_SPIN_LIMIT) { err = 1; break; }
+                            __nanosleep(200);
+                        }
+                    }
                 }
-                if (ok) {
-                    if (lane == 0) FU_STAMP(tile, 8);
-                    p_head = (p_head + 1) % PEND;
-                    --n_pend;
-                    head_published = false;
-                    progress = true;
+                if (lane == 0 && tile == a.ntiles - 1) {
+                    // the sequence is done: sizes, the speculated branch, the counters of the next call (main.py:112-120)
+                    const long long s_keep = excl + total, n_merged = a.S - s_keep;
+                    const long long N = a.counters[C_N], n_vis = a.counters[C_NVIS];
+                    int ec = 0;
+                    if (n_vis == 0) ec = 1;                 // the reference divides by zero here (main.py:114)
+                    else if (!((double)n_merged / (double)n_vis < a.bound)) ec = 3;   // top-k branch: the host redoes the call
+                    a.counters[C_COUNT] = n_merged;
+                    a.counters[C_NNEXT] = N - n_merged;
+                    a.counters[C_SKEEP] = s_keep;
+                    a.counters[C_BRANCH] = 0;
+                    a.counters[C_K] = 0;
+                    a.counters[C_NMERGED] = n_merged;
+                    a.counters_next[C_N] = N - n_merged;
+                    a.counters_next[C_NVIS] = n_vis - n_merged;
+                    a.counters_next[C_COUNT] = 0;
+                    a.counters_next[C_TICKET] = 0;
+                    a.counters_next[C_TICKET2] = 0;
+                    a.status[FF_ST_SEQ_KEEP] = s_keep;
+                    a.status[FF_ST_COUNT] = n_merged;
+                    a.status[FF_ST_NVIS] = n_vis;
+                    a.status[FF_ST_NCHAIN] = N;
+                    a.status[FF_ST_BRANCH] = 0;
+                    a.status[FF_ST_TOPK] = 0;
+                    a.status[FF_ST_ERROR] = ec;
+                    a.status[FF_ST_NMERGED] = n_merged;
+                    a.status[FF_ST_FUSED] = 1;
                 }
+                __syncwarp();
+                if (lane == 0) FU_STAMP(tile, 8);
+                p_head = (p_head + 1) % PEND;
+                --n_pend;
+                progress = true;
             }
             if (exiting && cur < 0 && n_pend == 0) break;
             if (progress) idle = 0;

@@ -140,10 +140,10 @@ class FrameFusion(nn.Module):
         self._dev = {}                  # torch.device -> _DeviceState
         self._links_for = None          # (patch_type tensor, its _version, device) the workspace links describe
         self._have_order = False        # the workspace holds the compact by-patch order (the multi-kernel path needs it)
-        # merge-stage kernel choice: True = the read-once kernel (one launch, one HBM read of hidden_states; it falls
-        # back by itself for the top-k branch and for shapes it does not take), False = always the multi-kernel path
-        # (similarity -> scan -> gather/merge)
-        self.use_fused = True
+        # merge-stage kernel choice: False = multi-kernel path (similarity -> scan -> gather/merge: 159 us at C2, the faster
+        # one), True = the read-once kernel (one launch, one HBM read of hidden_states: 216 us at C2; it falls back by itself
+        # for the top-k branch and for shapes it does not take).  DESIGN.md section 5 has the measurements.
+        self.use_fused = False
         self.debug_trace = False        # tests: keep what flowed between the stages of the last call
         self.last_trace = None
         self.kernel_events = None       # bench: a list collects (name, start, end) CUDA events around ff_* launches
