@@ -733,13 +733,14 @@ int ff_importance(ff_ctx* ctx, const void* q, const void* k, int dtype, int64_t 
     if (Hq < 1 || Hk < 1 || Hq % Hk || S < 1 || D < 1 || num < 1 || num > S) return fail(FF_E_BADARG, "bad attention shape");
     if (scratch_bytes < Hq * num * S * 4) return fail(FF_E_WORKSPACE, "scratch needs %lld bytes", (long long)(Hq * num * S * 4));
     const int64_t group = Hq / Hk;
-    const size_t smem = (size_t)group * num * D * 4;
+    const size_t smem = ((size_t)group * num * D + IMP_LANES * IMP_PAD) * 4;
     if (smem > 96 * 1024) return fail(FF_E_UNSUPPORTED, "group*num*head_dim = %lld floats do not fit shared memory", (long long)(group * num * D));
     cudaStream_t st = (cudaStream_t)stream;
     FF_DEVICE(ctx);
     const int64_t eb = dtype == FF_F32 ? 4 : 2;
-    const bool vec = (D * eb) % 16 == 0 && ((uintptr_t)k & 15) == 0 && (k_hs * eb) % 16 == 0 && (k_ss * eb) % 16 == 0;
-    dim3 grid((unsigned)((S + IMP_THREADS - 1) / IMP_THREADS), (unsigned)Hk);
+    // the fast path: K rows of 16-byte vectors, four lanes per row with a whole number of vectors each
+    const bool vec = (D * eb) % (16 * IMP_LANES) == 0 && ((uintptr_t)k & 15) == 0 && (k_hs * eb) % 16 == 0 && (k_ss * eb) % 16 == 0;
+    dim3 grid(vec ? (unsigned)((S + IMP_KEYS - 1) / IMP_KEYS) : (unsigned)((S + IMP_THREADS - 1) / IMP_THREADS), (unsigned)Hk);
     int rc = dispatch_dtype(dtype, [&](auto dt) {
         constexpr int DT = decltype(dt)::value;
         if (vec) {

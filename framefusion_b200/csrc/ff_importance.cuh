@@ -11,20 +11,87 @@
 
 namespace ff {
 
-constexpr int IMP_THREADS = 128;
+constexpr int IMP_THREADS = 256;
+constexpr int IMP_LANES = 4;                              // lanes that share one key row
+constexpr int IMP_KEYS = IMP_THREADS / IMP_LANES;         // key rows per block
+constexpr int IMP_PAD = 8;                                // floats between the lanes' slices of q in shared memory (bank spread)
 
+// 16-byte vector of T -> float2 pairs (even element, odd element)
+template <int DT>
+__device__ __forceinline__ void unpack_pairs(const uint4& v, float2* p) {
+    float f[Num<DT>::EPV];
+    Num<DT>::unpack(v, f);
+#pragma unroll
+    for (int e = 0; e < Num<DT>::EPV / 2; ++e) p[e] = make_float2(f[2 * e], f[2 * e + 1]);
+}
+
+// VEC (rows of 16-byte vectors, head_dim a multiple of IMP_LANES vectors): four lanes share a key row — each reads a
+// contiguous quarter of it (a warp reads eight whole rows: 2 KB in one piece) and carries the partial dot products of every
+// (query head, query row) pair of the GQA group over its quarter, as packed float32 pairs; two shuffles add the quarters up.
+// One thread per key with the whole row (the first version) was a chain of ~3 000 dependent instructions at half a wave.
 template <int DT, bool VEC>
 __global__ void __launch_bounds__(IMP_THREADS)
 k_importance_logits(const void* __restrict__ q, const void* __restrict__ k, int n_q_heads, int n_kv_heads, int S, int D,
                     int num, int64_t q_hs, int64_t q_ss, int64_t k_hs, int64_t k_ss, int is_causal, float scale,
                     float* __restrict__ logits /* [Hq, num, S] float32 holding T values */) {
     pdl_enter();
-    extern __shared__ __align__(16) float s_q[];          // [group * num][D]
+    extern __shared__ __align__(16) float s_q[];
     typedef typename Num<DT>::store_t st;
     const int hk = blockIdx.y;
     const int group = n_q_heads / n_kv_heads;
     const int L = num;
-    for (int idx = threadIdx.x; idx < group * L * D; idx += blockDim.x) {
+    const int GL = group * L;
+    if (VEC) {
+        // q in shared memory as [lane slice][pair][D / 4] with IMP_PAD floats between the slices
+        const int DQ = D / IMP_LANES, slice = GL * DQ + IMP_PAD;
+        for (int idx = threadIdx.x; idx < GL * D; idx += blockDim.x) {
+            const int d = idx % D, gr = idx / D;
+            const int r = gr % L, g = gr / L;
+            const int h = hk * group + g;
+            s_q[(d / DQ) * slice + gr * DQ + (d % DQ)] = Num<DT>::load(q, (int64_t)h * q_hs + (int64_t)(S - L + r) * q_ss + d);
+        }
+        __syncthreads();
+        const int sub = threadIdx.x & (IMP_LANES - 1);
+        const int s = blockIdx.x * IMP_KEYS + (threadIdx.x >> 2);
+        const int sc = min(s, S - 1);                       // every lane of a warp stays for the shuffles
+        const char* kq = (const char*)((const st*)k + (int64_t)hk * k_hs + (int64_t)sc * k_ss) + (int64_t)sub * DQ * sizeof(st);
+        const float* qs = s_q + sub * slice;
+        const int nv = DQ / Num<DT>::EPV;                   // 16-byte vectors of this lane's quarter
+        for (int gb = 0; gb < GL; gb += 8) {
+            float2 acc[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) acc[g] = make_float2(0.f, 0.f);
+            for (int v = 0; v < nv; ++v) {
+                float2 kp[Num<DT>::EPV / 2];
+                unpack_pairs<DT>(ldg16(kq + (int64_t)v * 16), kp);
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    if (gb + g < GL) {
+                        const float2* qv = reinterpret_cast<const float2*>(qs + (gb + g) * DQ + v * Num<DT>::EPV);
+#pragma unroll
+                        for (int e = 0; e < Num<DT>::EPV / 2; ++e) acc[g] = __ffma2_rn(kp[e], qv[e], acc[g]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                float x = acc[g].x + acc[g].y;
+                x += __shfl_xor_sync(FULL, x, 1);
+                x += __shfl_xor_sync(FULL, x, 2);
+                // lane `sub` of the four writes the pairs gb + g == sub (mod 4)
+                if (gb + g < GL && s < S && ((gb + g) & (IMP_LANES - 1)) == sub) {
+                    const int r = (gb + g) % L, h = hk * group + (gb + g) / L;
+                    x = Num<DT>::rnd(x);                    // matmul output in T
+                    x = Num<DT>::rnd(x * scale);            // * scale_factor
+                    const float bias = (is_causal && s > S - L + r) ? -INFINITY : 0.f;
+                    x = Num<DT>::rnd(x + bias);             // += attn_bias
+                    logits[((int64_t)h * L + r) * S + s] = x;
+                }
+            }
+        }
+        return;
+    }
+    for (int idx = threadIdx.x; idx < GL * D; idx += blockDim.x) {
         const int d = idx % D, r = (idx / D) % L, g = idx / (D * L);
         const int h = hk * group + g;
         s_q[idx] = Num<DT>::load(q, (int64_t)h * q_hs + (int64_t)(S - L + r) * q_ss + d);
@@ -33,45 +100,6 @@ k_importance_logits(const void* __restrict__ q, const void* __restrict__ k, int 
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const st* krow = (const st*)k + (int64_t)hk * k_hs + (int64_t)s * k_ss;
-    const int GL = group * L;
-    if (VEC) {
-        // eight (query head, query row) dot products advance together over one pass of the K row (16-byte loads); more
-        // pairs than eight (Qwen2-VL: 7 heads x 4 query rows per KV head) take further passes, which the L1 serves
-        for (int gb = 0; gb < GL; gb += 8) {
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int v = 0; v < D / Num<DT>::EPV; ++v) {
-                float kf[Num<DT>::EPV];
-                Num<DT>::unpack(ldg16((const char*)krow + (int64_t)v * 16), kf);
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    if (gb + g < GL) {
-                        // 16-byte shared-memory reads: D is a multiple of the vector length on this path
-                        const float4* qv = reinterpret_cast<const float4*>(s_q + (gb + g) * D + v * Num<DT>::EPV);
-#pragma unroll
-                        for (int f = 0; f < Num<DT>::EPV / 4; ++f) {
-                            const float4 qq = qv[f];
-                            acc[g] = fmaf(kf[4 * f + 0], qq.x, acc[g]);
-                            acc[g] = fmaf(kf[4 * f + 1], qq.y, acc[g]);
-                            acc[g] = fmaf(kf[4 * f + 2], qq.z, acc[g]);
-                            acc[g] = fmaf(kf[4 * f + 3], qq.w, acc[g]);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                if (gb + g < GL) {
-                    const int r = (gb + g) % L, h = hk * group + (gb + g) / L;
-                    float x = Num<DT>::rnd(acc[g]);            // matmul output in T
-                    x = Num<DT>::rnd(x * scale);               // * scale_factor
-                    const float bias = (is_causal && s > S - L + r) ? -INFINITY : 0.f;
-                    x = Num<DT>::rnd(x + bias);                // += attn_bias
-                    logits[((int64_t)h * L + r) * S + s] = x;
-                }
-            }
-        }
-        return;
-    }
     for (int gr = 0; gr < GL; ++gr) {                      // rows that are not 16-byte aligned: element by element
         const float* qv = s_q + gr * D;
         float acc = 0.f;
