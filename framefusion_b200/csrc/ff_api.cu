@@ -79,7 +79,7 @@ struct ff_ctx {
     int have_seq;        // (pred, succ) of every sequence row valid for `parity` (read-once kernel)
     int last_fused;      // the last merge call ran the read-once kernel: sim[] is indexed by sequence row
     int fused_clean[2];  // state words / tile descriptors of the bank are known to be zero
-    int fused_attr[3];   // dynamic shared memory the kernel of each dtype was last opted in for
+    int fused_attr[3];   // resident CTAs per SM of the read-once kernel of each dtype (0: not asked yet)
     int sm_count;
     int max_smem;        // opt-in dynamic shared memory per block
     int smem_per_sm, smem_reserved;   // shared memory of an SM / what the system keeps per resident block
@@ -119,9 +119,8 @@ struct Ws {
     float* sim;
     uint8_t* flag;
     int2* link[2];      // [cap] (pred, succ) of every sequence row (read-once kernel)
-    unsigned* fflag[2];              // [cap] its front flags
-    unsigned* fdst[2];               // [cap] its destination words
-    unsigned long long* desc[2];     // [1 + tiles] ticket + tile descriptors
+    unsigned* fflag[2];              // [cap / FU_WARPS + 1] its kept masks, one word per tile
+    unsigned long long* desc[2];     // ticket, round words, exclusive prefixes of the tiles
     int* dst[2];
     int* srcidx;
     int4* rec;          // [cap] per kept chain row in by-patch order: (source row, destination row, by-patch position, run length)
@@ -152,9 +151,8 @@ Ws carve(void* base_ptr, int64_t cap, int64_t n_ids) {
     w.barrier = (unsigned*)take(256);
     w.sel_hist = (int*)take(4 * 256 * 4);
     for (int b = 0; b < 2; ++b) {
-        w.fflag[b] = (unsigned*)take((size_t)cap * 4);
-        w.fdst[b] = (unsigned*)take((size_t)cap * 4);
-        w.desc[b] = (unsigned long long*)take(((size_t)cap + 2 * FU_ROUND + 16) * 8 + (size_t)cap / 16);   // ticket, per tile two u32, per round u32 + u64 (one row per tile at worst)
+        w.fflag[b] = (unsigned*)take(((size_t)cap / FU_WARPS + 4) * 4);
+        w.desc[b] = (unsigned long long*)take(((size_t)cap / (FU_WARPS * FU_ROUND_TILES) + 4) * 8 + ((size_t)cap / FU_WARPS + 4) * 4);   // ticket, u64 per round, u32 per tile
     }
     w.zero_begin = zero_begin;
     w.zero_bytes = (size_t)((p ? p + off : (char*)nullptr) - zero_begin);
@@ -352,61 +350,44 @@ int check_shape(int64_t S, int64_t H, int dtype) {
     return FF_OK;
 }
 
-// shared memory of one CTA of the read-once kernel besides the row slots: mbarriers, tile scratch, the worker queue
-constexpr int FU_SMEM_EXTRA = (int)sizeof(FusedShared);
-
-// rows per tile (= tile warps per CTA) of the read-once kernel: two CTAs per SM, two slots per warp; 0 = rows too long
-int fused_tile_rows(const ff_ctx* ctx, int64_t row_bytes) {
-    const int64_t slot = (row_bytes + 127) / 128 * 128;
-    const int64_t per_cta = ctx->smem_per_sm / 2 - ctx->smem_reserved;
-    int64_t w = ((per_cta - FU_SMEM_EXTRA) / slot - FU_WSLOTS) / 2;       // the workers' slots come first
-    if (w > FU_WARPS - 1) w = FU_WARPS - 1;             // one warp of the front warpgroups is the dispatcher
-    return w < 1 ? 0 : (int)w;
-}
-
-// rows the read-once kernel handles: 16-byte multiples, a threshold no chain head (sim = -2) can pass, shared memory
-// for at least two warps
+// rows the read-once kernel handles: 16-byte multiples and a threshold no chain head (sim = -2) can pass
 bool fused_shape_ok(const ff_ctx* ctx, const void* hidden, const void* out, int dtype, int64_t S, int64_t H, double thr) {
+    (void)ctx;
     const int64_t row_bytes = H * (dtype == FF_F32 ? 4 : 2);
     if (row_bytes % 16 != 0 || (((uintptr_t)hidden | (uintptr_t)out) & 15) != 0) return false;
-    if (S >= (1ll << 24)) return false;                    // tile numbers travel in 24 bits of a queue item
-    if (!(thr > -2.0)) return false;
-    return fused_tile_rows(ctx, row_bytes) > 0;
+    if (S >= (1ll << 30)) return false;
+    return thr > -2.0;
+}
+
+// S tiles run this many tiles ahead of the G tiles (ff_fused.cuh); FF_FUSED_LAG overrides the default for experiments
+int fused_lag() {
+    static int lag = -1;
+    if (lag < 0) {
+        const char* e = getenv("FF_FUSED_LAG");
+        lag = e ? atoi(e) : FU_LAG_TILES;
+        if (lag < FU_ROUND_TILES) lag = FU_ROUND_TILES;     // a G tile only waits for S tiles with a smaller ticket
+    }
+    return lag;
 }
 
 int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* out, int dtype, int64_t S, int64_t H,
                  double thr, double bound, const AuxPack& ap, cudaStream_t st) {
     const int nb = bank ^ 1;
     FusedArgs a;
-    a.trace = nullptr;
-#ifdef FF_FUSED_TRACE
-    // development build: stamps of the last launch are left in a device buffer and dumped to $FF_FUSED_TRACE_FILE
-    static long long* g_trace = nullptr;
-    static size_t g_trace_n = 0;
-    const size_t need = ((size_t)(S + 1) / 2 + 2) * FU_TRACE_SLOTS;
-    if (need > g_trace_n) { if (g_trace) cudaFree(g_trace); cudaMalloc((void**)&g_trace, need * 8); g_trace_n = need; }
-    cudaMemsetAsync(g_trace, 0, need * 8, st);
-    a.trace = g_trace;
-#endif
     a.hidden = (const char*)hidden;
     a.out = (char*)out;
     a.S = (int)S;
     a.row_bytes = (int)(H * (dtype == FF_F32 ? 4 : 2));
     a.nvec = a.row_bytes / 16;
-    a.slot_bytes = (a.row_bytes + 127) / 128 * 128;
-    a.tile_rows = fused_tile_rows(ctx, a.row_bytes);
-    a.ntiles = (int)((S + a.tile_rows - 1) / a.tile_rows);
-    a.nrounds = (a.ntiles + FU_ROUND - 1) / FU_ROUND;
-    a.ntiles_pad = a.nrounds * FU_ROUND;
-    a.desc_words = 1 + (a.nrounds + 1) + (2 * a.ntiles_pad + a.nrounds + 1) / 2;
+    a.ntiles = (int)((S + FU_WARPS - 1) / FU_WARPS);
+    a.nrounds = (a.ntiles + FU_ROUND_TILES - 1) / FU_ROUND_TILES;
+    a.lag = fused_lag() < a.ntiles ? fused_lag() : a.ntiles;
+    a.desc_words = 1 + a.nrounds + (a.ntiles + 1) / 2;
     a.link = w.link[bank];
     a.link_next = w.link[nb];
-    a.fflag = w.fflag[bank];
-    a.fdst = w.fdst[bank];
     a.desc = w.desc[bank];
-    a.fflag_clr = w.fflag[nb];
-    a.fdst_clr = w.fdst[nb];
     a.desc_clr = w.desc[nb];
+    a.tile_mask = w.fflag[bank];
     a.sim_seq = w.sim;
     a.dst = w.dst[bank];
     a.counters = w.counters[bank];
@@ -429,42 +410,22 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
             a.auxf.dst[e] = (char*)x.dst + pl * x.dst_plane_stride;
         }
     }
-    if (!ctx->fused_clean[bank]) {
-        FF_CUDA(cudaMemsetAsync(w.fflag[bank], 0, (size_t)S * 4, st));
-        FF_CUDA(cudaMemsetAsync(w.fdst[bank], 0, (size_t)S * 4, st));
-        FF_CUDA(cudaMemsetAsync(w.desc[bank], 0, (size_t)a.desc_words * 8, st));
-    }
+    if (!ctx->fused_clean[bank]) FF_CUDA(cudaMemsetAsync(w.desc[bank], 0, (size_t)a.desc_words * 8, st));
     ctx->fused_clean[bank] = 0;
     ctx->fused_clean[nb] = 1;                              // the kernel clears the other bank on its way out
     ctx->h_status[FF_ST_INTERNAL] = 0;
-    const int smem = (2 * a.tile_rows + FU_WSLOTS) * a.slot_bytes + FU_SMEM_EXTRA;
-    const int threads = (FU_WARPS + FU_WORKERS) * 32;
+    const int threads = FU_WARPS * 32;
     return dispatch_dtype(dtype, [&](auto dt) {
         constexpr int DT = decltype(dt)::value;
-        if (ctx->fused_attr[DT] < smem) {
-            FF_CUDA(cudaFuncSetAttribute(k_fused_merge<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            ctx->fused_attr[DT] = smem;
+        if (ctx->fused_attr[DT] == 0) {
+            int per_sm = 0;
+            FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_merge<DT>, threads, 0));
+            if (per_sm < 1) return fail(FF_E_UNSUPPORTED, "the read-once kernel does not fit an SM");
+            ctx->fused_attr[DT] = per_sm;
         }
-        cudaFuncAttributes fa;
-        FF_CUDA(cudaFuncGetAttributes(&fa, k_fused_merge<DT>));
-        if (fa.numRegs != FU_REGS_LAUNCH)                  // the warpgroups' register trade is computed for this allocation
-            return fail(FF_E_UNSUPPORTED, "k_fused_merge was built with %d registers per thread, the register trade expects %d", fa.numRegs, FU_REGS_LAUNCH);
-        int per_sm = 0;
-        FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_merge<DT>, threads, smem));
-        if (per_sm < 1) return fail(FF_E_UNSUPPORTED, "the read-once kernel does not fit an SM (%d bytes of shared memory)", smem);
-        int grid = per_sm * ctx->sm_count;
-        if (grid > a.ntiles) grid = a.ntiles;
-        FF_LAUNCH("k_fused_merge", k_fused_merge<DT>, grid, threads, smem, st, a, ap);
-#ifdef FF_FUSED_TRACE
-        if (const char* path = getenv("FF_FUSED_TRACE_FILE")) {
-            cudaStreamSynchronize(st);
-            const size_t n = (size_t)a.ntiles * FU_TRACE_SLOTS;
-            long long* h = (long long*)malloc(n * 8);
-            cudaMemcpy(h, a.trace, n * 8, cudaMemcpyDeviceToHost);
-            if (FILE* f = fopen(path, "wb")) { fwrite(h, 8, n, f); fclose(f); }
-            free(h);
-        }
-#endif
+        int grid = ctx->fused_attr[DT] * ctx->sm_count;
+        if (grid > 2 * a.ntiles) grid = 2 * a.ntiles;
+        FF_LAUNCH("k_fused_merge", k_fused_merge<DT>, grid, threads, 0, st, a, ap);
         return (int)FF_OK;
     });
 }
