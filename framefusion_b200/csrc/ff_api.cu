@@ -80,6 +80,8 @@ struct ff_ctx {
     int last_fused;      // the last merge call ran the read-once kernel: sim[] is indexed by sequence row
     int fused_clean[2];  // state words / tile descriptors of the bank are known to be zero
     int fused_attr[3];   // resident CTAs per SM of the read-once kernel of each dtype (0: not asked yet)
+    int fused_smem[3];   // dynamic shared memory the kernel of each dtype is opted in for
+    int fused_smem_last[3];   // ... and the size fused_attr was computed for
     int sm_count;
     int max_smem;        // opt-in dynamic shared memory per block
     int smem_per_sm, smem_reserved;   // shared memory of an SM / what the system keeps per resident block
@@ -119,8 +121,7 @@ struct Ws {
     float* sim;
     uint8_t* flag;
     int2* link[2];      // [cap] (pred, succ) of every sequence row (read-once kernel)
-    unsigned* fflag[2];              // [cap / FU_WARPS + 1] its kept masks, one word per tile
-    unsigned long long* desc[2];     // ticket, round words, exclusive prefixes of the tiles
+    unsigned long long* desc[2];     // ticket, band words, exclusive prefixes of the bands, kept masks
     int* dst[2];
     int* srcidx;
     int4* rec;          // [cap] per kept chain row in by-patch order: (source row, destination row, by-patch position, run length)
@@ -151,8 +152,7 @@ Ws carve(void* base_ptr, int64_t cap, int64_t n_ids) {
     w.barrier = (unsigned*)take(256);
     w.sel_hist = (int*)take(4 * 256 * 4);
     for (int b = 0; b < 2; ++b) {
-        w.fflag[b] = (unsigned*)take(((size_t)cap / FU_WARPS + 4) * 4);
-        w.desc[b] = (unsigned long long*)take(((size_t)cap / (FU_WARPS * FU_ROUND_TILES) + 4) * 8 + ((size_t)cap / FU_WARPS + 4) * 4);   // ticket, u64 per round, u32 per tile
+        w.desc[b] = (unsigned long long*)take(16 + ((size_t)cap / 32 + 2) * 12 + ((size_t)cap / 32 + 2) * 4 + 16);   // ticket, per band u64 + u32 (a band is 32 rows at least), a mask bit per row
     }
     w.zero_begin = zero_begin;
     w.zero_bytes = (size_t)((p ? p + off : (char*)nullptr) - zero_begin);
@@ -350,24 +350,36 @@ int check_shape(int64_t S, int64_t H, int dtype) {
     return FF_OK;
 }
 
-// rows the read-once kernel handles: 16-byte multiples and a threshold no chain head (sim = -2) can pass
-bool fused_shape_ok(const ff_ctx* ctx, const void* hidden, const void* out, int dtype, int64_t S, int64_t H, double thr) {
-    (void)ctx;
-    const int64_t row_bytes = H * (dtype == FF_F32 ? 4 : 2);
-    if (row_bytes % 16 != 0 || (((uintptr_t)hidden | (uintptr_t)out) & 15) != 0) return false;
-    if (S >= (1ll << 30)) return false;
-    return thr > -2.0;
+// FF_FUSED_BAND / FF_FUSED_LAG override the band and the lag of the read-once kernel (ff_fused.cuh) for experiments
+int fused_env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
-
-// S tiles run this many tiles ahead of the G tiles (ff_fused.cuh); FF_FUSED_LAG overrides the default for experiments
+int fused_band() {
+    static int band = -1;
+    if (band < 0) {
+        band = fused_env("FF_FUSED_BAND", FU_BAND) / 32 * 32;
+        if (band < 32) band = 32;
+    }
+    return band;
+}
 int fused_lag() {
     static int lag = -1;
     if (lag < 0) {
-        const char* e = getenv("FF_FUSED_LAG");
-        lag = e ? atoi(e) : FU_LAG_TILES;
-        if (lag < FU_ROUND_TILES) lag = FU_ROUND_TILES;     // a G tile only waits for S tiles with a smaller ticket
+        lag = fused_env("FF_FUSED_LAG", FU_LAG) / 32 * 32;
+        if (lag < fused_band()) lag = fused_band();        // a G unit only waits for S units with a smaller ticket
     }
     return lag;
+}
+
+// rows the read-once kernel handles: 16-byte multiples, a threshold no chain head (sim = -2) can pass, one row per warp
+// in shared memory
+bool fused_shape_ok(const ff_ctx* ctx, const void* hidden, const void* out, int dtype, int64_t S, int64_t H, double thr) {
+    const int64_t row_bytes = H * (dtype == FF_F32 ? 4 : 2);
+    if (row_bytes % 16 != 0 || (((uintptr_t)hidden | (uintptr_t)out) & 15) != 0) return false;
+    if (S >= (1ll << 30) - 2 * (int64_t)fused_lag()) return false;
+    if (FU_WARPS * row_bytes > ctx->max_smem) return false;
+    return thr > -2.0;
 }
 
 int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* out, int dtype, int64_t S, int64_t H,
@@ -379,15 +391,17 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
     a.S = (int)S;
     a.row_bytes = (int)(H * (dtype == FF_F32 ? 4 : 2));
     a.nvec = a.row_bytes / 16;
-    a.ntiles = (int)((S + FU_WARPS - 1) / FU_WARPS);
-    a.nrounds = (a.ntiles + FU_ROUND_TILES - 1) / FU_ROUND_TILES;
-    a.lag = fused_lag() < a.ntiles ? fused_lag() : a.ntiles;
-    a.desc_words = 1 + a.nrounds + (a.ntiles + 1) / 2;
+    a.slot_vecs = a.nvec;
+    a.band = fused_band();
+    a.nbands = (int)((S + a.band - 1) / a.band);
+    const int s32 = (int)((S + 31) / 32 * 32);
+    a.lag = fused_lag() < s32 ? fused_lag() : s32;
+    a.n_tickets = a.lag + 2 * s32;
+    a.desc_words = 1 + a.nbands + (a.nbands + s32 / 32 + 1) / 2;
     a.link = w.link[bank];
     a.link_next = w.link[nb];
     a.desc = w.desc[bank];
     a.desc_clr = w.desc[nb];
-    a.tile_mask = w.fflag[bank];
     a.sim_seq = w.sim;
     a.dst = w.dst[bank];
     a.counters = w.counters[bank];
@@ -415,17 +429,24 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
     ctx->fused_clean[nb] = 1;                              // the kernel clears the other bank on its way out
     ctx->h_status[FF_ST_INTERNAL] = 0;
     const int threads = FU_WARPS * 32;
+    const int smem = FU_WARPS * a.row_bytes;
     return dispatch_dtype(dtype, [&](auto dt) {
         constexpr int DT = decltype(dt)::value;
-        if (ctx->fused_attr[DT] == 0) {
+        if (ctx->fused_smem[DT] < smem) {
+            FF_CUDA(cudaFuncSetAttribute(k_fused_merge<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            ctx->fused_smem[DT] = smem;
+            ctx->fused_attr[DT] = 0;
+        }
+        if (ctx->fused_attr[DT] == 0 || ctx->fused_smem_last[DT] != smem) {
             int per_sm = 0;
-            FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_merge<DT>, threads, 0));
+            FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_merge<DT>, threads, smem));
             if (per_sm < 1) return fail(FF_E_UNSUPPORTED, "the read-once kernel does not fit an SM");
             ctx->fused_attr[DT] = per_sm;
+            ctx->fused_smem_last[DT] = smem;
         }
         int grid = ctx->fused_attr[DT] * ctx->sm_count;
-        if (grid > 2 * a.ntiles) grid = 2 * a.ntiles;
-        FF_LAUNCH("k_fused_merge", k_fused_merge<DT>, grid, threads, 0, st, a, ap);
+        if ((int64_t)grid * FU_WARPS > a.n_tickets) grid = (a.n_tickets + FU_WARPS - 1) / FU_WARPS;
+        FF_LAUNCH("k_fused_merge", k_fused_merge<DT>, grid, threads, smem, st, a, ap);
         return (int)FF_OK;
     });
 }
@@ -458,6 +479,8 @@ int ff_ctx_create(int device, ff_ctx** out) {
     c->last_fused = 0;
     c->fused_clean[0] = c->fused_clean[1] = 0;
     c->fused_attr[0] = c->fused_attr[1] = c->fused_attr[2] = 0;
+    c->fused_smem[0] = c->fused_smem[1] = c->fused_smem[2] = 0;
+    c->fused_smem_last[0] = c->fused_smem_last[1] = c->fused_smem_last[2] = 0;
     cudaError_t e = cudaHostAlloc((void**)&c->h_status, FF_ST_SLOTS * 8, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e != cudaSuccess) { delete c; return fail(FF_E_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
     memset(c->h_status, 0, FF_ST_SLOTS * 8);
