@@ -471,6 +471,7 @@ __device__ __forceinline__ void g_unit(const FusedArgs& a, const AuxPack& aux, c
     const int64_t row_bytes = a.row_bytes;
     if (b != bc.cb) {
         // entering a band: every band up to b must be complete; the prefix moves along with the band words
+        if (bc.cb < 0) bc.cb = 0;
         while (bc.cb < b) {
             const int kp = wait_band_done(d, bc.cb, err);
             if (kp < 0) return;
@@ -555,7 +556,7 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
     const int lag = a.lag, n_tickets = a.n_tickets;
     int err = 0;
     BandCache bc;
-    bc.cb = 0; bc.ce = 0; bc.pe = 0;
+    bc.cb = -1; bc.ce = 0; bc.pe = 0;
     int k = 0;
     if (lane == 0) k = (int)atomicAdd(d.ticket, 1ull);
     k = __shfl_sync(FULL, k, 0);
