@@ -77,6 +77,7 @@ struct ff_ctx {
     int64_t n_ids;
     int have_order;      // compact by-patch order / chain / rank arrays valid for `parity` (multi-kernel path)
     int have_seq;        // (pred, succ) of every sequence row valid for `parity` (read-once kernel)
+    int fresh_links;     // ... and they are the ones ff_build_links made (counters[C_FIRSTINV] valid: order of the S units)
     int last_fused;      // the last merge call ran the read-once kernel: sim[] is indexed by sequence row
     int fused_clean[2];  // state words / tile descriptors of the bank are known to be zero
     int fused_attr[3];   // resident CTAs per SM of the read-once kernel of each dtype (0: not asked yet)
@@ -152,7 +153,7 @@ Ws carve(void* base_ptr, int64_t cap, int64_t n_ids) {
     w.barrier = (unsigned*)take(256);
     w.sel_hist = (int*)take(4 * 256 * 4);
     for (int b = 0; b < 2; ++b) {
-        w.desc[b] = (unsigned long long*)take(16 + ((size_t)cap / 32 + 2) * 12 + ((size_t)cap / 32 + 2) * 4 + 16);   // ticket, per band u64 + u32 (a band is 32 rows at least), a mask bit per row
+        w.desc[b] = (unsigned long long*)take(16 + ((size_t)cap / 32 + 2) * 8 + ((size_t)cap / 1024 + 2) * 4 + 16);   // ticket, u64 per 32 rows, u32 per band
     }
     w.zero_begin = zero_begin;
     w.zero_bytes = (size_t)((p ? p + off : (char*)nullptr) - zero_begin);
@@ -350,35 +351,23 @@ int check_shape(int64_t S, int64_t H, int dtype) {
     return FF_OK;
 }
 
-// FF_FUSED_BAND / FF_FUSED_LAG override the band and the lag of the read-once kernel (ff_fused.cuh) for experiments
-int fused_env(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-int fused_band() {
-    static int band = -1;
-    if (band < 0) {
-        band = fused_env("FF_FUSED_BAND", FU_BAND) / 32 * 32;
-        if (band < 32) band = 32;
-    }
-    return band;
-}
+// FF_FUSED_LAG overrides the lag of the read-once kernel (ff_fused.cuh) for experiments
 int fused_lag() {
     static int lag = -1;
     if (lag < 0) {
-        lag = fused_env("FF_FUSED_LAG", FU_LAG) / 32 * 32;
-        if (lag < fused_band()) lag = fused_band();        // a G unit only waits for S units with a smaller ticket
+        const char* e = getenv("FF_FUSED_LAG");
+        lag = (e ? atoi(e) : FU_LAG) / 32 * 32;
+        if (lag < FU_BAND) lag = FU_BAND;                   // a G unit only waits for S units with a smaller ticket
     }
     return lag;
 }
 
-// rows the read-once kernel handles: 16-byte multiples, a threshold no chain head (sim = -2) can pass, one row per warp
-// in shared memory
+// rows the read-once kernel handles: 16-byte multiples and a threshold no chain head (sim = -2) can pass
 bool fused_shape_ok(const ff_ctx* ctx, const void* hidden, const void* out, int dtype, int64_t S, int64_t H, double thr) {
     const int64_t row_bytes = H * (dtype == FF_F32 ? 4 : 2);
     if (row_bytes % 16 != 0 || (((uintptr_t)hidden | (uintptr_t)out) & 15) != 0) return false;
     if (S >= (1ll << 30) - 2 * (int64_t)fused_lag()) return false;
-    if (FU_WARPS * row_bytes > ctx->max_smem) return false;
+    (void)ctx;
     return thr > -2.0;
 }
 
@@ -391,13 +380,18 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
     a.S = (int)S;
     a.row_bytes = (int)(H * (dtype == FF_F32 ? 4 : 2));
     a.nvec = a.row_bytes / 16;
-    a.slot_vecs = a.nvec;
-    a.band = fused_band();
-    a.nbands = (int)((S + a.band - 1) / a.band);
     const int s32 = (int)((S + 31) / 32 * 32);
-    a.lag = fused_lag() < s32 ? fused_lag() : s32;
+    a.nwords = s32 / 32;
+    a.nbands = (a.nwords + 31) / 32;
+    // S units patch by patch over FF_FUSED_SFRAMES frames on the call right after ff_build_links (uniform videos, ff_fused.cuh)
+    static const int s_frames = getenv("FF_FUSED_SFRAMES") ? atoi(getenv("FF_FUSED_SFRAMES")) : FU_SFRAMES;
+    a.perm_P = ctx->fresh_links && ctx->n_ids > 0 && ctx->n_ids * (int64_t)s_frames < (1 << 20) ? (int)ctx->n_ids : 0;
+    a.perm_F = a.perm_P ? s_frames : 0;
+    int lag = fused_lag();
+    if (a.perm_F > 1 && lag < a.perm_P * a.perm_F + 64) lag = (a.perm_P * a.perm_F + 64 + 31) / 32 * 32;   // a G unit only waits for S units with a smaller ticket
+    a.lag = lag < s32 ? lag : s32;
     a.n_tickets = a.lag + 2 * s32;
-    a.desc_words = 1 + a.nbands + (a.nbands + s32 / 32 + 1) / 2;
+    a.desc_words = 1 + a.nwords + (a.nbands + 1) / 2;
     a.link = w.link[bank];
     a.link_next = w.link[nb];
     a.desc = w.desc[bank];
@@ -429,7 +423,7 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
     ctx->fused_clean[nb] = 1;                              // the kernel clears the other bank on its way out
     ctx->h_status[FF_ST_INTERNAL] = 0;
     const int threads = FU_WARPS * 32;
-    const int smem = FU_WARPS * a.row_bytes;
+    const int smem = 0;
     return dispatch_dtype(dtype, [&](auto dt) {
         constexpr int DT = decltype(dt)::value;
         if (ctx->fused_smem[DT] < smem) {
@@ -444,7 +438,8 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
             ctx->fused_attr[DT] = per_sm;
             ctx->fused_smem_last[DT] = smem;
         }
-        int grid = ctx->fused_attr[DT] * ctx->sm_count;
+        static const int max_ctas = getenv("FF_FUSED_CTAS") ? atoi(getenv("FF_FUSED_CTAS")) : FU_MIN_CTAS;
+        int grid = (ctx->fused_attr[DT] < max_ctas ? ctx->fused_attr[DT] : max_ctas) * ctx->sm_count;
         if ((int64_t)grid * FU_WARPS > a.n_tickets) grid = (a.n_tickets + FU_WARPS - 1) / FU_WARPS;
         FF_LAUNCH("k_fused_merge", k_fused_merge<DT>, grid, threads, smem, st, a, ap);
         return (int)FF_OK;
@@ -476,6 +471,7 @@ int ff_ctx_create(int device, ff_ctx** out) {
     c->cap = 0;
     c->n_ids = 0;
     c->have_order = c->have_seq = 0;
+    c->fresh_links = 0;
     c->last_fused = 0;
     c->fused_clean[0] = c->fused_clean[1] = 0;
     c->fused_attr[0] = c->fused_attr[1] = c->fused_attr[2] = 0;
@@ -551,7 +547,7 @@ int ff_build_links(ff_ctx* ctx, void* ws, int64_t ws_bytes, const int64_t* patch
         FF_LAUNCH("k_links_scatter", k_links_scatter, n_chunks, LINK_CHUNK, 0, st, patch_type, (int)S, (int)n_ids, w.hist,
                   w.base, w.order[0], w.chain[0], w.rank[0]);
         FF_LAUNCH("k_links_seq", k_links_seq, (int)((S + 255) / 256), 256, 0, st, w.rank[0], w.order[0], w.chain[0], w.counters[0],
-                  (int)S, w.link[0]);
+                  (int)S, w.link[0], (unsigned long long*)&w.counters[0][C_FIRSTINV]);
     } else {
         k_links_status<<<1, 1, 0, st>>>(w.counters[0], ctx->d_status);
         FF_LAUNCH_CHECK("k_links_status");
@@ -560,6 +556,7 @@ int ff_build_links(ff_ctx* ctx, void* ws, int64_t ws_bytes, const int64_t* patch
     ctx->last_parity = 0;
     ctx->links_S = S;
     ctx->have_order = ctx->have_seq = 1;
+    ctx->fresh_links = 1;
     ctx->last_fused = 0;
     return FF_OK;
 }
@@ -640,8 +637,9 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
         if (ctx->ev_start) FF_CUDA(cudaEventRecord(ctx->ev_start, st));
         if (!ctx->have_seq)                                // the previous call took the multi-kernel path: links from its arrays
             FF_LAUNCH("k_links_seq", k_links_seq, (int)((S + 255) / 256), 256, 0, st, w.rank[bank], w.order[bank], w.chain[bank],
-                      w.counters[bank], (int)S, w.link[bank]);
+                      w.counters[bank], (int)S, w.link[bank], (unsigned long long*)nullptr);
         if (int rc = launch_fused(ctx, w, bank, hidden, hidden_out, dtype, S, H, thr, bound, ap, st)) return rc;
+        ctx->fresh_links = 0;
         if (ctx->ev_stop) FF_CUDA(cudaEventRecord(ctx->ev_stop, st));
         ctx->count_clean[bank] = 0;
         ctx->count_clean[nb] = 1;
@@ -705,6 +703,7 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     ctx->links_S = -2;                                     // = S_keep, known once the host has synchronised
     ctx->have_order = 1;
     ctx->have_seq = 0;                                     // the multi-kernel path keeps the compact arrays only
+    ctx->fresh_links = 0;
     ctx->last_fused = 0;
     return FF_OK;
 }

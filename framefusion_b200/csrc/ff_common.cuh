@@ -33,6 +33,7 @@ enum Counter {
     C_NMERGED = 8,
     C_NNEXT = 9,    // N of the links written for the next call
     C_TICKET2 = 10, // records handed out to the rows outside the chains (k_keep_scan / k_decide_scan)
+    C_FIRSTINV = 11,// S - (first chain row), 0 if there is none (k_links_seq; order of the read-once kernel's S units)
     C_SLOTS = 32
 };
 

@@ -6,28 +6,27 @@
 // predecessor, main.py:216-238) — 576 rows (4 MB) back on the first call of a uniform video — while the output is
 // compacted in SEQUENCE order (main.py:132-138): a row's destination is the number of kept rows before it, known only
 // when every earlier row has been compared.  So every row is visited twice by the warps of one persistent grid — once
-// for its similarity (from HBM), once for the gather (from the L2) — and the warps are independent workers that take
-// units of work from ONE ticket:
+// for its similarity (from HBM), once for the gather (from the L2, a few thousand rows later) — and the warps are
+// independent workers that take units of work, one row each, from ONE ticket:
 //
-//   S unit (row r).  The sequence is cut into bands of B rows.  If r is the first row of its chain inside its band, the
-//     warp walks the chain through the band: the row arrives from HBM in registers and stays in the warp's shared-memory
-//     slot as the next step's predecessor, so that a row is fetched once although it takes part in two similarities
-//     (the head of a segment fetches its predecessor — a row of the previous band — from the L2).  Three row sums, the
-//     reference's rounding chain, sim >= thr -> merged away; kept rows set their bit in mask[r / 32].  At the end of the
-//     segment the band receives ONE release-atomic: (rows << 32) | kept rows.  Any other row: nothing to do.  An S unit
-//     waits for nothing.
-//   G unit (row r), `lag` rows behind the S units.  It waits until its band is complete and the band's exclusive prefix
-//     is published (by the G unit of the band's first row, from the previous band's prefix and count) — then every flag
-//     of every earlier row is known.  A kept row ends the run of its chain predecessor: the warp walks the masks back to
-//     the run's anchor and writes the anchor's destination row: the raw row if the run has no members, else
-//     T(T(..T(anchor + m1) + ..) + mL) / T(L+1), one rounding to T per add in chain order (the sequence torch-CPU
-//     index_add_ performs, main.py:304-311) and one division (main.py:314-317).  Chain tails end their own run, rows
-//     outside the chains are copied.  The aux rows and the (pred, succ) links of the next call go with it.  All of these
-//     rows were read by S units at most `lag` + a run's length ago: they come out of the L2.
+//   S unit (row r).  The row (HBM, plain loads: `ld.global.nc.L1::no_allocate` data is dropped from the L2 first, and
+//     the gather would find nothing) and its chain predecessor (an L2 hit: some S unit's own row a moment ago), three
+//     row sums, the reference's rounding chain, sim >= thr -> merged away.  ONE relaxed 64-bit reduction into
+//     word[r / 32] carries both facts the gather needs: (1 << 32) | (kept << (r % 32)) — rows reported in the high
+//     half, kept mask in the low half.  An S unit waits for nothing.
+//   G unit (row r), `lag` rows behind the S units.  It waits until the words up to its own are complete — then every
+//     flag of every earlier row is known — and counts the kept rows before r: the prefix of its band (1024 rows: one
+//     word per lane), carried from band to band in registers, plus the masks of the band.  A kept row ends the run
+//     of its chain predecessor: the warp walks the masks back to the run's anchor and writes the anchor's destination
+//     row: the raw row if the run has no members, else T(T(..T(anchor + m1) + ..) + mL) / T(L+1), one rounding to T per
+//     add in chain order (the sequence torch-CPU index_add_ performs, main.py:304-311) and one division
+//     (main.py:314-317).  Chain tails end their own run, rows outside the chains are copied.  The aux rows and the
+//     (pred, succ) links of the next call go with it.
 //
-// Tickets are handed out in a fixed order — S(0 .. lag-1), then 32 S units and 32 G units alternating — so every
-// wait is for work with a smaller ticket, held by a warp that is running: no deadlock whatever is resident; every spin is
-// bounded all the same (FF_ST_INTERNAL).
+// Tickets run in a fixed order — S(0 .. lag-1), then 32 S units and 32 G units alternating — and a CTA draws them eight
+// at a time (one global atomic per eight units; its warps pick them from shared memory in order, the next eight already
+// requested).  Every wait is for work with a smaller ticket that a running warp has picked or will pick before anything
+// larger: no deadlock whatever is resident; every spin is bounded all the same (FF_ST_INTERNAL).
 //
 // The branch decision (main.py:114-116) needs the global count, known only at the end: the kernel speculates on the
 // threshold branch, the G unit of the last row checks count / n_vis < bound and otherwise reports FF_ST_ERROR = 3; the
@@ -39,10 +38,16 @@
 
 namespace ff {
 
-constexpr int FU_WARPS = 8;                        // warps per CTA (independent workers; a CTA only shares its shared memory)
-constexpr int FU_MIN_CTAS = 2;                     // per SM: up to 128 registers per thread
-constexpr int FU_BAND = 2048;                      // rows per band (multiple of 32; FF_FUSED_BAND)
-constexpr int FU_LAG = 4096;                       // S units run this many rows ahead of the G units (>= band; FF_FUSED_LAG)
+constexpr int FU_WARPS = 8;                        // warps per CTA (independent workers; a CTA shares its ticket ring)
+constexpr int FU_MIN_CTAS = 4;                     // per SM: 32 warps of at most 64 registers per thread
+constexpr int FU_BAND = 1024;                      // rows per band: 32 words of 32 rows, one word per lane
+constexpr int FU_LAG = 4096;                       // S units run this many rows ahead of the G units (FF_FUSED_LAG)
+constexpr int FU_SFRAMES = 2;                      // frames whose S units are taken patch by patch (FF_FUSED_SFRAMES; 1: sequence order)
+constexpr int FU_BATCH = 8;                        // tickets per draw
+#ifndef FU_PREFETCH_SLOT
+#define FU_PREFETCH_SLOT (FU_BATCH / 2)
+#endif
+constexpr int FU_RING = 16;                        // draws a CTA remembers
 constexpr int FU_SPIN_LIMIT = 1 << 20;             // polls (~100 ns apart) before a wait gives up and reports FF_ST_INTERNAL
 
 // the aux tensors, one entry per (tensor, plane): rows of at most 512 bytes in 16- or 8-byte pieces, one piece per lane
@@ -58,12 +63,13 @@ struct FusedArgs {
     AuxFlat auxf;
     const char* hidden;
     char* out;
-    int S, nvec, row_bytes, slot_vecs, band, nbands, lag, n_tickets;
+    int S, nvec, row_bytes, nwords, nbands, lag, n_tickets;
+    int perm_P, perm_F;                            // order of the S units on a uniform video (0: sequence order): see s_row()
     const int2* link;                              // [S] (pred, succ): row index, -1 = chain head / tail, -2 = not a chain row
     int2* link_next;                               // [S_keep] the same for the compacted sequence
-    unsigned long long* desc;                      // zero on entry, desc_words u64 in all: the ticket, band words [nbands]
-                                                   // ((rows done << 32) | kept rows), then u32 band_excl [nbands] (exclusive
-                                                   // prefix + 1) and u32 mask [ceil(S / 32)] (bit = kept)
+    unsigned long long* desc;                      // zero on entry, desc_words u64 in all: the ticket, word [nwords]
+                                                   // ((rows reported << 32) | kept mask of rows 32 i .. 32 i + 31), then u32
+                                                   // band_excl [nbands] (kept rows before the band + 1)
     int desc_words;
     unsigned long long* desc_clr;                  // other bank: cleared for the next call
     float* sim_seq;                                // [S] similarity with the chain predecessor (introspection)
@@ -76,14 +82,9 @@ struct FusedArgs {
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long ld_acquire64(const unsigned long long* p) {
+__device__ __forceinline__ unsigned long long ld_relaxed64(const unsigned long long* p) {
     unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned ld_acquire32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned ld_relaxed32(const unsigned* p) {
@@ -91,71 +92,112 @@ __device__ __forceinline__ unsigned ld_relaxed32(const unsigned* p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release32(unsigned* p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed32(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void red_release_add64(unsigned long long* p, unsigned long long v) {
-    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void red_or32(unsigned* p, unsigned v) {
-    asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void red_add64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
-// the arrays behind the ticket
-struct FusedDesc {
-    unsigned long long* ticket;
-    unsigned long long* band_word;                          // [nbands] (rows done << 32) | kept rows
-    unsigned* band_excl;                                    // [nbands] kept rows before the band + 1
-    unsigned* mask;                                         // [ceil(S / 32)] bit = kept
-    int S, band;
-    __device__ __forceinline__ int band_rows(int b) const { return min(band, S - b * band); }
+// ---- tickets: a CTA draws FU_BATCH at a time; its warps pick them in order from shared memory -----------------------
+struct TicketRing {
+    unsigned taken;                                         // picks of this CTA so far
+    int base[FU_RING];                                      // first ticket of draw i (slot i % FU_RING)
+    unsigned ready[FU_RING];                                // i + 1 once base is there
 };
 
-// every row of band b has been compared (the S units that do it hold smaller tickets); the kept rows of the band, -1 after a time-out
-__device__ __forceinline__ int wait_band_done(const FusedDesc& d, int b, int* err) {
-    const unsigned need = (unsigned)d.band_rows(b);
-    unsigned long long w = ld_acquire64(d.band_word + b);
-    int spins = 0;
-    while ((unsigned)(w >> 32) != need) {
-        if (++spins > FU_SPIN_LIMIT) { *err = 1; return -1; }
-        __nanosleep(100);
-        w = ld_acquire64(d.band_word + b);
+__device__ __forceinline__ void ticket_init(TicketRing* tr, unsigned long long* gticket) {
+    if (threadIdx.x < FU_RING) tr->ready[threadIdx.x] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tr->taken = 0u;
+        tr->base[0] = (int)atomicAdd(gticket, (unsigned long long)FU_BATCH);
+        tr->ready[0] = 1u;
     }
-    return (int)(unsigned)w;
+    __syncthreads();
 }
-// kept rows before band b (published by the G unit of the band's first row, which holds a smaller ticket); -1 after a time-out
-__device__ __forceinline__ int wait_band_excl(const FusedDesc& d, int b, int* err) {
-    unsigned v = ld_acquire32(d.band_excl + b);
+
+// whole warp; n_tickets (or more) when the work is exhausted or the ring timed out
+__device__ __forceinline__ int ticket_take(TicketRing* tr, unsigned long long* gticket, int n_tickets, int lane, int* err) {
+    unsigned n = 0;
+    if (lane == 0) n = atomicAdd(&tr->taken, 1u);
+    n = __shfl_sync(FULL, n, 0);
+    const unsigned draw = n / FU_BATCH, slot = n % FU_BATCH;
+    if (slot == FU_PREFETCH_SLOT && lane == 0) {
+        // half of this draw is gone: request the next one (this lane alone waits for the answer)
+        const int b = (int)atomicAdd(gticket, (unsigned long long)FU_BATCH);
+        *(volatile int*)&tr->base[(draw + 1) % FU_RING] = b;
+        __threadfence_block();
+        *(volatile unsigned*)&tr->ready[(draw + 1) % FU_RING] = draw + 2u;
+    }
+    __syncwarp();
     int spins = 0;
-    while (v == 0u) {
+    while (*(volatile unsigned*)&tr->ready[draw % FU_RING] != draw + 1u) {
+        if (++spins > FU_SPIN_LIMIT) { *err = 1; return n_tickets; }
+        __nanosleep(40);
+    }
+    __threadfence_block();
+    return *(volatile int*)&tr->base[draw % FU_RING] + (int)slot;
+}
+
+// ---- flags and prefixes ------------------------------------------------------------------------------------------
+struct FusedDesc {
+    unsigned long long* ticket;
+    unsigned long long* word;                               // [nwords] (rows reported << 32) | kept mask
+    unsigned* band_excl;                                    // [nbands] kept rows before the band + 1
+    int S, nwords;
+};
+
+// the 32 words of band b, one per lane (words behind the sequence read as 0); returns once the first `upto` of them are
+// complete — every row of theirs has been compared, by S units with smaller tickets
+__device__ __forceinline__ unsigned long long band_words(const FusedDesc& d, int b, int upto, int lane, int* err) {
+    const int i = b * 32 + lane;
+    const bool have = i < d.nwords;
+    const unsigned need = have ? (unsigned)min(32, d.S - i * 32) : 0u;
+    unsigned long long w = 0ull;
+    int spins = 0;
+    while (true) {
+        if (have) w = ld_relaxed64(d.word + i);
+        const bool ok = lane >= upto || (unsigned)(w >> 32) == need;
+        if (__all_sync(FULL, ok)) break;
         if (++spins > FU_SPIN_LIMIT) { *err = 1; break; }
         __nanosleep(100);
-        v = ld_acquire32(d.band_excl + b);
     }
-    return (int)v - 1;
+    return w;
 }
+
 // What a warp remembers between its G units: the band it last worked in, the kept rows before that band and before the
-// band in front of it.  Bands complete in order for a warp's purposes (it enters band b only when all bands up to b are
-// complete), so the prefix of the next band follows from the cached one and the band word — nobody waits for a publisher.
+// band in front of it.  A warp enters band b only when all earlier bands are complete, so the prefix of the next band
+// follows from the cached one and the band's words — nobody waits for a publisher.
 struct BandCache {
     int cb, ce, pe;                                         // band, kept rows before it, kept rows before band cb - 1
 };
 
-// kept rows before row x of a complete band (whole warp); *mx = the mask word of x
+__device__ __forceinline__ int wait_band_excl(const FusedDesc& d, int b, int* err) {
+    unsigned v = ld_relaxed32(d.band_excl + b);
+    int spins = 0;
+    while (v == 0u) {
+        if (++spins > FU_SPIN_LIMIT) { *err = 1; break; }
+        __nanosleep(100);
+        v = ld_relaxed32(d.band_excl + b);
+    }
+    return (int)v - 1;
+}
+
+// kept rows before row x, x in an earlier row than the caller's and therefore flagged (whole warp); *mx = the mask of x's word
 __device__ __forceinline__ int prefix_at(const FusedDesc& d, const BandCache& bc, int x, int lane, unsigned* mx, int* err) {
-    const int b = x / d.band, w0 = b * (d.band >> 5), wx = x >> 5;
-    int cnt = 0;
-    for (int i = w0 + lane; i < wx; i += 32) cnt += __popc(ld_relaxed32(d.mask + i));
-    const unsigned m = ld_relaxed32(d.mask + wx);
+    const int b = x >> 10, wi = (x >> 5) & 31;
+    const unsigned long long w = ld_relaxed64(d.word + min(b * 32 + lane, d.nwords - 1));
     const int e = b == bc.cb ? bc.ce : (b == bc.cb - 1 ? bc.pe : wait_band_excl(d, b, err));
-    cnt = warp_sum_int(cnt);
+    const int cnt = warp_sum_int(lane < wi ? __popc((unsigned)w) : 0);
+    const unsigned m = __shfl_sync(FULL, (unsigned)w, wi);
     *mx = m;
     return e < 0 ? -1 : e + cnt + __popc(m & ((1u << (x & 31)) - 1u));
 }
 
-// ---- row movers: 16-byte vectors; a row is cut into pieces of N vectors per lane (N = 8, 4, 2, 1: 256 ... 32 vectors)
-// and a last partial piece, so that every piece issues its N (or 2 N) loads back to back with no predicate in between —
-// predicated loads are not batched by ptxas, and a warp with one or two loads in flight is latency bound.
+// ---- row movers: 16-byte vectors; a row is cut into pieces of N vectors per lane (N = MAXN ... 1) and a last partial
+// piece, so that every piece issues its N (or 2 N) loads back to back with no predicate in between — predicated loads
+// are not batched by ptxas, and a warp with one or two loads in flight is latency bound.
 template <int N>
 __device__ __forceinline__ void copy_piece(const char* __restrict__ src, char* __restrict__ dst) {
     uint4 x[N];
@@ -165,7 +207,7 @@ __device__ __forceinline__ void copy_piece(const char* __restrict__ src, char* _
     for (int q = 0; q < N; ++q) st_stream16(dst + q * 512, x[q]);
 }
 
-// src row -> dst row
+// src row -> dst row (read for the last time, written once: streaming both ways)
 __device__ __forceinline__ void copy_row(const char* __restrict__ src, char* __restrict__ dst, int nvec, int lane) {
     int v = 0;                                              // vectors done (warp-uniform)
     src += lane * 16;
@@ -178,6 +220,19 @@ __device__ __forceinline__ void copy_row(const char* __restrict__ src, char* __r
     if (v + lane < nvec) copy_piece<1>(src + (int64_t)v * 16, dst + (int64_t)v * 16);
 }
 
+// the row an S unit reads for the first time: it must stay in the L2 for its successor's S unit and for the gather
+#ifdef FU_EVICT_LAST
+__device__ __forceinline__ uint4 ld_keep16(const void* p) {
+    uint4 r;
+    asm volatile("{\n.reg .b64 pol;\ncreatepolicy.fractional.L2::evict_last.b64 pol, 1.0;\n"
+                 "ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], pol;\n}"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+#else
+__device__ __forceinline__ uint4 ld_keep16(const void* p) { return ldg16(p); }
+#endif
+
 struct SimAcc {
     float2 d0, d1, a0, a1, b0, b1;
 };
@@ -187,8 +242,8 @@ __device__ __forceinline__ void sim_piece(const char* __restrict__ pr, const cha
     uint4 p[N], c[N];
 #pragma unroll
     for (int q = 0; q < N; ++q) {
-        c[q] = ld_stream16(cr + q * 512);
-        p[q] = ld_stream16(pr + q * 512);
+        c[q] = ld_keep16(cr + q * 512);
+        p[q] = ldg16(pr + q * 512);
     }
 #pragma unroll
     for (int q = 0; q < N; ++q) {
@@ -199,7 +254,7 @@ __device__ __forceinline__ void sim_piece(const char* __restrict__ pr, const cha
 
 // cosine similarity of rows pr (predecessor) and cr with the reference's rounding chain (main.py:345-349).  The three
 // row sums are float32 (ATen accumulates the reductions in float32; their order is torch's own and unknown, which the
-// oracle brackets), split over four independent chains per lane.
+// oracle brackets), split over four independent chains per lane; four + four vectors in flight.
 template <int DT>
 __device__ __forceinline__ float row_similarity(const char* __restrict__ pr, const char* __restrict__ cr, int nvec, int lane) {
     SimAcc s;
@@ -208,8 +263,7 @@ __device__ __forceinline__ float row_similarity(const char* __restrict__ pr, con
     pr += lane * 16;
     cr += lane * 16;
 #pragma unroll 1
-    for (; v + 256 <= nvec; v += 256) sim_piece<DT, 8>(pr + (int64_t)v * 16, cr + (int64_t)v * 16, s);
-    if (v + 128 <= nvec) { sim_piece<DT, 4>(pr + (int64_t)v * 16, cr + (int64_t)v * 16, s); v += 128; }
+    for (; v + 128 <= nvec; v += 128) sim_piece<DT, 4>(pr + (int64_t)v * 16, cr + (int64_t)v * 16, s);
     if (v + 64 <= nvec) { sim_piece<DT, 2>(pr + (int64_t)v * 16, cr + (int64_t)v * 16, s); v += 64; }
     if (v + 32 <= nvec) { sim_piece<DT, 1>(pr + (int64_t)v * 16, cr + (int64_t)v * 16, s); v += 32; }
     if (v + lane < nvec) sim_piece<DT, 1>(pr + (int64_t)v * 16, cr + (int64_t)v * 16, s);
@@ -217,74 +271,6 @@ __device__ __forceinline__ float row_similarity(const char* __restrict__ pr, con
     const float na = warp_sum((s.a0.x + s.a0.y) + (s.a1.x + s.a1.y));
     const float nb = warp_sum((s.b0.x + s.b0.y) + (s.b1.x + s.b1.y));
     return finish_cosine<DT>(dot, na, nb);
-}
-
-// ---- the walk of an S unit: the current row against the row in the warp's shared-memory slot, which it then replaces
-// dot += T(p * c), nb += c * c on one 16-byte vector pair (cf. acc_pair2: the same arithmetic without the sum of p * p)
-template <int DT>
-__device__ __forceinline__ void acc_dot_nb(const uint4& vp, const uint4& vc, float2& dot, float2& nb) {
-    if (DT == FF_BF16) {
-        const uint32_t pw[4] = {vp.x, vp.y, vp.z, vp.w}, cw[4] = {vc.x, vc.y, vc.z, vc.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            __nv_bfloat162 pp = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&pw[q]), *reinterpret_cast<const __nv_bfloat162*>(&cw[q]));
-            const uint32_t w = *reinterpret_cast<uint32_t*>(&pp);
-            dot = __fadd2_rn(dot, make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)));
-            const float2 cf = make_float2(__uint_as_float(cw[q] << 16), __uint_as_float(cw[q] & 0xffff0000u));
-            nb = __ffma2_rn(cf, cf, nb);
-        }
-    } else {
-        float p[Num<DT>::EPV], c[Num<DT>::EPV];
-        Num<DT>::unpack(vp, p);
-        Num<DT>::unpack(vc, c);
-#pragma unroll
-        for (int e = 0; e < Num<DT>::EPV; e += 2) {
-            if (DT == FF_F32) { dot.x += __fmul_rn(p[e], c[e]); dot.y += __fmul_rn(p[e + 1], c[e + 1]); }
-            else { dot.x += Num<DT>::rnd(p[e] * c[e]); dot.y += Num<DT>::rnd(p[e + 1] * c[e + 1]); }
-            nb.x = fmaf(c[e], c[e], nb.x);
-            nb.y = fmaf(c[e + 1], c[e + 1], nb.y);
-        }
-    }
-}
-
-struct StepAcc {
-    float2 d0, d1, b0, b1;
-};
-
-// N vectors per lane of the current row: loads back to back, then per vector the slot's vector (predecessor), the sums,
-// and the current vector takes its place.  DOT = false: no predecessor (the row is only parked and its norm taken).
-template <int DT, int N, bool DOT>
-__device__ __forceinline__ void step_piece(const char* __restrict__ cr, uint4* __restrict__ sl, StepAcc& s) {
-    uint4 c[N];
-#pragma unroll
-    for (int q = 0; q < N; ++q) c[q] = ld_stream16(cr + q * 512);
-#pragma unroll
-    for (int q = 0; q < N; ++q) {
-        const uint4 p = DOT ? sl[q * 32] : c[q];
-        if (q & 1) acc_dot_nb<DT>(p, c[q], s.d1, s.b1);
-        else acc_dot_nb<DT>(p, c[q], s.d0, s.b0);
-        sl[q * 32] = c[q];
-    }
-}
-
-// row cr against the slot; returns (dot, |cr|^2) summed over the warp
-template <int DT, bool DOT>
-__device__ __forceinline__ float2 row_step(const char* __restrict__ cr, uint4* __restrict__ slot, int nvec, int lane) {
-    StepAcc s;
-    s.d0 = s.d1 = s.b0 = s.b1 = make_float2(0.f, 0.f);
-    int v = 0;
-    cr += lane * 16;
-    uint4* sl = slot + lane;
-#pragma unroll 1
-    for (; v + 256 <= nvec; v += 256) step_piece<DT, 8, DOT>(cr + (int64_t)v * 16, sl + v, s);
-    if (v + 128 <= nvec) { step_piece<DT, 4, DOT>(cr + (int64_t)v * 16, sl + v, s); v += 128; }
-    if (v + 64 <= nvec) { step_piece<DT, 2, DOT>(cr + (int64_t)v * 16, sl + v, s); v += 64; }
-    if (v + 32 <= nvec) { step_piece<DT, 1, DOT>(cr + (int64_t)v * 16, sl + v, s); v += 32; }
-    if (v + lane < nvec) step_piece<DT, 1, DOT>(cr + (int64_t)v * 16, sl + v, s);
-    float2 r;
-    r.x = DOT ? warp_sum((s.d0.x + s.d0.y) + (s.d1.x + s.d1.y)) : 0.f;
-    r.y = warp_sum((s.b0.x + s.b0.y) + (s.b1.x + s.b1.y));
-    return r;
 }
 
 // the members of a run in chain order: lane k of `mine` holds the k-th member from the END (runs of at most 32 members);
@@ -343,12 +329,11 @@ __device__ __forceinline__ void sum_run(const char* __restrict__ hidden, int nve
     int v = 0;
     const int64_t lo = lane * 16;
 #pragma unroll 1
-    for (; v + 256 <= nvec; v += 256) run_piece<DT, 8>(hidden, row_bytes, lo + (int64_t)v * 16, w, first, dv, orow);
-    if (v + 128 <= nvec) { run_piece<DT, 4>(hidden, row_bytes, lo + (int64_t)v * 16, w, first, dv, orow); v += 128; }
+    for (; v + 128 <= nvec; v += 128) run_piece<DT, 4>(hidden, row_bytes, lo + (int64_t)v * 16, w, first, dv, orow);
     if (v + 64 <= nvec) { run_piece<DT, 2>(hidden, row_bytes, lo + (int64_t)v * 16, w, first, dv, orow); v += 64; }
     if (v + 32 <= nvec) { run_piece<DT, 1>(hidden, row_bytes, lo + (int64_t)v * 16, w, first, dv, orow); v += 32; }
     // (the shuffles inside a piece are warp-wide: the partial piece is walked by every lane, out-of-range lanes re-read
-    // their last full vector and store nothing)
+    // their first vector and store nothing)
     if (v < nvec) {
         const bool in = v + lane < nvec;
         const int64_t off = in ? lo + (int64_t)v * 16 : lo;
@@ -417,74 +402,60 @@ __device__ __forceinline__ void fused_finish(const FusedArgs& a, long long s_kee
     a.status[FF_ST_FUSED] = 1;
 }
 
+// Order of the S units.  On the first call of a uniform video (frames x P vision rows in one span, chains = patches) the
+// S units of F consecutive frames are taken patch by patch — (f, p), (f + 1, p), .., (f, p + 1) .. — so that the unit of
+// (f + 1, p) runs next to the unit of (f, p), on the same SM at the same time: its predecessor row is the neighbour's own
+// row (one request to the L2 instead of two that miss together), and the predecessor of (f, p) was fetched F frames of
+// units ago and has arrived.  Any layout is served correctly (the map is a bijection of the rows whatever the links
+// say); other layouts keep the sequence order.
+struct SOrder {
+    int first, span, P, F, frames;                          // span = frames * P rows from `first`; F = 0: identity
+    __device__ __forceinline__ int row(int s) const {
+        const int local = s - first;
+        if (F == 0 || local < 0 || local >= span) return s;
+        const int bi = local / (F * P), w = local - bi * (F * P), f0 = bi * F;
+        const int fb = min(F, frames - f0);
+        const int p = w / fb;
+        return first + (f0 + (w - p * fb)) * P + p;
+    }
+};
+
 // S unit of row r (see the head of the file)
 template <int DT>
-__device__ __forceinline__ void s_unit(const FusedArgs& a, const FusedDesc& d, int r, uint4* slot, int lane) {
-    int2 lk = __ldg(a.link + r);
-    const int b = r / a.band, band_end = min(b * a.band + a.band, a.S);
-    if (lk.x >= b * a.band) return;                         // its chain predecessor walks the band
-    int rows = 0, kept_rows = 0;
-    if (lk.x == -2) {                                       // outside the chains: kept (main.py:132)
-        if (lane == 0) { a.sim_seq[r] = -2.0f; red_or32(d.mask + (r >> 5), 1u << (r & 31)); }
-        rows = kept_rows = 1;
-    } else {
-        const int nvec = a.nvec;
-        const int64_t row_bytes = a.row_bytes;
-        float na = 0.f;
-        bool have_prev = lk.x >= 0;
-        if (have_prev) na = row_step<DT, false>(a.hidden + (int64_t)lk.x * row_bytes, slot, nvec, lane).y;
-        int cur = r;
-#pragma unroll 1
-        while (true) {
-            float s = -2.0f;                                // IGNORE_TOKEN at chain heads (main.py:225-238)
-            float2 t;
-            if (have_prev) {
-                t = row_step<DT, true>(a.hidden + (int64_t)cur * row_bytes, slot, nvec, lane);
-                s = finish_cosine<DT>(t.x, na, t.y);
-            } else {
-                t = row_step<DT, false>(a.hidden + (int64_t)cur * row_bytes, slot, nvec, lane);
-            }
-            const int kept = !(have_prev && s >= a.thr);    // NaN compares false: kept
-            if (lane == 0) {
-                a.sim_seq[cur] = s;
-                if (kept) red_or32(d.mask + (cur >> 5), 1u << (cur & 31));
-            }
-            ++rows;
-            kept_rows += kept;
-            na = t.y;
-            have_prev = true;
-            const int nxt = lk.y;
-            if (nxt < 0 || nxt >= band_end) break;
-            cur = nxt;
-            lk = __ldg(a.link + cur);
-        }
+__device__ __forceinline__ void s_unit(const FusedArgs& a, const FusedDesc& d, int r, int lane) {
+    const int2 lk = __ldg(a.link + r);
+    float s = -2.0f;                                        // IGNORE_TOKEN at chain heads (main.py:225-238)
+    if (lk.x >= 0) s = row_similarity<DT>(a.hidden + (int64_t)lk.x * a.row_bytes, a.hidden + (int64_t)r * a.row_bytes, a.nvec, lane);
+    const unsigned kept = !(lk.x >= 0 && s >= a.thr);       // NaN compares false: kept
+    if (lane == 0) {
+        a.sim_seq[r] = s;
+        red_add64(d.word + (r >> 5), (1ull << 32) | ((unsigned long long)kept << (r & 31)));
     }
-    if (lane == 0) red_release_add64(d.band_word + b, ((unsigned long long)rows << 32) | (unsigned long long)kept_rows);
 }
 
 // G unit of row r (see the head of the file)
 template <int DT>
 __device__ __forceinline__ void g_unit(const FusedArgs& a, const AuxPack& aux, const FusedDesc& d, BandCache& bc, int r, int lane, int* err) {
     const int2 lk = __ldg(a.link + r);
-    const int b = r / a.band;
+    const int b = r >> 10, wi = (r >> 5) & 31;
     const int nvec = a.nvec;
     const int64_t row_bytes = a.row_bytes;
     if (b != bc.cb) {
-        // entering a band: every band up to b must be complete; the prefix moves along with the band words
+        // entering a band: the prefix moves along with the words of the bands in between, all complete by now
         if (bc.cb < 0) bc.cb = 0;
         while (bc.cb < b) {
-            const int kp = wait_band_done(d, bc.cb, err);
-            if (kp < 0) return;
+            const unsigned long long w = band_words(d, bc.cb, 32, lane, err);
             bc.pe = bc.ce;
-            bc.ce += kp;
+            bc.ce += warp_sum_int(__popc((unsigned)w));
             ++bc.cb;
         }
-        if (wait_band_done(d, b, err) < 0) return;
     }
-    if (r == b * a.band && lane == 0) st_release32(d.band_excl + b, (unsigned)bc.ce + 1u);   // for walks that end in older bands
-    unsigned m;
-    const int ex = prefix_at(d, bc, r, lane, &m, err);
-    if (ex < 0) return;
+    if (*err) return;
+    if ((r & 1023) == 0 && lane == 0) st_relaxed32(d.band_excl + b, (unsigned)bc.ce + 1u);   // for walks that end in older bands
+    const unsigned long long wown = band_words(d, b, wi + 1, lane, err);
+    if (*err) return;
+    const unsigned m = __shfl_sync(FULL, (unsigned)wown, wi);
+    const int ex = bc.ce + warp_sum_int(lane < wi ? __popc((unsigned)wown) : 0) + __popc(m & ((1u << (r & 31)) - 1u));
     const bool is_kept = m >> (r & 31) & 1u;
     const int d_r = is_kept ? ex : -1;
     if (lane == 0) {
@@ -510,7 +481,7 @@ __device__ __forceinline__ void g_unit(const FusedArgs& a, const AuxPack& aux, c
         // every lane walks (uniform loads); lane k remembers the k-th member from the end
         int x = start, L = 0, mine = -1;
         while (true) {
-            const unsigned mx = ld_relaxed32(d.mask + (x >> 5));
+            const unsigned mx = (unsigned)ld_relaxed64(d.word + (x >> 5));
             if (mx >> (x & 31) & 1u) break;                 // kept: the anchor
             if (lane == L) mine = x;
             ++L;
@@ -542,28 +513,36 @@ __device__ __forceinline__ void g_unit(const FusedArgs& a, const AuxPack& aux, c
 template <int DT>
 __global__ void __launch_bounds__(FU_WARPS * 32, FU_MIN_CTAS)
 k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPack aux) {
-    extern __shared__ uint4 fu_slots[];                     // one row per warp
+    __shared__ TicketRing ring;
     pdl_enter();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint4* const slot = fu_slots + (size_t)wid * a.slot_vecs;
+    const int lane = threadIdx.x & 31;
     FusedDesc d;
     d.ticket = a.desc;
-    d.band_word = a.desc + 1;
-    d.band_excl = reinterpret_cast<unsigned*>(a.desc + 1 + a.nbands);
-    d.mask = d.band_excl + a.nbands;
+    d.word = a.desc + 1;
+    d.band_excl = reinterpret_cast<unsigned*>(a.desc + 1 + a.nwords);
     d.S = a.S;
-    d.band = a.band;
+    d.nwords = a.nwords;
     const int lag = a.lag, n_tickets = a.n_tickets;
+    SOrder so;
+    so.F = 0;
+    if (a.perm_F > 1 && a.perm_P > 0) {
+        const long long inv = a.counters[C_FIRSTINV], nvis = a.counters[C_NVIS];
+        if (inv > 0 && nvis > 0 && nvis % a.perm_P == 0 && (long long)a.S - inv + nvis <= a.S) {
+            so.first = (int)(a.S - inv);
+            so.span = (int)nvis;
+            so.P = a.perm_P;
+            so.F = a.perm_F;
+            so.frames = (int)(nvis / a.perm_P);
+        }
+    }
     int err = 0;
     BandCache bc;
     bc.cb = -1; bc.ce = 0; bc.pe = 0;
-    int k = 0;
-    if (lane == 0) k = (int)atomicAdd(d.ticket, 1ull);
-    k = __shfl_sync(FULL, k, 0);
+    ticket_init(&ring, d.ticket);
 #pragma unroll 1
-    while (k < n_tickets) {
-        int next = 0;
-        if (lane == 0) next = (int)atomicAdd(d.ticket, 1ull);         // the next ticket travels while this unit is done
+    while (true) {
+        const int k = ticket_take(&ring, d.ticket, n_tickets, lane, &err);
+        if (k >= n_tickets) break;
         // ticket -> unit: S(0 .. lag-1), then 32 S units (rows lag + 32 i ..) and 32 G units (rows 32 i ..) alternating
         bool is_g = false;
         int r = k;
@@ -574,11 +553,10 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
         }
         if (r < a.S) {
             if (is_g) g_unit<DT>(a, aux, d, bc, r, lane, &err);
-            else s_unit<DT>(a, d, r, slot, lane);
+            else s_unit<DT>(a, d, so.row(r), lane);
         }
-        k = __shfl_sync(FULL, next, 0);
     }
-    // leave the other bank's ticket, band words, prefixes and masks zeroed for the next call of the prefill
+    // leave the other bank's ticket, words and prefixes zeroed for the next call of the prefill
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.desc_words; i += (int64_t)gridDim.x * blockDim.x)
         a.desc_clr[i] = 0ull;
     if (err && lane == 0) a.status[FF_ST_INTERNAL] = 1;
@@ -587,7 +565,7 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
 // (pred, succ) of every sequence row from the compact by-patch arrays (ff_links.cuh / the scan kernels)
 __global__ void __launch_bounds__(256)
 k_links_seq(const int* __restrict__ rank, const int* __restrict__ order, const int* __restrict__ chain,
-            const int64_t* __restrict__ counters, int S, int2* __restrict__ link) {
+            const int64_t* __restrict__ counters, int S, int2* __restrict__ link, unsigned long long* first_inv) {
     pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S) return;
@@ -598,6 +576,7 @@ k_links_seq(const int* __restrict__ rank, const int* __restrict__ order, const i
         const int c = chain[j];
         l.x = (j > 0 && chain[j - 1] == c) ? order[j - 1] : -1;
         l.y = (j + 1 < N && chain[j + 1] == c) ? order[j + 1] : -1;
+        if (first_inv && (i == 0 || rank[i - 1] < 0)) atomicMax(first_inv, (unsigned long long)(S - i));   // start of a span of chain rows
     }
     link[i] = l;
 }
