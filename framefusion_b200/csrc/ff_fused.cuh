@@ -41,7 +41,7 @@ namespace ff {
 constexpr int FU_WARPS = 8;                        // warps per CTA (independent workers; a CTA shares its ticket ring)
 constexpr int FU_MIN_CTAS = 4;                     // per SM: 32 warps of at most 64 registers per thread
 constexpr int FU_BAND = 1024;                      // rows per band: 32 words of 32 rows, one word per lane
-constexpr int FU_LAG = 4096;                       // S units run this many rows ahead of the G units (FF_FUSED_LAG)
+constexpr int FU_LAG = 8192;                       // S units run this many rows ahead of the G units (FF_FUSED_LAG)
 constexpr int FU_SFRAMES = 2;                      // frames whose S units are taken patch by patch (FF_FUSED_SFRAMES; 1: sequence order)
 constexpr int FU_BATCH = 8;                        // tickets per draw
 #ifndef FU_PREFETCH_SLOT
