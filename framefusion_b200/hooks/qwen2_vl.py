@@ -7,7 +7,10 @@ re-targeted to the transformers 5.x layout (``Qwen2VLForConditionalGeneration.mo
 * importance uses the last FOUR queries (``num=4``, reference :289-301).
 
 The top-level ``forward`` patch of the reference only builds ``patch_type`` and calls ``prepare``
-(models/qwenvl/modeling_qwen2_vl.py:117-138); here that is ``framefusion_b200.layout.qwen2vl_prepare_args``.
+(models/qwenvl/modeling_qwen2_vl.py:117-138).  The reference does it by pasting a copy of the whole
+``Qwen2VLForConditionalGeneration.forward`` around those lines; here ``forward`` below does the same layout step and
+then hands every argument to the model class's own ``forward`` — nothing of transformers is duplicated, so the patch
+follows the installed version.
 """
 from __future__ import annotations
 
@@ -22,6 +25,34 @@ from transformers.models.qwen2_vl.modeling_qwen2_vl import apply_multimodal_rota
 
 from ..utils import scaled_dot_product_attention
 from .qwen2 import Qwen2DecoderLayer_merge_then_prune_by_cost_forward as Qwen2VLDecoderLayer_merge_then_fastv_cost_given_forward
+
+
+def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
+            labels=None, use_cache=None, pixel_values=None, pixel_values_videos=None, image_grid_thw=None,
+            video_grid_thw=None, **kwargs):
+    """Embed-stage patch of ``Qwen2VLForConditionalGeneration`` (reference models/qwenvl/modeling_qwen2_vl.py:11-138,
+    installed by ``apply_framefusion`` / ``get_token_type``): on a prefill with one video, derive the token layout from
+    ``input_ids`` and ``video_grid_thw`` — ``patch_num = H * W / merge^2`` tokens per frame between the first and the last
+    video placeholder (reference :118-127) —, remember it on the model like the reference (:129-133) and call
+    ``self.framefusion.prepare`` (:136-137, skipped when the model carries a ``mode`` attribute); then run the model's own
+    forward.  Decode steps (one token) and calls without a video pass straight through."""
+    from .. import layout
+    seq = input_ids.shape[1] if input_ids is not None else (inputs_embeds.shape[1] if inputs_embeds is not None else 1)
+    if seq != 1 and video_grid_thw is not None and input_ids is not None:
+        vision_cfg = getattr(self.config, "vision_config", None)
+        merge = getattr(vision_cfg, "spatial_merge_size", None)
+        if merge is None:                                    # transformers 4.x keeps it on the tower
+            merge = self.visual.config.spatial_merge_size
+        device = self.get_input_embeddings().weight.device
+        args = layout.qwen2vl_prepare_args(input_ids, self.config.video_token_id, video_grid_thw, merge, device=device)
+        (_patch_type, self.patch_num, self.image_token_start_index, self.image_token_end_index,
+         self.image_token_length, self.original_length) = args
+        if not hasattr(self, "mode"):
+            self.framefusion.prepare(*args)
+    return type(self).forward(self, input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
+                              past_key_values=past_key_values, inputs_embeds=inputs_embeds, labels=labels,
+                              use_cache=use_cache, pixel_values=pixel_values, pixel_values_videos=pixel_values_videos,
+                              image_grid_thw=image_grid_thw, video_grid_thw=video_grid_thw, **kwargs)
 
 
 def llm_key(model) -> str:

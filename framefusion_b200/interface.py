@@ -7,11 +7,13 @@ module, rebinding their ``forward`` with ``MethodType``.  The three callables st
 reference documents them as its extension point (README.md:171-175).
 
 Families handled here are the ones on the north-star path: a plain Qwen2 decoder stack (LLaVA-Video's
-``LlavaQwenForCausalLM``, ``Qwen2ForCausalLM``; keys ``model / layers / self_attn``, reference :69-77) and the
-wrappers that hold one under ``llm.model`` (MiniCPM-V, NVILA; reference :80-99).  The vision-side embed patches of
-those families live in un-vendored third-party packages (``llava``, remote-code models) and are out of scope:
-callers hand the token layout to ``model.framefusion.prepare`` themselves, or use ``framefusion_b200.layout`` to
-build it.  Anything else raises ``NotImplementedError`` after printing the model, like the reference (:120-124).
+``LlavaQwenForCausalLM``, ``Qwen2ForCausalLM``; keys ``model / layers / self_attn``, reference :69-77), the
+wrappers that hold one under ``llm.model`` (MiniCPM-V, NVILA; reference :80-99) and Qwen2-VL (reference :101-109),
+whose embed-stage patch — the top-level ``forward`` that derives the token layout and calls ``prepare`` — is
+installed as well (``hooks/qwen2_vl.forward``).  The embed patches of the other families rewrite functions of
+un-vendored third-party packages (``llava``, remote-code models) that are not in this image: for those, callers hand
+the token layout to ``model.framefusion.prepare`` themselves, or use ``framefusion_b200.layout`` to build it.
+Anything else raises ``NotImplementedError`` after printing the model, like the reference (:120-124).
 """
 from __future__ import annotations
 
@@ -32,6 +34,16 @@ def _qwen2_trio():
                               Qwen2SdpaAttention_merge_then_prune_by_cost_forward)
     return (Qwen2Model_merge_then_fastv_cost_given_forward, Qwen2DecoderLayer_merge_then_prune_by_cost_forward,
             Qwen2SdpaAttention_merge_then_prune_by_cost_forward)
+
+
+def _embed_patch(model):
+    """The embed-stage patch of the model's family (what the reference's ``get_token_type`` installs, :140-166), or None
+    when it belongs to third-party code that is not in this image."""
+    names = {c.__name__ for c in type(model).__mro__}
+    if "Qwen2VLForConditionalGeneration" in names:
+        from .hooks.qwen2_vl import forward
+        return "forward", forward
+    return None
 
 
 def _family(model):
@@ -61,16 +73,28 @@ def apply_framefusion(model, cost, similarity_lower_bound, ratio_lower_bound):
         print(model)
         raise NotImplementedError
     llm_key, trio = family
+    patch = _embed_patch(model)
+    if patch is not None:
+        setattr(model, patch[0], MethodType(patch[1], model))
     replace_framefusion_forward(model, cost, similarity_lower_bound, ratio_lower_bound, *trio,
                                 llm_key=llm_key, decoder_key="layers", attention_key="self_attn")
 
 
 def get_token_type(model):
-    """The reference installs only the embed-stage patch here (:140-166).  Those patches belong to third-party
-    model code that is not in this image; the token layout builders are in ``framefusion_b200.layout``."""
+    """Installs ONLY the embed-stage patch of the model's family (reference :140-166) — the function that derives the
+    token layout (``patch_type``, ``patch_num``, the vision span) during the prefill and leaves it on the model.  Qwen2-VL:
+    the top-level ``forward`` (reference :157-158).  The patches of the other families rewrite third-party functions that
+    are not in this image (``llava``'s ``prepare_inputs_labels_for_multimodal``, NVILA's ``_embed``, MiniCPM-V's
+    ``get_vllm_embedding``): for them this raises ``NotImplementedError`` naming ``framefusion_b200.layout``, whose
+    builders produce the same arguments.  Unknown models raise ``NotImplementedError`` like the reference (:165-166)."""
     if _family(model) is None:
         raise NotImplementedError
-    return None
+    patch = _embed_patch(model)
+    if patch is None:
+        raise NotImplementedError(
+            f"the embed-stage patch of {type(model).__name__} rewrites third-party code that is not installed here; "
+            "build the layout with framefusion_b200.layout and call model.framefusion.prepare(...)")
+    setattr(model, patch[0], MethodType(patch[1], model))
 
 
 def _rebind(target: nn.Module, fn: Callable, operator: FrameFusion):

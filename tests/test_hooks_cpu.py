@@ -267,3 +267,118 @@ def test_layer_split_moves_inputs_between_blocks(patched_importance):
         model.framefusion.prepare(*wl.prepare_args())
         got = model.model(inputs_embeds=wl.hidden.clone(), use_cache=True).last_hidden_state
     assert torch.allclose(got, want, rtol=1e-4, atol=1e-5)
+
+
+# ---- Qwen2-VL embed-stage patch (reference models/qwenvl/modeling_qwen2_vl.py:117-138) and the drop-in import path ----
+def tiny_qwen2vl_video():
+    """The tiny Qwen2-VL with in-vocabulary placeholder ids, and one video: grid (T, H, W) = (4, 4, 6) merged 2 x 2 ->
+    4 frames of 6 tokens between 3 leading and 4 trailing text tokens."""
+    from transformers import Qwen2VLConfig, Qwen2VLForConditionalGeneration
+    torch.manual_seed(0)
+    cfg = Qwen2VLConfig(
+        text_config=dict(vocab_size=128, hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4,
+                         num_key_value_heads=2, max_position_embeddings=4096,
+                         rope_parameters={"rope_type": "default", "mrope_section": [2, 3, 3], "rope_theta": 1e6}),
+        vision_config=dict(depth=1, embed_dim=32, hidden_size=64, num_heads=2, in_channels=3, patch_size=14,
+                           spatial_merge_size=2, temporal_patch_size=2),
+        video_token_id=100, image_token_id=101, vision_start_token_id=102, vision_end_token_id=103)
+    model = Qwen2VLForConditionalGeneration(cfg).eval().float()
+    t, h, w = 4, 4, 6
+    n_tok = t * h * w // 4
+    ids = torch.tensor([[1, 2, 102] + [100] * n_tok + [103, 5, 6, 7]])
+    inputs = dict(input_ids=ids, pixel_values_videos=torch.randn(t * h * w, 3 * 2 * 14 * 14),
+                  video_grid_thw=torch.tensor([[t, h, w]]), mm_token_type_ids=(ids == 100).int() * 2)
+    return model, inputs, n_tok
+
+
+class RecordingOperator(OracleOperator):
+    def prepare(self, *a):
+        self.prepared = a
+        super().prepare(*a)
+
+
+def _swap_operator(model, op):
+    llm = model.model.language_model
+    shared = model.framefusion
+    for m in [model, llm] + list(llm.layers) + [l.self_attn for l in llm.layers]:
+        assert m.framefusion is shared
+        m.framefusion = op
+
+
+def test_qwen2vl_embed_patch_prepares_the_layout_from_the_video_grid(monkeypatch):
+    """apply_framefusion installs the top-level forward patch: a prefill with video_grid_thw reaches ``prepare`` with the
+    reference's arguments (:118-137), leaves them on the model (:129-133), reduces the sequence, and a decode step passes
+    through without another ``prepare``."""
+    import framefusion_b200.hooks.qwen2_vl as hk
+    monkeypatch.setattr(hk, "scaled_dot_product_attention",
+                        lambda q, k, v, num=1, attn_mask=None, dropout_p=0.0, is_causal=False, scale=None, enable_gqa=False:
+                        port.last_query_attention(q, k, num=num, is_causal=is_causal, scale=scale))
+    from framefusion_b200.interface import apply_framefusion
+    model, inputs, n_tok = tiny_qwen2vl_video()
+    apply_framefusion(model, 0.3, 0.6, 0.1)
+    assert model.forward.__func__ is hk.forward
+    op = RecordingOperator(0.3, 0.6, 0.1)
+    _swap_operator(model, op)
+    with torch.no_grad():
+        out = model(**inputs, use_cache=True)
+    pt, patch_num, start, end, length, orig = op.prepared
+    seq = inputs["input_ids"].shape[1]
+    assert (patch_num, int(start), int(end), length, orig) == (6, 3, 3 + n_tok - 1, n_tok, seq)
+    assert pt.tolist() == [[-1] * 3 + list(range(6)) * 4 + [-1] * 4]
+    assert (model.patch_num, int(model.image_token_start_index), model.image_token_length, model.original_length) == (6, 3, n_tok, seq)
+    assert op.calls and out.logits.shape[1] < seq                                 # the prefill was reduced
+    cache = out.past_key_values
+    assert cache.get_seq_length(0) == seq and cache.get_seq_length(3) == out.logits.shape[1]
+    del op.prepared
+    n_calls = len(op.calls)
+    with torch.no_grad():
+        step = model(input_ids=torch.tensor([[9]]), past_key_values=cache, use_cache=True)
+    assert step.logits.shape[1] == 1 and not hasattr(op, "prepared")
+    assert all(c[0] == 1 for c in op.calls[n_calls:])                             # q_len == 1: the operator is a no-op
+
+
+def test_get_token_type_installs_only_the_embed_patch():
+    """reference interface.py:140-166: the layout is derived and left on the model, the decoder keeps its own forwards; a
+    model that carries a ``mode`` attribute is not prepared (:136)."""
+    import framefusion_b200.hooks.qwen2_vl as hk
+    from framefusion_b200.interface import get_token_type
+    model, inputs, n_tok = tiny_qwen2vl_video()
+    llm_forward = model.model.language_model.forward
+    get_token_type(model)
+    assert model.forward.__func__ is hk.forward and model.model.language_model.forward == llm_forward
+    model.mode = "token_type_only"
+    with torch.no_grad():
+        out = model(**inputs)
+    assert out.logits.shape[1] == inputs["input_ids"].shape[1]                    # dense: nothing was reduced
+    assert (model.patch_num, model.image_token_length) == (6, n_tok)
+    with pytest.raises(NotImplementedError):
+        get_token_type(torch.nn.Linear(2, 2))
+    with pytest.raises(NotImplementedError, match="layout"):
+        get_token_type(tiny_model())                                              # Qwen2: its embed patch is third-party code
+
+
+def test_drop_in_import_path_resolves_to_this_implementation():
+    """reference README.md:123 / example_llava.py:136: ``from framefusion.interface import apply_framefusion``."""
+    import framefusion
+    import framefusion.interface as fi
+    import framefusion.main as fm
+    import framefusion.utils as fu
+    import framefusion.models.qwen2.modeling_qwen2 as q2
+    import framefusion.models.qwen2.modeling_qwen2_vl as q2vl
+    import framefusion.models.qwenvl.modeling_qwen2_vl as qvl
+    import framefusion_b200.interface as bi
+    import framefusion_b200.main as bm
+    assert fi.apply_framefusion is bi.apply_framefusion and fi.replace_framefusion_forward is bi.replace_framefusion_forward
+    assert fi.get_token_type is bi.get_token_type and fm.FrameFusion is bm.FrameFusion and framefusion.FrameFusion is bm.FrameFusion
+    assert fu.TEXT_TOKEN == -1 and fu.IGNORE_TOKEN == -2 and callable(fu.scaled_dot_product_attention) and callable(fu.get_attr_by_name)
+    assert callable(fm.find_contigious_latter_index) and callable(fm.cosine_similarity)
+    for mod, names in ((q2, ("Qwen2Model_merge_then_fastv_cost_given_forward", "Qwen2DecoderLayer_merge_then_prune_by_cost_forward",
+                             "Qwen2SdpaAttention_merge_then_prune_by_cost_forward")),
+                       (q2vl, ("Qwen2VLModel_merge_then_fastv_cost_given_forward", "Qwen2VLDecoderLayer_merge_then_fastv_cost_given_forward",
+                               "Qwen2VLSdpaAttention_merge_then_fastv_cost_given_forward")),
+                       (qvl, ("forward",))):
+        for n in names:
+            assert callable(getattr(mod, n))
+    model = tiny_model()
+    fi.apply_framefusion(model, 0.3, 0.6, 0.1)                                    # the reference's call, unchanged
+    assert type(model.framefusion) is bm.FrameFusion
