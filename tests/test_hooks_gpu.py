@@ -155,3 +155,126 @@ def test_qwen2vl_prefill_matches_oracle_call_by_call():
     assert res.last_hidden_state.shape[1] == calls[-1][1] < wl.seq_len
     assert ff.finish_pruning and any(c[2] for c in calls)
     assert ff.sparsity_list == o.sparsity_list
+
+
+# ---- f2: decode after a reduced prefill, by value ---------------------------------------------------------------------
+class PortOperator(torch.nn.Module):
+    """The reference's op sequence (oracle/ff_torch_port.py, torch ops on the same device) behind the same hooks: the
+    checker for everything downstream of the operator — caches, masks, decode steps."""
+
+    def __init__(self, cost, slb, rlb):
+        super().__init__()
+        from oracle import ff_torch_port as port
+        object.__setattr__(self, "op", port.TorchPortFrameFusion(cost, slb, rlb))
+
+    def prepare(self, *a, **k):
+        self.op.prepare(*a, **k)
+
+    def forward(self, hidden, pos, mask, attn=None):
+        return self.op(hidden.clone(), pos, mask, attn)          # the reference merges in place (main.py:304-317)
+
+    finish_merging = property(lambda s: s.op.finish_merging)
+    finish_pruning = property(lambda s: s.op.finish_pruning)
+    sparsity_list = property(lambda s: s.op.sparsity_list)
+
+
+@pytest.mark.parametrize("lo,hi", [(0.0, 1.0), (0.0, 0.5)], ids=["mixed", "lowsim_prune"])
+def test_prefill_then_decode_logits_match_the_reference_operator_behind_the_same_hooks(lo, hi):
+    """The reference never compacts the KV cache: layer l keeps the keys of the tokens IT saw (modeling_qwen2.py:143-145),
+    so after a reduced prefill the caches are ragged and a decode step attends to a different key set per layer.  Here the
+    hooks leave the cache alone in the same way.  Proof by value: the same weights, once with the CUDA operator and once
+    with the reference's op sequence behind the same hooks, give the same logits for the prefill and for four greedy
+    decode steps, and the same cache contents layer by layer."""
+    from framefusion_b200.interface import apply_framefusion
+    wl = synth.make_workload(10, 24, 256, torch.bfloat16, seed=11, r_lo=lo, r_hi=hi, n_pre=5, n_post=7, rot_dim=64)
+    args = synth.to_device(wl, "cuda").prepare_args()
+    runs = []
+    for kind in ("cuda", "port"):
+        model = tiny_model()                                    # same seed: same weights
+        apply_framefusion(model, cost=0.3, similarity_lower_bound=0.6, ratio_lower_bound=0.1)
+        if kind == "port":
+            op = PortOperator(0.3, 0.6, 0.1)
+            for m in [model, model.model] + list(model.model.layers) + [l.self_attn for l in model.model.layers]:
+                m.framefusion = op
+        ff = model.framefusion
+        logits, tokens = [], []
+        with torch.no_grad():
+            ff.prepare(*[a.clone() if isinstance(a, torch.Tensor) else a for a in args])
+            out = model(inputs_embeds=wl.hidden.cuda(), use_cache=True)
+            cache = out.past_key_values
+            lens = [cache.get_seq_length(i) for i in range(len(model.model.layers))]
+            keys = [cache.layers[i].keys.clone() for i in range(len(model.model.layers))]
+            logits.append(out.logits[:, -1].float().clone())
+            for step in range(4):
+                tok = logits[-1].argmax(-1, keepdim=True)
+                tokens.append(int(tok))
+                out = model(input_ids=tok, past_key_values=cache, use_cache=True)
+                cache = out.past_key_values
+                logits.append(out.logits[:, -1].float().clone())
+        runs.append(dict(lens=lens, keys=keys, logits=logits, tokens=tokens, state=(ff.finish_merging, ff.finish_pruning, list(ff.sparsity_list))))
+    a, b = runs
+    assert a["lens"] == b["lens"] and a["lens"][0] == wl.seq_len > a["lens"][-1]        # ragged, and identical
+    assert a["state"] == b["state"]
+    for i, (ka, kb) in enumerate(zip(a["keys"], b["keys"])):
+        assert torch.equal(ka, kb), f"layer {i}: cached keys differ"
+    assert a["tokens"] == b["tokens"]
+    for i, (la, lb) in enumerate(zip(a["logits"], b["logits"])):
+        assert torch.equal(la, lb), f"logits of step {i} differ (max {float((la - lb).abs().max())})"
+
+
+# ---- f1: the Qwen2-VL embed-stage patch on the GPU ----------------------------------------------------------------------
+def test_qwen2vl_video_prefill_through_the_embed_patch_matches_the_oracle():
+    """``apply_framefusion`` on Qwen2VLForConditionalGeneration installs the top-level forward patch (reference
+    models/qwenvl/modeling_qwen2_vl.py:117-138): the layout comes from ``input_ids`` / ``video_grid_thw``, nobody calls
+    ``prepare`` by hand.  Every operator call of the prefill is checked against the numpy oracle prepared with the layout the
+    reference's formula gives, and the decode step after it passes through."""
+    from transformers import Qwen2VLConfig, Qwen2VLForConditionalGeneration
+    from framefusion_b200.interface import apply_framefusion
+    torch.manual_seed(0)
+    cfg = Qwen2VLConfig(
+        text_config=dict(vocab_size=128, hidden_size=256, intermediate_size=512, num_hidden_layers=5, num_attention_heads=4,
+                         num_key_value_heads=2, max_position_embeddings=4096,
+                         rope_parameters={"rope_type": "default", "mrope_section": [8, 12, 12], "rope_theta": 1e6}),
+        vision_config=dict(depth=1, embed_dim=32, hidden_size=256, num_heads=2, in_channels=3, patch_size=14,
+                           spatial_merge_size=2, temporal_patch_size=2),
+        video_token_id=100, image_token_id=101, vision_start_token_id=102, vision_end_token_id=103)
+    cfg.text_config._attn_implementation = "sdpa"
+    model = Qwen2VLForConditionalGeneration(cfg).eval().to(torch.bfloat16).cuda()
+    apply_framefusion(model, cost=0.3, similarity_lower_bound=0.6, ratio_lower_bound=0.1)
+    ff = model.framefusion
+    t, h, w = 8, 8, 12                                          # 8 frames of 24 tokens
+    n_tok, patch_num = t * h * w // 4, h * w // 4
+    ids = torch.tensor([[1, 2, 3, 4, 102] + [100] * n_tok + [103, 5, 6, 7, 8, 9]], device="cuda")
+    # frames that resemble each other, so that the first layers have something to merge
+    base = torch.randn(h * w, 3 * 2 * 14 * 14)
+    pv = torch.cat([base + 0.05 * f * torch.randn_like(base) for f in range(t)]).to(torch.bfloat16).cuda()
+    seq = ids.shape[1]
+    o = orc.OracleFrameFusion(0.3, 0.6, 0.1, "bf16")
+    want_pt = np.array([[-1] * 5 + list(range(patch_num)) * t + [-1] * 6])
+    o.prepare(want_pt, patch_num, 5, 5 + n_tok - 1, n_tok, seq)
+    calls, inner = [], ff.forward
+
+    def checked(hidden, pos, mask, attn=None):
+        h_in = t2f(hidden[0]); p_in = [t2f(pos[0][:, 0]), t2f(pos[1][:, 0])]
+        a_in = None if attn is None else t2f(attn[0])
+        out = inner(hidden, pos, mask, attn)
+        want_h, want_p, _ = o.forward(h_in, [p[:, None] for p in p_in], None, a_in)
+        fragile = o.last is not None and o.last.get("stage") == "merge" and bool(o.last["sim"].fragile.any())
+        got = t2f(out[0][0])
+        if got.shape == want_h.shape or not fragile:
+            assert np.array_equal(got, want_h), f"call {len(calls)}: hidden_states differ from the oracle"
+        assert (ff.finish_merging, ff.finish_pruning) == (o.finish_merging, o.finish_pruning)
+        calls.append((hidden.shape[1], out[0].shape[1]))
+        return out
+
+    ff.forward = checked
+    with torch.no_grad():
+        out = model(input_ids=ids, pixel_values_videos=pv, video_grid_thw=torch.tensor([[t, h, w]], device="cuda"),
+                    mm_token_type_ids=(ids == 100).int() * 2, use_cache=True)
+    assert torch.equal(ff.patch_type.cpu() if ff.patch_type.shape[1] == seq else torch.tensor(want_pt), torch.tensor(want_pt)) or calls[0][1] < seq
+    assert (model.patch_num, int(model.image_token_start_index), model.image_token_length, model.original_length) == (patch_num, 5, n_tok, seq)
+    assert calls and calls[0][0] == seq and out.logits.shape[1] == calls[-1][1] < seq
+    assert torch.isfinite(out.logits.float()).all()
+    with torch.no_grad():
+        step = model(input_ids=out.logits[:, -1].argmax(-1, keepdim=True), past_key_values=out.past_key_values, use_cache=True)
+    assert step.logits.shape[1] == 1 and torch.isfinite(step.logits.float()).all()
