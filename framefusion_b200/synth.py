@@ -74,7 +74,12 @@ def make_workload(
     n_post: int = 20,
     rot_dim: int = 128,
     device: Optional[torch.device] = None,
+    frozen_patches: int = 0,
+    zero_rows=(),
 ) -> Workload:
+    """``frozen_patches``: the first k patch columns repeat their frame-0 row in every frame (one run over all frames);
+    ``zero_rows``: ``(frame, patch)`` pairs whose row is all zeros (zero norm -> NaN similarity).  Both are
+    applied after the random draws, so the other rows are the same as without them."""
     g = torch.Generator().manual_seed(seed)
     F, P, H = frames, patch_num, hidden
     S = n_pre + F * P + n_post
@@ -84,6 +89,9 @@ def make_workload(
         r = (torch.rand(1, P, generator=g) * (r_hi - r_lo) + r_lo).expand(F, P)
     else:
         r = torch.rand(F, P, generator=g) * (r_hi - r_lo) + r_lo
+    if frozen_patches:
+        r = r.clone()
+        r[:, :frozen_patches] = 1.0
     x = torch.randn(P, H, generator=g)
     for f in range(F):
         if f > 0:
@@ -91,6 +99,8 @@ def make_workload(
             eps = torch.randn(P, H, generator=g)
             x = rf * x + torch.sqrt(1.0 - rf * rf) * eps
         out[n_pre + f * P: n_pre + (f + 1) * P] = x.to(dtype)
+    for (f, p) in zero_rows:
+        out[n_pre + f * P + p] = 0
     out[n_pre + F * P:] = torch.randn(n_post, H, generator=g).to(dtype)
     cos = torch.randn(1, S, rot_dim, generator=g).to(dtype)
     sin = torch.randn(1, S, rot_dim, generator=g).to(dtype)

@@ -301,7 +301,9 @@ def merge_tokens_and_get_mask(hidden: np.ndarray, order: np.ndarray, merge_index
         hidden[arow] = round_to(hidden[arow] + src[order[sel]], dtype)
     anchors = np.unique(anchor[members])
     arow = order[anchors]
-    div = (run_len[anchors] + 1).astype(np.float32)[:, None]
+    # the divisor tensor is cast to T before the division (in-place op on a T tensor, main.py:314-317): exact up to 256
+    # rows in bf16, T(301) = 300 beyond
+    div = round_to((run_len[anchors] + 1).astype(np.float32), dtype)[:, None]
     hidden[arow] = round_to(hidden[arow] / div, dtype)
     return hidden, keep
 

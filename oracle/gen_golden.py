@@ -116,6 +116,11 @@ CASES = {
     "posids2d": dict(wl=_wl(frames=8, patch_num=24, hidden=512, dtype="bf16", seed=7), cost=0.3, slb=0.5, rlb=0.1, calls=4, pos="tensor2d"),
     "mask4d": dict(wl=_wl(frames=6, patch_num=16, hidden=256, dtype="bf16", seed=8, r_lo=0.0, r_hi=0.55), cost=0.3, slb=0.6, rlb=0.15, calls=4, mask=True),
     "oddhidden": dict(wl=_wl(frames=7, patch_num=13, hidden=1000, dtype="bf16", seed=9, n_pre=3, n_post=5), cost=0.4, slb=0.6, rlb=0.1, calls=3),
+    # SURVEY H9 corner cases
+    "H9_run300": dict(wl=_wl(frames=301, patch_num=4, hidden=64, dtype="bf16", seed=20, r_lo=0.0, r_hi=0.5, frozen_patches=1), cost=0.3, slb=0.6, rlb=0.1, calls=1),
+    "H9_zero_thr": dict(wl=_wl(frames=8, patch_num=24, hidden=256, dtype="bf16", seed=21, zero_rows=[[2, 3], [3, 3], [5, 7], [0, 11], [7, 20]]), cost=0.3, slb=0.6, rlb=0.1, calls=2),
+    "H9_zero_topk": dict(wl=_wl(frames=8, patch_num=24, hidden=256, dtype="bf16", seed=22, r_lo=0.8, r_hi=1.0, zero_rows=[[2, 3], [3, 3], [5, 7], [0, 11], [7, 20]]), cost=0.3, slb=0.6, rlb=0.1, calls=1),
+    "H9_topk_sentinels": dict(wl=_wl(frames=8, patch_num=16, hidden=256, dtype="bf16", seed=23), cost=0.05, slb=-2.0, rlb=0.1, calls=1),
     "floatpatchnum": dict(wl=_wl(frames=6, patch_num=20, hidden=384, dtype="bf16", seed=10), cost=0.3, slb=0.6, rlb=0.1, calls=2, patch_num_float=True),
 }
 
