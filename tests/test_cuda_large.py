@@ -13,15 +13,15 @@ pytestmark = pytest.mark.gpu
 
 
 def drive(frames, patches, hidden, lo, hi, fused, drift=0.0, cost=0.3, max_calls=6, per_patch_r=False, n_pre=14, n_post=20,
-          dtype=torch.bfloat16):
+          dtype=torch.bfloat16, slb=0.6, frozen_patches=0, zero_rows=()):
     from framefusion_b200.main import FrameFusion
     wl = synth.make_workload(frames, patches, hidden, dtype, seed=9, r_lo=lo, r_hi=hi, per_patch_r=per_patch_r,
-                             n_pre=n_pre, n_post=n_post)
+                             n_pre=n_pre, n_post=n_post, frozen_patches=frozen_patches, zero_rows=zero_rows)
     assert wl.seq_len >= 2048
-    ff = FrameFusion(cost, 0.6, 0.1)
+    ff = FrameFusion(cost, slb, 0.1)
     ff.use_fused = fused
     ff.prepare(*synth.to_device(wl, "cuda").prepare_args())
-    o = orc.OracleFrameFusion(cost, 0.6, 0.1, {torch.bfloat16: "bf16", torch.float16: "f16", torch.float32: "f32"}[dtype])
+    o = orc.OracleFrameFusion(cost, slb, 0.1, {torch.bfloat16: "bf16", torch.float16: "f16", torch.float32: "f32"}[dtype])
     o.prepare(wl.patch_type.numpy(), wl.patch_num, *wl.prepare_args()[2:])
     h, pos = wl.hidden.cuda(), [wl.cos.cuda(), wl.sin.cuda()]
     stages = []
@@ -218,3 +218,40 @@ def test_4d_mask_is_compacted_at_scale():
         assert np.array_equal(t2f(h[0]), want_h), f"call {c}: hidden_states differ"
         assert m.shape == (1, 1, want_m.shape[0], want_m.shape[1]) and np.array_equal(t2f(m[0, 0]), want_m), f"call {c}: mask differs"
     assert "merge" in stages and stages[-1] == "prune"
+
+
+# ---- SURVEY H9 corner cases on the multi-block kernels (the small-sequence kernels see them through the fixtures
+# case_H9_*.npz generated from the unmodified reference) ------------------------------------------------------------
+@pytest.mark.parametrize("fused", [False, True], ids=["two_pass", "single_pass"])
+def test_h9_run_longer_than_256_rows(fused):
+    """One chain is identical in all 301 frames: a run of 300 members behind its anchor.  The sum stalls once the
+    accumulator outgrows the member (each add is rounded to T), and the divisor is T(301) = 300 in bf16 — the in-place
+    division casts it (main.py:314-317).  300 is a length bf16 holds exactly; lengths it cannot hold (257, 259 ..) make the
+    reference itself misplace the anchor (its run-length tensor is kept in the hidden dtype, main.py:269-274), so there is
+    nothing to match beyond this."""
+    stages = drive(301, 8, 256, 0.0, 0.5, fused, frozen_patches=2, max_calls=1)
+    assert stages == ["threshold"]
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["two_pass", "single_pass"])
+def test_h9_zero_norm_rows_threshold_branch(fused):
+    """All-zero rows: 0 / 0 = NaN similarity on both sides of the row; NaN >= threshold is false (kept, main.py:113)."""
+    zr = [(f, p) for f in (0, 3, 4, 17, 31) for p in (0, 5, 143)]
+    stages = drive(32, 144, 512, 0.0, 1.0, fused, zero_rows=zr, max_calls=2)
+    assert stages[0] == "threshold"
+
+
+def test_h9_zero_norm_rows_topk_branch():
+    """torch.topk ranks NaN above every number (main.py:122): the rows next to a zero row are merged first."""
+    zr = [(f, p) for f in (1, 3, 4, 17, 23) for p in (0, 5, 127)]
+    stages = drive(24, 128, 512, 0.8, 1.0, False, zero_rows=zr, max_calls=1)
+    assert stages == ["topk"]
+
+
+def test_h9_topk_reaches_the_sentinels_and_wraps():
+    """similarity_lower_bound = -2 lets the chain heads (sim = -2, main.py:225-238) count, the ratio is 1 and the top-k
+    branch asks for k = int(0.95 N) > N - P positions: it takes chain heads too (all tied at -2: lowest index first, what
+    torch-CUDA does), and the head at by-patch position 0 merges into anchor index -1 = the LAST by-patch position
+    (main.py:290, 306)."""
+    stages = drive(24, 128, 512, 0.0, 1.0, False, cost=0.05, slb=-2.0, max_calls=1)
+    assert stages == ["topk"]

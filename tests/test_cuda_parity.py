@@ -200,3 +200,107 @@ def test_kernel_events_hook_times_the_library_side_launches():
     ff.prepare(*wl.prepare_args())
     h2, _pos, _m = ff(wl.hidden, [wl.cos, wl.sin], None)               # the hook off again: same result, no events touched
     assert torch.equal(h, h2)
+
+
+# ---- importance -> prune, end to end at full size ------------------------------------------------------------------------
+def test_importance_to_prune_selection_at_full_size():
+    """q / K -> ff_importance -> head mean -> top-k at C2's post-merge length (S = 22 290, k = 30 % of the vision rows):
+    the retained index set against the reference's arithmetic (utils.py:27-57 -> main.py:69-92, restated in the oracle and
+    pinned by tests/golden/importance.npz).  The selection kernel must reproduce the oracle's choice exactly on the GPU's
+    own importance; against the reference's importance every differing index must be explained by one of two causes:
+    a tie at the k-th value (torch.topk leaves the choice among equal values open) or a probability that differs by one
+    ulp of T and sits next to the k-th value."""
+    from framefusion_b200 import synth
+    from framefusion_b200.main import FrameFusion
+    from framefusion_b200.utils import scaled_dot_product_attention
+    S, n_pre, n_post, H = 22290, 14, 20, 256
+    length = S - n_pre - n_post
+    q, k = synth.make_attention_inputs(S, 28, 4, 128, torch.bfloat16, seed=3)
+    q_last = q[:, :, -1:, :].contiguous()
+    gpu_attn = scaled_dot_product_attention(q_last.cuda(), k.cuda(), None, num=1, is_causal=True, enable_gqa=True)
+    assert gpu_attn.shape == (1, 28, 1, S)
+    ref_attn = orc.last_query_attention(t2f(q[0]), t2f(k[0]), 1, "bf16", is_causal=True)            # [28, 1, S]
+    got_attn = t2f(gpu_attn[0])
+    ulp = np.abs(got_attn.view(np.int32) - ref_attn.view(np.int32)) >> 16                           # bf16 steps (same sign: probabilities)
+    assert ulp.max() <= 1
+    n_ulp = int((ulp != 0).sum())
+    # the operator on the GPU's importance
+    g = torch.Generator().manual_seed(5)
+    hidden = torch.randn(1, S, H, generator=g).to(torch.bfloat16).cuda()
+    pos = [torch.randn(1, S, 128, generator=g).to(torch.bfloat16).cuda() for _ in range(2)]
+    pt = torch.tensor([[-1] * n_pre + [i % 576 for i in range(length)] + [-1] * n_post])
+    ff = FrameFusion(0.3, 0.6, 0.1)
+    ff.debug_trace = True
+    ff.prepare(pt.cuda(), 576, n_pre, n_pre + length - 1, length, S, finish_merging=True)
+    out, _pos, _ = ff(hidden, pos, None, gpu_attn)
+    keep_gpu = ff.last_trace["keep"]
+    ratio = orc.compute_pruning_ratio([], 0.3)
+    kk = round(length * (1 - ratio))
+    imp_gpu = orc.mean_heads(got_attn, "bf16")
+    keep_same_input = orc.prune_keep_indices(imp_gpu, n_pre, length, S, ratio)
+    assert np.array_equal(keep_gpu, keep_same_input), "selection differs from the oracle on identical importance"
+    assert out.shape[1] == n_pre + kk + n_post
+    # against the reference's importance
+    imp_ref = orc.mean_heads(ref_attn, "bf16")
+    keep_ref = orc.prune_keep_indices(imp_ref, n_pre, length, S, ratio)
+    diff = np.setxor1d(keep_gpu, keep_ref)
+    vis = imp_ref[n_pre:n_pre + length]
+    kth = np.sort(vis)[::-1][kk - 1]
+    tie = imp_ref[diff] == kth
+    moved = imp_gpu[diff] != imp_ref[diff]
+    # a row whose own value did not move and is not tied can only change sides because a neighbour in the ranking did
+    pushed = ~tie & ~moved
+    n_tied_total = int((vis == kth).sum())
+    print(f"S={S} k={kk}: probabilities differing by 1 bf16 ulp {n_ulp} of {ulp.size}; mean-importance values differing "
+          f"{int((imp_gpu != imp_ref).sum())} of {S}; retained indices differing {diff.size} "
+          f"(tie at the k-th value: {int(tie.sum())} of {n_tied_total} tied rows, own value moved by one ulp: {int((~tie & moved).sum())}, "
+          f"displaced by those: {int(pushed.sum())})")
+    one_step = np.abs(imp_gpu.view(np.int32) - imp_ref.view(np.int32)) >> 16
+    assert one_step.max() <= 1
+    assert np.all(np.abs(imp_ref[diff].view(np.int32) - kth.view(np.int32)) >> 16 <= 1), "a differing index is not next to the k-th value"
+    assert diff.size <= 2 * (n_tied_total + int((imp_gpu != imp_ref).sum()))
+
+
+# ---- the whole bench step at full size --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", ["C2", "C3", "C4"])
+def test_full_step_against_oracle(cfg):
+    """Every call of the bench step — merge, merge (closes merging), importance, prune — at the BASELINE sizes, CUDA against
+    the numpy oracle call by call on identical bits (the oracle gets the GPU's importance: the step above pins that)."""
+    from framefusion_b200 import synth
+    from framefusion_b200.main import FrameFusion
+    from framefusion_b200.utils import scaled_dot_product_attention
+    c = synth.CONFIGS[cfg]
+    wl = synth.make_workload(c["frames"], c["patch_num"], c["hidden"], c["dtype"], seed=0)
+    q, k = synth.make_attention_inputs(wl.seq_len, 28, 4, 128, c["dtype"], seed=0)
+    q_last, k = q[:, :, -1:, :].contiguous().cuda(), k.cuda()
+    ff = FrameFusion(c["cost"], c["slb"], c["rlb"])
+    ff.debug_trace = True
+    ff.prepare(*synth.to_device(wl, "cuda").prepare_args())
+    o = orc.OracleFrameFusion(c["cost"], c["slb"], c["rlb"], "bf16")
+    o.prepare(wl.patch_type.numpy(), wl.patch_num, *wl.prepare_args()[2:])
+    h, pos = wl.hidden.cuda(), [wl.cos.cuda(), wl.sin.cuda()]
+    stages = []
+    for call in range(8):
+        if ff.finish_merging and ff.finish_pruning:
+            break
+        attn = None
+        if ff.finish_merging:
+            attn = scaled_dot_product_attention(q_last, k[:, :, :h.shape[1]], None, num=1, is_causal=True, enable_gqa=True)
+        h_in, p_in = t2f(h[0]), [t2f(pos[0][0]), t2f(pos[1][0])]
+        h, pos, _ = ff(h, pos, None, attn)
+        want_h, want_p, _ = o.forward(h_in, p_in, None, None if attn is None else t2f(attn[0]))
+        stage = o.last["stage"]
+        stages.append(stage)
+        if stage == "merge":
+            sr, got_sim = o.last["sim"], ff.last_trace["sim_values"]
+            neq = got_sim != sr.sim
+            assert not (neq & ~sr.fragile).any() and ((got_sim >= sr.lo) & (got_sim <= sr.hi))[neq].all()
+            thr = orc.threshold_in_dtype(c["slb"], "bf16")
+            assert int(((got_sim >= thr) != (sr.sim >= thr)).sum()) == 0, "a fragile similarity crossed the threshold: pick another seed"
+        assert h.shape[1] == want_h.shape[0], f"{cfg} call {call} ({stage}): kept {h.shape[1]}, oracle {want_h.shape[0]}"
+        assert np.array_equal(t2f(h[0]), want_h), f"{cfg} call {call} ({stage}): hidden_states differ"
+        assert np.array_equal(t2f(pos[0][0]), want_p[0]) and np.array_equal(t2f(pos[1][0]), want_p[1])
+        assert (ff.finish_merging, ff.finish_pruning) == (o.finish_merging, o.finish_pruning)
+        assert ff.sparsity_list == o.sparsity_list
+    assert stages[0] == "merge" and stages[-1] == "prune", stages
+    print(f"{cfg}: S {wl.seq_len} -> {h.shape[1]} through {stages}")
