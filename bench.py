@@ -253,13 +253,149 @@ def whole_job_throughput(n_tokens, steps, ms, world):
 
 
 # --------------------------------------------------------------------------------------------------
+# BASELINE config 5: prefill of a random-init LLaVA-Video-7B-shape decoder, layers split over the GPUs of one box
+# --------------------------------------------------------------------------------------------------
+def prefill_c5(args, rank, world):
+    """``--workload C5``: Qwen2 decoder of the LLaVA-Video-7B shape (28 layers, hidden 3584, 28 heads / 4 KV heads, MLP
+    18 944, bf16, sdpa), random weights, input = the C2 synthetic video embeddings; ``apply_framefusion`` installs the hooks.
+    The reference shards this model by LAYERS (``device_map="auto"``): one process, contiguous layer blocks on the GPUs,
+    activations hop at the block boundaries (``framefusion_b200/dispatch.py``); no collective.  Under ``torch.distributed.run``
+    rank 0 alone drives all ``--gpus`` devices and the other ranks exit.  A step is one prefill.  Both operators run in the
+    same process on the same weights: this repository's, and the reference's op sequence in torch ops behind the same hooks
+    (``oracle/ff_torch_port.py`` — the reference's own hooks do not import under transformers 5.x), which is the
+    ``--impl reference`` arm of this workload."""
+    if rank != 0:
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    n_dev = min(args.gpus, torch.cuda.device_count())
+    devices = [torch.device("cuda", k) for k in range(n_dev)]
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+    from framefusion_b200 import _lib
+    from framefusion_b200.interface import apply_framefusion
+    from framefusion_b200.dispatch import split_layers
+    import framefusion_b200.hooks.qwen2 as hk
+    from oracle import ff_torch_port as port
+    lib = _lib.load()
+    c = synth.CONFIGS["C2"]
+    mcfg = Qwen2Config(vocab_size=152064, hidden_size=3584, intermediate_size=18944, num_hidden_layers=args.layers,
+                       num_attention_heads=N_HEADS, num_key_value_heads=N_KV_HEADS, max_position_embeddings=131072, rope_theta=1e6)
+    mcfg._attn_implementation = "sdpa"
+    torch.manual_seed(0)
+    with torch.device(devices[0]):
+        model = Qwen2ForCausalLM(mcfg).to(torch.bfloat16).eval()
+    llm = model.model
+    apply_framefusion(model, cost=c["cost"], similarity_lower_bound=c["slb"], ratio_lower_bound=c["rlb"])
+    ours = model.framefusion
+    if n_dev > 1:
+        split_layers(llm, devices)
+    holders = [model, llm] + list(llm.layers) + [l.self_attn for l in llm.layers]
+
+    class TorchOperator(torch.nn.Module):                    # the port behind the attribute surface the hooks read
+        def __init__(self):
+            super().__init__()
+            object.__setattr__(self, "p", port.TorchPortFrameFusion(c["cost"], c["slb"], c["rlb"]))
+            self.p.trace = False
+
+        def prepare(self, *a):
+            self.p.prepare(*a)
+
+        def forward(self, h, pos, mask, attn=None):
+            return self.p(h, pos, mask, attn)
+
+        finish_merging = property(lambda s: s.p.finish_merging)
+        finish_pruning = property(lambda s: s.p.finish_pruning)
+        sparsity_list = property(lambda s: s.p.sparsity_list)
+
+    ours_sdpa = hk.scaled_dot_product_attention
+    port_sdpa = lambda q, k, v, num=1, attn_mask=None, dropout_p=0.0, is_causal=False, scale=None, enable_gqa=False: \
+        port.last_query_attention(q, k, num=num, is_causal=is_causal, scale=scale)
+
+    def use(op, sdpa):
+        for m in holders:
+            m.framefusion = op
+        hk.scaled_dot_product_attention = sdpa
+
+    wl = synth.make_workload(c["frames"], c["patch_num"], c["hidden"], c["dtype"], seed=0)
+    host_embeds = wl.hidden.pin_memory()
+    embeds = host_embeds.to(devices[0])
+    pt = wl.patch_type.to(devices[0])
+
+    def sync_all():
+        for d in devices:
+            torch.cuda.synchronize(d)
+
+    def prefill(op, e2e=False):
+        x = host_embeds.to(devices[0], non_blocking=True) if e2e else embeds
+        op.prepare(pt, wl.patch_num, wl.n_pre, wl.n_pre + wl.n_vision - 1, wl.n_vision, wl.seq_len)
+        with torch.no_grad():
+            out = llm(inputs_embeds=x, use_cache=True)
+        kept = out.last_hidden_state.shape[1]
+        last = out.last_hidden_state[:, -1].float().cpu() if e2e else None      # the row the LM head would read
+        return kept, last
+
+    def timed(op, steps, warm, e2e=False):
+        for _ in range(warm):
+            prefill(op, e2e)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            kept, _ = prefill(op, e2e)
+        sync_all()
+        return (time.perf_counter() - t0) / steps * 1e3, kept
+
+    steps, warm = max(1, min(args.steps, 10)), max(1, min(args.warmup, 3))
+    res = {}
+    if args.impl == "b200":
+        use(ours, ours_sdpa)
+        l0 = lib.ff_launch_count()
+        with ClockSampler(0) as clk:
+            ms, kept = timed(ours, steps, warm)
+        launches = lib.ff_launch_count() - l0
+        ms_e2e, _ = timed(ours, max(1, steps // 2), 1, e2e=True)
+        res["ours"] = (ms, kept)
+    use(TorchOperator(), port_sdpa)
+    ms_t, kept_t = timed(holders[0].framefusion, steps if args.impl == "reference" else max(1, steps // 2), warm)
+    res["torch"] = (ms_t, kept_t)
+    use(ours, ours_sdpa)
+
+    metric = "prefill tokens/sec, random-init LLaVA-Video-7B-shape decoder with the FrameFusion hooks (BASELINE config 5)"
+    config = {"workload": f"C5: {args.layers}-layer Qwen2 decoder (hidden 3584, 28/4 heads, MLP 18944) on the C2 video embeddings "
+                          f"({c['frames']} frames x {c['patch_num']} tokens), cost={c['cost']}",
+              "seq_len": wl.seq_len, "parallelism": f"layer split over {n_dev} GPU(s), one process (rank 0) drives them all",
+              "l2": "weights (15 GB) and activations exceed the L2; no explicit flush"}
+    if args.impl == "reference":
+        line = {"impl": "reference", "metric": metric, "value": wl.seq_len / (ms_t * 1e-3), "unit": "tokens/s", "n_gpus": n_dev,
+                "steps": steps, "warmup": warm, "ms_per_step": ms_t, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+                "tokens_after_last_layer": kept_t,
+                "note": "reference torch path: the reference's op sequence (oracle/ff_torch_port.py, torch-CUDA) behind the same hooks"}
+    else:
+        ms, kept = res["ours"]
+        line = {"metric": metric, "value": wl.seq_len / (ms * 1e-3), "unit": "tokens/s", "n_gpus": n_dev, "steps": steps,
+                "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic", "config": config, "tokens_after_last_layer": kept,
+                "e2e": {"value": wl.seq_len / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": host_embeds.numel() * host_embeds.element_size(), "d2h_bytes_per_step": 3584 * 4},
+                "reference_torch_path": {"value": wl.seq_len / (ms_t * 1e-3), "unit": "tokens/s", "ms_per_step": ms_t,
+                                         "tokens_after_last_layer": kept_t,
+                                         "what": "the reference's op sequence (oracle/ff_torch_port.py, torch-CUDA) behind the same hooks, same weights, same run"},
+                "speedup_vs_reference_torch_path": ms_t / ms,
+                "gpu_launches": int(launches), "clocks": clk.summary()}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(synth.CONFIGS))
+    ap.add_argument("--workload", default="C2", choices=sorted(synth.CONFIGS) + ["C5"],
+                    help="C2 (default), C3, C4: the operator step on that shape; C5: BASELINE config 5, prefill of a random-init "
+                         "LLaVA-Video-7B-shape decoder with the hooks installed, layers split over --gpus GPUs")
+    ap.add_argument("--layers", type=int, default=28, help="C5: decoder layers (28 = the 7B shape)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--torch-gpu-port", action="store_true", help="also time the torch port of the reference on this GPU")
     args = ap.parse_args()
@@ -267,6 +403,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cfg = args.workload
+    if cfg == "C5":
+        prefill_c5(args, rank, world)
+        return
     if args.impl == "reference":
         reference_arm(args, cfg, rank, world)
         return

@@ -278,3 +278,31 @@ def test_qwen2vl_video_prefill_through_the_embed_patch_matches_the_oracle():
     with torch.no_grad():
         step = model(input_ids=out.logits[:, -1].argmax(-1, keepdim=True), past_key_values=out.past_key_values, use_cache=True)
     assert step.logits.shape[1] == 1 and torch.isfinite(step.logits.float()).all()
+
+
+# ---- config 5: the decoder split by layers over two GPUs -------------------------------------------------------------
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (the driver's 1-GPU tier skips it)")
+def test_layer_split_over_two_gpus_matches_one_gpu():
+    """``dispatch.split_layers``: the same weights on one GPU and split over two give the same reduced prefill — the
+    operator keeps a context and a workspace per device, rebuilds its chain links where the sequence changes device, and the
+    importance / prune stages run wherever their layer lives."""
+    from framefusion_b200.interface import apply_framefusion
+    from framefusion_b200.dispatch import split_layers
+    wl = synth.make_workload(10, 24, 256, torch.bfloat16, seed=11, r_lo=0.0, r_hi=0.5, n_pre=5, n_post=7, rot_dim=64)
+    outs = []
+    for devices in (["cuda:0"], ["cuda:0", "cuda:1"]):
+        model = tiny_model()
+        apply_framefusion(model, cost=0.3, similarity_lower_bound=0.6, ratio_lower_bound=0.1)
+        if len(devices) > 1:
+            placement = split_layers(model.model, devices)
+            assert {str(d) for d in placement} == {"cuda:0", "cuda:1"}
+        ff = model.framefusion
+        with torch.no_grad():
+            ff.prepare(*synth.to_device(wl, "cuda:0").prepare_args())
+            res = model.model(inputs_embeds=wl.hidden.to("cuda:0"), use_cache=True)
+        outs.append((res.last_hidden_state.cpu(), list(ff.sparsity_list), ff.finish_merging, ff.finish_pruning,
+                     [res.past_key_values.get_seq_length(i) for i in range(len(model.model.layers))]))
+        assert torch.cuda.current_device() == 0                 # the entry points restore the caller's device
+    a, b = outs
+    assert a[1:] == b[1:]
+    assert torch.equal(a[0], b[0])
