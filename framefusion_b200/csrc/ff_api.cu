@@ -723,18 +723,45 @@ int ff_importance(ff_ctx* ctx, const void* q, const void* k, int dtype, int64_t 
     const int64_t eb = dtype == FF_F32 ? 4 : 2;
     // the fast path: K rows of 16-byte vectors, four lanes per row with a whole number of vectors each
     const bool vec = (D * eb) % (16 * IMP_LANES) == 0 && ((uintptr_t)k & 15) == 0 && (k_hs * eb) % 16 == 0 && (k_ss * eb) % 16 == 0;
-    dim3 grid(vec ? (unsigned)((S + IMP_KEYS - 1) / IMP_KEYS) : (unsigned)((S + IMP_THREADS - 1) / IMP_THREADS), (unsigned)Hk);
+    // tensor-core path: 16-bit elements, head_dim a multiple of 32, rows the 16-byte loads can take
+    const bool mma = vec && dtype != FF_F32 && D % 32 == 0 && D <= IMP_MMA_MAX_D && ((uintptr_t)q & 1) == 0;
+    dim3 grid(mma ? (unsigned)((S + IMP_MMA_KEYS - 1) / IMP_MMA_KEYS)
+                  : (vec ? (unsigned)((S + IMP_KEYS - 1) / IMP_KEYS) : (unsigned)((S + IMP_THREADS - 1) / IMP_THREADS)), (unsigned)Hk);
     int rc = dispatch_dtype(dtype, [&](auto dt) {
         constexpr int DT = decltype(dt)::value;
+        if (mma) {
+            constexpr int DM = DT == FF_F32 ? FF_BF16 : DT;  // (never taken for f32; keeps the instantiation set small)
+            const size_t sm = (size_t)((group * num + 7) / 8 * 8) * (D + IMP_MMA_PAD) * 2;
+            auto go = [&](auto nj) {
+                constexpr int NJ = decltype(nj)::value;
+                if (sm > 48 * 1024) FF_CUDA(cudaFuncSetAttribute(k_importance_logits_mma<DM, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                FF_LAUNCH("k_importance_logits_mma", (k_importance_logits_mma<DM, NJ>), grid, IMP_THREADS, sm, st, q, k, (int)Hq, (int)Hk,
+                          (int)S, (int)num, q_hs, q_ss, k_hs, k_ss, is_causal, (float)scale, (float*)scratch);
+                return (int)FF_OK;
+            };
+            int r2;
+            switch (D / 32) {
+                case 1: r2 = go(std::integral_constant<int, 1>()); break;
+                case 2: r2 = go(std::integral_constant<int, 2>()); break;
+                case 3: r2 = go(std::integral_constant<int, 3>()); break;
+                case 4: r2 = go(std::integral_constant<int, 4>()); break;
+                case 6: r2 = go(std::integral_constant<int, 6>()); break;
+                case 8: r2 = go(std::integral_constant<int, 8>()); break;
+                default: r2 = -1;
+            }
+            if (r2 > 0) return r2;
+            if (r2 == 0) goto softmax;
+        }
         if (vec) {
             if (smem > 48 * 1024) FF_CUDA(cudaFuncSetAttribute(k_importance_logits<DT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            FF_LAUNCH("k_importance_logits", (k_importance_logits<DT, true>), grid, IMP_THREADS, smem, st, q, k, (int)Hq, (int)Hk,
+            FF_LAUNCH("k_importance_logits", (k_importance_logits<DT, true>), dim3(vec ? (unsigned)((S + IMP_KEYS - 1) / IMP_KEYS) : 1, (unsigned)Hk), IMP_THREADS, smem, st, q, k, (int)Hq, (int)Hk,
                       (int)S, (int)D, (int)num, q_hs, q_ss, k_hs, k_ss, is_causal, (float)scale, (float*)scratch);
         } else {
             if (smem > 48 * 1024) FF_CUDA(cudaFuncSetAttribute(k_importance_logits<DT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            FF_LAUNCH("k_importance_logits", (k_importance_logits<DT, false>), grid, IMP_THREADS, smem, st, q, k, (int)Hq, (int)Hk,
+            FF_LAUNCH("k_importance_logits", (k_importance_logits<DT, false>), dim3((unsigned)((S + IMP_THREADS - 1) / IMP_THREADS), (unsigned)Hk), IMP_THREADS, smem, st, q, k, (int)Hq, (int)Hk,
                       (int)S, (int)D, (int)num, q_hs, q_ss, k_hs, k_ss, is_causal, (float)scale, (float*)scratch);
         }
+    softmax:
         FF_LAUNCH("k_softmax_rows", k_softmax_rows<DT>, (int)(Hq * num) * SOFTMAX_CLUSTER, 1024, 0, st, (const float*)scratch, (int)S, probs_out);
         return (int)FF_OK;
     });

@@ -113,6 +113,81 @@ k_importance_logits(const void* __restrict__ q, const void* __restrict__ k, int 
     }
 }
 
+// The same logits on the tensor cores (bf16 / f16, head_dim a multiple of 32 up to IMP_MMA_MAX_D): per KV head the logits are
+// K [S x D] times the group's queries [D x group*num] — "a bf16 matmul with float32 accumulation, rounded once to T", which
+// is what the reference's matmul is.  A warp owns 16 keys: every lane fetches its two rows' pieces with 16-byte loads, all in
+// flight at once (the whole 4 KB tile is one round trip), and feeds them to mma.sync m16n8k16 as they lie: the k index of a
+// dot product may be permuted freely as long as both operands agree, so the eight consecutive elements a lane holds serve as
+// the fragment columns {2c, 2c+1, 2c+8, 2c+9} of two k-steps, and the queries are read from shared memory in the same order.
+// Replaces a kernel whose duration was the dependent load / FMA chain of one warp (25 us at S = 22 290 for 23 MB).
+constexpr int IMP_MMA_KEYS = 16 * (IMP_THREADS / 32);     // keys per block
+constexpr int IMP_MMA_MAX_D = 256;
+constexpr int IMP_MMA_PAD = 8;                            // elements between query rows in shared memory (bank spread)
+
+template <int DT>
+__device__ __forceinline__ void mma_16x8x16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    if (DT == FF_BF16)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int DT, int NJ>                                 // NJ = D / 32
+__global__ void __launch_bounds__(IMP_THREADS)
+k_importance_logits_mma(const void* __restrict__ q, const void* __restrict__ k, int n_q_heads, int n_kv_heads, int S, int num,
+                        int64_t q_hs, int64_t q_ss, int64_t k_hs, int64_t k_ss, int is_causal, float scale,
+                        float* __restrict__ logits /* [Hq, num, S] float32 holding T values */) {
+    pdl_enter();
+    extern __shared__ __align__(16) uint16_t s_qh[];       // [GLpad][D + IMP_MMA_PAD] raw 16-bit elements
+    constexpr int D = NJ * 32, ROW = D + IMP_MMA_PAD;
+    const int hk = blockIdx.y, group = n_q_heads / n_kv_heads, L = num, GL = group * L, GLpad = (GL + 7) / 8 * 8;
+    const uint16_t* q16 = (const uint16_t*)q;
+    for (int idx = threadIdx.x; idx < GLpad * D; idx += blockDim.x) {
+        const int d = idx % D, gr = idx / D;
+        uint16_t v = 0;
+        if (gr < GL) v = q16[(int64_t)(hk * group + gr / L) * q_hs + (int64_t)(S - L + gr % L) * q_ss + d];
+        s_qh[gr * ROW + d] = v;
+    }
+    const int lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+    const int key0 = (blockIdx.x * (IMP_THREADS / 32) + (threadIdx.x >> 5)) * 16;
+    const int s0 = key0 + g, s1 = s0 + 8;
+    const char* r0 = (const char*)((const uint16_t*)k + (int64_t)hk * k_hs + (int64_t)min(s0, S - 1) * k_ss) + c * 16;
+    const char* r1 = (const char*)((const uint16_t*)k + (int64_t)hk * k_hs + (int64_t)min(s1, S - 1) * k_ss) + c * 16;
+    uint4 lo[NJ], hi[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        lo[j] = ldg16(r0 + j * 64);
+        hi[j] = ldg16(r1 + j * 64);
+    }
+    __syncthreads();
+    if (key0 >= S) return;
+#pragma unroll 1
+    for (int nt = 0; nt < GLpad; nt += 8) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint16_t* qrow = s_qh + (nt + g) * ROW + c * 8;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const uint4 b = *reinterpret_cast<const uint4*>(qrow + j * 32);
+            mma_16x8x16<DT>(acc, lo[j].x, hi[j].x, lo[j].y, hi[j].y, b.x, b.y);
+            mma_16x8x16<DT>(acc, lo[j].z, hi[j].z, lo[j].w, hi[j].w, b.z, b.w);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int n = nt + 2 * c + (e & 1), s = (e & 2) ? s1 : s0;
+            if (n < GL && s < S) {
+                const int r = n % L, h = hk * group + n / L;
+                float x = Num<DT>::rnd(acc[e]);             // matmul output in T
+                x = Num<DT>::rnd(x * scale);                // * scale_factor
+                const float bias = (is_causal && s > S - L + r) ? -INFINITY : 0.f;
+                x = Num<DT>::rnd(x + bias);                 // += attn_bias
+                logits[((int64_t)h * L + r) * S + s] = x;
+            }
+        }
+    }
+}
+
 // One thread-block CLUSTER of four CTAs per (head, query) row: each CTA owns a quarter of the row, keeps it in registers
 // between the passes when it fits, and the four partial maxima / sums meet through distributed shared memory (two
 // cluster barriers instead of a second kernel or 28 lonely blocks on 148 SMs).  The partial sums are added in rank order,
