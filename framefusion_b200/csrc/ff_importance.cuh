@@ -143,13 +143,7 @@ k_importance_logits_mma(const void* __restrict__ q, const void* __restrict__ k, 
     extern __shared__ __align__(16) uint16_t s_qh[];       // [GLpad][D + IMP_MMA_PAD] raw 16-bit elements
     constexpr int D = NJ * 32, ROW = D + IMP_MMA_PAD;
     const int hk = blockIdx.y, group = n_q_heads / n_kv_heads, L = num, GL = group * L, GLpad = (GL + 7) / 8 * 8;
-    const uint16_t* q16 = (const uint16_t*)q;
-    for (int idx = threadIdx.x; idx < GLpad * D; idx += blockDim.x) {
-        const int d = idx % D, gr = idx / D;
-        uint16_t v = 0;
-        if (gr < GL) v = q16[(int64_t)(hk * group + gr / L) * q_hs + (int64_t)(S - L + gr % L) * q_ss + d];
-        s_qh[gr * ROW + d] = v;
-    }
+    // the K tile first: its 2 * NJ loads per lane travel while the queries are staged
     const int lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
     const int key0 = (blockIdx.x * (IMP_THREADS / 32) + (threadIdx.x >> 5)) * 16;
     const int s0 = key0 + g, s1 = s0 + 8;
@@ -160,6 +154,13 @@ k_importance_logits_mma(const void* __restrict__ q, const void* __restrict__ k, 
     for (int j = 0; j < NJ; ++j) {
         lo[j] = ldg16(r0 + j * 64);
         hi[j] = ldg16(r1 + j * 64);
+    }
+    const uint16_t* q16 = (const uint16_t*)q;
+    for (int idx = threadIdx.x; idx < GLpad * D; idx += blockDim.x) {
+        const int d = idx % D, gr = idx / D;
+        uint16_t v = 0;
+        if (gr < GL) v = q16[(int64_t)(hk * group + gr / L) * q_hs + (int64_t)(S - L + gr % L) * q_ss + d];
+        s_qh[gr * ROW + d] = v;
     }
     __syncthreads();
     if (key0 >= S) return;

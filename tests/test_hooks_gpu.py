@@ -159,19 +159,25 @@ def test_qwen2vl_prefill_matches_oracle_call_by_call():
 
 # ---- f2: decode after a reduced prefill, by value ---------------------------------------------------------------------
 class PortOperator(torch.nn.Module):
-    """The reference's op sequence (oracle/ff_torch_port.py, torch ops on the same device) behind the same hooks: the
-    checker for everything downstream of the operator — caches, masks, decode steps."""
+    """The reference's op sequence (oracle/ff_torch_port.py) behind the same hooks: the checker for everything downstream of
+    the operator — caches, masks, decode steps.  It runs on the CPU, where the reference's arithmetic is defined (torch-CUDA
+    adds the members of a run with atomics in no fixed order and reduces the similarity sums in another order: the same
+    ops give slightly different merged rows there); the tensors hop to the host and back around every call."""
 
     def __init__(self, cost, slb, rlb):
         super().__init__()
         from oracle import ff_torch_port as port
         object.__setattr__(self, "op", port.TorchPortFrameFusion(cost, slb, rlb))
 
-    def prepare(self, *a, **k):
-        self.op.prepare(*a, **k)
+    def prepare(self, patch_type, *a, **k):
+        self.op.prepare(patch_type.cpu(), *[x.cpu() if isinstance(x, torch.Tensor) else x for x in a], **k)
 
     def forward(self, hidden, pos, mask, attn=None):
-        return self.op(hidden.clone(), pos, mask, attn)          # the reference merges in place (main.py:304-317)
+        dev = hidden.device
+        cpu = lambda x: None if x is None else x.cpu()
+        h, p, m = self.op(hidden.cpu(), [cpu(pos[0]), cpu(pos[1])], cpu(mask), cpu(attn))
+        pos[0], pos[1] = p[0].to(dev), p[1].to(dev)              # the hooks hand the same list from layer to layer
+        return h.to(dev), pos, None if m is None else m.to(dev)
 
     finish_merging = property(lambda s: s.op.finish_merging)
     finish_pruning = property(lambda s: s.op.finish_pruning)
