@@ -17,11 +17,11 @@ FF_BF16, FF_F16, FF_F32 = 0, 1, 2
 FF_MAX_AUX = 6
 
 # status slots (enum ff_status_slot)
-ST_SEQ_KEEP, ST_COUNT, ST_NVIS, ST_NCHAIN, ST_BRANCH, ST_TOPK, ST_ERROR, ST_NMERGED, ST_FUSED, ST_INTERNAL = range(10)
+ST_SEQ_KEEP, ST_COUNT, ST_NVIS, ST_NCHAIN, ST_BRANCH, ST_TOPK, ST_ERROR, ST_NMERGED, ST_FUSED, ST_INTERNAL, ST_SEQ = range(11)
 ST_SLOTS = 16
 
 EXPORTS = [
-    "ff_abi_version", "ff_last_error", "ff_launch_count", "ff_ctx_create", "ff_ctx_destroy", "ff_ctx_status", "ff_ctx_timing", "ff_stream_sync", "ff_workspace_bytes",
+    "ff_abi_version", "ff_last_error", "ff_launch_count", "ff_ctx_create", "ff_ctx_destroy", "ff_ctx_status", "ff_ctx_timing", "ff_stream_sync", "ff_status_wait", "ff_workspace_bytes",
     "ff_build_links", "ff_similarity", "ff_merge_apply", "ff_merge_layer", "ff_importance", "ff_prune_layer",
     "ff_compact_mask", "ff_debug_read",
 ]
@@ -60,6 +60,7 @@ def load():
     lib.ff_ctx_status.argtypes = [_vp]
     lib.ff_ctx_status.restype = C.POINTER(_i64)
     lib.ff_stream_sync.argtypes = [_vp, _vp]
+    lib.ff_status_wait.argtypes = [_vp, _vp]
     lib.ff_ctx_timing.argtypes = [_vp, _vp, _vp]
     lib.ff_workspace_bytes.argtypes = [_i64, _i64]
     lib.ff_workspace_bytes.restype = _i64

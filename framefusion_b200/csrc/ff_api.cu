@@ -90,6 +90,7 @@ struct ff_ctx {
     int count_clean[2];  // counters[bank][C_COUNT] is known to be zero (set by the kernel that decided the previous call)
     unsigned bar_base;   // value of the grid-barrier word before the next k_keep_scan (it is not reset between merge calls)
     int bar_dirty;       // the prune stage left the barrier word at an unknown value
+    long long seq;       // number of the last reducing call (status[FF_ST_SEQ] when its results are in the status block)
 };
 
 // every entry point runs on the context's device and leaves the caller's current device as it found it (PyTorch
@@ -403,6 +404,7 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
     a.status = ctx->d_status;
     a.thr = (float)thr;
     a.bound = bound;
+    a.seq = ++ctx->seq;
     // the aux tensors as (tensor, plane) entries of one piece per lane, when they have that form
     a.auxf.n = 0;
     for (int q = 0; q < ap.n && a.auxf.n >= 0; ++q) {
@@ -472,6 +474,7 @@ int ff_ctx_create(int device, ff_ctx** out) {
     c->n_ids = 0;
     c->have_order = c->have_seq = 0;
     c->fresh_links = 0;
+    c->seq = 0;
     c->last_fused = 0;
     c->fused_clean[0] = c->fused_clean[1] = 0;
     c->fused_attr[0] = c->fused_attr[1] = c->fused_attr[2] = 0;
@@ -512,6 +515,27 @@ int ff_ctx_timing(ff_ctx* ctx, void* ev_start, void* ev_stop) {
 int ff_stream_sync(ff_ctx* ctx, void* stream) {
     if (!ctx) return fail(FF_E_BADARG, "null ctx");
     FF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return FF_OK;
+}
+
+int ff_status_wait(ff_ctx* ctx, void* stream) {
+    if (!ctx) return fail(FF_E_BADARG, "null ctx");
+    cudaStream_t st = (cudaStream_t)stream;
+    const volatile int64_t* seq = &ctx->h_status[FF_ST_SEQ];
+    // the deciding kernel of a call runs a few tens of microseconds after its launch: poll the mapped word; look at the
+    // stream now and then (a failed launch never writes it), and give up polling after a generous while
+    for (long spins = 0; *seq != ctx->seq; ++spins) {
+        if ((spins & 1023) == 1023) {
+            const cudaError_t e = cudaStreamQuery(st);
+            if (e == cudaSuccess) break;                   // everything has run: the word is there, or this call decided nothing
+            if (e != cudaErrorNotReady) return fail(FF_E_CUDA, "stream: %s", cudaGetErrorString(e));
+            if (spins > (1l << 26)) {
+                FF_CUDA(cudaStreamSynchronize(st));
+                break;
+            }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
     return FF_OK;
 }
 
@@ -676,6 +700,7 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     a.rank_next = w.rank[nb];
     a.counters_next = w.counters[nb];
     a.force_branch = -1;
+    a.seq = ++ctx->seq;
     if (S >= 2 * SEL_THREADS) {
         // a grid of co-resident blocks for the threshold branch; its block 0 handles the top-k branch alone
         ScanArgs sa;
@@ -806,6 +831,7 @@ int ff_prune_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* attn, in
     a.start = (int)start;
     a.length = (int)length;
     a.k = k;
+    a.seq = ++ctx->seq;
     if (grid_select) {
         PruneGridArgs ga;
         ga.p = a;

@@ -79,6 +79,7 @@ struct FusedArgs {
     int64_t* status;
     float thr;
     double bound;
+    long long seq;                                 // number of this call: status[FF_ST_SEQ] once the block is complete
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------
@@ -400,6 +401,8 @@ __device__ __forceinline__ void fused_finish(const FusedArgs& a, long long s_kee
     a.status[FF_ST_ERROR] = ec;
     a.status[FF_ST_NMERGED] = n_merged;
     a.status[FF_ST_FUSED] = 1;
+    __threadfence_system();
+    *(volatile int64_t*)&a.status[FF_ST_SEQ] = a.seq;
 }
 
 // Order of the S units.  On the first call of a uniform video (frames x P vision rows in one span, chains = patches) the

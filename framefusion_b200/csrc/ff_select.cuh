@@ -101,7 +101,14 @@ struct DecideArgs {
     int* rank_next;
     int64_t* counters_next;     // counter bank of the next call: N, n_vis carried over, count reset
     int force_branch;           // -1 = decide from count (main.py:116); 0/1 = flags are given (static API)
+    long long seq;              // number of this call: status[FF_ST_SEQ] once every other slot is written (ff_status_wait)
 };
+
+// the status block is complete: publish the call's number behind a system-wide fence (the host polls this word)
+__device__ __forceinline__ void publish_status(int64_t* status, long long seq) {
+    __threadfence_system();
+    *(volatile int64_t*)&status[FF_ST_SEQ] = seq;
+}
 
 // a kept row outside the chains (text): its record goes to the END of rec[], growing downwards, in no particular order
 // (the gather treats every record independently); the rows of the chains fill rec[] from the front in by-patch order
@@ -232,6 +239,7 @@ __device__ __forceinline__ void decide_scan_block(const DecideArgs& a) {
         a.status[FF_ST_ERROR] = s_err;
         a.status[FF_ST_NMERGED] = N - n_next;
         a.status[FF_ST_FUSED] = 0;
+        publish_status(a.status, a.seq);
     }
 }
 
@@ -395,6 +403,7 @@ k_keep_scan(ScanArgs a) {
         d.status[FF_ST_ERROR] = 0;
         d.status[FF_ST_NMERGED] = N - n_next;
         d.status[FF_ST_FUSED] = 0;
+        publish_status(d.status, d.seq);
     }
 }
 
@@ -408,6 +417,7 @@ struct PruneArgs {
     int* srcidx;
     int S, start, length;
     long long k;
+    long long seq;              // see DecideArgs
 };
 
 __global__ void __launch_bounds__(SEL_THREADS)
@@ -448,6 +458,7 @@ k_prune_scan(PruneArgs a) {
         a.status[FF_ST_SEQ_KEEP] = carry;
         a.status[FF_ST_TOPK] = a.k;
         a.status[FF_ST_ERROR] = 0;
+        publish_status(a.status, a.seq);
     }
 }
 
@@ -596,6 +607,7 @@ k_prune_select(PruneGridArgs a) {
         p.status[FF_ST_SEQ_KEEP] = s_keep;
         p.status[FF_ST_TOPK] = p.k;
         p.status[FF_ST_ERROR] = 0;
+        publish_status(p.status, p.seq);
     }
 }
 

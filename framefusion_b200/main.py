@@ -321,7 +321,8 @@ class FrameFusion(nn.Module):
             st.ctx, wp, wb, attn.data_ptr(), attn.shape[0], hidden.data_ptr(), out.data_ptr(), _dtype_code(hidden),
             q_len, hidden_size, start, length, k, self._pack_aux(auxes), len(auxes),
             imp.data_ptr() if imp is not None else None, stream))
-        _lib.check(st.lib.ff_stream_sync(st.ctx, stream))
+        # the selection kernel writes S_keep before the gather runs: the host goes on while the rows move
+        _lib.check(st.lib.ff_status_wait(st.ctx, stream))
         s_keep = int(st.status[_lib.ST_SEQ_KEEP])
         outs = self._narrow(auxes, s_keep)
         position_embeddings = rebuild(outs)
@@ -375,7 +376,11 @@ class FrameFusion(nn.Module):
                     st.lib.ff_ctx_timing(st.ctx, None, None)
             if ev is not None:
                 ev.append(("ff_merge_layer", q_len, e0, e1))
-            _lib.check(st.lib.ff_stream_sync(st.ctx, stream))
+            # multi-kernel path: the scan kernel writes the status block before the gather runs, and the host goes on
+            # while the rows move (everything it enqueues next is ordered behind them).  The read-once kernel reports at
+            # its very end, a timed-out wait (FF_ST_INTERNAL) even later: wait for the stream.
+            wait = st.lib.ff_stream_sync if flags else st.lib.ff_status_wait
+            _lib.check(wait(st.ctx, stream))
 
         try:
             launch(fused)

@@ -55,6 +55,8 @@ enum ff_status_slot {
                               threshold branch and the count says top-k: call again without flag bit 0 */
     FF_ST_NMERGED = 7,     /* tokens merged away by this call */
     FF_ST_FUSED = 8,       /* 1 if the read-once kernel produced this result, 0 for the multi-kernel path */
+    FF_ST_SEQ = 10,        /* number of the reducing call whose results the block holds: written LAST, after a system-wide
+                            * fence, by the kernel that decides the call (ff_status_wait) */
     FF_ST_INTERNAL = 9,    /* 1 if a wait inside the read-once kernel gave up (the results of the call are invalid) */
     FF_ST_SLOTS = 16
 };
@@ -88,6 +90,13 @@ const int64_t* ff_ctx_status(const ff_ctx* ctx);
 /* waits for the work enqueued on `stream`: the one synchronisation a reducing call needs before the status block
  * (S_keep, the branch taken) can be read */
 int ff_stream_sync(ff_ctx* ctx, void* stream);
+/* Returns as soon as the status block holds the results of the last ff_merge_layer / ff_prune_layer call enqueued on
+ * `stream` — S_keep, the count, the branch — which the deciding kernel writes BEFORE the gather of that call runs: the host
+ * learns the output length (the reference learns it from `.item()` / a boolean-mask select, main.py:112-138) while the rows
+ * are still being moved, and its work for the next call overlaps them.  Everything enqueued later on the same stream is
+ * ordered behind the call as usual; a host read of the outputs needs its own synchronisation (ff_stream_sync, or any
+ * stream-ordered copy).  Falls back to waiting for the stream if the status does not show up. */
+int ff_status_wait(ff_ctx* ctx, void* stream);
 /* Profiling aid: two caller-owned cudaEvent_t (timing enabled), or NULLs to switch it off.  While set, ff_merge_layer and
  * ff_prune_layer record `ev_start` on the stream right before their first kernel launch and `ev_stop` right after their
  * last one, so the elapsed time between them is the GPU time of the call's launches and nothing of the host's path to
