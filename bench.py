@@ -107,6 +107,26 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def pin_rank_to_gpu_cpus(local_rank: int):
+    """One process per GPU: keep the rank on the CPUs next to its GPU (NVML's affinity mask), so that its pinned staging
+    buffers are first touched — and its copies driven — from the GPU's own NUMA node.  Returns the CPU set, or None when
+    NVML has nothing to say (a virtualised single-node host) or the call is not permitted."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus or len(cpus) == len(os.sched_getaffinity(0)):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:  # noqa: BLE001 - an optimisation, never a requirement
+        return None
+
+
 # --------------------------------------------------------------------------------------------------
 # one step, any implementation with the FrameFusion call contract
 # --------------------------------------------------------------------------------------------------
@@ -414,6 +434,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     warm = max(args.warmup, 3)
     torch.cuda.set_device(local)
+    pinned_cpus = pin_rank_to_gpu_cpus(local) if world > 1 else None
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
@@ -584,6 +605,7 @@ def main():
         "config": {"workload": workload_name(cfg), "seq_len": wl.seq_len, "kept_after_merge": s_keep0,
                    "kept_after_prune": int(h_final.shape[1]), "l2": "inputs (264 MB at C2) exceed the 126 MB L2; no explicit flush",
                    "parallelism": "replicas" if world > 1 else "single-gpu",
+                   "cpu_affinity": "rank pinned to its GPU's CPUs (NVML)" if pinned_cpus else "unpinned",
                    "calls_per_step": "merge, merge (closes merging), importance, prune"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "ff_merge_layer call #0: " + ("k_stream_merge (single pass)" if fused else "two-pass path (k_similarity + k_keep_scan + k_merge_gather)"),
