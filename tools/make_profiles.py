@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """Turn the outputs of tools/final_round.sh (gpurun_out/*_<tag>.*) into the tracked summaries under profiles/.
 
-    python tools/make_profiles.py <tag> [<ncu-rep of the two-pass path>]
+    python tools/make_profiles.py <tag> [<ncu-rep of the two-pass path>]      (FF_ROUND=r02 names the files)
 """
 import csv, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RND = os.environ.get("FF_ROUND", "r02")
 tag = sys.argv[1]
 rep = sys.argv[2] if len(sys.argv) > 2 else None
 out = os.path.join(ROOT, "gpurun_out")
@@ -27,9 +28,9 @@ bench = json.loads(open(f"{out}/bench_{tag}.json").read().strip().splitlines()[-
 first_gather = next(i for i, d in enumerate(step) if "k_merge_gather" in d[0])
 first_sim = next(i for i, d in enumerate(step) if "k_similarity" in d[0])
 m0 = sum(d[1] for d in step[first_sim:first_gather + 1])
-doc = ["# r01 — kernels of one bench step (C2), ncu launch list (final code of the round)", "",
+doc = [f"# {RND} — kernels of one bench step (C2), ncu launch list (final code of the round)", "",
        "Command (on the B200 box): `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline`",
-       "(raw list: `r01_bench_launches_raw.csv`; per-launch times under ncu are cold-cache and serialised — compare shares, not absolutes).", "",
+       f"(raw list: `{RND}_bench_launches_raw.csv`; per-launch times under ncu are cold-cache and serialised — compare shares, not absolutes).", "",
        "| # | kernel | grid | block | time (us) | share |", "|---|---|---|---|---|---|"]
 for i, d in enumerate(step):
     doc.append(f"| {i} | `{short(d[0])}` | {d[2]} | {d[3]} | {d[1]:.1f} | {100 * d[1] / tot:.1f} % |")
@@ -38,13 +39,14 @@ doc += ["", f"Sum: {tot:.1f} us in {len(step)} launches.  Merge call #0 (the roo
         f"k_merge_gather) is {m0:.1f} us = {100 * m0 / tot:.1f} % of the step's kernel time; CUDA-event timing of the same launches inside bench.py, warm and "
         f"back to back: {r['kernel_us']:.1f} us -> {r['achieved']:.0f} GB/s algorithmic = {r['frac']:.3f} of the {r['peak']:.0f} GB/s peak ({r['peak_source']}).", "",
         f"Step wall time in the same bench run without ncu: {bench['ms_per_step'] * 1000:.0f} us for {len(step)} launches + 3 status reads; the difference to the "
-        "kernel sum is host dispatch (Python + ctypes + the one stream sync per call).",
+        "kernel sum is host dispatch (Python + ctypes) that the GPU does not hide: the host reads the status block as soon as the deciding kernel "
+        "has published it (ff_status_wait) and prepares the next call while the gather runs.",
         "The second merge call closes merging: nothing crosses the threshold any more, its gather returns after reading the counter and the operator hands its inputs back.",
         "The last `k_merge_gather` compacts the pruned sequence (no averaging)."]
-open(f"{prof}/r01_bench_step_launches.md", "w").write("\n".join(doc) + "\n")
-subprocess.run(["cp", f"{out}/bench_launches_{tag}.csv", f"{prof}/r01_bench_launches_raw.csv"], check=True)
-subprocess.run(["cp", f"{out}/bench_{tag}.json", f"{prof}/r01_bench_line.json"], check=True)
-subprocess.run(["cp", f"{out}/bench_ref_{tag}.json", f"{prof}/r01_bench_reference_line.json"], check=True)
+open(f"{prof}/{RND}_bench_step_launches.md", "w").write("\n".join(doc) + "\n")
+subprocess.run(["cp", f"{out}/bench_launches_{tag}.csv", f"{prof}/{RND}_bench_launches_raw.csv"], check=True)
+subprocess.run(["cp", f"{out}/bench_{tag}.json", f"{prof}/{RND}_bench_line.json"], check=True)
+subprocess.run(["cp", f"{out}/bench_ref_{tag}.json", f"{prof}/{RND}_bench_reference_line.json"], check=True)
 print("\n".join(doc[-6:]))
 
 if rep:
@@ -56,10 +58,10 @@ if rep:
         if "dram__bytes_read.sum" in blk or "dram__bytes_write.sum" in blk:
             dram.append(float(blk.split()[1]))
     total = sum(dram)
-    doc = f"""# r01 — ncu --set full, two-pass merge path, C2 (k_similarity, k_keep_scan, k_merge_gather) — final code of the round
+    doc = f"""# {RND} — ncu --set full, two-pass merge path, C2 (k_similarity, k_keep_scan, k_merge_gather) — final code of the round
 
 Command: `ncu --set full --clock-control none --import-source on -k regex:"k_similarity|k_keep_scan|k_merge_gather" -s 6 -c 3 python tools/time_merge.py --cfg C2 --fused 0 --iters 2`
-(per-launch times under ncu are cold-cache and serialised; the launch list in r01_bench_step_launches.md comes from bench.py itself)
+(per-launch times under ncu are cold-cache and serialised; the launch list in {RND}_bench_step_launches.md comes from bench.py itself)
 
 ```
 {head}
@@ -74,17 +76,13 @@ DRAM traffic of the call (reads + writes of the three kernels): **{total:.1f} MB
 {lines.rstrip()}
 ```
 
-Every hot line waits on `long_scoreboard` (global loads): the path is latency bound, not issue bound.  What moved the
-gather in this round (probes in `tools/*_probe.cu`, numbers in DESIGN.md section 5): packed bf16 adds and an exact
-reciprocal multiply instead of unpack / add / round / IEEE divide in the anchor rows (-20 us), aux rows in blocks of
-their own with every load of a row in flight (-4 us), records handed to the gather last-to-first so that it starts on
-rows the similarity pass left in the L2 (-6 us), dependent launches (-9 us).  What did not: a persistent grid, L2
-eviction-priority hints on either pass, `st.global.cs`, packed arithmetic or shared norms in the similarity kernel
-(it is bound by its read pattern: the same kernel without any arithmetic takes the same 54 us).
+Every hot line waits on `long_scoreboard` (global loads): the path is latency bound, not issue bound.  The three kernels
+are the ones of r01 (DESIGN.md section 5 has what moved them and what did not); this round's work on the merge stage went
+into the read-once kernel ({RND}_read_once_kernel.md), which ends level with this path.
 """
-    open(f"{prof}/r01_two_pass_ncu_full.md", "w").write(doc)
+    open(f"{prof}/{RND}_two_pass_ncu_full.md", "w").write(doc)
     t = json.load(open(f"{prof}/traffic.json"))
     t["C2"]["dram_bytes_per_launch"] = int(round(total * 1e6, -5))
-    t["C2"]["kernel"] = "ff_merge_layer call #0, two-pass path: k_similarity + k_keep_scan + k_merge_gather (ncu --set full, r01_two_pass_ncu_full.md; writes still in L2 at kernel end are not counted)"
+    t["C2"]["kernel"] = "ff_merge_layer call #0, two-pass path: k_similarity + k_keep_scan + k_merge_gather (ncu --set full, " + RND + "_two_pass_ncu_full.md; writes still in L2 at kernel end are not counted)"
     json.dump(t, open(f"{prof}/traffic.json", "w"), indent=1)
     print("traffic", total)
