@@ -39,9 +39,9 @@
 namespace ff {
 
 constexpr int FU_WARPS = 8;                        // warps per CTA (independent workers; a CTA shares its ticket ring)
-constexpr int FU_MIN_CTAS = 2;                     // per SM: 16 warps of up to 128 registers per thread — a whole row in flight per warp
+constexpr int FU_MIN_CTAS = 4;                     // per SM: 32 warps of at most 64 registers per thread
 constexpr int FU_BAND = 1024;                      // rows per band: 32 words of 32 rows, one word per lane
-constexpr int FU_LAG = 4096;                       // S units run this many rows ahead of the G units (FF_FUSED_LAG)
+constexpr int FU_LAG = 8192;                       // S units run this many rows ahead of the G units (FF_FUSED_LAG)
 constexpr int FU_SFRAMES = 2;                      // frames whose S units are taken patch by patch (FF_FUSED_SFRAMES; 1: sequence order)
 constexpr int FU_BATCH = 8;                        // tickets per draw
 #ifndef FU_PREFETCH_SLOT
@@ -208,9 +208,9 @@ __device__ __forceinline__ void copy_piece(const char* __restrict__ src, char* _
     for (int q = 0; q < N; ++q) st_stream16(dst + q * 512, x[q]);
 }
 
-// src row -> dst row from vector v0 on (read for the last time, written once: streaming both ways)
-__device__ __forceinline__ void copy_row(const char* __restrict__ src, char* __restrict__ dst, int nvec, int lane, int v0 = 0) {
-    int v = v0;                                             // vectors done (warp-uniform)
+// src row -> dst row (read for the last time, written once: streaming both ways)
+__device__ __forceinline__ void copy_row(const char* __restrict__ src, char* __restrict__ dst, int nvec, int lane) {
+    int v = 0;                                              // vectors done (warp-uniform)
     src += lane * 16;
     dst += lane * 16;
 #pragma unroll 1
@@ -268,41 +268,6 @@ __device__ __forceinline__ float row_similarity(const char* __restrict__ pr, con
     if (v + 64 <= nvec) { sim_piece<DT, 2>(pr + (int64_t)v * 16, cr + (int64_t)v * 16, s); v += 64; }
     if (v + 32 <= nvec) { sim_piece<DT, 1>(pr + (int64_t)v * 16, cr + (int64_t)v * 16, s); v += 32; }
     if (v + lane < nvec) sim_piece<DT, 1>(pr + (int64_t)v * 16, cr + (int64_t)v * 16, s);
-    const float dot = warp_sum((s.d0.x + s.d0.y) + (s.d1.x + s.d1.y));
-    const float na = warp_sum((s.a0.x + s.a0.y) + (s.a1.x + s.a1.y));
-    const float nb = warp_sum((s.b0.x + s.b0.y) + (s.b1.x + s.b1.y));
-    return finish_cosine<DT>(dot, na, nb);
-}
-
-// The same with the row's own NV x 32 vectors ALL in flight from the start (rows of exactly NV vectors per lane: the shapes
-// of the BASELINE configs); the predecessor follows in two halves once its index is known.  One HBM round trip per S unit
-// instead of one per piece.
-template <int DT, int NV>
-__device__ __forceinline__ float row_similarity_wide(const uint4 (&c)[NV], const char* __restrict__ pr, int lane) {
-    SimAcc s;
-    s.d0 = s.d1 = s.a0 = s.a1 = s.b0 = s.b1 = make_float2(0.f, 0.f);
-    constexpr int H1 = (NV + 1) / 2;
-    pr += lane * 16;
-    {
-        uint4 p[H1];
-#pragma unroll
-        for (int q = 0; q < H1; ++q) p[q] = ldg16(pr + q * 512);
-#pragma unroll
-        for (int q = 0; q < H1; ++q) {
-            if (q & 1) acc_pair2<DT>(p[q], c[q], s.d1, s.a1, s.b1);
-            else acc_pair2<DT>(p[q], c[q], s.d0, s.a0, s.b0);
-        }
-    }
-    {
-        uint4 p[NV - H1];
-#pragma unroll
-        for (int q = H1; q < NV; ++q) p[q - H1] = ldg16(pr + q * 512);
-#pragma unroll
-        for (int q = H1; q < NV; ++q) {
-            if (q & 1) acc_pair2<DT>(p[q - H1], c[q], s.d1, s.a1, s.b1);
-            else acc_pair2<DT>(p[q - H1], c[q], s.d0, s.a0, s.b0);
-        }
-    }
     const float dot = warp_sum((s.d0.x + s.d0.y) + (s.d1.x + s.d1.y));
     const float na = warp_sum((s.a0.x + s.a0.y) + (s.a1.x + s.a1.y));
     const float nb = warp_sum((s.b0.x + s.b0.y) + (s.b1.x + s.b1.y));
@@ -384,27 +349,29 @@ __device__ __forceinline__ void sum_run(const char* __restrict__ hidden, int nve
     }
 }
 
-// the aux rows of sequence row r -> destination row d: one 16- or 8-byte piece per lane and entry.  Loads and stores are
-// separate calls: the G unit requests the aux rows first and stores them last, so their latency hides behind its own
-template <bool LOAD>
-__device__ __forceinline__ void fused_aux_io(const FusedArgs& a, int row, int lane, uint4 (&v)[8]) {
+// the aux rows of sequence row r -> destination row d: one 16- or 8-byte piece per lane and entry, all loads first
+__device__ __forceinline__ void fused_aux(const FusedArgs& a, const AuxPack& aux, int r, int d, int lane) {
     const AuxFlat& f = a.auxf;
+    if (f.n < 0) { gather_aux_rows(aux, r, d, lane); return; }
+    uint4 v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
+        v[e] = make_uint4(0, 0, 0, 0);
         if (e < f.n) {
             const int rb = f.row_bytes[e];
-            if (LOAD) {
-                const char* s = f.src[e] + (int64_t)row * rb;
-                v[e] = make_uint4(0, 0, 0, 0);
-                if (f.piece[e] == 8) { if (lane * 8 < rb) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(s) + lane); v[e].x = t.x; v[e].y = t.y; } }
-                else if (lane * 16 < rb) v[e] = __ldg(reinterpret_cast<const uint4*>(s) + lane);
-            } else {
-                char* o = f.dst[e] + (int64_t)row * rb;
-                if (f.piece[e] == 8) { if (lane * 8 < rb) reinterpret_cast<uint2*>(o)[lane] = make_uint2(v[e].x, v[e].y); }
-                else if (lane * 16 < rb) reinterpret_cast<uint4*>(o)[lane] = v[e];
-            }
+            const char* s = f.src[e] + (int64_t)r * rb;
+            if (f.piece[e] == 8) { if (lane * 8 < rb) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(s) + lane); v[e].x = t.x; v[e].y = t.y; } }
+            else if (lane * 16 < rb) v[e] = __ldg(reinterpret_cast<const uint4*>(s) + lane);
         }
     }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        if (e < f.n) {
+            const int rb = f.row_bytes[e];
+            char* o = f.dst[e] + (int64_t)d * rb;
+            if (f.piece[e] == 8) { if (lane * 8 < rb) reinterpret_cast<uint2*>(o)[lane] = make_uint2(v[e].x, v[e].y); }
+            else if (lane * 16 < rb) reinterpret_cast<uint4*>(o)[lane] = v[e];
+        }
 }
 
 // the sequence is done: sizes, the speculated branch, the counters of the next call (main.py:112-120)
@@ -457,30 +424,11 @@ struct SOrder {
 };
 
 // S unit of row r (see the head of the file)
-template <int DT, int NV>
-__device__ __forceinline__ float s_similarity_wide(const FusedArgs& a, int r, const int2** lkp, int2* lk_out, int lane) {
-    const char* cr = a.hidden + (int64_t)r * a.row_bytes + lane * 16;
-    const int2 lk = __ldg(a.link + r);                      // travels with the row
-    uint4 c[NV];
-#pragma unroll
-    for (int q = 0; q < NV; ++q) c[q] = ldg16(cr + q * 512);          // plain loads: the gather must find the row in the L2
-    *lk_out = lk;
-    if (lk.x < 0) return -2.0f;                             // (the loads are dropped: a chain head is first read by the gather)
-    return row_similarity_wide<DT, NV>(c, a.hidden + (int64_t)lk.x * a.row_bytes, lane);
-}
-
 template <int DT>
 __device__ __forceinline__ void s_unit(const FusedArgs& a, const FusedDesc& d, int r, int lane) {
-    int2 lk;
-    float s;
-    if (a.nvec == 14 * 32) s = s_similarity_wide<DT, 14>(a, r, nullptr, &lk, lane);
-    else if (a.nvec == 16 * 32) s = s_similarity_wide<DT, 16>(a, r, nullptr, &lk, lane);
-    else if (a.nvec == 8 * 32) s = s_similarity_wide<DT, 8>(a, r, nullptr, &lk, lane);
-    else {
-        lk = __ldg(a.link + r);
-        s = -2.0f;                                          // IGNORE_TOKEN at chain heads (main.py:225-238)
-        if (lk.x >= 0) s = row_similarity<DT>(a.hidden + (int64_t)lk.x * a.row_bytes, a.hidden + (int64_t)r * a.row_bytes, a.nvec, lane);
-    }
+    const int2 lk = __ldg(a.link + r);
+    float s = -2.0f;                                        // IGNORE_TOKEN at chain heads (main.py:225-238)
+    if (lk.x >= 0) s = row_similarity<DT>(a.hidden + (int64_t)lk.x * a.row_bytes, a.hidden + (int64_t)r * a.row_bytes, a.nvec, lane);
     const unsigned kept = !(lk.x >= 0 && s >= a.thr);       // NaN compares false: kept
     if (lane == 0) {
         a.sim_seq[r] = s;
@@ -488,22 +436,13 @@ __device__ __forceinline__ void s_unit(const FusedArgs& a, const FusedDesc& d, i
     }
 }
 
-// G unit of row r (see the head of the file).  Loads are requested as early as their address is known and consumed as
-// late as possible: the aux rows and the first 4 KB of the predecessor's row (the row this unit writes in most cases: its
-// predecessor is an anchor without members) travel while the walk and the prefix are worked out.
+// G unit of row r (see the head of the file)
 template <int DT>
 __device__ __forceinline__ void g_unit(const FusedArgs& a, const AuxPack& aux, const FusedDesc& d, BandCache& bc, int r, int lane, int* err) {
     const int2 lk = __ldg(a.link + r);
     const int b = r >> 10, wi = (r >> 5) & 31;
     const int nvec = a.nvec;
     const int64_t row_bytes = a.row_bytes;
-    const bool early = lk.x >= 0 && nvec >= 256;            // (a merged row needs it only at the end of its chain: rare)
-    uint4 x0[8];
-    const char* srow = a.hidden + (int64_t)max(lk.x, 0) * row_bytes;
-    if (early) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) x0[q] = ldg16(srow + lane * 16 + q * 512);
-    }
     if (b != bc.cb) {
         // entering a band: the prefix moves along with the words of the bands in between, all complete by now
         if (bc.cb < 0) bc.cb = 0;
@@ -526,9 +465,6 @@ __device__ __forceinline__ void g_unit(const FusedArgs& a, const AuxPack& aux, c
         a.dst[r] = d_r;
         if (r == a.S - 1) fused_finish(a, (long long)ex + (is_kept ? 1 : 0));
     }
-    uint4 av[8];
-    const bool aux_flat = is_kept && aux.n && a.auxf.n >= 0;
-    if (aux_flat) fused_aux_io<true>(a, r, lane, av);
     int start = -1;                                         // where the walk back starts
     bool self = false;
     if (is_kept) {
@@ -545,10 +481,10 @@ __device__ __forceinline__ void g_unit(const FusedArgs& a, const AuxPack& aux, c
         start = r;                                          // merged away, and the chain ends here
     }
     if (start >= 0) {
-        // every lane walks (uniform loads); lane k remembers the k-th member from the end.  Words of this band are at hand.
+        // every lane walks (uniform loads); lane k remembers the k-th member from the end
         int x = start, L = 0, mine = -1;
         unsigned mx;
-        while (true) {
+        while (true) {                                      // (the words of this band are at hand: no load)
             mx = (x >> 10) == b ? __shfl_sync(FULL, (unsigned)wown, (x >> 5) & 31) : (unsigned)ld_relaxed64(d.word + (x >> 5));
             if (mx >> (x & 31) & 1u) break;                 // kept: the anchor
             if (lane == L) mine = x;
@@ -570,15 +506,8 @@ __device__ __forceinline__ void g_unit(const FusedArgs& a, const AuxPack& aux, c
                     else a.link_next[d_a].y = -1;
                 }
                 char* orow = a.out + (int64_t)d_a * row_bytes;
-                if (L == 0) {
-                    if (early && x == lk.x) {               // the row that has been travelling since the unit began
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) st_stream16(orow + lane * 16 + q * 512, x0[q]);
-                        copy_row(srow, orow, nvec, lane, 256);
-                    } else {
-                        copy_row(a.hidden + (int64_t)x * row_bytes, orow, nvec, lane);
-                    }
-                } else {
+                if (L == 0) copy_row(a.hidden + (int64_t)x * row_bytes, orow, nvec, lane);
+                else {
                     RunWalk rw;
                     rw.link = a.link; rw.L = L; rw.mine = mine; rw.anchor = x;
                     sum_run<DT>(a.hidden, nvec, row_bytes, rw, orow, lane);
@@ -587,8 +516,7 @@ __device__ __forceinline__ void g_unit(const FusedArgs& a, const AuxPack& aux, c
         }
     }
     if (self) copy_row(a.hidden + (int64_t)r * row_bytes, a.out + (int64_t)d_r * row_bytes, nvec, lane);
-    if (aux_flat) fused_aux_io<false>(a, d_r, lane, av);
-    else if (is_kept && aux.n) gather_aux_rows(aux, r, d_r, lane);
+    if (is_kept && aux.n) fused_aux(a, aux, r, d_r, lane);
 }
 
 template <int DT>
