@@ -13,6 +13,7 @@ from . import _build
 _i64 = C.c_int64
 _vp = C.c_void_p
 
+ABI_VERSION = 3            # FF_ABI_VERSION of include/framefusion_b200.h
 FF_BF16, FF_F16, FF_F32 = 0, 1, 2
 FF_MAX_AUX = 6
 
@@ -79,8 +80,8 @@ def load():
         fn = getattr(lib, name)
         if name not in ("ff_last_error", "ff_launch_count", "ff_ctx_status", "ff_workspace_bytes"):
             fn.restype = C.c_int
-    if lib.ff_abi_version() != 2:
-        raise FFError(f"ABI version {lib.ff_abi_version()} != 2")
+    if lib.ff_abi_version() != ABI_VERSION:
+        raise FFError(f"ABI version {lib.ff_abi_version()} != {ABI_VERSION}")
     _lib = lib
     return lib
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FF_ABI_VERSION 2
+#define FF_ABI_VERSION 3
 
 enum ff_dtype { FF_BF16 = 0, FF_F16 = 1, FF_F32 = 2 };
 
