@@ -13,7 +13,7 @@ from . import _build
 _i64 = C.c_int64
 _vp = C.c_void_p
 
-ABI_VERSION = 3            # FF_ABI_VERSION of include/framefusion_b200.h
+ABI_VERSION = 4            # FF_ABI_VERSION of include/framefusion_b200.h
 FF_BF16, FF_F16, FF_F32 = 0, 1, 2
 FF_MAX_AUX = 6
 
@@ -24,7 +24,7 @@ ST_SLOTS = 16
 EXPORTS = [
     "ff_abi_version", "ff_last_error", "ff_launch_count", "ff_ctx_create", "ff_ctx_destroy", "ff_ctx_status", "ff_ctx_timing", "ff_stream_sync", "ff_status_wait", "ff_workspace_bytes",
     "ff_build_links", "ff_similarity", "ff_merge_apply", "ff_merge_layer", "ff_importance", "ff_prune_layer",
-    "ff_compact_mask", "ff_debug_read",
+    "ff_compact_mask", "ff_debug_read", "ff_debug_frame_trace",
 ]
 
 
@@ -76,6 +76,7 @@ def load():
                                    C.POINTER(FFAux), C.c_int, _vp, _vp]
     lib.ff_compact_mask.argtypes = [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp]
     lib.ff_debug_read.argtypes = [_vp, _vp, _i64, C.c_int, _vp, _i64, C.c_int, _vp]
+    lib.ff_debug_frame_trace.argtypes = [_vp, _vp, _i64]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("ff_last_error", "ff_launch_count", "ff_ctx_status", "ff_workspace_bytes"):

@@ -8,6 +8,7 @@
 #include <new>
 
 #include "ff_common.cuh"
+#include "ff_frame.cuh"
 #include "ff_fused.cuh"
 #include "ff_importance.cuh"
 #include "ff_links.cuh"
@@ -91,6 +92,9 @@ struct ff_ctx {
     unsigned bar_base;   // value of the grid-barrier word before the next k_keep_scan (it is not reset between merge calls)
     int bar_dirty;       // the prune stage left the barrier word at an unknown value
     long long seq;       // number of the last reducing call (status[FF_ST_SEQ] when its results are in the status block)
+    int frame_smem[6];   // dynamic shared memory the frame-pipelined kernel of each (dtype, build) is opted in for
+    long long* frame_trace;          // ff_debug_frame_trace: device buffer for time stamps of the next frame-kernel launch
+    int64_t frame_trace_bytes;
 };
 
 // every entry point runs on the context's device and leaves the caller's current device as it found it (PyTorch
@@ -448,6 +452,104 @@ int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* o
     });
 }
 
+// The frame-pipelined kernel (ff_frame.cuh) serves the first merge call of a prefill when the rows are 16-byte
+// multiples, no chain head can pass the threshold, and a ring of at least four frames of the CTA's chains fits shared
+// memory.  Whether the layout is the uniform video it is built for is checked on the device (status ERROR = 3 if not).
+struct FramePlan {
+    int R, n_stages, smem, grid, threads;
+};
+
+bool frame_plan(const ff_ctx* ctx, const void* hidden, const void* out, int dtype, int64_t S, int64_t H, double thr, FramePlan* fp) {
+    static const int off = getenv("FF_NO_FRAME") ? atoi(getenv("FF_NO_FRAME")) : 0;
+    if (off || !ctx->fresh_links || ctx->n_ids < 1 || S < 1 || S >= (1ll << 30)) return false;
+    const int64_t row_bytes = H * (dtype == FF_F32 ? 4 : 2);
+    if (row_bytes % 16 != 0 || (((uintptr_t)hidden | (uintptr_t)out) & 15) != 0 || !(thr > -2.0)) return false;
+    const int64_t P = ctx->n_ids;
+    const int64_t R = (P + ctx->sm_count - 1) / ctx->sm_count;
+    if (R > FR_MAXR) return false;
+    const int64_t stage = R * row_bytes;
+    int64_t n_stages = ((int64_t)ctx->max_smem - FR_META - stage) / stage;
+    static const int max_stages = getenv("FF_FRAME_STAGES") ? atoi(getenv("FF_FRAME_STAGES")) : FR_MAXSTAGES;
+    if (n_stages > max_stages) n_stages = max_stages;
+    if (n_stages > FR_MAXSTAGES) n_stages = FR_MAXSTAGES;
+    if (n_stages < 4) return false;
+    fp->R = (int)R;
+    fp->n_stages = (int)n_stages;
+    fp->smem = (int)(FR_META + (n_stages + 1) * stage);
+    fp->grid = (int)((P + R - 1) / R);
+    fp->threads = 32 * (2 + 3 * (int)R);
+    return true;
+}
+
+int launch_frame(ff_ctx* ctx, const Ws& w, int bank, const FramePlan& fp, const void* hidden, void* out, int dtype, int64_t S,
+                 int64_t H, double thr, double bound, const AuxPack& ap, cudaStream_t st) {
+    const int nb = bank ^ 1;
+    FrameArgs a;
+    a.hidden = (const char*)hidden;
+    a.out = (char*)out;
+    a.S = (int)S;
+    a.P = (int)ctx->n_ids;
+    a.R = fp.R;
+    a.row_bytes = (int)(H * (dtype == FF_F32 ? 4 : 2));
+    a.nvec = a.row_bytes / 16;
+    a.n_stages = fp.n_stages;
+    a.gbar = reinterpret_cast<unsigned*>(w.desc[bank]);
+    a.words = w.desc[bank] + 1;
+    a.sim = w.sim;
+    a.flag = w.flag;
+    a.dst = w.dst[bank];
+    a.keptdst = reinterpret_cast<int*>(w.rec);
+    a.len_next = w.len[1];
+    a.order_next = w.order[nb];
+    a.chain_next = w.chain[nb];
+    a.rank_next = w.rank[nb];
+    a.counters = w.counters[bank];
+    a.counters_next = w.counters[nb];
+    a.status = ctx->d_status;
+    a.thr = (float)thr;
+    a.bound = bound;
+    a.seq = ++ctx->seq;
+    a.trace = nullptr;
+    a.trace_frames = 0;
+    if (ctx->frame_trace) {
+        const int64_t per_frame = (int64_t)fp.grid * FR_TRACE_K * 8;
+        a.trace_frames = (int)(ctx->frame_trace_bytes / per_frame < 4096 ? ctx->frame_trace_bytes / per_frame : 4096);
+        a.trace = a.trace_frames > 0 ? ctx->frame_trace : nullptr;
+        ctx->frame_trace = nullptr;                        // one launch
+    }
+    a.auxf.n = 0;
+    for (int q = 0; q < ap.n && a.auxf.n >= 0; ++q) {
+        const ff_aux& x = ap.a[q];
+        const uintptr_t al = (uintptr_t)x.src | (uintptr_t)x.dst | (uintptr_t)x.src_plane_stride | (uintptr_t)x.dst_plane_stride | (uintptr_t)x.row_bytes;
+        const int piece = (al & 15) == 0 ? 16 : ((al & 7) == 0 ? 8 : 0);
+        if (piece == 0 || x.row_bytes > 32 * piece || a.auxf.n + x.planes > 8) { a.auxf.n = -1; break; }
+        for (int64_t pl = 0; pl < x.planes; ++pl) {
+            const int e = a.auxf.n++;
+            a.auxf.row_bytes[e] = (int)x.row_bytes;
+            a.auxf.piece[e] = piece;
+            a.auxf.src[e] = (const char*)x.src + pl * x.src_plane_stride;
+            a.auxf.dst[e] = (char*)x.dst + pl * x.dst_plane_stride;
+        }
+    }
+    if (!ctx->fused_clean[bank]) FF_CUDA(cudaMemsetAsync(w.desc[bank], 0, (size_t)(S / 32 + 2) * 8, st));
+    ctx->fused_clean[bank] = 0;
+    return dispatch_dtype(dtype, [&](auto dt) {
+        constexpr int DT = decltype(dt)::value;
+        // two builds: up to four chains per CTA (14 warps, no register pressure) and up to FR_MAXR
+        auto go = [&](auto mr) {
+            constexpr int MR = decltype(mr)::value;
+            constexpr int slot = DT * 2 + (MR > 4 ? 1 : 0);
+            if (ctx->frame_smem[slot] < fp.smem) {
+                FF_CUDA(cudaFuncSetAttribute((k_frame_merge<DT, MR>), cudaFuncAttributeMaxDynamicSharedMemorySize, fp.smem));
+                ctx->frame_smem[slot] = fp.smem;
+            }
+            FF_LAUNCH("k_frame_merge", (k_frame_merge<DT, MR>), fp.grid, fp.threads, fp.smem, st, a, ap);
+            return (int)FF_OK;
+        };
+        return fp.R <= 4 ? go(std::integral_constant<int, 4>()) : go(std::integral_constant<int, FR_MAXR>());
+    });
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -480,6 +582,9 @@ int ff_ctx_create(int device, ff_ctx** out) {
     c->fused_attr[0] = c->fused_attr[1] = c->fused_attr[2] = 0;
     c->fused_smem[0] = c->fused_smem[1] = c->fused_smem[2] = 0;
     c->fused_smem_last[0] = c->fused_smem_last[1] = c->fused_smem_last[2] = 0;
+    for (int i = 0; i < 6; ++i) c->frame_smem[i] = 0;
+    c->frame_trace = nullptr;
+    c->frame_trace_bytes = 0;
     cudaError_t e = cudaHostAlloc((void**)&c->h_status, FF_ST_SLOTS * 8, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e != cudaSuccess) { delete c; return fail(FF_E_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
     memset(c->h_status, 0, FF_ST_SLOTS * 8);
@@ -571,7 +676,7 @@ int ff_build_links(ff_ctx* ctx, void* ws, int64_t ws_bytes, const int64_t* patch
         FF_LAUNCH("k_links_scatter", k_links_scatter, n_chunks, LINK_CHUNK, 0, st, patch_type, (int)S, (int)n_ids, w.hist,
                   w.base, w.order[0], w.chain[0], w.rank[0]);
         FF_LAUNCH("k_links_seq", k_links_seq, (int)((S + 255) / 256), 256, 0, st, w.rank[0], w.order[0], w.chain[0], w.counters[0],
-                  (int)S, w.link[0], (unsigned long long*)&w.counters[0][C_FIRSTINV]);
+                  (int)S, (int)(n_ids > 0 ? n_ids : 1), w.link[0], (unsigned long long*)&w.counters[0][C_FIRSTINV]);
     } else {
         k_links_status<<<1, 1, 0, st>>>(w.counters[0], ctx->d_status);
         FF_LAUNCH_CHECK("k_links_status");
@@ -661,7 +766,7 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
         if (ctx->ev_start) FF_CUDA(cudaEventRecord(ctx->ev_start, st));
         if (!ctx->have_seq)                                // the previous call took the multi-kernel path: links from its arrays
             FF_LAUNCH("k_links_seq", k_links_seq, (int)((S + 255) / 256), 256, 0, st, w.rank[bank], w.order[bank], w.chain[bank],
-                      w.counters[bank], (int)S, w.link[bank], (unsigned long long*)nullptr);
+                      w.counters[bank], (int)S, 1, w.link[bank], (unsigned long long*)nullptr);
         if (int rc = launch_fused(ctx, w, bank, hidden, hidden_out, dtype, S, H, thr, bound, ap, st)) return rc;
         ctx->fresh_links = 0;
         if (ctx->ev_stop) FF_CUDA(cudaEventRecord(ctx->ev_stop, st));
@@ -676,6 +781,23 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
         return FF_OK;
     }
     if (!ctx->have_order) return fail(FF_E_BADARG, "by-patch order not in the workspace (the read-once kernel does not keep it): call ff_build_links");
+
+    FramePlan fp;
+    if (!(flags & 2) && frame_plan(ctx, hidden, hidden_out, dtype, S, H, thr, &fp)) {
+        if (ctx->ev_start) FF_CUDA(cudaEventRecord(ctx->ev_start, st));
+        if (int rc = launch_frame(ctx, w, bank, fp, hidden, hidden_out, dtype, S, H, thr, bound, ap, st)) return rc;
+        if (ctx->ev_stop) FF_CUDA(cudaEventRecord(ctx->ev_stop, st));
+        ctx->count_clean[bank] = 0;
+        ctx->count_clean[nb] = 1;
+        ctx->last_parity = bank;
+        ctx->parity = nb;
+        ctx->links_S = -2;
+        ctx->have_order = 1;                               // the kernel leaves the compact by-patch arrays of the next call
+        ctx->have_seq = 0;
+        ctx->fresh_links = 0;
+        ctx->last_fused = 0;
+        return FF_OK;
+    }
 
     if (!ctx->count_clean[bank]) FF_CUDA(cudaMemsetAsync(&w.counters[bank][C_COUNT], 0, 8, st));
     ctx->count_clean[bank] = 0;
@@ -893,6 +1015,13 @@ int ff_compact_mask(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* mask, v
         default: return fail(FF_E_BADARG, "elem_bytes %lld", (long long)elem_bytes);
     }
     FF_LAUNCH_CHECK("k_compact_mask");
+    return FF_OK;
+}
+
+int ff_debug_frame_trace(ff_ctx* ctx, void* device_buf, int64_t bytes) {
+    if (!ctx) return fail(FF_E_BADARG, "null ctx");
+    ctx->frame_trace = (long long*)device_buf;
+    ctx->frame_trace_bytes = device_buf ? bytes : 0;
     return FF_OK;
 }
 

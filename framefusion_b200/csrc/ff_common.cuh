@@ -34,6 +34,8 @@ enum Counter {
     C_NNEXT = 9,    // N of the links written for the next call
     C_TICKET2 = 10, // records handed out to the rows outside the chains (k_keep_scan / k_decide_scan)
     C_FIRSTINV = 11,// S - (first chain row), 0 if there is none (k_links_seq; order of the read-once kernel's S units)
+    C_SPANS = 12,   // spans of consecutive chain rows in the sequence (k_links_seq, first call of a prefill)
+    C_NONUNI = 13,  // != 0: inside a span the patch ids do not run 0, 1, .., P-1, 0, 1, .. (k_links_seq)
     C_SLOTS = 32
 };
 

@@ -571,10 +571,12 @@ k_fused_merge(const __grid_constant__ FusedArgs a, const __grid_constant__ AuxPa
     if (err && lane == 0) a.status[FF_ST_INTERNAL] = 1;
 }
 
-// (pred, succ) of every sequence row from the compact by-patch arrays (ff_links.cuh / the scan kernels)
+// (pred, succ) of every sequence row from the compact by-patch arrays (ff_links.cuh / the scan kernels).  On the first
+// call of a prefill (first_inv != null) it also says whether the sequence is a uniform video — ONE span of chain rows
+// whose patch ids run 0, 1, .., n_ids - 1, 0, 1, .. — which is what the frame-pipelined kernel (ff_frame.cuh) serves.
 __global__ void __launch_bounds__(256)
 k_links_seq(const int* __restrict__ rank, const int* __restrict__ order, const int* __restrict__ chain,
-            const int64_t* __restrict__ counters, int S, int2* __restrict__ link, unsigned long long* first_inv) {
+            int64_t* __restrict__ counters, int S, int n_ids, int2* __restrict__ link, unsigned long long* first_inv) {
     pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S) return;
@@ -585,7 +587,16 @@ k_links_seq(const int* __restrict__ rank, const int* __restrict__ order, const i
         const int c = chain[j];
         l.x = (j > 0 && chain[j - 1] == c) ? order[j - 1] : -1;
         l.y = (j + 1 < N && chain[j + 1] == c) ? order[j + 1] : -1;
-        if (first_inv && (i == 0 || rank[i - 1] < 0)) atomicMax(first_inv, (unsigned long long)(S - i));   // start of a span of chain rows
+        if (first_inv) {
+            const int jp = i > 0 ? rank[i - 1] : -1;
+            if (jp < 0) {                                       // start of a span of chain rows
+                atomicMax(first_inv, (unsigned long long)(S - i));
+                atomicAdd((unsigned long long*)&counters[C_SPANS], 1ull);
+                if (c != 0) counters[C_NONUNI] = 1;
+            } else if (c != (chain[jp] + 1) % n_ids) {
+                counters[C_NONUNI] = 1;
+            }
+        }
     }
     link[i] = l;
 }

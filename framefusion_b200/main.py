@@ -379,7 +379,7 @@ class FrameFusion(nn.Module):
             # multi-kernel path: the scan kernel writes the status block before the gather runs, and the host goes on
             # while the rows move (everything it enqueues next is ordered behind them).  The read-once kernel reports at
             # its very end, a timed-out wait (FF_ST_INTERNAL) even later: wait for the stream.
-            wait = st.lib.ff_stream_sync if flags else st.lib.ff_status_wait
+            wait = st.lib.ff_stream_sync if flags & 1 else st.lib.ff_status_wait
             _lib.check(wait(st.ctx, stream))
 
         try:
@@ -394,15 +394,16 @@ class FrameFusion(nn.Module):
             launch(0)
         status = st.status
         ran_fused = bool(fused) and int(status[_lib.ST_FUSED]) == 1
-        if ran_fused and int(status[_lib.ST_INTERNAL]) != 0:
-            raise _lib.FFError("framefusion_b200: a wait inside the read-once merge kernel timed out")
-        if ran_fused and int(status[_lib.ST_ERROR]) == 3:
-            # the read-once kernel speculates on the threshold branch; the count says top-k: redo with the multi-kernel
-            # path (the input is untouched)
+        ran_frame = int(status[_lib.ST_FUSED]) == 2        # the library took the frame-pipelined kernel (first call of a prefill)
+        if (ran_fused or ran_frame) and int(status[_lib.ST_INTERNAL]) != 0:
+            raise _lib.FFError("framefusion_b200: a wait inside the single-launch merge kernel timed out")
+        if (ran_fused or ran_frame) and int(status[_lib.ST_ERROR]) == 3:
+            # the single-launch kernels speculate on the threshold branch (and the frame-pipelined one on a uniform video
+            # layout); the device says otherwise: redo with the multi-kernel path (the input is untouched)
             self._links_for = None
             self._ensure_links(st, q_len, need_order=True)
-            launch(0)
-            ran_fused = False
+            launch(2)
+            ran_fused = ran_frame = False
         err = int(status[_lib.ST_ERROR])
         if err == 1:
             raise ZeroDivisionError("division by zero")                      # frame_token_num == 0 (main.py:114)
@@ -427,7 +428,7 @@ class FrameFusion(nn.Module):
             else:
                 self._record_merge_trace(st, hidden, q_len, int(status[_lib.ST_NCHAIN]), branch)
 
-        if not ran_fused and int(status[_lib.ST_NMERGED]) == 0:
+        if not ran_fused and not ran_frame and int(status[_lib.ST_NMERGED]) == 0:
             # nothing was merged: the sequence is unchanged and the gather kernel did not run — hand the inputs back
             # (the reference returns copies with the same values; its callers rebind them, modeling_qwen2.py:46,67)
             self._links_for = (self.patch_type, self.patch_type._version, device)

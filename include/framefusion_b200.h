@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FF_ABI_VERSION 3
+#define FF_ABI_VERSION 4
 
 enum ff_dtype { FF_BF16 = 0, FF_F16 = 1, FF_F32 = 2 };
 
@@ -51,13 +51,16 @@ enum ff_status_slot {
     FF_ST_NCHAIN = 3,      /* N: tokens whose patch id is in [0, n_ids)             (main.py:208-214) */
     FF_ST_BRANCH = 4,      /* 0 = threshold branch, 1 = top-k branch                (main.py:116-127) */
     FF_ST_TOPK = 5,        /* k used by the branch that ran (merge top-k or prune top-k) */
-    FF_ST_ERROR = 6,       /* device-side error: 0 ok, 1 n_vis == 0, 2 k > N, 3 the read-once kernel speculated on the
-                              threshold branch and the count says top-k: call again without flag bit 0 */
+    FF_ST_ERROR = 6,       /* device-side error: 0 ok, 1 n_vis == 0, 2 k > N, 3 a single-launch kernel (FUSED = 1 or 2) could
+                              not serve the call — it speculated on the threshold branch and the count says top-k, or the
+                              sequence is not the uniform video the frame-pipelined kernel is built for: hidden is
+                              untouched, rebuild the links and call again with flags = 2 */
     FF_ST_NMERGED = 7,     /* tokens merged away by this call */
-    FF_ST_FUSED = 8,       /* 1 if the read-once kernel produced this result, 0 for the multi-kernel path */
+    FF_ST_FUSED = 8,       /* 0 multi-kernel path, 1 the read-once kernel, 2 the frame-pipelined kernel (first merge call of a
+                              prefill on a uniform video) */
     FF_ST_SEQ = 10,        /* number of the reducing call whose results the block holds: written LAST, after a system-wide
                             * fence, by the kernel that decides the call (ff_status_wait) */
-    FF_ST_INTERNAL = 9,    /* 1 if a wait inside the read-once kernel gave up (the results of the call are invalid) */
+    FF_ST_INTERNAL = 9,    /* 1 if a wait inside a single-launch kernel gave up (the results of the call are invalid) */
     FF_ST_SLOTS = 16
 };
 
@@ -131,7 +134,11 @@ int ff_merge_apply(ff_ctx* ctx, void* ws, int64_t ws_bytes, void* hidden, int dt
  * hidden [S,H] is read only; hidden_out must hold S rows (only S_keep are written).  patch_type is aux[0]
  * by convention of the host wrapper but the library does not care.  status: SEQ_KEEP, COUNT, NVIS, NCHAIN,
  * BRANCH, TOPK, ERROR, NMERGED, FUSED, INTERNAL.  `flags`: bit 0 = allow the read-once kernel (one launch, one HBM
- * read of hidden; it handles the threshold branch and reports ERROR = 3 otherwise, leaving hidden untouched). */
+ * read of hidden; it handles the threshold branch and reports ERROR = 3 otherwise, leaving hidden untouched);
+ * bit 1 = do NOT use the frame-pipelined kernel.  Without bit 1 the first merge call after ff_build_links runs as ONE
+ * launch in which every row travels HBM -> shared memory -> HBM once (csrc/ff_frame.cuh) whenever the row size allows
+ * it; the kernel checks on the device that the sequence is a uniform video (one span of chain rows, patch ids
+ * 0 .. n_ids-1 repeating) and that the threshold branch applies, and reports ERROR = 3 / FUSED = 2 otherwise. */
 int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, void* hidden_out, int dtype,
                    int64_t seq_len, int64_t hidden_size, double thr, double bound, const ff_aux* aux,
                    int n_aux, int flags, void* stream);
@@ -165,6 +172,11 @@ int ff_compact_mask(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* mask, v
  *       1 and 3 exist after a multi-kernel call only */
 int ff_debug_read(ff_ctx* ctx, void* ws, int64_t ws_bytes, int what, void* dst_device, int64_t n, int dtype,
                   void* stream);
+
+/* ---- measurement aid: the next frame-pipelined launch writes %globaltimer stamps into device_buf, laid out
+ * [CTA][frame][8] int64 (0 load requested, 1 similarity done, 2 destinations known, 3 rows out, 4 aux rows out);
+ * null switches it off.  The buffer must stay alive until that launch has run. */
+int ff_debug_frame_trace(ff_ctx* ctx, void* device_buf, int64_t bytes);
 
 #ifdef __cplusplus
 }
