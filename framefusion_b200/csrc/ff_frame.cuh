@@ -41,6 +41,31 @@ constexpr int FR_MAXSTAGES = 16;                   // ring stages (frames in sha
 constexpr int FR_NQ = 32;                          // frames the flag / destination rings in shared memory hold (> stages + 2)
 constexpr int FR_META = 2048;                      // bytes of shared memory in front of the stages
 constexpr long long FR_TIMEOUT_NS = 400ll * 1000 * 1000;   // a launch older than this gives up at its next wait
+constexpr int FR_PW = 4;                           // 32-word chunks of flag words one poll of the prefix warp can fetch
+#ifndef FR_G_EARLY_ADD
+#define FR_G_EARLY_ADD 1                           // G warps add run members before the destination of the anchor is known
+#endif
+#ifndef FR_AUX_BATCH
+#define FR_AUX_BATCH 1                             // frames an aux warp moves per round (1 or 2)
+#endif
+#ifndef FR_INFLIGHT
+#define FR_INFLIGHT 16                             // bulk loads a CTA keeps outstanding (16: as many as the ring allows)
+#endif
+#ifndef FR_SW
+#define FR_SW 1                                    // similarity warps per chain in the build for up to four chains per CTA
+#endif
+#ifndef FR_S_FENCE
+#define FR_S_FENCE 0
+#endif
+#ifndef FR_NPW
+#define FR_NPW 3                                   // prefix warps (they take the frames in turn)
+#endif
+#ifndef FR_PF
+#define FR_PF 1                                    // frames one poll looks at
+#endif
+#ifndef FR_POLL_NS
+#define FR_POLL_NS 64                              // pause after a poll that retired nothing
+#endif
 constexpr int FR_TRACE_K = 8;                      // time stamps per (CTA, frame) of a traced launch
 
 struct FrameArgs {
@@ -70,13 +95,13 @@ struct FrameArgs {
 
 struct FrameShared {
     unsigned long long full[FR_MAXSTAGES];         // mbarriers: stage loaded
-    volatile int s_done[FR_MAXR];                  // frames whose similarity S warp w has finished
+    volatile int s_cnt[FR_MAXR][2];                // frames S warp (w, h) has finished: it takes the frames f = h (mod SW)
     volatile int g_free[FR_MAXR];                  // G warp w no longer needs the stages of frames below this
     volatile int a_done[FR_MAXR];                  // frames aux warp w has finished
     volatile int p_done;                           // frames whose destinations are in dstv[]
     volatile int abort;
     volatile int base_total;                       // kept rows before the first row behind the span
-    int pad;
+    volatile int base_next;                        // kept rows before the next frame to be published (prefix warps)
     volatile int dstv[FR_NQ][FR_MAXR];
     volatile unsigned char kept[FR_NQ][FR_MAXR];
 };
@@ -104,7 +129,7 @@ __device__ __forceinline__ void fr_tma_store(void* dst, uint32_t src_smem, uint3
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(src_smem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void fr_tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void fr_tma_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void fr_tma_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fr_tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fr_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint4 fr_lds16(uint32_t addr) {
@@ -136,13 +161,21 @@ struct FrameCtx {
         return true;
     }
     // whole warp: until *ctr >= need; false once the kernel is giving up
-    __device__ __forceinline__ bool wait_ge(const volatile int* ctr, int need) const {
+    // (waiting warps share their scheduler with the warps that work: the ones with slack sleep longer between polls)
+    __device__ __forceinline__ bool wait_ge(const volatile int* ctr, int need, unsigned sleep_ns = 32) const {
         int spins = 0;
         while (*ctr < need) {
             if (sh->abort || expired(++spins)) return false;
-            __nanosleep(20);
+            __nanosleep(sleep_ns);
         }
         return true;
+    }
+    // whole warp: until the similarity of frames 0 .. f of chain w is there (SW warps per chain take the frames in turn)
+    template <int SW>
+    __device__ __forceinline__ bool wait_s(int w, int f, unsigned sleep_ns = 32) const {
+        if (SW == 1) return wait_ge(&sh->s_cnt[w][0], f + 1, sleep_ns);
+        if (!wait_ge(&sh->s_cnt[w][f & 1], (f >> 1) + 1, sleep_ns)) return false;
+        return f == 0 || wait_ge(&sh->s_cnt[w][(f - 1) & 1], ((f - 1) >> 1) + 1, sleep_ns);
     }
 };
 
@@ -186,10 +219,8 @@ __device__ __forceinline__ void fr_nb(const uint4& vc, float2& nb) {
     }
 }
 
-// the aux rows of sequence row r -> destination row d (one piece per lane and entry when the tensors have that form)
-__device__ __forceinline__ void frame_aux(const AuxFlat& f, const AuxPack& aux, int r, int d, int lane) {
-    if (f.n < 0) { gather_aux_rows(aux, r, d, lane); return; }
-    uint4 v[8];
+// the aux rows of sequence row r -> destination row d, one 16- or 8-byte piece per lane and entry: all loads, then all stores
+__device__ __forceinline__ void frame_aux_load(const AuxFlat& f, int r, int lane, uint4* v) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         v[e] = make_uint4(0, 0, 0, 0);
@@ -200,6 +231,8 @@ __device__ __forceinline__ void frame_aux(const AuxFlat& f, const AuxPack& aux, 
             else if (lane * 16 < rb) v[e] = __ldg(reinterpret_cast<const uint4*>(s) + lane);
         }
     }
+}
+__device__ __forceinline__ void frame_aux_store(const AuxFlat& f, int d, int lane, const uint4* v) {
 #pragma unroll
     for (int e = 0; e < 8; ++e)
         if (e < f.n) {
@@ -208,6 +241,12 @@ __device__ __forceinline__ void frame_aux(const AuxFlat& f, const AuxPack& aux, 
             if (f.piece[e] == 8) { if (lane * 8 < rb) reinterpret_cast<uint2*>(o)[lane] = make_uint2(v[e].x, v[e].y); }
             else if (lane * 16 < rb) reinterpret_cast<uint4*>(o)[lane] = v[e];
         }
+}
+__device__ __forceinline__ void frame_aux(const AuxFlat& f, const AuxPack& aux, int r, int d, int lane) {
+    if (f.n < 0) { gather_aux_rows(aux, r, d, lane); return; }
+    uint4 v[8];
+    frame_aux_load(f, r, lane, v);
+    frame_aux_store(f, d, lane, v);
 }
 
 // the call is decided: sizes, the speculated branch, the counters of the next call (main.py:112-120)
@@ -238,10 +277,380 @@ __device__ __forceinline__ void frame_finish(const FrameArgs& a, long long N, lo
     *(volatile int64_t*)&a.status[FF_ST_SEQ] = a.seq;
 }
 
+#define FR_NOTE(f, k, val) do { if (a.trace && (f) < a.trace_frames) a.trace[((int64_t)blockIdx.x * a.trace_frames + (f)) * FR_TRACE_K + (k)] = (val); } while (0)
 #define FR_STAMP(f, k) do { if (a.trace && (f) < a.trace_frames) a.trace[((int64_t)blockIdx.x * a.trace_frames + (f)) * FR_TRACE_K + (k)] = fr_time(); } while (0)
 
-template <int DT, int MAXR>
-__global__ void __launch_bounds__(32 * (2 + 3 * MAXR), 1)
+// what every role of a CTA knows (the roles are inlined: as separate functions they read the kernel arguments through
+// memory and ran 40 % slower)
+struct FrameGeo {
+    FrameShared* sh;
+    FrameCtx cx;
+    int F, first, p0, Rc, NS, R, P, S, lane;
+    long long N;
+    int64_t rb;
+    uint32_t stage_bytes, stages0, acc0;
+};
+
+__device__ __forceinline__ void fr_role_producer(const FrameArgs& a, const AuxPack& aux, const FrameGeo& g, int w_role) {
+    FrameShared* const sh = g.sh;
+    const FrameCtx cx = g.cx;
+    const int F = g.F, first = g.first, p0 = g.p0, Rc = g.Rc, NS = g.NS, R = g.R, P = g.P, S = g.S, lane = g.lane;
+    const long long N = g.N;
+    const int64_t rb = g.rb;
+    const uint32_t stage_bytes = g.stage_bytes, stages0 = g.stages0, acc0 = g.acc0;
+    (void)F; (void)first; (void)p0; (void)Rc; (void)NS; (void)R; (void)P; (void)S; (void)lane; (void)N; (void)rb; (void)stage_bytes; (void)stages0; (void)acc0; (void)sh;
+    // ================================ producer ================================
+    if (lane == 0) {
+        for (int f = 0; f < F; ++f) {
+            const int st = f % NS;
+            if (f >= NS) {
+                // the stage is free once the G warps are through frame f - NS; the aux warps touch no stage, they only
+                // have to stay within the flag / destination rings (FR_NQ frames)
+                bool ok = true;
+                for (int w = 0; w < Rc && ok; ++w) ok = cx.wait_ge(&sh->g_free[w], f - NS + 1) && cx.wait_ge(&sh->a_done[w], f - (FR_NQ - 4));
+                if (!ok) break;
+            }
+            if (FR_INFLIGHT < FR_MAXSTAGES && f >= FR_INFLIGHT) {
+                // no more than FR_INFLIGHT loads outstanding: everything this SM asks of the memory system — the polls
+                // of the prefix warp above all — waits behind the bulk data already requested
+                const int fo = f - FR_INFLIGHT;
+                const uint32_t bo = fr_smem_u32(&sh->full[fo % NS]), po = (uint32_t)((fo / NS) & 1);
+                int spins = 0;
+                bool ok = true;
+                while (!fr_mbar_try_wait(bo, po)) {
+                    if (sh->abort || cx.expired(++spins)) { ok = false; break; }
+                }
+                if (!ok) break;
+            }
+            const uint32_t bar = fr_smem_u32(&sh->full[st]);
+            const uint32_t bytes = (uint32_t)(Rc * rb);
+            fr_mbar_expect_tx(bar, bytes);
+            fr_tma_load(stages0 + (uint32_t)st * stage_bytes, a.hidden + ((int64_t)first + (int64_t)f * P + p0) * rb, bytes, bar);
+            FR_STAMP(f, 0);
+        }
+    }
+}
+
+template <int SW>
+__device__ __forceinline__ void fr_role_prefix(const FrameArgs& a, const AuxPack& aux, const FrameGeo& g, int w_role) {
+    FrameShared* const sh = g.sh;
+    const FrameCtx cx = g.cx;
+    const int F = g.F, first = g.first, p0 = g.p0, Rc = g.Rc, NS = g.NS, R = g.R, P = g.P, S = g.S, lane = g.lane;
+    const long long N = g.N;
+    const int64_t rb = g.rb;
+    const uint32_t stage_bytes = g.stage_bytes, stages0 = g.stages0, acc0 = g.acc0;
+    (void)F; (void)first; (void)p0; (void)Rc; (void)NS; (void)R; (void)P; (void)S; (void)lane; (void)N; (void)rb; (void)stage_bytes; (void)stages0; (void)acc0; (void)sh;
+    // ================================ prefix: FR_NPW warps take the frames in turn ================================
+    // A poll of the flag words is a round trip through a memory system busy with bulk copies (1 - 2 us), and a frame
+    // needs at least one: ONE warp doing the frames one after the other made that round trip the period of the whole
+    // pipeline.  So warp k polls the frames k, k + FR_NPW, ..: it counts the kept rows of its frame and the prefixes of
+    // the CTA's own rows as soon as every patch has reported, then takes the running base from the warp of the previous
+    // frame through shared memory (p_done / base_next) and publishes.
+    const int kw = w_role;
+    int polls = 0;
+    for (int f = kw; f < F; f += FR_NPW) {
+        // nobody has all the flags of a frame before this CTA's own S warps are through it
+        bool ok = true;
+        for (int w = 0; w < Rc && ok; ++w) ok = cx.template wait_s<SW>(w, f);
+        if (!ok) break;
+        const int lo = first + f * P, hi = lo + P;      // rows of the frame
+        const int w_lo = lo >> 5, w_hi = (hi - 1) >> 5;
+        int total = 0;                                  // kept rows of the frame
+        int mine[FR_MAXR];                              // kept rows of the frame in front of the CTA's row w (lane 0 .. whoever holds the word)
+#pragma unroll
+        for (int w = 0; w < FR_MAXR; ++w) mine[w] = 0;
+        for (int c0 = w_lo; c0 <= w_hi && ok; c0 += 32) {
+            const int wi = c0 + lane;
+            unsigned need = 0u;
+            if (wi <= w_hi) {
+                need = 0xffffffffu;
+                if (wi == w_lo) need &= 0xffffffffu << (lo & 31);
+                if (wi == w_hi) need &= 0xffffffffu >> (31 - ((hi - 1) & 31));
+            }
+            unsigned long long v = 0ull;
+            while (true) {
+                if (need) v = ld_relaxed64(a.words + wi);
+                if (__all_sync(FULL, ((unsigned)(v >> 32) & need) == need)) break;
+                ++polls;
+                if (sh->abort || ((polls & 63) == 0 && ld_relaxed32(a.gbar + 1) != 0u) || cx.expired(polls)) { ok = false; break; }
+                __nanosleep(FR_POLL_NS);
+            }
+            if (!ok) break;
+            const unsigned km = (unsigned)v & need;
+            const int k = __popc(km);
+            int incl = k;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+#pragma unroll
+            for (int w = 0; w < FR_MAXR; ++w) {
+                const int r = lo + p0 + w;
+                const int here = (w < Rc && (r >> 5) == wi) ? total + incl - k + __popc(km & ((1u << (r & 31)) - 1u)) : 0;
+                mine[w] += __shfl_sync(FULL, here, (r >> 5) - c0 < 32 && (r >> 5) >= c0 ? (r >> 5) - c0 : 0);
+            }
+            total += __shfl_sync(FULL, incl, 31);
+        }
+        if (!ok) { sh->abort = 1; break; }
+        // the frames in front of this one are published by the other prefix warps
+        if (!cx.wait_ge(&sh->p_done, f)) break;
+        if (lane == 0) {
+            const int base = f == 0 ? first : sh->base_next;   // rows in front of the span are all kept
+#pragma unroll
+            for (int w = 0; w < FR_MAXR; ++w)
+                if (w < Rc) sh->dstv[f % FR_NQ][w] = base + mine[w];
+            sh->base_next = base + total;
+            if (f == F - 1) sh->base_total = base + total;
+            sh->p_done = f + 1;
+            FR_STAMP(f, 2);
+        }
+        __syncwarp();
+    }
+}
+
+template <int DT, int SW>
+__device__ __forceinline__ void fr_role_sim(const FrameArgs& a, const AuxPack& aux, const FrameGeo& g, int w_role) {
+    FrameShared* const sh = g.sh;
+    const FrameCtx cx = g.cx;
+    const int F = g.F, first = g.first, p0 = g.p0, Rc = g.Rc, NS = g.NS, R = g.R, P = g.P, S = g.S, lane = g.lane;
+    const long long N = g.N;
+    const int64_t rb = g.rb;
+    const uint32_t stage_bytes = g.stage_bytes, stages0 = g.stages0, acc0 = g.acc0;
+    (void)F; (void)first; (void)p0; (void)Rc; (void)NS; (void)R; (void)P; (void)S; (void)lane; (void)N; (void)rb; (void)stage_bytes; (void)stages0; (void)acc0; (void)sh;
+    // ================================ similarity, chain p0 + w, frames h, h + SW, .. ================================
+    // A row takes one warp ~1 us (a few hundred dependent instructions, two warp reductions, the rounding chain): with ONE
+    // warp per chain that is the period of the whole pipeline.  Two warps take the frames in turn (each then sums both
+    // norms itself); with one warp the norm of the previous row is carried in a register.
+    const int w = w_role % R, h = w_role / R;
+    if (w < Rc) {
+        const int p = p0 + w;
+        float na_prev = 0.f;
+        long long c_wait = 0, c_busy = 0, c0 = clock64();   // (traced launches: where this warp's cycles go)
+        for (int f = h; f < F; f += SW) {
+            const int st = f % NS;
+            const uint32_t bar = fr_smem_u32(&sh->full[st]);
+            const uint32_t parity = (uint32_t)((f / NS) & 1);
+            int spins = 0;
+            bool ok = true;
+            while (!fr_mbar_try_wait(bar, parity)) {
+                if (sh->abort || cx.expired(++spins)) { ok = false; break; }
+            }
+            if (SW > 1 && f > 0 && ok) {
+                // the previous frame was another warp's: this one has to see ITS stage complete as well (a warp that has
+                // not observed the barrier has no promise that the bulk copy's bytes are visible to it)
+                const uint32_t bp = fr_smem_u32(&sh->full[(f - 1) % NS]), pp = (uint32_t)(((f - 1) / NS) & 1);
+                while (!fr_mbar_try_wait(bp, pp)) {
+                    if (sh->abort || cx.expired(++spins)) { ok = false; break; }
+                }
+            }
+            if (!ok) break;
+            if (w == 0 && lane == 0) FR_STAMP(f, 5);    // the frame's rows are in shared memory
+            if (a.trace) { const long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
+            const uint32_t cur = stages0 + (uint32_t)st * stage_bytes + (uint32_t)(w * rb) + lane * 16;
+            const uint32_t prv = stages0 + (uint32_t)((f + NS - 1) % NS) * stage_bytes + (uint32_t)(w * rb) + lane * 16;
+            float2 d0 = make_float2(0.f, 0.f), d1 = d0, b0 = d0, b1 = d0, a0 = d0, a1 = d0;
+            const int nvec = a.nvec;
+            if (f > 0) {
+#pragma unroll 2
+                for (int v = lane; v < nvec; v += 64) {
+                    const uint4 pa = fr_lds16(prv + (v - lane) * 16), ca = fr_lds16(cur + (v - lane) * 16);
+                    uint4 pb = make_uint4(0, 0, 0, 0), cb = pb;
+                    const bool two = v + 32 < nvec;
+                    if (two) { pb = fr_lds16(prv + (v - lane + 32) * 16); cb = fr_lds16(cur + (v - lane + 32) * 16); }
+                    if (SW == 1) {
+                        fr_dot_nb<DT>(pa, ca, d0, b0);
+                        if (two) fr_dot_nb<DT>(pb, cb, d1, b1);
+                    } else {
+                        acc_pair2<DT>(pa, ca, d0, a0, b0);
+                        if (two) acc_pair2<DT>(pb, cb, d1, a1, b1);
+                    }
+                }
+            } else {
+                for (int v = lane; v < nvec; v += 64) {
+                    fr_nb<DT>(fr_lds16(cur + (v - lane) * 16), b0);
+                    if (v + 32 < nvec) fr_nb<DT>(fr_lds16(cur + (v - lane + 32) * 16), b1);
+                }
+            }
+            const float dot = warp_sum((d0.x + d0.y) + (d1.x + d1.y));
+            const float nb = warp_sum((b0.x + b0.y) + (b1.x + b1.y));
+            if (SW != 1) na_prev = warp_sum((a0.x + a0.y) + (a1.x + a1.y));
+            float s = -2.0f;                            // IGNORE_TOKEN at chain heads (main.py:225-238)
+            if (f > 0) s = finish_cosine<DT>(dot, na_prev, nb);
+            na_prev = nb;
+            const unsigned kept = !(f > 0 && s >= a.thr);   // NaN compares false: kept
+            if (lane == 0) {
+                // No fence in this loop: a fence waits for the thread's outstanding GLOBAL writes to be acknowledged
+                // (a microsecond each frame).  Shared memory is written and read in program order on an SM: the flag
+                // first, then the counter that says it is there (both volatile), then the global writes.
+                const int r = first + f * P + p;
+                const int64_t j = (int64_t)p * F + f;
+                sh->kept[f % FR_NQ][w] = (unsigned char)kept;
+                sh->s_cnt[w][h] = f / SW + 1;
+                red_add64(a.words + (r >> 5), (1ull << (32 + (r & 31))) | ((unsigned long long)kept << (r & 31)));
+                a.sim[j] = s;
+                a.flag[j] = (uint8_t)(kept ^ 1u);
+                if (FR_S_FENCE) __threadfence_block();
+                if (w == 0) FR_STAMP(f, 1);
+            }
+            __syncwarp();
+            if (a.trace) { const long long c1 = clock64(); c_busy += c1 - c0; c0 = c1; }
+        }
+        if (w == 0 && h == 0 && lane == 0) { FR_NOTE(0, 7, c_busy); FR_NOTE(1, 7, c_wait); }
+    }
+}
+
+template <int DT, int SW>
+__device__ __forceinline__ void fr_role_merge(const FrameArgs& a, const AuxPack& aux, const FrameGeo& g, int w_role) {
+    FrameShared* const sh = g.sh;
+    const FrameCtx cx = g.cx;
+    const int F = g.F, first = g.first, p0 = g.p0, Rc = g.Rc, NS = g.NS, R = g.R, P = g.P, S = g.S, lane = g.lane;
+    const long long N = g.N;
+    const int64_t rb = g.rb;
+    const uint32_t stage_bytes = g.stage_bytes, stages0 = g.stages0, acc0 = g.acc0;
+    (void)F; (void)first; (void)p0; (void)Rc; (void)NS; (void)R; (void)P; (void)S; (void)lane; (void)N; (void)rb; (void)stage_bytes; (void)stages0; (void)acc0; (void)sh;
+    const int w_g = w_role;
+    // ================================ merge + rows out, chain p0 + w_g ================================
+    // Step f looks one row ahead: if row f + 1 merges, it is added NOW — into the raw row f if that one is kept (it
+    // opens the run), else into the running sum — and if row f + 2 is kept the same pass divides and the row goes
+    // out.  A kept row with a kept successor goes out as it is.  So step f is the last reader of stage f.
+    if (w_g < Rc) {
+        const int w = w_g;
+        const uint32_t accp = acc0 + (uint32_t)(w * rb);
+        const int nvec = a.nvec;
+        int L = 0, anchor_d = -1;
+        long long c_wait = 0, c_busy = 0, c0 = clock64();
+        for (int f = 0; f < F; ++f) {
+            if (!cx.template wait_s<SW>(w, min(f + 3, F) - 1, 100)) break;
+            if (a.trace) { const long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
+            const bool kept = sh->kept[f % FR_NQ][w] != 0;
+            const bool nxt_kept = f + 1 < F ? sh->kept[(f + 1) % FR_NQ][w] != 0 : true;
+            const bool nn_kept = f + 2 < F ? sh->kept[(f + 2) % FR_NQ][w] != 0 : true;
+            const uint32_t cur = stages0 + (uint32_t)(f % NS) * stage_bytes + (uint32_t)(w * rb);
+            if (kept) L = 0;
+#if !FR_G_EARLY_ADD
+            if (!cx.wait_ge(&sh->p_done, f + 1)) break;
+#endif
+            if (!nxt_kept) {
+                // the arithmetic needs no destination: it runs ahead of the prefix warp
+                const uint32_t nxt = stages0 + (uint32_t)((f + 1) % NS) * stage_bytes + (uint32_t)(w * rb);
+                const uint32_t src = kept ? cur : accp;       // the anchor itself, or the running sum
+                ++L;
+                if (nn_kept) {
+                    const Divider<DT> dv(L + 1);
+#pragma unroll 2
+                    for (int v = lane; v < nvec; v += 32) {
+                        const uint4 y = fr_lds16(src + v * 16), x = fr_lds16(nxt + v * 16);
+                        fr_sts16(accp + v * 16, dv.vec_fast(Num<DT>::add_vec(y, x)));    // T(T(acc + member) / T(L + 1))
+                    }
+                    fr_fence_async();
+                } else {
+#pragma unroll 2
+                    for (int v = lane; v < nvec; v += 32) {
+                        const uint4 y = fr_lds16(src + v * 16), x = fr_lds16(nxt + v * 16);
+                        fr_sts16(accp + v * 16, Num<DT>::add_vec(y, x));                  // T(acc + member), main.py:304
+                    }
+                }
+            }
+            if (kept) {
+                if (a.trace) { const long long c1 = clock64(); c_busy += c1 - c0; c0 = c1; }
+                if (!cx.wait_ge(&sh->p_done, f + 1)) break;
+                if (a.trace) { const long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
+                anchor_d = sh->dstv[f % FR_NQ][w];
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (nxt_kept) { if (kept) fr_tma_store(a.out + (int64_t)anchor_d * rb, cur, (uint32_t)rb); }
+                else if (nn_kept) fr_tma_store(a.out + (int64_t)anchor_d * rb, accp, (uint32_t)rb);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                fr_tma_commit();
+                fr_tma_wait_read_0();                   // this step's store has left shared memory: stage f is free
+                sh->g_free[w] = f + 1;
+                if (w == 0) FR_STAMP(f, 3);
+            }
+            __syncwarp();
+            if (a.trace) { const long long c1 = clock64(); c_busy += c1 - c0; c0 = c1; }
+        }
+        if (w == 0 && lane == 0) { FR_NOTE(2, 7, c_busy); FR_NOTE(3, 7, c_wait); }
+        if (lane == 0) fr_tma_wait_all();
+    }
+}
+
+__device__ __forceinline__ void fr_role_aux(const FrameArgs& a, const AuxPack& aux, const FrameGeo& g, int w_role) {
+    FrameShared* const sh = g.sh;
+    const FrameCtx cx = g.cx;
+    const int F = g.F, first = g.first, p0 = g.p0, Rc = g.Rc, NS = g.NS, R = g.R, P = g.P, S = g.S, lane = g.lane;
+    const long long N = g.N;
+    const int64_t rb = g.rb;
+    const uint32_t stage_bytes = g.stage_bytes, stages0 = g.stages0, acc0 = g.acc0;
+    (void)F; (void)first; (void)p0; (void)Rc; (void)NS; (void)R; (void)P; (void)S; (void)lane; (void)N; (void)rb; (void)stage_bytes; (void)stages0; (void)acc0; (void)sh;
+    const int w_a = w_role;
+    // ================================ aux rows, dst[], rows outside the chains ================================
+    const int w = w_a;
+    const int unit = blockIdx.x * R + w, n_units = gridDim.x * R;
+    const int nvec = a.nvec;
+    for (int t = unit; t < first; t += n_units) {       // rows in front of the span keep their place
+        copy_row(a.hidden + (int64_t)t * rb, a.out + (int64_t)t * rb, nvec, lane);
+        if (aux.n) frame_aux(a.auxf, aux, t, t, lane);
+        if (lane == 0) { a.dst[t] = t; a.rank_next[t] = -1; }
+    }
+    bool ok = true;
+    if (w < Rc) {
+        // two frames per round: the loads of both rows are requested before either is stored (a round is one trip
+        // through the memory system, and one frame per trip would be too slow)
+        const int p = p0 + w;
+        const bool flat = a.auxf.n >= 0;
+        int nk = 0;
+        for (int f = 0; f < F;) {
+            if (!cx.wait_ge(&sh->p_done, f + 1, 200)) { ok = false; break; }
+            const int nb = min(FR_AUX_BATCH, min((int)sh->p_done, F) - f);
+            const bool k0 = sh->kept[f % FR_NQ][w] != 0, k1 = nb > 1 && sh->kept[(f + 1) % FR_NQ][w] != 0;
+            const int d0 = k0 ? sh->dstv[f % FR_NQ][w] : -1, d1 = k1 ? sh->dstv[(f + 1) % FR_NQ][w] : -1;
+            const int r0 = first + f * P + p, r1 = r0 + P;
+            if (aux.n) {
+                if (flat) {
+                    uint4 v0[8], v1[8];
+                    if (k0) frame_aux_load(a.auxf, r0, lane, v0);
+                    if (k1) frame_aux_load(a.auxf, r1, lane, v1);
+                    if (k0) frame_aux_store(a.auxf, d0, lane, v0);
+                    if (k1) frame_aux_store(a.auxf, d1, lane, v1);
+                } else {
+                    if (k0) gather_aux_rows(aux, r0, d0, lane);
+                    if (k1) gather_aux_rows(aux, r1, d1, lane);
+                }
+            }
+            if (lane == 0) {
+                a.dst[r0] = d0;
+                a.keptdst[(int64_t)p * F + f] = d0;
+                if (nb > 1) {
+                    a.dst[r1] = d1;
+                    a.keptdst[(int64_t)p * F + f + 1] = d1;
+                }
+                sh->a_done[w] = f + nb;
+                if (w == 0) FR_STAMP(f, 4);
+            }
+            nk += (int)k0 + (int)k1;
+            f += nb;
+            __syncwarp();
+        }
+        if (lane == 0) a.len_next[p] = nk;
+    }
+    if (ok && cx.wait_ge(&sh->p_done, F)) {             // rows behind the span move up by the merged rows
+        __threadfence_block();
+        const int bt = sh->base_total, n_post = S - first - (int)N;
+        for (int t = unit; t < n_post; t += n_units) {
+            const int r = first + (int)N + t, d = bt + t;
+            copy_row(a.hidden + (int64_t)r * rb, a.out + (int64_t)d * rb, nvec, lane);
+            if (aux.n) frame_aux(a.auxf, aux, r, d, lane);
+            if (lane == 0) { a.dst[r] = d; a.rank_next[d] = -1; }
+        }
+    }
+}
+
+template <int DT, int MAXR, int SW>
+__global__ void __launch_bounds__(32 * (1 + FR_NPW + (SW + 2) * MAXR), 1)
 k_frame_merge(const __grid_constant__ FrameArgs a, const __grid_constant__ AuxPack aux) {
     extern __shared__ __align__(128) unsigned char fr_smem[];
     pdl_wait();
@@ -270,11 +679,12 @@ k_frame_merge(const __grid_constant__ FrameArgs a, const __grid_constant__ AuxPa
         for (int s = 0; s < NS; ++s) fr_mbar_init(fr_smem_u32(&sh->full[s]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         sh->p_done = 0;
+        sh->base_next = 0;
         sh->abort = 0;
         sh->base_total = 0;
     }
     if (threadIdx.x < FR_MAXR) {
-        sh->s_done[threadIdx.x] = 0;
+        sh->s_cnt[threadIdx.x][0] = sh->s_cnt[threadIdx.x][1] = 0;
         sh->g_free[threadIdx.x] = 0;
         sh->a_done[threadIdx.x] = 0;
     }
@@ -283,239 +693,24 @@ k_frame_merge(const __grid_constant__ FrameArgs a, const __grid_constant__ AuxPa
     cx.sh = sh;
     cx.gbar = a.gbar;
     cx.t_end = fr_time() + FR_TIMEOUT_NS;
+    if (threadIdx.x == 0) FR_STAMP(0, 6);                   // kernel under way
 
-    const int w_s = wid - 2, w_g = wid - 2 - R, w_a = wid - 2 - 2 * R;    // index inside the role
+    const int w_s = wid - 1 - FR_NPW, w_g = w_s - SW * R, w_a = w_s - (SW + 1) * R;    // index inside the role
 
-    if (wid == 0) {
-        // ================================ producer ================================
-        if (lane == 0) {
-            for (int f = 0; f < F; ++f) {
-                const int st = f % NS;
-                if (f >= NS) {
-                    bool ok = true;
-                    for (int w = 0; w < Rc && ok; ++w) ok = cx.wait_ge(&sh->g_free[w], f - NS + 1) && cx.wait_ge(&sh->a_done[w], f - NS + 1);
-                    if (!ok) break;
-                }
-                const uint32_t bar = fr_smem_u32(&sh->full[st]);
-                const uint32_t bytes = (uint32_t)(Rc * rb);
-                fr_mbar_expect_tx(bar, bytes);
-                fr_tma_load(stages0 + (uint32_t)st * stage_bytes, a.hidden + ((int64_t)first + (int64_t)f * P + p0) * rb, bytes, bar);
-                FR_STAMP(f, 0);
-            }
-        }
-    } else if (wid == 1) {
-        // ================================ prefix ================================
-        int base = first;                                   // rows in front of the span are all kept
-        for (int f = 0; f < F; ++f) {
-            // nobody has all the flags of frame f before this CTA's own S warps are through it
-            bool ok = true;
-            for (int w = 0; w < Rc && ok; ++w) ok = cx.wait_ge(&sh->s_done[w], f + 1);
-            if (!ok) break;
-            const int lo = first + f * P, hi = lo + P;     // rows of the frame
-            const int w_lo = lo >> 5, w_hi = (hi - 1) >> 5, nW = w_hi - w_lo + 1;
-            int running = base;
-            for (int c0 = 0; c0 < nW && ok; c0 += 32) {
-                const int wi = w_lo + c0 + lane;
-                const bool have = c0 + lane < nW;
-                unsigned need = 0u;
-                if (have) {
-                    need = 0xffffffffu;
-                    if (wi == w_lo) need &= 0xffffffffu << (lo & 31);
-                    if (wi == w_hi) need &= 0xffffffffu >> (31 - ((hi - 1) & 31));
-                }
-                unsigned long long v = 0ull;
-                int spins = 0;
-                while (true) {
-                    if (have) v = ld_relaxed64(a.words + wi);
-                    const bool done = ((unsigned)(v >> 32) & need) == need;
-                    if (__all_sync(FULL, done)) break;
-                    ++spins;
-                    if (sh->abort || ((spins & 63) == 0 && ld_relaxed32(a.gbar + 1) != 0u) || cx.expired(spins)) { ok = false; break; }
-                    __nanosleep(64);
-                }
-                if (!ok) break;
-                const unsigned km = (unsigned)v & need;
-                const int k = __popc(km);
-                int incl = k;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                for (int w = 0; w < Rc; ++w) {
-                    const int r = lo + p0 + w;
-                    if (have && (r >> 5) == wi) sh->dstv[f % FR_NQ][w] = running + incl - k + __popc(km & ((1u << (r & 31)) - 1u));
-                }
-                running += __shfl_sync(FULL, incl, 31);
-            }
-            if (!ok) { sh->abort = 1; break; }
-            base = running;
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) {
-                if (f == F - 1) sh->base_total = base;
-                __threadfence_block();
-                sh->p_done = f + 1;
-                FR_STAMP(f, 2);
-            }
-        }
-    } else if (w_s < R) {
-        // ================================ similarity, chain p0 + w_s ================================
-        if (w_s < Rc) {
-            const int w = w_s, p = p0 + w;
-            float na_prev = 0.f;
-            for (int f = 0; f < F; ++f) {
-                const int st = f % NS;
-                const uint32_t bar = fr_smem_u32(&sh->full[st]);
-                const uint32_t parity = (uint32_t)((f / NS) & 1);
-                int spins = 0;
-                bool ok = true;
-                while (!fr_mbar_try_wait(bar, parity)) {
-                    if (sh->abort || cx.expired(++spins)) { ok = false; break; }
-                }
-                if (!ok) break;
-                const uint32_t cur = stages0 + (uint32_t)st * stage_bytes + (uint32_t)(w * rb) + lane * 16;
-                const uint32_t prv = stages0 + (uint32_t)((f + NS - 1) % NS) * stage_bytes + (uint32_t)(w * rb) + lane * 16;
-                float2 d0 = make_float2(0.f, 0.f), d1 = d0, b0 = d0, b1 = d0;
-                const int nvec = a.nvec;
-                if (f > 0) {
-#pragma unroll 2
-                    for (int v = lane; v < nvec; v += 64) {
-                        const uint4 pa = fr_lds16(prv + (v - lane) * 16), ca = fr_lds16(cur + (v - lane) * 16);
-                        uint4 pb = make_uint4(0, 0, 0, 0), cb = pb;
-                        const bool two = v + 32 < nvec;
-                        if (two) { pb = fr_lds16(prv + (v - lane + 32) * 16); cb = fr_lds16(cur + (v - lane + 32) * 16); }
-                        fr_dot_nb<DT>(pa, ca, d0, b0);
-                        if (two) fr_dot_nb<DT>(pb, cb, d1, b1);
-                    }
-                } else {
-                    for (int v = lane; v < nvec; v += 64) {
-                        fr_nb<DT>(fr_lds16(cur + (v - lane) * 16), b0);
-                        if (v + 32 < nvec) fr_nb<DT>(fr_lds16(cur + (v - lane + 32) * 16), b1);
-                    }
-                }
-                const float dot = warp_sum((d0.x + d0.y) + (d1.x + d1.y));
-                const float nb = warp_sum((b0.x + b0.y) + (b1.x + b1.y));
-                float s = -2.0f;                            // IGNORE_TOKEN at chain heads (main.py:225-238)
-                if (f > 0) s = finish_cosine<DT>(dot, na_prev, nb);
-                na_prev = nb;
-                const unsigned kept = !(f > 0 && s >= a.thr);   // NaN compares false: kept
-                if (lane == 0) {
-                    const int r = first + f * P + p;
-                    const int64_t j = (int64_t)p * F + f;
-                    sh->kept[f % FR_NQ][w] = (unsigned char)kept;
-                    red_add64(a.words + (r >> 5), (1ull << (32 + (r & 31))) | ((unsigned long long)kept << (r & 31)));
-                    a.sim[j] = s;
-                    a.flag[j] = (uint8_t)(kept ^ 1u);
-                    __threadfence_block();
-                    sh->s_done[w] = f + 1;
-                    if (w == 0) FR_STAMP(f, 1);
-                }
-                __syncwarp();
-            }
-        }
-    } else if (w_g < R) {
-        // ================================ merge + rows out, chain p0 + w_g ================================
-        if (w_g < Rc) {
-            const int w = w_g;
-            const uint32_t accp = acc0 + (uint32_t)(w * rb);
-            const int nvec = a.nvec;
-            int L = 0, anchor_d = -1;
-            for (int f = 0; f < F; ++f) {
-                if (!cx.wait_ge(&sh->s_done[w], min(f + 2, F)) || !cx.wait_ge(&sh->p_done, f + 1)) break;
-                __threadfence_block();
-                const bool kept = sh->kept[f % FR_NQ][w] != 0;
-                const bool nxt_kept = f + 1 < F ? sh->kept[(f + 1) % FR_NQ][w] != 0 : true;
-                const uint32_t cur = stages0 + (uint32_t)(f % NS) * stage_bytes + (uint32_t)(w * rb);
-                if (kept) {
-                    const int d = sh->dstv[f % FR_NQ][w];
-                    if (nxt_kept) {
-                        if (lane == 0) fr_tma_store(a.out + (int64_t)d * rb, cur, (uint32_t)rb);
-                    } else {
-                        anchor_d = d;
-                        L = 0;
-                    }
-                } else {
-                    const uint32_t prv = stages0 + (uint32_t)((f + NS - 1) % NS) * stage_bytes + (uint32_t)(w * rb);
-                    const uint32_t src = L == 0 ? prv : accp;     // the anchor itself, or the running sum
-                    ++L;
-                    if (nxt_kept) {
-                        const Divider<DT> dv(L + 1);
-#pragma unroll 2
-                        for (int v = lane; v < nvec; v += 32) {
-                            const uint4 y = fr_lds16(src + v * 16), x = fr_lds16(cur + v * 16);
-                            fr_sts16(accp + v * 16, dv.vec_fast(Num<DT>::add_vec(y, x)));    // T(T(acc + member) / T(L + 1))
-                        }
-                        fr_fence_async();
-                        __syncwarp();
-                        if (lane == 0) fr_tma_store(a.out + (int64_t)anchor_d * rb, accp, (uint32_t)rb);
-                        L = 0;
-                    } else {
-#pragma unroll 2
-                        for (int v = lane; v < nvec; v += 32) {
-                            const uint4 y = fr_lds16(src + v * 16), x = fr_lds16(cur + v * 16);
-                            fr_sts16(accp + v * 16, Num<DT>::add_vec(y, x));                  // T(acc + member), main.py:304
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    fr_tma_commit();
-                    fr_tma_wait_read_1();                   // the stores of frame f - 1 have left shared memory
-                    sh->g_free[w] = f;
-                    if (w == 0) FR_STAMP(f, 3);
-                }
-                __syncwarp();
-            }
-            if (lane == 0) fr_tma_wait_all();
-        }
-    } else if (w_a < R) {
-        // ================================ aux rows, dst[], rows outside the chains ================================
-        const int w = w_a;
-        const int unit = blockIdx.x * R + w, n_units = gridDim.x * R;
-        const int nvec = a.nvec;
-        for (int t = unit; t < first; t += n_units) {       // rows in front of the span keep their place
-            copy_row(a.hidden + (int64_t)t * rb, a.out + (int64_t)t * rb, nvec, lane);
-            if (aux.n) frame_aux(a.auxf, aux, t, t, lane);
-            if (lane == 0) { a.dst[t] = t; a.rank_next[t] = -1; }
-        }
-        bool ok = true;
-        if (w < Rc) {
-            const int p = p0 + w;
-            int nk = 0;
-            for (int f = 0; f < F; ++f) {
-                if (!cx.wait_ge(&sh->p_done, f + 1)) { ok = false; break; }
-                __threadfence_block();
-                const bool kept = sh->kept[f % FR_NQ][w] != 0;
-                const int d = kept ? sh->dstv[f % FR_NQ][w] : -1;
-                const int r = first + f * P + p;
-                if (kept && aux.n) frame_aux(a.auxf, aux, r, d, lane);
-                if (lane == 0) {
-                    a.dst[r] = d;
-                    a.keptdst[(int64_t)p * F + f] = d;
-                    sh->a_done[w] = f + 1;
-                    if (w == 0) FR_STAMP(f, 4);
-                }
-                nk += kept;
-                __syncwarp();
-            }
-            if (lane == 0) a.len_next[p] = nk;
-        }
-        if (ok && cx.wait_ge(&sh->p_done, F)) {             // rows behind the span move up by the merged rows
-            __threadfence_block();
-            const int bt = sh->base_total, n_post = S - first - (int)N;
-            for (int t = unit; t < n_post; t += n_units) {
-                const int r = first + (int)N + t, d = bt + t;
-                copy_row(a.hidden + (int64_t)r * rb, a.out + (int64_t)d * rb, nvec, lane);
-                if (aux.n) frame_aux(a.auxf, aux, r, d, lane);
-                if (lane == 0) { a.dst[r] = d; a.rank_next[d] = -1; }
-            }
-        }
-    }
+    FrameGeo g;
+    g.sh = sh; g.cx = cx;
+    g.F = F; g.first = first; g.p0 = p0; g.Rc = Rc; g.NS = NS; g.R = R; g.P = P; g.S = S; g.lane = lane;
+    g.N = N; g.rb = rb; g.stage_bytes = stage_bytes; g.stages0 = stages0; g.acc0 = acc0;
+    if (wid == 0) fr_role_producer(a, aux, g, 0);
+    else if (wid <= FR_NPW) fr_role_prefix<SW>(a, aux, g, wid - 1);
+    else if (w_s < SW * R) fr_role_sim<DT, SW>(a, aux, g, w_s);
+    else if (w_g < R) fr_role_merge<DT, SW>(a, aux, g, w_g);
+    else if (w_a < R) fr_role_aux(a, aux, g, w_a);
 
     // ---- every chain is through: one barrier over the grid, then the by-patch arrays of the next call
     __syncthreads();
     if (threadIdx.x == 0) {
+        FR_STAMP(1, 6);                                     // this CTA's chains are through
         __threadfence();
         atomicAdd(a.gbar, 1u);
         int spins = 0;
@@ -525,6 +720,7 @@ k_frame_merge(const __grid_constant__ FrameArgs a, const __grid_constant__ AuxPa
         }
         if (ld_relaxed32(a.gbar + 1) != 0u) sh->abort = 1;
         __threadfence();
+        FR_STAMP(2, 6);                                     // the grid is through
     }
     __syncthreads();
     const bool failed = sh->abort != 0;
@@ -552,6 +748,7 @@ k_frame_merge(const __grid_constant__ FrameArgs a, const __grid_constant__ AuxPa
         int ec = 0;
         if (failed || !((double)n_merged / (double)n_vis < a.bound)) ec = 3;    // top-k branch (or a wait gave up): the host redoes the call
         frame_finish(a, N, n_vis, n_merged, ec, failed ? 1 : 0);
+        FR_STAMP(3, 6);                                     // status block out
     }
     pdl_trigger();
 }

@@ -120,7 +120,7 @@ class FrameFusion(nn.Module):
     _PLAIN = frozenset((
         "cost", "similarity_lower_bound", "ratio_lower_bound", "patch_type", "patch_num", "image_token_start_index",
         "image_token_end_index", "image_token_length", "original_length", "finish_merging", "finish_pruning",
-        "sparsity_list", "use_fused", "debug_trace", "last_trace", "kernel_events", "_links_for", "_have_order",
+        "sparsity_list", "use_fused", "use_frame", "debug_trace", "last_trace", "kernel_events", "_links_for", "_have_order",
         "_dev"))
 
     def __setattr__(self, name, value):
@@ -144,6 +144,10 @@ class FrameFusion(nn.Module):
         # one), True = the read-once kernel (one launch, one HBM read of hidden_states: 216 us at C2; it falls back by itself
         # for the top-k branch and for shapes it does not take).  DESIGN.md section 5 has the measurements.
         self.use_fused = False
+        # the first merge call of a prefill on a uniform video runs as ONE launch (csrc/ff_frame.cuh: rows travel HBM ->
+        # shared memory -> HBM once); the library checks the layout on the device and this class redoes the call on the
+        # multi-kernel path if it says no.  False: never ask for it.
+        self.use_frame = True
         self.debug_trace = False        # tests: keep what flowed between the stages of the last call
         self.last_trace = None
         self.kernel_events = None       # bench: a list collects (name, start, end) CUDA events around ff_* launches
@@ -346,8 +350,8 @@ class FrameFusion(nn.Module):
         # align devices (main.py:106)
         self.patch_type = self.patch_type.to(device)
         sparsity_upper_bound = self._compute_pruning_ratio(self.sparsity_list, self.cost)
-        fused = 1 if self.use_fused else 0
-        self._ensure_links(st, q_len, need_order=not fused)
+        fused = (1 if self.use_fused else 0) | (0 if self.use_frame else 2)
+        self._ensure_links(st, q_len, need_order=not (fused & 1))
 
         dt = hidden_states.dtype
         thr = _threshold_in(self.similarity_lower_bound, dt)                 # the scalar is compared in T
@@ -385,15 +389,15 @@ class FrameFusion(nn.Module):
         try:
             launch(fused)
         except ValueError:
-            if not fused or self._have_order:
+            if not (fused & 1) or self._have_order:
                 raise
             # the library declined the read-once kernel for this call (row size / alignment) and the previous call left
             # no by-patch order: rebuild the links, multi-kernel path
             self._links_for = None
             self._ensure_links(st, q_len, need_order=True)
-            launch(0)
+            launch(fused & 2)
         status = st.status
-        ran_fused = bool(fused) and int(status[_lib.ST_FUSED]) == 1
+        ran_fused = bool(fused & 1) and int(status[_lib.ST_FUSED]) == 1
         ran_frame = int(status[_lib.ST_FUSED]) == 2        # the library took the frame-pipelined kernel (first call of a prefill)
         if (ran_fused or ran_frame) and int(status[_lib.ST_INTERNAL]) != 0:
             raise _lib.FFError("framefusion_b200: a wait inside the single-launch merge kernel timed out")
