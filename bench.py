@@ -543,10 +543,16 @@ def main():
     fused = int(ff._state(dev).status[_lib.ST_FUSED])
     alg = synth.algorithmic_bytes(wl.seq_len, s_keep0, c["hidden"], devt["hidden"].element_size())
     peak, peak_src = hbm_peak()
+    # which kernel served call #0: 2 = the frame-pipelined kernel (one launch, every row HBM -> shared memory -> HBM once),
+    # 0 = the multi-kernel path (similarity, scan, gather), 1 = the read-once kernel of r02 (opt-in)
+    kernel_names = {2: "k_frame_merge (one launch: rows travel HBM -> shared memory -> HBM once)",
+                    1: "k_fused_merge (one launch, second visit of a row out of the L2)",
+                    0: "multi-kernel path (k_similarity + k_keep_scan + k_merge_gather)"}
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(cfg, {}).get("dram_bytes_per_launch")
+            tj = json.load(f).get(cfg, {})
+            traffic = tj.get({2: "frame_kernel_dram_bytes_per_launch", 1: "single_pass_kernel_dram_bytes_per_launch"}.get(fused, "dram_bytes_per_launch"))
     except Exception:
         pass
     achieved = alg / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
@@ -570,11 +576,11 @@ def main():
     except Exception:  # noqa: BLE001
         queued_ms = None
 
-    # the single-pass streaming kernel on the same call, for the record (DESIGN.md compares the two designs)
+    # the multi-kernel path on the same call, for the record (DESIGN.md compares the designs)
     single_ms = None
     try:
         ff1 = FrameFusion(c["cost"], c["slb"], c["rlb"])
-        ff1.use_fused = True
+        ff1.use_frame = False
         ts = []
         for _ in range(5):
             ff1.prepare(*wl.prepare_args())
@@ -608,8 +614,8 @@ def main():
                    "cpu_affinity": "rank pinned to its GPU's CPUs (NVML)" if pinned_cpus else "unpinned",
                    "calls_per_step": "merge, merge (closes merging), importance, prune"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "ff_merge_layer call #0: " + ("k_stream_merge (single pass)" if fused else "two-pass path (k_similarity + k_keep_scan + k_merge_gather)"),
-                     "single_pass_kernel_us": None if single_ms is None else single_ms * 1e3,
+                     "traffic": traffic, "kernel": "ff_merge_layer call #0: " + kernel_names.get(fused, str(fused)),
+                     "multi_kernel_path_us": None if single_ms is None else single_ms * 1e3,
                      "kernel_us": k_ms * 1e3, "kernel_us_queued": None if queued_ms is None else queued_ms * 1e3,
                      "algorithmic_bytes": alg, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0},

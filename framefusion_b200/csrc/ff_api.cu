@@ -477,7 +477,7 @@ bool frame_plan(const ff_ctx* ctx, const void* hidden, const void* out, int dtyp
     fp->n_stages = (int)n_stages;
     fp->smem = (int)(FR_META + (n_stages + 1) * stage);
     fp->grid = (int)((P + R - 1) / R);
-    fp->threads = 32 * (1 + FR_NPW + ((R <= 4 ? FR_SW : 1) + 2) * (int)R);   // producer, prefix, S warps (two per chain up to four chains), G, aux
+    fp->threads = 32 * (2 + (R <= 4 ? FR_NPW : 1) + 3 * (int)R);   // producer, prefix warps, finisher, then S / G / aux per chain   // producer, prefix, S warps (two per chain up to four chains), G, aux
     return true;
 }
 
@@ -538,13 +538,13 @@ int launch_frame(ff_ctx* ctx, const Ws& w, int bank, const FramePlan& fp, const 
         // two builds: up to four chains per CTA (14 warps, no register pressure) and up to FR_MAXR
         auto go = [&](auto mr) {
             constexpr int MR = decltype(mr)::value;
-            constexpr int SW = MR > 4 ? 1 : FR_SW;         // similarity warps per chain (FramePlan::threads)
+            constexpr int NPW = MR > 4 ? 1 : FR_NPW;       // prefix warps (FramePlan::threads)
             constexpr int slot = DT * 2 + (MR > 4 ? 1 : 0);
             if (ctx->frame_smem[slot] < fp.smem) {
-                FF_CUDA(cudaFuncSetAttribute((k_frame_merge<DT, MR, SW>), cudaFuncAttributeMaxDynamicSharedMemorySize, fp.smem));
+                FF_CUDA(cudaFuncSetAttribute((k_frame_merge<DT, MR, NPW>), cudaFuncAttributeMaxDynamicSharedMemorySize, fp.smem));
                 ctx->frame_smem[slot] = fp.smem;
             }
-            FF_LAUNCH("k_frame_merge", (k_frame_merge<DT, MR, SW>), fp.grid, fp.threads, fp.smem, st, a, ap);
+            FF_LAUNCH("k_frame_merge", (k_frame_merge<DT, MR, NPW>), fp.grid, fp.threads, fp.smem, st, a, ap);
             return (int)FF_OK;
         };
         return fp.R <= 4 ? go(std::integral_constant<int, 4>()) : go(std::integral_constant<int, FR_MAXR>());

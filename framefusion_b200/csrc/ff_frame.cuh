@@ -38,8 +38,8 @@ namespace ff {
 
 constexpr int FR_MAXR = 8;                         // chains per CTA
 constexpr int FR_MAXSTAGES = 16;                   // ring stages (frames in shared memory)
-constexpr int FR_NQ = 32;                          // frames the flag / destination rings in shared memory hold (> stages + 2)
-constexpr int FR_META = 2048;                      // bytes of shared memory in front of the stages
+constexpr int FR_NQ = 16;                          // frames the flag / destination rings in shared memory hold (> stages + 2)
+constexpr int FR_META = 2560;                      // bytes of shared memory in front of the stages
 constexpr long long FR_TIMEOUT_NS = 400ll * 1000 * 1000;   // a launch older than this gives up at its next wait
 constexpr int FR_PW = 4;                           // 32-word chunks of flag words one poll of the prefix warp can fetch
 #ifndef FR_G_EARLY_ADD
@@ -57,8 +57,14 @@ constexpr int FR_PW = 4;                           // 32-word chunks of flag wor
 #ifndef FR_S_FENCE
 #define FR_S_FENCE 0
 #endif
+#ifndef FR_FINISHER
+#define FR_FINISHER 0                              // 1: a finisher warp closes the rows (rounding chain, flags, global writes) for the S warps
+#endif
+#ifndef FR_G_WIDE
+#define FR_G_WIDE 0                                // 1: the G warps' adds keep four vector pairs per lane in flight
+#endif
 #ifndef FR_NPW
-#define FR_NPW 3                                   // prefix warps (they take the frames in turn)
+#define FR_NPW 2                                   // prefix warps (they take the frames in turn)
 #endif
 #ifndef FR_PF
 #define FR_PF 1                                    // frames one poll looks at
@@ -95,15 +101,17 @@ struct FrameArgs {
 
 struct FrameShared {
     unsigned long long full[FR_MAXSTAGES];         // mbarriers: stage loaded
-    volatile int s_cnt[FR_MAXR][2];                // frames S warp (w, h) has finished: it takes the frames f = h (mod SW)
-    volatile int g_free[FR_MAXR];                  // G warp w no longer needs the stages of frames below this
+    unsigned long long empty[FR_MAXSTAGES];        // mbarriers: the G warps are through the stage (count = chains of the CTA)
+    unsigned long long qbar[FR_NQ];                // mbarriers: the row sums of frame f (slot f % FR_NQ) are in psum[] for every chain
+    unsigned long long sbar[FR_NQ];                // mbarriers: the merge flags of frame f are in kept[] for every chain
+    unsigned long long pbar[FR_NQ];                // mbarriers: the destinations of frame f are in dstv[]
     volatile int a_done[FR_MAXR];                  // frames aux warp w has finished
-    volatile int p_done;                           // frames whose destinations are in dstv[]
     volatile int abort;
     volatile int base_total;                       // kept rows before the first row behind the span
     volatile int base_next;                        // kept rows before the next frame to be published (prefix warps)
     volatile int dstv[FR_NQ][FR_MAXR];
     volatile unsigned char kept[FR_NQ][FR_MAXR];
+    volatile float psum[FR_NQ][FR_MAXR][2];        // float32 row sums of frame f, chain w: T(a*b) products, squares of row f
 };
 static_assert(sizeof(FrameShared) <= FR_META, "FR_META too small");
 
@@ -111,6 +119,9 @@ static_assert(sizeof(FrameShared) <= FR_META, "FR_META too small");
 __device__ __forceinline__ uint32_t fr_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void fr_mbar_init(uint32_t bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fr_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
 __device__ __forceinline__ void fr_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
@@ -130,6 +141,7 @@ __device__ __forceinline__ void fr_tma_store(void* dst, uint32_t src_smem, uint3
 }
 __device__ __forceinline__ void fr_tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void fr_tma_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fr_tma_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void fr_tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fr_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint4 fr_lds16(uint32_t addr) {
@@ -161,21 +173,27 @@ struct FrameCtx {
         return true;
     }
     // whole warp: until *ctr >= need; false once the kernel is giving up
-    // (waiting warps share their scheduler with the warps that work: the ones with slack sleep longer between polls)
-    __device__ __forceinline__ bool wait_ge(const volatile int* ctr, int need, unsigned sleep_ns = 32) const {
+    // Hand-overs between the warps of a CTA go through mbarriers: a waiting warp is suspended by the hardware (try_wait)
+    // instead of polling — polling warps took 40 % of the issue slots of the warps that work.
+    __device__ __forceinline__ bool wait_bar(unsigned long long* bar, int use) const {
+        const uint32_t b = fr_smem_u32(bar), parity = (uint32_t)(use & 1);
+        int spins = 0;
+        while (!fr_mbar_try_wait(b, parity)) {
+            if (sh->abort || expired(++spins)) return false;
+        }
+        return true;
+    }
+    // until the merge flags of frames 0 .. f are there for every chain of the CTA (frames are finished in order)
+    __device__ __forceinline__ bool wait_s(int f) const { return wait_bar(&sh->sbar[f % FR_NQ], f / FR_NQ); }
+    __device__ __forceinline__ bool wait_p(int f) const { return wait_bar(&sh->pbar[f % FR_NQ], f / FR_NQ); }
+    // whole warp: until *ctr >= need (the one polled counter left: the aux warps' progress, which nobody is close to)
+    __device__ __forceinline__ bool wait_ge(const volatile int* ctr, int need, unsigned sleep_ns = 200) const {
         int spins = 0;
         while (*ctr < need) {
             if (sh->abort || expired(++spins)) return false;
             __nanosleep(sleep_ns);
         }
         return true;
-    }
-    // whole warp: until the similarity of frames 0 .. f of chain w is there (SW warps per chain take the frames in turn)
-    template <int SW>
-    __device__ __forceinline__ bool wait_s(int w, int f, unsigned sleep_ns = 32) const {
-        if (SW == 1) return wait_ge(&sh->s_cnt[w][0], f + 1, sleep_ns);
-        if (!wait_ge(&sh->s_cnt[w][f & 1], (f >> 1) + 1, sleep_ns)) return false;
-        return f == 0 || wait_ge(&sh->s_cnt[w][(f - 1) & 1], ((f - 1) >> 1) + 1, sleep_ns);
     }
 };
 
@@ -307,7 +325,8 @@ __device__ __forceinline__ void fr_role_producer(const FrameArgs& a, const AuxPa
                 // the stage is free once the G warps are through frame f - NS; the aux warps touch no stage, they only
                 // have to stay within the flag / destination rings (FR_NQ frames)
                 bool ok = true;
-                for (int w = 0; w < Rc && ok; ++w) ok = cx.wait_ge(&sh->g_free[w], f - NS + 1) && cx.wait_ge(&sh->a_done[w], f - (FR_NQ - 4));
+                ok = cx.wait_bar(&sh->empty[st], f / NS - 1);
+                for (int w = 0; w < Rc && ok; ++w) ok = cx.wait_ge(&sh->a_done[w], f - (FR_NQ - 4));
                 if (!ok) break;
             }
             if (FR_INFLIGHT < FR_MAXSTAGES && f >= FR_INFLIGHT) {
@@ -331,7 +350,7 @@ __device__ __forceinline__ void fr_role_producer(const FrameArgs& a, const AuxPa
     }
 }
 
-template <int SW>
+template <int NPW>
 __device__ __forceinline__ void fr_role_prefix(const FrameArgs& a, const AuxPack& aux, const FrameGeo& g, int w_role) {
     FrameShared* const sh = g.sh;
     const FrameCtx cx = g.cx;
@@ -348,10 +367,10 @@ __device__ __forceinline__ void fr_role_prefix(const FrameArgs& a, const AuxPack
     // frame through shared memory (p_done / base_next) and publishes.
     const int kw = w_role;
     int polls = 0;
-    for (int f = kw; f < F; f += FR_NPW) {
+    for (int f = kw; f < F; f += NPW) {
         // nobody has all the flags of a frame before this CTA's own S warps are through it
         bool ok = true;
-        for (int w = 0; w < Rc && ok; ++w) ok = cx.template wait_s<SW>(w, f);
+        ok = cx.wait_s(f);
         if (!ok) break;
         const int lo = first + f * P, hi = lo + P;      // rows of the frame
         const int w_lo = lo >> 5, w_hi = (hi - 1) >> 5;
@@ -394,7 +413,7 @@ __device__ __forceinline__ void fr_role_prefix(const FrameArgs& a, const AuxPack
         }
         if (!ok) { sh->abort = 1; break; }
         // the frames in front of this one are published by the other prefix warps
-        if (!cx.wait_ge(&sh->p_done, f)) break;
+        if (f > 0 && !cx.wait_p(f - 1)) break;
         if (lane == 0) {
             const int base = f == 0 ? first : sh->base_next;   // rows in front of the span are all kept
 #pragma unroll
@@ -402,14 +421,14 @@ __device__ __forceinline__ void fr_role_prefix(const FrameArgs& a, const AuxPack
                 if (w < Rc) sh->dstv[f % FR_NQ][w] = base + mine[w];
             sh->base_next = base + total;
             if (f == F - 1) sh->base_total = base + total;
-            sh->p_done = f + 1;
+            fr_mbar_arrive(fr_smem_u32(&sh->pbar[f % FR_NQ]));
             FR_STAMP(f, 2);
         }
         __syncwarp();
     }
 }
 
-template <int DT, int SW>
+template <int DT>
 __device__ __forceinline__ void fr_role_sim(const FrameArgs& a, const AuxPack& aux, const FrameGeo& g, int w_role) {
     FrameShared* const sh = g.sh;
     const FrameCtx cx = g.cx;
@@ -418,39 +437,30 @@ __device__ __forceinline__ void fr_role_sim(const FrameArgs& a, const AuxPack& a
     const int64_t rb = g.rb;
     const uint32_t stage_bytes = g.stage_bytes, stages0 = g.stages0, acc0 = g.acc0;
     (void)F; (void)first; (void)p0; (void)Rc; (void)NS; (void)R; (void)P; (void)S; (void)lane; (void)N; (void)rb; (void)stage_bytes; (void)stages0; (void)acc0; (void)sh;
-    // ================================ similarity, chain p0 + w, frames h, h + SW, .. ================================
-    // A row takes one warp ~1 us (a few hundred dependent instructions, two warp reductions, the rounding chain): with ONE
-    // warp per chain that is the period of the whole pipeline.  Two warps take the frames in turn (each then sums both
-    // norms itself); with one warp the norm of the previous row is carried in a register.
-    const int w = w_role % R, h = w_role / R;
+    // ================================ row sums, chain p0 + w ================================
+    // The S warp of a chain only SUMS: T(a*b) products and the squares of the new row over the 448 vectors of a row
+    // pair, two warp reductions, two floats into shared memory.  What follows — the rounding chain with its square roots
+    // and its division, the flag, the global writes — is a few hundred DEPENDENT instructions per row and belongs to the
+    // finisher warp, which does the four chains of a frame in four lanes at once: left here it was half of this warp's
+    // time per row, and this warp's time per row is the period of the whole pipeline.
+    const int w = w_role;
     if (w < Rc) {
-        const int p = p0 + w;
-        float na_prev = 0.f;
         long long c_wait = 0, c_busy = 0, c0 = clock64();   // (traced launches: where this warp's cycles go)
-        for (int f = h; f < F; f += SW) {
+        float na_prev = 0.f;                                // (no finisher: the squares of the previous row)
+        (void)na_prev;
+        for (int f = 0; f < F; ++f) {
             const int st = f % NS;
-            const uint32_t bar = fr_smem_u32(&sh->full[st]);
-            const uint32_t parity = (uint32_t)((f / NS) & 1);
-            int spins = 0;
-            bool ok = true;
-            while (!fr_mbar_try_wait(bar, parity)) {
-                if (sh->abort || cx.expired(++spins)) { ok = false; break; }
-            }
-            if (SW > 1 && f > 0 && ok) {
-                // the previous frame was another warp's: this one has to see ITS stage complete as well (a warp that has
-                // not observed the barrier has no promise that the bulk copy's bytes are visible to it)
-                const uint32_t bp = fr_smem_u32(&sh->full[(f - 1) % NS]), pp = (uint32_t)(((f - 1) / NS) & 1);
-                while (!fr_mbar_try_wait(bp, pp)) {
-                    if (sh->abort || cx.expired(++spins)) { ok = false; break; }
-                }
-            }
-            if (!ok) break;
+            if (!cx.wait_bar(&sh->full[st], f / NS)) break;
             if (w == 0 && lane == 0) FR_STAMP(f, 5);    // the frame's rows are in shared memory
             if (a.trace) { const long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
             const uint32_t cur = stages0 + (uint32_t)st * stage_bytes + (uint32_t)(w * rb) + lane * 16;
             const uint32_t prv = stages0 + (uint32_t)((f + NS - 1) % NS) * stage_bytes + (uint32_t)(w * rb) + lane * 16;
-            float2 d0 = make_float2(0.f, 0.f), d1 = d0, b0 = d0, b1 = d0, a0 = d0, a1 = d0;
+            float2 d0 = make_float2(0.f, 0.f), d1 = d0, b0 = d0, b1 = d0;
+#ifdef FR_DIAG_S_DIV
+            const int nvec = a.nvec / FR_DIAG_S_DIV;     // diagnostic build: wrong similarities, a fraction of the arithmetic
+#else
             const int nvec = a.nvec;
+#endif
             if (f > 0) {
 #pragma unroll 2
                 for (int v = lane; v < nvec; v += 64) {
@@ -458,13 +468,8 @@ __device__ __forceinline__ void fr_role_sim(const FrameArgs& a, const AuxPack& a
                     uint4 pb = make_uint4(0, 0, 0, 0), cb = pb;
                     const bool two = v + 32 < nvec;
                     if (two) { pb = fr_lds16(prv + (v - lane + 32) * 16); cb = fr_lds16(cur + (v - lane + 32) * 16); }
-                    if (SW == 1) {
-                        fr_dot_nb<DT>(pa, ca, d0, b0);
-                        if (two) fr_dot_nb<DT>(pb, cb, d1, b1);
-                    } else {
-                        acc_pair2<DT>(pa, ca, d0, a0, b0);
-                        if (two) acc_pair2<DT>(pb, cb, d1, a1, b1);
-                    }
+                    fr_dot_nb<DT>(pa, ca, d0, b0);
+                    if (two) fr_dot_nb<DT>(pb, cb, d1, b1);
                 }
             } else {
                 for (int v = lane; v < nvec; v += 64) {
@@ -474,33 +479,71 @@ __device__ __forceinline__ void fr_role_sim(const FrameArgs& a, const AuxPack& a
             }
             const float dot = warp_sum((d0.x + d0.y) + (d1.x + d1.y));
             const float nb = warp_sum((b0.x + b0.y) + (b1.x + b1.y));
-            if (SW != 1) na_prev = warp_sum((a0.x + a0.y) + (a1.x + a1.y));
+#if FR_FINISHER
+            if (lane == 0) {
+                sh->psum[f % FR_NQ][w][0] = dot;
+                sh->psum[f % FR_NQ][w][1] = nb;
+                fr_mbar_arrive(fr_smem_u32(&sh->qbar[f % FR_NQ]));
+            }
+#else
             float s = -2.0f;                            // IGNORE_TOKEN at chain heads (main.py:225-238)
             if (f > 0) s = finish_cosine<DT>(dot, na_prev, nb);
             na_prev = nb;
             const unsigned kept = !(f > 0 && s >= a.thr);   // NaN compares false: kept
             if (lane == 0) {
-                // No fence in this loop: a fence waits for the thread's outstanding GLOBAL writes to be acknowledged
-                // (a microsecond each frame).  Shared memory is written and read in program order on an SM: the flag
-                // first, then the counter that says it is there (both volatile), then the global writes.
-                const int r = first + f * P + p;
-                const int64_t j = (int64_t)p * F + f;
+                const int r = first + f * P + p0 + w;
+                const int64_t j = (int64_t)(p0 + w) * F + f;
                 sh->kept[f % FR_NQ][w] = (unsigned char)kept;
-                sh->s_cnt[w][h] = f / SW + 1;
+                fr_mbar_arrive(fr_smem_u32(&sh->sbar[f % FR_NQ]));   // (global writes after the hand-over: nothing in the CTA waits for them)
                 red_add64(a.words + (r >> 5), (1ull << (32 + (r & 31))) | ((unsigned long long)kept << (r & 31)));
                 a.sim[j] = s;
                 a.flag[j] = (uint8_t)(kept ^ 1u);
-                if (FR_S_FENCE) __threadfence_block();
                 if (w == 0) FR_STAMP(f, 1);
             }
+#endif
             __syncwarp();
             if (a.trace) { const long long c1 = clock64(); c_busy += c1 - c0; c0 = c1; }
         }
-        if (w == 0 && h == 0 && lane == 0) { FR_NOTE(0, 7, c_busy); FR_NOTE(1, 7, c_wait); }
+        if (w == 0 && lane == 0) { FR_NOTE(0, 7, c_busy); FR_NOTE(1, 7, c_wait); }
     }
 }
 
-template <int DT, int SW>
+// ================================ finisher: lane w closes chain p0 + w of every frame ================================
+template <int DT>
+__device__ __forceinline__ void fr_role_finish(const FrameArgs& a, const AuxPack& aux, const FrameGeo& g, int w_role) {
+    FrameShared* const sh = g.sh;
+    const FrameCtx cx = g.cx;
+    const int F = g.F, first = g.first, p0 = g.p0, Rc = g.Rc, P = g.P, lane = g.lane;
+    const int w = lane, p = p0 + lane;
+    float na_prev = 0.f;                                    // the squares of the previous row of this lane's chain
+    for (int f = 0; f < F; ++f) {
+        if (!cx.wait_bar(&sh->qbar[f % FR_NQ], f / FR_NQ)) break;
+        float s = -2.0f;                                    // IGNORE_TOKEN at chain heads (main.py:225-238)
+        unsigned kept = 1u;
+        if (w < Rc) {
+            const float dot = sh->psum[f % FR_NQ][w][0], nb = sh->psum[f % FR_NQ][w][1];
+            if (f > 0) s = finish_cosine<DT>(dot, na_prev, nb);
+            na_prev = nb;
+            kept = !(f > 0 && s >= a.thr);                  // NaN compares false: kept
+            sh->kept[f % FR_NQ][w] = (unsigned char)kept;
+        }
+        __syncwarp();                                       // (orders the lanes' flags before lane 0's arrival)
+        if (lane == 0) {
+            fr_mbar_arrive(fr_smem_u32(&sh->sbar[f % FR_NQ]));
+            FR_STAMP(f, 1);
+        }
+        if (w < Rc) {
+            // (global writes after the hand-over: nothing in the CTA waits for them)
+            const int r = first + f * P + p;
+            const int64_t j = (int64_t)p * F + f;
+            red_add64(a.words + (r >> 5), (1ull << (32 + (r & 31))) | ((unsigned long long)kept << (r & 31)));
+            a.sim[j] = s;
+            a.flag[j] = (uint8_t)(kept ^ 1u);
+        }
+    }
+}
+
+template <int DT>
 __device__ __forceinline__ void fr_role_merge(const FrameArgs& a, const AuxPack& aux, const FrameGeo& g, int w_role) {
     FrameShared* const sh = g.sh;
     const FrameCtx cx = g.cx;
@@ -521,7 +564,7 @@ __device__ __forceinline__ void fr_role_merge(const FrameArgs& a, const AuxPack&
         int L = 0, anchor_d = -1;
         long long c_wait = 0, c_busy = 0, c0 = clock64();
         for (int f = 0; f < F; ++f) {
-            if (!cx.template wait_s<SW>(w, min(f + 3, F) - 1, 100)) break;
+            if (!cx.wait_s(min(f + 3, F) - 1)) break;
             if (a.trace) { const long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
             const bool kept = sh->kept[f % FR_NQ][w] != 0;
             const bool nxt_kept = f + 1 < F ? sh->kept[(f + 1) % FR_NQ][w] != 0 : true;
@@ -529,7 +572,7 @@ __device__ __forceinline__ void fr_role_merge(const FrameArgs& a, const AuxPack&
             const uint32_t cur = stages0 + (uint32_t)(f % NS) * stage_bytes + (uint32_t)(w * rb);
             if (kept) L = 0;
 #if !FR_G_EARLY_ADD
-            if (!cx.wait_ge(&sh->p_done, f + 1)) break;
+            if (!cx.wait_p(f)) break;
 #endif
             if (!nxt_kept) {
                 // the arithmetic needs no destination: it runs ahead of the prefix warp
@@ -538,23 +581,47 @@ __device__ __forceinline__ void fr_role_merge(const FrameArgs& a, const AuxPack&
                 ++L;
                 if (nn_kept) {
                     const Divider<DT> dv(L + 1);
+#if FR_G_WIDE
+                    for (int v0 = lane; v0 < nvec; v0 += 128) {         // four vector pairs per lane in flight
+                        uint4 y[4], x[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (v0 + 32 * q < nvec) { y[q] = fr_lds16(src + (v0 + 32 * q) * 16); x[q] = fr_lds16(nxt + (v0 + 32 * q) * 16); }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (v0 + 32 * q < nvec) fr_sts16(accp + (v0 + 32 * q) * 16, dv.vec_fast(Num<DT>::add_vec(y[q], x[q])));   // T(T(acc + member) / T(L + 1))
+                    }
+#else
 #pragma unroll 2
                     for (int v = lane; v < nvec; v += 32) {
                         const uint4 y = fr_lds16(src + v * 16), x = fr_lds16(nxt + v * 16);
                         fr_sts16(accp + v * 16, dv.vec_fast(Num<DT>::add_vec(y, x)));    // T(T(acc + member) / T(L + 1))
                     }
+#endif
                     fr_fence_async();
                 } else {
+#if FR_G_WIDE
+                    for (int v0 = lane; v0 < nvec; v0 += 128) {
+                        uint4 y[4], x[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (v0 + 32 * q < nvec) { y[q] = fr_lds16(src + (v0 + 32 * q) * 16); x[q] = fr_lds16(nxt + (v0 + 32 * q) * 16); }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (v0 + 32 * q < nvec) fr_sts16(accp + (v0 + 32 * q) * 16, Num<DT>::add_vec(y[q], x[q]));   // T(acc + member), main.py:304
+                    }
+#else
 #pragma unroll 2
                     for (int v = lane; v < nvec; v += 32) {
                         const uint4 y = fr_lds16(src + v * 16), x = fr_lds16(nxt + v * 16);
                         fr_sts16(accp + v * 16, Num<DT>::add_vec(y, x));                  // T(acc + member), main.py:304
                     }
+#endif
                 }
             }
             if (kept) {
                 if (a.trace) { const long long c1 = clock64(); c_busy += c1 - c0; c0 = c1; }
-                if (!cx.wait_ge(&sh->p_done, f + 1)) break;
+                if (!cx.wait_p(f)) break;
                 if (a.trace) { const long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
                 anchor_d = sh->dstv[f % FR_NQ][w];
             }
@@ -565,9 +632,11 @@ __device__ __forceinline__ void fr_role_merge(const FrameArgs& a, const AuxPack&
             }
             __syncwarp();
             if (lane == 0) {
+                // the store of this step drains while the next step runs: what is known to have left shared memory now
+                // is the store of the step before, and with it stage f - 1 (and the accumulator row) can be reused
                 fr_tma_commit();
-                fr_tma_wait_read_0();                   // this step's store has left shared memory: stage f is free
-                sh->g_free[w] = f + 1;
+                fr_tma_wait_read_1();
+                if (f > 0) fr_mbar_arrive(fr_smem_u32(&sh->empty[(f - 1) % NS]));
                 if (w == 0) FR_STAMP(f, 3);
             }
             __syncwarp();
@@ -604,8 +673,8 @@ __device__ __forceinline__ void fr_role_aux(const FrameArgs& a, const AuxPack& a
         const bool flat = a.auxf.n >= 0;
         int nk = 0;
         for (int f = 0; f < F;) {
-            if (!cx.wait_ge(&sh->p_done, f + 1, 200)) { ok = false; break; }
-            const int nb = min(FR_AUX_BATCH, min((int)sh->p_done, F) - f);
+            if (!cx.wait_p(f)) { ok = false; break; }
+            const int nb = 1;
             const bool k0 = sh->kept[f % FR_NQ][w] != 0, k1 = nb > 1 && sh->kept[(f + 1) % FR_NQ][w] != 0;
             const int d0 = k0 ? sh->dstv[f % FR_NQ][w] : -1, d1 = k1 ? sh->dstv[(f + 1) % FR_NQ][w] : -1;
             const int r0 = first + f * P + p, r1 = r0 + P;
@@ -637,7 +706,7 @@ __device__ __forceinline__ void fr_role_aux(const FrameArgs& a, const AuxPack& a
         }
         if (lane == 0) a.len_next[p] = nk;
     }
-    if (ok && cx.wait_ge(&sh->p_done, F)) {             // rows behind the span move up by the merged rows
+    if (ok && cx.wait_p(F - 1)) {                      // rows behind the span move up by the merged rows
         __threadfence_block();
         const int bt = sh->base_total, n_post = S - first - (int)N;
         for (int t = unit; t < n_post; t += n_units) {
@@ -649,8 +718,8 @@ __device__ __forceinline__ void fr_role_aux(const FrameArgs& a, const AuxPack& a
     }
 }
 
-template <int DT, int MAXR, int SW>
-__global__ void __launch_bounds__(32 * (1 + FR_NPW + (SW + 2) * MAXR), 1)
+template <int DT, int MAXR, int NPW>
+__global__ void __launch_bounds__(32 * (2 + NPW + 3 * MAXR), 1)
 k_frame_merge(const __grid_constant__ FrameArgs a, const __grid_constant__ AuxPack aux) {
     extern __shared__ __align__(128) unsigned char fr_smem[];
     pdl_wait();
@@ -676,18 +745,21 @@ k_frame_merge(const __grid_constant__ FrameArgs a, const __grid_constant__ AuxPa
     const uint32_t acc0 = stages0 + (uint32_t)NS * stage_bytes;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; ++s) fr_mbar_init(fr_smem_u32(&sh->full[s]), 1);
+        for (int s = 0; s < NS; ++s) {
+            fr_mbar_init(fr_smem_u32(&sh->full[s]), 1);
+            fr_mbar_init(fr_smem_u32(&sh->empty[s]), Rc);
+        }
+        for (int q = 0; q < FR_NQ; ++q) {
+            fr_mbar_init(fr_smem_u32(&sh->qbar[q]), Rc);
+            fr_mbar_init(fr_smem_u32(&sh->sbar[q]), FR_FINISHER ? 1 : Rc);
+            fr_mbar_init(fr_smem_u32(&sh->pbar[q]), 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        sh->p_done = 0;
         sh->base_next = 0;
         sh->abort = 0;
         sh->base_total = 0;
     }
-    if (threadIdx.x < FR_MAXR) {
-        sh->s_cnt[threadIdx.x][0] = sh->s_cnt[threadIdx.x][1] = 0;
-        sh->g_free[threadIdx.x] = 0;
-        sh->a_done[threadIdx.x] = 0;
-    }
+    if (threadIdx.x < FR_MAXR) sh->a_done[threadIdx.x] = 0;
     __syncthreads();
     FrameCtx cx;
     cx.sh = sh;
@@ -695,16 +767,17 @@ k_frame_merge(const __grid_constant__ FrameArgs a, const __grid_constant__ AuxPa
     cx.t_end = fr_time() + FR_TIMEOUT_NS;
     if (threadIdx.x == 0) FR_STAMP(0, 6);                   // kernel under way
 
-    const int w_s = wid - 1 - FR_NPW, w_g = w_s - SW * R, w_a = w_s - (SW + 1) * R;    // index inside the role
+    const int w_s = wid - 2 - NPW, w_g = w_s - R, w_a = w_s - 2 * R;    // index inside the role
 
     FrameGeo g;
     g.sh = sh; g.cx = cx;
     g.F = F; g.first = first; g.p0 = p0; g.Rc = Rc; g.NS = NS; g.R = R; g.P = P; g.S = S; g.lane = lane;
     g.N = N; g.rb = rb; g.stage_bytes = stage_bytes; g.stages0 = stages0; g.acc0 = acc0;
     if (wid == 0) fr_role_producer(a, aux, g, 0);
-    else if (wid <= FR_NPW) fr_role_prefix<SW>(a, aux, g, wid - 1);
-    else if (w_s < SW * R) fr_role_sim<DT, SW>(a, aux, g, w_s);
-    else if (w_g < R) fr_role_merge<DT, SW>(a, aux, g, w_g);
+    else if (wid <= NPW) fr_role_prefix<NPW>(a, aux, g, wid - 1);
+    else if (wid == NPW + 1) { if (FR_FINISHER) fr_role_finish<DT>(a, aux, g, 0); }
+    else if (w_s < R) fr_role_sim<DT>(a, aux, g, w_s);
+    else if (w_g < R) fr_role_merge<DT>(a, aux, g, w_g);
     else if (w_a < R) fr_role_aux(a, aux, g, w_a);
 
     // ---- every chain is through: one barrier over the grid, then the by-patch arrays of the next call

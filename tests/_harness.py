@@ -191,3 +191,18 @@ def run_and_compare(name, make_impl, device="cpu", check_sim_with_oracle=True):
                 assert np.array_equal(tensor_checksum(mask[0, 0]), z[p + "mask"]), f"call {c}: mask"
             assert np.array_equal(impl.patch_type[0].cpu().numpy().astype(np.int32), z[p + "patch_type"]), f"call {c}: patch_type"
     return report
+
+
+# merge-stage kernel choice of framefusion_b200.main.FrameFusion: "frame" = the default (the first merge call of a prefill
+# on a uniform video runs the frame-pipelined kernel, everything else the multi-kernel path), "multi" = the multi-kernel
+# path for every call, "fused" = the read-once kernel of r02 for every call
+MODES = ["frame", "multi", "fused"]
+
+
+def set_mode(ff, mode):
+    if mode is True:
+        mode = "fused"
+    elif mode is False:
+        mode = "frame"
+    ff.use_fused = mode == "fused"
+    ff.use_frame = mode == "frame"

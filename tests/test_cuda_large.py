@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from _harness import t2f
+from _harness import MODES, set_mode, t2f
 from oracle import ff_oracle as orc
 from framefusion_b200 import synth
 
@@ -19,7 +19,7 @@ def drive(frames, patches, hidden, lo, hi, fused, drift=0.0, cost=0.3, max_calls
                              n_pre=n_pre, n_post=n_post, frozen_patches=frozen_patches, zero_rows=zero_rows)
     assert wl.seq_len >= 2048
     ff = FrameFusion(cost, slb, 0.1)
-    ff.use_fused = fused
+    set_mode(ff, fused)
     ff.prepare(*synth.to_device(wl, "cuda").prepare_args())
     o = orc.OracleFrameFusion(cost, slb, 0.1, {torch.bfloat16: "bf16", torch.float16: "f16", torch.float32: "f32"}[dtype])
     o.prepare(wl.patch_type.numpy(), wl.patch_num, *wl.prepare_args()[2:])
@@ -51,13 +51,13 @@ def drive(frames, patches, hidden, lo, hi, fused, drift=0.0, cost=0.3, max_calls
     return stages
 
 
-@pytest.mark.parametrize("fused", [False, True], ids=["two_pass", "single_pass"])
+@pytest.mark.parametrize("fused", MODES)
 def test_multi_call_merging_then_prune(fused):
     stages = drive(32, 144, 512, 0.0, 1.0, fused, drift=0.35)
     assert stages.count("threshold") >= 2 and stages[-1] == "prune"
 
 
-@pytest.mark.parametrize("fused", [False, True], ids=["two_pass", "single_pass"])
+@pytest.mark.parametrize("fused", MODES)
 def test_topk_branch_at_scale(fused):
     stages = drive(24, 128, 512, 0.8, 1.0, fused)
     assert stages == ["topk"]
@@ -112,13 +112,13 @@ def ragged_case(seed=3, frames=36, patches=120, hidden=512, n_pre=9, n_post=15):
     return h, cos, sin, pt, patches, (first, last, last - first + 1, S)
 
 
-@pytest.mark.parametrize("fused", [False, True], ids=["two_pass", "single_pass"])
+@pytest.mark.parametrize("fused", MODES)
 def test_ragged_chains_with_text_between_frames(fused):
     from framefusion_b200.main import FrameFusion
     h, cos, sin, pt, P, span = ragged_case()
     assert h.shape[1] >= 2048
     ff = FrameFusion(0.3, 0.6, 0.1)
-    ff.use_fused = fused
+    set_mode(ff, fused)
     ff.prepare(pt.cuda(), P, *span)
     o = orc.OracleFrameFusion(0.3, 0.6, 0.1, "bf16")
     o.prepare(pt.numpy(), P, *span)
@@ -222,7 +222,7 @@ def test_4d_mask_is_compacted_at_scale():
 
 # ---- SURVEY H9 corner cases on the multi-block kernels (the small-sequence kernels see them through the fixtures
 # case_H9_*.npz generated from the unmodified reference) ------------------------------------------------------------
-@pytest.mark.parametrize("fused", [False, True], ids=["two_pass", "single_pass"])
+@pytest.mark.parametrize("fused", MODES)
 def test_h9_run_longer_than_256_rows(fused):
     """One chain is identical in all 301 frames: a run of 300 members behind its anchor.  The sum stalls once the
     accumulator outgrows the member (each add is rounded to T), and the divisor is T(301) = 300 in bf16 — the in-place
@@ -233,7 +233,7 @@ def test_h9_run_longer_than_256_rows(fused):
     assert stages == ["threshold"]
 
 
-@pytest.mark.parametrize("fused", [False, True], ids=["two_pass", "single_pass"])
+@pytest.mark.parametrize("fused", MODES)
 def test_h9_zero_norm_rows_threshold_branch(fused):
     """All-zero rows: 0 / 0 = NaN similarity on both sides of the row; NaN >= threshold is false (kept, main.py:113)."""
     zr = [(f, p) for f in (0, 3, 4, 17, 31) for p in (0, 5, 143)]

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from _harness import GOLDEN_DIR, DT, case_names, run_and_compare, t2f
+from _harness import MODES, set_mode, GOLDEN_DIR, DT, case_names, run_and_compare, t2f
 from oracle import ff_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -21,7 +21,7 @@ class CudaAdapter:
         from framefusion_b200.main import FrameFusion
         self.ff = FrameFusion(cost, slb, rlb)
         self.ff.debug_trace = True
-        self.ff.use_fused = fused
+        set_mode(self.ff, fused)
 
     def prepare(self, *args):
         self.ff.prepare(*args)
@@ -38,7 +38,7 @@ class CudaAdapter:
         return self.ff.last_trace
 
 
-@pytest.mark.parametrize("fused", [False, True], ids=["generic", "fused"])
+@pytest.mark.parametrize("fused", MODES)
 @pytest.mark.parametrize("name", case_names())
 def test_cuda_matches_reference_sequence(name, fused):
     rep = run_and_compare(name, lambda c, s, r, dt: CudaAdapter(c, s, r, dt, fused), device="cuda")
@@ -138,7 +138,7 @@ def test_errors_and_passthrough():
         ff(wl.hidden, [wl.cos, wl.sin], None)
 
 
-@pytest.mark.parametrize("fused", [False, True], ids=["generic", "fused"])
+@pytest.mark.parametrize("fused", MODES)
 @pytest.mark.parametrize("cfg", ["C2", "C4"])
 def test_full_size_against_oracle(cfg, fused):
     """BASELINE configs at full size: first merge call, CUDA vs the numpy oracle on identical bits."""
@@ -147,7 +147,7 @@ def test_full_size_against_oracle(cfg, fused):
     c = synth.CONFIGS[cfg]
     wl = synth.make_workload(c["frames"], c["patch_num"], c["hidden"], c["dtype"], seed=0)
     ff = FrameFusion(c["cost"], c["slb"], c["rlb"])
-    ff.use_fused = fused
+    set_mode(ff, fused)
     ff.debug_trace = True
     ff.prepare(*wl.prepare_args())
     pos = [wl.cos.cuda(), wl.sin.cuda()]

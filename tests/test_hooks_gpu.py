@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from _harness import t2f
+from _harness import MODES, set_mode, t2f
 from oracle import ff_oracle as orc
 from framefusion_b200 import synth
 
@@ -21,14 +21,14 @@ def tiny_model():
     return Qwen2ForCausalLM(cfg).eval().to(torch.bfloat16).cuda()
 
 
-@pytest.mark.parametrize("fused", [False, True], ids=["two_pass", "single_pass"])
+@pytest.mark.parametrize("fused", MODES)
 @pytest.mark.parametrize("lo,hi", [(0.0, 1.0), (0.0, 0.5)], ids=["mixed", "lowsim_prune"])
 def test_patched_prefill_matches_oracle_call_by_call(lo, hi, fused):
     from framefusion_b200.interface import apply_framefusion
     model = tiny_model()
     apply_framefusion(model, cost=0.3, similarity_lower_bound=0.6, ratio_lower_bound=0.1)
     ff = model.framefusion
-    ff.use_fused = fused
+    set_mode(ff, fused)
     wl = synth.make_workload(10, 24, 256, torch.bfloat16, seed=11, r_lo=lo, r_hi=hi, n_pre=5, n_post=7, rot_dim=64)
     o = orc.OracleFrameFusion(0.3, 0.6, 0.1, "bf16")
     o.prepare(wl.patch_type.numpy(), wl.patch_num, *wl.prepare_args()[2:])
@@ -62,7 +62,7 @@ def test_patched_prefill_matches_oracle_call_by_call(lo, hi, fused):
         assert ff.finish_pruning and any(c[2] for c in calls)      # importance was produced and consumed
 
 
-@pytest.mark.parametrize("fused", [False, True], ids=["two_pass", "single_pass"])
+@pytest.mark.parametrize("fused", MODES)
 def test_merge_call_is_repeatable_bit_for_bit(fused):
     """The kernels contain spin-waits and atomics: the result must not depend on their timing."""
     from framefusion_b200.main import FrameFusion
@@ -70,7 +70,7 @@ def test_merge_call_is_repeatable_bit_for_bit(fused):
     ref = None
     for rep in range(25):
         ff = FrameFusion(0.3, 0.6, 0.1)
-        ff.use_fused = fused
+        set_mode(ff, fused)
         ff.prepare(*wl.prepare_args())
         h, pos, _ = ff(wl.hidden, [wl.cos, wl.sin], None)
         cur = (h.clone(), pos[0].clone(), ff.patch_type.clone())
