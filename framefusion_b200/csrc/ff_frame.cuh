@@ -60,6 +60,12 @@ constexpr int FR_PW = 4;                           // 32-word chunks of flag wor
 #ifndef FR_FINISHER
 #define FR_FINISHER 0                              // 1: a finisher warp closes the rows (rounding chain, flags, global writes) for the S warps
 #endif
+#ifndef FR_S_WIDE
+#define FR_S_WIDE 2                                // 1: the S warps' loop keeps four vector pairs per lane in flight
+#endif
+#ifndef FR_EARLY_STATUS
+#define FR_EARLY_STATUS 1                          // 1: aux warp 0 of CTA 0 sends the status block as soon as the last frame is decided
+#endif
 #ifndef FR_G_WIDE
 #define FR_G_WIDE 0                                // 1: the G warps' adds keep four vector pairs per lane in flight
 #endif
@@ -109,6 +115,7 @@ struct FrameShared {
     volatile int abort;
     volatile int base_total;                       // kept rows before the first row behind the span
     volatile int base_next;                        // kept rows before the next frame to be published (prefix warps)
+    volatile int published;                        // CTA 0: the status block went out before the end of the kernel
     volatile int dstv[FR_NQ][FR_MAXR];
     volatile unsigned char kept[FR_NQ][FR_MAXR];
     volatile float psum[FR_NQ][FR_MAXR][2];        // float32 row sums of frame f, chain w: T(a*b) products, squares of row f
@@ -366,7 +373,7 @@ __device__ __forceinline__ void fr_role_prefix(const FrameArgs& a, const AuxPack
     // the CTA's own rows as soon as every patch has reported, then takes the running base from the warp of the previous
     // frame through shared memory (p_done / base_next) and publishes.
     const int kw = w_role;
-    int polls = 0;
+    int polls = 0, last_done = -1;
     for (int f = kw; f < F; f += NPW) {
         // nobody has all the flags of a frame before this CTA's own S warps are through it
         bool ok = true;
@@ -425,7 +432,20 @@ __device__ __forceinline__ void fr_role_prefix(const FrameArgs& a, const AuxPack
             FR_STAMP(f, 2);
         }
         __syncwarp();
+        last_done = f;
     }
+#if FR_EARLY_STATUS
+    if (blockIdx.x == 0 && lane == 0 && last_done == F - 1 && !sh->abort) {
+        // This warp has just published the last frame: every flag of the sequence is in, the sizes and the branch are
+        // decided, and the host is told NOW — the last rows, the barrier over the grid and the arrays of the next call
+        // take a few more microseconds, which its work for the next call overlaps (ff_status_wait).  A wait that gives up
+        // after this is still reported (FF_ST_INTERNAL): the host looks again at its next call.
+        const long long n_merged = N - ((long long)sh->base_total - first);
+        const long long n_vis = a.counters[C_NVIS];
+        frame_finish(a, N, n_vis, n_merged, (double)n_merged / (double)n_vis < a.bound ? 0 : 3, 0);
+        sh->published = 1;
+    }
+#endif
 }
 
 template <int DT>
@@ -462,6 +482,53 @@ __device__ __forceinline__ void fr_role_sim(const FrameArgs& a, const AuxPack& a
             const int nvec = a.nvec;
 #endif
             if (f > 0) {
+#if FR_S_WIDE == 2
+                // groups of two vector pairs per lane, the next group's four loads requested before the arithmetic of the
+                // current one (two register sets in turn): no load latency is exposed after the first group
+                const int ng = nvec >> 6;
+                float2 d2 = d0, d3 = d0, b2 = d0, b3 = d0;
+                uint4 pa0, ca0, pa1, ca1, pb0, cb0, pb1, cb1;
+                pa0 = ca0 = pa1 = ca1 = pb0 = cb0 = pb1 = cb1 = make_uint4(0, 0, 0, 0);
+                if (ng > 0) { pa0 = fr_lds16(prv); ca0 = fr_lds16(cur); pa1 = fr_lds16(prv + 512); ca1 = fr_lds16(cur + 512); }
+                int gi = 0;
+#pragma unroll 1
+                for (; gi + 1 < ng; gi += 2) {
+                    const uint32_t o1 = (uint32_t)(gi + 1) * 1024u;
+                    pb0 = fr_lds16(prv + o1); cb0 = fr_lds16(cur + o1); pb1 = fr_lds16(prv + o1 + 512); cb1 = fr_lds16(cur + o1 + 512);
+                    fr_dot_nb<DT>(pa0, ca0, d0, b0);
+                    fr_dot_nb<DT>(pa1, ca1, d1, b1);
+                    if (gi + 2 < ng) {
+                        const uint32_t o2 = (uint32_t)(gi + 2) * 1024u;
+                        pa0 = fr_lds16(prv + o2); ca0 = fr_lds16(cur + o2); pa1 = fr_lds16(prv + o2 + 512); ca1 = fr_lds16(cur + o2 + 512);
+                    }
+                    fr_dot_nb<DT>(pb0, cb0, d2, b2);
+                    fr_dot_nb<DT>(pb1, cb1, d3, b3);
+                }
+                if (gi < ng) {
+                    fr_dot_nb<DT>(pa0, ca0, d0, b0);
+                    fr_dot_nb<DT>(pa1, ca1, d1, b1);
+                }
+                for (int v = (ng << 6) + lane; v < nvec; v += 32) fr_dot_nb<DT>(fr_lds16(prv + (v - lane) * 16), fr_lds16(cur + (v - lane) * 16), d0, b0);
+                d0 = make_float2(d0.x + d2.x, d0.y + d2.y); d1 = make_float2(d1.x + d3.x, d1.y + d3.y);
+                b0 = make_float2(b0.x + b2.x, b0.y + b2.y); b1 = make_float2(b1.x + b3.x, b1.y + b3.y);
+#elif FR_S_WIDE
+                // four vector pairs per lane in flight, whole groups first (no predicate between the loads), then the rest
+                int v = lane;
+                float2 d2 = d0, d3 = d0, b2 = d0, b3 = d0;
+#pragma unroll 1
+                for (; v + 96 < nvec; v += 128) {
+                    const uint32_t po = prv + (v - lane) * 16, co = cur + (v - lane) * 16;
+                    const uint4 p0v = fr_lds16(po), c0v = fr_lds16(co), p1v = fr_lds16(po + 512), c1v = fr_lds16(co + 512);
+                    const uint4 p2v = fr_lds16(po + 1024), c2v = fr_lds16(co + 1024), p3v = fr_lds16(po + 1536), c3v = fr_lds16(co + 1536);
+                    fr_dot_nb<DT>(p0v, c0v, d0, b0);
+                    fr_dot_nb<DT>(p1v, c1v, d1, b1);
+                    fr_dot_nb<DT>(p2v, c2v, d2, b2);
+                    fr_dot_nb<DT>(p3v, c3v, d3, b3);
+                }
+                for (; v < nvec; v += 32) fr_dot_nb<DT>(fr_lds16(prv + (v - lane) * 16), fr_lds16(cur + (v - lane) * 16), d0, b0);
+                d0 = make_float2(d0.x + d2.x, d0.y + d2.y); d1 = make_float2(d1.x + d3.x, d1.y + d3.y);
+                b0 = make_float2(b0.x + b2.x, b0.y + b2.y); b1 = make_float2(b1.x + b3.x, b1.y + b3.y);
+#else
 #pragma unroll 2
                 for (int v = lane; v < nvec; v += 64) {
                     const uint4 pa = fr_lds16(prv + (v - lane) * 16), ca = fr_lds16(cur + (v - lane) * 16);
@@ -471,6 +538,7 @@ __device__ __forceinline__ void fr_role_sim(const FrameArgs& a, const AuxPack& a
                     fr_dot_nb<DT>(pa, ca, d0, b0);
                     if (two) fr_dot_nb<DT>(pb, cb, d1, b1);
                 }
+#endif
             } else {
                 for (int v = lane; v < nvec; v += 64) {
                     fr_nb<DT>(fr_lds16(cur + (v - lane) * 16), b0);
@@ -707,7 +775,6 @@ __device__ __forceinline__ void fr_role_aux(const FrameArgs& a, const AuxPack& a
         if (lane == 0) a.len_next[p] = nk;
     }
     if (ok && cx.wait_p(F - 1)) {                      // rows behind the span move up by the merged rows
-        __threadfence_block();
         const int bt = sh->base_total, n_post = S - first - (int)N;
         for (int t = unit; t < n_post; t += n_units) {
             const int r = first + (int)N + t, d = bt + t;
@@ -756,6 +823,7 @@ k_frame_merge(const __grid_constant__ FrameArgs a, const __grid_constant__ AuxPa
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         sh->base_next = 0;
+        sh->published = 0;
         sh->abort = 0;
         sh->base_total = 0;
     }
@@ -816,12 +884,18 @@ k_frame_merge(const __grid_constant__ FrameArgs a, const __grid_constant__ AuxPa
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const long long kept_vis = (long long)sh->base_total - first;
-        const long long n_merged = failed ? 0 : N - kept_vis;
-        int ec = 0;
-        if (failed || !((double)n_merged / (double)n_vis < a.bound)) ec = 3;    // top-k branch (or a wait gave up): the host redoes the call
-        frame_finish(a, N, n_vis, n_merged, ec, failed ? 1 : 0);
-        FR_STAMP(3, 6);                                     // status block out
+        if (!sh->published) {
+            const long long kept_vis = (long long)sh->base_total - first;
+            const long long n_merged = failed ? 0 : N - kept_vis;
+            int ec = 0;
+            if (failed || !((double)n_merged / (double)n_vis < a.bound)) ec = 3;    // top-k branch (or a wait gave up): the host redoes the call
+            frame_finish(a, N, n_vis, n_merged, ec, failed ? 1 : 0);
+        } else if (failed) {
+            a.status[FF_ST_INTERNAL] = 1;                   // after the status block went out
+            a.status[FF_ST_ERROR] = 3;
+            __threadfence_system();
+        }
+        FR_STAMP(3, 6);                                     // kernel done
     }
     pdl_trigger();
 }

@@ -327,6 +327,9 @@ class FrameFusion(nn.Module):
             imp.data_ptr() if imp is not None else None, stream))
         # the selection kernel writes S_keep before the gather runs: the host goes on while the rows move
         _lib.check(st.lib.ff_status_wait(st.ctx, stream))
+        if int(st.status[_lib.ST_INTERNAL]) != 0:
+            st.status[_lib.ST_INTERNAL] = 0
+            raise _lib.FFError("framefusion_b200: a wait inside the single-launch merge kernel of an earlier call timed out")
         s_keep = int(st.status[_lib.ST_SEQ_KEEP])
         outs = self._narrow(auxes, s_keep)
         position_embeddings = rebuild(outs)
@@ -399,7 +402,10 @@ class FrameFusion(nn.Module):
         status = st.status
         ran_fused = bool(fused & 1) and int(status[_lib.ST_FUSED]) == 1
         ran_frame = int(status[_lib.ST_FUSED]) == 2        # the library took the frame-pipelined kernel (first call of a prefill)
-        if (ran_fused or ran_frame) and int(status[_lib.ST_INTERNAL]) != 0:
+        if int(status[_lib.ST_INTERNAL]) != 0:
+            # (the frame-pipelined kernel publishes the status block before its last rows are out: a wait that gave up
+            # after that shows here at the latest at the next call)
+            status[_lib.ST_INTERNAL] = 0
             raise _lib.FFError("framefusion_b200: a wait inside the single-launch merge kernel timed out")
         if (ran_fused or ran_frame) and int(status[_lib.ST_ERROR]) == 3:
             # the single-launch kernels speculate on the threshold branch (and the frame-pipelined one on a uniform video
