@@ -459,7 +459,7 @@ struct FramePlan {
     int R, n_stages, smem, grid, threads;
 };
 
-bool frame_plan(const ff_ctx* ctx, const void* hidden, const void* out, int dtype, int64_t S, int64_t H, double thr, FramePlan* fp) {
+bool frame_plan(const ff_ctx* ctx, const void* hidden, const void* out, int dtype, int64_t S, int64_t H, double thr, bool force, FramePlan* fp) {
     static const int off = getenv("FF_NO_FRAME") ? atoi(getenv("FF_NO_FRAME")) : 0;
     if (off || !ctx->fresh_links || ctx->n_ids < 1 || S < 1 || S >= (1ll << 30)) return false;
     const int64_t row_bytes = H * (dtype == FF_F32 ? 4 : 2);
@@ -473,10 +473,16 @@ bool frame_plan(const ff_ctx* ctx, const void* hidden, const void* out, int dtyp
     if (n_stages > max_stages) n_stages = max_stages;
     if (n_stages > FR_MAXSTAGES) n_stages = FR_MAXSTAGES;
     if (n_stages < 4) return false;
+    const int64_t grid = (P + R - 1) / R;
+    // Where it pays (profiles/r02_sweep.jsonl): the pipeline advances one FRAME per ~1.45 us whatever a frame of a CTA
+    // holds, so a CTA has to move enough bytes per frame (>= 20 KB: 4 rows of 7 KB; 2 rows — 210 tokens per frame — lose
+    // to the multi-kernel path), nearly every SM has to have chains, and the ring has to cover the ~9 us a stage lives
+    // (>= 6 frames; five chains of 8-KB rows leave four).  `force` (flags bit 2) takes the kernel wherever it CAN run.
+    if (!force && (stage < 20 * 1024 || n_stages < 6 || grid * 10 < (int64_t)ctx->sm_count * 9)) return false;
     fp->R = (int)R;
     fp->n_stages = (int)n_stages;
     fp->smem = (int)(FR_META + (n_stages + 1) * stage);
-    fp->grid = (int)((P + R - 1) / R);
+    fp->grid = (int)grid;
     fp->threads = 32 * (2 + (R <= 4 ? FR_NPW : 1) + 3 * (int)R);   // producer, prefix warps, finisher, then S / G / aux per chain   // producer, prefix, S warps (two per chain up to four chains), G, aux
     return true;
 }
@@ -784,7 +790,7 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     if (!ctx->have_order) return fail(FF_E_BADARG, "by-patch order not in the workspace (the read-once kernel does not keep it): call ff_build_links");
 
     FramePlan fp;
-    if (!(flags & 2) && frame_plan(ctx, hidden, hidden_out, dtype, S, H, thr, &fp)) {
+    if (!(flags & 2) && frame_plan(ctx, hidden, hidden_out, dtype, S, H, thr, (flags & 4) != 0, &fp)) {
         if (ctx->ev_start) FF_CUDA(cudaEventRecord(ctx->ev_start, st));
         if (int rc = launch_frame(ctx, w, bank, fp, hidden, hidden_out, dtype, S, H, thr, bound, ap, st)) return rc;
         if (ctx->ev_stop) FF_CUDA(cudaEventRecord(ctx->ev_stop, st));

@@ -146,7 +146,7 @@ class FrameFusion(nn.Module):
         self.use_fused = False
         # the first merge call of a prefill on a uniform video runs as ONE launch (csrc/ff_frame.cuh: rows travel HBM ->
         # shared memory -> HBM once); the library checks the layout on the device and this class redoes the call on the
-        # multi-kernel path if it says no.  False: never ask for it.
+        # multi-kernel path if it says no.  False: never ask for it; "force": also on shapes where it is the slower one.
         self.use_frame = True
         self.debug_trace = False        # tests: keep what flowed between the stages of the last call
         self.last_trace = None
@@ -353,7 +353,7 @@ class FrameFusion(nn.Module):
         # align devices (main.py:106)
         self.patch_type = self.patch_type.to(device)
         sparsity_upper_bound = self._compute_pruning_ratio(self.sparsity_list, self.cost)
-        fused = (1 if self.use_fused else 0) | (0 if self.use_frame else 2)
+        fused = (1 if self.use_fused else 0) | (0 if self.use_frame else 2) | (4 if self.use_frame == "force" else 0)
         self._ensure_links(st, q_len, need_order=not (fused & 1))
 
         dt = hidden_states.dtype
@@ -398,7 +398,7 @@ class FrameFusion(nn.Module):
             # no by-patch order: rebuild the links, multi-kernel path
             self._links_for = None
             self._ensure_links(st, q_len, need_order=True)
-            launch(fused & 2)
+            launch(fused & 6)
         status = st.status
         ran_fused = bool(fused & 1) and int(status[_lib.ST_FUSED]) == 1
         ran_frame = int(status[_lib.ST_FUSED]) == 2        # the library took the frame-pipelined kernel (first call of a prefill)

@@ -205,4 +205,4 @@ def set_mode(ff, mode):
     elif mode is False:
         mode = "frame"
     ff.use_fused = mode == "fused"
-    ff.use_frame = mode == "frame"
+    ff.use_frame = "force" if mode == "frame" else False    # (the tests' shapes are mostly ones the library would not pick it for)

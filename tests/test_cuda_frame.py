@@ -62,6 +62,7 @@ def test_frame_kernel_feeds_the_calls_behind_it():
     oracle call by call."""
     wl = synth.make_workload(24, 300, 1024, torch.bfloat16, seed=11, r_lo=0.0, r_hi=1.0)
     ff = FrameFusion(0.3, 0.6, 0.1)
+    ff.use_frame = "force"
     ff.prepare(*synth.to_device(wl, "cuda").prepare_args())
     o = orc.OracleFrameFusion(0.3, 0.6, 0.1, "bf16")
     o.prepare(wl.patch_type.numpy(), wl.patch_num, *wl.prepare_args()[2:])
@@ -88,6 +89,7 @@ def test_frame_kernel_feeds_the_calls_behind_it():
 
 def run_against_oracle(wl, cost=0.3, slb=0.6):
     ff = FrameFusion(cost, slb, 0.1)
+    ff.use_frame = "force"
     ff.prepare(*synth.to_device(wl, "cuda").prepare_args())
     o = orc.OracleFrameFusion(cost, slb, 0.1, "bf16")
     o.prepare(wl.patch_type.numpy(), wl.patch_num, *wl.prepare_args()[2:])
@@ -166,3 +168,16 @@ def test_repeated_launches_are_identical():
         ff, h, pos, k = first_call(wl, "frame")
         assert k == 2
         assert same(h, h0) and same(pos[0], pos0[0]) and same(pos[1], pos0[1]), f"launch {it} differs"
+
+
+def test_the_library_picks_the_frame_kernel_where_it_is_the_faster_one():
+    """Default settings: 576 patches of 7-KB rows (C2 / C3) take the frame kernel; 210 tokens per frame, five chains of 8-KB
+    rows per SM (C4) and float32 C1 rows stay on the multi-kernel path (profiles/r02_sweep.jsonl)."""
+    for frames, patches, hidden, dtype, want in ((8, 576, 3584, torch.bfloat16, 2), (8, 210, 3584, torch.bfloat16, 0),
+                                                 (6, 729, 4096, torch.bfloat16, 0), (8, 196, 1024, torch.float32, 0)):
+        wl = synth.to_device(synth.make_workload(frames, patches, hidden, dtype, seed=1), "cuda")
+        ff = FrameFusion(0.3, 0.6, 0.1)
+        ff.prepare(*wl.prepare_args())
+        ff(wl.hidden, [wl.cos, wl.sin], None)
+        torch.cuda.synchronize()
+        assert int(ff._state(wl.hidden.device).status[_lib.ST_FUSED]) == want, (frames, patches, hidden)
