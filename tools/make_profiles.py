@@ -25,8 +25,14 @@ start = max(i for i, d in enumerate(data) if d[0].startswith("k_links_hist"))
 step = data[start:]
 tot = sum(d[1] for d in step)
 bench = json.loads(open(f"{out}/bench_{tag}.json").read().strip().splitlines()[-1])
-first_gather = next(i for i, d in enumerate(step) if "k_merge_gather" in d[0])
-first_sim = next(i for i, d in enumerate(step) if "k_similarity" in d[0])
+frame = [i for i, d in enumerate(step) if "k_frame_merge" in d[0]]
+if frame:
+    first_sim = first_gather = frame[0]
+    m0_names = "k_frame_merge, one launch"
+else:
+    first_gather = next(i for i, d in enumerate(step) if "k_merge_gather" in d[0])
+    first_sim = next(i for i, d in enumerate(step) if "k_similarity" in d[0])
+    m0_names = "k_similarity + k_keep_scan + k_merge_gather"
 m0 = sum(d[1] for d in step[first_sim:first_gather + 1])
 doc = [f"# {RND} — kernels of one bench step (C2), ncu launch list (final code of the round)", "",
        "Command (on the B200 box): `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline`",
@@ -35,12 +41,13 @@ doc = [f"# {RND} — kernels of one bench step (C2), ncu launch list (final code
 for i, d in enumerate(step):
     doc.append(f"| {i} | `{short(d[0])}` | {d[2]} | {d[3]} | {d[1]:.1f} | {100 * d[1] / tot:.1f} % |")
 r = bench["roofline"]
-doc += ["", f"Sum: {tot:.1f} us in {len(step)} launches.  Merge call #0 (the roofline kernel set, rows {first_sim}-{first_gather}: k_similarity + k_keep_scan + "
-        f"k_merge_gather) is {m0:.1f} us = {100 * m0 / tot:.1f} % of the step's kernel time; CUDA-event timing of the same launches inside bench.py, warm and "
+doc += ["", f"Sum: {tot:.1f} us in {len(step)} launches.  Merge call #0 (the roofline kernel set, rows {first_sim}-{first_gather}: {m0_names}) "
+        f"is {m0:.1f} us = {100 * m0 / tot:.1f} % of the step's kernel time; CUDA-event timing of the same launches inside bench.py, warm and "
         f"back to back: {r['kernel_us']:.1f} us -> {r['achieved']:.0f} GB/s algorithmic = {r['frac']:.3f} of the {r['peak']:.0f} GB/s peak ({r['peak_source']}).", "",
         f"Step wall time in the same bench run without ncu: {bench['ms_per_step'] * 1000:.0f} us for {len(step)} launches + 3 status reads; the difference to the "
         "kernel sum is host dispatch (Python + ctypes) that the GPU does not hide: the host reads the status block as soon as the deciding kernel "
-        "has published it (ff_status_wait) and prepares the next call while the gather runs.",
+        "has published it (ff_status_wait) and prepares the next call while the rest of that call runs (the frame-pipelined kernel sends it "
+        "when the last frame is decided, a few microseconds before its end; the scan kernels before their gather).",
         "The second merge call closes merging: nothing crosses the threshold any more, its gather returns after reading the counter and the operator hands its inputs back.",
         "The last `k_merge_gather` compacts the pruned sequence (no averaging)."]
 open(f"{prof}/{RND}_bench_step_launches.md", "w").write("\n".join(doc) + "\n")
