@@ -13,7 +13,7 @@ from . import _build
 _i64 = C.c_int64
 _vp = C.c_void_p
 
-ABI_VERSION = 4            # FF_ABI_VERSION of include/framefusion_b200.h
+ABI_VERSION = 5            # FF_ABI_VERSION of include/framefusion_b200.h
 FF_BF16, FF_F16, FF_F32 = 0, 1, 2
 FF_MAX_AUX = 6
 
@@ -23,7 +23,7 @@ ST_SLOTS = 16
 
 EXPORTS = [
     "ff_abi_version", "ff_last_error", "ff_launch_count", "ff_ctx_create", "ff_ctx_destroy", "ff_ctx_status", "ff_ctx_timing", "ff_stream_sync", "ff_status_wait", "ff_workspace_bytes",
-    "ff_build_links", "ff_similarity", "ff_merge_apply", "ff_merge_layer", "ff_importance", "ff_prune_layer",
+    "ff_build_links", "ff_build_links_for", "ff_similarity", "ff_merge_apply", "ff_merge_layer", "ff_importance", "ff_prune_layer",
     "ff_compact_mask", "ff_debug_read", "ff_debug_frame_trace",
 ]
 
@@ -66,6 +66,7 @@ def load():
     lib.ff_workspace_bytes.argtypes = [_i64, _i64]
     lib.ff_workspace_bytes.restype = _i64
     lib.ff_build_links.argtypes = [_vp, _vp, _i64, _vp, _i64, _i64, _vp]
+    lib.ff_build_links_for.argtypes = [_vp, _vp, _i64, _vp, _i64, _i64, _i64, C.c_int, _vp]
     lib.ff_similarity.argtypes = [_vp, _vp, _i64, _vp, C.c_int, _i64, _i64, C.c_double, _vp, _vp, _vp]
     lib.ff_merge_apply.argtypes = [_vp, _vp, _i64, _vp, C.c_int, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _vp]
     lib.ff_merge_layer.argtypes = [_vp, _vp, _i64, _vp, _vp, C.c_int, _i64, _i64, C.c_double, C.c_double,

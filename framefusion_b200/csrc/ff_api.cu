@@ -92,6 +92,8 @@ struct ff_ctx {
     unsigned bar_base;   // value of the grid-barrier word before the next k_keep_scan (it is not reset between merge calls)
     int bar_dirty;       // the prune stage left the barrier word at an unknown value
     long long seq;       // number of the last reducing call (status[FF_ST_SEQ] when its results are in the status block)
+    int links_lite;      // ff_build_links_for left only the counters: the next merge call must be the frame-pipelined kernel
+    int links_lite_last; // ... and the last merge call ran on such links (no by-patch order to read back)
     int frame_smem[6];   // dynamic shared memory the frame-pipelined kernel of each (dtype, build) is opted in for
     long long* frame_trace;          // ff_debug_frame_trace: device buffer for time stamps of the next frame-kernel launch
     int64_t frame_trace_bytes;
@@ -459,12 +461,12 @@ struct FramePlan {
     int R, n_stages, smem, grid, threads;
 };
 
-bool frame_plan(const ff_ctx* ctx, const void* hidden, const void* out, int dtype, int64_t S, int64_t H, double thr, bool force, FramePlan* fp) {
+// the part of the decision that depends on the shape alone (ff_build_links_for asks before the tensors are known)
+bool frame_shape(const ff_ctx* ctx, int64_t n_ids, int64_t S, int64_t row_bytes, bool force, FramePlan* fp) {
     static const int off = getenv("FF_NO_FRAME") ? atoi(getenv("FF_NO_FRAME")) : 0;
-    if (off || !ctx->fresh_links || ctx->n_ids < 1 || S < 1 || S >= (1ll << 30)) return false;
-    const int64_t row_bytes = H * (dtype == FF_F32 ? 4 : 2);
-    if (row_bytes % 16 != 0 || (((uintptr_t)hidden | (uintptr_t)out) & 15) != 0 || !(thr > -2.0)) return false;
-    const int64_t P = ctx->n_ids;
+    if (off || n_ids < 1 || S < 1 || S >= (1ll << 30)) return false;
+    if (row_bytes < 16 || row_bytes % 16 != 0) return false;
+    const int64_t P = n_ids;
     const int64_t R = (P + ctx->sm_count - 1) / ctx->sm_count;
     if (R > FR_MAXR) return false;
     const int64_t stage = R * row_bytes;
@@ -483,8 +485,13 @@ bool frame_plan(const ff_ctx* ctx, const void* hidden, const void* out, int dtyp
     fp->n_stages = (int)n_stages;
     fp->smem = (int)(FR_META + (n_stages + 1) * stage);
     fp->grid = (int)grid;
-    fp->threads = 32 * (2 + (R <= 4 ? FR_NPW : 1) + 3 * (int)R);   // producer, prefix warps, finisher, then S / G / aux per chain   // producer, prefix, S warps (two per chain up to four chains), G, aux
+    fp->threads = 32 * (2 + (R <= 4 ? FR_NPW : 1) + 3 * (int)R);   // producer, prefix warps, (finisher slot), then S / G / aux per chain
     return true;
+}
+
+bool frame_plan(const ff_ctx* ctx, const void* hidden, const void* out, int dtype, int64_t S, int64_t H, double thr, bool force, FramePlan* fp) {
+    if (!ctx->fresh_links || (((uintptr_t)hidden | (uintptr_t)out) & 15) != 0 || !(thr > -2.0)) return false;
+    return frame_shape(ctx, ctx->n_ids, S, H * (dtype == FF_F32 ? 4 : 2), force, fp);
 }
 
 int launch_frame(ff_ctx* ctx, const Ws& w, int bank, const FramePlan& fp, const void* hidden, void* out, int dtype, int64_t S,
@@ -590,6 +597,7 @@ int ff_ctx_create(int device, ff_ctx** out) {
     c->fused_smem[0] = c->fused_smem[1] = c->fused_smem[2] = 0;
     c->fused_smem_last[0] = c->fused_smem_last[1] = c->fused_smem_last[2] = 0;
     for (int i = 0; i < 6; ++i) c->frame_smem[i] = 0;
+    c->links_lite = c->links_lite_last = 0;
     c->frame_trace = nullptr;
     c->frame_trace_bytes = 0;
     cudaError_t e = cudaHostAlloc((void**)&c->h_status, FF_ST_SLOTS * 8, cudaHostAllocMapped | cudaHostAllocPortable);
@@ -658,6 +666,11 @@ int64_t ff_workspace_bytes(int64_t seq_capacity, int64_t n_ids) {
 
 int ff_build_links(ff_ctx* ctx, void* ws, int64_t ws_bytes, const int64_t* patch_type, int64_t S, int64_t n_ids,
                    void* stream) {
+    return ff_build_links_for(ctx, ws, ws_bytes, patch_type, S, n_ids, 0, 0, stream);
+}
+
+int ff_build_links_for(ff_ctx* ctx, void* ws, int64_t ws_bytes, const int64_t* patch_type, int64_t S, int64_t n_ids,
+                       int64_t next_row_bytes, int next_flags, void* stream) {
     Ws w;
     if (S < 0 || n_ids < 0 || S > (1ll << 30) || n_ids > (1ll << 24)) return fail(FF_E_BADARG, "bad S / n_ids");
     if (!ctx) return fail(FF_E_BADARG, "null ctx");
@@ -675,6 +688,21 @@ int ff_build_links(ff_ctx* ctx, void* ws, int64_t ws_bytes, const int64_t* patch
     ctx->bar_base = 0;
     ctx->bar_dirty = 0;
     ctx->count_clean[0] = ctx->count_clean[1] = 1;
+    ctx->links_lite = ctx->links_lite_last = 0;
+    FramePlan fp;
+    if (next_row_bytes > 0 && !(next_flags & 3) && S > 0 && frame_shape(ctx, n_ids, S, next_row_bytes, (next_flags & 4) != 0, &fp)) {
+        // the frame-pipelined kernel will serve the next call: it needs the counters and the layout check, not the order
+        k_links_uniform<<<n_chunks, LINK_CHUNK, 0, st>>>(patch_type, (int)S, (int)n_ids, w.counters[0], ctx->d_status);
+        FF_LAUNCH_CHECK("k_links_uniform");
+        ctx->parity = 0;
+        ctx->last_parity = 0;
+        ctx->links_S = S;
+        ctx->have_order = ctx->have_seq = 0;
+        ctx->fresh_links = 1;
+        ctx->links_lite = 1;
+        ctx->last_fused = 0;
+        return FF_OK;
+    }
     if (S > 0) {
         k_links_hist<<<n_chunks, LINK_CHUNK, 0, st>>>(patch_type, (int)S, (int)n_ids, w.hist, w.counters[0]);
         FF_LAUNCH_CHECK("k_links_hist");
@@ -769,7 +797,7 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     FF_DEVICE(ctx);
     const int bank = ctx->parity, nb = bank ^ 1;
 
-    if ((flags & 1) && S > 0 && fused_shape_ok(ctx, hidden, hidden_out, dtype, S, H, thr) && (ctx->have_seq || ctx->have_order)) {
+    if ((flags & 1) && !ctx->links_lite && S > 0 && fused_shape_ok(ctx, hidden, hidden_out, dtype, S, H, thr) && (ctx->have_seq || ctx->have_order)) {
         if (ctx->ev_start) FF_CUDA(cudaEventRecord(ctx->ev_start, st));
         if (!ctx->have_seq)                                // the previous call took the multi-kernel path: links from its arrays
             FF_LAUNCH("k_links_seq", k_links_seq, (int)((S + 255) / 256), 256, 0, st, w.rank[bank], w.order[bank], w.chain[bank],
@@ -784,13 +812,17 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
         ctx->links_S = -2;
         ctx->have_order = 0;
         ctx->have_seq = 1;
+        ctx->links_lite_last = 0;
         ctx->last_fused = 1;
         return FF_OK;
     }
-    if (!ctx->have_order) return fail(FF_E_BADARG, "by-patch order not in the workspace (the read-once kernel does not keep it): call ff_build_links");
-
     FramePlan fp;
-    if (!(flags & 2) && frame_plan(ctx, hidden, hidden_out, dtype, S, H, thr, (flags & 4) != 0, &fp)) {
+    const bool take_frame = !(flags & 2) && frame_plan(ctx, hidden, hidden_out, dtype, S, H, thr, (flags & 4) != 0, &fp);
+    if (ctx->links_lite && !take_frame)
+        return fail(FF_E_BADARG, "ff_build_links_for left the links for the frame-pipelined kernel only, and this call cannot take it: call ff_build_links");
+    if (!take_frame && !ctx->have_order) return fail(FF_E_BADARG, "by-patch order not in the workspace (the read-once kernel does not keep it): call ff_build_links");
+
+    if (take_frame) {
         if (ctx->ev_start) FF_CUDA(cudaEventRecord(ctx->ev_start, st));
         if (int rc = launch_frame(ctx, w, bank, fp, hidden, hidden_out, dtype, S, H, thr, bound, ap, st)) return rc;
         if (ctx->ev_stop) FF_CUDA(cudaEventRecord(ctx->ev_stop, st));
@@ -802,6 +834,8 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
         ctx->have_order = 1;                               // the kernel leaves the compact by-patch arrays of the next call
         ctx->have_seq = 0;
         ctx->fresh_links = 0;
+        ctx->links_lite_last = ctx->links_lite;
+        ctx->links_lite = 0;
         ctx->last_fused = 0;
         return FF_OK;
     }
@@ -858,6 +892,7 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     ctx->have_order = 1;
     ctx->have_seq = 0;                                     // the multi-kernel path keeps the compact arrays only
     ctx->fresh_links = 0;
+    ctx->links_lite_last = 0;
     ctx->last_fused = 0;
     return FF_OK;
 }
@@ -1046,7 +1081,9 @@ int ff_debug_read(ff_ctx* ctx, void* ws, int64_t ws_bytes, int what, void* dst_d
         case 0: k_keep_from_dst<<<grid, 256, 0, st>>>(w.dst[bank], (int)n, (uint8_t*)dst_device); break;
         case 1: k_copy_u8<<<grid, 256, 0, st>>>(w.flag, (int)n, (uint8_t*)dst_device); break;
         case 2: k_store_vals<<<grid, 256, 0, st>>>(w.sim, (int)n, dtype, dst_device); break;
-        case 3: k_store_order<<<grid, 256, 0, st>>>(w.order[bank], (int)n, (int64_t*)dst_device); break;
+        case 3:
+            if (ctx->links_lite_last) return fail(FF_E_BADARG, "the by-patch order was not built (ff_build_links_for): call ff_build_links");
+            k_store_order<<<grid, 256, 0, st>>>(w.order[bank], (int)n, (int64_t*)dst_device); break;
         default: return fail(FF_E_BADARG, "what=%d", what);
     }
     FF_LAUNCH_CHECK("debug_read");

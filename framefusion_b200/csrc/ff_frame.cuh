@@ -133,10 +133,18 @@ __device__ __forceinline__ void fr_mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void fr_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
+#ifndef FR_SUSPEND_NS
+#define FR_SUSPEND_NS 0                            // suspend-time hint of a try_wait: the warp sleeps until the phase completes or this long
+#endif
 __device__ __forceinline__ bool fr_mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+#if FR_SUSPEND_NS > 0
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)FR_SUSPEND_NS) : "memory");
+#else
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
     return ok != 0;
 }
 __device__ __forceinline__ void fr_tma_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {

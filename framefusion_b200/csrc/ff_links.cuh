@@ -126,4 +126,40 @@ k_links_scatter(const int64_t* __restrict__ pt, int S, int n_ids, const int* __r
     rank[i] = key < n_ids ? pos : -1;                      // by-patch position, chain rows only
 }
 
+// What the frame-pipelined merge kernel needs of the links, and nothing else: N (chain tokens), n_vis, the first chain
+// row, and whether the sequence is a uniform video — ONE span of chain rows whose patch ids run 0, 1, .., n_ids - 1, 0, ..
+// (the same counters k_links_hist / k_links_colscan / k_links_seq leave; no order, no ranks).
+__global__ void __launch_bounds__(LINK_CHUNK)
+k_links_uniform(const int64_t* __restrict__ pt, int S, int n_ids, int64_t* counters, int64_t* status) {
+    pdl_trigger();
+    __shared__ int s_nv[LINK_CHUNK / 32], s_nc[LINK_CHUNK / 32];
+    const int i = blockIdx.x * LINK_CHUNK + threadIdx.x;
+    int vis = 0, chain = 0;
+    if (i < S) {
+        const int64_t id = pt[i], pid = i > 0 ? pt[i - 1] : -1;
+        vis = (id != -1);
+        chain = (id >= 0 && id < n_ids);
+        if (chain) {
+            if (!(pid >= 0 && pid < n_ids)) {                   // start of a span of chain rows
+                atomicMax((unsigned long long*)&counters[C_FIRSTINV], (unsigned long long)(S - i));
+                atomicAdd((unsigned long long*)&counters[C_SPANS], 1ull);
+                if (id != 0) counters[C_NONUNI] = 1;
+            } else if (id != (pid + 1) % n_ids) {
+                counters[C_NONUNI] = 1;
+            }
+        }
+    }
+    vis = warp_sum_int(vis);
+    chain = warp_sum_int(chain);
+    if ((threadIdx.x & 31) == 0) { s_nv[threadIdx.x >> 5] = vis; s_nc[threadIdx.x >> 5] = chain; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tv = 0, tc = 0;
+        for (int w = 0; w < LINK_CHUNK / 32; ++w) { tv += s_nv[w]; tc += s_nc[w]; }
+        if (tv) atomicAdd((unsigned long long*)&counters[C_NVIS], (unsigned long long)tv);
+        if (tc) atomicAdd((unsigned long long*)&counters[C_N], (unsigned long long)tc);
+        if (blockIdx.x == 0) status[FF_ST_ERROR] = 0;
+    }
+}
+
 }  // namespace ff

@@ -194,7 +194,10 @@ class FrameFusion(nn.Module):
             patch_num = patch_num.item()
         return int(math.ceil(float(patch_num)))
 
-    def _ensure_links(self, st: _DeviceState, q_len: int, need_order: bool = False):
+    def _ensure_links(self, st: _DeviceState, q_len: int, need_order: bool = False, next_row_bytes: int = 0, next_flags: int = 0):
+        """Links of the current ``patch_type`` in the workspace.  ``next_row_bytes`` / ``next_flags`` describe the merge call
+        that follows: if the library will serve it with the frame-pipelined kernel it only counts the tokens and checks the
+        layout here (``ff_build_links_for``: one small kernel instead of the counting sort's four)."""
         pt = self.patch_type
         key = self._links_for
         if key is not None and key[0] is pt and key[1] == pt._version and key[2] == st.device \
@@ -206,9 +209,10 @@ class FrameFusion(nn.Module):
         st.workspace(q_len, n_ids)
         ptc = pt.reshape(-1).to(torch.int64).contiguous()
         wp, wb = st.ws_ptr()
-        _lib.check(st.lib.ff_build_links(st.ctx, wp, wb, ptc.data_ptr(), q_len, n_ids, _stream(st.device)))
+        _lib.check(st.lib.ff_build_links_for(st.ctx, wp, wb, ptc.data_ptr(), q_len, n_ids, next_row_bytes, next_flags,
+                                             _stream(st.device)))
         self._links_for = (pt, pt._version, st.device)
-        self._have_order = True
+        self._have_order = True      # (or the library keeps what its own next kernel needs: it refuses anything else)
 
     def _pos_aux(self, position_embeddings, auxes):
         """Registers the position container's tensors for compaction; returns a closure that rebuilds it."""
@@ -354,10 +358,12 @@ class FrameFusion(nn.Module):
         self.patch_type = self.patch_type.to(device)
         sparsity_upper_bound = self._compute_pruning_ratio(self.sparsity_list, self.cost)
         fused = (1 if self.use_fused else 0) | (0 if self.use_frame else 2) | (4 if self.use_frame == "force" else 0)
-        self._ensure_links(st, q_len, need_order=not (fused & 1))
-
         dt = hidden_states.dtype
         thr = _threshold_in(self.similarity_lower_bound, dt)                 # the scalar is compared in T
+        # tell the library what call follows: if it is going to be the frame-pipelined kernel, the counting sort of the
+        # links is not needed (debug_trace reads the by-patch order back, and a threshold at the sentinel never takes it)
+        lite_row_bytes = 0 if (self.debug_trace or (fused & 3) or not thr > -2.0) else hidden_size * hidden_states.element_size()
+        self._ensure_links(st, q_len, need_order=not (fused & 1), next_row_bytes=lite_row_bytes, next_flags=fused)
         hidden = hidden_states.contiguous()
         out = torch.empty_like(hidden)
         auxes = [_aux_of(self.patch_type.reshape(1, -1).to(torch.int64), 1) + (1,)]
@@ -392,13 +398,21 @@ class FrameFusion(nn.Module):
         try:
             launch(fused)
         except ValueError:
-            if not (fused & 1) or self._have_order:
+            if lite_row_bytes:
+                # the links were left for the frame-pipelined kernel only and the library cannot take it for these tensors
+                # (alignment): build them in full and let it choose again
+                lite_row_bytes = 0
+                self._links_for = None
+                self._ensure_links(st, q_len, need_order=True)
+                launch(fused)
+            elif not (fused & 1) or self._have_order:
                 raise
-            # the library declined the read-once kernel for this call (row size / alignment) and the previous call left
-            # no by-patch order: rebuild the links, multi-kernel path
-            self._links_for = None
-            self._ensure_links(st, q_len, need_order=True)
-            launch(fused & 6)
+            else:
+                # the library declined the read-once kernel for this call (row size / alignment) and the previous call left
+                # no by-patch order: rebuild the links, multi-kernel path
+                self._links_for = None
+                self._ensure_links(st, q_len, need_order=True)
+                launch(fused & 6)
         status = st.status
         ran_fused = bool(fused & 1) and int(status[_lib.ST_FUSED]) == 1
         ran_frame = int(status[_lib.ST_FUSED]) == 2        # the library took the frame-pipelined kernel (first call of a prefill)

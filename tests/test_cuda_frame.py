@@ -15,10 +15,10 @@ from framefusion_b200.main import FrameFusion
 pytestmark = pytest.mark.gpu
 
 
-def first_call(wl, mode, cost=0.3, slb=0.6, rlb=0.1):
+def first_call(wl, mode, cost=0.3, slb=0.6, rlb=0.1, debug=True):
     ff = FrameFusion(cost, slb, rlb)
     set_mode(ff, mode)
-    ff.debug_trace = True
+    ff.debug_trace = debug          # (with it the by-patch order is built in full; without, ff_build_links_for only checks the layout)
     ff.prepare(*wl.prepare_args())
     h, pos, _ = ff(wl.hidden, [wl.cos, wl.sin], None)
     torch.cuda.synchronize()
@@ -181,3 +181,35 @@ def test_the_library_picks_the_frame_kernel_where_it_is_the_faster_one():
         ff(wl.hidden, [wl.cos, wl.sin], None)
         torch.cuda.synchronize()
         assert int(ff._state(wl.hidden.device).status[_lib.ST_FUSED]) == want, (frames, patches, hidden)
+
+
+def test_links_left_for_the_frame_kernel_only():
+    """Without debug_trace the host announces the merge call to ff_build_links_for, which then skips the counting sort: same
+    outputs, four launches fewer, and the library refuses what it has no links for."""
+    lib = _lib.load()
+    wl = synth.to_device(synth.make_workload(10, 576, 1024, torch.bfloat16, seed=12, r_lo=0.0, r_hi=1.0), "cuda")
+    _ffm, h_m, pos_m, k_m = first_call(wl, "multi")
+    n0 = lib.ff_launch_count()
+    ff_full, h_full, pos_full, k_full = first_call(wl, "frame", debug=True)
+    n1 = lib.ff_launch_count()
+    ff_lite, h_lite, pos_lite, k_lite = first_call(wl, "frame", debug=False)
+    n2 = lib.ff_launch_count()
+    assert k_full == 2 and k_lite == 2
+    assert same(h_lite, h_m) and same(pos_lite[0], pos_m[0]) and same(pos_lite[1], pos_m[1]) and same(ff_lite.patch_type, ff_full.patch_type)
+    # full: 4 link kernels + the merge kernel + 4 debug reads; lite: 1 + 1
+    assert n2 - n1 == 2, (n1 - n0, n2 - n1)
+    # a second merge call runs the multi-kernel path on the arrays the frame kernel left
+    h2, pos2, _ = ff_lite(h_lite, pos_lite, None)
+    h2m, pos2m, _ = ff_full(h_full, pos_full, None)
+    torch.cuda.synchronize()
+    assert same(h2, h2m) and same(pos2[0], pos2m[0])
+    # straight through the C ABI: after ff_build_links_for nothing but the frame kernel may follow
+    st = ff_lite._state(wl.hidden.device)
+    wp, wb = st.ws_ptr()
+    pt = wl.patch_type.reshape(-1).to(torch.int64).contiguous()
+    stream = torch.cuda.current_stream().cuda_stream
+    assert lib.ff_build_links_for(st.ctx, wp, wb, pt.data_ptr(), wl.seq_len, 576, 2048, 0, stream) == 0
+    out = torch.empty_like(wl.hidden)
+    rc = lib.ff_merge_layer(st.ctx, wp, wb, wl.hidden.data_ptr(), out.data_ptr(), 0, wl.seq_len, 1024, 0.6, 0.7, None, 0, 2, stream)
+    assert rc == -1 and b"ff_build_links" in lib.ff_last_error()
+    torch.cuda.synchronize()
