@@ -473,7 +473,7 @@ __device__ __forceinline__ void fr_role_sim(const FrameArgs& a, const AuxPack& a
     // time per row, and this warp's time per row is the period of the whole pipeline.
     const int w = w_role;
     if (w < Rc) {
-        long long c_wait = 0, c_busy = 0, c0 = clock64();   // (traced launches: where this warp's cycles go)
+        long long c_wait = 0, c_busy = 0, c_loop = 0, c_red = 0, c0 = clock64();   // (traced launches: where this warp's cycles go)
         float na_prev = 0.f;                                // (no finisher: the squares of the previous row)
         (void)na_prev;
         for (int f = 0; f < F; ++f) {
@@ -553,8 +553,11 @@ __device__ __forceinline__ void fr_role_sim(const FrameArgs& a, const AuxPack& a
                     if (v + 32 < nvec) fr_nb<DT>(fr_lds16(cur + (v - lane + 32) * 16), b1);
                 }
             }
+            long long c_l = 0, c_r = 0;
+            if (a.trace) c_l = clock64();
             const float dot = warp_sum((d0.x + d0.y) + (d1.x + d1.y));
             const float nb = warp_sum((b0.x + b0.y) + (b1.x + b1.y));
+            if (a.trace) { c_r = clock64(); c_loop += c_l - c0; c_red += c_r - c_l; }
 #if FR_FINISHER
             if (lane == 0) {
                 sh->psum[f % FR_NQ][w][0] = dot;
@@ -580,7 +583,7 @@ __device__ __forceinline__ void fr_role_sim(const FrameArgs& a, const AuxPack& a
             __syncwarp();
             if (a.trace) { const long long c1 = clock64(); c_busy += c1 - c0; c0 = c1; }
         }
-        if (w == 0 && lane == 0) { FR_NOTE(0, 7, c_busy); FR_NOTE(1, 7, c_wait); }
+        if (w == 0 && lane == 0) { FR_NOTE(0, 7, c_busy); FR_NOTE(1, 7, c_wait); FR_NOTE(4, 7, c_loop); FR_NOTE(5, 7, c_red); }
     }
 }
 

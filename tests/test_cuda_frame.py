@@ -208,7 +208,7 @@ def test_links_left_for_the_frame_kernel_only():
     wp, wb = st.ws_ptr()
     pt = wl.patch_type.reshape(-1).to(torch.int64).contiguous()
     stream = torch.cuda.current_stream().cuda_stream
-    assert lib.ff_build_links_for(st.ctx, wp, wb, pt.data_ptr(), wl.seq_len, 576, 2048, 0, stream) == 0
+    assert lib.ff_build_links_for(st.ctx, wp, wb, pt.data_ptr(), wl.seq_len, 576, 2048, 4, stream) == 0     # (4: wherever it can run)
     out = torch.empty_like(wl.hidden)
     rc = lib.ff_merge_layer(st.ctx, wp, wb, wl.hidden.data_ptr(), out.data_ptr(), 0, wl.seq_len, 1024, 0.6, 0.7, None, 0, 2, stream)
     assert rc == -1 and b"ff_build_links" in lib.ff_last_error()

@@ -33,7 +33,7 @@ def main():
         h, pos, _m = ff(wl.hidden, [wl.cos, wl.sin], None)
         torch.cuda.synchronize()
     raw = buf.cpu().numpy().reshape(-1)[: n_cta * frames * K].reshape(n_cta, frames, K).astype(np.float64)
-    notes = raw[:, :4, 7].copy()                            # cycle counts, not time stamps
+    notes = raw[:, :6, 7].copy()                            # cycle counts, not time stamps
     raw[:, :, 7] = 0
     t = raw
     t0 = t[:, :, 0][t[:, :, 0] > 0].min()
@@ -47,6 +47,7 @@ def main():
     print(f"grid through: median {np.nanmedian(t[:, 2, 6]):.2f} [{np.nanmin(t[:, 2, 6]):.2f}, {np.nanmax(t[:, 2, 6]):.2f}];  status block out: {np.nanmax(t[:, 3, 6]):.2f}")
     mhz = 1.92e3
     print(f"cycles of S warp 0 / frame: busy {np.median(notes[:, 0]) / frames:.0f} ({np.median(notes[:, 0]) / frames / mhz:.2f} us at 1.92 GHz), waiting {np.median(notes[:, 1]) / frames:.0f}; "
+          f"[S: loop {np.median(notes[:, 4]) / frames:.0f}, the two warp reductions {np.median(notes[:, 5]) / frames:.0f}, rounding chain + flag + global writes {(np.median(notes[:, 0]) - np.median(notes[:, 4]) - np.median(notes[:, 5])) / frames:.0f}] "
           f"G warp 0 / frame: busy {np.median(notes[:, 2]) / frames:.0f} ({np.median(notes[:, 2]) / frames / mhz:.2f} us), waiting {np.median(notes[:, 3]) / frames:.0f}")
     d = np.diff(np.nanmedian(t[:, :, 3], axis=0))
     print(f"rows-out period per frame: median {np.nanmedian(d):.2f} us, mean {np.nanmean(d):.2f} us; span {np.nanmax(t):.1f} us")
