@@ -85,6 +85,16 @@ def Qwen2SdpaAttention_merge_then_prune_by_cost_forward(
     **kwargs,
 ):
     """-> ``(attn_output, importance_or_None)``.  ``importance`` is ``[1, heads, 1, S]`` (reference :166-178)."""
+    ff = self.framefusion
+    want = hidden_states.shape[1] > 1 and ff.finish_merging and not ff.finish_pruning
+    return attention_with_importance(self, hidden_states, position_embeddings, attention_mask, past_key_values, want, **kwargs)
+
+
+def attention_with_importance(self, hidden_states, position_embeddings, attention_mask, past_key_values, want_importance,
+                              **kwargs):
+    """The stock attention forward plus, when ``want_importance``, the last query's attention probabilities
+    ``[1, heads, 1, S]`` as second output (shared by the FrameFusion hook above and the FastV baseline hook,
+    ``hooks/qwen2_baselines.py``)."""
     for stale in ("position_ids", "use_cache", "output_attentions", "cache_position"):
         kwargs.pop(stale, None)
     input_shape = hidden_states.shape[:-1]
@@ -111,8 +121,7 @@ def Qwen2SdpaAttention_merge_then_prune_by_cost_forward(
     is_causal = attention_mask is None and q_len > 1
 
     attn_weights = None
-    ff = self.framefusion
-    if q_len > 1 and ff.finish_merging and not ff.finish_pruning:
+    if want_importance:
         attn_weights = scaled_dot_product_attention(
             query_states, key_states, value_states, num=1, attn_mask=None,
             dropout_p=self.attention_dropout if self.training else 0.0,
@@ -128,20 +137,10 @@ def Qwen2SdpaAttention_merge_then_prune_by_cost_forward(
     return attn_output, attn_weights
 
 
-def Qwen2Model_merge_then_fastv_cost_given_forward(
-    self,
-    input_ids: Optional[torch.LongTensor] = None,
-    attention_mask: Optional[torch.Tensor] = None,
-    position_ids: Optional[torch.LongTensor] = None,
-    past_key_values: Optional[Cache] = None,
-    inputs_embeds: Optional[torch.FloatTensor] = None,
-    use_cache: Optional[bool] = None,
-    output_attentions: Optional[bool] = None,
-    output_hidden_states: Optional[bool] = None,
-    return_dict: Optional[bool] = None,
-    cache_position: Optional[torch.LongTensor] = None,
-    **kwargs,
-):
+def model_inputs(self, input_ids, attention_mask, position_ids, past_key_values, inputs_embeds, use_cache):
+    """What every patched model forward does before its layer loop: embeddings, cache, positions, the causal masks per
+    layer kind and the position embeddings as a LIST (so that an operator can swap its entries, reference :262-266).
+    -> ``(hidden_states, position_ids, past_key_values, masks, position_embeddings, use_cache)``."""
     use_cache = use_cache if use_cache is not None else self.config.use_cache
     if (input_ids is None) ^ (inputs_embeds is not None):
         raise ValueError("You must specify exactly one of input_ids or inputs_embeds")
@@ -173,9 +172,41 @@ def Qwen2Model_merge_then_fastv_cost_given_forward(
     hidden_states = inputs_embeds
     # a list, so that FrameFusion can replace its entries (reference :262-266)
     position_embeddings = list(self.rotary_emb(hidden_states, position_ids))
+    return hidden_states, position_ids, past_key_values, dict(causal_mask_mapping), position_embeddings, use_cache
+
+
+def model_outputs(self, hidden_states, past_key_values, use_cache, all_hidden_states, return_dict):
+    hidden_states = self.norm(hidden_states)
+    if all_hidden_states is not None:
+        all_hidden_states += (hidden_states,)
+    out = BaseModelOutputWithPast(
+        last_hidden_state=hidden_states,
+        past_key_values=past_key_values if use_cache else None,
+        hidden_states=all_hidden_states,
+    )
+    if return_dict is False:
+        return out.to_tuple()
+    return out
+
+
+def Qwen2Model_merge_then_fastv_cost_given_forward(
+    self,
+    input_ids: Optional[torch.LongTensor] = None,
+    attention_mask: Optional[torch.Tensor] = None,
+    position_ids: Optional[torch.LongTensor] = None,
+    past_key_values: Optional[Cache] = None,
+    inputs_embeds: Optional[torch.FloatTensor] = None,
+    use_cache: Optional[bool] = None,
+    output_attentions: Optional[bool] = None,
+    output_hidden_states: Optional[bool] = None,
+    return_dict: Optional[bool] = None,
+    cache_position: Optional[torch.LongTensor] = None,
+    **kwargs,
+):
+    hidden_states, position_ids, past_key_values, masks, position_embeddings, use_cache = model_inputs(
+        self, input_ids, attention_mask, position_ids, past_key_values, inputs_embeds, use_cache)
 
     all_hidden_states = () if output_hidden_states else None
-    masks = dict(causal_mask_mapping)
     for i, decoder_layer in enumerate(self.layers[: self.config.num_hidden_layers]):
         if output_hidden_states:
             all_hidden_states += (hidden_states,)
@@ -194,14 +225,4 @@ def Qwen2Model_merge_then_fastv_cost_given_forward(
         position_embeddings = layer_outputs[-2]
         masks[kind] = layer_outputs[-1]
 
-    hidden_states = self.norm(hidden_states)
-    if output_hidden_states:
-        all_hidden_states += (hidden_states,)
-    out = BaseModelOutputWithPast(
-        last_hidden_state=hidden_states,
-        past_key_values=past_key_values if use_cache else None,
-        hidden_states=all_hidden_states,
-    )
-    if return_dict is False:
-        return out.to_tuple()
-    return out
+    return model_outputs(self, hidden_states, past_key_values, use_cache, all_hidden_states, return_dict)

@@ -295,7 +295,9 @@ class FrameFusion(nn.Module):
         if not t.is_cuda:
             raise RuntimeError("framefusion_b200 runs on CUDA tensors only (there is no CPU fallback)")
 
-    def _prune(self, hidden_states, position_embeddings, attention_mask, self_attn_weights):
+    def _prune(self, hidden_states, position_embeddings, attention_mask, self_attn_weights, pruning_ratio=None):
+        """One prune stage.  ``pruning_ratio`` None: the budget formula (main.py:76-78); a number: that fraction of the
+        vision span goes (the fixed-ratio baselines, ``baselines.py``)."""
         self._require_cuda(hidden_states)
         bsz, q_len, hidden_size = hidden_states.size()
         assert bsz == 1, "Only support batch size 1"
@@ -312,7 +314,8 @@ class FrameFusion(nn.Module):
         if attn.shape[-1] != q_len:
             raise RuntimeError(f"self_attn_weights covers {attn.shape[-1]} keys, hidden_states has {q_len} tokens")
         attn = attn.reshape(-1, q_len).to(hidden_states.dtype).contiguous()
-        pruning_ratio = self._compute_pruning_ratio(self.sparsity_list, self.cost)
+        if pruning_ratio is None:
+            pruning_ratio = self._compute_pruning_ratio(self.sparsity_list, self.cost)
         k = round(length * (1 - pruning_ratio))
         if k < 0 or k > length or start < 0 or start + length > q_len:
             raise RuntimeError(f"selected index k out of range (k={k}, vision span [{start}, {start + length}) of {q_len})")
@@ -347,7 +350,11 @@ class FrameFusion(nn.Module):
                                    start=start, length=length)
         return hidden_states, position_embeddings, attention_mask
 
-    def _merge(self, hidden_states, position_embeddings, attention_mask):
+    def _merge(self, hidden_states, position_embeddings, attention_mask, fixed_sparsity=None):
+        """One merge stage.  ``fixed_sparsity`` None: threshold / budget as in main.py:109-127; a number s: exactly the
+        ``int(s * n_vis)`` most similar tokens merge (the top-k branch with a given k — the fixed-sparsity baseline,
+        ``baselines.py``): the threshold sits below the chain-head sentinel, so every token counts and the device takes the
+        top-k branch with ``bound = s``; the operator's own state (flags, ``sparsity_list``) is left alone."""
         self._require_cuda(hidden_states)
         bsz, q_len, hidden_size = hidden_states.size()
         assert bsz == 1, "Only support batch size 1"
@@ -356,10 +363,13 @@ class FrameFusion(nn.Module):
 
         # align devices (main.py:106)
         self.patch_type = self.patch_type.to(device)
-        sparsity_upper_bound = self._compute_pruning_ratio(self.sparsity_list, self.cost)
+        fixed = fixed_sparsity is not None
+        sparsity_upper_bound = float(fixed_sparsity) if fixed else self._compute_pruning_ratio(self.sparsity_list, self.cost)
         fused = (1 if self.use_fused else 0) | (0 if self.use_frame else 2) | (4 if self.use_frame == "force" else 0)
+        if fixed:
+            fused = 2                                                        # the top-k branch lives on the multi-kernel path
         dt = hidden_states.dtype
-        thr = _threshold_in(self.similarity_lower_bound, dt)                 # the scalar is compared in T
+        thr = -3.0 if fixed else _threshold_in(self.similarity_lower_bound, dt)   # the scalar is compared in T
         # tell the library what call follows: if it is going to be the frame-pipelined kernel, the counting sort of the
         # links is not needed (debug_trace reads the by-patch order back, and a threshold at the sentinel never takes it)
         lite_row_bytes = 0 if (self.debug_trace or (fused & 3) or not thr > -2.0) else hidden_size * hidden_states.element_size()
@@ -437,7 +447,9 @@ class FrameFusion(nn.Module):
         s_keep, branch = int(status[_lib.ST_SEQ_KEEP]), int(status[_lib.ST_BRANCH])
         above_k_ratio = count / frame_token_num
         assert (above_k_ratio < sparsity_upper_bound) == (branch == 0), "device / host branch decision disagree"
-        if above_k_ratio < sparsity_upper_bound:
+        if fixed:
+            pass                                                             # a given k: no budget bookkeeping
+        elif above_k_ratio < sparsity_upper_bound:
             self.sparsity_list.append(above_k_ratio)
             if above_k_ratio < self.ratio_lower_bound:
                 self.finish_merging = True
