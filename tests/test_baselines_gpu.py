@@ -123,7 +123,8 @@ def test_patched_prefill_call_by_call(mode, kw):
     def merge_at(i, hidden, pos, mask):
         h_in = t2f(hidden[0])
         pt_in = op.patch_type.reshape(-1).cpu().numpy().copy()
-        assert np.array_equal(pt_in, o.patch_type)
+        if op.sparsity is not None and any(s > 0 for s in op.sparsity[i:]):
+            assert np.array_equal(pt_in, o.patch_type)      # (the layout is only kept up while merges are still to come)
         out = inner_merge(i, hidden, pos, mask)
         if out[0].shape[1] != h_in.shape[0]:
             keep = check_merge_call(op, h_in, pt_in, wl.patch_num, op.sparsity[i], out)
