@@ -544,6 +544,8 @@ int launch_frame(ff_ctx* ctx, const Ws& w, int bank, const FramePlan& fp, const 
             a.auxf.dst[e] = (char*)x.dst + pl * x.dst_plane_stride;
         }
     }
+    // (ff_ctx_timing: the start event goes in when the arguments are ready — right in front of the call's first stream operation)
+    if (ctx->ev_start) FF_CUDA(cudaEventRecord(ctx->ev_start, st));
     if (!ctx->fused_clean[bank]) FF_CUDA(cudaMemsetAsync(w.desc[bank], 0, (size_t)(S / 32 + 2) * 8, st));
     ctx->fused_clean[bank] = 0;
     return dispatch_dtype(dtype, [&](auto dt) {
@@ -823,7 +825,6 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     if (!take_frame && !ctx->have_order) return fail(FF_E_BADARG, "by-patch order not in the workspace (the read-once kernel does not keep it): call ff_build_links");
 
     if (take_frame) {
-        if (ctx->ev_start) FF_CUDA(cudaEventRecord(ctx->ev_start, st));
         if (int rc = launch_frame(ctx, w, bank, fp, hidden, hidden_out, dtype, S, H, thr, bound, ap, st)) return rc;
         if (ctx->ev_stop) FF_CUDA(cudaEventRecord(ctx->ev_stop, st));
         ctx->count_clean[bank] = 0;

@@ -120,7 +120,7 @@ class FrameFusion(nn.Module):
     _PLAIN = frozenset((
         "cost", "similarity_lower_bound", "ratio_lower_bound", "patch_type", "patch_num", "image_token_start_index",
         "image_token_end_index", "image_token_length", "original_length", "finish_merging", "finish_pruning",
-        "sparsity_list", "use_fused", "use_frame", "debug_trace", "last_trace", "kernel_events", "_links_for", "_have_order",
+        "sparsity_list", "use_fused", "use_frame", "debug_trace", "last_trace", "kernel_events", "kernel_events_len", "_links_for", "_have_order",
         "_dev"))
 
     def __setattr__(self, name, value):
@@ -151,6 +151,7 @@ class FrameFusion(nn.Module):
         self.debug_trace = False        # tests: keep what flowed between the stages of the last call
         self.last_trace = None
         self.kernel_events = None       # bench: a list collects (name, start, end) CUDA events around ff_* launches
+        self.kernel_events_len = None   # ... of the merge calls whose sequence has this length only (None: of every merge call)
 
     # ---------------------------------------------------------------------------------------------
     def prepare(
@@ -385,6 +386,8 @@ class FrameFusion(nn.Module):
 
         def launch(flags):
             ev = self.kernel_events
+            if ev is not None and self.kernel_events_len not in (None, q_len):
+                ev = None                                                    # only calls on a sequence of that length are timed
             if ev is not None:
                 # the library records the two events right around its own launches (ff_ctx_timing): GPU time of the
                 # call's kernels, without the host's way to the first launch

@@ -21,7 +21,7 @@ rows = list(csv.reader(l for l in open(f"{out}/bench_launches_{tag}.csv") if l.s
 hdr = rows[0]
 ki, vi, gi, bi = (hdr.index(k) for k in ("Kernel Name", "Metric Value", "Grid Size", "Block Size"))
 data = [(r[ki].replace("void ", "").replace("ff::", ""), float(r[vi].replace(",", "")) / 1000, r[gi], r[bi]) for r in rows[1:]]
-start = max(i for i, d in enumerate(data) if d[0].startswith("k_links_hist"))
+start = max(i for i, d in enumerate(data) if d[0].startswith(("k_links_hist", "k_links_uniform")))   # the first kernel of a step
 step = data[start:]
 tot = sum(d[1] for d in step)
 bench = json.loads(open(f"{out}/bench_{tag}.json").read().strip().splitlines()[-1])
