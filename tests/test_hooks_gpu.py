@@ -315,3 +315,64 @@ def test_layer_split_over_two_gpus_matches_one_gpu():
     a, b = outs
     assert a[1:] == b[1:]
     assert torch.equal(a[0], b[0])
+
+
+@pytest.mark.parametrize("mode", ["default", "frame"])
+def test_two_operators_on_two_threads_and_streams(mode):
+    """Two models served from two host threads, each on its own stream (include/framefusion_b200.h: a context per operator and
+    device, the stream passed per call, ``ff_last_error`` thread-local): the interleaved runs give bit for bit what each
+    operator gives alone.  "frame": the first merge call of both runs as the frame-pipelined kernel (96 + 60 persistent CTAs
+    that wait for each other through global flags: more than the 148 SMs hold at once)."""
+    import threading
+    from framefusion_b200.main import FrameFusion
+    from framefusion_b200.utils import scaled_dot_product_attention
+
+    def make(seed, frames, patches, lo, hi):
+        wl = synth.to_device(synth.make_workload(frames, patches, 1024, torch.bfloat16, seed=seed, r_lo=lo, r_hi=hi), "cuda")
+        q, k = synth.make_attention_inputs(wl.seq_len, 28, 4, 128, torch.bfloat16, seed=seed)
+        return wl, q[:, :, -1:, :].contiguous().cuda(), k.cuda()
+
+    def run(ff, wl, q_last, keys):
+        ff.prepare(*wl.prepare_args())
+        h, pos = wl.hidden, [wl.cos, wl.sin]
+        guard = 0
+        while not ff.finish_merging and guard < 8:
+            h, pos, _ = ff(h, pos, None)
+            guard += 1
+        if not ff.finish_pruning:
+            attn = scaled_dot_product_attention(q_last, keys[:, :, :h.shape[1]], None, num=1, is_causal=True, enable_gqa=True)
+            h, pos, _ = ff(h, pos, None, attn)
+        return h.clone(), pos[0].clone(), list(ff.sparsity_list)
+
+    def operator():
+        ff = FrameFusion(0.3, 0.6, 0.1)
+        if mode == "frame":
+            ff.use_frame = "force"
+        return ff
+
+    jobs = [make(21, 24, 96, 0.0, 1.0), make(22, 32, 60, 0.0, 0.5)]
+    alone = [run(operator(), *j) for j in jobs]
+    torch.cuda.synchronize()
+    results, errors = [None, None], []
+
+    def worker(i):
+        try:
+            stream = torch.cuda.Stream()
+            ff = operator()
+            with torch.cuda.stream(stream):
+                for _ in range(12):
+                    out = run(ff, *jobs[i])
+                stream.synchronize()
+            results[i] = out
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errors, errors
+    for got, want in zip(results, alone):
+        assert got is not None and got[2] == want[2]
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
