@@ -12,7 +12,7 @@ legs (DESIGN.md "Measurement").
 
 Printed line (rank 0): the contract of the task statement — ``value`` is device-resident throughput (CUDA events,
 max over ranks), ``e2e`` the same step driven from pinned HOST buffers with the copies inside the timed region,
-``roofline`` the dominant kernel (the fused merge kernel of call #0) timed live with CUDA events on its stream,
+``roofline`` the dominant kernel (the single-launch merge kernel of call #0) timed live with CUDA events on its stream,
 ``cpu_baseline`` the reference's algorithm on this box's host cores.
 
 N > 1: the operator does not shard (SURVEY.md §8e — one request, batch 1, global top-k/count): every rank runs
@@ -614,15 +614,14 @@ def main():
     alg = synth.algorithmic_bytes(wl.seq_len, s_keep0, c["hidden"], devt["hidden"].element_size())
     peak, peak_src = hbm_peak()
     # which kernel served call #0: 2 = the frame-pipelined kernel (one launch, every row HBM -> shared memory -> HBM once),
-    # 0 = the multi-kernel path (similarity, scan, gather), 1 = the read-once kernel of r02 (opt-in)
+    # 0 = the multi-kernel path (similarity, scan, gather)
     kernel_names = {2: "k_frame_merge (one launch: rows travel HBM -> shared memory -> HBM once)",
-                    1: "k_fused_merge (one launch, second visit of a row out of the L2)",
                     0: "multi-kernel path (k_similarity + k_keep_scan + k_merge_gather)"}
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f).get(cfg, {})
-            traffic = tj.get({2: "frame_kernel_dram_bytes_per_launch", 1: "single_pass_kernel_dram_bytes_per_launch"}.get(fused, "dram_bytes_per_launch"))
+            traffic = tj.get({2: "frame_kernel_dram_bytes_per_launch"}.get(fused, "dram_bytes_per_launch"))
     except Exception:
         pass
     achieved = alg / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0

@@ -13,7 +13,7 @@ from . import _build
 _i64 = C.c_int64
 _vp = C.c_void_p
 
-ABI_VERSION = 5            # FF_ABI_VERSION of include/framefusion_b200.h
+ABI_VERSION = 6            # FF_ABI_VERSION of include/framefusion_b200.h
 FF_BF16, FF_F16, FF_F32 = 0, 1, 2
 FF_MAX_AUX = 6
 

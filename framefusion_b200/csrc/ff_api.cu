@@ -9,7 +9,6 @@
 
 #include "ff_common.cuh"
 #include "ff_frame.cuh"
-#include "ff_fused.cuh"
 #include "ff_importance.cuh"
 #include "ff_links.cuh"
 #include "ff_merge.cuh"
@@ -77,13 +76,8 @@ struct ff_ctx {
     int64_t cap;         // capacity the workspace is carved for (set by ff_build_links)
     int64_t n_ids;
     int have_order;      // compact by-patch order / chain / rank arrays valid for `parity` (multi-kernel path)
-    int have_seq;        // (pred, succ) of every sequence row valid for `parity` (read-once kernel)
-    int fresh_links;     // ... and they are the ones ff_build_links made (counters[C_FIRSTINV] valid: order of the S units)
-    int last_fused;      // the last merge call ran the read-once kernel: sim[] is indexed by sequence row
-    int fused_clean[2];  // state words / tile descriptors of the bank are known to be zero
-    int fused_attr[3];   // resident CTAs per SM of the read-once kernel of each dtype (0: not asked yet)
-    int fused_smem[3];   // dynamic shared memory the kernel of each dtype is opted in for
-    int fused_smem_last[3];   // ... and the size fused_attr was computed for
+    int fresh_links;     // ... and they are the ones ff_build_links made (counters[C_FIRSTINV / C_SPANS / C_NONUNI] valid)
+    int words_clean[2];  // the flag words of the bank (frame-pipelined kernel) are known to be zero
     int sm_count;
     int max_smem;        // opt-in dynamic shared memory per block
     int smem_per_sm, smem_reserved;   // shared memory of an SM / what the system keeps per resident block
@@ -128,8 +122,7 @@ struct Ws {
     int* len[2];        // [n_ids + 1] rows per chain; bucket n_ids = rows outside the chains
     float* sim;
     uint8_t* flag;
-    int2* link[2];      // [cap] (pred, succ) of every sequence row (read-once kernel)
-    unsigned long long* desc[2];     // ticket, band words, exclusive prefixes of the bands, kept masks
+    unsigned long long* desc[2];     // frame-pipelined kernel: barrier / abort words, then (reported << 32 | kept) per 32 rows
     int* dst[2];
     int* srcidx;
     int4* rec;          // [cap] per kept chain row in by-patch order: (source row, destination row, by-patch position, run length)
@@ -160,7 +153,7 @@ Ws carve(void* base_ptr, int64_t cap, int64_t n_ids) {
     w.barrier = (unsigned*)take(256);
     w.sel_hist = (int*)take(4 * 256 * 4);
     for (int b = 0; b < 2; ++b) {
-        w.desc[b] = (unsigned long long*)take(16 + ((size_t)cap / 32 + 2) * 8 + ((size_t)cap / 1024 + 2) * 4 + 16);   // ticket, u64 per 32 rows, u32 per band
+        w.desc[b] = (unsigned long long*)take(16 + ((size_t)cap / 32 + 2) * 8);   // two words in front, u64 per 32 rows
     }
     w.zero_begin = zero_begin;
     w.zero_bytes = (size_t)((p ? p + off : (char*)nullptr) - zero_begin);
@@ -172,8 +165,6 @@ Ws carve(void* base_ptr, int64_t cap, int64_t n_ids) {
     }
     w.sim = (float*)take(cap * 4);
     w.flag = (uint8_t*)take(cap);
-    w.link[0] = (int2*)take((size_t)cap * 8);
-    w.link[1] = (int2*)take((size_t)cap * 8);
     w.dst[0] = (int*)take(cap * 4);
     w.dst[1] = (int*)take(cap * 4);
     w.srcidx = (int*)take(cap * 4);
@@ -347,7 +338,7 @@ int links_ready(ff_ctx* ctx, int64_t S, bool need_order) {
     if (ctx->links_S != S)
         return fail(FF_E_BADARG, "chain links in the workspace describe S=%lld, not %lld: call ff_build_links", (long long)ctx->links_S, (long long)S);
     if (need_order && !ctx->have_order)
-        return fail(FF_E_BADARG, "by-patch order not in the workspace (the read-once kernel does not keep it): call ff_build_links");
+        return fail(FF_E_BADARG, "by-patch order not in the workspace: call ff_build_links");
     return FF_OK;
 }
 
@@ -356,102 +347,6 @@ int check_shape(int64_t S, int64_t H, int dtype) {
     if (S < 0 || H < 1) return fail(FF_E_BADARG, "bad shape S=%lld H=%lld", (long long)S, (long long)H);
     if (S > (1ll << 30) || H > (1ll << 24)) return fail(FF_E_UNSUPPORTED, "S=%lld H=%lld too large", (long long)S, (long long)H);
     return FF_OK;
-}
-
-// FF_FUSED_LAG overrides the lag of the read-once kernel (ff_fused.cuh) for experiments
-int fused_lag() {
-    static int lag = -1;
-    if (lag < 0) {
-        const char* e = getenv("FF_FUSED_LAG");
-        lag = (e ? atoi(e) : FU_LAG) / 32 * 32;
-        if (lag < FU_BAND) lag = FU_BAND;                   // a G unit only waits for S units with a smaller ticket
-    }
-    return lag;
-}
-
-// rows the read-once kernel handles: 16-byte multiples and a threshold no chain head (sim = -2) can pass
-bool fused_shape_ok(const ff_ctx* ctx, const void* hidden, const void* out, int dtype, int64_t S, int64_t H, double thr) {
-    const int64_t row_bytes = H * (dtype == FF_F32 ? 4 : 2);
-    if (row_bytes % 16 != 0 || (((uintptr_t)hidden | (uintptr_t)out) & 15) != 0) return false;
-    if (S >= (1ll << 30) - 2 * (int64_t)fused_lag()) return false;
-    (void)ctx;
-    return thr > -2.0;
-}
-
-int launch_fused(ff_ctx* ctx, const Ws& w, int bank, const void* hidden, void* out, int dtype, int64_t S, int64_t H,
-                 double thr, double bound, const AuxPack& ap, cudaStream_t st) {
-    const int nb = bank ^ 1;
-    FusedArgs a;
-    a.hidden = (const char*)hidden;
-    a.out = (char*)out;
-    a.S = (int)S;
-    a.row_bytes = (int)(H * (dtype == FF_F32 ? 4 : 2));
-    a.nvec = a.row_bytes / 16;
-    const int s32 = (int)((S + 31) / 32 * 32);
-    a.nwords = s32 / 32;
-    a.nbands = (a.nwords + 31) / 32;
-    // S units patch by patch over FF_FUSED_SFRAMES frames on the call right after ff_build_links (uniform videos, ff_fused.cuh)
-    static const int s_frames = getenv("FF_FUSED_SFRAMES") ? atoi(getenv("FF_FUSED_SFRAMES")) : FU_SFRAMES;
-    a.perm_P = ctx->fresh_links && ctx->n_ids > 0 && ctx->n_ids * (int64_t)s_frames < (1 << 20) ? (int)ctx->n_ids : 0;
-    a.perm_F = a.perm_P ? s_frames : 0;
-    int lag = fused_lag();
-    if (a.perm_F > 1 && lag < a.perm_P * a.perm_F + 64) lag = (a.perm_P * a.perm_F + 64 + 31) / 32 * 32;   // a G unit only waits for S units with a smaller ticket
-    a.lag = lag < s32 ? lag : s32;
-    a.n_tickets = a.lag + 2 * s32;
-    a.desc_words = 1 + a.nwords + (a.nbands + 1) / 2;
-    a.link = w.link[bank];
-    a.link_next = w.link[nb];
-    a.desc = w.desc[bank];
-    a.desc_clr = w.desc[nb];
-    a.sim_seq = w.sim;
-    a.dst = w.dst[bank];
-    a.counters = w.counters[bank];
-    a.counters_next = w.counters[nb];
-    a.status = ctx->d_status;
-    a.thr = (float)thr;
-    a.bound = bound;
-    a.seq = ++ctx->seq;
-    // the aux tensors as (tensor, plane) entries of one piece per lane, when they have that form
-    a.auxf.n = 0;
-    for (int q = 0; q < ap.n && a.auxf.n >= 0; ++q) {
-        const ff_aux& x = ap.a[q];
-        const uintptr_t al = (uintptr_t)x.src | (uintptr_t)x.dst | (uintptr_t)x.src_plane_stride | (uintptr_t)x.dst_plane_stride | (uintptr_t)x.row_bytes;
-        const int piece = (al & 15) == 0 ? 16 : ((al & 7) == 0 ? 8 : 0);
-        if (piece == 0 || x.row_bytes > 32 * piece || a.auxf.n + x.planes > 8) { a.auxf.n = -1; break; }
-        for (int64_t pl = 0; pl < x.planes; ++pl) {
-            const int e = a.auxf.n++;
-            a.auxf.row_bytes[e] = (int)x.row_bytes;
-            a.auxf.piece[e] = piece;
-            a.auxf.src[e] = (const char*)x.src + pl * x.src_plane_stride;
-            a.auxf.dst[e] = (char*)x.dst + pl * x.dst_plane_stride;
-        }
-    }
-    if (!ctx->fused_clean[bank]) FF_CUDA(cudaMemsetAsync(w.desc[bank], 0, (size_t)a.desc_words * 8, st));
-    ctx->fused_clean[bank] = 0;
-    ctx->fused_clean[nb] = 1;                              // the kernel clears the other bank on its way out
-    ctx->h_status[FF_ST_INTERNAL] = 0;
-    const int threads = FU_WARPS * 32;
-    const int smem = 0;
-    return dispatch_dtype(dtype, [&](auto dt) {
-        constexpr int DT = decltype(dt)::value;
-        if (ctx->fused_smem[DT] < smem) {
-            FF_CUDA(cudaFuncSetAttribute(k_fused_merge<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            ctx->fused_smem[DT] = smem;
-            ctx->fused_attr[DT] = 0;
-        }
-        if (ctx->fused_attr[DT] == 0 || ctx->fused_smem_last[DT] != smem) {
-            int per_sm = 0;
-            FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_merge<DT>, threads, smem));
-            if (per_sm < 1) return fail(FF_E_UNSUPPORTED, "the read-once kernel does not fit an SM");
-            ctx->fused_attr[DT] = per_sm;
-            ctx->fused_smem_last[DT] = smem;
-        }
-        static const int max_ctas = getenv("FF_FUSED_CTAS") ? atoi(getenv("FF_FUSED_CTAS")) : FU_MIN_CTAS;
-        int grid = (ctx->fused_attr[DT] < max_ctas ? ctx->fused_attr[DT] : max_ctas) * ctx->sm_count;
-        if ((int64_t)grid * FU_WARPS > a.n_tickets) grid = (a.n_tickets + FU_WARPS - 1) / FU_WARPS;
-        FF_LAUNCH("k_fused_merge", k_fused_merge<DT>, grid, threads, smem, st, a, ap);
-        return (int)FF_OK;
-    });
 }
 
 // The frame-pipelined kernel (ff_frame.cuh) serves the first merge call of a prefill when the rows are 16-byte
@@ -546,8 +441,8 @@ int launch_frame(ff_ctx* ctx, const Ws& w, int bank, const FramePlan& fp, const 
     }
     // (ff_ctx_timing: the start event goes in when the arguments are ready — right in front of the call's first stream operation)
     if (ctx->ev_start) FF_CUDA(cudaEventRecord(ctx->ev_start, st));
-    if (!ctx->fused_clean[bank]) FF_CUDA(cudaMemsetAsync(w.desc[bank], 0, (size_t)(S / 32 + 2) * 8, st));
-    ctx->fused_clean[bank] = 0;
+    if (!ctx->words_clean[bank]) FF_CUDA(cudaMemsetAsync(w.desc[bank], 0, (size_t)(S / 32 + 2) * 8, st));
+    ctx->words_clean[bank] = 0;
     return dispatch_dtype(dtype, [&](auto dt) {
         constexpr int DT = decltype(dt)::value;
         // two builds: up to four chains per CTA (14 warps, no register pressure) and up to FR_MAXR
@@ -590,14 +485,10 @@ int ff_ctx_create(int device, ff_ctx** out) {
     c->links_S = -1;
     c->cap = 0;
     c->n_ids = 0;
-    c->have_order = c->have_seq = 0;
+    c->have_order = 0;
     c->fresh_links = 0;
     c->seq = 0;
-    c->last_fused = 0;
-    c->fused_clean[0] = c->fused_clean[1] = 0;
-    c->fused_attr[0] = c->fused_attr[1] = c->fused_attr[2] = 0;
-    c->fused_smem[0] = c->fused_smem[1] = c->fused_smem[2] = 0;
-    c->fused_smem_last[0] = c->fused_smem_last[1] = c->fused_smem_last[2] = 0;
+    c->words_clean[0] = c->words_clean[1] = 0;
     for (int i = 0; i < 6; ++i) c->frame_smem[i] = 0;
     c->links_lite = c->links_lite_last = 0;
     c->frame_trace = nullptr;
@@ -686,7 +577,7 @@ int ff_build_links_for(ff_ctx* ctx, void* ws, int64_t ws_bytes, const int64_t* p
     const int n_chunks = (int)((S + LINK_CHUNK - 1) / LINK_CHUNK);
     const int n_b = (int)n_ids + 1;                        // chain buckets + the bucket of rows outside the chains
     FF_CUDA(cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, st));
-    ctx->fused_clean[0] = ctx->fused_clean[1] = 1;         // inside the region cleared above
+    ctx->words_clean[0] = ctx->words_clean[1] = 1;         // inside the region cleared above
     ctx->bar_base = 0;
     ctx->bar_dirty = 0;
     ctx->count_clean[0] = ctx->count_clean[1] = 1;
@@ -699,10 +590,9 @@ int ff_build_links_for(ff_ctx* ctx, void* ws, int64_t ws_bytes, const int64_t* p
         ctx->parity = 0;
         ctx->last_parity = 0;
         ctx->links_S = S;
-        ctx->have_order = ctx->have_seq = 0;
+        ctx->have_order = 0;
         ctx->fresh_links = 1;
         ctx->links_lite = 1;
-        ctx->last_fused = 0;
         return FF_OK;
     }
     if (S > 0) {
@@ -713,7 +603,7 @@ int ff_build_links_for(ff_ctx* ctx, void* ws, int64_t ws_bytes, const int64_t* p
         FF_LAUNCH("k_links_scatter", k_links_scatter, n_chunks, LINK_CHUNK, 0, st, patch_type, (int)S, (int)n_ids, w.hist,
                   w.base, w.order[0], w.chain[0], w.rank[0]);
         FF_LAUNCH("k_links_seq", k_links_seq, (int)((S + 255) / 256), 256, 0, st, w.rank[0], w.order[0], w.chain[0], w.counters[0],
-                  (int)S, (int)(n_ids > 0 ? n_ids : 1), w.link[0], (unsigned long long*)&w.counters[0][C_FIRSTINV]);
+                  (int)S, (int)(n_ids > 0 ? n_ids : 1), (unsigned long long*)&w.counters[0][C_FIRSTINV]);
     } else {
         k_links_status<<<1, 1, 0, st>>>(w.counters[0], ctx->d_status);
         FF_LAUNCH_CHECK("k_links_status");
@@ -721,9 +611,8 @@ int ff_build_links_for(ff_ctx* ctx, void* ws, int64_t ws_bytes, const int64_t* p
     ctx->parity = 0;
     ctx->last_parity = 0;
     ctx->links_S = S;
-    ctx->have_order = ctx->have_seq = 1;
+    ctx->have_order = 1;
     ctx->fresh_links = 1;
-    ctx->last_fused = 0;
     return FF_OK;
 }
 
@@ -760,8 +649,7 @@ int ff_merge_apply(ff_ctx* ctx, void* ws, int64_t ws_bytes, void* hidden, int dt
     if (!ctx) return fail(FF_E_BADARG, "null ctx");
     if (ctx->cap < S) { ctx->cap = S; ctx->n_ids = 0; }
     ctx->links_S = -1;                                     // scratch use of the order arrays
-    ctx->have_order = ctx->have_seq = 0;
-    ctx->last_fused = 0;
+    ctx->have_order = 0;
     if (int rc = check_ws(ctx, ws, ws_bytes, S, &w)) return rc;
     if (!keep_mask_out && S > 0) return fail(FF_E_BADARG, "keep_mask_out is null");
     cudaStream_t st = (cudaStream_t)stream;
@@ -799,30 +687,12 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     FF_DEVICE(ctx);
     const int bank = ctx->parity, nb = bank ^ 1;
 
-    if ((flags & 1) && !ctx->links_lite && S > 0 && fused_shape_ok(ctx, hidden, hidden_out, dtype, S, H, thr) && (ctx->have_seq || ctx->have_order)) {
-        if (ctx->ev_start) FF_CUDA(cudaEventRecord(ctx->ev_start, st));
-        if (!ctx->have_seq)                                // the previous call took the multi-kernel path: links from its arrays
-            FF_LAUNCH("k_links_seq", k_links_seq, (int)((S + 255) / 256), 256, 0, st, w.rank[bank], w.order[bank], w.chain[bank],
-                      w.counters[bank], (int)S, 1, w.link[bank], (unsigned long long*)nullptr);
-        if (int rc = launch_fused(ctx, w, bank, hidden, hidden_out, dtype, S, H, thr, bound, ap, st)) return rc;
-        ctx->fresh_links = 0;
-        if (ctx->ev_stop) FF_CUDA(cudaEventRecord(ctx->ev_stop, st));
-        ctx->count_clean[bank] = 0;
-        ctx->count_clean[nb] = 1;
-        ctx->last_parity = bank;
-        ctx->parity = nb;
-        ctx->links_S = -2;
-        ctx->have_order = 0;
-        ctx->have_seq = 1;
-        ctx->links_lite_last = 0;
-        ctx->last_fused = 1;
-        return FF_OK;
-    }
+    if (flags & 1) return fail(FF_E_BADARG, "flags bit 0 (the read-once kernel of ABI 2 .. 5) is reserved and must be 0");
     FramePlan fp;
     const bool take_frame = !(flags & 2) && frame_plan(ctx, hidden, hidden_out, dtype, S, H, thr, (flags & 4) != 0, &fp);
     if (ctx->links_lite && !take_frame)
         return fail(FF_E_BADARG, "ff_build_links_for left the links for the frame-pipelined kernel only, and this call cannot take it: call ff_build_links");
-    if (!take_frame && !ctx->have_order) return fail(FF_E_BADARG, "by-patch order not in the workspace (the read-once kernel does not keep it): call ff_build_links");
+    if (!take_frame && !ctx->have_order) return fail(FF_E_BADARG, "by-patch order not in the workspace: call ff_build_links");
 
     if (take_frame) {
         if (int rc = launch_frame(ctx, w, bank, fp, hidden, hidden_out, dtype, S, H, thr, bound, ap, st)) return rc;
@@ -833,11 +703,9 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
         ctx->parity = nb;
         ctx->links_S = -2;
         ctx->have_order = 1;                               // the kernel leaves the compact by-patch arrays of the next call
-        ctx->have_seq = 0;
         ctx->fresh_links = 0;
         ctx->links_lite_last = ctx->links_lite;
         ctx->links_lite = 0;
-        ctx->last_fused = 0;
         return FF_OK;
     }
 
@@ -891,10 +759,8 @@ int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, 
     ctx->parity = nb;
     ctx->links_S = -2;                                     // = S_keep, known once the host has synchronised
     ctx->have_order = 1;
-    ctx->have_seq = 0;                                     // the multi-kernel path keeps the compact arrays only
     ctx->fresh_links = 0;
     ctx->links_lite_last = 0;
-    ctx->last_fused = 0;
     return FF_OK;
 }
 
@@ -965,7 +831,7 @@ int ff_prune_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* attn, in
     AuxPack ap;
     if (int rc = check_shape(S, H, dtype)) return rc;
     if (!ctx) return fail(FF_E_BADARG, "null ctx");
-    if (ctx->cap < S) { ctx->cap = S; ctx->n_ids = 0; ctx->links_S = -1; ctx->have_order = ctx->have_seq = 0; }
+    if (ctx->cap < S) { ctx->cap = S; ctx->n_ids = 0; ctx->links_S = -1; ctx->have_order = 0; }
     if (int rc = check_ws(ctx, ws, ws_bytes, S, &w)) return rc;
     if (int rc = pack_aux(aux, n_aux, &ap)) return rc;
     if (!attn || !hidden || !hidden_out || n_rows < 1 || S < 1) return fail(FF_E_BADARG, "null / empty argument");

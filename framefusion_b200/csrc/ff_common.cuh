@@ -352,4 +352,58 @@ __device__ __forceinline__ uint32_t float_key(float x) {
 template <int DT>
 __device__ __forceinline__ float load_T(const void* p, int64_t i) { return Num<DT>::load(p, i); }
 
+// ---- shared by the single-launch kernel (ff_frame.cuh) and the gather ---------------------------------------------------
+// the aux tensors, one entry per (tensor, plane): rows of at most 512 bytes in 16- or 8-byte pieces, one piece per lane
+struct AuxFlat {
+    int n;                                         // entries; -1: the tensors do not fit this form (gather_aux_rows instead)
+    int row_bytes[8];
+    int piece[8];                                  // 16 or 8: bytes per lane
+    const char* src[8];
+    char* dst[8];
+};
+
+// relaxed device-scope accesses to the flag words the CTAs of a grid exchange
+// ---- PTX wrappers ----------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_relaxed64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed32(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// ---- row movers: 16-byte vectors; a row is cut into pieces of N vectors per lane (N = MAXN ... 1) and a last partial
+// piece, so that every piece issues its N (or 2 N) loads back to back with no predicate in between — predicated loads
+// are not batched by ptxas, and a warp with one or two loads in flight is latency bound.
+template <int N>
+__device__ __forceinline__ void copy_piece(const char* __restrict__ src, char* __restrict__ dst) {
+    uint4 x[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) x[q] = ld_stream16(src + q * 512);
+#pragma unroll
+    for (int q = 0; q < N; ++q) st_stream16(dst + q * 512, x[q]);
+}
+
+// src row -> dst row (read for the last time, written once: streaming both ways)
+__device__ __forceinline__ void copy_row(const char* __restrict__ src, char* __restrict__ dst, int nvec, int lane) {
+    int v = 0;                                              // vectors done (warp-uniform)
+    src += lane * 16;
+    dst += lane * 16;
+#pragma unroll 1
+    for (; v + 256 <= nvec; v += 256) copy_piece<8>(src + (int64_t)v * 16, dst + (int64_t)v * 16);
+    if (v + 128 <= nvec) { copy_piece<4>(src + (int64_t)v * 16, dst + (int64_t)v * 16); v += 128; }
+    if (v + 64 <= nvec) { copy_piece<2>(src + (int64_t)v * 16, dst + (int64_t)v * 16); v += 64; }
+    if (v + 32 <= nvec) { copy_piece<1>(src + (int64_t)v * 16, dst + (int64_t)v * 16); v += 32; }
+    if (v + lane < nvec) copy_piece<1>(src + (int64_t)v * 16, dst + (int64_t)v * 16);
+}
+
 }  // namespace ff

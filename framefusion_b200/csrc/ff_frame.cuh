@@ -31,7 +31,6 @@
 // FF_ST_ERROR = 3 and the host redoes the call on the multi-kernel path (the input is never modified).
 #pragma once
 #include "ff_common.cuh"
-#include "ff_fused.cuh"
 #include "ff_merge.cuh"
 
 namespace ff {

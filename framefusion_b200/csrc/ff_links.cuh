@@ -162,4 +162,27 @@ k_links_uniform(const int64_t* __restrict__ pt, int S, int n_ids, int64_t* count
     }
 }
 
+// Is the sequence a uniform video — ONE span of chain rows whose patch ids run 0, 1, .., n_ids - 1, 0, 1, .. ?  That is the
+// layout the frame-pipelined kernel (ff_frame.cuh) serves; counted from the compact by-patch arrays after the counting sort
+// (first call of a prefill): C_FIRSTINV = S - first chain row, C_SPANS, C_NONUNI.
+__global__ void __launch_bounds__(256)
+k_links_seq(const int* __restrict__ rank, const int* __restrict__ order, const int* __restrict__ chain,
+            int64_t* __restrict__ counters, int S, int n_ids, unsigned long long* first_inv) {
+    pdl_enter();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const int j = rank[i];
+    if (j >= 0) {
+        const int c = chain[j];
+        const int jp = i > 0 ? rank[i - 1] : -1;
+        if (jp < 0) {                                           // start of a span of chain rows
+            atomicMax(first_inv, (unsigned long long)(S - i));
+            atomicAdd((unsigned long long*)&counters[C_SPANS], 1ull);
+            if (c != 0) counters[C_NONUNI] = 1;
+        } else if (c != (chain[jp] + 1) % n_ids) {
+            counters[C_NONUNI] = 1;
+        }
+    }
+}
+
 }  // namespace ff

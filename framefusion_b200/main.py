@@ -120,7 +120,7 @@ class FrameFusion(nn.Module):
     _PLAIN = frozenset((
         "cost", "similarity_lower_bound", "ratio_lower_bound", "patch_type", "patch_num", "image_token_start_index",
         "image_token_end_index", "image_token_length", "original_length", "finish_merging", "finish_pruning",
-        "sparsity_list", "use_fused", "use_frame", "debug_trace", "last_trace", "kernel_events", "kernel_events_len", "_links_for", "_have_order",
+        "sparsity_list", "use_frame", "debug_trace", "last_trace", "kernel_events", "kernel_events_len", "_links_for", "_have_order",
         "_dev"))
 
     def __setattr__(self, name, value):
@@ -140,10 +140,6 @@ class FrameFusion(nn.Module):
         self._dev = {}                  # torch.device -> _DeviceState
         self._links_for = None          # (patch_type tensor, its _version, device) the workspace links describe
         self._have_order = False        # the workspace holds the compact by-patch order (the multi-kernel path needs it)
-        # merge-stage kernel choice: False = multi-kernel path (similarity -> scan -> gather/merge: 159 us at C2, the faster
-        # one), True = the read-once kernel (one launch, one HBM read of hidden_states: 216 us at C2; it falls back by itself
-        # for the top-k branch and for shapes it does not take).  DESIGN.md section 5 has the measurements.
-        self.use_fused = False
         # the first merge call of a prefill on a uniform video runs as ONE launch (csrc/ff_frame.cuh: rows travel HBM ->
         # shared memory -> HBM once); the library checks the layout on the device and this class redoes the call on the
         # multi-kernel path if it says no.  False: never ask for it; "force": also on shapes where it is the slower one.
@@ -366,15 +362,15 @@ class FrameFusion(nn.Module):
         self.patch_type = self.patch_type.to(device)
         fixed = fixed_sparsity is not None
         sparsity_upper_bound = float(fixed_sparsity) if fixed else self._compute_pruning_ratio(self.sparsity_list, self.cost)
-        fused = (1 if self.use_fused else 0) | (0 if self.use_frame else 2) | (4 if self.use_frame == "force" else 0)
+        flags = (0 if self.use_frame else 2) | (4 if self.use_frame == "force" else 0)
         if fixed:
-            fused = 2                                                        # the top-k branch lives on the multi-kernel path
+            flags = 2                                                        # the top-k branch lives on the multi-kernel path
         dt = hidden_states.dtype
         thr = -3.0 if fixed else _threshold_in(self.similarity_lower_bound, dt)   # the scalar is compared in T
         # tell the library what call follows: if it is going to be the frame-pipelined kernel, the counting sort of the
         # links is not needed (debug_trace reads the by-patch order back, and a threshold at the sentinel never takes it)
-        lite_row_bytes = 0 if (self.debug_trace or (fused & 3) or not thr > -2.0) else hidden_size * hidden_states.element_size()
-        self._ensure_links(st, q_len, need_order=not (fused & 1), next_row_bytes=lite_row_bytes, next_flags=fused)
+        lite_row_bytes = 0 if (self.debug_trace or (flags & 2) or not thr > -2.0) else hidden_size * hidden_states.element_size()
+        self._ensure_links(st, q_len, need_order=True, next_row_bytes=lite_row_bytes, next_flags=flags)
         hidden = hidden_states.contiguous()
         out = torch.empty_like(hidden)
         auxes = [_aux_of(self.patch_type.reshape(1, -1).to(torch.int64), 1) + (1,)]
@@ -402,45 +398,36 @@ class FrameFusion(nn.Module):
                     st.lib.ff_ctx_timing(st.ctx, None, None)
             if ev is not None:
                 ev.append(("ff_merge_layer", q_len, e0, e1))
-            # multi-kernel path: the scan kernel writes the status block before the gather runs, and the host goes on
-            # while the rows move (everything it enqueues next is ordered behind them).  The read-once kernel reports at
-            # its very end, a timed-out wait (FF_ST_INTERNAL) even later: wait for the stream.
-            wait = st.lib.ff_stream_sync if flags & 1 else st.lib.ff_status_wait
-            _lib.check(wait(st.ctx, stream))
+            # the deciding kernel writes the status block before the rows have all moved (the scan kernel before the gather
+            # runs, the frame-pipelined kernel when its last frame is decided), and the host goes on meanwhile: everything it
+            # enqueues next is ordered behind them
+            _lib.check(st.lib.ff_status_wait(st.ctx, stream))
 
         try:
-            launch(fused)
+            launch(flags)
         except ValueError:
-            if lite_row_bytes:
-                # the links were left for the frame-pipelined kernel only and the library cannot take it for these tensors
-                # (alignment): build them in full and let it choose again
-                lite_row_bytes = 0
-                self._links_for = None
-                self._ensure_links(st, q_len, need_order=True)
-                launch(fused)
-            elif not (fused & 1) or self._have_order:
+            if not lite_row_bytes:
                 raise
-            else:
-                # the library declined the read-once kernel for this call (row size / alignment) and the previous call left
-                # no by-patch order: rebuild the links, multi-kernel path
-                self._links_for = None
-                self._ensure_links(st, q_len, need_order=True)
-                launch(fused & 6)
+            # the links were left for the frame-pipelined kernel only and the library cannot take it for these tensors
+            # (alignment): build them in full and let it choose again
+            lite_row_bytes = 0
+            self._links_for = None
+            self._ensure_links(st, q_len, need_order=True)
+            launch(flags)
         status = st.status
-        ran_fused = bool(fused & 1) and int(status[_lib.ST_FUSED]) == 1
         ran_frame = int(status[_lib.ST_FUSED]) == 2        # the library took the frame-pipelined kernel (first call of a prefill)
         if int(status[_lib.ST_INTERNAL]) != 0:
             # (the frame-pipelined kernel publishes the status block before its last rows are out: a wait that gave up
             # after that shows here at the latest at the next call)
             status[_lib.ST_INTERNAL] = 0
             raise _lib.FFError("framefusion_b200: a wait inside the single-launch merge kernel timed out")
-        if (ran_fused or ran_frame) and int(status[_lib.ST_ERROR]) == 3:
-            # the single-launch kernels speculate on the threshold branch (and the frame-pipelined one on a uniform video
-            # layout); the device says otherwise: redo with the multi-kernel path (the input is untouched)
+        if ran_frame and int(status[_lib.ST_ERROR]) == 3:
+            # the single-launch kernel speculates on the threshold branch and on a uniform video layout; the device says
+            # otherwise: redo with the multi-kernel path (the input is untouched)
             self._links_for = None
             self._ensure_links(st, q_len, need_order=True)
             launch(2)
-            ran_fused = ran_frame = False
+            ran_frame = False
         err = int(status[_lib.ST_ERROR])
         if err == 1:
             raise ZeroDivisionError("division by zero")                      # frame_token_num == 0 (main.py:114)
@@ -460,14 +447,11 @@ class FrameFusion(nn.Module):
             self.finish_merging = True
             self.finish_pruning = True
 
-        self._have_order = not ran_fused
+        self._have_order = True
         if self.debug_trace:
-            if ran_fused:
-                self._record_fused_trace(st, hidden, q_len)
-            else:
-                self._record_merge_trace(st, hidden, q_len, int(status[_lib.ST_NCHAIN]), branch)
+            self._record_merge_trace(st, hidden, q_len, int(status[_lib.ST_NCHAIN]), branch)
 
-        if not ran_fused and not ran_frame and int(status[_lib.ST_NMERGED]) == 0:
+        if not ran_frame and int(status[_lib.ST_NMERGED]) == 0:
             # nothing was merged: the sequence is unchanged and the gather kernel did not run — hand the inputs back
             # (the reference returns copies with the same values; its callers rebind them, modeling_qwen2.py:46,67)
             self._links_for = (self.patch_type, self.patch_type._version, device)
@@ -511,30 +495,6 @@ class FrameFusion(nn.Module):
             merge_index=np.nonzero(flags[:n_chain].cpu().numpy())[0],
             sim_values=sim[:n_chain].float().cpu().numpy(),
             order=order[:n_chain].cpu().numpy())
-
-    def _record_fused_trace(self, st, hidden, q_len):
-        """The fused kernel keeps similarities by sequence position and no by-patch order: rebuild the by-patch
-        view the parity harness compares (order from the static API on a separate workspace)."""
-        device = hidden.device
-        wp, wb = st.ws_ptr()
-        stream = _stream(device)
-        keep = torch.empty(q_len, dtype=torch.uint8, device=device)
-        sim_seq = torch.empty(q_len, dtype=hidden.dtype, device=device)
-        _lib.check(st.lib.ff_debug_read(st.ctx, wp, wb, 0, keep.data_ptr(), q_len, 0, stream))
-        _lib.check(st.lib.ff_debug_read(st.ctx, wp, wb, 2, sim_seq.data_ptr(), q_len, _dtype_code(hidden), stream))
-        pt = self.patch_type.reshape(-1)
-        _sim, order = FrameFusion.compute_similarity_and_token_index_by_patch(hidden, pt, self.patch_num)
-        order = order[0]
-        ids = pt[order]
-        head = torch.ones_like(ids, dtype=torch.bool)
-        if ids.numel() > 1:
-            head[1:] = ids[1:] != ids[:-1]
-        sim = sim_seq[order].float()
-        sim[head] = IGNORE_TOKEN
-        keep_np = keep.cpu().numpy().astype(bool)
-        order_np = order.cpu().numpy()
-        self.last_trace = dict(stage="merge", branch="threshold", keep_mask=keep_np,
-                               merge_index=np.nonzero(~keep_np[order_np])[0], sim_values=sim.cpu().numpy(), order=order_np)
 
     # ---------------------------------------------------------------------------------------------
     # static helpers with the reference's signatures (main.py:180-343)

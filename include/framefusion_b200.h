@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FF_ABI_VERSION 5
+#define FF_ABI_VERSION 6
 
 enum ff_dtype { FF_BF16 = 0, FF_F16 = 1, FF_F32 = 2 };
 
@@ -51,16 +51,16 @@ enum ff_status_slot {
     FF_ST_NCHAIN = 3,      /* N: tokens whose patch id is in [0, n_ids)             (main.py:208-214) */
     FF_ST_BRANCH = 4,      /* 0 = threshold branch, 1 = top-k branch                (main.py:116-127) */
     FF_ST_TOPK = 5,        /* k used by the branch that ran (merge top-k or prune top-k) */
-    FF_ST_ERROR = 6,       /* device-side error: 0 ok, 1 n_vis == 0, 2 k > N, 3 a single-launch kernel (FUSED = 1 or 2) could
+    FF_ST_ERROR = 6,       /* device-side error: 0 ok, 1 n_vis == 0, 2 k > N, 3 the single-launch kernel (FUSED = 2) could
                               not serve the call — it speculated on the threshold branch and the count says top-k, or the
                               sequence is not the uniform video the frame-pipelined kernel is built for: hidden is
                               untouched, rebuild the links and call again with flags = 2 */
     FF_ST_NMERGED = 7,     /* tokens merged away by this call */
-    FF_ST_FUSED = 8,       /* 0 multi-kernel path, 1 the read-once kernel, 2 the frame-pipelined kernel (first merge call of a
-                              prefill on a uniform video) */
+    FF_ST_FUSED = 8,       /* 0 multi-kernel path, 2 the frame-pipelined kernel (first merge call of a prefill on a uniform
+                              video); 1 was the read-once kernel of ABI 2 .. 5, removed in ABI 6 */
     FF_ST_SEQ = 10,        /* number of the reducing call whose results the block holds: written LAST, after a system-wide
                             * fence, by the kernel that decides the call (ff_status_wait) */
-    FF_ST_INTERNAL = 9,    /* 1 if a wait inside a single-launch kernel gave up (the results of the call are invalid) */
+    FF_ST_INTERNAL = 9,    /* 1 if a wait inside the single-launch kernel gave up (the results of the call are invalid) */
     FF_ST_SLOTS = 16
 };
 
@@ -143,8 +143,8 @@ int ff_merge_apply(ff_ctx* ctx, void* ws, int64_t ws_bytes, void* hidden, int dt
  * -> runs -> merged rows -> compaction of hidden and of every aux tensor, and the links for the next call.
  * hidden [S,H] is read only; hidden_out must hold S rows (only S_keep are written).  patch_type is aux[0]
  * by convention of the host wrapper but the library does not care.  status: SEQ_KEEP, COUNT, NVIS, NCHAIN,
- * BRANCH, TOPK, ERROR, NMERGED, FUSED, INTERNAL.  `flags`: bit 0 = allow the read-once kernel (one launch, one HBM
- * read of hidden; it handles the threshold branch and reports ERROR = 3 otherwise, leaving hidden untouched);
+ * BRANCH, TOPK, ERROR, NMERGED, FUSED, INTERNAL.  `flags`: bit 0 is reserved and must be 0 (the read-once kernel of ABI 2 .. 5:
+ * FF_E_BADARG);
  * bit 1 = do NOT use the frame-pipelined kernel, bit 2 = use it wherever it can run.  Without bit 1 the first merge call
  * after ff_build_links runs as ONE launch in which every row travels HBM -> shared memory -> HBM once
  * (csrc/ff_frame.cuh) when the shape is one it is faster on (at least 20 KB of rows per frame and SM, chains on at
@@ -180,8 +180,8 @@ int ff_compact_mask(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* mask, v
 
 /* ---- introspection of the last merge call (tests, static API): copies device arrays out of `ws` ------
  * what: 0 = keep mask by sequence position (uint8 [S]), 1 = merge flags by by-patch position (uint8 [N]),
- *       2 = sim (T [N] by by-patch position; after a read-once call T [S] by sequence position), 3 = order (int64 [N]);
- *       1 and 3 exist after a multi-kernel call only */
+ *       2 = sim (T [N] by by-patch position), 3 = order (int64 [N]; needs ff_build_links, not the short form of
+ *       ff_build_links_for) */
 int ff_debug_read(ff_ctx* ctx, void* ws, int64_t ws_bytes, int what, void* dst_device, int64_t n, int dtype,
                   void* stream);
 

@@ -193,16 +193,11 @@ def run_and_compare(name, make_impl, device="cpu", check_sim_with_oracle=True):
     return report
 
 
-# merge-stage kernel choice of framefusion_b200.main.FrameFusion: "frame" = the default (the first merge call of a prefill
-# on a uniform video runs the frame-pipelined kernel, everything else the multi-kernel path), "multi" = the multi-kernel
-# path for every call, "fused" = the read-once kernel of r02 for every call
-MODES = ["frame", "multi", "fused"]
+# merge-stage kernel choice of framefusion_b200.main.FrameFusion: "frame" = the first merge call of a prefill on a uniform
+# video runs the frame-pipelined kernel (forced: the tests' shapes are mostly ones the library would not pick it for),
+# everything else the multi-kernel path; "multi" = the multi-kernel path for every call
+MODES = ["frame", "multi"]
 
 
 def set_mode(ff, mode):
-    if mode is True:
-        mode = "fused"
-    elif mode is False:
-        mode = "frame"
-    ff.use_fused = mode == "fused"
-    ff.use_frame = "force" if mode == "frame" else False    # (the tests' shapes are mostly ones the library would not pick it for)
+    ff.use_frame = "force" if mode == "frame" else False

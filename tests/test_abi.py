@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     assert set(_lib.EXPORTS) <= set(names)
     l = _lib.load()
-    assert l.ff_abi_version() == _lib.ABI_VERSION == 5
+    assert l.ff_abi_version() == _lib.ABI_VERSION == 6
     assert l.ff_workspace_bytes(36898, 576) > 36898 * 4 * 8
     assert l.ff_workspace_bytes(-1, 0) == -1
 

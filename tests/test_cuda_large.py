@@ -12,14 +12,14 @@ from framefusion_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def drive(frames, patches, hidden, lo, hi, fused, drift=0.0, cost=0.3, max_calls=6, per_patch_r=False, n_pre=14, n_post=20,
+def drive(frames, patches, hidden, lo, hi, mode, drift=0.0, cost=0.3, max_calls=6, per_patch_r=False, n_pre=14, n_post=20,
           dtype=torch.bfloat16, slb=0.6, frozen_patches=0, zero_rows=()):
     from framefusion_b200.main import FrameFusion
     wl = synth.make_workload(frames, patches, hidden, dtype, seed=9, r_lo=lo, r_hi=hi, per_patch_r=per_patch_r,
                              n_pre=n_pre, n_post=n_post, frozen_patches=frozen_patches, zero_rows=zero_rows)
     assert wl.seq_len >= 2048
     ff = FrameFusion(cost, slb, 0.1)
-    set_mode(ff, fused)
+    set_mode(ff, mode)
     ff.prepare(*synth.to_device(wl, "cuda").prepare_args())
     o = orc.OracleFrameFusion(cost, slb, 0.1, {torch.bfloat16: "bf16", torch.float16: "f16", torch.float32: "f32"}[dtype])
     o.prepare(wl.patch_type.numpy(), wl.patch_num, *wl.prepare_args()[2:])
@@ -51,15 +51,15 @@ def drive(frames, patches, hidden, lo, hi, fused, drift=0.0, cost=0.3, max_calls
     return stages
 
 
-@pytest.mark.parametrize("fused", MODES)
-def test_multi_call_merging_then_prune(fused):
-    stages = drive(32, 144, 512, 0.0, 1.0, fused, drift=0.35)
+@pytest.mark.parametrize("mode", MODES)
+def test_multi_call_merging_then_prune(mode):
+    stages = drive(32, 144, 512, 0.0, 1.0, mode, drift=0.35)
     assert stages.count("threshold") >= 2 and stages[-1] == "prune"
 
 
-@pytest.mark.parametrize("fused", MODES)
-def test_topk_branch_at_scale(fused):
-    stages = drive(24, 128, 512, 0.8, 1.0, fused)
+@pytest.mark.parametrize("mode", MODES)
+def test_topk_branch_at_scale(mode):
+    stages = drive(24, 128, 512, 0.8, 1.0, mode)
     assert stages == ["topk"]
 
 
@@ -112,13 +112,13 @@ def ragged_case(seed=3, frames=36, patches=120, hidden=512, n_pre=9, n_post=15):
     return h, cos, sin, pt, patches, (first, last, last - first + 1, S)
 
 
-@pytest.mark.parametrize("fused", MODES)
-def test_ragged_chains_with_text_between_frames(fused):
+@pytest.mark.parametrize("mode", MODES)
+def test_ragged_chains_with_text_between_frames(mode):
     from framefusion_b200.main import FrameFusion
     h, cos, sin, pt, P, span = ragged_case()
     assert h.shape[1] >= 2048
     ff = FrameFusion(0.3, 0.6, 0.1)
-    set_mode(ff, fused)
+    set_mode(ff, mode)
     ff.prepare(pt.cuda(), P, *span)
     o = orc.OracleFrameFusion(0.3, 0.6, 0.1, "bf16")
     o.prepare(pt.numpy(), P, *span)
@@ -222,22 +222,22 @@ def test_4d_mask_is_compacted_at_scale():
 
 # ---- SURVEY H9 corner cases on the multi-block kernels (the small-sequence kernels see them through the fixtures
 # case_H9_*.npz generated from the unmodified reference) ------------------------------------------------------------
-@pytest.mark.parametrize("fused", MODES)
-def test_h9_run_longer_than_256_rows(fused):
+@pytest.mark.parametrize("mode", MODES)
+def test_h9_run_longer_than_256_rows(mode):
     """One chain is identical in all 301 frames: a run of 300 members behind its anchor.  The sum stalls once the
     accumulator outgrows the member (each add is rounded to T), and the divisor is T(301) = 300 in bf16 — the in-place
     division casts it (main.py:314-317).  300 is a length bf16 holds exactly; lengths it cannot hold (257, 259 ..) make the
     reference itself misplace the anchor (its run-length tensor is kept in the hidden dtype, main.py:269-274), so there is
     nothing to match beyond this."""
-    stages = drive(301, 8, 256, 0.0, 0.5, fused, frozen_patches=2, max_calls=1)
+    stages = drive(301, 8, 256, 0.0, 0.5, mode, frozen_patches=2, max_calls=1)
     assert stages == ["threshold"]
 
 
-@pytest.mark.parametrize("fused", MODES)
-def test_h9_zero_norm_rows_threshold_branch(fused):
+@pytest.mark.parametrize("mode", MODES)
+def test_h9_zero_norm_rows_threshold_branch(mode):
     """All-zero rows: 0 / 0 = NaN similarity on both sides of the row; NaN >= threshold is false (kept, main.py:113)."""
     zr = [(f, p) for f in (0, 3, 4, 17, 31) for p in (0, 5, 143)]
-    stages = drive(32, 144, 512, 0.0, 1.0, fused, zero_rows=zr, max_calls=2)
+    stages = drive(32, 144, 512, 0.0, 1.0, mode, zero_rows=zr, max_calls=2)
     assert stages[0] == "threshold"
 
 

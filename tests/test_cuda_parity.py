@@ -17,11 +17,11 @@ pytestmark = pytest.mark.gpu
 class CudaAdapter:
     """``framefusion_b200.main.FrameFusion`` behind the interface the harness drives."""
 
-    def __init__(self, cost, slb, rlb, dtype, fused):
+    def __init__(self, cost, slb, rlb, dtype, mode):
         from framefusion_b200.main import FrameFusion
         self.ff = FrameFusion(cost, slb, rlb)
         self.ff.debug_trace = True
-        set_mode(self.ff, fused)
+        set_mode(self.ff, mode)
 
     def prepare(self, *args):
         self.ff.prepare(*args)
@@ -38,10 +38,10 @@ class CudaAdapter:
         return self.ff.last_trace
 
 
-@pytest.mark.parametrize("fused", MODES)
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name", case_names())
-def test_cuda_matches_reference_sequence(name, fused):
-    rep = run_and_compare(name, lambda c, s, r, dt: CudaAdapter(c, s, r, dt, fused), device="cuda")
+def test_cuda_matches_reference_sequence(name, mode):
+    rep = run_and_compare(name, lambda c, s, r, dt: CudaAdapter(c, s, r, dt, mode), device="cuda")
     assert rep["n_sim"] > 0
 
 
@@ -138,16 +138,16 @@ def test_errors_and_passthrough():
         ff(wl.hidden, [wl.cos, wl.sin], None)
 
 
-@pytest.mark.parametrize("fused", MODES)
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("cfg", ["C2", "C4"])
-def test_full_size_against_oracle(cfg, fused):
+def test_full_size_against_oracle(cfg, mode):
     """BASELINE configs at full size: first merge call, CUDA vs the numpy oracle on identical bits."""
     from framefusion_b200 import synth
     from framefusion_b200.main import FrameFusion
     c = synth.CONFIGS[cfg]
     wl = synth.make_workload(c["frames"], c["patch_num"], c["hidden"], c["dtype"], seed=0)
     ff = FrameFusion(c["cost"], c["slb"], c["rlb"])
-    set_mode(ff, fused)
+    set_mode(ff, mode)
     ff.debug_trace = True
     ff.prepare(*wl.prepare_args())
     pos = [wl.cos.cuda(), wl.sin.cuda()]

@@ -21,14 +21,14 @@ def tiny_model():
     return Qwen2ForCausalLM(cfg).eval().to(torch.bfloat16).cuda()
 
 
-@pytest.mark.parametrize("fused", MODES)
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("lo,hi", [(0.0, 1.0), (0.0, 0.5)], ids=["mixed", "lowsim_prune"])
-def test_patched_prefill_matches_oracle_call_by_call(lo, hi, fused):
+def test_patched_prefill_matches_oracle_call_by_call(lo, hi, mode):
     from framefusion_b200.interface import apply_framefusion
     model = tiny_model()
     apply_framefusion(model, cost=0.3, similarity_lower_bound=0.6, ratio_lower_bound=0.1)
     ff = model.framefusion
-    set_mode(ff, fused)
+    set_mode(ff, mode)
     wl = synth.make_workload(10, 24, 256, torch.bfloat16, seed=11, r_lo=lo, r_hi=hi, n_pre=5, n_post=7, rot_dim=64)
     o = orc.OracleFrameFusion(0.3, 0.6, 0.1, "bf16")
     o.prepare(wl.patch_type.numpy(), wl.patch_num, *wl.prepare_args()[2:])
@@ -62,15 +62,15 @@ def test_patched_prefill_matches_oracle_call_by_call(lo, hi, fused):
         assert ff.finish_pruning and any(c[2] for c in calls)      # importance was produced and consumed
 
 
-@pytest.mark.parametrize("fused", MODES)
-def test_merge_call_is_repeatable_bit_for_bit(fused):
+@pytest.mark.parametrize("mode", MODES)
+def test_merge_call_is_repeatable_bit_for_bit(mode):
     """The kernels contain spin-waits and atomics: the result must not depend on their timing."""
     from framefusion_b200.main import FrameFusion
     wl = synth.to_device(synth.make_workload(16, 96, 3584, torch.bfloat16, seed=5, per_patch_r=True), "cuda")
     ref = None
     for rep in range(25):
         ff = FrameFusion(0.3, 0.6, 0.1)
-        set_mode(ff, fused)
+        set_mode(ff, mode)
         ff.prepare(*wl.prepare_args())
         h, pos, _ = ff(wl.hidden, [wl.cos, wl.sin], None)
         cur = (h.clone(), pos[0].clone(), ff.patch_type.clone())

@@ -26,7 +26,7 @@ for rep in range(int(sys.argv[2]) if len(sys.argv) > 2 else 1):
     if len(bad):
         n_bad_runs += 1
         break
-print("shapes", got.shape, oh.shape, "fused", int(ff._state(h.device).status[8]), "bad after reps", rep, n_bad_runs)
+print("shapes", got.shape, oh.shape, "kernel", int(ff._state(h.device).status[8]), "bad after reps", rep, n_bad_runs)
 print("rows differing:", len(bad), bad[:20])
 for r in bad[:6]:
     src = keep[r]

@@ -15,7 +15,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg", default="C2")
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--fused", type=int, default=1)
+    ap.add_argument("--frame", type=int, default=1, help="0: multi-kernel path for call #0 as well")
     ap.add_argument("--calls", type=int, default=1)
     a = ap.parse_args()
     c = synth.CONFIGS[a.cfg]
@@ -24,7 +24,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     times = []
     ff = FrameFusion(c["cost"], c["slb"], c["rlb"])
-    ff.use_fused = bool(a.fused)
+    ff.use_frame = bool(a.frame)
     ker = []
     for it in range(a.iters + 3):
         ff.prepare(*wl.prepare_args())
@@ -51,7 +51,7 @@ def main():
     s_keep = h.shape[1]
     nbytes = synth.algorithmic_bytes(wl.seq_len, s_keep, c["hidden"], wl.hidden.element_size())
     k_us = sorted(ker)[len(ker) // 2] * 1e3
-    print(f"{a.cfg} fused={a.fused}: S={wl.seq_len} -> {s_keep}  ff_merge_layer {k_us:.1f} us = {nbytes/k_us/1e3:.0f} GB/s | whole call: device {dev*1e3:.1f} us  wall {wall*1e3:.1f} us  "
+    print(f"{a.cfg} frame={a.frame}: S={wl.seq_len} -> {s_keep}  ff_merge_layer {k_us:.1f} us = {nbytes/k_us/1e3:.0f} GB/s | whole call: device {dev*1e3:.1f} us  wall {wall*1e3:.1f} us  "
           f"alg {nbytes/1e6:.1f} MB -> {nbytes/dev/1e6:.0f} GB/s  {wl.n_vision/dev*1e3:.3e} vision tok/s")
 
 
