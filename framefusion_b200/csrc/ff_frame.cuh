@@ -78,6 +78,8 @@ constexpr int FR_PW = 4;                           // 32-word chunks of flag wor
 #define FR_POLL_NS 64                              // pause after a poll that retired nothing
 #endif
 constexpr int FR_TRACE_K = 8;                      // time stamps per (CTA, frame) of a traced launch
+constexpr int FR_DK = 4;                           // 32-frame chunks of its chain's destinations an aux warp keeps in registers for the tail
+struct FrameKept { int v0, v1, v2, v3; };          // lane l: destination of the chain's row of frame 32 c + l, or -1
 
 struct FrameArgs {
     AuxFlat auxf;
@@ -725,7 +727,7 @@ __device__ __forceinline__ void fr_role_merge(const FrameArgs& a, const AuxPack&
     }
 }
 
-__device__ __forceinline__ void fr_role_aux(const FrameArgs& a, const AuxPack& aux, const FrameGeo& g, int w_role) {
+__device__ __forceinline__ void fr_role_aux(const FrameArgs& a, const AuxPack& aux, const FrameGeo& g, int w_role, FrameKept& dk) {
     FrameShared* const sh = g.sh;
     const FrameCtx cx = g.cx;
     const int F = g.F, first = g.first, p0 = g.p0, Rc = g.Rc, NS = g.NS, R = g.R, P = g.P, S = g.S, lane = g.lane;
@@ -736,6 +738,7 @@ __device__ __forceinline__ void fr_role_aux(const FrameArgs& a, const AuxPack& a
     const int w_a = w_role;
     // ================================ aux rows, dst[], rows outside the chains ================================
     const int w = w_a;
+    dk.v0 = dk.v1 = dk.v2 = dk.v3 = -1;                    // (read by the tail of the kernel)
     const int unit = blockIdx.x * R + w, n_units = gridDim.x * R;
     const int nvec = a.nvec;
     for (int t = unit; t < first; t += n_units) {       // rows in front of the span keep their place
@@ -767,6 +770,13 @@ __device__ __forceinline__ void fr_role_aux(const FrameArgs& a, const AuxPack& a
                     if (k0) gather_aux_rows(aux, r0, d0, lane);
                     if (k1) gather_aux_rows(aux, r1, d1, lane);
                 }
+            }
+            if ((f & 31) == lane) {
+                const int c = f >> 5;
+                dk.v0 = c == 0 ? d0 : dk.v0;
+                dk.v1 = c == 1 ? d0 : dk.v1;
+                dk.v2 = c == 2 ? d0 : dk.v2;
+                dk.v3 = c == 3 ? d0 : dk.v3;
             }
             if (lane == 0) {
                 a.dst[r0] = d0;
@@ -851,12 +861,13 @@ k_frame_merge(const __grid_constant__ FrameArgs a, const __grid_constant__ AuxPa
     g.sh = sh; g.cx = cx;
     g.F = F; g.first = first; g.p0 = p0; g.Rc = Rc; g.NS = NS; g.R = R; g.P = P; g.S = S; g.lane = lane;
     g.N = N; g.rb = rb; g.stage_bytes = stage_bytes; g.stages0 = stages0; g.acc0 = acc0;
+    FrameKept dk;                                           // (aux warps only: set in their role, read in the tail)
     if (wid == 0) fr_role_producer(a, aux, g, 0);
     else if (wid <= NPW) fr_role_prefix<NPW>(a, aux, g, wid - 1);
     else if (wid == NPW + 1) { if (FR_FINISHER) fr_role_finish<DT>(a, aux, g, 0); }
     else if (w_s < R) fr_role_sim<DT>(a, aux, g, w_s);
     else if (w_g < R) fr_role_merge<DT>(a, aux, g, w_g);
-    else if (w_a < R) fr_role_aux(a, aux, g, w_a);
+    else if (w_a < R) fr_role_aux(a, aux, g, w_a, dk);
 
     // ---- every chain is through: one barrier over the grid, then the by-patch arrays of the next call
     __syncthreads();
@@ -876,13 +887,20 @@ k_frame_merge(const __grid_constant__ FrameArgs a, const __grid_constant__ AuxPa
     __syncthreads();
     const bool failed = sh->abort != 0;
     if (!failed && w_a >= 0 && w_a < Rc) {
+        // The tail is latency: everything it reads comes in as few round trips as possible.  The kept rows of the chains in
+        // front of this one: 20 loads per lane in flight at once (unconditional — predicated loads are not batched; 640 chains
+        // per trip), the destinations of the chain's own rows: out of this warp's registers for the first 32 FR_DK frames.
         const int p = p0 + w_a;
         int ex = 0;
-        for (int q = lane; q < p; q += 32) ex += __ldcg(a.len_next + q);
+        for (int q0 = 0; q0 < p; q0 += 32 * 20) {
+            int v[20];
+#pragma unroll
+            for (int u = 0; u < 20; ++u) v[u] = __ldcg(a.len_next + min(q0 + 32 * u + lane, P - 1));
+#pragma unroll
+            for (int u = 0; u < 20; ++u) ex += q0 + 32 * u + lane < p ? v[u] : 0;
+        }
         ex = warp_sum_int(ex);                              // kept chain rows of the chains in front of this one
-        for (int f0 = 0; f0 < F; f0 += 32) {
-            const int f = f0 + lane;
-            const int d = f < F ? __ldcg(a.keptdst + (int64_t)p * F + f) : -1;
+        auto emit = [&](int d) {
             const unsigned m = __ballot_sync(FULL, d >= 0);
             if (d >= 0) {
                 const int e = ex + __popc(m & ((1u << lane) - 1u));
@@ -891,6 +909,14 @@ k_frame_merge(const __grid_constant__ FrameArgs a, const __grid_constant__ AuxPa
                 a.rank_next[d] = e;
             }
             ex += __popc(m);
+        };
+        emit(dk.v0);
+        if (F > 32) emit(dk.v1);
+        if (F > 64) emit(dk.v2);
+        if (F > 96) emit(dk.v3);
+        for (int f0 = FR_DK * 32; f0 < F; f0 += 32) {
+            const int f = f0 + lane;
+            emit(f < F ? __ldcg(a.keptdst + (int64_t)p * F + f) : -1);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
