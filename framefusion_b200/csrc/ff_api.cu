@@ -365,7 +365,8 @@ bool frame_shape(const ff_ctx* ctx, int64_t n_ids, int64_t S, int64_t row_bytes,
     const int64_t R = (P + ctx->sm_count - 1) / ctx->sm_count;
     if (R > FR_MAXR) return false;
     const int64_t stage = R * row_bytes;
-    int64_t n_stages = ((int64_t)ctx->max_smem - FR_META - stage) / stage;
+    // (FR_ACC_INPLACE: run sums live in the stage slots themselves, else one stage-sized block of accumulator rows)
+    int64_t n_stages = ((int64_t)ctx->max_smem - FR_META - (FR_ACC_INPLACE ? 0 : stage)) / stage;
     static const int max_stages = getenv("FF_FRAME_STAGES") ? atoi(getenv("FF_FRAME_STAGES")) : FR_MAXSTAGES;
     if (n_stages > max_stages) n_stages = max_stages;
     if (n_stages > FR_MAXSTAGES) n_stages = FR_MAXSTAGES;
@@ -374,11 +375,12 @@ bool frame_shape(const ff_ctx* ctx, int64_t n_ids, int64_t S, int64_t row_bytes,
     // Where it pays (profiles/r02_sweep.jsonl): the pipeline advances one FRAME per ~1.45 us whatever a frame of a CTA
     // holds, so a CTA has to move enough bytes per frame (>= 20 KB: 4 rows of 7 KB; 2 rows — 210 tokens per frame — lose
     // to the multi-kernel path), nearly every SM has to have chains, and the ring has to cover the ~9 us a stage lives
-    // (>= 6 frames; five chains of 8-KB rows leave four).  `force` (flags bit 2) takes the kernel wherever it CAN run.
-    if (!force && (stage < 20 * 1024 || n_stages < 6 || grid * 10 < (int64_t)ctx->sm_count * 9)) return false;
+    // (>= 5 frames: five chains of 8-KB rows — C4 — leave five since the run sums moved into the stage slots, and win by
+    // 5 %; with the four they had before they lost by 50 %).  `force` (flags bit 2) takes the kernel wherever it CAN run.
+    if (!force && (stage < 20 * 1024 || n_stages < 5 || grid * 10 < (int64_t)ctx->sm_count * 9)) return false;
     fp->R = (int)R;
     fp->n_stages = (int)n_stages;
-    fp->smem = (int)(FR_META + (n_stages + 1) * stage);
+    fp->smem = (int)(FR_META + (n_stages + (FR_ACC_INPLACE ? 0 : 1)) * stage);
     fp->grid = (int)grid;
     fp->threads = 32 * (2 + (R <= 4 ? FR_NPW : 1) + 3 * (int)R);   // producer, prefix warps, (finisher slot), then S / G / aux per chain
     return true;

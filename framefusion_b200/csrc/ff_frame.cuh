@@ -68,6 +68,9 @@ constexpr int FR_PW = 4;                           // 32-word chunks of flag wor
 #ifndef FR_G_WIDE
 #define FR_G_WIDE 0                                // 1: the G warps' adds keep four vector pairs per lane in flight
 #endif
+#ifndef FR_ACC_INPLACE
+#define FR_ACC_INPLACE 1                           // 1: a run's sum lives in the stage slot of its newest member (no accumulator rows: one more stage)
+#endif
 #ifndef FR_NPW
 #define FR_NPW 2                                   // prefix warps (they take the frames in turn)
 #endif
@@ -650,14 +653,27 @@ __device__ __forceinline__ void fr_role_merge(const FrameArgs& a, const AuxPack&
             const bool nxt_kept = f + 1 < F ? sh->kept[(f + 1) % FR_NQ][w] != 0 : true;
             const bool nn_kept = f + 2 < F ? sh->kept[(f + 2) % FR_NQ][w] != 0 : true;
             const uint32_t cur = stages0 + (uint32_t)(f % NS) * stage_bytes + (uint32_t)(w * rb);
+            const uint32_t nxt = stages0 + (uint32_t)((f + 1) % NS) * stage_bytes + (uint32_t)(w * rb);
+#if FR_ACC_INPLACE
+            // The running sum of a run lives in the slot of its NEWEST member: this step adds row f + 1 into what slot f holds
+            // (the anchor itself, or the sum so far) and leaves the result in slot f + 1.  Nobody else wants that slot's
+            // original bytes any more: its last reader is the S warp's pass over frame f + 2 (as the previous row), and this
+            // step has waited for the flags of frame f + 2.  So no accumulator rows, and the ring is one stage deeper.
+            const uint32_t accw = nxt;
+#else
+            const uint32_t accw = accp;
+#endif
             if (kept) L = 0;
 #if !FR_G_EARLY_ADD
             if (!cx.wait_p(f)) break;
 #endif
             if (!nxt_kept) {
                 // the arithmetic needs no destination: it runs ahead of the prefix warp
-                const uint32_t nxt = stages0 + (uint32_t)((f + 1) % NS) * stage_bytes + (uint32_t)(w * rb);
+#if FR_ACC_INPLACE
+                const uint32_t src = cur;                     // the anchor itself, or the running sum step f - 1 left there
+#else
                 const uint32_t src = kept ? cur : accp;       // the anchor itself, or the running sum
+#endif
                 ++L;
                 if (nn_kept) {
                     const Divider<DT> dv(L + 1);
@@ -669,13 +685,13 @@ __device__ __forceinline__ void fr_role_merge(const FrameArgs& a, const AuxPack&
                             if (v0 + 32 * q < nvec) { y[q] = fr_lds16(src + (v0 + 32 * q) * 16); x[q] = fr_lds16(nxt + (v0 + 32 * q) * 16); }
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
-                            if (v0 + 32 * q < nvec) fr_sts16(accp + (v0 + 32 * q) * 16, dv.vec_fast(Num<DT>::add_vec(y[q], x[q])));   // T(T(acc + member) / T(L + 1))
+                            if (v0 + 32 * q < nvec) fr_sts16(accw + (v0 + 32 * q) * 16, dv.vec_fast(Num<DT>::add_vec(y[q], x[q])));   // T(T(acc + member) / T(L + 1))
                     }
 #else
 #pragma unroll 2
                     for (int v = lane; v < nvec; v += 32) {
                         const uint4 y = fr_lds16(src + v * 16), x = fr_lds16(nxt + v * 16);
-                        fr_sts16(accp + v * 16, dv.vec_fast(Num<DT>::add_vec(y, x)));    // T(T(acc + member) / T(L + 1))
+                        fr_sts16(accw + v * 16, dv.vec_fast(Num<DT>::add_vec(y, x)));    // T(T(acc + member) / T(L + 1))
                     }
 #endif
                     fr_fence_async();
@@ -688,13 +704,13 @@ __device__ __forceinline__ void fr_role_merge(const FrameArgs& a, const AuxPack&
                             if (v0 + 32 * q < nvec) { y[q] = fr_lds16(src + (v0 + 32 * q) * 16); x[q] = fr_lds16(nxt + (v0 + 32 * q) * 16); }
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
-                            if (v0 + 32 * q < nvec) fr_sts16(accp + (v0 + 32 * q) * 16, Num<DT>::add_vec(y[q], x[q]));   // T(acc + member), main.py:304
+                            if (v0 + 32 * q < nvec) fr_sts16(accw + (v0 + 32 * q) * 16, Num<DT>::add_vec(y[q], x[q]));   // T(acc + member), main.py:304
                     }
 #else
 #pragma unroll 2
                     for (int v = lane; v < nvec; v += 32) {
                         const uint4 y = fr_lds16(src + v * 16), x = fr_lds16(nxt + v * 16);
-                        fr_sts16(accp + v * 16, Num<DT>::add_vec(y, x));                  // T(acc + member), main.py:304
+                        fr_sts16(accw + v * 16, Num<DT>::add_vec(y, x));                  // T(acc + member), main.py:304
                     }
 #endif
                 }
@@ -708,7 +724,7 @@ __device__ __forceinline__ void fr_role_merge(const FrameArgs& a, const AuxPack&
             __syncwarp();
             if (lane == 0) {
                 if (nxt_kept) { if (kept) fr_tma_store(a.out + (int64_t)anchor_d * rb, cur, (uint32_t)rb); }
-                else if (nn_kept) fr_tma_store(a.out + (int64_t)anchor_d * rb, accp, (uint32_t)rb);
+                else if (nn_kept) fr_tma_store(a.out + (int64_t)anchor_d * rb, accw, (uint32_t)rb);
             }
             __syncwarp();
             if (lane == 0) {
@@ -829,7 +845,7 @@ k_frame_merge(const __grid_constant__ FrameArgs a, const __grid_constant__ AuxPa
     const int64_t rb = a.row_bytes;
     const uint32_t stage_bytes = (uint32_t)(R * rb);
     const uint32_t stages0 = fr_smem_u32(fr_smem + FR_META);
-    const uint32_t acc0 = stages0 + (uint32_t)NS * stage_bytes;
+    const uint32_t acc0 = stages0 + (uint32_t)NS * stage_bytes;      // (FR_ACC_INPLACE = 0: the accumulator rows behind the stages)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) {

@@ -171,10 +171,11 @@ def test_repeated_launches_are_identical():
 
 
 def test_the_library_picks_the_frame_kernel_where_it_is_the_faster_one():
-    """Default settings: 576 patches of 7-KB rows (C2 / C3) take the frame kernel; 210 tokens per frame, five chains of 8-KB
-    rows per SM (C4) and float32 C1 rows stay on the multi-kernel path (profiles/r02_sweep.jsonl)."""
+    """Default settings: 576 patches of 7-KB rows (C2 / C3) and 729 patches of 8-KB rows (C4: five chains per SM, a ring of
+    five frames) take the frame kernel; 210 tokens per frame and float32 C1 rows stay on the multi-kernel path
+    (profiles/r02_sweep.jsonl)."""
     for frames, patches, hidden, dtype, want in ((8, 576, 3584, torch.bfloat16, 2), (8, 210, 3584, torch.bfloat16, 0),
-                                                 (6, 729, 4096, torch.bfloat16, 0), (8, 196, 1024, torch.float32, 0)):
+                                                 (6, 729, 4096, torch.bfloat16, 2), (8, 196, 1024, torch.float32, 0)):
         wl = synth.to_device(synth.make_workload(frames, patches, hidden, dtype, seed=1), "cuda")
         ff = FrameFusion(0.3, 0.6, 0.1)
         ff.prepare(*wl.prepare_args())

@@ -15,7 +15,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg", default="C2")
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--frame", type=int, default=1, help="0: multi-kernel path for call #0 as well")
+    ap.add_argument("--frame", type=int, default=1, help="0: multi-kernel path for call #0 as well, 2: the frame-pipelined kernel forced")
     ap.add_argument("--calls", type=int, default=1)
     a = ap.parse_args()
     c = synth.CONFIGS[a.cfg]
@@ -24,7 +24,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     times = []
     ff = FrameFusion(c["cost"], c["slb"], c["rlb"])
-    ff.use_frame = bool(a.frame)
+    ff.use_frame = "force" if a.frame == 2 else bool(a.frame)
     ker = []
     for it in range(a.iters + 3):
         ff.prepare(*wl.prepare_args())
