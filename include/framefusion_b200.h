@@ -148,7 +148,7 @@ int ff_merge_apply(ff_ctx* ctx, void* ws, int64_t ws_bytes, void* hidden, int dt
  * bit 1 = do NOT use the frame-pipelined kernel, bit 2 = use it wherever it can run.  Without bit 1 the first merge call
  * after ff_build_links runs as ONE launch in which every row travels HBM -> shared memory -> HBM once
  * (csrc/ff_frame.cuh) when the shape is one it is faster on (at least 20 KB of rows per frame and SM, chains on at
- * least nine SMs in ten, a ring of six frames in shared memory: 300 .. 592 patches of 7-KB rows on a B200; bit 2 drops
+ * least nine SMs in ten, a ring of five frames in shared memory: 300 .. 592 patches of 7-KB rows, 729 of 8-KB rows on a B200; bit 2 drops
  * these three conditions); the kernel checks on the device that the sequence is a uniform video (one span of chain rows,
  * patch ids 0 .. n_ids-1 repeating) and that the threshold branch applies, and reports ERROR = 3 / FUSED = 2 otherwise. */
 int ff_merge_layer(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* hidden, void* hidden_out, int dtype,
