@@ -88,7 +88,7 @@ struct ff_ctx {
     long long seq;       // number of the last reducing call (status[FF_ST_SEQ] when its results are in the status block)
     int links_lite;      // ff_build_links_for left only the counters: the next merge call must be the frame-pipelined kernel
     int links_lite_last; // ... and the last merge call ran on such links (no by-patch order to read back)
-    int frame_smem[6];   // dynamic shared memory the frame-pipelined kernel of each (dtype, build) is opted in for
+    int frame_smem[9];   // dynamic shared memory the frame-pipelined kernel of each (dtype, build) is opted in for
     long long* frame_trace;          // ff_debug_frame_trace: device buffer for time stamps of the next frame-kernel launch
     int64_t frame_trace_bytes;
 };
@@ -447,11 +447,12 @@ int launch_frame(ff_ctx* ctx, const Ws& w, int bank, const FramePlan& fp, const 
     ctx->words_clean[bank] = 0;
     return dispatch_dtype(dtype, [&](auto dt) {
         constexpr int DT = decltype(dt)::value;
-        // two builds: up to four chains per CTA (14 warps, no register pressure) and up to FR_MAXR
+        // three builds: up to four chains per CTA (16 warps), exactly five (C4: 18 warps — 112 registers, what the roles need
+        // without spilling; the build for up to FR_MAXR chains has 27 warps, 72 registers and spills) and up to FR_MAXR
         auto go = [&](auto mr) {
             constexpr int MR = decltype(mr)::value;
-            constexpr int NPW = MR > 4 ? 1 : FR_NPW;       // prefix warps (FramePlan::threads)
-            constexpr int slot = DT * 2 + (MR > 4 ? 1 : 0);
+            constexpr int NPW = MR > 4 ? 1 : FR_NPW;       // prefix warps (FramePlan::threads); two changed nothing in the five-chain build
+            constexpr int slot = DT * 3 + (MR > 5 ? 2 : MR > 4 ? 1 : 0);
             if (ctx->frame_smem[slot] < fp.smem) {
                 FF_CUDA(cudaFuncSetAttribute((k_frame_merge<DT, MR, NPW>), cudaFuncAttributeMaxDynamicSharedMemorySize, fp.smem));
                 ctx->frame_smem[slot] = fp.smem;
@@ -459,7 +460,9 @@ int launch_frame(ff_ctx* ctx, const Ws& w, int bank, const FramePlan& fp, const 
             FF_LAUNCH("k_frame_merge", (k_frame_merge<DT, MR, NPW>), fp.grid, fp.threads, fp.smem, st, a, ap);
             return (int)FF_OK;
         };
-        return fp.R <= 4 ? go(std::integral_constant<int, 4>()) : go(std::integral_constant<int, FR_MAXR>());
+        if (fp.R <= 4) return go(std::integral_constant<int, 4>());
+        if (fp.R == 5) return go(std::integral_constant<int, 5>());
+        return go(std::integral_constant<int, FR_MAXR>());
     });
 }
 
@@ -491,7 +494,7 @@ int ff_ctx_create(int device, ff_ctx** out) {
     c->fresh_links = 0;
     c->seq = 0;
     c->words_clean[0] = c->words_clean[1] = 0;
-    for (int i = 0; i < 6; ++i) c->frame_smem[i] = 0;
+    for (int i = 0; i < 9; ++i) c->frame_smem[i] = 0;
     c->links_lite = c->links_lite_last = 0;
     c->frame_trace = nullptr;
     c->frame_trace_bytes = 0;
