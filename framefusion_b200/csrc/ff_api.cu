@@ -934,6 +934,8 @@ int ff_compact_mask(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* mask, v
 
 int ff_debug_frame_trace(ff_ctx* ctx, void* device_buf, int64_t bytes) {
     if (!ctx) return fail(FF_E_BADARG, "null ctx");
+    if (!FR_TRACE && device_buf)
+        return fail(FF_E_UNSUPPORTED, "this build carries no tracing code: build a variant with -DFR_TRACE=1 (tools/build_variant.sh) and select it with FF_LIB_PATH");
     ctx->frame_trace = (long long*)device_buf;
     ctx->frame_trace_bytes = device_buf ? bytes : 0;
     return FF_OK;

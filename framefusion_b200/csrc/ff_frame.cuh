@@ -71,6 +71,9 @@ constexpr int FR_PW = 4;                           // 32-word chunks of flag wor
 #ifndef FR_ACC_INPLACE
 #define FR_ACC_INPLACE 1                           // 1: a run's sum lives in the stage slot of its newest member (no accumulator rows: one more stage)
 #endif
+#ifndef FR_TRACE
+#define FR_TRACE 0                                 // 1: the time stamps / cycle counters of ff_debug_frame_trace are compiled in (tools/build_variant.sh trace -DFR_TRACE=1)
+#endif
 #ifndef FR_NPW
 #define FR_NPW 2                                   // prefix warps (they take the frames in turn)
 #endif
@@ -314,8 +317,15 @@ __device__ __forceinline__ void frame_finish(const FrameArgs& a, long long N, lo
     *(volatile int64_t*)&a.status[FF_ST_SEQ] = a.seq;
 }
 
+// (the shipped build carries no tracing code: every role's loop is on the critical path, and code added to the S warps' role
+// has cost 8 us twice, profiles/r02_frame_kernel.md)
+#if FR_TRACE
 #define FR_NOTE(f, k, val) do { if (a.trace && (f) < a.trace_frames) a.trace[((int64_t)blockIdx.x * a.trace_frames + (f)) * FR_TRACE_K + (k)] = (val); } while (0)
 #define FR_STAMP(f, k) do { if (a.trace && (f) < a.trace_frames) a.trace[((int64_t)blockIdx.x * a.trace_frames + (f)) * FR_TRACE_K + (k)] = fr_time(); } while (0)
+#else
+#define FR_NOTE(f, k, val) do { } while (0)
+#define FR_STAMP(f, k) do { } while (0)
+#endif
 
 // what every role of a CTA knows (the roles are inlined: as separate functions they read the kernel arguments through
 // memory and ran 40 % slower)
@@ -484,7 +494,7 @@ __device__ __forceinline__ void fr_role_sim(const FrameArgs& a, const AuxPack& a
             const int st = f % NS;
             if (!cx.wait_bar(&sh->full[st], f / NS)) break;
             if (w == 0 && lane == 0) FR_STAMP(f, 5);    // the frame's rows are in shared memory
-            if (a.trace) { const long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
+            if (FR_TRACE && a.trace) { const long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
             const uint32_t cur = stages0 + (uint32_t)st * stage_bytes + (uint32_t)(w * rb) + lane * 16;
             const uint32_t prv = stages0 + (uint32_t)((f + NS - 1) % NS) * stage_bytes + (uint32_t)(w * rb) + lane * 16;
             float2 d0 = make_float2(0.f, 0.f), d1 = d0, b0 = d0, b1 = d0;
@@ -558,10 +568,10 @@ __device__ __forceinline__ void fr_role_sim(const FrameArgs& a, const AuxPack& a
                 }
             }
             long long c_l = 0, c_r = 0;
-            if (a.trace) c_l = clock64();
+            if (FR_TRACE && a.trace) c_l = clock64();
             const float dot = warp_sum((d0.x + d0.y) + (d1.x + d1.y));
             const float nb = warp_sum((b0.x + b0.y) + (b1.x + b1.y));
-            if (a.trace) { c_r = clock64(); c_loop += c_l - c0; c_red += c_r - c_l; }
+            if (FR_TRACE && a.trace) { c_r = clock64(); c_loop += c_l - c0; c_red += c_r - c_l; }
 #if FR_FINISHER
             if (lane == 0) {
                 sh->psum[f % FR_NQ][w][0] = dot;
@@ -585,7 +595,7 @@ __device__ __forceinline__ void fr_role_sim(const FrameArgs& a, const AuxPack& a
             }
 #endif
             __syncwarp();
-            if (a.trace) { const long long c1 = clock64(); c_busy += c1 - c0; c0 = c1; }
+            if (FR_TRACE && a.trace) { const long long c1 = clock64(); c_busy += c1 - c0; c0 = c1; }
         }
         if (w == 0 && lane == 0) { FR_NOTE(0, 7, c_busy); FR_NOTE(1, 7, c_wait); FR_NOTE(4, 7, c_loop); FR_NOTE(5, 7, c_red); }
     }
@@ -648,7 +658,7 @@ __device__ __forceinline__ void fr_role_merge(const FrameArgs& a, const AuxPack&
         long long c_wait = 0, c_busy = 0, c0 = clock64();
         for (int f = 0; f < F; ++f) {
             if (!cx.wait_s(min(f + 3, F) - 1)) break;
-            if (a.trace) { const long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
+            if (FR_TRACE && a.trace) { const long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
             const bool kept = sh->kept[f % FR_NQ][w] != 0;
             const bool nxt_kept = f + 1 < F ? sh->kept[(f + 1) % FR_NQ][w] != 0 : true;
             const bool nn_kept = f + 2 < F ? sh->kept[(f + 2) % FR_NQ][w] != 0 : true;
@@ -716,9 +726,9 @@ __device__ __forceinline__ void fr_role_merge(const FrameArgs& a, const AuxPack&
                 }
             }
             if (kept) {
-                if (a.trace) { const long long c1 = clock64(); c_busy += c1 - c0; c0 = c1; }
+                if (FR_TRACE && a.trace) { const long long c1 = clock64(); c_busy += c1 - c0; c0 = c1; }
                 if (!cx.wait_p(f)) break;
-                if (a.trace) { const long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
+                if (FR_TRACE && a.trace) { const long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
                 anchor_d = sh->dstv[f % FR_NQ][w];
             }
             __syncwarp();
@@ -736,7 +746,7 @@ __device__ __forceinline__ void fr_role_merge(const FrameArgs& a, const AuxPack&
                 if (w == 0) FR_STAMP(f, 3);
             }
             __syncwarp();
-            if (a.trace) { const long long c1 = clock64(); c_busy += c1 - c0; c0 = c1; }
+            if (FR_TRACE && a.trace) { const long long c1 = clock64(); c_busy += c1 - c0; c0 = c1; }
         }
         if (w == 0 && lane == 0) { FR_NOTE(2, 7, c_busy); FR_NOTE(3, 7, c_wait); }
         if (lane == 0) fr_tma_wait_all();

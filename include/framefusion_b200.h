@@ -185,7 +185,8 @@ int ff_compact_mask(ff_ctx* ctx, void* ws, int64_t ws_bytes, const void* mask, v
 int ff_debug_read(ff_ctx* ctx, void* ws, int64_t ws_bytes, int what, void* dst_device, int64_t n, int dtype,
                   void* stream);
 
-/* ---- measurement aid: the next frame-pipelined launch writes %globaltimer stamps into device_buf, laid out
+/* ---- measurement aid (libraries built with -DFR_TRACE=1 only; the shipped build returns FF_E_UNSUPPORTED for a non-null
+ * buffer: its kernel carries no tracing code): the next frame-pipelined launch writes %globaltimer stamps into device_buf, laid out
  * [CTA][frame][8] int64 (0 load requested, 1 similarity done, 2 destinations known, 3 rows out, 4 aux rows out);
  * null switches it off.  The buffer must stay alive until that launch has run. */
 int ff_debug_frame_trace(ff_ctx* ctx, void* device_buf, int64_t bytes);

@@ -1,4 +1,5 @@
-"""Time stamps of one frame-pipelined merge launch (ff_debug_frame_trace): where a frame's time goes.
+"""(needs a library built with tracing: tools/build_variant.sh trace -DFR_TRACE=1; FF_LIB_PATH=framefusion_b200/variants/libff_trace.so)
+Time stamps of one frame-pipelined merge launch (ff_debug_frame_trace): where a frame's time goes.
 Development tool; bench.py is the judged entry point."""
 import argparse
 import os
