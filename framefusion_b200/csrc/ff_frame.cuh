@@ -348,13 +348,15 @@ __device__ __forceinline__ void fr_role_producer(const FrameArgs& a, const AuxPa
     (void)F; (void)first; (void)p0; (void)Rc; (void)NS; (void)R; (void)P; (void)S; (void)lane; (void)N; (void)rb; (void)stage_bytes; (void)stages0; (void)acc0; (void)sh;
     // ================================ producer ================================
     if (lane == 0) {
-        for (int f = 0; f < F; ++f) {
-            const int st = f % NS;
+        // (the stage of a frame and the phase of its barriers are counted along: NS is a run-time value, and f % NS, f / NS are
+        // some twenty dependent instructions each — on the S and G warps' paths they were paid several times per frame)
+        int st = 0, ph = 0;
+        for (int f = 0; f < F; ++f, st = st + 1 == NS ? 0 : st + 1, ph ^= (st == 0)) {
             if (f >= NS) {
                 // the stage is free once the G warps are through frame f - NS; the aux warps touch no stage, they only
                 // have to stay within the flag / destination rings (FR_NQ frames)
                 bool ok = true;
-                ok = cx.wait_bar(&sh->empty[st], f / NS - 1);
+                ok = cx.wait_bar(&sh->empty[st], ph ^ 1);
                 for (int w = 0; w < Rc && ok; ++w) ok = cx.wait_ge(&sh->a_done[w], f - (FR_NQ - 4));
                 if (!ok) break;
             }
@@ -490,13 +492,13 @@ __device__ __forceinline__ void fr_role_sim(const FrameArgs& a, const AuxPack& a
         long long c_wait = 0, c_busy = 0, c_loop = 0, c_red = 0, c0 = clock64();   // (traced launches: where this warp's cycles go)
         float na_prev = 0.f;                                // (no finisher: the squares of the previous row)
         (void)na_prev;
-        for (int f = 0; f < F; ++f) {
-            const int st = f % NS;
-            if (!cx.wait_bar(&sh->full[st], f / NS)) break;
+        int st = 0, st_prev = NS - 1, ph = 0;               // stage of frame f, of frame f - 1, parity of f / NS (counted along, see the producer)
+        for (int f = 0; f < F; ++f, st_prev = st, st = st + 1 == NS ? 0 : st + 1, ph ^= (st == 0)) {
+            if (!cx.wait_bar(&sh->full[st], ph)) break;
             if (w == 0 && lane == 0) FR_STAMP(f, 5);    // the frame's rows are in shared memory
             if (FR_TRACE && a.trace) { const long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
             const uint32_t cur = stages0 + (uint32_t)st * stage_bytes + (uint32_t)(w * rb) + lane * 16;
-            const uint32_t prv = stages0 + (uint32_t)((f + NS - 1) % NS) * stage_bytes + (uint32_t)(w * rb) + lane * 16;
+            const uint32_t prv = stages0 + (uint32_t)st_prev * stage_bytes + (uint32_t)(w * rb) + lane * 16;
             float2 d0 = make_float2(0.f, 0.f), d1 = d0, b0 = d0, b1 = d0;
 #ifdef FR_DIAG_S_DIV
             const int nvec = a.nvec / FR_DIAG_S_DIV;     // diagnostic build: wrong similarities, a fraction of the arithmetic
@@ -656,14 +658,15 @@ __device__ __forceinline__ void fr_role_merge(const FrameArgs& a, const AuxPack&
         const int nvec = a.nvec;
         int L = 0, anchor_d = -1;
         long long c_wait = 0, c_busy = 0, c0 = clock64();
-        for (int f = 0; f < F; ++f) {
+        int st = 0, st_nxt = 1, st_prv = NS - 1;            // stages of the frames f, f + 1, f - 1 (counted along, see the producer)
+        for (int f = 0; f < F; ++f, st_prv = st, st = st_nxt, st_nxt = st_nxt + 1 == NS ? 0 : st_nxt + 1) {
             if (!cx.wait_s(min(f + 3, F) - 1)) break;
             if (FR_TRACE && a.trace) { const long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
             const bool kept = sh->kept[f % FR_NQ][w] != 0;
             const bool nxt_kept = f + 1 < F ? sh->kept[(f + 1) % FR_NQ][w] != 0 : true;
             const bool nn_kept = f + 2 < F ? sh->kept[(f + 2) % FR_NQ][w] != 0 : true;
-            const uint32_t cur = stages0 + (uint32_t)(f % NS) * stage_bytes + (uint32_t)(w * rb);
-            const uint32_t nxt = stages0 + (uint32_t)((f + 1) % NS) * stage_bytes + (uint32_t)(w * rb);
+            const uint32_t cur = stages0 + (uint32_t)st * stage_bytes + (uint32_t)(w * rb);
+            const uint32_t nxt = stages0 + (uint32_t)st_nxt * stage_bytes + (uint32_t)(w * rb);
 #if FR_ACC_INPLACE
             // The running sum of a run lives in the slot of its NEWEST member: this step adds row f + 1 into what slot f holds
             // (the anchor itself, or the sum so far) and leaves the result in slot f + 1.  Nobody else wants that slot's
@@ -742,7 +745,7 @@ __device__ __forceinline__ void fr_role_merge(const FrameArgs& a, const AuxPack&
                 // is the store of the step before, and with it stage f - 1 (and the accumulator row) can be reused
                 fr_tma_commit();
                 fr_tma_wait_read_1();
-                if (f > 0) fr_mbar_arrive(fr_smem_u32(&sh->empty[(f - 1) % NS]));
+                if (f > 0) fr_mbar_arrive(fr_smem_u32(&sh->empty[st_prv]));
                 if (w == 0) FR_STAMP(f, 3);
             }
             __syncwarp();
