@@ -18,9 +18,11 @@
 //   prefix warp       polls the flag words of frame f until every patch has reported, popcounts: destination rows of
 //                     the CTA's own rows of that frame, and the running base of the next frame;
 //   G warps (one per chain)   a kept row whose successor is kept goes out as it is (bulk copy shared -> global); a kept
-//                     row whose successor merges opens a run: members are added into the chain's accumulator row in
-//                     shared memory, one rounding to T per add in chain order, and the closing add divides by T(L+1)
-//                     (main.py:304-317) and sends the row out.  Nothing is read twice, not even from the L2;
+//                     row whose successor merges opens a run: every member is added IN PLACE — the running sum lives in
+//                     the stage slot of the run's newest member, whose original bytes nobody needs once the S warp is two
+//                     frames further (so there are no accumulator rows and the ring is one stage deeper) — one rounding to
+//                     T per add in chain order, and the closing add divides by T(L+1) (main.py:304-317) and sends the row
+//                     out.  Nothing is read twice, not even from the L2;
 //   aux warps (one per chain)   cos / sin / patch_type / position-id rows of the kept rows, dst[], and — after one grid
 //                     barrier at the very end — the by-patch arrays of the next call (order / chain / rank), so that the
 //                     multi-kernel path can serve the following calls.  They also move the rows outside the chains.
@@ -654,7 +656,9 @@ __device__ __forceinline__ void fr_role_merge(const FrameArgs& a, const AuxPack&
     // out.  A kept row with a kept successor goes out as it is.  So step f is the last reader of stage f.
     if (w_g < Rc) {
         const int w = w_g;
+#if !FR_ACC_INPLACE
         const uint32_t accp = acc0 + (uint32_t)(w * rb);
+#endif
         const int nvec = a.nvec;
         int L = 0, anchor_d = -1;
         long long c_wait = 0, c_busy = 0, c0 = clock64();
