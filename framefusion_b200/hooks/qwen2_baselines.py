@@ -27,6 +27,7 @@ import torch
 from transformers.cache_utils import Cache
 
 from ..baselines import TokenReductionBaseline, compute_density_overhead
+from ..utils import get_attr_by_name
 from .qwen2 import attention_with_importance, model_inputs, model_outputs
 
 
@@ -141,12 +142,14 @@ Qwen2DecoderLayer_merge_then_fastv_forward = Qwen2DecoderLayer_fastv_forward
 Qwen2SdpaAttention_merge_then_fastv_forward = Qwen2SdpaAttention_fastv_forward
 
 
-def _install(model, operator: TokenReductionBaseline):
-    names = {c.__name__ for c in type(model.model).__mro__}
+def _install(model, operator: TokenReductionBaseline, llm_key: str = "model"):
+    """``llm_key``: dotted path of the Qwen2 decoder stack — ``model`` for LLaVA-Video / Qwen2 (reference :179), ``llm.model``
+    for the MiniCPM-V and NVILA wrappers (reference :194, :209)."""
+    llm = get_attr_by_name(model, llm_key)
+    names = {c.__name__ for c in type(llm).__mro__}
     if "Qwen2Model" not in names:
         raise TypeError("language model is not Qwen2.")                           # reference :187-188
     model.baseline = operator
-    llm = model.model
     llm.baseline = operator
     llm.forward = MethodType(Qwen2Model_fastv_forward, llm)
     for layer in llm.layers:
@@ -193,6 +196,52 @@ def replace_Qwen2_streamingllm(model, init_num=4, length_rate=0.3):
     raise NotImplementedError(
         "StreamingLLM replaces the attention kernel (minference.streaming_forward, not installed) and reduces no tokens; "
         "it is outside the merge / prune path this package implements")
+
+
+def replace_minicpmv_fastv(model, fastv_k=3, fastv_r=0.5):
+    """reference :190-203 (the decoder stack sits under ``model.llm.model``)"""
+    model.fastv_k = fastv_k
+    model.fastv_r = fastv_r
+    return _install(model, TokenReductionBaseline(None, fastv_k, fastv_r), llm_key="llm.model")
+
+
+def replace_nvila_fastv(model, fastv_k=3, fastv_r=0.5):
+    """reference :205-218"""
+    return replace_minicpmv_fastv(model, fastv_k, fastv_r)
+
+
+def replace_minicpmv_streamingllm(model, init_num=4, length_rate=0.3):
+    """reference :592-603"""
+    return replace_Qwen2_streamingllm(model, init_num, length_rate)
+
+
+def replace_nvila_streamingllm(model, init_num=4, length_rate=0.3):
+    """reference :605-616"""
+    return replace_Qwen2_streamingllm(model, init_num, length_rate)
+
+
+def _wrapper_forward(name, installers, model, mode, kwargs):
+    print(f"{name} mode: {mode} and kwargs: {kwargs}")
+    if mode == "fastv":
+        cfg = {"fastv_k": kwargs.get("fastv_k", 3), "fastv_r": kwargs.get("fastv_r", 0.5)}
+        print(f"Config\n{cfg}")
+        return installers[0](model, **cfg)
+    if mode == "streamingllm":
+        cfg = {"init_num": kwargs.get("init_num", 8), "length_rate": kwargs.get("length_rate", 0.3)}
+        print(f"Config\n{cfg}")
+        return installers[1](model, **cfg)
+    raise NotImplementedError(f"Mode {mode} is not implemented yet.")
+
+
+def replace_minicpmv_forward(model, mode="fastv", **kwargs):
+    """Meta interface of the MiniCPM-V wrapper (reference :111-135)."""
+    return _wrapper_forward("replace_minicpmv_forward", (replace_minicpmv_fastv, replace_minicpmv_streamingllm), model, mode, kwargs)
+
+
+def replace_nvila_forward(model, mode="merge_then_fastv_cost_given", **kwargs):
+    """Meta interface of the NVILA wrapper (reference :138-164); like the reference's, its default mode raises."""
+    model.mode = mode
+    return _wrapper_forward("replace_nvila_forward", (replace_nvila_fastv, replace_nvila_streamingllm), model, mode, kwargs)
 
 
 def replace_Qwen2_forward(model, mode="merge_then_fastv_cost_given", **kwargs):

@@ -227,3 +227,40 @@ def test_fixed_sparsity_oracle_counts():
         assert before - h.shape[0] == k
         n_vis -= k
         assert int((o.patch_type != -1).sum()) == n_vis and int((o.patch_type == -1).sum()) == wl.seq_len - 80
+
+
+def test_wrapper_models_hold_the_decoder_under_llm(patched_importance, capsys):
+    """MiniCPM-V / NVILA keep the Qwen2 stack under ``model.llm.model`` (reference :190-218, meta interfaces :111-164)."""
+    class Wrapper(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.llm = tiny_model()
+    for installer, kw in ((qb.replace_minicpmv_forward, dict(mode="fastv", fastv_k=2, fastv_r=0.5)),
+                          (qb.replace_nvila_forward, dict(mode="fastv", fastv_k=2, fastv_r=0.5))):
+        model = Wrapper()
+        op_cuda = installer(model, **kw)
+        assert isinstance(op_cuda, TokenReductionBaseline) and model.baseline is op_cuda and (model.fastv_k, model.fastv_r) == (2, 0.5)
+        assert installer.__name__ in capsys.readouterr().out
+        inner = model.llm.model
+        assert inner.baseline is op_cuda and all(l.baseline is op_cuda and l.self_attn.baseline is op_cuda for l in inner.layers)
+        op = OracleBaselineOperator(None, 2, 0.5)
+        for m in [model, inner] + list(inner.layers) + [l.self_attn for l in inner.layers]:
+            m.baseline = op
+        wl = workload(frames=6, patches=12)
+        with torch.no_grad():
+            want = manual_reference(model.llm, wl, OracleBaselineOperator(None, 2, 0.5))
+            op.prepare(*wl.prepare_args())
+            out = inner(inputs_embeds=wl.hidden.clone(), use_cache=True)
+        assert torch.allclose(out.last_hidden_state, want, atol=1e-5, rtol=1e-5) and out.last_hidden_state.shape[1] < wl.seq_len
+    with pytest.raises(NotImplementedError, match="minference"):
+        qb.replace_minicpmv_forward(Wrapper(), mode="streamingllm")
+    with pytest.raises(NotImplementedError, match="not implemented"):
+        qb.replace_nvila_forward(Wrapper())                                  # the reference's default mode raises too (:163-164)
+
+    class NotQwen(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.llm = torch.nn.Module()
+            self.llm.model = torch.nn.Linear(2, 2)
+    with pytest.raises(TypeError, match="not Qwen2"):
+        qb.replace_minicpmv_fastv(NotQwen())
