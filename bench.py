@@ -678,11 +678,12 @@ def main():
         "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "priming_steps": args.priming_steps,
-        "config": {"workload": workload_name(cfg), "seq_len": wl.seq_len, "kept_after_merge": s_keep0,
-                   "kept_after_prune": int(h_final.shape[1]), "l2": "inputs (264 MB at C2) exceed the 126 MB L2; no explicit flush",
-                   "parallelism": "replicas" if world > 1 else "single-gpu",
-                   "cpu_affinity": "rank pinned to its GPU's CPUs (NVML)" if pinned_cpus else "unpinned",
-                   "calls_per_step": "merge, merge (closes merging), importance, prune"},
+        # the workload, with exactly the keys and values of the reference arm's line (bench_config); what is particular to
+        # this arm's run sits next to it
+        "config": bench_config(cfg, wl.seq_len),
+        "run": {"kept_after_merge": s_keep0, "kept_after_prune": int(h_final.shape[1]),
+                "parallelism": "replicas" if world > 1 else "single-gpu",
+                "cpu_affinity": "rank pinned to its GPU's CPUs (NVML)" if pinned_cpus else "unpinned"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "ff_merge_layer call #0: " + kernel_names.get(fused, str(fused)),
                      "multi_kernel_path_us": None if single_ms is None else single_ms * 1e3,
